@@ -1,0 +1,92 @@
+"""The oracle restatement (oracle/model.py, oracle/ref_ops.py) against the golden outputs of
+the reference's own sources (tests/golden/make_golden.py).  CPU only."""
+import torch
+
+from conftest import sd_from_manifest
+from oracle import model as O
+from oracle import ref_ops as R
+
+TOL = dict(rtol=2e-5, atol=2e-6)
+
+
+def test_synthetic_data_and_extended_graph(golden, golden_batch):
+    mols, batch = golden_batch
+    assert torch.equal(torch.tensor([m.num_nodes for m in mols]), golden["graph"]["num_nodes"])
+    assert torch.equal(batch.extended_edge_index, golden["graph"]["extended_edge_index"])
+
+
+def test_radius_graph_and_schnet(golden, golden_batch):
+    _, batch = golden_batch
+    sd = sd_from_manifest(golden["manifest"]["schnet"], golden["meta"]["weight_seed"])
+    out, h, ei = O.schnet_forward(sd, batch.x[:, 0], batch.positions, batch.batch, batch.num_graphs)
+    assert torch.equal(ei, golden["schnet"]["radius_edge_index"])
+    torch.testing.assert_close(h, golden["schnet"]["h"], **TOL)
+    torch.testing.assert_close(out, golden["schnet"]["out"], **TOL)
+
+
+def test_dual_cl(golden):
+    X, Y = golden["gnn"]["h_eval"], golden["schnet"]["h"]
+    n1, n2 = golden["cl"]["neg_index"]
+    loss, acc = O.dual_cl(X, Y, 0.1, n1, n2)
+    torch.testing.assert_close(loss, golden["cl"]["loss"], **TOL)
+    assert abs(acc - golden["cl"]["acc"].item()) < 1e-7
+
+
+def _sde(kind):
+    return O.make_sde(kind, 0.2, 1.0, 1000)
+
+
+def test_get_score_2d3d(golden, golden_batch):
+    _, batch = golden_batch
+    for kind in ("VE", "VP"):
+        sec = golden["sde2d3d_" + kind]
+        sd = sd_from_manifest(golden["manifest"]["sde2d3d"], golden["meta"]["weight_seed"])
+        s = O.get_score_2d3d(sd, _sde(kind), golden["gnn"]["h_eval"], batch.extended_edge_index,
+                             sec["pos_perturbed"], sec["t"])
+        torch.testing.assert_close(s, sec["score"], rtol=1e-4, atol=1e-5)
+
+
+def test_train_loss_2d3d(golden, golden_batch):
+    _, batch = golden_batch
+    for kind in ("VE", "VP"):
+        sec = golden["sde2d3d_" + kind]
+        sd = sd_from_manifest(golden["manifest"]["sde2d3d"], golden["meta"]["weight_seed"])
+        draws = sec["train_draws"]
+        assert [k for k, _ in draws] == ["randn", "randint"] + ["dropout"] * 8
+        noise, ts = draws[0][1], draws[1][1]
+        masks = [v for _, v in draws[2:]]
+        dropout = [(masks[2 * i], masks[2 * i + 1]) for i in range(4)]
+        stats = {}
+        loss = O.loss_2d3d(sd, _sde(kind), golden["gnn"]["h_eval"], batch.extended_edge_index, batch.positions,
+                           batch.batch, batch.num_graphs, noise, ts, 1000, 0.0, dropout, True, stats)
+        torch.testing.assert_close(loss, sec["train_loss"], **TOL)
+        torch.testing.assert_close(stats["running_mean"], sec["bn_running_mean"], **TOL)
+        torch.testing.assert_close(stats["running_var"], sec["bn_running_var"], **TOL)
+
+
+def test_pc_sampler_2d3d(golden, golden_batch):
+    from moleculesde_b200.data import repeat_data
+    mols, _ = golden_batch
+    for kind in ("VE", "VP"):
+        pc = golden["sde2d3d_" + kind]["pc"]
+        rb = repeat_data(mols[0], pc["repeat"])
+        sd = sd_from_manifest(golden["manifest"]["sde2d3d"], golden["meta"]["weight_seed"])
+        draws = pc["draws"]
+        pos_init = draws[0]
+        steps = pc["steps"]
+        noise_c = [draws[1 + 2 * i] for i in range(steps)]
+        noise_p = [draws[2 + 2 * i] for i in range(steps)]
+        pos, pos_mean, trace = O.pc_sample_2d3d(sd, _sde(kind), pc["representation"], rb.extended_edge_index,
+                                               rb.batch, rb.num_graphs, pos_init, noise_c, noise_p,
+                                               n_diff_steps=steps, record=True)
+        calls = pc["calls"]
+        assert len(calls) == 2 * steps
+        for i in range(steps):
+            # per-step score agreement along the shared (teacher-forced) trajectory
+            pos_in, grad, pos_c, score = trace[i][:4]
+            sc = O.get_score_2d3d(sd, _sde(kind), pc["representation"], rb.extended_edge_index, calls[2 * i][0], calls[2 * i][1])
+            torch.testing.assert_close(sc, calls[2 * i][2], rtol=1e-4, atol=1e-5)
+            sp = O.get_score_2d3d(sd, _sde(kind), pc["representation"], rb.extended_edge_index, calls[2 * i + 1][0], calls[2 * i + 1][1])
+            torch.testing.assert_close(sp, calls[2 * i + 1][2], rtol=1e-4, atol=1e-5)
+        # free-running trajectory of the oracle stays on the reference's
+        torch.testing.assert_close(pos_mean, pc["pos_mean"], rtol=1e-3, atol=1e-3)
