@@ -1,0 +1,165 @@
+/*
+ * molsde_b200 -- C ABI of the B200-native (sm_100a) MoleculeSDE hot path.
+ *
+ * The reference (chao1224/MoleculeSDE) is pure Python and has no FFI: its hot path calls
+ * third-party wheels (torch_cluster / torch_sparse / torch_scatter / torch_geometric) and
+ * torch ops.  Each entry point below replaces one of those call sequences; the reference
+ * site it replaces is cited as `file:line` relative to the reference root.  A Python host
+ * binds these with ctypes (see INTEGRATION.md and moleculesde_b200/_abi.py).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - no entry point allocates, synchronises or keeps global state; all work is enqueued on
+ *     `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = MOLSDE_OK, negative = error (see molsde_status); launch errors are
+ *     reported as MOLSDE_ERR_CUDA, and molsde_last_error_string() describes the last one;
+ *   - node / edge indices inside the kernels are int32; the int64 `[2,E]` tensors of the
+ *     reference API are accepted/produced where the reference exposes them.
+ */
+#ifndef MOLSDE_B200_H_
+#define MOLSDE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum molsde_status {
+    MOLSDE_OK = 0,
+    MOLSDE_ERR_INVALID = -1,     /* bad argument (null pointer, size out of range) */
+    MOLSDE_ERR_UNSUPPORTED = -2, /* shape beyond a compiled limit (see limits below) */
+    MOLSDE_ERR_CUDA = -3,        /* CUDA runtime / launch failure */
+    MOLSDE_ERR_WORKSPACE = -4    /* workspace too small */
+} molsde_status;
+
+/* compiled limits */
+#define MOLSDE_MAX_MOL_NODES 128   /* atoms per molecule for the graph builders */
+#define MOLSDE_CHUNK_MAX_NODES 224 /* atoms per CTA chunk of the 2D->3D score / PC kernels */
+#define MOLSDE_TILE_EDGES 128      /* edges per tile (tiles are aligned to target nodes) */
+#define MOLSDE_HID 32              /* hidden_dim of SDEModel2Dto3D_02 (pretrain_MoleculeSDE.py:226) */
+#define MOLSDE_EMB 300             /* emb_dim (config.py:84) */
+
+const char* molsde_version(void);
+const char* molsde_last_error_string(void);
+/* compute capability check: returns MOLSDE_OK only on an sm_100 device */
+int molsde_check_device(int device);
+
+/* ------------------------------------------------------------------------------------
+ * Graph construction (bit-exact integer kernels)
+ * ---------------------------------------------------------------------------------- */
+
+/* ptr[s] = first position p in [0,M) with key(p) >= s, s = 0..num_segments; key(p) =
+ * keys[p] (indirect == NULL) or keys[indirect[p]].  keys must be ascending along p.
+ * Replaces the per-graph offsets PyG's Batch keeps (`batch` vector bookkeeping,
+ * SDE_model_3D_to_2D_node_adj_dense.py:124-127). */
+int molsde_segment_ptr(const int64_t* keys, const int64_t* indirect, int64_t M, int32_t num_segments,
+                       int32_t* ptr, void* stream);
+
+/* exclusive scan of int32 counts[n] into out[n+1] (out[n] = total), single launch. */
+int molsde_exclusive_scan_i32(const int32_t* counts, int64_t n, int32_t* out, void* stream);
+
+/* extend_graph, Geom3D/datasets/dataset_3D.py:12-35 (torch_sparse.spspmm + coalesce, twice):
+ * per molecule E2 = E u (E.E \ diag), E4 = E2 u (E2.E2 \ diag).
+ *   edge_index  int64 [2,E_b] (global node ids, grouped by molecule), node_ptr/edge_ptr
+ *   int32 [B+1] molecule offsets.  Pass 1 writes deg[N] (row lengths); after an exclusive
+ *   scan into rowptr[N+1], pass 2 writes col int32[E_x] (row-major sorted == coalesce order)
+ *   and, if non-NULL, the reference-layout int64 [2,E_x] tensor `ext_edge_index`. */
+int molsde_extend_graph_count(const int64_t* edge_index, int64_t E_b, const int32_t* node_ptr,
+                              const int32_t* edge_ptr, int32_t B, int32_t* deg, void* stream);
+int molsde_extend_graph_fill(const int64_t* edge_index, int64_t E_b, const int32_t* node_ptr,
+                             const int32_t* edge_ptr, int32_t B, const int32_t* rowptr, int64_t E_x,
+                             int32_t* col, int64_t* ext_edge_index, void* stream);
+
+/* radius_graph, Geom3D/models/schnet.py:91 (torch_cluster.radius_graph, CUDA semantics:
+ * d^2 < r^2 strict, first max_num_neighbors+1 hits by ascending index incl. self, self dropped).
+ * Output CSR by target with ascending sources; `edge_index` int64 [2,E_r] (row0 = source). */
+int molsde_radius_graph_count(const float* pos, const int32_t* node_ptr, int32_t B, float r,
+                              int32_t max_num_neighbors, int32_t* deg, void* stream);
+int molsde_radius_graph_fill(const float* pos, const int32_t* node_ptr, int32_t B, float r,
+                             int32_t max_num_neighbors, const int32_t* rowptr, int64_t E_r, int32_t* col,
+                             int64_t* edge_index, void* stream);
+
+/* CSR-by-target view of a generic `[2,E]` int64 edge_index (row0 = source j, row1 = target i,
+ * edges grouped by molecule): rowptr[N+1], src[E] and perm[E] (position in the input list), stable
+ * in input order -- the accumulation order of MessagePassing.propagate
+ * (schnet.py:190, equivariant_scorenetwork.py:71). Two passes like the builders above. */
+int molsde_csr_by_target_count(const int64_t* edge_index, int64_t E, int64_t N, int32_t* deg, void* stream);
+int molsde_csr_by_target_fill(const int64_t* edge_index, int64_t E, const int32_t* node_ptr,
+                              const int32_t* edge_ptr, int32_t B, const int32_t* rowptr, int32_t* src,
+                              int32_t* perm, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dense node-level linear layer  Y[M,N] = act(X[M,K] . W[N,K]^T + b)   (fp32 FFMA)
+ * Replaces torch.nn.Linear on node-major tensors (SDE_model_2D_to_3D.py:264,375; schnet.py).
+ * act: 0 none, 1 relu, 2 silu, 3 shifted softplus.
+ * ---------------------------------------------------------------------------------- */
+int molsde_linear(const float* X, int64_t M, int32_t K, int64_t ldx, const float* W, const float* b,
+                  int32_t N, float* Y, int64_t ldy, int32_t act, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * SDEModel2Dto3D_02 (Geom3D/models/MoleculeSDE/SDE_model_2D_to_3D.py:252-445)
+ *
+ * A "plan" describes how a batch is cut into CTA chunks (whole molecules, <=
+ * MOLSDE_CHUNK_MAX_NODES atoms) and target-aligned tiles of <= MOLSDE_TILE_EDGES edges:
+ *   chunk_tile_ptr int32 [C+1], tile_tgt_ptr int32 [T+1] (first target node of each tile; chunk
+ *   boundaries are tile boundaries), rowptr int32 [N+1] / src int32 [E] the CSR by target.
+ * Per-edge tensors exchanged between kernels use the tile layout  [T][MOLSDE_HID][TILE_EDGES]
+ * (feature-major inside a tile, edge slot = csr_position - rowptr[first target of the tile]).
+ * ---------------------------------------------------------------------------------- */
+
+/* float offsets of the packed parameter blob (built by the host from the state_dict) */
+typedef struct molsde_sde2d3d_params {
+    const float* blob;  /* layout: see csrc/sde2d3d_params.h (MOLSDE_P_* offsets) */
+    int64_t blob_floats;
+} molsde_sde2d3d_params;
+
+typedef struct molsde_plan {
+    int32_t num_chunks, num_tiles;
+    int64_t N, E;
+    const int32_t* chunk_tile_ptr; /* [C+1] */
+    const int32_t* tile_tgt_ptr;   /* [T+1] */
+    const int32_t* rowptr;         /* [N+1] */
+    const int32_t* src;            /* [E]   */
+} molsde_plan;
+
+/* edge_2D_emb in eval mode (BatchNorm running stats), SDE_model_2D_to_3D.py:265,405-407:
+ *   uv [N,600] = node-factored first layer with BN folded in (host: molsde_linear on the folded
+ *   weights), out e2d in tile layout = W3 . relu(uv[src,:300] + uv[tgt,300:]) + b3. */
+int molsde_edge2d_emb_eval(const molsde_plan* plan, const float* uv, const float* w3t /*[300][32]*/,
+                           const float* b3 /*[32]*/, float* e2d_tiles, void* stream);
+
+/* get_score, SDE_model_2D_to_3D.py:393-445: score[N,3] = -gradient / std.
+ *   nattr [N,32] = node_emb(node_2D_repr) (loop invariant), e2d_tiles from the call above,
+ *   pos [N,3], std [N] = marGINal_prob(.., t)[1].  scratch: num_ctas * max_chunk_tiles *
+ *   MOLSDE_HID * MOLSDE_TILE_EDGES floats. */
+int molsde_sde2d3d_score(const molsde_plan* plan, const molsde_sde2d3d_params* params, const float* nattr,
+                         const float* e2d_tiles, const float* pos, const float* std, float* score,
+                         float* scratch, int64_t scratch_floats, int32_t* status_flag, void* stream);
+int64_t molsde_sde2d3d_scratch_floats(const molsde_plan* plan, int32_t max_chunk_tiles, int32_t* num_ctas_out);
+
+/* position_PC_generation, examples/pretrain_MoleculeSDE_inference_2D_to_3D_VE_VP.py:92-138:
+ * the whole reverse-SDE loop (LangevinCorrector :191-212 + ReverseDiffusionPredictor :163-168 over
+ * RSDE.discretize, SDE_sparse.py:94-100) for independent sampling groups; one chunk == one group
+ * (the corrector step size is a mean over the group's atoms, F9), one persistent CTA per group.
+ *   step_table float [steps][8]: {std, G, sqrt_alpha (VE: 1), corr_alpha, 0,0,0,0} per reverse step,
+ *   computed by the host from the SDE object exactly as the reference does.
+ *   noise: if noise_corr/noise_pred are non-NULL they are [steps][N][3] injected draws (parity
+ *   mode); otherwise Philox4x32-10 + Box-Muller in-kernel with (seed, node, step) counters. */
+typedef struct molsde_pc_config {
+    int32_t steps;
+    float snr, scale_eps;
+    uint64_t seed;
+} molsde_pc_config;
+int molsde_sde2d3d_pc_sample(const molsde_plan* plan, const molsde_sde2d3d_params* params,
+                             const float* nattr, const float* e2d_tiles, const float* pos_init,
+                             const float* step_table, const molsde_pc_config* cfg, const float* noise_corr,
+                             const float* noise_pred, float* pos_out, float* pos_mean_out, float* scratch,
+                             int64_t scratch_floats, int32_t* work_counter, int32_t* status_flag,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOLSDE_B200_H_ */

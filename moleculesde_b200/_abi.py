@@ -1,0 +1,128 @@
+"""ctypes binding of the C ABI in `include/molsde_b200.h` (the only way Python reaches the kernels).
+
+The library is built in-tree by `__graft_entry__.build()` / `moleculesde_b200.build.build()` as
+`moleculesde_b200/libmolsde_b200.so`.  There is no fallback: if the library is missing or the
+device is not sm_100, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_uint64, c_void_p
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmolsde_b200.so")
+
+# keep in sync with include/molsde_b200.h
+MAX_MOL_NODES = 128
+CHUNK_MAX_NODES = 224
+TILE_EDGES = 128
+HID = 32
+EMB = 300
+MAX_CHUNK_TILES = 64
+
+EXPORTS = [
+    "molsde_version", "molsde_last_error_string", "molsde_check_device",
+    "molsde_segment_ptr", "molsde_exclusive_scan_i32",
+    "molsde_extend_graph_count", "molsde_extend_graph_fill",
+    "molsde_radius_graph_count", "molsde_radius_graph_fill",
+    "molsde_csr_by_target_count", "molsde_csr_by_target_fill",
+    "molsde_linear",
+    "molsde_edge2d_emb_eval", "molsde_sde2d3d_score", "molsde_sde2d3d_scratch_floats",
+    "molsde_sde2d3d_pc_sample",
+]
+
+
+class MolsdeError(RuntimeError):
+    pass
+
+
+class Plan(Structure):
+    _fields_ = [("num_chunks", c_int32), ("num_tiles", c_int32), ("N", c_int64), ("E", c_int64),
+                ("chunk_tile_ptr", c_void_p), ("tile_tgt_ptr", c_void_p), ("rowptr", c_void_p), ("src", c_void_p)]
+
+
+class Params(Structure):
+    _fields_ = [("blob", c_void_p), ("blob_floats", c_int64)]
+
+
+class PCConfig(Structure):
+    _fields_ = [("steps", c_int32), ("snr", c_float), ("scale_eps", c_float), ("seed", c_uint64)]
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the CUDA library; raises MolsdeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MolsdeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). moleculesde_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    L.molsde_version.restype = c_char_p
+    L.molsde_last_error_string.restype = c_char_p
+    L.molsde_check_device.argtypes = [c_int32]
+    L.molsde_segment_ptr.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    L.molsde_exclusive_scan_i32.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+    L.molsde_extend_graph_count.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
+    L.molsde_extend_graph_fill.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_int64,
+                                           c_void_p, c_void_p, c_void_p]
+    L.molsde_radius_graph_count.argtypes = [c_void_p, c_void_p, c_int32, c_float, c_int32, c_void_p, c_void_p]
+    L.molsde_radius_graph_fill.argtypes = [c_void_p, c_void_p, c_int32, c_float, c_int32, c_void_p, c_int64,
+                                           c_void_p, c_void_p, c_void_p]
+    L.molsde_csr_by_target_count.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p]
+    L.molsde_csr_by_target_fill.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                            c_void_p, c_void_p]
+    L.molsde_linear.argtypes = [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_void_p,
+                                c_int64, c_int32, c_void_p]
+    L.molsde_edge2d_emb_eval.argtypes = [POINTER(Plan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.molsde_sde2d3d_score.argtypes = [POINTER(Plan), POINTER(Params), c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+    L.molsde_sde2d3d_scratch_floats.argtypes = [POINTER(Plan), c_int32, POINTER(c_int32)]
+    L.molsde_sde2d3d_scratch_floats.restype = c_int64
+    L.molsde_sde2d3d_pc_sample.argtypes = [POINTER(Plan), POINTER(Params), c_void_p, c_void_p, c_void_p, c_void_p,
+                                           POINTER(PCConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_int64, c_void_p, c_void_p, c_void_p]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if fn.restype is ctypes.c_int:
+            fn.restype = c_int32
+    _lib = L
+    return L
+
+
+_device_checked = set()
+
+
+def require_device(t: torch.Tensor) -> None:
+    """Fail loudly unless `t` lives on an sm_100 CUDA device."""
+    if not t.is_cuda:
+        raise MolsdeError("moleculesde_b200 kernels need CUDA tensors (no CPU fallback)")
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx not in _device_checked:
+        check(lib().molsde_check_device(idx), "check_device")
+        _device_checked.add(idx)
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().molsde_last_error_string().decode()
+        raise MolsdeError(f"{what} failed with status {status}: {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_contiguous(), "C ABI needs contiguous tensors"
+    return t.data_ptr()
+
+
+def stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream

@@ -1,0 +1,92 @@
+"""Chunk / tile plan of a batch for the 2D->3D score and PC kernels (host bookkeeping only).
+
+A chunk is a run of whole molecules that one CTA keeps in shared memory (<= CHUNK_MAX_NODES atoms,
+<= MAX_CHUNK_TILES tiles); a tile is a run of whole target nodes with <= TILE_EDGES incoming edges.
+Built once per batch from the CSR row pointer (static graph structure); the arrays are described in
+`include/molsde_b200.h` (`molsde_plan`).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _abi
+from .graph import CSR
+
+
+@dataclass
+class TilePlan:
+    csr: CSR
+    chunk_tile_ptr: torch.Tensor  # int32 [C+1]
+    tile_tgt_ptr: torch.Tensor    # int32 [T+1]
+    num_chunks: int
+    num_tiles: int
+    max_chunk_tiles: int
+    N: int
+    E: int
+
+    def as_struct(self) -> _abi.Plan:
+        return _abi.Plan(self.num_chunks, self.num_tiles, self.N, self.E, self.chunk_tile_ptr.data_ptr(),
+                         self.tile_tgt_ptr.data_ptr(), self.csr.rowptr.data_ptr(),
+                         self.csr.col.data_ptr() if self.E else None)
+
+
+def _tiles_of_range(rowptr: np.ndarray, a: int, b: int, te: int) -> List[int]:
+    """Greedy target-aligned tiling of nodes [a,b): returns the first node of every tile."""
+    starts = []
+    i = a
+    while i < b:
+        starts.append(i)
+        # last j with rowptr[j] - rowptr[i] <= te
+        j = int(np.searchsorted(rowptr, rowptr[i] + te, side="right")) - 1
+        if j <= i:
+            raise _abi.MolsdeError(f"node {i} has more than {te} incoming edges (unsupported)")
+        i = min(j, b, i + te)  # whole targets only; also bounds the targets per tile
+    return starts
+
+
+def build_plan(csr: CSR, node_ptr: torch.Tensor, groups: Optional[Sequence[int]] = None) -> TilePlan:
+    """`node_ptr`: molecule offsets [B+1] (any device).  `groups`: optional molecule offsets
+    [G+1] of fixed chunks (sampling groups: one chunk per group, required by the PC kernel);
+    otherwise molecules are packed greedily into chunks."""
+    rowptr = csr.rowptr.detach().cpu().numpy().astype(np.int64)
+    nptr = node_ptr.detach().cpu().numpy().astype(np.int64)
+    N, E = int(nptr[-1]), int(rowptr[-1])
+    te, maxn, maxt = _abi.TILE_EDGES, _abi.CHUNK_MAX_NODES, _abi.MAX_CHUNK_TILES
+    if groups is not None:
+        chunk_bounds = [int(nptr[m]) for m in np.asarray(groups, dtype=np.int64)]
+    else:
+        chunk_bounds = [0]
+        B = len(nptr) - 1
+        edge_budget = int(maxt * te * 0.6)  # tiles are ~60-95% full; verified exactly below
+        m = 0
+        while m < B:
+            end = m
+            while end < B and nptr[end + 1] - nptr[m] <= maxn and \
+                    rowptr[nptr[end + 1]] - rowptr[nptr[m]] <= edge_budget:
+                end += 1
+            if end == m:
+                end = m + 1  # a single big molecule: let the exact checks below decide
+            chunk_bounds.append(int(nptr[end]))
+            m = end
+    chunk_tile_ptr = [0]
+    tile_starts: List[int] = []
+    max_tiles = 0
+    for c in range(len(chunk_bounds) - 1):
+        a, b = chunk_bounds[c], chunk_bounds[c + 1]
+        if b - a > maxn:
+            raise _abi.MolsdeError(f"sampling group {c} has {b - a} atoms; the fused PC kernel holds at most {maxn}")
+        ts = _tiles_of_range(rowptr, a, b, te)
+        if len(ts) > maxt:
+            raise _abi.MolsdeError(f"chunk {c} needs {len(ts)} tiles (> {maxt})")
+        tile_starts.extend(ts)
+        chunk_tile_ptr.append(len(tile_starts))
+        max_tiles = max(max_tiles, len(ts))
+    tile_starts.append(N)
+    dev = csr.rowptr.device
+    return TilePlan(csr, torch.tensor(chunk_tile_ptr, dtype=torch.int32, device=dev),
+                    torch.tensor(tile_starts, dtype=torch.int32, device=dev),
+                    len(chunk_bounds) - 1, len(tile_starts) - 1, max_tiles, N, E)

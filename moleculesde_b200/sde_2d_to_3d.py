@@ -1,0 +1,299 @@
+"""SDEModel2Dto3D_02 with the reference's constructor, `get_score` signature and state_dict keys
+(`Geom3D/models/MoleculeSDE/SDE_model_2D_to_3D.py:252-445`), computing through the sm_100a kernels
+of `csrc/sde2d3d.cu`.  The `nn.Module` tree below only OWNS parameters (so that reference
+checkpoints load key-for-key); it never runs a torch forward.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _abi
+from ._abi import check, lib, ptr, require_device, stream_ptr
+from .graph import CSR, csr_by_target, segment_ptr
+from .plan import TilePlan, build_plan
+from .sde import VESDE, VPSDE
+
+# float offsets of csrc/sde2d3d_params.h
+P_GFP_DIST_W, P_GFP_COFF_W = 0, 32
+P_IN_WT, P_IN_B = 64, 2112
+P_COFF_WT, P_COFF_B = 2144, 6240
+P_PROJ0_WT, P_PROJ0_B = 6272, 8448
+P_PROJ1_WT, P_PROJ1_B = 8480, 9504
+P_GAT0, P_GAT_SZ = 9536, 7488
+P_BASIS0, P_BASIS_SZ = 39488, 8708
+P_TOTAL = 56904
+_G = dict(WQ_T=0, WK_T=1024, WV_T=2048, WS_T=3072, BQ=4096, BK=4128, BV=4160, BS=4192, WE_T=4224,
+          LN1_W=5248, LN1_B=5280, F0_WT=5312, F0_B=6336, F3_WT=6368, F3_B=7392, LN2_W=7424, LN2_B=7456)
+_B = dict(W1_T=0, B1=8192, W2=8320, B2=8704)
+
+
+class MultiLayerPerceptron(nn.Module):
+    """Parameter container with the key layout of `layers/common.py:5-40` (`layers.{i}.weight/bias`)."""
+
+    def __init__(self, input_dim, hidden_dims, activation="relu", dropout=0):
+        super().__init__()
+        self.dims = [input_dim] + list(hidden_dims)
+        self.activation_name = activation
+        self.layers = nn.ModuleList(nn.Linear(self.dims[i], self.dims[i + 1]) for i in range(len(self.dims) - 1))
+        for layer in self.layers:
+            nn.init.xavier_uniform_(layer.weight)
+            nn.init.constant_(layer.bias, 0.0)
+
+
+class GaussianFourierProjection(nn.Module):
+    """`SDE_model_2D_to_3D.py:57-66`: fixed random frequencies stored as a frozen Parameter `W`."""
+
+    def __init__(self, embedding_size, scale=1.0):
+        super().__init__()
+        self.W = nn.Parameter(torch.randn(embedding_size) * scale, requires_grad=False)
+
+
+class _TransformerConvParams(nn.Module):
+    """Keys of torch_geometric.nn.TransformerConv (heads=8, concat, root_weight, edge_dim=hidden)."""
+
+    def __init__(self, hidden_dim, heads):
+        super().__init__()
+        self.heads, self.out_channels = heads, hidden_dim // heads
+        self.lin_key = nn.Linear(hidden_dim, hidden_dim)
+        self.lin_query = nn.Linear(hidden_dim, hidden_dim)
+        self.lin_value = nn.Linear(hidden_dim, hidden_dim)
+        self.lin_edge = nn.Linear(hidden_dim, hidden_dim, bias=False)
+        self.lin_skip = nn.Linear(hidden_dim, hidden_dim)
+
+
+class GATLayer(nn.Module):
+    """Keys of `equivariant_scorenetwork.py:13-32` (MHA, FFN.0/.3, norm1, norm2)."""
+
+    def __init__(self, n_head, hidden_dim, dropout=0.2):
+        super().__init__()
+        assert hidden_dim % n_head == 0
+        self.MHA = _TransformerConvParams(hidden_dim, n_head)
+        self.FFN = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nn.SiLU(), nn.Dropout(dropout),
+                                 nn.Linear(hidden_dim, hidden_dim))
+        self.norm1 = nn.LayerNorm(hidden_dim)
+        self.norm2 = nn.LayerNorm(hidden_dim)
+
+
+class _EquiLayerParams(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("eps", torch.Tensor([0.0]))
+
+
+class EquivariantScoreNetwork(nn.Module):
+    """Parameter tree of `equivariant_scorenetwork.py:84-119` (2 blocks x 2 GATLayers + basis MLP)."""
+
+    def __init__(self, hidden_dim, hidden_coff_dim=64, activation="silu", short_cut=False, concat_hidden=False):
+        super().__init__()
+        if short_cut or concat_hidden:
+            raise NotImplementedError("short_cut / concat_hidden are not used by any reference script")
+        self.hidden_dim, self.hidden_coff_dim = hidden_dim, hidden_coff_dim
+        self.num_layers, self.num_convs, self.num_head, self.dropout = 2, 2, 8, 0.1
+        self.gnn_layers = nn.ModuleList()
+        self.equi_modules = nn.ModuleList()
+        self.basis_mlp_modules = nn.ModuleList()
+        for _ in range(self.num_layers):
+            self.gnn_layers.append(nn.ModuleList(GATLayer(self.num_head, hidden_dim, self.dropout)
+                                                 for _ in range(self.num_convs)))
+            self.equi_modules.append(_EquiLayerParams())
+            self.basis_mlp_modules.append(nn.Sequential(nn.Linear(2 * hidden_dim, hidden_coff_dim), nn.SiLU(),
+                                                        nn.Linear(hidden_coff_dim, 3)))
+
+
+class PreparedGraph:
+    """CSR-by-target + tile plan of the (extended) edge list of one batch, built once and cached on
+    the batch object."""
+
+    def __init__(self, csr: CSR, plan: TilePlan, node_ptr: torch.Tensor):
+        self.csr, self.plan, self.node_ptr = csr, plan, node_ptr
+        self.scratch: Optional[torch.Tensor] = None
+        self.status = torch.zeros(1, dtype=torch.int32, device=csr.rowptr.device)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=csr.rowptr.device)
+
+    def get_scratch(self) -> torch.Tensor:
+        if self.scratch is None:
+            ctas = ctypes.c_int32(0)
+            st = self.plan.as_struct()
+            n = lib().molsde_sde2d3d_scratch_floats(ctypes.byref(st), self.plan.max_chunk_tiles, ctypes.byref(ctas))
+            self.scratch = torch.empty(max(int(n), 1), dtype=torch.float32, device=self.csr.rowptr.device)
+        return self.scratch
+
+
+def prepare_graph(edge_index: torch.Tensor, batch: torch.Tensor, num_graphs: int,
+                  group_ptr: Optional[torch.Tensor] = None, csr: Optional[CSR] = None) -> PreparedGraph:
+    """edge_index int64 [2,E] (reference layout), batch int64 [N] ascending."""
+    require_device(edge_index)
+    if csr is None:
+        csr = csr_by_target(edge_index, batch, num_graphs)
+    node_ptr = segment_ptr(batch, num_graphs)
+    plan = build_plan(csr, node_ptr, None if group_ptr is None else group_ptr.tolist())
+    return PreparedGraph(csr, plan, node_ptr)
+
+
+class SDEModel2Dto3D_02(nn.Module):
+    def __init__(self, emb_dim, hidden_dim, beta_schedule, beta_min, beta_max, num_diffusion_timesteps,
+                 SDE_type="VE", short_cut=False, concat_hidden=False, use_extend_graph=False):
+        super().__init__()
+        if hidden_dim != _abi.HID:
+            raise NotImplementedError(f"kernels are compiled for hidden_dim={_abi.HID} (pretrain_MoleculeSDE.py:226)")
+        self.emb_dim, self.hidden_dim = emb_dim, hidden_dim
+        self.SDE_type, self.use_extend_graph = SDE_type, use_extend_graph
+        self.node_emb = MultiLayerPerceptron(emb_dim, [hidden_dim], activation="silu")
+        self.edge_2D_emb = nn.Sequential(nn.Linear(emb_dim * 2, emb_dim), nn.BatchNorm1d(emb_dim), nn.ReLU(),
+                                         nn.Linear(emb_dim, hidden_dim))
+        self.dist_gaussian_fourier = GaussianFourierProjection(hidden_dim, scale=1)
+        self.input_mlp = MultiLayerPerceptron(2 * hidden_dim, [hidden_dim], activation="silu")
+        self.coff_gaussian_fourier = GaussianFourierProjection(hidden_dim, scale=1)
+        self.coff_mlp = nn.Linear(4 * hidden_dim, hidden_dim)
+        self.project = MultiLayerPerceptron(2 * hidden_dim + 2, [hidden_dim, hidden_dim], activation="silu")
+        self.score_network = EquivariantScoreNetwork(hidden_dim=hidden_dim, hidden_coff_dim=128, activation="silu",
+                                                     short_cut=short_cut, concat_hidden=concat_hidden)
+        if SDE_type in ("VE", "VE_test"):
+            self.sde_pos = VESDE(sigma_min=beta_min, sigma_max=beta_max, N=num_diffusion_timesteps)
+        elif SDE_type in ("VP", "VP_test"):
+            self.sde_pos = VPSDE(beta_min=beta_min, beta_max=beta_max, N=num_diffusion_timesteps)
+        else:
+            raise NotImplementedError(f"SDE_type {SDE_type!r} (discrete_VE is not on the BASELINE path)")
+        self.num_diffusion_timesteps = num_diffusion_timesteps
+        self._packed: Optional[Tuple[tuple, Dict[str, torch.Tensor]]] = None
+        self._invariants: Dict[tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    # ------------------------------------------------------------------ parameters -> kernel layout
+    def _param_version(self) -> tuple:
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def packed_params(self) -> Dict[str, torch.Tensor]:
+        """Parameter blob (csrc/sde2d3d_params.h) + BN-folded edge_2D_emb first layer; rebuilt only when
+        a parameter changes."""
+        ver = self._param_version()
+        if self._packed is not None and self._packed[0] == ver:
+            return self._packed[1]
+        sd = {k: v.detach().float() for k, v in self.state_dict().items()}
+        dev = sd["coff_mlp.weight"].device
+        blob = torch.zeros(P_TOTAL, dtype=torch.float32, device=dev)
+
+        def put(off, t):
+            blob[off:off + t.numel()] = t.reshape(-1)
+
+        put(P_GFP_DIST_W, sd["dist_gaussian_fourier.W"])
+        put(P_GFP_COFF_W, sd["coff_gaussian_fourier.W"])
+        put(P_IN_WT, sd["input_mlp.layers.0.weight"].t().contiguous())
+        put(P_IN_B, sd["input_mlp.layers.0.bias"])
+        put(P_COFF_WT, sd["coff_mlp.weight"].t().contiguous())
+        put(P_COFF_B, sd["coff_mlp.bias"])
+        put(P_PROJ0_WT, sd["project.layers.0.weight"].t().contiguous())  # 66 rows; 2 pad rows stay zero
+        put(P_PROJ0_B, sd["project.layers.0.bias"])
+        put(P_PROJ1_WT, sd["project.layers.1.weight"].t().contiguous())
+        put(P_PROJ1_B, sd["project.layers.1.bias"])
+        for m in range(2):
+            for c in range(2):
+                base = P_GAT0 + (2 * m + c) * P_GAT_SZ
+                p = f"score_network.gnn_layers.{m}.{c}."
+                put(base + _G["WQ_T"], sd[p + "MHA.lin_query.weight"].t().contiguous())
+                put(base + _G["WK_T"], sd[p + "MHA.lin_key.weight"].t().contiguous())
+                put(base + _G["WV_T"], sd[p + "MHA.lin_value.weight"].t().contiguous())
+                put(base + _G["WS_T"], sd[p + "MHA.lin_skip.weight"].t().contiguous())
+                put(base + _G["BQ"], sd[p + "MHA.lin_query.bias"])
+                put(base + _G["BK"], sd[p + "MHA.lin_key.bias"])
+                put(base + _G["BV"], sd[p + "MHA.lin_value.bias"])
+                put(base + _G["BS"], sd[p + "MHA.lin_skip.bias"])
+                put(base + _G["WE_T"], sd[p + "MHA.lin_edge.weight"].t().contiguous())
+                put(base + _G["LN1_W"], sd[p + "norm1.weight"])
+                put(base + _G["LN1_B"], sd[p + "norm1.bias"])
+                put(base + _G["F0_WT"], sd[p + "FFN.0.weight"].t().contiguous())
+                put(base + _G["F0_B"], sd[p + "FFN.0.bias"])
+                put(base + _G["F3_WT"], sd[p + "FFN.3.weight"].t().contiguous())
+                put(base + _G["F3_B"], sd[p + "FFN.3.bias"])
+                put(base + _G["LN2_W"], sd[p + "norm2.weight"])
+                put(base + _G["LN2_B"], sd[p + "norm2.bias"])
+            base = P_BASIS0 + m * P_BASIS_SZ
+            p = f"score_network.basis_mlp_modules.{m}."
+            put(base + _B["W1_T"], sd[p + "0.weight"].t().contiguous())
+            put(base + _B["B1"], sd[p + "0.bias"])
+            put(base + _B["W2"], sd[p + "2.weight"])
+            put(base + _B["B2"], sd[p + "2.bias"])
+        # edge_2D_emb, eval mode: y = relu(BN(W0 [h_row,h_col] + b0)); BN folded into W0/b0 and the
+        # layer factored per node:  W0 [h_r, h_c] = Wa h_r + Wb h_c   (SDE_model_2D_to_3D.py:265,405-407)
+        W0, b0 = sd["edge_2D_emb.0.weight"], sd["edge_2D_emb.0.bias"]
+        s = sd["edge_2D_emb.1.weight"] / torch.sqrt(sd["edge_2D_emb.1.running_var"] + 1e-5)
+        shift = sd["edge_2D_emb.1.bias"] - sd["edge_2D_emb.1.running_mean"] * s
+        E = self.emb_dim
+        w_uv = torch.cat([W0[:, :E] * s[:, None], W0[:, E:] * s[:, None]], dim=0).contiguous()  # [2E, E]
+        b_uv = torch.cat([b0 * s + shift, torch.zeros_like(b0)]).contiguous()
+        packed = {
+            "blob": blob, "w_uv": w_uv, "b_uv": b_uv,
+            "w3t": sd["edge_2D_emb.3.weight"].t().contiguous(), "b3": sd["edge_2D_emb.3.bias"].contiguous(),
+            "w_node": sd["node_emb.layers.0.weight"].contiguous(), "b_node": sd["node_emb.layers.0.bias"].contiguous(),
+        }
+        self._packed = (ver, packed)
+        self._invariants.clear()
+        return packed
+
+    # ------------------------------------------------------------------ graph / invariants
+    def _edge_index(self, data):
+        return data.extended_edge_index if self.use_extend_graph else data.edge_index
+
+    def prepared(self, data, group_ptr: Optional[torch.Tensor] = None) -> PreparedGraph:
+        key = "_molsde_prep_ext" if self.use_extend_graph else "_molsde_prep_bond"
+        prep = getattr(data, key, None)
+        if prep is None or (group_ptr is not None and getattr(prep, "group_key", None) != tuple(group_ptr.tolist())):
+            csr = getattr(data, "_molsde_ext_csr", None) if self.use_extend_graph else None
+            prep = prepare_graph(self._edge_index(data), data.batch, data.num_graphs, group_ptr, csr)
+            prep.group_key = None if group_ptr is None else tuple(group_ptr.tolist())
+            setattr(data, key, prep)
+        return prep
+
+    def invariants(self, node_2D_repr: torch.Tensor, prep: PreparedGraph) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Loop-invariant inputs of the score network: `node_emb(h)` [N,32] and the `edge_2D_emb`
+        output in tile layout.  The reference recomputes both in every `get_score` call
+        (`SDE_model_2D_to_3D.py:395,404-407,435`); they depend only on `node_2D_repr`."""
+        pk = self.packed_params()
+        key = (id(prep), node_2D_repr.data_ptr(), node_2D_repr._version, tuple(node_2D_repr.shape))
+        hit = self._invariants.get(key)
+        if hit is not None:
+            return hit
+        h = node_2D_repr.detach().float().contiguous()
+        N, dev, s = h.size(0), h.device, stream_ptr(h)
+        nattr = torch.empty(N, _abi.HID, dtype=torch.float32, device=dev)
+        check(lib().molsde_linear(ptr(h), N, self.emb_dim, self.emb_dim, ptr(pk["w_node"]), ptr(pk["b_node"]), _abi.HID,
+                                  ptr(nattr), _abi.HID, 0, s), "node_emb")
+        uv = torch.empty(N, 2 * self.emb_dim, dtype=torch.float32, device=dev)
+        check(lib().molsde_linear(ptr(h), N, self.emb_dim, self.emb_dim, ptr(pk["w_uv"]), ptr(pk["b_uv"]),
+                                  2 * self.emb_dim, ptr(uv), 2 * self.emb_dim, 0, s), "edge_2D_emb.0")
+        e2d = torch.empty(max(prep.plan.num_tiles, 1) * _abi.HID * _abi.TILE_EDGES, dtype=torch.float32, device=dev)
+        st = prep.plan.as_struct()
+        check(lib().molsde_edge2d_emb_eval(ctypes.byref(st), ptr(uv), ptr(pk["w3t"]), ptr(pk["b3"]), ptr(e2d), s),
+              "edge2d_emb_eval")
+        if len(self._invariants) > 8:
+            self._invariants.clear()
+        self._invariants[key] = (nattr, e2d)
+        return nattr, e2d
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, node_2D_repr, data, anneal_power):
+        raise NotImplementedError(
+            "training loss of SDEModel2Dto3D_02 (backward kernels) is not built yet; see DESIGN.md, scope table row a6/a13")
+
+    @torch.no_grad()
+    def get_score(self, node_2D_repr, data, pos_perturbed, sigma, t_pos):
+        """`SDE_model_2D_to_3D.py:393-445`: score [N,3] = -gradient / std(t)."""
+        require_device(pos_perturbed)
+        prep = self.prepared(data)
+        pk = self.packed_params()
+        nattr, e2d = self.invariants(node_2D_repr, prep)
+        pos = pos_perturbed.detach().float().contiguous()
+        _, std = self.sde_pos.marGINal_prob(pos, t_pos)
+        std = std.float().contiguous()
+        score = torch.empty_like(pos)
+        scratch = prep.get_scratch()
+        st = prep.plan.as_struct()
+        prm = _abi.Params(pk["blob"].data_ptr(), pk["blob"].numel())
+        prep.status.zero_()
+        check(lib().molsde_sde2d3d_score(ctypes.byref(st), ctypes.byref(prm), ptr(nattr), ptr(e2d), ptr(pos), ptr(std),
+                                         ptr(score), ptr(scratch), scratch.numel(), ptr(prep.status), stream_ptr(pos)),
+              "sde2d3d_score")
+        return score

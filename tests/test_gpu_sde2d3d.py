@@ -1,0 +1,206 @@
+"""GPU parity of the 2D->3D score network and the fused PC sampler against the golden fixtures
+(reference sources over shims) and the oracle, all through the C ABI.  Tolerance: 1e-4 relative
+(fp32, BASELINE.json north_star) measured as max |a-b| / max |b| per tensor, plus elementwise
+rtol=1e-3/atol=1e-4*scale to catch localised errors."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import sd_from_manifest  # noqa: E402
+from oracle import model as O  # noqa: E402
+from oracle import ref_ops as R  # noqa: E402
+
+REL_TOL = 1e-4
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def rel_err(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def assert_parity(a, b, what):
+    a, b = a.detach().cpu().float(), b.detach().cpu().float()
+    assert torch.isfinite(a).all(), f"{what}: non-finite output"
+    e = rel_err(a, b)
+    assert e <= REL_TOL, f"{what}: max-norm relative error {e:.3e} > {REL_TOL}"
+    scale = b.abs().max().item()
+    torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-4 * scale, msg=lambda m: f"{what}: {m}")
+
+
+def _model(golden, kind, dev):
+    from moleculesde_b200.sde_2d_to_3d import SDEModel2Dto3D_02
+    m = SDEModel2Dto3D_02(emb_dim=300, hidden_dim=32, beta_schedule=None, beta_min=0.2, beta_max=1.0,
+                          num_diffusion_timesteps=1000, SDE_type=kind, use_extend_graph=True)
+    sd = sd_from_manifest(golden["manifest"]["sde2d3d"], golden["meta"]["weight_seed"])
+    m.load_state_dict(sd)
+    return m.to(dev).eval(), sd
+
+
+def _gpu_batch(batch, dev, ext_from_kernel=True):
+    """Move a batch to the GPU; the extended graph comes from the CUDA kernel (product path)."""
+    from moleculesde_b200 import graph as G
+    b = batch.to(dev)
+    if ext_from_kernel:
+        csr = G.extend_graph(b.edge_index, b.batch, b.num_graphs)
+        b.extended_edge_index = csr.edge_index
+    return b
+
+
+@pytest.mark.parametrize("kind", ["VE", "VP"])
+def test_get_score_vs_golden(kind, golden, golden_batch):
+    dev = _dev()
+    _, batch = golden_batch
+    model, _ = _model(golden, kind, dev)
+    sec = golden["sde2d3d_" + kind]
+    b = _gpu_batch(batch, dev)
+    assert torch.equal(b.extended_edge_index.cpu(), golden["graph"]["extended_edge_index"])
+    h2d = golden["gnn"]["h_eval"].to(dev)
+    score = model.get_score(h2d, b, sec["pos_perturbed"].to(dev), None, sec["t"].to(dev))
+    assert_parity(score, sec["score"], f"get_score[{kind}] vs reference")
+    # second call hits the invariant cache and must give identical bits (deterministic kernels)
+    score2 = model.get_score(h2d, b, sec["pos_perturbed"].to(dev), None, sec["t"].to(dev))
+    assert torch.equal(score, score2)
+
+
+def test_edge2d_and_node_invariants_vs_oracle(golden, golden_batch):
+    from moleculesde_b200 import _abi
+    dev = _dev()
+    _, batch = golden_batch
+    model, sd = _model(golden, "VE", dev)
+    b = _gpu_batch(batch, dev)
+    h2d = golden["gnn"]["h_eval"]
+    prep = model.prepared(b)
+    nattr, e2d = model.invariants(h2d.to(dev), prep)
+    assert_parity(nattr, O.node_emb(sd, h2d), "node_emb")
+    # un-tile the kernel's [T][32][128] layout back to CSR edge order, then to the reference order
+    ei = batch.extended_edge_index
+    ref = O.edge_2d_emb(sd, h2d, ei, training=False)  # reference order: sorted by (row, col); row=source
+    tt = prep.plan.tile_tgt_ptr.cpu().long()
+    rp = prep.csr.rowptr.cpu().long()
+    e2d = e2d.cpu().view(-1, 32, _abi.TILE_EDGES)
+    rows = []
+    for t in range(prep.plan.num_tiles):
+        ne = int(rp[tt[t + 1]] - rp[tt[t]])
+        rows.append(e2d[t, :, :ne].t())
+        assert torch.all(e2d[t, :, ne:] == 0)
+    got = torch.cat(rows)  # CSR-by-target order: (target asc, source asc)
+    perm = prep.csr.perm.cpu().long()  # position of each CSR edge in the reference list
+    assert_parity(got, ref[perm], "edge_2D_emb (eval)")
+
+
+@pytest.mark.parametrize("kind,num,seed", [("pcqm", 64, 11), ("drug", 6, 12)])
+def test_get_score_vs_oracle_multichunk(kind, num, seed, golden):
+    """Batches that need several CTA chunks / many tiles, incl. drug-sized molecules (<=100 atoms)."""
+    from moleculesde_b200.data import Batch, synth_molecules
+    dev = _dev()
+    mols = synth_molecules(num, seed, kind)
+    batch = Batch.from_data_list(mols)
+    model, sd = _model(golden, "VE", dev)
+    b = _gpu_batch(batch, dev)
+    ext = torch.cat([R.extend_graph_index(m.edge_index, m.num_nodes) + int(o) for m, o in zip(mols, batch.ptr[:-1])], dim=1)
+    assert torch.equal(b.extended_edge_index.cpu(), ext)
+    g = torch.Generator().manual_seed(seed)
+    N = batch.positions.size(0)
+    h2d = torch.randn(N, 300, generator=g)
+    pos = batch.positions + 0.2 * torch.randn(N, 3, generator=g)
+    t = (torch.rand(num, generator=g) * 0.9 + 0.05)[batch.batch]
+    ref = O.get_score_2d3d(sd, O.make_sde("VE", 0.2, 1.0, 1000), h2d, ext, pos, t)
+    got = model.get_score(h2d.to(dev), b, pos.to(dev), None, t.to(dev))
+    prep = model.prepared(b)
+    assert prep.plan.num_chunks > 1
+    assert int(prep.status.item()) == 0
+    assert_parity(got, ref, f"get_score multichunk {kind}")
+
+
+@pytest.mark.parametrize("kind", ["VE", "VP"])
+def test_pc_sampler_vs_golden(kind, golden, golden_batch):
+    """Per-step score agreement along the reference's own trajectory (teacher forced) and the
+    free-running fused kernel with the reference's recorded noise draws."""
+    from moleculesde_b200.data import repeat_data
+    from moleculesde_b200.sampler import position_PC_generation
+    dev = _dev()
+    mols, _ = golden_batch
+    pc = golden["sde2d3d_" + kind]["pc"]
+    model, sd = _model(golden, kind, dev)
+    rb = _gpu_batch(repeat_data(mols[0], pc["repeat"]), dev)
+    rep = pc["representation"].to(dev)
+    for i, (pos_in, tt, score) in enumerate(pc["calls"]):
+        got = model.get_score(rep, rb, pos_in.to(dev), None, tt.to(dev))
+        assert_parity(got, score, f"per-step score, call {i} [{kind}]")
+    draws, steps = pc["draws"], pc["steps"]
+    noise_c = torch.stack([draws[1 + 2 * i] for i in range(steps)]).to(dev)
+    noise_p = torch.stack([draws[2 + 2 * i] for i in range(steps)]).to(dev)
+    _, pos_mean = position_PC_generation(rep, rb, draws[0].to(dev), model, model.sde_pos, n_steps=1,
+                                         noise_corr=noise_c, noise_pred=noise_p, diffusion_steps=steps)
+    torch.cuda.synchronize()
+    assert int(model.prepared(rb).status.item()) == 0
+    # trajectories amplify rounding differences step by step: tolerance for the 6-step end point
+    a, b = pos_mean.cpu(), pc["pos_mean"]
+    assert torch.isfinite(a).all()
+    assert rel_err(a, b) < 2e-3, f"free-running pos_mean [{kind}] rel err {rel_err(a, b):.3e}"
+    _, pos = position_PC_generation(rep, rb, draws[0].to(dev), model, model.sde_pos, n_steps=1, denoise=False,
+                                    noise_corr=noise_c, noise_pred=noise_p, diffusion_steps=steps)
+    assert torch.isfinite(pos).all() and not torch.equal(pos, pos_mean)
+
+
+def test_pc_sampler_groups_vs_oracle(golden):
+    """Several independent sampling groups in one launch == the oracle run group by group (each
+    group has its own Langevin step size, F9)."""
+    from moleculesde_b200.data import Batch, repeat_data, synth_molecules
+    from moleculesde_b200.sampler import position_PC_generation
+    dev = _dev()
+    mols = synth_molecules(3, 21, "pcqm")
+    reps = [3, 5, 2]
+    groups = [repeat_data(m, r) for m, r in zip(mols, reps)]
+    datas = [d for gb in groups for d in gb.to_data_list()]
+    big = Batch.from_data_list(datas)
+    group_ptr = torch.tensor([0, 3, 8, 10])
+    model, sd = _model(golden, "VE", dev)
+    sde = O.make_sde("VE", 0.2, 1.0, 1000)
+    b = _gpu_batch(big, dev)
+    g = torch.Generator().manual_seed(5)
+    N = big.positions.size(0)
+    rep = torch.randn(N, 300, generator=g)
+    steps = 4
+    pos0 = torch.randn(N, 3, generator=g)
+    nc = torch.randn(steps, N, 3, generator=g)
+    npd = torch.randn(steps, N, 3, generator=g)
+    _, pos_mean = position_PC_generation(rep.to(dev), b, pos0.to(dev), model, model.sde_pos, group_ptr=group_ptr,
+                                         noise_corr=nc.to(dev), noise_pred=npd.to(dev), diffusion_steps=steps)
+    assert int(model.prepared(b).status.item()) == 0
+    ptr = big.ptr
+    ext = b.extended_edge_index.cpu()
+    for gi in range(3):
+        a, e = int(ptr[group_ptr[gi]]), int(ptr[group_ptr[gi + 1]])
+        m = (ext[0] >= a) & (ext[0] < e)
+        sub_ei = ext[:, m] - a
+        sub_batch = big.batch[a:e] - int(group_ptr[gi])
+        _, ref = O.pc_sample_2d3d(sd, sde, rep[a:e], sub_ei, sub_batch, int(group_ptr[gi + 1] - group_ptr[gi]), pos0[a:e],
+                                  nc[:, a:e], npd[:, a:e], n_diff_steps=steps)
+        assert rel_err(pos_mean[a:e].cpu(), ref) < 2e-3, f"group {gi}"
+
+
+def test_pc_sampler_philox_mode(golden):
+    """Throughput mode (in-kernel Philox noise): finite, seed-reproducible, seed-sensitive."""
+    from moleculesde_b200.data import repeat_data, synth_molecules
+    from moleculesde_b200.sampler import position_PC_generation
+    dev = _dev()
+    mol = synth_molecules(1, 33, "pcqm")[0]
+    rb = _gpu_batch(repeat_data(mol, 10), dev)
+    model, _ = _model(golden, "VE", dev)
+    g = torch.Generator().manual_seed(1)
+    rep = torch.randn(rb.positions.size(0), 300, generator=g).to(dev)
+    pos0 = torch.randn(rb.positions.size(0), 3, generator=g).to(dev)
+    outs = []
+    for seed in (7, 7, 8):
+        _, p = position_PC_generation(rep, rb, pos0, model, model.sde_pos, seed=seed, diffusion_steps=5)
+        outs.append(p.clone())
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
+    assert not torch.equal(outs[0], outs[2])

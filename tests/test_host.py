@@ -1,0 +1,144 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol the header declares
+(no compute calls), state_dict layouts match the reference manifests, schedules and the tile
+planner behave."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from moleculesde_b200 import build
+    path = build.build()
+    assert os.path.exists(path)
+    return path
+
+
+def test_library_exports_header_symbols(built_lib):
+    header = open(os.path.join(REPO, "include", "molsde_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(molsde_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 15
+    L = ctypes.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/molsde_b200.h but not exported"
+    from moleculesde_b200 import _abi
+    assert sorted(_abi.EXPORTS) == declared
+    L.molsde_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in L.molsde_version()
+
+
+def test_param_offsets_match_header():
+    from moleculesde_b200 import sde_2d_to_3d as M
+    hdr = open(os.path.join(REPO, "moleculesde_b200", "csrc", "sde2d3d_params.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(MOLSDE_\w+)\s+(\d+)", hdr)}
+    assert defs["MOLSDE_P_TOTAL"] == M.P_TOTAL == defs["MOLSDE_P_BASIS0"] + 2 * defs["MOLSDE_P_BASIS_SZ"]
+    assert defs["MOLSDE_P_GAT0"] == M.P_GAT0 and defs["MOLSDE_P_GAT_SZ"] == M.P_GAT_SZ
+    assert defs["MOLSDE_P_BASIS0"] == M.P_BASIS0 == M.P_GAT0 + 4 * M.P_GAT_SZ
+    for k, v in M._G.items():
+        assert defs["MOLSDE_G_" + k] == v
+    for k, v in M._B.items():
+        assert defs["MOLSDE_B_" + k] == v
+    for name in ("IN_WT", "IN_B", "COFF_WT", "COFF_B", "PROJ0_WT", "PROJ0_B", "PROJ1_WT", "PROJ1_B"):
+        assert defs["MOLSDE_P_" + name] == getattr(M, "P_" + name)
+        assert defs["MOLSDE_P_" + name] % 4 == 0
+
+
+def test_state_dict_layout_matches_reference(golden):
+    from moleculesde_b200.sde_2d_to_3d import SDEModel2Dto3D_02
+    m = SDEModel2Dto3D_02(emb_dim=300, hidden_dim=32, beta_schedule=None, beta_min=0.2, beta_max=1.0,
+                          num_diffusion_timesteps=1000, SDE_type="VE", use_extend_graph=True)
+    mine = {k: (tuple(v.shape), str(v.dtype)) for k, v in m.state_dict().items()}
+    assert mine == golden["manifest"]["sde2d3d"]
+
+
+def test_packed_blob_roundtrip(golden):
+    from conftest import sd_from_manifest
+    from moleculesde_b200 import sde_2d_to_3d as M
+    m = M.SDEModel2Dto3D_02(300, 32, None, 0.2, 1.0, 1000, "VE", use_extend_graph=True)
+    sd = sd_from_manifest(golden["manifest"]["sde2d3d"], 1)
+    m.load_state_dict(sd)
+    pk = m.packed_params()
+    blob = pk["blob"]
+    assert blob.numel() == M.P_TOTAL
+    W = sd["coff_mlp.weight"]
+    assert torch.equal(blob[M.P_COFF_WT:M.P_COFF_WT + 128 * 32].view(128, 32), W.t())
+    base = M.P_GAT0 + 3 * M.P_GAT_SZ
+    assert torch.equal(blob[base + M._G["WE_T"]:base + M._G["WE_T"] + 1024].view(32, 32),
+                       sd["score_network.gnn_layers.1.1.MHA.lin_edge.weight"].t())
+    base = M.P_BASIS0 + M.P_BASIS_SZ
+    assert torch.equal(blob[base + M._B["W2"]:base + M._B["W2"] + 384].view(3, 128),
+                       sd["score_network.basis_mlp_modules.1.2.weight"])
+    # BN-folded, node-factored first layer of edge_2D_emb equals the reference layer in eval mode
+    h = torch.randn(7, 300)
+    row, col = torch.tensor([0, 3, 5]), torch.tensor([1, 2, 6])
+    x = torch.cat([h[row], h[col]], -1) @ sd["edge_2D_emb.0.weight"].t() + sd["edge_2D_emb.0.bias"]
+    x = torch.nn.functional.batch_norm(x, sd["edge_2D_emb.1.running_mean"], sd["edge_2D_emb.1.running_var"],
+                                       sd["edge_2D_emb.1.weight"], sd["edge_2D_emb.1.bias"], False, 0.1, 1e-5)
+    uv = h @ pk["w_uv"].t() + pk["b_uv"]
+    torch.testing.assert_close(uv[row, :300] + uv[col, 300:], x, rtol=1e-4, atol=1e-5)
+    # cache: unchanged parameters -> same object; in-place change -> repack
+    assert m.packed_params() is pk
+    with torch.no_grad():
+        m.coff_mlp.bias.add_(1.0)
+    assert m.packed_params() is not pk
+
+
+def test_sde_schedules_match_oracle():
+    from moleculesde_b200 import sde as S
+    from oracle import model as O
+    t = torch.linspace(1, 1e-4, 1000)
+    for mine, ref in ((S.VESDE(0.2, 1.0, 1000), O.VESDE(0.2, 1.0, 1000)), (S.VPSDE(0.2, 1.0, 1000), O.VPSDE(0.2, 1.0, 1000))):
+        x = torch.randn(1000, 3)
+        m1, s1 = mine.marGINal_prob(x, t)
+        m2, s2 = ref.marginal_prob(x, t)
+        assert torch.equal(m1, m2) and torch.equal(s1, s2)
+        f1, g1 = mine.discretize(x, t)
+        f2, g2 = ref.discretize(x, t)
+        assert torch.equal(f1, f2) and torch.equal(g1, g2)
+        tab = mine.step_table(t)
+        assert torch.equal(tab[:, 0], s2) and torch.equal(tab[:, 1], g2)
+        assert torch.equal(tab[:, 3], ref.corrector_alpha(t))
+        torch.testing.assert_close(tab[:, 2:3] * x - x, f2, rtol=0, atol=0)
+
+
+def test_tile_planner(golden_batch):
+    from moleculesde_b200 import _abi
+    from moleculesde_b200.graph import CSR
+    from moleculesde_b200.plan import build_plan
+    _, batch = golden_batch
+    ei = batch.extended_edge_index
+    N = batch.positions.size(0)
+    deg = torch.bincount(ei[0], minlength=N)
+    rowptr = torch.cat([torch.zeros(1, dtype=torch.long), deg.cumsum(0)]).int()
+    csr = CSR(rowptr, ei[1].int())
+    plan = build_plan(csr, batch.ptr)
+    tt = plan.tile_tgt_ptr.numpy()
+    ct = plan.chunk_tile_ptr.numpy()
+    assert tt[0] == 0 and tt[-1] == N and np.all(np.diff(tt) > 0)
+    rp = rowptr.numpy()
+    assert np.all(rp[tt[1:]] - rp[tt[:-1]] <= _abi.TILE_EDGES)
+    # chunks are unions of whole molecules within the per-CTA limits
+    mol_bounds = set(batch.ptr.tolist())
+    for c in range(plan.num_chunks):
+        a, b = tt[ct[c]], tt[ct[c + 1]]
+        assert a in mol_bounds and b in mol_bounds and b - a <= _abi.CHUNK_MAX_NODES
+        assert ct[c + 1] - ct[c] <= _abi.MAX_CHUNK_TILES
+    # fixed groups: one chunk per group
+    plan2 = build_plan(csr, batch.ptr, [0, 3, 8])
+    assert plan2.num_chunks == 2
+    with pytest.raises(_abi.MolsdeError):
+        big = torch.tensor([0, 300])
+        build_plan(CSR(torch.zeros(301, dtype=torch.int32), torch.zeros(0, dtype=torch.int32)), big, [0, 1])
+
+
+def test_no_cpu_fallback():
+    from moleculesde_b200 import _abi
+    from moleculesde_b200.graph import radius_graph
+    with pytest.raises(_abi.MolsdeError):
+        radius_graph(torch.zeros(4, 3), 10.0, torch.zeros(4, dtype=torch.long), 1)
