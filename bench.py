@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: 2D->3D VE reverse-SDE conformer generation (BASELINE.json configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            # B200 arm (one process per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # CPU reference arm (oracle port, host cores)
+
+One bench "step" = one full `position_PC_generation` pass (1000 predictor-corrector reverse steps,
+2 score-network evaluations each) over the workload: `--molecules` synthetic PCQM4Mv2-shaped
+molecules x `--repeat` conformers each (reference `num_repeat_SDE_inference=10`); every molecule's
+conformers form one sampling group (the Langevin step size is a per-group mean).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "2D->3D reverse-SDE conformers/sec"
+UNIT = "conformers/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--molecules", type=int, default=1024, help="molecules per GPU (BASELINE configs[1]: 1024)")
+    p.add_argument("--repeat", type=int, default=10, help="conformers per molecule (config.py:133)")
+    p.add_argument("--pc-steps", type=int, default=1000, help="reverse-SDE steps (num_diffusion_timesteps)")
+    p.add_argument("--cpu-pc-steps", type=int, default=10, help="PC steps of the bounded CPU sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--seed", type=int, default=0)
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def build_workload(num_mols: int, repeat: int, seed: int):
+    """Host-side batch: every molecule repeated `repeat` times (repeat_data semantics), collated."""
+    from moleculesde_b200.data import Batch, synth_molecules
+    mols = synth_molecules(num_mols, seed, "pcqm")
+    xs, eis, eas, poss, bvec, ptr = [], [], [], [], [], [0]
+    off, g = 0, 0
+    for m in mols:
+        n = m.num_nodes
+        for _ in range(repeat):
+            xs.append(m.x); eas.append(m.edge_attr); poss.append(m.positions)
+            eis.append(m.edge_index + off)
+            bvec.append(torch.full((n,), g, dtype=torch.long))
+            off += n; g += 1
+            ptr.append(off)
+    b = Batch()
+    b.x, b.edge_attr, b.positions = torch.cat(xs), torch.cat(eas), torch.cat(poss)
+    b.edge_index = torch.cat(eis, dim=1)
+    b.batch = torch.cat(bvec)
+    b.ptr = torch.tensor(ptr, dtype=torch.long)
+    b.num_graphs = g
+    group_ptr = torch.arange(0, g + 1, repeat, dtype=torch.long)
+    return mols, b, group_ptr
+
+
+def make_model(dev, seed=1):
+    from moleculesde_b200.sde_2d_to_3d import SDEModel2Dto3D_02
+    torch.manual_seed(seed)
+    m = SDEModel2Dto3D_02(emb_dim=300, hidden_dim=32, beta_schedule=None, beta_min=0.2, beta_max=1.0,
+                          num_diffusion_timesteps=1000, SDE_type="VE", use_extend_graph=True)
+    with torch.no_grad():  # random-init weights; BN running stats as after some training
+        m.edge_2D_emb[1].running_mean.uniform_(-0.1, 0.1)
+        m.edge_2D_emb[1].running_var.uniform_(0.5, 1.5)
+    return m.to(dev).eval()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm (test infrastructure used as the measured
+# baseline here and nowhere else)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(mols, repeat, pc_steps_sample, total_pc_steps, state_dict, reps=1):
+    """conformers/s of the reference algorithm on this box's host cores: `pc_steps_sample` PC steps on
+    one sampling group (molecule 0 x `repeat` conformers), extrapolated to `total_pc_steps`."""
+    from moleculesde_b200.data import repeat_data
+    from oracle import model as O
+    from oracle.ref_ops import extend_graph_index
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: v.detach().cpu().float() for k, v in state_dict.items()}
+    mol = mols[0]
+    mol.extended_edge_index = extend_graph_index(mol.edge_index, mol.num_nodes)
+    rb = repeat_data(mol, repeat)
+    sde = O.make_sde("VE", 0.2, 1.0, 1000)
+    g = torch.Generator().manual_seed(0)
+    n = rb.positions.size(0)
+    rep = torch.randn(n, 300, generator=g)
+    pos0 = torch.randn(n, 3, generator=g)
+    nc = torch.randn(pc_steps_sample, n, 3, generator=g)
+    npd = torch.randn(pc_steps_sample, n, 3, generator=g)
+    best = None
+    for _ in range(max(reps, 1)):
+        t0 = time.perf_counter()
+        O.pc_sample_2d3d(sd, sde, rep, rb.extended_edge_index, rb.batch, rb.num_graphs, pos0, nc, npd,
+                         n_diff_steps=pc_steps_sample)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    per_pc_step = best / pc_steps_sample
+    rate = repeat / (per_pc_step * total_pc_steps)
+    sample = (f"{pc_steps_sample} PC steps (2 score evals each) on one group of {repeat} conformers of a "
+              f"{mol.num_nodes}-atom molecule, extrapolated x{total_pc_steps / pc_steps_sample:g} to {total_pc_steps} steps; "
+              "oracle port (pure-torch restatement of the reference), fp32")
+    return rate, per_pc_step, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mols, _, _ = build_workload(min(args.molecules, 4), args.repeat, args.seed)
+    model = make_model("cpu")
+    times = []
+    for i in range(args.warmup + args.steps):
+        rate, per_step, sample = cpu_reference_rate(mols, args.repeat, args.cpu_pc_steps, args.pc_steps, model.state_dict())
+        if i >= args.warmup:
+            times.append(per_step * args.pc_steps)  # seconds for `repeat` conformers, extrapolated
+    t = float(np.mean(times))
+    value = args.repeat / t
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"BASELINE configs[1]: 2D->3D VE reverse-SDE (SDEModel2Dto3D_02, sigma 0.2..1, "
+                        f"{args.pc_steps}-step predictor-corrector, snr 0.2, corrector n_steps 1), "
+                        f"{args.molecules} synthetic PCQM4Mv2-shaped molecules x {args.repeat} conformers per GPU",
+            "molecules_per_gpu": args.molecules, "conformers_per_molecule": args.repeat, "pc_steps": args.pc_steps,
+            "emb_dim": 300, "hidden_dim": 32, "use_extend_graph": True,
+            "l2": "inputs (edge_2D_emb tiles + 2D representation, >400 MB at the default size) exceed the 126 MB L2; no explicit flush",
+            "noise": "in-kernel Philox4x32-10 + Box-Muller"}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (B200 arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from moleculesde_b200 import build as _b
+    _b.build()
+    from moleculesde_b200 import graph as G
+    from moleculesde_b200.sampler import position_PC_generation
+
+    # workload (weak scaling: every rank its own molecules)
+    mols, hb, group_ptr = build_workload(args.molecules, args.repeat, args.seed + rank)
+    n_atoms = hb.positions.size(0)
+    n_conf = hb.num_graphs
+    g = torch.Generator().manual_seed(100 + rank)
+    rep_h = torch.randn(n_atoms, 300, generator=g).pin_memory()
+    pos0_h = torch.randn(n_atoms, 3, generator=g).pin_memory()
+    ei_h, batch_h = hb.edge_index.pin_memory(), hb.batch.pin_memory()
+    model = make_model(dev)
+
+    class DevBatch:
+        pass
+
+    def stage_inputs():
+        """H2D of one step's inputs + graph construction (extended graph, CSR, tile plan)."""
+        d = hb.__class__()
+        d.edge_index = ei_h.to(dev, non_blocking=True)
+        d.batch = batch_h.to(dev, non_blocking=True)
+        d.num_graphs = n_conf
+        rep = rep_h.to(dev, non_blocking=True)
+        pos0 = pos0_h.to(dev, non_blocking=True)
+        csr = G.extend_graph(d.edge_index, d.batch, n_conf, want_edge_index=True)
+        d.extended_edge_index = csr.edge_index
+        d._molsde_ext_csr = csr
+        return d, rep, pos0
+
+    def hot_path(d, rep, pos0, step_seed):
+        model._invariants.clear()  # the reference recomputes node_emb / edge_2D_emb inside the call
+        _, pos_mean = position_PC_generation(rep, d, pos0, model, model.sde_pos, n_steps=1, group_ptr=group_ptr,
+                                             seed=step_seed, diffusion_steps=args.pc_steps)
+        return pos_mean
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (`value`) ----------------
+    d, rep, pos0 = stage_inputs()
+    prep = model.prepared(d, group_ptr)
+    for w in range(args.warmup):
+        hot_path(d, rep, pos0, w)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    pc_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        model._invariants.clear()
+        nattr_e2d = model.invariants(rep, prep)  # 3 launches: node_emb, edge_2D_emb layer 0 (folded BN), edge tiles
+        pc_ev[k][0].record()
+        pm = hot_path_pc_only(model, d, rep, pos0, group_ptr, 1000 + k, args.pc_steps)
+        pc_ev[k][1].record()
+    ev[1].record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = ev[0].elapsed_time(ev[1])
+    pc_ms = float(np.mean([a.elapsed_time(b) for a, b in pc_ev]))
+    if not torch.isfinite(pm).all():
+        raise SystemExit("non-finite positions out of the sampler")
+    if int(prep.status.item()) != 0:
+        raise SystemExit(f"kernel reported an unsupported chunk ({int(prep.status.item())})")
+
+    # ---------------- end to end (`e2e`): host buffers in, host result out ----------------
+    out_h = torch.empty(n_atoms, 3).pin_memory()
+    e2e_steps = max(1, min(args.steps, 2))
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        d2, rep2, pos2 = stage_inputs()
+        pm2 = hot_path(d2, rep2, pos2, 2000 + k)
+        out_h.copy_(pm2, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    h2d = rep_h.numel() * 4 + pos0_h.numel() * 4 + ei_h.numel() * 8 + batch_h.numel() * 8
+    d2h = out_h.numel() * 4
+
+    # ---------------- reduce over ranks (max time) ----------------
+    tt = torch.tensor([elapsed_ms, pc_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    elapsed_ms, pc_ms, e2e_s = [float(x) for x in tt.tolist()]
+    ms_per_step = elapsed_ms / args.steps
+    value = world * n_conf / (ms_per_step * 1e-3)
+    e2e_value = world * n_conf / e2e_s
+
+    if rank == 0:
+        # roofline of the dominant kernel (sde2d3d_pc_kernel): SURVEY section 8(d) algorithmic work per launch
+        N, Ex = n_atoms, prep.plan.E
+        evals = 2 * args.pc_steps
+        k3_bytes = 156 * N + 132 * Ex + 4 * (N + 1) + 266_000
+        bytes_launch = evals * k3_bytes + args.pc_steps * 48 * N
+        flops_launch = evals * (2 * (34_624 * Ex + 24_576 * N))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = bytes_launch / (pc_ms * 1e-3) / 1e9
+        fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+        tflops = flops_launch / (pc_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "includes": "pinned-host H2D of representation/positions/edge_index/batch, extended-graph + CSR + tile plan, "
+                                "invariants, fused PC kernel, D2H of pos_mean"},
+            "gpu_launches": args.steps * 4,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                         "kernel": "sde2d3d_pc_kernel", "kernel_ms": pc_ms,
+                         "note": "algorithmic bytes = layer-granular figure of SURVEY 8(d); the fused kernel keeps node state in smem "
+                                 "and is FP32-FFMA bound, see roofline_fp32"},
+            "roofline_fp32": {"bound": "fp32_ffma", "achieved": tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tflops / fp32_peak,
+                              "note": "derived peak = 148 SM x 128 lanes x 2 x max SM clock; FLOPs = reference-form 2*(34,624 E_x + 24,576 N) per score eval"},
+            "atoms": N, "edges": Ex, "groups": int(group_ptr.numel() - 1),
+        }
+        if not args.no_cpu_baseline:
+            rate, per_step, sample = cpu_reference_rate(mols, args.repeat, args.cpu_pc_steps, args.pc_steps, model.state_dict())
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def hot_path_pc_only(model, d, rep, pos0, group_ptr, seed, pc_steps):
+    from moleculesde_b200.sampler import position_PC_generation
+    _, pos_mean = position_PC_generation(rep, d, pos0, model, model.sde_pos, n_steps=1, group_ptr=group_ptr,
+                                         seed=seed, diffusion_steps=pc_steps)
+    return pos_mean
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

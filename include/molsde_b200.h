@@ -38,6 +38,7 @@ typedef enum molsde_status {
 #define MOLSDE_MAX_MOL_NODES 128   /* atoms per molecule for the graph builders */
 #define MOLSDE_CHUNK_MAX_NODES 224 /* atoms per CTA chunk of the 2D->3D score / PC kernels */
 #define MOLSDE_TILE_EDGES 128      /* edges per tile (tiles are aligned to target nodes) */
+#define MOLSDE_TILE_LD 136         /* padded row length of a per-edge attribute tile [MOLSDE_HID][MOLSDE_TILE_LD] */
 #define MOLSDE_HID 32              /* hidden_dim of SDEModel2Dto3D_02 (pretrain_MoleculeSDE.py:226) */
 #define MOLSDE_EMB 300             /* emb_dim (config.py:84) */
 
@@ -105,8 +106,9 @@ int molsde_linear(const float* X, int64_t M, int32_t K, int64_t ldx, const float
  * MOLSDE_CHUNK_MAX_NODES atoms) and target-aligned tiles of <= MOLSDE_TILE_EDGES edges:
  *   chunk_tile_ptr int32 [C+1], tile_tgt_ptr int32 [T+1] (first target node of each tile; chunk
  *   boundaries are tile boundaries), rowptr int32 [N+1] / src int32 [E] the CSR by target.
- * Per-edge tensors exchanged between kernels use the tile layout  [T][MOLSDE_HID][TILE_EDGES]
- * (feature-major inside a tile, edge slot = csr_position - rowptr[first target of the tile]).
+ * Per-edge tensors exchanged between kernels use the tile layout  [T][MOLSDE_HID][MOLSDE_TILE_LD]
+ * (feature-major inside a tile, edge slot = csr_position - rowptr[first target of the tile], slots
+ * >= the tile's edge count and the 8 pad columns are zero); molsde_tile_floats() floats per tile.
  * ---------------------------------------------------------------------------------- */
 
 /* float offsets of the packed parameter blob (built by the host from the state_dict) */
@@ -133,11 +135,12 @@ int molsde_edge2d_emb_eval(const molsde_plan* plan, const float* uv, const float
 /* get_score, SDE_model_2D_to_3D.py:393-445: score[N,3] = -gradient / std.
  *   nattr [N,32] = node_emb(node_2D_repr) (loop invariant), e2d_tiles from the call above,
  *   pos [N,3], std [N] = marGINal_prob(.., t)[1].  scratch: num_ctas * max_chunk_tiles *
- *   MOLSDE_HID * MOLSDE_TILE_EDGES floats. */
+ *   molsde_tile_floats() floats. */
 int molsde_sde2d3d_score(const molsde_plan* plan, const molsde_sde2d3d_params* params, const float* nattr,
                          const float* e2d_tiles, const float* pos, const float* std, float* score,
                          float* scratch, int64_t scratch_floats, int32_t* status_flag, void* stream);
 int64_t molsde_sde2d3d_scratch_floats(const molsde_plan* plan, int32_t max_chunk_tiles, int32_t* num_ctas_out);
+int64_t molsde_tile_floats(void);
 
 /* position_PC_generation, examples/pretrain_MoleculeSDE_inference_2D_to_3D_VE_VP.py:92-138:
  * the whole reverse-SDE loop (LangevinCorrector :191-212 + ReverseDiffusionPredictor :163-168 over

@@ -20,6 +20,8 @@ LIB_PATH = os.path.join(_HERE, "libmolsde_b200.so")
 MAX_MOL_NODES = 128
 CHUNK_MAX_NODES = 224
 TILE_EDGES = 128
+TILE_LD = 136
+TILE_FLOATS = 32 * TILE_LD
 HID = 32
 EMB = 300
 MAX_CHUNK_TILES = 64
@@ -31,7 +33,7 @@ EXPORTS = [
     "molsde_radius_graph_count", "molsde_radius_graph_fill",
     "molsde_csr_by_target_count", "molsde_csr_by_target_fill",
     "molsde_linear",
-    "molsde_edge2d_emb_eval", "molsde_sde2d3d_score", "molsde_sde2d3d_scratch_floats",
+    "molsde_edge2d_emb_eval", "molsde_sde2d3d_score", "molsde_sde2d3d_scratch_floats", "molsde_tile_floats",
     "molsde_sde2d3d_pc_sample",
 ]
 
@@ -87,6 +89,7 @@ def lib() -> ctypes.CDLL:
                                        c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     L.molsde_sde2d3d_scratch_floats.argtypes = [POINTER(Plan), c_int32, POINTER(c_int32)]
     L.molsde_sde2d3d_scratch_floats.restype = c_int64
+    L.molsde_tile_floats.restype = c_int64
     L.molsde_sde2d3d_pc_sample.argtypes = [POINTER(Plan), POINTER(Params), c_void_p, c_void_p, c_void_p, c_void_p,
                                            POINTER(PCConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_int64, c_void_p, c_void_p, c_void_p]

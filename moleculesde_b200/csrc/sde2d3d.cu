@@ -5,18 +5,21 @@
 // examples/pretrain_MoleculeSDE_inference_2D_to_3D_VE_VP.py:92-212.
 //
 // Design (B200-first):
-//   * one persistent CTA (256 threads, 1 CTA/SM, ~214 KB smem) owns one "chunk" = a set of whole
+//   * one persistent CTA (512 threads, 1 CTA/SM, ~223 KB smem) owns one "chunk" = a set of whole
 //     molecules with <= 224 atoms; node state (hidden features, q/k/v, positions, score) lives in
 //     shared memory for the WHOLE score evaluation -- and, in the PC kernel, for all 1000 reverse
 //     steps -- so HBM sees only the initial/final positions;
 //   * edges are processed in CSR-by-target order in tiles of <= 128 edges aligned to target nodes,
 //     so the segment softmax / mean aggregation of a tile is self-contained and runs in a fixed,
 //     atomic-free, ascending-source order (deterministic, same order as the reference scatter);
-//   * every per-edge MLP is a register-tiled fp32 FFMA GEMM over the tile (A operand k-major in
-//     smem, weights streamed from the packed parameter blob into smem once per phase);
-//   * the per-edge attribute (32 floats) is the only per-edge state that survives between phases;
-//     it goes to an L2-resident per-CTA scratch in the tile layout [tile][32][128], so re-loading
-//     it is a straight 16 KB cp.async copy.
+//   * every per-edge / per-node MLP is a tile GEMM on the tensor cores: mma.sync m16n8k8 TF32 with
+//     the 3xTF32 error-compensated split (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate), which
+//     keeps fp32-grade accuracy (north_star: 1e-4) at ~3x the math rate the FFMA register tile reaches
+//     from shared memory (profiles/r1_ubench_mma_rate.txt).  A operands are k-major in smem with a
+//     padded leading dimension (== 8 mod 32) so fragment loads are bank-conflict free;
+//   * the per-edge attribute (32 floats) is the only per-edge state that survives between phases; it
+//     goes to an L2-resident per-CTA scratch in the smem tile layout [32][136], so re-loading it is
+//     a straight 17 KB cp.async copy.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -25,22 +28,27 @@
 namespace molsde {
 
 constexpr int TE = MOLSDE_TILE_EDGES;         // 128 edges per tile
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 512;
+constexpr int NWARPS = NTHREADS / 32;
 constexpr int MAXN = MOLSDE_CHUNK_MAX_NODES;  // 224 atoms per chunk
 constexpr int MAXT = 64;                      // tiles per chunk
+constexpr int LDA = MOLSDE_TILE_LD;           // 136: leading dim of a k-major edge tile
+constexpr int LDX = 232;                      // leading dim of the k-major node matrix (>= MAXN, == 8 mod 32)
+constexpr int TILE_FLOATS = 32 * LDA;         // one [32][136] per-edge attribute tile
+constexpr int LD32 = MOLSDE_LD32, LD96 = MOLSDE_LD96, LD128 = MOLSDE_LD128;
 constexpr float EPS = 1e-6f;                  // SDE_model_2D_to_3D.py:10
 constexpr float LN_EPS = 1e-5f;
 
 // ---- shared memory carve-up (float offsets) ----
-constexpr int S_XT = 0;                      // [32][MAXN]  node hidden, k-major
-constexpr int S_Q = S_XT + 32 * MAXN;        // [MAXN][32]  query  (aggregate written in place)
+constexpr int S_XT = 0;                      // [32][LDX]   node hidden, k-major
+constexpr int S_Q = S_XT + 32 * LDX;         // [MAXN][32]  query  (aggregate written in place)
 constexpr int S_K = S_Q + 32 * MAXN;         // [MAXN][32]
 constexpr int S_V = S_K + 32 * MAXN;         // [MAXN][32]
-constexpr int S_WG = S_V + 32 * MAXN;        // [7488]      weights of the current GAT layer
-constexpr int S_A = S_WG + MOLSDE_P_GAT_SZ;  // [64][TE]    A operand (k-major); E0 spills 4 rows into S_M
-constexpr int S_M = S_A + 64 * TE;           // [TE][32]    weighted messages / basis mix
-constexpr int S_L = S_M + TE * 32;           // [TE][8]     logits / geometry scalars / dyn coeffs
-constexpr int S_MS = S_L + TE * 8;           // [2][TE][8]  softmax max / sum
+constexpr int S_WG = S_V + 32 * MAXN;        // [P_GAT_SZ]  weights of the current GAT layer
+constexpr int S_A = S_WG + MOLSDE_P_GAT_SZ;  // [64][LDA]   A operand (k-major); node phases stage [32][LDX] here
+constexpr int S_M = S_A + 64 * LDA;          // [TILE_FLOATS] weighted messages [TE][32] / e2d + edge_attr tile
+constexpr int S_L = S_M + TILE_FLOATS;       // [TE][8]     logits / geometry scalars / partial dyn coeffs
+constexpr int S_MS = S_L + TE * 8;           // [2][TE][8]  softmax max, sum / basis mix
 constexpr int S_POS = S_MS + 2 * TE * 8;     // [MAXN*3]
 constexpr int S_GRAD = S_POS + MAXN * 3;     // [MAXN*3]  network output ("gradient")
 constexpr int S_SCORE = S_GRAD + MAXN * 3;   // [MAXN*3]
@@ -48,7 +56,7 @@ constexpr int S_NOISE = S_SCORE + MAXN * 3;  // [MAXN*3]
 constexpr int S_RED = S_NOISE + MAXN * 3;    // [64]
 constexpr int S_FLOATS = S_RED + 64;
 // int region (after the floats)
-constexpr int SI_ROWL = 0;                 // [MAXN+1] edge offsets local to the chunk
+constexpr int SI_ROWL = 0;                   // [MAXN+1] edge offsets local to the chunk
 constexpr int SI_TTGT = SI_ROWL + MAXN + 1;  // [MAXT+1] tile target boundaries local to the chunk
 constexpr int SI_ESRC = SI_TTGT + MAXT + 1;  // [TE]
 constexpr int SI_ETGT = SI_ESRC + TE;        // [TE]
@@ -58,6 +66,9 @@ constexpr size_t SMEM_BYTES = sizeof(float) * S_FLOATS + sizeof(int) * S_INTS;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 static_assert(MOLSDE_P_E0_END <= 3 * 32 * MAXN, "E0 weights are staged in the q/k/v region");
 static_assert(MOLSDE_P_BASIS_SZ <= 3 * 32 * MAXN, "basis weights are staged in the q/k/v region");
+static_assert(32 * LDX <= 64 * LDA, "node staging aliases the A region");
+static_assert(LDX >= MAXN && LDX % 32 == 8 && LDA % 32 == 8, "padded leading dimensions");
+static_assert(S_A % 4 == 0 && S_M % 4 == 0 && S_WG % 4 == 0 && S_Q % 4 == 0, "16B alignment for cp.async");
 
 struct Chunk {
     float* sm;
@@ -70,45 +81,72 @@ struct Chunk {
 };
 
 // ---------------------------------------------------------------------------------------
-// register-tiled GEMM over one tile:  acc[TM][TN] += A[k][row] * W[k][col]
-//   rows  = te*TM .. te*TM+TM-1                      (edges or nodes)
-//   cols  = to*4..to*4+3 (TN==4)   or additionally NOUT/2 + to*4..+3 (TN==8)
+// fast, accuracy-checked elementwise helpers (absolute / relative error ~1e-6, far below the 1e-4 bar)
 // ---------------------------------------------------------------------------------------
-template <int TM, int TN, int NOUT, int LDA>
-__device__ __forceinline__ void gemm_acc(const float* __restrict__ As, const float* __restrict__ Ws, int K, int te,
-                                         int to, float (&acc)[TM][TN]) {
-    static_assert(TM % 4 == 0 && (TN == 4 || TN == 8), "tile shape");
-    const float* ap = As + te * TM;
-    const float* wp = Ws + to * 4;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-        float a[TM], b[TN];
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// sin/cos of an fp32 argument of magnitude up to ~1e5: 2-term Cody-Waite reduction by 2*pi (exact
+// products through FMA), then the SFU approximations on |r| <= pi (abs error < 1e-6).
+__device__ __forceinline__ void sincos_reduced(float x, float& s, float& c) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, x);
+    r = fmaf(-k, -1.7484555314695172e-7f, r);
+    s = __sinf(r);
+    c = __cosf(r);
+}
+
+// ---------------------------------------------------------------------------------------
+// tensor-core tile GEMM: c[nb] (16 rows x 8 cols per n-block) += A[16 x K] . W[K x 8*NB]
+//   As: k-major, As[k*LDA_ + row], pointing at the warp's first row;  Ws: Ws[k*LDW_ + col],
+//   pointing at the warp's first column.  3xTF32 split, small terms first.
+//   fragment layout (PTX ISA, mma.m16n8k8 .tf32): g = lane/4, t = lane%4
+//     a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  b0 (k=t, n=g) b1 (k=t+4, n=g)
+//     c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int NB, int LDA_, int LDW_>
+__device__ __forceinline__ void mma_gemm(const float* __restrict__ As, const float* __restrict__ Ws, int K, int lane,
+                                         float (&c)[NB][4]) {
+    const int g = lane >> 2, t = lane & 3;
+    const float* ap = As + t * LDA_ + g;
+    const float* wp = Ws + t * LDW_ + g;
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        const float av[4] = {ap[k0 * LDA_], ap[k0 * LDA_ + 8], ap[(k0 + 4) * LDA_], ap[(k0 + 4) * LDA_ + 8]};
+        uint32_t ah[4], al[4];
 #pragma unroll
-        for (int i = 0; i < TM / 4; ++i) {
-            const float4 v = *reinterpret_cast<const float4*>(ap + k * LDA + 4 * i);
-            a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
-        }
-        {
-            const float4 v = *reinterpret_cast<const float4*>(wp + k * NOUT);
-            b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
-        }
-        if (TN == 8) {
-            const float4 v = *reinterpret_cast<const float4*>(wp + k * NOUT + NOUT / 2);
-            b[4] = v.x; b[5] = v.y; b[6] = v.z; b[7] = v.w;
+        for (int i = 0; i < 4; ++i) {
+            ah[i] = tf32_hi(av[i]);
+            al[i] = __float_as_uint(av[i] - __uint_as_float(ah[i]));
         }
 #pragma unroll
-        for (int i = 0; i < TM; ++i)
-#pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int nb = 0; nb < NB; ++nb) {
+            const float b0 = wp[k0 * LDW_ + nb * 8], b1 = wp[(k0 + 4) * LDW_ + nb * 8];
+            const uint32_t bh0 = tf32_hi(b0), bh1 = tf32_hi(b1);
+            const uint32_t bl0 = __float_as_uint(b0 - __uint_as_float(bh0));
+            const uint32_t bl1 = __float_as_uint(b1 - __uint_as_float(bh1));
+            mma_tf32(c[nb], al, bh0, bh1);
+            mma_tf32(c[nb], ah, bl0, bl1);
+            mma_tf32(c[nb], ah, bh0, bh1);
+        }
     }
 }
 
-template <int TM, int TN>
-__device__ __forceinline__ void zero_acc(float (&acc)[TM][TN]) {
+template <int NB>
+__device__ __forceinline__ void zero_frag(float (&c)[NB][4]) {
 #pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+    for (int i = 0; i < NB; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.0f;
 }
 
 // cooperative global->shared copy of `nfloat` floats (multiple of 4, 16B aligned both sides)
@@ -167,45 +205,50 @@ __device__ __forceinline__ int build_tile_edges(const Chunk& c, const int32_t* _
     return ne;
 }
 
-// sin/cos Fourier features of one scalar per edge into A rows [row0, row0+64):
+// sin/cos Fourier features of one scalar per edge into A rows [0, 64):
 // GaussianFourierProjection.forward, SDE_model_2D_to_3D.py:64-66  (x * W * 2 * pi, fp32, in that order)
-__device__ __forceinline__ void fill_fourier(float* A, int row0, const float* __restrict__ xs, const float* __restrict__ W) {
+__device__ __forceinline__ void fill_fourier(float* A, const float* __restrict__ xs, const float* __restrict__ W) {
     const int edge = threadIdx.x & (TE - 1);
-    const int w0 = threadIdx.x >> 7;  // 0 or 1
+    const int w0 = threadIdx.x >> 7;  // 0..3
     const float x = xs[edge];
-#pragma unroll 4
-    for (int it = 0; it < 16; ++it) {
-        const int w = w0 + 2 * it;
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+        const int w = w0 + 4 * it;
         const float arg = __fmul_rn(__fmul_rn(__fmul_rn(x, W[w]), 2.0f), 3.14159274101257324f);
         float s, co;
-        sincosf(arg, &s, &co);
-        A[(row0 + w) * TE + edge] = s;
-        A[(row0 + 32 + w) * TE + edge] = co;
+        sincos_reduced(arg, s, co);
+        A[w * LDA + edge] = s;
+        A[(32 + w) * LDA + edge] = co;
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // Phase E0: per-edge attribute  edge_attr = input_mlp(gfp(d)) * e2d + project([sin,cos,emb_i,emb_j])
-// SDE_model_2D_to_3D.py:402-432
+// SDE_model_2D_to_3D.py:402-432.  coff_mlp (a bare Linear) is folded into project.layers.0 on the
+// host (MOLSDE_P_H_W), so the hidden layer accumulates directly over the four Fourier blocks.
 // ---------------------------------------------------------------------------------------
-__device__ void phase_edge_features(const Chunk& c, const float* __restrict__ blob, const int32_t* __restrict__ src_g,
-                                    const float* __restrict__ e2d_tiles, float* __restrict__ scratch) {
+__device__ __noinline__ void phase_edge_features(const Chunk c, const float* __restrict__ blob,
+                                                 const int32_t* __restrict__ src_g, const float* __restrict__ e2d_tiles,
+                                                 float* __restrict__ scratch) {
     float* sm = c.sm;
     float* W = sm + S_Q;  // E0 weights staged over the (currently dead) q/k/v region
     float* A = sm + S_A;
+    float* EA = sm + S_M;   // e2d tile in, edge_attr tile out  [32][LDA]
     float* geo = sm + S_L;  // [7][TE]: d, ci0, ci2, cj0, cj2, psin, pcos
     const float* pos = sm + S_POS;
-    const int tid = threadIdx.x;
-    const int to = tid & 7, te = tid >> 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = (warp & 7) * 16, n0 = (warp >> 3) * 16;
+    const int g = lane >> 2, t4 = lane & 3;
     stage_async(W, blob, MOLSDE_P_E0_END);
     cp_async_wait<0>();
     __syncthreads();
     for (int t = 0; t < c.ntiles; ++t) {
         int ta, tb, ea;
+        stage_async(EA, e2d_tiles + static_cast<size_t>(c.tile0 + t) * TILE_FLOATS, TILE_FLOATS);
         const int ne = build_tile_edges(c, src_g, t, ta, tb, ea);
         __syncthreads();
         if (tid < TE) {
-            float g[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float gq[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (tid < ne) {
                 const float* pr = pos + 3 * (c.si + SI_ESRC)[tid];  // row = source j
                 const float* pc = pos + 3 * (c.si + SI_ETGT)[tid];  // col = target i
@@ -221,80 +264,67 @@ __device__ void phase_edge_features(const Chunk& c, const float* __restrict__ bl
                 const float nj = sqrtf(dot3_rn(cj0, cj1, cj2, cj0, cj1, cj2));
                 const float pcos = __fdiv_rn(__fdiv_rn(dot3_rn(ci0, ci1, ci2, cj0, cj1, cj2), __fadd_rn(ni, EPS)),
                                              __fadd_rn(nj, EPS));
-                const float psin = sqrtf(__fsub_rn(1.0f, __fmul_rn(pcos, pcos)));  // :425 (NaN if |cos|>1, as the reference)
-                g[0] = f.dist; g[1] = ci0; g[2] = ci2; g[3] = cj0; g[4] = cj2; g[5] = psin; g[6] = pcos;
+                // :425  sqrt(1 - cos^2).  For (anti)parallel r_i, r_j rounding can make the argument a tiny negative
+                // number and the reference then returns NaN for the whole batch; the limit value 0 is used instead
+                // (only inputs on which the reference output is NaN are affected).
+                const float psin = sqrtf(fmaxf(__fsub_rn(1.0f, __fmul_rn(pcos, pcos)), 0.0f));
+                gq[0] = f.dist; gq[1] = ci0; gq[2] = ci2; gq[3] = cj0; gq[4] = cj2; gq[5] = psin; gq[6] = pcos;
             }
 #pragma unroll
-            for (int q = 0; q < 7; ++q) geo[q * TE + tid] = g[q];
+            for (int q = 0; q < 7; ++q) geo[q * TE + tid] = gq[q];
         }
         __syncthreads();
         // ---- edge_attr_3D_invariant = input_mlp(gfp_dist(d))  (:409-410) ----
-        float inv[4][4];
-        zero_acc(inv);
-        fill_fourier(A, 0, geo, W + MOLSDE_P_GFP_DIST_W);
+        float inv[2][4], h[2][4], fr[2][4];
+        zero_frag(inv);
+        fill_fourier(A, geo, W + MOLSDE_P_GFP_DIST_W);
         __syncthreads();
-        gemm_acc<4, 4, 32, TE>(A, W + MOLSDE_P_IN_WT, 64, te, to, inv);
+        mma_gemm<2, LDA, LD32>(A + m0, W + MOLSDE_P_IN_W + n0, 64, lane, inv);
         __syncthreads();
-        // ---- embed_i / embed_j = coff_mlp([gfp(c0), gfp(c2)])  (:297-304, 427-428) ----
-        float emb[2][4][4];
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            zero_acc(emb[side]);
-#pragma unroll
-            for (int comp = 0; comp < 2; ++comp) {
-                fill_fourier(A, 0, geo + (1 + 2 * side + comp) * TE, W + MOLSDE_P_GFP_COFF_W);
-                __syncthreads();
-                gemm_acc<4, 4, 32, TE>(A, W + MOLSDE_P_COFF_WT + comp * 64 * 32, 64, te, to, emb[side]);
-                __syncthreads();
-            }
-        }
-        // ---- project: Linear(66,32) silu Linear(32,32) on [psin, pcos, emb_i, emb_j]  (:429-430) ----
-        if (tid < TE) {
-            A[0 * TE + tid] = geo[5 * TE + tid];
-            A[1 * TE + tid] = geo[6 * TE + tid];
-            A[66 * TE + tid] = 0.0f;
-            A[67 * TE + tid] = 0.0f;
+        // ---- hidden of `project` accumulated over gfp(ci0), gfp(ci2), gfp(cj0), gfp(cj2)  (:427-430) ----
+        zero_frag(h);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            fill_fourier(A, geo + (1 + q) * TE, W + MOLSDE_P_GFP_COFF_W);
+            __syncthreads();
+            mma_gemm<2, LDA, LD32>(A + m0, W + MOLSDE_P_H_W + q * 64 * LD32 + n0, 64, lane, h);
+            __syncthreads();
         }
 #pragma unroll
-        for (int side = 0; side < 2; ++side)
+        for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float bj = W[MOLSDE_P_COFF_B + to * 4 + j];
-                float4 v = make_float4(emb[side][0][j] + bj, emb[side][1][j] + bj, emb[side][2][j] + bj,
-                                       emb[side][3][j] + bj);
-                *reinterpret_cast<float4*>(&A[(2 + 32 * side + to * 4 + j) * TE + te * 4]) = v;
+            for (int j = 0; j < 2; ++j) {
+                const int col = n0 + nb * 8 + 2 * t4 + j;
+                const float bh = W[MOLSDE_P_H_B + col], ws = W[MOLSDE_P_H_WSIN + col], wc = W[MOLSDE_P_H_WCOS + col];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int row = m0 + g + 8 * rr;
+                    const float v = h[nb][2 * rr + j] + bh + geo[5 * TE + row] * ws + geo[6 * TE + row] * wc;
+                    A[col * LDA + row] = silu_fast(v);
+                }
             }
         __syncthreads();
-        float h[4][4];
-        zero_acc(h);
-        gemm_acc<4, 4, 32, TE>(A, W + MOLSDE_P_PROJ0_WT, 68, te, to, h);
+        zero_frag(fr);
+        mma_gemm<2, LDA, LD32>(A + m0, W + MOLSDE_P_P1_W + n0, 32, lane, fr);
+        cp_async_wait<0>();
         __syncthreads();
+        // ---- edge_attr = inv3d * e2d + frame  (:432), in place over the e2d tile ----
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float bj = W[MOLSDE_P_PROJ0_B + to * 4 + j];
-            float4 v = make_float4(silu_f(h[0][j] + bj), silu_f(h[1][j] + bj), silu_f(h[2][j] + bj),
-                                   silu_f(h[3][j] + bj));
-            *reinterpret_cast<float4*>(&A[(to * 4 + j) * TE + te * 4]) = v;
-        }
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int col = n0 + nb * 8 + 2 * t4 + j;
+                const float bi = W[MOLSDE_P_IN_B + col], bf = W[MOLSDE_P_P1_B + col];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int idx = col * LDA + m0 + g + 8 * rr;
+                    EA[idx] = fmaf(inv[nb][2 * rr + j] + bi, EA[idx], fr[nb][2 * rr + j] + bf);
+                }
+            }
         __syncthreads();
-        float fr[4][4];
-        zero_acc(fr);
-        gemm_acc<4, 4, 32, TE>(A, W + MOLSDE_P_PROJ1_WT, 32, te, to, fr);
-        // ---- edge_attr = inv3d * e2d + frame  (:432) -> scratch tile ----
-        const float* e2d_t = e2d_tiles + static_cast<size_t>(c.tile0 + t) * (32 * TE);
-        float* sc_t = scratch + static_cast<size_t>(t) * (32 * TE);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = to * 4 + j;
-            const float bi = W[MOLSDE_P_IN_B + col], bf = W[MOLSDE_P_PROJ1_B + col];
-            const float4 e2 = __ldg(reinterpret_cast<const float4*>(e2d_t + col * TE + te * 4));
-            float4 o;
-            o.x = fmaf(inv[0][j] + bi, e2.x, fr[0][j] + bf);
-            o.y = fmaf(inv[1][j] + bi, e2.y, fr[1][j] + bf);
-            o.z = fmaf(inv[2][j] + bi, e2.z, fr[2][j] + bf);
-            o.w = fmaf(inv[3][j] + bi, e2.w, fr[3][j] + bf);
-            *reinterpret_cast<float4*>(sc_t + col * TE + te * 4) = o;
-        }
+        float* sc_t = scratch + static_cast<size_t>(t) * TILE_FLOATS;
+        for (int i = tid * 4; i < TILE_FLOATS; i += NTHREADS * 4)
+            *reinterpret_cast<float4*>(sc_t + i) = *reinterpret_cast<const float4*>(EA + i);
         __syncthreads();
     }
 }
@@ -302,32 +332,34 @@ __device__ void phase_edge_features(const Chunk& c, const float* __restrict__ bl
 // ---------------------------------------------------------------------------------------
 // GAT layer pieces  (equivariant_scorenetwork.py:34-40, TransformerConv heads=8 C=4)
 // ---------------------------------------------------------------------------------------
-__device__ void node_qkv(const Chunk& c) {
+// q|k|v = Linear(x): each warp owns 16 nodes and all 96 output columns
+__device__ __noinline__ void node_qkv(const Chunk c) {
     float* sm = c.sm;
     const float* Wg = sm + S_WG;
-    const int tid = threadIdx.x, to = tid & 7, te = tid >> 3;
-    for (int nt = 0; nt * TE < c.n; ++nt) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m0 = warp * 16, g = lane >> 2, t4 = lane & 3;
+    if (m0 >= c.n) return;
+    float acc[12][4];
+    zero_frag(acc);
+    mma_gemm<12, LDX, LD96>(sm + S_XT + m0, Wg + MOLSDE_G_WQKV, 32, lane, acc);
 #pragma unroll
-        for (int which = 0; which < 3; ++which) {
-            float acc[4][4];
-            zero_acc(acc);
-            gemm_acc<4, 4, 32, MAXN>(sm + S_XT + nt * TE, Wg + MOLSDE_G_WQ_T + which * 1024, 32, te, to, acc);
-            const float4 b = *reinterpret_cast<const float4*>(Wg + MOLSDE_G_BQ + which * 32 + to * 4);
-            float* dst = sm + S_Q + which * 32 * MAXN;
+    for (int nb = 0; nb < 12; ++nb) {
+        const int col = nb * 8 + 2 * t4;  // 0..95: q | k | v
+        const float b0 = Wg[MOLSDE_G_BQKV + col], b1 = Wg[MOLSDE_G_BQKV + col + 1];
+        float* dst = sm + S_Q + (col >> 5) * (32 * MAXN) + (col & 31);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int node = nt * TE + te * 4 + i;
-                if (node < c.n)
-                    *reinterpret_cast<float4*>(dst + node * 32 + to * 4) =
-                        make_float4(acc[i][0] + b.x, acc[i][1] + b.y, acc[i][2] + b.z, acc[i][3] + b.w);
-            }
+        for (int rr = 0; rr < 2; ++rr) {
+            const int node = m0 + g + 8 * rr;
+            if (node < c.n)
+                *reinterpret_cast<float2*>(dst + node * 32) = make_float2(acc[nb][2 * rr] + b0, acc[nb][2 * rr + 1] + b1);
         }
     }
 }
 
 // attention over the incoming edges of every target: logits, segment softmax (+1e-16), weighted
 // messages, deterministic ascending-source sum; the aggregate overwrites q[target].
-__device__ void gat_edge_phase(const Chunk& c, const int32_t* __restrict__ src_g, const float* __restrict__ scratch) {
+__device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __restrict__ src_g,
+                                            const float* __restrict__ scratch) {
     float* sm = c.sm;
     float* A = sm + S_A;
     float* Mm = sm + S_M;
@@ -341,31 +373,36 @@ __device__ void gat_edge_phase(const Chunk& c, const int32_t* __restrict__ src_g
     const int* rowl = c.si + SI_ROWL;
     const int* esrc = c.si + SI_ESRC;
     const int* etgt = c.si + SI_ETGT;
-    const int tid = threadIdx.x, to = tid & 7, te = tid >> 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = (warp & 7) * 16, n0 = (warp >> 3) * 16;
+    const int g = lane >> 2, t4 = lane & 3;
     for (int t = 0; t < c.ntiles; ++t) {
         int ta, tb, ea;
-        stage_async(A, scratch + static_cast<size_t>(t) * (32 * TE), 32 * TE);
+        stage_async(A, scratch + static_cast<size_t>(t) * TILE_FLOATS, TILE_FLOATS);
         const int ne = build_tile_edges(c, src_g, t, ta, tb, ea);
         cp_async_wait<0>();
         __syncthreads();
-        // e = lin_edge(edge_attr): thread holds head `to` of 4 consecutive edges
-        float e[4][4];
-        zero_acc(e);
-        gemm_acc<4, 4, 32, TE>(A, Wg + MOLSDE_G_WE_T, 32, te, to, e);
+        // e = lin_edge(edge_attr); this thread: rows m0+g, m0+g+8; columns n0 + nb*8 + 2*t4 + {0,1}
+        float e[2][4];
+        zero_frag(e);
+        mma_gemm<2, LDA, LD32>(A + m0, Wg + MOLSDE_G_WE + n0, 32, lane, e);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int s = te * 4 + i;
-            if (s < ne) {
-                const float4 k4 = *reinterpret_cast<const float4*>(Kk + esrc[s] * 32 + to * 4);
-                const float4 q4 = *reinterpret_cast<const float4*>(Q + etgt[s] * 32 + to * 4);
-                const float4 v4 = *reinterpret_cast<const float4*>(V + esrc[s] * 32 + to * 4);
-                // alpha = (q_i . (k_j + e)) / sqrt(C)
-                float lg = q4.x * (k4.x + e[i][0]);
-                lg = fmaf(q4.y, k4.y + e[i][1], lg);
-                lg = fmaf(q4.z, k4.z + e[i][2], lg);
-                lg = fmaf(q4.w, k4.w + e[i][3], lg);
-                L[s * 8 + to] = lg * 0.5f;
-                e[i][0] += v4.x; e[i][1] += v4.y; e[i][2] += v4.z; e[i][3] += v4.w;  // v_j + e
+        for (int rr = 0; rr < 2; ++rr) {
+            const int s = m0 + g + 8 * rr;
+            const bool live = s < ne;
+            const int sj = esrc[s], ti = etgt[s];
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+                const int col = n0 + nb * 8 + 2 * t4;
+                const float2 k2 = *reinterpret_cast<const float2*>(Kk + sj * 32 + col);
+                const float2 q2 = *reinterpret_cast<const float2*>(Q + ti * 32 + col);
+                const float2 v2 = *reinterpret_cast<const float2*>(V + sj * 32 + col);
+                // alpha = (q_i . (k_j + e)) / sqrt(C): a head (4 columns) is split over the lane pair (t4, t4^1)
+                float part = fmaf(q2.y, k2.y + e[nb][2 * rr + 1], q2.x * (k2.x + e[nb][2 * rr]));
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                if (live && (t4 & 1) == 0) L[s * 8 + (col >> 2)] = part * 0.5f;
+                e[nb][2 * rr] += v2.x;      // v_j + e
+                e[nb][2 * rr + 1] += v2.y;
             }
         }
         __syncthreads();
@@ -377,19 +414,22 @@ __device__ void gat_edge_phase(const Chunk& c, const int32_t* __restrict__ src_g
             float m = -CUDART_INF_F;
             for (int s = s0; s < s1; ++s) m = fmaxf(m, L[s * 8 + hd]);
             float z = 0.0f;
-            for (int s = s0; s < s1; ++s) z += expf(L[s * 8 + hd] - m);
+            for (int s = s0; s < s1; ++s) z += __expf(L[s * 8 + hd] - m);
             smax[p] = m;
             ssum[p] = z;
         }
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int s = te * 4 + i;
+        for (int rr = 0; rr < 2; ++rr) {
+            const int s = m0 + g + 8 * rr;
             if (s < ne) {
-                const int p = (etgt[s] - ta) * 8 + to;
-                const float a = __fdiv_rn(expf(L[s * 8 + to] - smax[p]), ssum[p] + 1e-16f);
-                *reinterpret_cast<float4*>(Mm + s * 32 + to * 4) =
-                    make_float4(e[i][0] * a, e[i][1] * a, e[i][2] * a, e[i][3] * a);
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) {
+                    const int col = n0 + nb * 8 + 2 * t4;
+                    const int p = (etgt[s] - ta) * 8 + (col >> 2);
+                    const float a = __fdividef(__expf(L[s * 8 + (col >> 2)] - smax[p]), ssum[p] + 1e-16f);
+                    *reinterpret_cast<float2*>(Mm + s * 32 + col) = make_float2(e[nb][2 * rr] * a, e[nb][2 * rr + 1] * a);
+                }
             }
         }
         __syncthreads();
@@ -404,173 +444,187 @@ __device__ void gat_edge_phase(const Chunk& c, const int32_t* __restrict__ src_g
     }
 }
 
-// LayerNorm over the 32 columns of a row held by the 8 `to` lanes (4 columns each)
-__device__ __forceinline__ void layer_norm_rows(float (&v)[4][4], const float* __restrict__ w, const float* __restrict__ b,
-                                                int to) {
-    const float4 w4 = *reinterpret_cast<const float4*>(w + to * 4);
-    const float4 b4 = *reinterpret_cast<const float4*>(b + to * 4);
+// LayerNorm over the 32 columns of two rows held by a lane quad (8 columns per lane and row)
+__device__ __forceinline__ void layer_norm_quad(float (&v)[4][4], const float* __restrict__ w, const float* __restrict__ b,
+                                                int t4) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float s = (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    for (int rr = 0; rr < 2; ++rr) {
+        float s = 0.0f;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) s += v[nb][2 * rr] + v[nb][2 * rr + 1];
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
         const float mean = s * (1.0f / 32.0f);
-        const float d0 = v[i][0] - mean, d1 = v[i][1] - mean, d2 = v[i][2] - mean, d3 = v[i][3] - mean;
-        float q = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        float q = 0.0f;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            const float d0 = v[nb][2 * rr] - mean, d1 = v[nb][2 * rr + 1] - mean;
+            q += d0 * d0 + d1 * d1;
+        }
         q += __shfl_xor_sync(0xffffffffu, q, 1);
         q += __shfl_xor_sync(0xffffffffu, q, 2);
-        q += __shfl_xor_sync(0xffffffffu, q, 4);
         const float rstd = 1.0f / sqrtf(q * (1.0f / 32.0f) + LN_EPS);
-        v[i][0] = d0 * rstd * w4.x + b4.x;
-        v[i][1] = d1 * rstd * w4.y + b4.y;
-        v[i][2] = d2 * rstd * w4.z + b4.z;
-        v[i][3] = d3 * rstd * w4.w + b4.w;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int col = nb * 8 + 2 * t4 + j;
+                v[nb][2 * rr + j] = (v[nb][2 * rr + j] - mean) * rstd * w[col] + b[col];
+            }
     }
 }
 
 // x <- x + LN1(agg + skip(x));  x <- x + LN2(FFN(x));  optional SiLU  (equivariant_scorenetwork.py:35-38,140-141)
-__device__ void node_update(const Chunk& c, bool silu_after) {
+// Each warp owns 16 nodes end to end (only __syncwarp between its GEMMs).
+__device__ __noinline__ void node_update(const Chunk c, bool silu_after) {
     float* sm = c.sm;
     float* XT = sm + S_XT;
-    float* A = sm + S_A;
+    float* NT = sm + S_A;  // [32][LDX] staging of the FFN input / hidden, k-major
     const float* Q = sm + S_Q;
     const float* Wg = sm + S_WG;
-    const int tid = threadIdx.x, to = tid & 7, te = tid >> 3;
-    for (int nt = 0; nt * TE < c.n; ++nt) {
-        float acc[4][4], x1[4][4];
-        zero_acc(acc);
-        gemm_acc<4, 4, 32, MAXN>(XT + nt * TE, Wg + MOLSDE_G_WS_T, 32, te, to, acc);
-        const float4 bs = *reinterpret_cast<const float4*>(Wg + MOLSDE_G_BS + to * 4);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m0 = warp * 16, g = lane >> 2, t4 = lane & 3;
+    if (m0 >= c.n) return;
+    float acc[4][4], x1[4][4];
+    zero_frag(acc);
+    mma_gemm<4, LDX, LD32>(XT + m0, Wg + MOLSDE_G_WS, 32, lane, acc);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int node = nt * TE + te * 4 + i;
-            float4 ag = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (node < c.n) ag = *reinterpret_cast<const float4*>(Q + node * 32 + to * 4);
-            acc[i][0] += bs.x + ag.x; acc[i][1] += bs.y + ag.y; acc[i][2] += bs.z + ag.z; acc[i][3] += bs.w + ag.w;
+    for (int nb = 0; nb < 4; ++nb) {
+        const int col = nb * 8 + 2 * t4;
+        const float b0 = Wg[MOLSDE_G_BS + col], b1 = Wg[MOLSDE_G_BS + col + 1];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int node = m0 + g + 8 * rr;
+            float2 ag = make_float2(0.f, 0.f);
+            if (node < c.n) ag = *reinterpret_cast<const float2*>(Q + node * 32 + col);
+            acc[nb][2 * rr] += b0 + ag.x;
+            acc[nb][2 * rr + 1] += b1 + ag.y;
         }
-        layer_norm_rows(acc, Wg + MOLSDE_G_LN1_W, Wg + MOLSDE_G_LN1_B, to);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int node = nt * TE + te * 4 + i;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float xo = (node < c.n) ? XT[(to * 4 + j) * MAXN + node] : 0.0f;
-                x1[i][j] = xo + acc[i][j];
-            }
-        }
-        // FFN: Linear silu Linear on x1 (A operand staged k-major)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(&A[(to * 4 + j) * TE + te * 4]) = make_float4(x1[0][j], x1[1][j], x1[2][j], x1[3][j]);
-        __syncthreads();
-        zero_acc(acc);
-        gemm_acc<4, 4, 32, TE>(A, Wg + MOLSDE_G_F0_WT, 32, te, to, acc);
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float bj = Wg[MOLSDE_G_F0_B + to * 4 + j];
-            *reinterpret_cast<float4*>(&A[(to * 4 + j) * TE + te * 4]) =
-                make_float4(silu_f(acc[0][j] + bj), silu_f(acc[1][j] + bj), silu_f(acc[2][j] + bj), silu_f(acc[3][j] + bj));
-        }
-        __syncthreads();
-        zero_acc(acc);
-        gemm_acc<4, 4, 32, TE>(A, Wg + MOLSDE_G_F3_WT, 32, te, to, acc);
-        const float4 b3 = *reinterpret_cast<const float4*>(Wg + MOLSDE_G_F3_B + to * 4);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { acc[i][0] += b3.x; acc[i][1] += b3.y; acc[i][2] += b3.z; acc[i][3] += b3.w; }
-        layer_norm_rows(acc, Wg + MOLSDE_G_LN2_W, Wg + MOLSDE_G_LN2_B, to);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int node = nt * TE + te * 4 + i;
-            if (node < c.n) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float x2 = x1[i][j] + acc[i][j];
-                    if (silu_after) x2 = silu_f(x2);
-                    XT[(to * 4 + j) * MAXN + node] = x2;
-                }
-            }
-        }
-        __syncthreads();
     }
+    layer_norm_quad(acc, Wg + MOLSDE_G_LN1_W, Wg + MOLSDE_G_LN1_B, t4);
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col = nb * 8 + 2 * t4 + j;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int node = m0 + g + 8 * rr;
+                const float xo = (node < c.n) ? XT[col * LDX + node] : 0.0f;
+                x1[nb][2 * rr + j] = xo + acc[nb][2 * rr + j];
+                NT[col * LDX + node] = x1[nb][2 * rr + j];
+            }
+        }
+    __syncwarp();
+    zero_frag(acc);
+    mma_gemm<4, LDX, LD32>(NT + m0, Wg + MOLSDE_G_F0, 32, lane, acc);
+    __syncwarp();
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col = nb * 8 + 2 * t4 + j;
+            const float bj = Wg[MOLSDE_G_F0_B + col];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) NT[col * LDX + m0 + g + 8 * rr] = silu_fast(acc[nb][2 * rr + j] + bj);
+        }
+    __syncwarp();
+    zero_frag(acc);
+    mma_gemm<4, LDX, LD32>(NT + m0, Wg + MOLSDE_G_F3, 32, lane, acc);
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float bj = Wg[MOLSDE_G_F3_B + nb * 8 + 2 * t4 + j];
+            acc[nb][j] += bj;
+            acc[nb][2 + j] += bj;
+        }
+    layer_norm_quad(acc, Wg + MOLSDE_G_LN2_W, Wg + MOLSDE_G_LN2_B, t4);
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col = nb * 8 + 2 * t4 + j;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int node = m0 + g + 8 * rr;
+                float x2 = x1[nb][2 * rr + j] + acc[nb][2 * rr + j];
+                if (silu_after) x2 = silu_fast(x2);
+                if (node < c.n) XT[col * LDX + node] = x2;
+            }
+        }
 }
 
 // ---------------------------------------------------------------------------------------
 // basis MLP + equivariant mean aggregation  (equivariant_scorenetwork.py:154-164)
 // ---------------------------------------------------------------------------------------
-__device__ void phase_basis(const Chunk& c, const float* __restrict__ blob, const int32_t* __restrict__ src_g,
-                            const float* __restrict__ scratch, int module) {
+__device__ __noinline__ void phase_basis(const Chunk c, const float* __restrict__ blob, const int32_t* __restrict__ src_g,
+                                         const float* __restrict__ scratch, int module) {
     float* sm = c.sm;
     float* Wb = sm + S_Q;  // staged over q/k/v (dead between GAT blocks)
     float* A = sm + S_A;
-    float* mix = sm + S_M;   // [TE][4]
-    float* dyn = sm + S_L;   // [TE][4]
+    float* dynp = sm + S_L;  // [2][TE][4] partial dyn coefficients of the two column halves
+    float* mix = sm + S_MS;  // [TE][4]
     const float* XT = sm + S_XT;
     const float* pos = sm + S_POS;
     float* grad = sm + S_GRAD;
     const int* rowl = c.si + SI_ROWL;
     const int* esrc = c.si + SI_ESRC;
     const int* etgt = c.si + SI_ETGT;
-    const int tid = threadIdx.x;
-    const int to = tid & 15, te = tid >> 4;  // 16 column groups x 16 edge groups, 8x8 micro-tile
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = (warp & 7) * 16, nh = warp >> 3, n0 = nh * 64;
+    const int g = lane >> 2, t4 = lane & 3;
     stage_async(Wb, blob + MOLSDE_P_BASIS0 + module * MOLSDE_P_BASIS_SZ, MOLSDE_P_BASIS_SZ);
     cp_async_wait<0>();
     __syncthreads();
     for (int t = 0; t < c.ntiles; ++t) {
         int ta, tb, ea;
-        stage_async(A + 32 * TE, scratch + static_cast<size_t>(t) * (32 * TE), 32 * TE);
+        stage_async(A + 32 * LDA, scratch + static_cast<size_t>(t) * TILE_FLOATS, TILE_FLOATS);
         const int ne = build_tile_edges(c, src_g, t, ta, tb, ea);
         __syncthreads();
         {   // rows 0..31: h_row + h_col
-            const int edge = tid & (TE - 1), k0 = (tid >> 7) * 16;
+            const int edge = tid & (TE - 1), k0 = (tid >> 7) * 8;
             const int sj = esrc[edge], ti = etgt[edge];
             const bool live = edge < ne;
-#pragma unroll 4
-            for (int k = k0; k < k0 + 16; ++k) A[k * TE + edge] = live ? XT[k * MAXN + sj] + XT[k * MAXN + ti] : 0.0f;
+#pragma unroll
+            for (int k = k0; k < k0 + 8; ++k) A[k * LDA + edge] = live ? XT[k * LDX + sj] + XT[k * LDX + ti] : 0.0f;
         }
         cp_async_wait<0>();
         __syncthreads();
-        float acc[8][8];
-        zero_acc(acc);
-        gemm_acc<8, 8, 128, TE>(A, Wb + MOLSDE_B_W1_T, 64, te, to, acc);
-        float part[8][3];
+        float acc[8][4];
+        zero_frag(acc);
+        mma_gemm<8, LDA, LD128>(A + m0, Wb + MOLSDE_B_W1 + n0, 64, lane, acc);
+        float part[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) part[i][0] = part[i][1] = part[i][2] = 0.0f;
+        for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int col = (j < 4) ? (to * 4 + j) : (64 + to * 4 + (j - 4));
-            const float b1 = Wb[MOLSDE_B_B1 + col];
-            const float w0 = Wb[MOLSDE_B_W2 + col], w1 = Wb[MOLSDE_B_W2 + 128 + col], w2 = Wb[MOLSDE_B_W2 + 256 + col];
+            for (int j = 0; j < 2; ++j) {
+                const int col = n0 + nb * 8 + 2 * t4 + j;
+                const float b1 = Wb[MOLSDE_B_B1 + col];
+                const float w0 = Wb[MOLSDE_B_W2 + col], w1 = Wb[MOLSDE_B_W2 + 128 + col], w2 = Wb[MOLSDE_B_W2 + 256 + col];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float hv = silu_f(acc[i][j] + b1);
-                part[i][0] = fmaf(hv, w0, part[i][0]);
-                part[i][1] = fmaf(hv, w1, part[i][1]);
-                part[i][2] = fmaf(hv, w2, part[i][2]);
+                for (int rr = 0; rr < 2; ++rr) {
+                    const float hv = silu_fast(acc[nb][2 * rr + j] + b1);
+                    part[rr][0] = fmaf(hv, w0, part[rr][0]);
+                    part[rr][1] = fmaf(hv, w1, part[rr][1]);
+                    part[rr][2] = fmaf(hv, w2, part[rr][2]);
+                }
             }
-        }
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
-                float v = part[i][o];
+                float v = part[rr][o];
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                part[i][o] = v;
+                if (t4 == 0) dynp[(nh * TE + m0 + g + 8 * rr) * 4 + o] = v;
             }
-        if (to == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int o = 0; o < 3; ++o) dyn[(te * 8 + i) * 4 + o] = part[i][o] + Wb[MOLSDE_B_B2 + o];
-        }
         __syncthreads();
         if (tid < ne) {
             const Frame f = coord2basis(pos + 3 * esrc[tid], pos + 3 * etgt[tid]);
-            const float d0 = dyn[tid * 4], d1 = dyn[tid * 4 + 1], d2 = dyn[tid * 4 + 2];
+            const float d0 = dynp[tid * 4] + dynp[(TE + tid) * 4] + Wb[MOLSDE_B_B2];
+            const float d1 = dynp[tid * 4 + 1] + dynp[(TE + tid) * 4 + 1] + Wb[MOLSDE_B_B2 + 1];
+            const float d2 = dynp[tid * 4 + 2] + dynp[(TE + tid) * 4 + 2] + Wb[MOLSDE_B_B2 + 2];
             mix[tid * 4 + 0] = d0 * f.dx + d1 * f.cx + d2 * f.vx;
             mix[tid * 4 + 1] = d0 * f.dy + d1 * f.cy + d2 * f.vy;
             mix[tid * 4 + 2] = d0 * f.dz + d1 * f.cz + d2 * f.vz;
@@ -592,15 +646,15 @@ __device__ void phase_basis(const Chunk& c, const float* __restrict__ blob, cons
 // ---------------------------------------------------------------------------------------
 // one full network evaluation on the chunk: positions in smem -> "gradient" in smem
 // ---------------------------------------------------------------------------------------
-__device__ void score_eval(const Chunk& c, const float* __restrict__ blob, const int32_t* __restrict__ src_g,
-                           const float* __restrict__ nattr, const float* __restrict__ e2d_tiles,
-                           float* __restrict__ scratch) {
+__device__ __noinline__ void score_eval(const Chunk c, const float* __restrict__ blob, const int32_t* __restrict__ src_g,
+                                        const float* __restrict__ nattr, const float* __restrict__ e2d_tiles,
+                                        float* __restrict__ scratch) {
     float* sm = c.sm;
     phase_edge_features(c, blob, src_g, e2d_tiles, scratch);
     // conv_input = node_attr (loop-invariant node_emb output), k-major
     for (int idx = threadIdx.x; idx < c.n * 32; idx += NTHREADS) {
         const int node = idx >> 5, k = idx & 31;
-        sm[S_XT + k * MAXN + node] = __ldg(nattr + static_cast<size_t>(c.node0 + node) * 32 + k);
+        sm[S_XT + k * LDX + node] = __ldg(nattr + static_cast<size_t>(c.node0 + node) * 32 + k);
     }
     __syncthreads();
     for (int module = 0; module < 2; ++module) {
@@ -612,6 +666,7 @@ __device__ void score_eval(const Chunk& c, const float* __restrict__ blob, const
             __syncthreads();
             gat_edge_phase(c, src_g, scratch);
             node_update(c, conv == 0);
+            __syncthreads();
         }
         phase_basis(c, blob, src_g, scratch, module);
     }
@@ -680,7 +735,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, u
         k1 += 0xBB67AE85u;
     }
 }
-__device__ __forceinline__ void normal3(uint64_t seed, uint32_t node, uint32_t step, uint32_t stream, float* out) {
+__device__ __noinline__ void normal3(uint64_t seed, uint32_t node, uint32_t step, uint32_t stream, float* out) {
     uint32_t ctr[4] = {node, step, stream, 0x5DEu};
     philox4x32_10(ctr, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     const float u1 = (static_cast<float>(ctr[0] >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
@@ -703,7 +758,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     __syncthreads();
     float s = 0.0f;
 #pragma unroll
-    for (int w = 0; w < NTHREADS / 32; ++w) s += red[w];
+    for (int w = 0; w < NWARPS; ++w) s += red[w];
     return s;
 }
 
@@ -799,9 +854,12 @@ sde2d3d_pc_kernel(molsde_plan plan, const float* __restrict__ blob, const float*
 
 // ---------------------------------------------------------------------------------------
 // edge_2D_emb (eval): e2d tile = W3 . relu(U[src] + V[tgt]) + b3,  SDE_model_2D_to_3D.py:405-407
-// uv [N][600]: columns 0..299 = folded first layer applied to h[row], 300..599 to h[col]
+// uv [N][600]: columns 0..299 = folded first layer applied to h[row], 300..599 to h[col].
+// One-time (loop-invariant) kernel: fp32 FFMA register tile, 256 threads, output in the [32][136] tile layout.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1)
+constexpr int E2D_THREADS = 256;
+
+__global__ void __launch_bounds__(E2D_THREADS, 1)
 edge2d_emb_kernel(molsde_plan plan, const float* __restrict__ uv, const float* __restrict__ w3t,
                   const float* __restrict__ b3, float* __restrict__ e2d_tiles) {
     extern __shared__ __align__(16) float smem[];
@@ -809,17 +867,18 @@ edge2d_emb_kernel(molsde_plan plan, const float* __restrict__ uv, const float* _
     float* W = smem + 64 * TE;   // [320][32] (rows >= 300 zero)
     __shared__ int s_src[TE], s_tgt[TE];
     const int tid = threadIdx.x, to = tid & 7, te = tid >> 3;
-    for (int i = tid; i < 320 * 32; i += NTHREADS) W[i] = (i < 300 * 32) ? w3t[i] : 0.0f;
+    for (int i = tid; i < 320 * 32; i += E2D_THREADS) W[i] = (i < 300 * 32) ? w3t[i] : 0.0f;
     __syncthreads();
     for (int tile = blockIdx.x; tile < plan.num_tiles; tile += gridDim.x) {
         const int ta = plan.tile_tgt_ptr[tile], tb = plan.tile_tgt_ptr[tile + 1];
         const int ea = plan.rowptr[ta], ne = plan.rowptr[tb] - ea;
         __syncthreads();
-        for (int i = ta + tid; i < tb; i += NTHREADS)
+        for (int i = ta + tid; i < tb; i += E2D_THREADS)
             for (int e = plan.rowptr[i]; e < plan.rowptr[i + 1]; ++e) { s_tgt[e - ea] = i; s_src[e - ea] = plan.src[e]; }
         __syncthreads();
         float acc[4][4];
-        zero_acc(acc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
         for (int k0 = 0; k0 < 320; k0 += 64) {
             const int edge = tid & (TE - 1), kh = (tid >> 7) * 32;
             const bool live = edge < ne;
@@ -833,10 +892,20 @@ edge2d_emb_kernel(molsde_plan plan, const float* __restrict__ uv, const float* _
                 A[(kh + kk) * TE + edge] = v;
             }
             __syncthreads();
-            gemm_acc<4, 4, 32, TE>(A, W + k0 * 32, 64, te, to, acc);
+            const float* wk = W + k0 * 32;
+#pragma unroll 4
+            for (int k = 0; k < 64; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(A + k * TE + te * 4);
+                const float4 b = *reinterpret_cast<const float4*>(wk + k * 32 + to * 4);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
             __syncthreads();
         }
-        float* out = e2d_tiles + static_cast<size_t>(tile) * (32 * TE);
+        float* out = e2d_tiles + static_cast<size_t>(tile) * TILE_FLOATS;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int col = to * 4 + j;
@@ -849,8 +918,9 @@ edge2d_emb_kernel(molsde_plan plan, const float* __restrict__ uv, const float* _
                 if (s + 2 >= ne) o.z = 0.f;
                 if (s + 3 >= ne) o.w = 0.f;
             }
-            *reinterpret_cast<float4*>(out + col * TE + s) = o;
+            *reinterpret_cast<float4*>(out + col * LDA + s) = o;
         }
+        if (tid < 32 * (LDA - TE)) out[(tid / (LDA - TE)) * LDA + TE + tid % (LDA - TE)] = 0.0f;  // pad columns
     }
 }
 
@@ -865,12 +935,14 @@ static int plan_ok(const molsde_plan* p) {
 
 extern "C" {
 
+int64_t molsde_tile_floats(void) { return TILE_FLOATS; }
+
 int64_t molsde_sde2d3d_scratch_floats(const molsde_plan* plan, int32_t max_chunk_tiles, int32_t* num_ctas_out) {
     if (!plan || max_chunk_tiles < 0) return MOLSDE_ERR_INVALID;
     int ctas = plan->num_chunks < kNumSMs ? plan->num_chunks : kNumSMs;
     if (ctas < 1) ctas = 1;
     if (num_ctas_out) *num_ctas_out = ctas;
-    return static_cast<int64_t>(ctas) * max_chunk_tiles * 32 * TE;
+    return static_cast<int64_t>(ctas) * max_chunk_tiles * TILE_FLOATS;
 }
 
 int molsde_edge2d_emb_eval(const molsde_plan* plan, const float* uv, const float* w3t, const float* b3,
@@ -881,7 +953,7 @@ int molsde_edge2d_emb_eval(const molsde_plan* plan, const float* uv, const float
     cudaError_t err = cudaFuncSetAttribute(edge2d_emb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) { set_last_error(cudaGetErrorString(err)); return MOLSDE_ERR_CUDA; }
     int grid = plan->num_tiles < 2 * kNumSMs ? plan->num_tiles : 2 * kNumSMs;
-    edge2d_emb_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(*plan, uv, w3t, b3, e2d_tiles);
+    edge2d_emb_kernel<<<grid, E2D_THREADS, smem, as_stream(stream)>>>(*plan, uv, w3t, b3, e2d_tiles);
     return check_launch("edge2d_emb");
 }
 
@@ -893,8 +965,8 @@ int molsde_sde2d3d_score(const molsde_plan* plan, const molsde_sde2d3d_params* p
     if (params->blob_floats < MOLSDE_P_TOTAL) return MOLSDE_ERR_INVALID;
     if (plan->num_chunks == 0) return MOLSDE_OK;
     int ctas = plan->num_chunks < kNumSMs ? plan->num_chunks : kNumSMs;
-    const int64_t stride = (scratch_floats / ctas) / (32 * TE) * (32 * TE);
-    if (stride < 32 * TE) return MOLSDE_ERR_WORKSPACE;
+    const int64_t stride = (scratch_floats / ctas) / TILE_FLOATS * TILE_FLOATS;
+    if (stride < TILE_FLOATS) return MOLSDE_ERR_WORKSPACE;
     cudaError_t err = cudaFuncSetAttribute(sde2d3d_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (err != cudaSuccess) { set_last_error(cudaGetErrorString(err)); return MOLSDE_ERR_CUDA; }
     sde2d3d_score_kernel<<<ctas, NTHREADS, SMEM_BYTES, as_stream(stream)>>>(*plan, params->blob, nattr, e2d_tiles, pos,
@@ -914,8 +986,8 @@ int molsde_sde2d3d_pc_sample(const molsde_plan* plan, const molsde_sde2d3d_param
     if ((noise_corr == nullptr) != (noise_pred == nullptr)) return MOLSDE_ERR_INVALID;
     if (plan->num_chunks == 0) return MOLSDE_OK;
     int ctas = plan->num_chunks < kNumSMs ? plan->num_chunks : kNumSMs;
-    const int64_t stride = (scratch_floats / ctas) / (32 * TE) * (32 * TE);
-    if (stride < 32 * TE) return MOLSDE_ERR_WORKSPACE;
+    const int64_t stride = (scratch_floats / ctas) / TILE_FLOATS * TILE_FLOATS;
+    if (stride < TILE_FLOATS) return MOLSDE_ERR_WORKSPACE;
     cudaError_t err = cudaFuncSetAttribute(sde2d3d_pc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (err != cudaSuccess) { set_last_error(cudaGetErrorString(err)); return MOLSDE_ERR_CUDA; }
     err = cudaMemsetAsync(work_counter, 0, sizeof(int32_t), as_stream(stream));

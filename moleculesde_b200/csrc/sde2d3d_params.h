@@ -1,52 +1,55 @@
 /* Float offsets inside the packed SDEModel2Dto3D_02 parameter blob (molsde_sde2d3d_params.blob).
- * The host (moleculesde_b200/sde_2d_to_3d.py::pack_params) builds it from the reference
- * state_dict keys; every `*_WT` block is the nn.Linear weight transposed to
- * [in][out] (k-major) so the kernels stream it as the B operand.  All offsets are multiples of 4
- * floats (16 B, cp.async granularity). */
+ * The host (moleculesde_b200/sde_2d_to_3d.py::packed_params) builds it from the reference
+ * state_dict keys.  Every `*_W` matrix is stored k-major (`[in][ld]`, i.e. the
+ * nn.Linear weight transposed) with a padded leading dimension ld == 8 (mod 32) so that the
+ * mma.sync B-fragment loads (lane -> (k = lane%4, n = lane/4)) are shared-memory bank-conflict free.
+ * All offsets are multiples of 4 floats (16 B, cp.async granularity). */
 #ifndef MOLSDE_SDE2D3D_PARAMS_H_
 #define MOLSDE_SDE2D3D_PARAMS_H_
 
-#define MOLSDE_P_GFP_DIST_W 0    /* dist_gaussian_fourier.W [32] */
-#define MOLSDE_P_GFP_COFF_W 32   /* coff_gaussian_fourier.W [32] */
-#define MOLSDE_P_IN_WT 64        /* input_mlp.layers.0.weight^T [64][32] */
-#define MOLSDE_P_IN_B 2112       /* [32] */
-#define MOLSDE_P_COFF_WT 2144    /* coff_mlp.weight^T [128][32] */
-#define MOLSDE_P_COFF_B 6240     /* [32] */
-#define MOLSDE_P_PROJ0_WT 6272   /* project.layers.0.weight^T [68][32] (rows 66,67 zero) */
-#define MOLSDE_P_PROJ0_B 8448    /* [32] */
-#define MOLSDE_P_PROJ1_WT 8480   /* project.layers.1.weight^T [32][32] */
-#define MOLSDE_P_PROJ1_B 9504    /* [32] */
-#define MOLSDE_P_E0_END 9536
+#define MOLSDE_LD32 40   /* leading dimension of a 32-column weight block  */
+#define MOLSDE_LD96 104  /* q|k|v block                                     */
+#define MOLSDE_LD128 136 /* 128-column weight block                         */
 
-/* one GATLayer (score_network.gnn_layers.{m}.{c}), base = MOLSDE_P_GAT0 + (2*m+c)*MOLSDE_P_GAT_SZ */
-#define MOLSDE_P_GAT0 9536
-#define MOLSDE_G_WQ_T 0      /* MHA.lin_query.weight^T [32][32] */
-#define MOLSDE_G_WK_T 1024   /* MHA.lin_key */
-#define MOLSDE_G_WV_T 2048   /* MHA.lin_value */
-#define MOLSDE_G_WS_T 3072   /* MHA.lin_skip */
-#define MOLSDE_G_BQ 4096
-#define MOLSDE_G_BK 4128
-#define MOLSDE_G_BV 4160
-#define MOLSDE_G_BS 4192
-#define MOLSDE_G_WE_T 4224   /* MHA.lin_edge.weight^T [32][32] (no bias) */
-#define MOLSDE_G_LN1_W 5248
-#define MOLSDE_G_LN1_B 5280
-#define MOLSDE_G_F0_WT 5312  /* FFN.0 */
-#define MOLSDE_G_F0_B 6336
-#define MOLSDE_G_F3_WT 6368  /* FFN.3 */
-#define MOLSDE_G_F3_B 7392
-#define MOLSDE_G_LN2_W 7424
-#define MOLSDE_G_LN2_B 7456
-#define MOLSDE_P_GAT_SZ 7488
+/* ---- per-edge feature stage (SDE_model_2D_to_3D.py:402-432) ---- */
+#define MOLSDE_P_GFP_DIST_W 0   /* dist_gaussian_fourier.W [32] */
+#define MOLSDE_P_GFP_COFF_W 32  /* coff_gaussian_fourier.W [32] */
+#define MOLSDE_P_IN_B 64        /* input_mlp.layers.0.bias [32] */
+#define MOLSDE_P_H_B 96         /* fused bias: project.0.bias + P_i b_c + P_j b_c [32] */
+#define MOLSDE_P_H_WSIN 128     /* project.layers.0.weight[:,0] (pseudo_sin) [32] */
+#define MOLSDE_P_H_WCOS 160     /* project.layers.0.weight[:,1] (pseudo_cos) [32] */
+#define MOLSDE_P_P1_B 192       /* project.layers.1.bias [32] */
+#define MOLSDE_P_IN_W 224       /* input_mlp.layers.0.weight^T [64][40] */
+#define MOLSDE_P_H_W 2784       /* (project.0.weight[:,2:34] @ coff_mlp.weight)^T rows 0..127,
+                                   (project.0.weight[:,34:66] @ coff_mlp.weight)^T rows 128..255; [256][40] */
+#define MOLSDE_P_P1_W 13024     /* project.layers.1.weight^T [32][40] */
+#define MOLSDE_P_E0_END 14304
 
-/* one basis MLP (score_network.basis_mlp_modules.{m}), base = MOLSDE_P_BASIS0 + m*MOLSDE_P_BASIS_SZ */
-#define MOLSDE_P_BASIS0 39488
-#define MOLSDE_B_W1_T 0      /* .0.weight^T [64][128]: rows 0..31 act on h_row+h_col, 32..63 on edge_attr */
-#define MOLSDE_B_B1 8192     /* [128] */
-#define MOLSDE_B_W2 8320     /* .2.weight [3][128] */
-#define MOLSDE_B_B2 8704     /* [3] + 1 pad */
-#define MOLSDE_P_BASIS_SZ 8708
+/* ---- one GATLayer (score_network.gnn_layers.{m}.{c}), base = P_GAT0 + (2m+c)*P_GAT_SZ ---- */
+#define MOLSDE_P_GAT0 14304
+#define MOLSDE_G_WQKV 0     /* [lin_query | lin_key | lin_value].weight^T [32][104] */
+#define MOLSDE_G_WS 3328    /* MHA.lin_skip.weight^T [32][40] */
+#define MOLSDE_G_WE 4608    /* MHA.lin_edge.weight^T [32][40] (no bias) */
+#define MOLSDE_G_F0 5888    /* FFN.0.weight^T [32][40] */
+#define MOLSDE_G_F3 7168    /* FFN.3.weight^T [32][40] */
+#define MOLSDE_G_BQKV 8448  /* [96] */
+#define MOLSDE_G_BS 8544
+#define MOLSDE_G_LN1_W 8576
+#define MOLSDE_G_LN1_B 8608
+#define MOLSDE_G_F0_B 8640
+#define MOLSDE_G_F3_B 8672
+#define MOLSDE_G_LN2_W 8704
+#define MOLSDE_G_LN2_B 8736
+#define MOLSDE_P_GAT_SZ 8768
 
-#define MOLSDE_P_TOTAL 56904
+/* ---- one basis MLP (score_network.basis_mlp_modules.{m}), base = P_BASIS0 + m*P_BASIS_SZ ---- */
+#define MOLSDE_P_BASIS0 49376
+#define MOLSDE_B_W1 0      /* .0.weight^T [64][136]: rows 0..31 act on h_row+h_col, 32..63 on edge_attr */
+#define MOLSDE_B_B1 8704   /* [128] */
+#define MOLSDE_B_W2 8832   /* .2.weight [3][128] */
+#define MOLSDE_B_B2 9216   /* [3] + 1 pad */
+#define MOLSDE_P_BASIS_SZ 9220
+
+#define MOLSDE_P_TOTAL 67816
 
 #endif

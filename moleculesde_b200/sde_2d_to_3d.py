@@ -18,17 +18,16 @@ from .plan import TilePlan, build_plan
 from .sde import VESDE, VPSDE
 
 # float offsets of csrc/sde2d3d_params.h
+LD32, LD96, LD128 = 40, 104, 136
 P_GFP_DIST_W, P_GFP_COFF_W = 0, 32
-P_IN_WT, P_IN_B = 64, 2112
-P_COFF_WT, P_COFF_B = 2144, 6240
-P_PROJ0_WT, P_PROJ0_B = 6272, 8448
-P_PROJ1_WT, P_PROJ1_B = 8480, 9504
-P_GAT0, P_GAT_SZ = 9536, 7488
-P_BASIS0, P_BASIS_SZ = 39488, 8708
-P_TOTAL = 56904
-_G = dict(WQ_T=0, WK_T=1024, WV_T=2048, WS_T=3072, BQ=4096, BK=4128, BV=4160, BS=4192, WE_T=4224,
-          LN1_W=5248, LN1_B=5280, F0_WT=5312, F0_B=6336, F3_WT=6368, F3_B=7392, LN2_W=7424, LN2_B=7456)
-_B = dict(W1_T=0, B1=8192, W2=8320, B2=8704)
+P_IN_B, P_H_B, P_H_WSIN, P_H_WCOS, P_P1_B = 64, 96, 128, 160, 192
+P_IN_W, P_H_W, P_P1_W, P_E0_END = 224, 2784, 13024, 14304
+P_GAT0, P_GAT_SZ = 14304, 8768
+P_BASIS0, P_BASIS_SZ = 49376, 9220
+P_TOTAL = 67816
+_G = dict(WQKV=0, WS=3328, WE=4608, F0=5888, F3=7168, BQKV=8448, BS=8544, LN1_W=8576, LN1_B=8608, F0_B=8640,
+          F3_B=8672, LN2_W=8704, LN2_B=8736)
+_B = dict(W1=0, B1=8704, W2=8832, B2=9216)
 
 
 class MultiLayerPerceptron(nn.Module):
@@ -179,40 +178,54 @@ class SDEModel2Dto3D_02(nn.Module):
         def put(off, t):
             blob[off:off + t.numel()] = t.reshape(-1)
 
+        def put_kmajor(off, w, ld):
+            """nn.Linear weight [out,in] -> k-major block [in][ld] (columns >= out stay zero)."""
+            out_f, in_f = w.shape
+            blk = torch.zeros(in_f, ld, dtype=torch.float32, device=dev)
+            blk[:, :out_f] = w.t()
+            put(off, blk)
+
         put(P_GFP_DIST_W, sd["dist_gaussian_fourier.W"])
         put(P_GFP_COFF_W, sd["coff_gaussian_fourier.W"])
-        put(P_IN_WT, sd["input_mlp.layers.0.weight"].t().contiguous())
         put(P_IN_B, sd["input_mlp.layers.0.bias"])
-        put(P_COFF_WT, sd["coff_mlp.weight"].t().contiguous())
-        put(P_COFF_B, sd["coff_mlp.bias"])
-        put(P_PROJ0_WT, sd["project.layers.0.weight"].t().contiguous())  # 66 rows; 2 pad rows stay zero
-        put(P_PROJ0_B, sd["project.layers.0.bias"])
-        put(P_PROJ1_WT, sd["project.layers.1.weight"].t().contiguous())
-        put(P_PROJ1_B, sd["project.layers.1.bias"])
+        put_kmajor(P_IN_W, sd["input_mlp.layers.0.weight"], LD32)
+        # coff_mlp is a bare Linear feeding project.layers.0 (SDE_model_2D_to_3D.py:297-304,429-430): fold it in
+        # (float64 products, rounded once) so the hidden layer accumulates straight from the Fourier features.
+        H = self.hidden_dim
+        P0 = sd["project.layers.0.weight"].double()                     # [32, 66] = [psin, pcos, emb_i(32), emb_j(32)]
+        Wc, bc = sd["coff_mlp.weight"].double(), sd["coff_mlp.bias"].double()  # [32,128], [32]
+        Pi, Pj = P0[:, 2:2 + H], P0[:, 2 + H:2 + 2 * H]
+        w_h = torch.cat([Pi @ Wc, Pj @ Wc], dim=1)                       # [32, 256]
+        b_h = sd["project.layers.0.bias"].double() + Pi @ bc + Pj @ bc
+        put_kmajor(P_H_W, w_h.float(), LD32)
+        put(P_H_B, b_h.float())
+        put(P_H_WSIN, P0[:, 0].float())
+        put(P_H_WCOS, P0[:, 1].float())
+        put_kmajor(P_P1_W, sd["project.layers.1.weight"], LD32)
+        put(P_P1_B, sd["project.layers.1.bias"])
         for m in range(2):
             for c in range(2):
                 base = P_GAT0 + (2 * m + c) * P_GAT_SZ
                 p = f"score_network.gnn_layers.{m}.{c}."
-                put(base + _G["WQ_T"], sd[p + "MHA.lin_query.weight"].t().contiguous())
-                put(base + _G["WK_T"], sd[p + "MHA.lin_key.weight"].t().contiguous())
-                put(base + _G["WV_T"], sd[p + "MHA.lin_value.weight"].t().contiguous())
-                put(base + _G["WS_T"], sd[p + "MHA.lin_skip.weight"].t().contiguous())
-                put(base + _G["BQ"], sd[p + "MHA.lin_query.bias"])
-                put(base + _G["BK"], sd[p + "MHA.lin_key.bias"])
-                put(base + _G["BV"], sd[p + "MHA.lin_value.bias"])
+                wqkv = torch.cat([sd[p + "MHA.lin_query.weight"], sd[p + "MHA.lin_key.weight"],
+                                  sd[p + "MHA.lin_value.weight"]], dim=0)  # [96, 32]
+                put_kmajor(base + _G["WQKV"], wqkv, LD96)
+                put(base + _G["BQKV"], torch.cat([sd[p + "MHA.lin_query.bias"], sd[p + "MHA.lin_key.bias"],
+                                                  sd[p + "MHA.lin_value.bias"]]))
+                put_kmajor(base + _G["WS"], sd[p + "MHA.lin_skip.weight"], LD32)
                 put(base + _G["BS"], sd[p + "MHA.lin_skip.bias"])
-                put(base + _G["WE_T"], sd[p + "MHA.lin_edge.weight"].t().contiguous())
+                put_kmajor(base + _G["WE"], sd[p + "MHA.lin_edge.weight"], LD32)
                 put(base + _G["LN1_W"], sd[p + "norm1.weight"])
                 put(base + _G["LN1_B"], sd[p + "norm1.bias"])
-                put(base + _G["F0_WT"], sd[p + "FFN.0.weight"].t().contiguous())
+                put_kmajor(base + _G["F0"], sd[p + "FFN.0.weight"], LD32)
                 put(base + _G["F0_B"], sd[p + "FFN.0.bias"])
-                put(base + _G["F3_WT"], sd[p + "FFN.3.weight"].t().contiguous())
+                put_kmajor(base + _G["F3"], sd[p + "FFN.3.weight"], LD32)
                 put(base + _G["F3_B"], sd[p + "FFN.3.bias"])
                 put(base + _G["LN2_W"], sd[p + "norm2.weight"])
                 put(base + _G["LN2_B"], sd[p + "norm2.bias"])
             base = P_BASIS0 + m * P_BASIS_SZ
             p = f"score_network.basis_mlp_modules.{m}."
-            put(base + _B["W1_T"], sd[p + "0.weight"].t().contiguous())
+            put_kmajor(base + _B["W1"], sd[p + "0.weight"], LD128)
             put(base + _B["B1"], sd[p + "0.bias"])
             put(base + _B["W2"], sd[p + "2.weight"])
             put(base + _B["B2"], sd[p + "2.bias"])
@@ -264,7 +277,7 @@ class SDEModel2Dto3D_02(nn.Module):
         uv = torch.empty(N, 2 * self.emb_dim, dtype=torch.float32, device=dev)
         check(lib().molsde_linear(ptr(h), N, self.emb_dim, self.emb_dim, ptr(pk["w_uv"]), ptr(pk["b_uv"]),
                                   2 * self.emb_dim, ptr(uv), 2 * self.emb_dim, 0, s), "edge_2D_emb.0")
-        e2d = torch.empty(max(prep.plan.num_tiles, 1) * _abi.HID * _abi.TILE_EDGES, dtype=torch.float32, device=dev)
+        e2d = torch.empty(max(prep.plan.num_tiles, 1) * _abi.TILE_FLOATS, dtype=torch.float32, device=dev)
         st = prep.plan.as_struct()
         check(lib().molsde_edge2d_emb_eval(ctypes.byref(st), ptr(uv), ptr(pk["w3t"]), ptr(pk["b3"]), ptr(e2d), s),
               "edge2d_emb_eval")

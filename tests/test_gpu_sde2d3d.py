@@ -83,7 +83,7 @@ def test_edge2d_and_node_invariants_vs_oracle(golden, golden_batch):
     ref = O.edge_2d_emb(sd, h2d, ei, training=False)  # reference order: sorted by (row, col); row=source
     tt = prep.plan.tile_tgt_ptr.cpu().long()
     rp = prep.csr.rowptr.cpu().long()
-    e2d = e2d.cpu().view(-1, 32, _abi.TILE_EDGES)
+    e2d = e2d.cpu().view(-1, 32, _abi.TILE_LD)
     rows = []
     for t in range(prep.plan.num_tiles):
         ne = int(rp[tt[t + 1]] - rp[tt[t]])

@@ -34,19 +34,29 @@ def test_library_exports_header_symbols(built_lib):
 
 
 def test_param_offsets_match_header():
+    from moleculesde_b200 import _abi
     from moleculesde_b200 import sde_2d_to_3d as M
     hdr = open(os.path.join(REPO, "moleculesde_b200", "csrc", "sde2d3d_params.h")).read()
     defs = {k: int(v) for k, v in re.findall(r"#define\s+(MOLSDE_\w+)\s+(\d+)", hdr)}
     assert defs["MOLSDE_P_TOTAL"] == M.P_TOTAL == defs["MOLSDE_P_BASIS0"] + 2 * defs["MOLSDE_P_BASIS_SZ"]
-    assert defs["MOLSDE_P_GAT0"] == M.P_GAT0 and defs["MOLSDE_P_GAT_SZ"] == M.P_GAT_SZ
+    assert defs["MOLSDE_P_GAT0"] == M.P_GAT0 == defs["MOLSDE_P_E0_END"] and defs["MOLSDE_P_GAT_SZ"] == M.P_GAT_SZ
     assert defs["MOLSDE_P_BASIS0"] == M.P_BASIS0 == M.P_GAT0 + 4 * M.P_GAT_SZ
+    assert (defs["MOLSDE_LD32"], defs["MOLSDE_LD96"], defs["MOLSDE_LD128"]) == (M.LD32, M.LD96, M.LD128)
+    for ld in (M.LD32, M.LD96, M.LD128):
+        assert ld % 32 == 8  # bank-conflict-free mma B-fragment loads
     for k, v in M._G.items():
-        assert defs["MOLSDE_G_" + k] == v
+        assert defs["MOLSDE_G_" + k] == v and v % 4 == 0
     for k, v in M._B.items():
-        assert defs["MOLSDE_B_" + k] == v
-    for name in ("IN_WT", "IN_B", "COFF_WT", "COFF_B", "PROJ0_WT", "PROJ0_B", "PROJ1_WT", "PROJ1_B"):
+        assert defs["MOLSDE_B_" + k] == v and v % 4 == 0
+    for name in ("IN_B", "H_B", "H_WSIN", "H_WCOS", "P1_B", "IN_W", "H_W", "P1_W", "E0_END"):
         assert defs["MOLSDE_P_" + name] == getattr(M, "P_" + name)
         assert defs["MOLSDE_P_" + name] % 4 == 0
+    # blocks do not overlap
+    assert M.P_IN_W + 64 * M.LD32 == M.P_H_W and M.P_H_W + 256 * M.LD32 == M.P_P1_W and M.P_P1_W + 32 * M.LD32 == M.P_E0_END
+    assert M._G["WQKV"] + 32 * M.LD96 == M._G["WS"] and M._G["F3"] + 32 * M.LD32 == M._G["BQKV"]
+    assert M._B["W1"] + 64 * M.LD128 == M._B["B1"]
+    api = open(os.path.join(REPO, "include", "molsde_b200.h")).read()
+    assert int(re.search(r"#define MOLSDE_TILE_LD (\d+)", api).group(1)) == _abi.TILE_LD
 
 
 def test_state_dict_layout_matches_reference(golden):
@@ -66,14 +76,25 @@ def test_packed_blob_roundtrip(golden):
     pk = m.packed_params()
     blob = pk["blob"]
     assert blob.numel() == M.P_TOTAL
-    W = sd["coff_mlp.weight"]
-    assert torch.equal(blob[M.P_COFF_WT:M.P_COFF_WT + 128 * 32].view(128, 32), W.t())
+    # fused project.0 o coff_mlp block reproduces the two-layer reference expression
+    g_i, g_j, ang = torch.randn(5, 128), torch.randn(5, 128), torch.randn(5, 2)
+    emb_i = g_i @ sd["coff_mlp.weight"].t() + sd["coff_mlp.bias"]
+    emb_j = g_j @ sd["coff_mlp.weight"].t() + sd["coff_mlp.bias"]
+    ref = torch.cat([ang, emb_i, emb_j], -1) @ sd["project.layers.0.weight"].t() + sd["project.layers.0.bias"]
+    WH = blob[M.P_H_W:M.P_H_W + 256 * M.LD32].view(256, M.LD32)[:, :32]
+    got = torch.cat([g_i, g_j], -1) @ WH + blob[M.P_H_B:M.P_H_B + 32] + ang[:, :1] * blob[M.P_H_WSIN:M.P_H_WSIN + 32] \
+        + ang[:, 1:] * blob[M.P_H_WCOS:M.P_H_WCOS + 32]
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
     base = M.P_GAT0 + 3 * M.P_GAT_SZ
-    assert torch.equal(blob[base + M._G["WE_T"]:base + M._G["WE_T"] + 1024].view(32, 32),
-                       sd["score_network.gnn_layers.1.1.MHA.lin_edge.weight"].t())
+    we = blob[base + M._G["WE"]:base + M._G["WE"] + 32 * M.LD32].view(32, M.LD32)
+    assert torch.equal(we[:, :32], sd["score_network.gnn_layers.1.1.MHA.lin_edge.weight"].t()) and torch.all(we[:, 32:] == 0)
+    wqkv = blob[base + M._G["WQKV"]:base + M._G["WQKV"] + 32 * M.LD96].view(32, M.LD96)
+    assert torch.equal(wqkv[:, 32:64], sd["score_network.gnn_layers.1.1.MHA.lin_key.weight"].t())
     base = M.P_BASIS0 + M.P_BASIS_SZ
     assert torch.equal(blob[base + M._B["W2"]:base + M._B["W2"] + 384].view(3, 128),
                        sd["score_network.basis_mlp_modules.1.2.weight"])
+    w1 = blob[base + M._B["W1"]:base + M._B["W1"] + 64 * M.LD128].view(64, M.LD128)
+    assert torch.equal(w1[:, :128], sd["score_network.basis_mlp_modules.1.0.weight"].t())
     # BN-folded, node-factored first layer of edge_2D_emb equals the reference layer in eval mode
     h = torch.randn(7, 300)
     row, col = torch.tensor([0, 3, 5]), torch.tensor([1, 2, 6])
