@@ -103,11 +103,11 @@ __device__ __forceinline__ void sincos_reduced(float x, float& s, float& c) {
 //     a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  b0 (k=t, n=g) b1 (k=t+4, n=g)
 //     c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t tf32_hi(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// hi part of the 3xTF32 split: the top 19 bits of the fp32 pattern (what the tensor core keeps of a .tf32 operand).
+// `cvt.rna.tf32.f32` is not native on sm_100a (ptxas expands it to FSETP+IADD3+SEL+LOP3, profiles/r1_pc_v2_lines.txt),
+// so the split truncates with one LOP3; lo = x - hi is exact, and the dropped lo*lo term plus the tensor core's own
+// truncation of lo stay below 2^-20 relative.
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
