@@ -5,7 +5,7 @@
 // examples/pretrain_MoleculeSDE_inference_2D_to_3D_VE_VP.py:92-212.
 //
 // Design (B200-first):
-//   * one persistent CTA (512 threads, 1 CTA/SM, ~223 KB smem) owns one "chunk" = a set of whole
+//   * one persistent CTA (512 threads = 2 decoupled groups of 8 warps, 1 CTA/SM, ~219 KB smem) owns one "chunk" = a set of whole
 //     molecules with <= 224 atoms; node state (hidden features, q/k/v, positions, score) lives in
 //     shared memory for the WHOLE score evaluation -- and, in the PC kernel, for all 1000 reverse
 //     steps -- so HBM sees only the initial/final positions;
@@ -30,11 +30,14 @@ namespace molsde {
 constexpr int TE = MOLSDE_TILE_EDGES;         // 128 edges per tile
 constexpr int NTHREADS = 512;
 constexpr int NWARPS = NTHREADS / 32;
+constexpr int GROUPS = 2;                     // two 8-warp groups work on alternate tiles, decoupled
+constexpr int GTHREADS = NTHREADS / GROUPS;
 constexpr int MAXN = MOLSDE_CHUNK_MAX_NODES;  // 224 atoms per chunk
 constexpr int MAXT = 64;                      // tiles per chunk
 constexpr int LDA = MOLSDE_TILE_LD;           // 136: leading dim of a k-major edge tile
 constexpr int LDX = 232;                      // leading dim of the k-major node matrix (>= MAXN, == 8 mod 32)
 constexpr int TILE_FLOATS = 32 * LDA;         // one [32][136] per-edge attribute tile
+constexpr int LDM = 33;                       // padded row of the slot-major message tile [TE][33]
 constexpr int LD32 = MOLSDE_LD32, LD96 = MOLSDE_LD96, LD128 = MOLSDE_LD128;
 constexpr float EPS = 1e-6f;                  // SDE_model_2D_to_3D.py:10
 constexpr float LN_EPS = 1e-5f;
@@ -45,11 +48,11 @@ constexpr int S_Q = S_XT + 32 * LDX;         // [MAXN][32]  query  (aggregate wr
 constexpr int S_K = S_Q + 32 * MAXN;         // [MAXN][32]
 constexpr int S_V = S_K + 32 * MAXN;         // [MAXN][32]
 constexpr int S_WG = S_V + 32 * MAXN;        // [P_GAT_SZ]  weights of the current GAT layer
-constexpr int S_A = S_WG + MOLSDE_P_GAT_SZ;  // [64][LDA]   A operand (k-major); node phases stage [32][LDX] here
-constexpr int S_M = S_A + 64 * LDA;          // [TILE_FLOATS] weighted messages [TE][32] / e2d + edge_attr tile
-constexpr int S_L = S_M + TILE_FLOATS;       // [TE][8]     logits / geometry scalars / partial dyn coeffs
-constexpr int S_MS = S_L + TE * 8;           // [2][TE][8]  softmax max, sum / basis mix
-constexpr int S_POS = S_MS + 2 * TE * 8;     // [MAXN*3]
+constexpr int S_A = S_WG + MOLSDE_P_GAT_SZ;  // [GROUPS][32][LDA] A operand per group (k-major); also the message tile
+                                             //                   [TE][33] of the group and the node staging [32][LDX]
+constexpr int S_L = S_A + GROUPS * TILE_FLOATS;  // [GROUPS][TE][8]    logits / per-warp geometry scalars
+constexpr int S_MS = S_L + GROUPS * TE * 8;      // [GROUPS][2][TE][8] softmax max, sum / basis mix
+constexpr int S_POS = S_MS + GROUPS * 2 * TE * 8;  // [MAXN*3]
 constexpr int S_GRAD = S_POS + MAXN * 3;     // [MAXN*3]  network output ("gradient")
 constexpr int S_SCORE = S_GRAD + MAXN * 3;   // [MAXN*3]
 constexpr int S_NOISE = S_SCORE + MAXN * 3;  // [MAXN*3]
@@ -58,17 +61,18 @@ constexpr int S_FLOATS = S_RED + 64;
 // int region (after the floats)
 constexpr int SI_ROWL = 0;                   // [MAXN+1] edge offsets local to the chunk
 constexpr int SI_TTGT = SI_ROWL + MAXN + 1;  // [MAXT+1] tile target boundaries local to the chunk
-constexpr int SI_ESRC = SI_TTGT + MAXT + 1;  // [TE]
-constexpr int SI_ETGT = SI_ESRC + TE;        // [TE]
-constexpr int SI_MISC = SI_ETGT + TE;        // [4]
+constexpr int SI_ESRC = SI_TTGT + MAXT + 1;  // [GROUPS][TE]
+constexpr int SI_ETGT = SI_ESRC + GROUPS * TE;  // [GROUPS][TE]
+constexpr int SI_MISC = SI_ETGT + GROUPS * TE;  // [4]
 constexpr int S_INTS = SI_MISC + 4;
 constexpr size_t SMEM_BYTES = sizeof(float) * S_FLOATS + sizeof(int) * S_INTS;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 static_assert(MOLSDE_P_E0_END <= 3 * 32 * MAXN, "E0 weights are staged in the q/k/v region");
 static_assert(MOLSDE_P_BASIS_SZ <= 3 * 32 * MAXN, "basis weights are staged in the q/k/v region");
-static_assert(32 * LDX <= 64 * LDA, "node staging aliases the A region");
+static_assert(32 * LDX <= GROUPS * TILE_FLOATS, "node staging aliases the A region");
+static_assert(TE * LDM <= TILE_FLOATS, "message tile aliases the group's A region");
 static_assert(LDX >= MAXN && LDX % 32 == 8 && LDA % 32 == 8, "padded leading dimensions");
-static_assert(S_A % 4 == 0 && S_M % 4 == 0 && S_WG % 4 == 0 && S_Q % 4 == 0, "16B alignment for cp.async");
+static_assert(S_A % 4 == 0 && S_WG % 4 == 0 && S_Q % 4 == 0 && TILE_FLOATS % 4 == 0, "16B alignment for cp.async");
 
 struct Chunk {
     float* sm;
@@ -184,74 +188,103 @@ __device__ __forceinline__ Frame coord2basis(const float* pr, const float* pc) {
     return f;
 }
 
-// per-tile edge bookkeeping: local source / target of every slot, returns #edges in the tile
-__device__ __forceinline__ int build_tile_edges(const Chunk& c, const int32_t* __restrict__ src_g, int t, int& ta,
-                                                int& tb, int& ea) {
-    const int* rowl = c.si + SI_ROWL;
-    const int* ttgt = c.si + SI_TTGT;
-    int* esrc = c.si + SI_ESRC;
-    int* etgt = c.si + SI_ETGT;
-    ta = ttgt[t];
-    tb = ttgt[t + 1];
-    ea = rowl[ta];
-    const int ne = rowl[tb] - ea;
-    for (int i = ta + threadIdx.x; i < tb; i += NTHREADS) {
-        for (int e = rowl[i]; e < rowl[i + 1]; ++e) {
-            etgt[e - ea] = i;
-            esrc[e - ea] = src_g[c.edge0 + e] - c.node0;
-        }
-    }
-    for (int s = ne + threadIdx.x; s < TE; s += NTHREADS) { esrc[s] = 0; etgt[s] = 0; }
-    return ne;
+// ---- group / tile helpers -------------------------------------------------------------------
+// The 16 warps form two groups of 8; group g walks tiles g, g+2, ... of the chunk.  Inside a group
+// warp `slab` owns edge slots [16*slab, 16*slab+16) of the current tile and the matching 16-column
+// stripe of the group's A buffer, so producer -> GEMM -> epilogue chains need only __syncwarp();
+// the group meets on a named barrier only where a target's edge segment may span stripes.
+__device__ __forceinline__ void group_sync(int grp) {
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(GTHREADS) : "memory");
 }
 
-// sin/cos Fourier features of one scalar per edge into A rows [0, 64):
-// GaussianFourierProjection.forward, SDE_model_2D_to_3D.py:64-66  (x * W * 2 * pi, fp32, in that order)
-__device__ __forceinline__ void fill_fourier(float* A, const float* __restrict__ xs, const float* __restrict__ W) {
-    const int edge = threadIdx.x & (TE - 1);
-    const int w0 = threadIdx.x >> 7;  // 0..3
-    const float x = xs[edge];
-#pragma unroll 2
-    for (int it = 0; it < 8; ++it) {
-        const int w = w0 + 4 * it;
-        const float arg = __fmul_rn(__fmul_rn(__fmul_rn(x, W[w]), 2.0f), 3.14159274101257324f);
-        float s, co;
-        sincos_reduced(arg, s, co);
-        A[w * LDA + edge] = s;
-        A[(32 + w) * LDA + edge] = co;
+struct TileInfo {
+    int ta, tb, ea, ne;  // first / end target (chunk-local), first edge (chunk-local), #edges
+};
+__device__ __forceinline__ TileInfo tile_info(const Chunk& c, int t) {
+    const int* rowl = c.si + SI_ROWL;
+    const int* ttgt = c.si + SI_TTGT;
+    TileInfo ti;
+    ti.ta = ttgt[t];
+    ti.tb = ttgt[t + 1];
+    ti.ea = rowl[ti.ta];
+    ti.ne = rowl[ti.tb] - ti.ea;
+    return ti;
+}
+
+// warp-private bookkeeping: lanes 0..15 resolve (source, target) of their slot by bisection on rowptr
+__device__ __forceinline__ void slot_edges(const Chunk& c, const int32_t* __restrict__ src_g, const TileInfo& ti,
+                                           int slab, int lane, int* esrc, int* etgt) {
+    if (lane < 16) {
+        const int* rowl = c.si + SI_ROWL;
+        const int slot = slab * 16 + lane;
+        int sj = 0, tg = 0;
+        if (slot < ti.ne) {
+            const int e = ti.ea + slot;
+            int lo = ti.ta, hi = ti.tb;  // largest i in [ta, tb) with rowl[i] <= e
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (rowl[mid] <= e) lo = mid; else hi = mid;
+            }
+            tg = lo;
+            sj = src_g[c.edge0 + e] - c.node0;
+        }
+        esrc[slot] = sj;
+        etgt[slot] = tg;
     }
+    __syncwarp();
+}
+
+// copy the warp's 16-column stripe of a [32][LDA] tile from global into its smem stripe (4 x 16 B per lane)
+__device__ __forceinline__ void load_stripe_async(float* stripe, const float* __restrict__ tile_stripe, int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int chunk = lane + 32 * i, k = chunk >> 2, c4 = (chunk & 3) * 4;
+        cp_async16(stripe + k * LDA + c4, tile_stripe + k * LDA + c4);
+    }
+    cp_async_commit();
 }
 
 // ---------------------------------------------------------------------------------------
 // Phase E0: per-edge attribute  edge_attr = input_mlp(gfp(d)) * e2d + project([sin,cos,emb_i,emb_j])
 // SDE_model_2D_to_3D.py:402-432.  coff_mlp (a bare Linear) is folded into project.layers.0 on the
 // host (MOLSDE_P_H_W), so the hidden layer accumulates directly over the four Fourier blocks.
+// Entirely warp-private: no block- or group-level barrier inside the tile loop.
 // ---------------------------------------------------------------------------------------
 __device__ __noinline__ void phase_edge_features(const Chunk c, const float* __restrict__ blob,
                                                  const int32_t* __restrict__ src_g, const float* __restrict__ e2d_tiles,
                                                  float* __restrict__ scratch) {
     float* sm = c.sm;
     float* W = sm + S_Q;  // E0 weights staged over the (currently dead) q/k/v region
-    float* A = sm + S_A;
-    float* EA = sm + S_M;   // e2d tile in, edge_attr tile out  [32][LDA]
-    float* geo = sm + S_L;  // [7][TE]: d, ci0, ci2, cj0, cj2, psin, pcos
     const float* pos = sm + S_POS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m0 = (warp & 7) * 16, n0 = (warp >> 3) * 16;
+    const int grp = warp >> 3, slab = warp & 7;
     const int g = lane >> 2, t4 = lane & 3;
+    float* A = sm + S_A + grp * TILE_FLOATS + slab * 16;   // stripe: element (k, r) at A[k*LDA + r]
+    float* geo = sm + S_L + grp * (TE * 8) + slab * 112;    // [7][16]: d, ci0, ci2, cj0, cj2, psin, pcos
+    int* esrc = c.si + SI_ESRC + grp * TE;
+    int* etgt = c.si + SI_ETGT + grp * TE;
     stage_async(W, blob, MOLSDE_P_E0_END);
     cp_async_wait<0>();
     __syncthreads();
-    for (int t = 0; t < c.ntiles; ++t) {
-        int ta, tb, ea;
-        stage_async(EA, e2d_tiles + static_cast<size_t>(c.tile0 + t) * TILE_FLOATS, TILE_FLOATS);
-        const int ne = build_tile_edges(c, src_g, t, ta, tb, ea);
-        __syncthreads();
-        if (tid < TE) {
+    for (int t = grp; t < c.ntiles; t += GROUPS) {
+        const TileInfo ti = tile_info(c, t);
+        slot_edges(c, src_g, ti, slab, lane, esrc, etgt);
+        // this thread's 16 elements of the e2d tile (rows g, g+8; columns nb*8 + 2*t4 + j), fetched early
+        const float* e2d_t = e2d_tiles + static_cast<size_t>(c.tile0 + t) * TILE_FLOATS + slab * 16;
+        float e2[4][4];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+                    e2[nb][2 * rr + j] = __ldg(e2d_t + (nb * 8 + 2 * t4 + j) * LDA + g + 8 * rr);
+        if (lane < 16) {
+            const int slot = slab * 16 + lane;
             float gq[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (tid < ne) {
-                const float* pr = pos + 3 * (c.si + SI_ESRC)[tid];  // row = source j
-                const float* pc = pos + 3 * (c.si + SI_ETGT)[tid];  // col = target i
+            if (slot < ti.ne) {
+                const float* pr = pos + 3 * esrc[slot];  // row = source j
+                const float* pc = pos + 3 * etgt[slot];  // col = target i
                 const Frame f = coord2basis(pr, pc);
                 // coff = edge_basis @ r  (:417-418), |.| on component 1 (:419-420)
                 const float ci0 = dot3_rn(f.dx, f.dy, f.dz, pr[0], pr[1], pr[2]);
@@ -271,62 +304,74 @@ __device__ __noinline__ void phase_edge_features(const Chunk c, const float* __r
                 gq[0] = f.dist; gq[1] = ci0; gq[2] = ci2; gq[3] = cj0; gq[4] = cj2; gq[5] = psin; gq[6] = pcos;
             }
 #pragma unroll
-            for (int q = 0; q < 7; ++q) geo[q * TE + tid] = gq[q];
+            for (int q = 0; q < 7; ++q) geo[q * 16 + lane] = gq[q];
         }
-        __syncthreads();
-        // ---- edge_attr_3D_invariant = input_mlp(gfp_dist(d))  (:409-410) ----
-        float inv[2][4], h[2][4], fr[2][4];
-        zero_frag(inv);
-        fill_fourier(A, geo, W + MOLSDE_P_GFP_DIST_W);
-        __syncthreads();
-        mma_gemm<2, LDA, LD32>(A + m0, W + MOLSDE_P_IN_W + n0, 64, lane, inv);
-        __syncthreads();
-        // ---- hidden of `project` accumulated over gfp(ci0), gfp(ci2), gfp(cj0), gfp(cj2)  (:427-430) ----
-        zero_frag(h);
+        __syncwarp();
+        // Fourier block 0 (distance) feeds input_mlp (:409-410); blocks 1..4 (ci0, ci2, cj0, cj2) feed the fused
+        // hidden layer of `project` (:427-430).  Each block: sin half -> GEMM(K=32), cos half -> GEMM(K=32).
+        float inv[4][4], acc[4][4];
+        zero_frag(acc);
+        const int fe = lane & 15, wbase = (lane >> 4) * 16;
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-            fill_fourier(A, geo + (1 + q) * TE, W + MOLSDE_P_GFP_COFF_W);
-            __syncthreads();
-            mma_gemm<2, LDA, LD32>(A + m0, W + MOLSDE_P_H_W + q * 64 * LD32 + n0, 64, lane, h);
-            __syncthreads();
+        for (int blk = 0; blk < 5; ++blk) {
+            const float x = geo[blk * 16 + fe];
+            const float* Wf = W + (blk == 0 ? MOLSDE_P_GFP_DIST_W : MOLSDE_P_GFP_COFF_W) + wbase;
+            const float* Wm = (blk == 0) ? W + MOLSDE_P_IN_W : W + MOLSDE_P_H_W + (blk - 1) * 64 * LD32;
+            float cs[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                // GaussianFourierProjection.forward, :64-66  (x * W * 2 * pi, fp32, in that order)
+                const float arg = __fmul_rn(__fmul_rn(__fmul_rn(x, Wf[i]), 2.0f), 3.14159274101257324f);
+                float sn;
+                sincos_reduced(arg, sn, cs[i]);
+                A[(wbase + i) * LDA + fe] = sn;
+            }
+            __syncwarp();
+            mma_gemm<4, LDA, LD32>(A, Wm, 32, lane, acc);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) A[(wbase + i) * LDA + fe] = cs[i];
+            __syncwarp();
+            mma_gemm<4, LDA, LD32>(A, Wm + 32 * LD32, 32, lane, acc);
+            __syncwarp();
+            if (blk == 0) {
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { inv[nb][q] = acc[nb][q]; acc[nb][q] = 0.0f; }
+            }
         }
 #pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
+        for (int nb = 0; nb < 4; ++nb)
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int col = n0 + nb * 8 + 2 * t4 + j;
+                const int col = nb * 8 + 2 * t4 + j;
                 const float bh = W[MOLSDE_P_H_B + col], ws = W[MOLSDE_P_H_WSIN + col], wc = W[MOLSDE_P_H_WCOS + col];
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
-                    const int row = m0 + g + 8 * rr;
-                    const float v = h[nb][2 * rr + j] + bh + geo[5 * TE + row] * ws + geo[6 * TE + row] * wc;
-                    A[col * LDA + row] = silu_fast(v);
+                    const int r = g + 8 * rr;
+                    const float v = acc[nb][2 * rr + j] + bh + geo[5 * 16 + r] * ws + geo[6 * 16 + r] * wc;
+                    A[col * LDA + r] = silu_fast(v);
                 }
             }
-        __syncthreads();
-        zero_frag(fr);
-        mma_gemm<2, LDA, LD32>(A + m0, W + MOLSDE_P_P1_W + n0, 32, lane, fr);
-        cp_async_wait<0>();
-        __syncthreads();
-        // ---- edge_attr = inv3d * e2d + frame  (:432), in place over the e2d tile ----
+        __syncwarp();
+        zero_frag(acc);
+        mma_gemm<4, LDA, LD32>(A, W + MOLSDE_P_P1_W, 32, lane, acc);
+        // ---- edge_attr = inv3d * e2d + frame  (:432) -> scratch tile (own stripe) ----
+        float* sc_t = scratch + static_cast<size_t>(t) * TILE_FLOATS + slab * 16;
 #pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
+        for (int nb = 0; nb < 4; ++nb)
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int col = n0 + nb * 8 + 2 * t4 + j;
+                const int col = nb * 8 + 2 * t4 + j;
                 const float bi = W[MOLSDE_P_IN_B + col], bf = W[MOLSDE_P_P1_B + col];
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int idx = col * LDA + m0 + g + 8 * rr;
-                    EA[idx] = fmaf(inv[nb][2 * rr + j] + bi, EA[idx], fr[nb][2 * rr + j] + bf);
-                }
+                for (int rr = 0; rr < 2; ++rr)
+                    sc_t[col * LDA + g + 8 * rr] = fmaf(inv[nb][2 * rr + j] + bi, e2[nb][2 * rr + j], acc[nb][2 * rr + j] + bf);
             }
-        __syncthreads();
-        float* sc_t = scratch + static_cast<size_t>(t) * TILE_FLOATS;
-        for (int i = tid * 4; i < TILE_FLOATS; i += NTHREADS * 4)
-            *reinterpret_cast<float4*>(sc_t + i) = *reinterpret_cast<const float4*>(EA + i);
-        __syncthreads();
+        __syncwarp();
     }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -361,41 +406,42 @@ __device__ __noinline__ void node_qkv(const Chunk c) {
 __device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __restrict__ src_g,
                                             const float* __restrict__ scratch) {
     float* sm = c.sm;
-    float* A = sm + S_A;
-    float* Mm = sm + S_M;
-    float* L = sm + S_L;
-    float* smax = sm + S_MS;
-    float* ssum = sm + S_MS + TE * 8;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = warp >> 3, slab = warp & 7, gt = tid & (GTHREADS - 1);
+    const int g = lane >> 2, t4 = lane & 3;
+    float* Ag = sm + S_A + grp * TILE_FLOATS;
+    float* stripe = Ag + slab * 16;
+    float* Mm = Ag;  // [TE][LDM] slot-major messages, written only after the group's GEMMs are done
+    float* L = sm + S_L + grp * (TE * 8);
+    float* smax = sm + S_MS + grp * (2 * TE * 8);
+    float* ssum = smax + TE * 8;
     float* Q = sm + S_Q;
     const float* Kk = sm + S_K;
     const float* V = sm + S_V;
     const float* Wg = sm + S_WG;
     const int* rowl = c.si + SI_ROWL;
-    const int* esrc = c.si + SI_ESRC;
-    const int* etgt = c.si + SI_ETGT;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m0 = (warp & 7) * 16, n0 = (warp >> 3) * 16;
-    const int g = lane >> 2, t4 = lane & 3;
-    for (int t = 0; t < c.ntiles; ++t) {
-        int ta, tb, ea;
-        stage_async(A, scratch + static_cast<size_t>(t) * TILE_FLOATS, TILE_FLOATS);
-        const int ne = build_tile_edges(c, src_g, t, ta, tb, ea);
+    int* esrc = c.si + SI_ESRC + grp * TE;
+    int* etgt = c.si + SI_ETGT + grp * TE;
+    for (int t = grp; t < c.ntiles; t += GROUPS) {
+        const TileInfo ti = tile_info(c, t);
+        load_stripe_async(stripe, scratch + static_cast<size_t>(t) * TILE_FLOATS + slab * 16, lane);
+        slot_edges(c, src_g, ti, slab, lane, esrc, etgt);
         cp_async_wait<0>();
-        __syncthreads();
-        // e = lin_edge(edge_attr); this thread: rows m0+g, m0+g+8; columns n0 + nb*8 + 2*t4 + {0,1}
-        float e[2][4];
+        __syncwarp();
+        // e = lin_edge(edge_attr); this thread: slots 16*slab + g, +8; columns nb*8 + 2*t4 + {0,1}
+        float e[4][4];
         zero_frag(e);
-        mma_gemm<2, LDA, LD32>(A + m0, Wg + MOLSDE_G_WE + n0, 32, lane, e);
+        mma_gemm<4, LDA, LD32>(stripe, Wg + MOLSDE_G_WE, 32, lane, e);
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            const int s = m0 + g + 8 * rr;
-            const bool live = s < ne;
-            const int sj = esrc[s], ti = etgt[s];
+            const int s = slab * 16 + g + 8 * rr;
+            const bool live = s < ti.ne;
+            const int sj = esrc[s], tg = etgt[s];
 #pragma unroll
-            for (int nb = 0; nb < 2; ++nb) {
-                const int col = n0 + nb * 8 + 2 * t4;
+            for (int nb = 0; nb < 4; ++nb) {
+                const int col = nb * 8 + 2 * t4;
                 const float2 k2 = *reinterpret_cast<const float2*>(Kk + sj * 32 + col);
-                const float2 q2 = *reinterpret_cast<const float2*>(Q + ti * 32 + col);
+                const float2 q2 = *reinterpret_cast<const float2*>(Q + tg * 32 + col);
                 const float2 v2 = *reinterpret_cast<const float2*>(V + sj * 32 + col);
                 // alpha = (q_i . (k_j + e)) / sqrt(C): a head (4 columns) is split over the lane pair (t4, t4^1)
                 float part = fmaf(q2.y, k2.y + e[nb][2 * rr + 1], q2.x * (k2.x + e[nb][2 * rr]));
@@ -405,12 +451,12 @@ __device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __rest
                 e[nb][2 * rr + 1] += v2.y;
             }
         }
-        __syncthreads();
+        group_sync(grp);
         // per (target, head): max and sum(exp) over the target's contiguous edge segment
-        const int ntg = tb - ta;
-        for (int p = tid; p < ntg * 8; p += NTHREADS) {
-            const int i = ta + (p >> 3), hd = p & 7;
-            const int s0 = rowl[i] - ea, s1 = rowl[i + 1] - ea;
+        const int ntg = ti.tb - ti.ta;
+        for (int p = gt; p < ntg * 8; p += GTHREADS) {
+            const int i = ti.ta + (p >> 3), hd = p & 7;
+            const int s0 = rowl[i] - ti.ea, s1 = rowl[i + 1] - ti.ea;
             float m = -CUDART_INF_F;
             for (int s = s0; s < s1; ++s) m = fmaxf(m, L[s * 8 + hd]);
             float z = 0.0f;
@@ -418,29 +464,30 @@ __device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __rest
             smax[p] = m;
             ssum[p] = z;
         }
-        __syncthreads();
+        group_sync(grp);
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            const int s = m0 + g + 8 * rr;
-            if (s < ne) {
+            const int s = slab * 16 + g + 8 * rr;
+            if (s < ti.ne) {
+                const int pb = (etgt[s] - ti.ta) * 8;
 #pragma unroll
-                for (int nb = 0; nb < 2; ++nb) {
-                    const int col = n0 + nb * 8 + 2 * t4;
-                    const int p = (etgt[s] - ta) * 8 + (col >> 2);
-                    const float a = __fdividef(__expf(L[s * 8 + (col >> 2)] - smax[p]), ssum[p] + 1e-16f);
-                    *reinterpret_cast<float2*>(Mm + s * 32 + col) = make_float2(e[nb][2 * rr] * a, e[nb][2 * rr + 1] * a);
+                for (int nb = 0; nb < 4; ++nb) {
+                    const int col = nb * 8 + 2 * t4, hd = col >> 2;
+                    const float a = __fdividef(__expf(L[s * 8 + hd] - smax[pb + hd]), ssum[pb + hd] + 1e-16f);
+                    Mm[s * LDM + col] = e[nb][2 * rr] * a;
+                    Mm[s * LDM + col + 1] = e[nb][2 * rr + 1] * a;
                 }
             }
         }
-        __syncthreads();
-        for (int p = tid; p < ntg * 32; p += NTHREADS) {
-            const int i = ta + (p >> 5), col = p & 31;
-            const int s0 = rowl[i] - ea, s1 = rowl[i + 1] - ea;
+        group_sync(grp);
+        for (int p = gt; p < ntg * 32; p += GTHREADS) {
+            const int i = ti.ta + (p >> 5), col = p & 31;
+            const int s0 = rowl[i] - ti.ea, s1 = rowl[i + 1] - ti.ea;
             float acc = 0.0f;
-            for (int s = s0; s < s1; ++s) acc += Mm[s * 32 + col];
+            for (int s = s0; s < s1; ++s) acc += Mm[s * LDM + col];
             Q[i * 32 + col] = acc;
         }
-        __syncthreads();
+        group_sync(grp);
     }
 }
 
@@ -562,44 +609,48 @@ __device__ __noinline__ void phase_basis(const Chunk c, const float* __restrict_
                                          const float* __restrict__ scratch, int module) {
     float* sm = c.sm;
     float* Wb = sm + S_Q;  // staged over q/k/v (dead between GAT blocks)
-    float* A = sm + S_A;
-    float* dynp = sm + S_L;  // [2][TE][4] partial dyn coefficients of the two column halves
-    float* mix = sm + S_MS;  // [TE][4]
     const float* XT = sm + S_XT;
     const float* pos = sm + S_POS;
     float* grad = sm + S_GRAD;
     const int* rowl = c.si + SI_ROWL;
-    const int* esrc = c.si + SI_ESRC;
-    const int* etgt = c.si + SI_ETGT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m0 = (warp & 7) * 16, nh = warp >> 3, n0 = nh * 64;
+    const int grp = warp >> 3, slab = warp & 7, gt = tid & (GTHREADS - 1);
     const int g = lane >> 2, t4 = lane & 3;
+    float* stripe = sm + S_A + grp * TILE_FLOATS + slab * 16;
+    float* mix = sm + S_MS + grp * (2 * TE * 8);  // [TE][4]
+    int* esrc = c.si + SI_ESRC + grp * TE;
+    int* etgt = c.si + SI_ETGT + grp * TE;
     stage_async(Wb, blob + MOLSDE_P_BASIS0 + module * MOLSDE_P_BASIS_SZ, MOLSDE_P_BASIS_SZ);
     cp_async_wait<0>();
     __syncthreads();
-    for (int t = 0; t < c.ntiles; ++t) {
-        int ta, tb, ea;
-        stage_async(A + 32 * LDA, scratch + static_cast<size_t>(t) * TILE_FLOATS, TILE_FLOATS);
-        const int ne = build_tile_edges(c, src_g, t, ta, tb, ea);
-        __syncthreads();
-        {   // rows 0..31: h_row + h_col
-            const int edge = tid & (TE - 1), k0 = (tid >> 7) * 8;
-            const int sj = esrc[edge], ti = etgt[edge];
-            const bool live = edge < ne;
+    for (int t = grp; t < c.ntiles; t += GROUPS) {
+        const TileInfo ti = tile_info(c, t);
+        slot_edges(c, src_g, ti, slab, lane, esrc, etgt);
+        {   // K rows 0..31 of edge_feature: h_row + h_col   (:154-155)
+            const int fe = lane & 15, kb = (lane >> 4) * 16;
+            const int slot = slab * 16 + fe;
+            const int sj = esrc[slot], tg = etgt[slot];
+            const bool live = slot < ti.ne;
 #pragma unroll
-            for (int k = k0; k < k0 + 8; ++k) A[k * LDA + edge] = live ? XT[k * LDX + sj] + XT[k * LDX + ti] : 0.0f;
+            for (int i = 0; i < 16; ++i)
+                stripe[(kb + i) * LDA + fe] = live ? XT[(kb + i) * LDX + sj] + XT[(kb + i) * LDX + tg] : 0.0f;
         }
-        cp_async_wait<0>();
-        __syncthreads();
-        float acc[8][4];
+        __syncwarp();
+        float acc[16][4];
         zero_frag(acc);
-        mma_gemm<8, LDA, LD128>(A + m0, Wb + MOLSDE_B_W1 + n0, 64, lane, acc);
+        mma_gemm<16, LDA, LD128>(stripe, Wb + MOLSDE_B_W1, 32, lane, acc);
+        __syncwarp();
+        // K rows 32..63: edge_attr stripe
+        load_stripe_async(stripe, scratch + static_cast<size_t>(t) * TILE_FLOATS + slab * 16, lane);
+        cp_async_wait<0>();
+        __syncwarp();
+        mma_gemm<16, LDA, LD128>(stripe, Wb + MOLSDE_B_W1 + 32 * LD128, 32, lane, acc);
         float part[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb)
+        for (int nb = 0; nb < 16; ++nb)
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int col = n0 + nb * 8 + 2 * t4 + j;
+                const int col = nb * 8 + 2 * t4 + j;
                 const float b1 = Wb[MOLSDE_B_B1 + col];
                 const float w0 = Wb[MOLSDE_B_W2 + col], w1 = Wb[MOLSDE_B_W2 + 128 + col], w2 = Wb[MOLSDE_B_W2 + 256 + col];
 #pragma unroll
@@ -617,30 +668,33 @@ __device__ __noinline__ void phase_basis(const Chunk c, const float* __restrict_
                 float v = part[rr][o];
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if (t4 == 0) dynp[(nh * TE + m0 + g + 8 * rr) * 4 + o] = v;
+                part[rr][o] = v;
             }
-        __syncthreads();
-        if (tid < ne) {
-            const Frame f = coord2basis(pos + 3 * esrc[tid], pos + 3 * etgt[tid]);
-            const float d0 = dynp[tid * 4] + dynp[(TE + tid) * 4] + Wb[MOLSDE_B_B2];
-            const float d1 = dynp[tid * 4 + 1] + dynp[(TE + tid) * 4 + 1] + Wb[MOLSDE_B_B2 + 1];
-            const float d2 = dynp[tid * 4 + 2] + dynp[(TE + tid) * 4 + 2] + Wb[MOLSDE_B_B2 + 2];
-            mix[tid * 4 + 0] = d0 * f.dx + d1 * f.cx + d2 * f.vx;
-            mix[tid * 4 + 1] = d0 * f.dy + d1 * f.cy + d2 * f.vy;
-            mix[tid * 4 + 2] = d0 * f.dz + d1 * f.cz + d2 * f.vz;
+        if (t4 < 2) {  // quad lane 0 finishes slot g, lane 1 slot g+8
+            const int slot = slab * 16 + g + 8 * t4;
+            if (slot < ti.ne) {
+                const Frame f = coord2basis(pos + 3 * esrc[slot], pos + 3 * etgt[slot]);
+                const float d0 = (t4 ? part[1][0] : part[0][0]) + Wb[MOLSDE_B_B2];
+                const float d1 = (t4 ? part[1][1] : part[0][1]) + Wb[MOLSDE_B_B2 + 1];
+                const float d2 = (t4 ? part[1][2] : part[0][2]) + Wb[MOLSDE_B_B2 + 2];
+                mix[slot * 4 + 0] = d0 * f.dx + d1 * f.cx + d2 * f.vx;
+                mix[slot * 4 + 1] = d0 * f.dy + d1 * f.cy + d2 * f.vy;
+                mix[slot * 4 + 2] = d0 * f.dz + d1 * f.cz + d2 * f.vz;
+            }
         }
-        __syncthreads();
-        const int ntg = tb - ta;
-        for (int p = tid; p < ntg * 3; p += NTHREADS) {
-            const int i = ta + p / 3, ax = p % 3;
-            const int s0 = rowl[i] - ea, s1 = rowl[i + 1] - ea;
-            float s = 0.0f;
-            for (int q = s0; q < s1; ++q) s += mix[q * 4 + ax];
-            s = __fdiv_rn(s, static_cast<float>(max(s1 - s0, 1)));  // aggr='mean'
-            grad[i * 3 + ax] = (module == 0) ? s : grad[i * 3 + ax] + s;
+        group_sync(grp);
+        const int ntg = ti.tb - ti.ta;
+        for (int p = gt; p < ntg * 3; p += GTHREADS) {
+            const int i = ti.ta + p / 3, ax = p % 3;
+            const int s0 = rowl[i] - ti.ea, s1 = rowl[i + 1] - ti.ea;
+            float sacc = 0.0f;
+            for (int q = s0; q < s1; ++q) sacc += mix[q * 4 + ax];
+            sacc = __fdiv_rn(sacc, static_cast<float>(max(s1 - s0, 1)));  // aggr='mean'
+            grad[i * 3 + ax] = (module == 0) ? sacc : grad[i * 3 + ax] + sacc;
         }
-        __syncthreads();
+        group_sync(grp);
     }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -665,6 +719,7 @@ __device__ __noinline__ void score_eval(const Chunk c, const float* __restrict__
             node_qkv(c);
             __syncthreads();
             gat_edge_phase(c, src_g, scratch);
+            __syncthreads();
             node_update(c, conv == 0);
             __syncthreads();
         }
