@@ -124,6 +124,8 @@ typedef struct molsde_plan {
     const int32_t* tile_tgt_ptr;   /* [T+1] */
     const int32_t* rowptr;         /* [N+1] */
     const int32_t* src;            /* [E]   */
+    const int32_t* chunk_order;    /* [C] or NULL: order in which the persistent PC kernel hands out chunks
+                                      (host sorts by descending tile count = longest-processing-time first) */
 } molsde_plan;
 
 /* edge_2D_emb in eval mode (BatchNorm running stats), SDE_model_2D_to_3D.py:265,405-407:

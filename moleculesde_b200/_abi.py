@@ -44,7 +44,8 @@ class MolsdeError(RuntimeError):
 
 class Plan(Structure):
     _fields_ = [("num_chunks", c_int32), ("num_tiles", c_int32), ("N", c_int64), ("E", c_int64),
-                ("chunk_tile_ptr", c_void_p), ("tile_tgt_ptr", c_void_p), ("rowptr", c_void_p), ("src", c_void_p)]
+                ("chunk_tile_ptr", c_void_p), ("tile_tgt_ptr", c_void_p), ("rowptr", c_void_p), ("src", c_void_p),
+                ("chunk_order", c_void_p)]
 
 
 class Params(Structure):

@@ -113,8 +113,7 @@ __device__ __forceinline__ void sincos_reduced(float x, float& s, float& c) {
 // truncation of lo stay below 2^-20 relative.
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -122,6 +121,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 template <int NB, int LDA_, int LDW_>
 __device__ __forceinline__ void mma_gemm(const float* __restrict__ As, const float* __restrict__ Ws, int K, int lane,
                                          float (&c)[NB][4]) {
+    static_assert(NB % 4 == 0, "n-blocks are processed four at a time");
     const int g = lane >> 2, t = lane & 3;
     const float* ap = As + t * LDA_ + g;
     const float* wp = Ws + t * LDW_ + g;
@@ -135,14 +135,23 @@ __device__ __forceinline__ void mma_gemm(const float* __restrict__ As, const flo
             al[i] = __float_as_uint(av[i] - __uint_as_float(ah[i]));
         }
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-            const float b0 = wp[k0 * LDW_ + nb * 8], b1 = wp[(k0 + 4) * LDW_ + nb * 8];
-            const uint32_t bh0 = tf32_hi(b0), bh1 = tf32_hi(b1);
-            const uint32_t bl0 = __float_as_uint(b0 - __uint_as_float(bh0));
-            const uint32_t bl1 = __float_as_uint(b1 - __uint_as_float(bh1));
-            mma_tf32(c[nb], al, bh0, bh1);
-            mma_tf32(c[nb], ah, bl0, bl1);
-            mma_tf32(c[nb], ah, bh0, bh1);
+        for (int nq = 0; nq < NB / 4; ++nq) {
+            // four independent accumulators per pass: the three split terms of one accumulator are 4 MMAs apart
+            uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float b0 = wp[k0 * LDW_ + (nq * 4 + q) * 8], b1 = wp[(k0 + 4) * LDW_ + (nq * 4 + q) * 8];
+                bh[q][0] = tf32_hi(b0);
+                bh[q][1] = tf32_hi(b1);
+                bl[q][0] = __float_as_uint(b0 - __uint_as_float(bh[q][0]));
+                bl[q][1] = __float_as_uint(b1 - __uint_as_float(bh[q][1]));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mma_tf32(c[nq * 4 + q], al, bh[q][0], bh[q][1]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mma_tf32(c[nq * 4 + q], ah, bl[q][0], bl[q][1]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mma_tf32(c[nq * 4 + q], ah, bh[q][0], bh[q][1]);
         }
     }
 }
@@ -843,8 +852,8 @@ sde2d3d_pc_kernel(molsde_plan plan, const float* __restrict__ blob, const float*
         __syncthreads();
         if (tid == 0) misc[0] = atomicAdd(work_counter, 1);
         __syncthreads();
-        const int chunk = misc[0];
-        if (chunk >= plan.num_chunks) break;
+        if (misc[0] >= plan.num_chunks) break;
+        const int chunk = plan.chunk_order ? plan.chunk_order[misc[0]] : misc[0];  // longest groups first
         if (!load_chunk(c, plan, chunk, status_flag)) continue;
         const int n3 = c.n * 3;
         const size_t g3 = static_cast<size_t>(c.node0) * 3;

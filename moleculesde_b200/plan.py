@@ -22,6 +22,7 @@ class TilePlan:
     csr: CSR
     chunk_tile_ptr: torch.Tensor  # int32 [C+1]
     tile_tgt_ptr: torch.Tensor    # int32 [T+1]
+    chunk_order: torch.Tensor     # int32 [C], chunks by descending tile count (work-queue order of the PC kernel)
     num_chunks: int
     num_tiles: int
     max_chunk_tiles: int
@@ -31,7 +32,7 @@ class TilePlan:
     def as_struct(self) -> _abi.Plan:
         return _abi.Plan(self.num_chunks, self.num_tiles, self.N, self.E, self.chunk_tile_ptr.data_ptr(),
                          self.tile_tgt_ptr.data_ptr(), self.csr.rowptr.data_ptr(),
-                         self.csr.col.data_ptr() if self.E else None)
+                         self.csr.col.data_ptr() if self.E else None, self.chunk_order.data_ptr())
 
 
 def _tiles_of_range(rowptr: np.ndarray, a: int, b: int, te: int) -> List[int]:
@@ -87,6 +88,9 @@ def build_plan(csr: CSR, node_ptr: torch.Tensor, groups: Optional[Sequence[int]]
         max_tiles = max(max_tiles, len(ts))
     tile_starts.append(N)
     dev = csr.rowptr.device
+    tiles_per_chunk = np.diff(np.asarray(chunk_tile_ptr, dtype=np.int64))
+    order = np.argsort(-tiles_per_chunk, kind="stable").astype(np.int32)
     return TilePlan(csr, torch.tensor(chunk_tile_ptr, dtype=torch.int32, device=dev),
                     torch.tensor(tile_starts, dtype=torch.int32, device=dev),
+                    torch.from_numpy(order).to(dev),
                     len(chunk_bounds) - 1, len(tile_starts) - 1, max_tiles, N, E)
