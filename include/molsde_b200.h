@@ -92,12 +92,13 @@ int molsde_csr_by_target_fill(const int64_t* edge_index, int64_t E, const int32_
                               int32_t* perm, void* stream);
 
 /* ------------------------------------------------------------------------------------
- * Dense node-level linear layer  Y[M,N] = act(X[M,K] . W[N,K]^T + b)   (fp32 FFMA)
- * Replaces torch.nn.Linear on node-major tensors (SDE_model_2D_to_3D.py:264,375; schnet.py).
- * act: 0 none, 1 relu, 2 silu, 3 shifted softplus.
+ * Dense node-level linear layer  Y[M,N] = act(X[M,K] . W[N,K]^T + b) (+ R)   (fp32 FFMA)
+ * Replaces torch.nn.Linear on node-major tensors (SDE_model_2D_to_3D.py:264,375; schnet.py:99-101,
+ * 163-167,189-191).  act: 0 none, 1 relu, 2 silu, 3 shifted softplus (schnet.py:210-216).
+ * R (nullable, leading dim ldr) is added after the activation (residual, schnet.py:97).
  * ---------------------------------------------------------------------------------- */
 int molsde_linear(const float* X, int64_t M, int32_t K, int64_t ldx, const float* W, const float* b,
-                  int32_t N, float* Y, int64_t ldy, int32_t act, void* stream);
+                  int32_t N, float* Y, int64_t ldy, int32_t act, const float* R, int64_t ldr, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * SDEModel2Dto3D_02 (Geom3D/models/MoleculeSDE/SDE_model_2D_to_3D.py:252-445)
@@ -163,6 +164,34 @@ int molsde_sde2d3d_pc_sample(const molsde_plan* plan, const molsde_sde2d3d_param
                              const float* noise_pred, float* pos_out, float* pos_mean_out, float* scratch,
                              int64_t scratch_floats, int32_t* work_counter, int32_t* status_flag,
                              void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * SchNet (Geom3D/models/schnet.py:16-216), forward
+ * ---------------------------------------------------------------------------------- */
+
+/* CFConv message passing of one InteractionBlock (schnet.py:185-195) fused with GaussianSmearing
+ * (:205-207), the filter MLP and the cosine cutoff:  agg[i,:] = sum_{j->i} x[j,:] * W_ij,
+ *   W_ij = (mlp.2 . ssp . mlp.0)(exp(coeff (d_ij - mu_k)^2)) * 0.5 (cos(d_ij pi / cutoff) + 1).
+ * plan: tiles over the radius-graph CSR (tile_tgt_ptr / rowptr / src; chunks unused);
+ * x [N,128] = conv.lin1(h); w1t [56][136] / w2t [128][136] k-major, zero padded; mu [56] offsets. */
+int molsde_schnet_cfconv(const molsde_plan* plan, const float* pos, const float* x, const float* w1t, const float* b1,
+                         const float* w2t, const float* b2, const float* mu, int32_t num_gaussians, float coeff,
+                         float cutoff, float* agg, void* stream);
+/* out[r,:] = table[idx[r],:]  (Embedding lookup, schnet.py:89) */
+int molsde_gather_rows(const float* table, const int64_t* idx, int64_t rows, int32_t cols, float* out, void* stream);
+/* per-segment sum (mean != 0: mean with count clamped to 1) in ascending row order (readout, schnet.py:115) */
+int molsde_segment_reduce(const float* x, const int32_t* ptr, int32_t segments, int32_t cols, int32_t mean, float* out,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * do_CL, metric EBM_node_dot_prod (examples/util.py:52-68), forward:
+ *   pred_pos[r] = <X[r],Y[r]>/T, pred_neg[r] = <X[r],Y[perm[r]]>/T,
+ *   loss_acc[0] = BCEWithLogits(pred_pos,1) + BCEWithLogits(pred_neg,0) (means), loss_acc[1] = CL_acc.
+ * workspace: >= 4 * min(ceil(N/8), 592) floats.
+ * ---------------------------------------------------------------------------------- */
+int molsde_ebm_node_dot(const float* X, const float* Y, const int64_t* perm, int64_t N, int32_t D, float T,
+                        float* pred_pos, float* pred_neg, float* loss_acc, float* workspace, int64_t workspace_floats,
+                        void* stream);
 
 #ifdef __cplusplus
 }

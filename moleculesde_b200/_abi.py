@@ -35,6 +35,7 @@ EXPORTS = [
     "molsde_linear",
     "molsde_edge2d_emb_eval", "molsde_sde2d3d_score", "molsde_sde2d3d_scratch_floats", "molsde_tile_floats",
     "molsde_sde2d3d_pc_sample",
+    "molsde_schnet_cfconv", "molsde_gather_rows", "molsde_segment_reduce", "molsde_ebm_node_dot",
 ]
 
 
@@ -84,7 +85,13 @@ def lib() -> ctypes.CDLL:
     L.molsde_csr_by_target_fill.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                             c_void_p, c_void_p]
     L.molsde_linear.argtypes = [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_void_p,
-                                c_int64, c_int32, c_void_p]
+                                c_int64, c_int32, c_void_p, c_int64, c_void_p]
+    L.molsde_schnet_cfconv.argtypes = [POINTER(Plan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_int32, c_float, c_float, c_void_p, c_void_p]
+    L.molsde_gather_rows.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    L.molsde_segment_reduce.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+    L.molsde_ebm_node_dot.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_int64, c_void_p]
     L.molsde_edge2d_emb_eval.argtypes = [POINTER(Plan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.molsde_sde2d3d_score.argtypes = [POINTER(Plan), POINTER(Params), c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_int64, c_void_p, c_void_p]

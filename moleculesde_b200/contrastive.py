@@ -1,0 +1,36 @@
+"""`do_CL` / `dual_CL` of `examples/util.py:22-79` for the pretraining metric `EBM_node_dot_prod`
+(forward: loss and accuracy) through `molsde_ebm_node_dot`."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from ._abi import check, lib, ptr, require_device, stream_ptr
+
+
+def do_CL(X: torch.Tensor, Y: torch.Tensor, args, neg_index: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, float]:
+    """Reference signature `do_CL(X, Y, args)`; `neg_index` injects the `torch.randperm(len(Y))` draw
+    (`util.py:55`, CPU generator in the reference)."""
+    if args.CL_similarity_metric != "EBM_node_dot_prod":
+        raise NotImplementedError("only EBM_node_dot_prod (the pretraining metric, README.md:86-94) is built")
+    require_device(X)
+    X = X.detach().float().contiguous()
+    Y = Y.detach().float().contiguous()
+    N, D = X.shape
+    if neg_index is None:
+        neg_index = torch.randperm(N)
+    perm = neg_index.to(X.device).long().contiguous()
+    pred_pos = torch.empty(N, dtype=torch.float32, device=X.device)
+    pred_neg = torch.empty(N, dtype=torch.float32, device=X.device)
+    out = torch.empty(2, dtype=torch.float32, device=X.device)
+    ws = torch.empty(4 * 592, dtype=torch.float32, device=X.device)
+    check(lib().molsde_ebm_node_dot(ptr(X), ptr(Y), ptr(perm), N, D, float(args.T), ptr(pred_pos), ptr(pred_neg), ptr(out),
+                                    ptr(ws), ws.numel(), stream_ptr(X)), "ebm_node_dot")
+    return out[0], float(out[1].item())  # the reference also syncs for CL_acc (.cpu().item(), util.py:68)
+
+
+def dual_CL(X, Y, args, neg_index_1=None, neg_index_2=None):
+    l1, a1 = do_CL(X, Y, args, neg_index_1)
+    l2, a2 = do_CL(Y, X, args, neg_index_2)
+    return (l1 + l2) / 2, (a1 + a2) / 2

@@ -19,7 +19,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 __global__ void __launch_bounds__(256)
 linear_kernel(const float* __restrict__ X, int64_t M, int K, int64_t ldx, const float* __restrict__ W,
-              const float* __restrict__ bias, int N, float* __restrict__ Y, int64_t ldy, int act) {
+              const float* __restrict__ bias, int N, float* __restrict__ Y, int64_t ldy, int act,
+              const float* __restrict__ R, int64_t ldr) {
     __shared__ float Xs[BK][BM + 4];
     __shared__ float Ws[BK][BN + 4];
     const int tid = threadIdx.x;
@@ -65,8 +66,9 @@ linear_kernel(const float* __restrict__ X, int64_t M, int K, int64_t ldx, const 
         for (int j = 0; j < 4; ++j) {
             int gn = n0 + tx * 4 + j;
             if (gn >= N) continue;
-            float v = acc[i][j] + (bias ? bias[gn] : 0.0f);
-            Y[gm * ldy + gn] = apply_act(v, act);
+            float v = apply_act(acc[i][j] + (bias ? bias[gn] : 0.0f), act);
+            if (R) v += R[gm * ldr + gn];  // residual (h = h + interaction(h), schnet.py:97)
+            Y[gm * ldy + gn] = v;
         }
     }
 }
@@ -76,10 +78,10 @@ linear_kernel(const float* __restrict__ X, int64_t M, int K, int64_t ldx, const 
 using namespace molsde;
 
 extern "C" int molsde_linear(const float* X, int64_t M, int32_t K, int64_t ldx, const float* W, const float* b,
-                             int32_t N, float* Y, int64_t ldy, int32_t act, void* stream) {
+                             int32_t N, float* Y, int64_t ldy, int32_t act, const float* R, int64_t ldr, void* stream) {
     if (!X || !W || !Y || M < 0 || K <= 0 || N <= 0) return MOLSDE_ERR_INVALID;
     if (M == 0) return MOLSDE_OK;
     dim3 grid((N + BN - 1) / BN, static_cast<unsigned>((M + BM - 1) / BM));
-    linear_kernel<<<grid, 256, 0, as_stream(stream)>>>(X, M, K, ldx, W, b, N, Y, ldy, act);
+    linear_kernel<<<grid, 256, 0, as_stream(stream)>>>(X, M, K, ldx, W, b, N, Y, ldy, act, R, ldr);
     return check_launch("linear");
 }
