@@ -222,9 +222,6 @@ def run_b200(args):
     ei_h, batch_h = hb.edge_index.pin_memory(), hb.batch.pin_memory()
     model = make_model(dev)
 
-    class DevBatch:
-        pass
-
     def stage_inputs():
         """H2D of one step's inputs + graph construction (extended graph, CSR, tile plan)."""
         d = hb.__class__()
@@ -293,10 +290,8 @@ def run_b200(args):
     d2h = out_h.numel() * 4
 
     # ---------------- reduce over ranks (max time) ----------------
-    tt = torch.tensor([elapsed_ms, pc_ms, e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    elapsed_ms, pc_ms, e2e_s = [float(x) for x in tt.tolist()]
+    from moleculesde_b200.dist_util import max_over_ranks
+    elapsed_ms, pc_ms, e2e_s = max_over_ranks([elapsed_ms, pc_ms, e2e_s], dev)
     ms_per_step = elapsed_ms / args.steps
     value = world * n_conf / (ms_per_step * 1e-3)
     e2e_value = world * n_conf / e2e_s

@@ -1,0 +1,59 @@
+"""world_size-2 gloo test (CPU) of the multi-rank plumbing used by bench.py and the samplers:
+group sharding without overlap, max-over-ranks timing, aggregate throughput."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from moleculesde_b200.dist_util import max_over_ranks, shard_groups, sum_over_ranks
+    a, b = shard_groups(1025, rank, world)
+    owned = torch.zeros(1025)
+    owned[a:b] = 1
+    dist.all_reduce(owned)
+    assert torch.all(owned == 1), "every sampling group is owned by exactly one rank"
+    per_rank_ms = 100.0 + 50.0 * rank  # rank 1 is slower
+    (ms,) = max_over_ranks([per_rank_ms], "cpu")
+    (conf,) = sum_over_ranks([float(b - a) * 10], "cpu")
+    if rank == 0:
+        out.put((ms, conf))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_timing():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ms, conf = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ms == 150.0       # max over ranks, not mean
+    assert conf == 10250.0   # whole-job conformers = sum over ranks
+
+
+def test_shard_groups_balanced():
+    from moleculesde_b200.dist_util import shard_groups
+    for n, w in ((1024, 8), (1025, 8), (3, 8), (0, 2)):
+        ranges = [shard_groups(n, r, w) for r in range(w)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in ranges]
+        assert max(sizes) - min(sizes) <= 1
