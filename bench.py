@@ -309,9 +309,17 @@ def run_b200(args):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = bytes_launch / (pc_ms * 1e-3) / 1e9
+        achieved_gbs = bytes_launch / (pc_ms * 1e-3) / 1e9
         fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
         tflops = flops_launch / (pc_ms * 1e-3) / 1e12
+        tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0  # derived: dense TF32 = bf16 / 2
+        traffic = None
+        try:  # dram bytes of one launch of this exact configuration, from an ncu capture committed under profiles/
+            tr = json.load(open(os.path.join(REPO, "profiles", "r1_pc_traffic.json")))
+            if tr.get("molecules") == args.molecules and tr.get("pc_steps") == args.pc_steps and tr.get("repeat") == args.repeat:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -321,13 +329,19 @@ def run_b200(args):
                     "includes": "pinned-host H2D of representation/positions/edge_index/batch, extended-graph + CSR + tile plan, "
                                 "invariants, fused PC kernel, D2H of pos_mean"},
             "gpu_launches": args.steps * 4,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                         "kernel": "sde2d3d_pc_kernel", "kernel_ms": pc_ms,
-                         "note": "algorithmic bytes = layer-granular figure of SURVEY 8(d); the fused kernel keeps node state in smem "
-                                 "and is FP32-FFMA bound, see roofline_fp32"},
+            "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tflops / tf32_peak,
+                         "traffic": traffic, "kernel": "sde2d3d_pc_kernel", "kernel_ms": pc_ms,
+                         "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (derived dense TF32)" if peaks
+                                         else "fallback 1400/2"),
+                         "note": "achieved = ALGORITHMIC FLOPs 2*(34,624 E_x + 24,576 N) per score eval x 2000 evals / kernel time. "
+                                 "The kernel issues 3x that on the tensor pipe (3xTF32 split for fp32-grade accuracy) through "
+                                 "legacy mma.sync (measured 476 MAC/clk/SM, profiles/r1_ubench_mma_rate.txt). traffic = ncu dram "
+                                 "bytes of one launch: node/edge state stays in shared memory for all 1000 steps."},
+            "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                             "note": "north_star's HBM view with the layer-granular algorithmic bytes of SURVEY 8(d): "
+                                     "(156 N + 132 E_x + 4(N+1) + 266k) per eval + 48 N per step; small by construction (fused)"},
             "roofline_fp32": {"bound": "fp32_ffma", "achieved": tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tflops / fp32_peak,
-                              "note": "derived peak = 148 SM x 128 lanes x 2 x max SM clock; FLOPs = reference-form 2*(34,624 E_x + 24,576 N) per score eval"},
+                              "note": "same algorithmic FLOPs against the derived fp32 FFMA peak 148 SM x 128 lanes x 2 x max clock"},
             "atoms": N, "edges": Ex, "groups": int(group_ptr.numel() - 1),
         }
         if not args.no_cpu_baseline:

@@ -370,3 +370,179 @@ def dual_cl(X: Tensor, Y: Tensor, T: float, neg_index_1: Tensor, neg_index_2: Te
     l1, a1 = do_cl_ebm_node_dot_prod(X, Y, T, neg_index_1)
     l2, a2 = do_cl_ebm_node_dot_prod(Y, X, T, neg_index_2)
     return (l1 + l2) / 2, (a1 + a2) / 2
+
+
+# ----------------------------------------------------------------------------
+# dense 3D -> 2D score model: SDE_model_3D_to_2D_node_adj_dense.py, invariant_scorenetwork_dense.py,
+# layers/edge_network_dense.py, layers/node_network_dense.py, SDE_dense.py
+# ----------------------------------------------------------------------------
+def mask_x(x: Tensor, flags: Tensor) -> Tensor:
+    """`SDE_model_3D_to_2D_node_adj_dense.py:559-562`."""
+    return x * flags[:, :, None]
+
+
+def mask_adjs(adjs: Tensor, flags: Tensor) -> Tensor:
+    """`SDE_model_3D_to_2D_node_adj_dense.py:543-556` (B x N x N or B x C x N x N)."""
+    if adjs.dim() == 4:
+        flags = flags.unsqueeze(1)
+    return adjs * flags.unsqueeze(-1) * flags.unsqueeze(-2)
+
+
+def node_flags(adj: Tensor, eps: float = 1e-5) -> Tensor:
+    """`:523-529`."""
+    return torch.abs(adj).sum(-1).gt(eps).to(torch.float32)
+
+
+def dense_gcn(weight: Tensor, bias: Tensor, x: Tensor, adj: Tensor) -> Tensor:
+    """NodeNetwork_dense.forward (DenseGCNConv clone, add_loop=True, weight stored [in,out]),
+    `layers/node_network_dense.py:46-85`."""
+    n = adj.size(-1)
+    adj = adj.clone()
+    idx = torch.arange(n)
+    adj[:, idx, idx] = 1
+    out = torch.matmul(x, weight)
+    dis = adj.sum(dim=-1).clamp(min=1).pow(-0.5)
+    adj = dis.unsqueeze(-1) * adj * dis.unsqueeze(-2)
+    return torch.matmul(adj, out) + bias
+
+
+def edge_layer(sd, prefix: str, x: Tensor, adj: Tensor, num_heads: int):
+    """EdgeLayer.forward with conv='MLP', `layers/edge_network_dense.py:55-82`."""
+    Q = mlp(sd, prefix + ".func_q", x, torch.tanh)
+    K = mlp(sd, prefix + ".func_k", x, torch.tanh)
+    V = dense_gcn(sd[prefix + ".func_v.weight"], sd[prefix + ".func_v.bias"], x, adj)
+    attn_dim = Q.size(-1) // 2  # hidden_dims = [2*attn_dim, 2*attn_dim] (:46)
+    dim_split = attn_dim // num_heads
+    Q_ = torch.cat(Q.split(dim_split, 2), 0)
+    K_ = torch.cat(K.split(dim_split, 2), 0)
+    A = torch.tanh(Q_.bmm(K_.transpose(1, 2)) / math.sqrt(dim_split))
+    A = A.view(-1, *adj.shape).mean(dim=0)
+    return V, (A + A.transpose(-1, -2)) / 2
+
+
+def edge_network_dense(sd, prefix: str, x: Tensor, adj: Tensor, flags: Tensor, num_heads: int = 4):
+    """EdgeNetwork_dense.forward, `layers/edge_network_dense.py:105-128`."""
+    n_in = adj.size(1)
+    masks, xs = [], []
+    for c in range(n_in):
+        V, A = edge_layer(sd, f"{prefix}.attn.{c}", x, adj[:, c], num_heads)
+        masks.append(A.unsqueeze(-1))
+        xs.append(V)
+    x_out = torch.tanh(mask_x(mlp(sd, prefix + ".multi_channel", torch.cat(xs, dim=-1), F.elu), flags))
+    mlp_in = torch.cat([torch.cat(masks, dim=-1), adj.permute(0, 2, 3, 1)], dim=-1)
+    shape = mlp_in.shape
+    out = mlp(sd, prefix + ".mlp", mlp_in.reshape(-1, shape[-1]), F.elu)
+    _adj = out.view(shape[0], shape[1], shape[2], -1).permute(0, 3, 1, 2)
+    _adj = _adj + _adj.transpose(-1, -2)
+    return x_out, mask_adjs(_adj, flags)
+
+
+def edge_score_network_dense(sd, prefix: str, x: Tensor, adj: Tensor, flags: Tensor, c_init: int = 2, num_layers: int = 4):
+    """EdgeScoreNetwork_dense.forward, `invariant_scorenetwork_dense.py:74-93` (pow_tensor :28-37)."""
+    chans = [adj.unsqueeze(1)]
+    a = adj.clone()
+    for _ in range(c_init - 1):
+        a = torch.bmm(a, adj)
+        chans.append(a.unsqueeze(1))
+    adjc = torch.cat(chans, dim=1)
+    adj_list = [adjc]
+    for li in range(num_layers):
+        x, adjc = edge_network_dense(sd, f"{prefix}.layers.{li}", x, adjc, flags)
+        adj_list.append(adjc)
+    adjs = torch.cat(adj_list, dim=1).permute(0, 2, 3, 1)
+    score = mlp(sd, prefix + ".final", adjs, F.silu).view(*adjs.shape[:-1])
+    n = adjs.size(1)
+    score = score * (torch.ones(n, n) - torch.eye(n)).unsqueeze(0)
+    return mask_adjs(score, flags)
+
+
+def node_score_network_dense(sd, prefix: str, x: Tensor, adj: Tensor, flags: Tensor, depth: int = 4):
+    """NodeScoreNetwork_dense.forward, `invariant_scorenetwork_dense.py:118-131`."""
+    x_list = [x]
+    for li in range(depth):
+        x = torch.tanh(dense_gcn(sd[f"{prefix}.layers.{li}.weight"], sd[f"{prefix}.layers.{li}.bias"], x, adj))
+        x_list.append(x)
+    xs = torch.cat(x_list, dim=-1)
+    out = mlp(sd, prefix + ".final", xs, F.silu).view(adj.shape[0], adj.shape[1], -1)
+    return mask_x(out, flags)
+
+
+class DenseVESDE(VESDE):
+    """`SDE_dense.py:176-233`: per-graph t [B]."""
+
+    def marginal_prob(self, x, t):
+        return x, self.sigma_min * (self.sigma_max / self.sigma_min) ** t
+
+
+class DenseVPSDE(VPSDE):
+    """`SDE_dense.py:110-173`."""
+
+    def marginal_prob(self, x, t):
+        lmc = -0.25 * t ** 2 * (self.beta_1 - self.beta_0) - 0.5 * t * self.beta_0
+        return torch.exp(lmc[:, None, None]) * x, torch.sqrt(1.0 - torch.exp(2.0 * lmc))
+
+    def discretize(self, x, t):
+        timestep = (t * (self.N - 1) / self.T).long()
+        beta, alpha = self.discrete_betas[timestep], self.alphas[timestep]
+        return torch.sqrt(alpha)[:, None, None] * x - x, torch.sqrt(beta)
+
+
+def make_dense_sde(kind: str, beta_min: float, beta_max: float, N: int):
+    return DenseVESDE(beta_min, beta_max, N) if kind == "VE" else DenseVPSDE(beta_min, beta_max, N)
+
+
+def embed_3d2d(sd, rep_dense: Tensor, x: Tensor) -> Tensor:
+    """`embedding_3D(h3D) + embedding_X(x)`, `SDE_model_3D_to_2D_node_adj_dense.py:156`."""
+    return _lin(sd, "embedding_3D", rep_dense) + _lin(sd, "embedding_X", x)
+
+
+def score_3d2d(sd, sde, which: str, emb: Tensor, adj: Tensor, flags: Tensor, t: Tensor) -> Tensor:
+    """`get_score_fn(...)(x, adj, flags, t)`, `:68-99`: -net(x, adj, flags) / std[:, None, None]."""
+    if which == "adj":
+        out = edge_score_network_dense(sd, "edge_score_network", emb, adj, flags)
+    else:
+        out = node_score_network_dense(sd, "node_score_network", emb, adj, flags)
+    std = sde.marginal_prob(torch.zeros_like(adj), t)[1]
+    return -out / std[:, None, None]
+
+
+def dense_inputs(h3d: Tensor, z: Tensor, edge_index: Tensor, bond_type: Tensor, batch: Tensor):
+    """to_dense_adj / to_dense_batch prologue of forward, `:118-134`: returns (adj, rep_dense, z_dense, flags)."""
+    edge_attr = bond_type.float() + 1
+    B = int(batch.max().item()) + 1
+    num_nodes = R.scatter(torch.ones_like(batch), batch, 0, B, "sum")
+    nmax = int(num_nodes.max().item())
+    adj = R.to_dense_adj(edge_index, batch, edge_attr=edge_attr, max_num_nodes=nmax)
+    rep, _ = R.to_dense_batch(h3d, batch, max_num_nodes=nmax)
+    zd, _ = R.to_dense_batch(z, batch, max_num_nodes=nmax)
+    return adj, rep, zd, node_flags(adj)
+
+
+def loss_3d2d(sd, sde_x, sde_adj, h3d: Tensor, z: Tensor, edge_index: Tensor, bond_type: Tensor, batch: Tensor,
+              t_half: Tensor, noise_adj: Tensor, noise_x: Tensor, N: int = 1000, num_class: int = 119,
+              anneal_power: float = 0.0):
+    """SDEModel3Dto2D_node_adj_dense.forward (noise_on_one_hot, reduce_mean=True, continuous), `:101-179`,
+    with the three random draws injected (`randint` :112, `randn_like(adj)` :135/533, `randn_like(one_hot)` :144)."""
+    adj, rep, zd, flags = dense_inputs(h3d, z, edge_index, bond_type, batch)
+    B = adj.size(0)
+    t = torch.cat([t_half, N - t_half - 1], dim=0)[:B]
+    t = t / N * (1 - EPSILON) + EPSILON
+    z_adj = noise_adj.triu(1)
+    z_adj = mask_adjs(z_adj + z_adj.transpose(-1, -2), flags)  # gen_noise(sym=True) :532-538
+    mean_adj, std_adj = sde_adj.marginal_prob(adj, t)
+    p_adj = mask_adjs(mean_adj + std_adj[:, None, None] * z_adj, flags)
+    one_hot = F.one_hot(zd, num_class).float()
+    z_x = mask_x(noise_x, flags)
+    mean_x, std_x = sde_x.marginal_prob(one_hot, t)
+    p_x = mask_x(mean_x + std_x[:, None, None] * z_x, flags)
+    emb = embed_3d2d(sd, rep, p_x)
+    s_adj = score_3d2d(sd, sde_adj, "adj", emb, p_adj, flags, t)
+    s_x = score_3d2d(sd, sde_x, "x", emb, p_adj, flags, t)
+    lx = torch.square(s_x + z_x)
+    la = torch.square(s_adj + z_adj)
+    if anneal_power != 0:
+        lx = lx * (std_x ** anneal_power)[:, None, None]
+        la = la * (std_adj ** anneal_power)[:, None, None]
+    lx = torch.mean(lx.reshape(B, -1), dim=-1)
+    la = torch.mean(la.reshape(B, -1), dim=-1)
+    return torch.mean(lx), torch.mean(la)
