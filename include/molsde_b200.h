@@ -94,11 +94,13 @@ int molsde_csr_by_target_fill(const int64_t* edge_index, int64_t E, const int32_
 /* ------------------------------------------------------------------------------------
  * Dense node-level linear layer  Y[M,N] = act(X[M,K] . W[N,K]^T + b) (+ R)   (fp32 FFMA)
  * Replaces torch.nn.Linear on node-major tensors (SDE_model_2D_to_3D.py:264,375; schnet.py:99-101,
- * 163-167,189-191).  act: 0 none, 1 relu, 2 silu, 3 shifted softplus (schnet.py:210-216).
+ * 163-167,189-191; layers/common.py:31-40).  act: 0 none, 1 relu, 2 silu, 3 shifted softplus
+ * (schnet.py:210-216), 4 tanh, 5 elu.  rowscale (nullable, [M]) multiplies the pre-activation (mask_x);
  * R (nullable, leading dim ldr) is added after the activation (residual, schnet.py:97).
  * ---------------------------------------------------------------------------------- */
 int molsde_linear(const float* X, int64_t M, int32_t K, int64_t ldx, const float* W, const float* b,
-                  int32_t N, float* Y, int64_t ldy, int32_t act, const float* R, int64_t ldr, void* stream);
+                  int32_t N, float* Y, int64_t ldy, int32_t act, const float* R, int64_t ldr, const float* rowscale,
+                  void* stream);
 
 /* ------------------------------------------------------------------------------------
  * SDEModel2Dto3D_02 (Geom3D/models/MoleculeSDE/SDE_model_2D_to_3D.py:252-445)
@@ -192,6 +194,57 @@ int molsde_segment_reduce(const float* x, const int32_t* ptr, int32_t segments, 
 int molsde_ebm_node_dot(const float* X, const float* Y, const int64_t* perm, int64_t N, int32_t D, float T,
                         float* pred_pos, float* pred_neg, float* loss_acc, float* workspace, int64_t workspace_floats,
                         void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dense 3D->2D score networks (SDE_model_3D_to_2D_node_adj_dense.py, invariant_scorenetwork_dense.py,
+ * layers/edge_network_dense.py, layers/node_network_dense.py) -- building blocks, Nm <= 64.
+ * Layouts: x [B,Nm,F]; adj [B,Nm,Nm]; adjacency stacks [B,C,Nm,Nm]; pair features [B,Nm,Nm,C].
+ * ---------------------------------------------------------------------------------- */
+/* to_dense_batch (:130-131): out[b,a,:] = x[node_ptr[b]+a,:] or 0 */
+int molsde_to_dense_batch(const float* x, const int32_t* node_ptr, int32_t B, int32_t Nm, int32_t F, float* out, int64_t ldo,
+                          void* stream);
+/* to_dense_adj (:129): adj[b,i,j] += val[e] + val_add  (val float or int64; :121 uses bond_type + 1) */
+int molsde_to_dense_adj(const int64_t* edge_index, int64_t E, const float* val, const int64_t* val_i64, float val_add,
+                        const int32_t* node_ptr, int32_t B, int32_t Nm, float* adj, void* stream);
+/* node_flags (:523-529): flags[b,i] = sum_j |adj[b,i,j]| > eps */
+int molsde_node_flags(const float* adj, int32_t B, int32_t Nm, float eps, float* flags, void* stream);
+/* Y[:, g*No:(g+1)*No] = act(X[:, g*Ki:(g+1)*Ki] . W[g]^T + b[g]), W [G][No][Ki] */
+int molsde_grouped_linear(const float* X, int64_t rows, int64_t ldx, const float* W, const float* b, int32_t G, int32_t Ki,
+                          int32_t No, float* Y, int64_t ldy, int32_t act, void* stream);
+/* pow_tensor with c_init = 2 (invariant_scorenetwork_dense.py:28-37) */
+int molsde_dense_pow2(const float* adj, int32_t B, int32_t Nm, float* adjc, float* allc, int32_t ld_all, int32_t all_off,
+                      void* stream);
+/* NodeNetwork_dense.forward (node_network_dense.py:46-85) for C channels at once */
+int molsde_dense_gcn(const float* adjc, int64_t adj_stride_b, int64_t adj_stride_c, int32_t B, int32_t C, int32_t Nm,
+                     const float* xw, int64_t ldxw, const float* bias, int32_t Fo, float* out, int64_t ldo, int32_t out_off,
+                     int32_t act, void* stream);
+/* EdgeLayer tanh-attention + symmetrisation (edge_network_dense.py:66-80) -> pair[..., c], adjc copy -> pair[..., C+c] */
+int molsde_dense_attn(const float* Q, const float* K, int64_t ldq, int32_t W, int32_t ds, const float* adjc, int32_t B,
+                      int32_t C, int32_t Nm, float* pair, void* stream);
+/* (m + m^T) masked (edge_network_dense.py:124-126) -> next adjacency stack + all-channels buffer */
+int molsde_dense_pair_post(const float* m, const float* flags, int32_t B, int32_t Nm, int32_t Co, float* adjc_next, float* allc,
+                           int32_t ld_all, int32_t all_off, void* stream);
+/* zero diagonal, mask, optional per-graph scale (invariant_scorenetwork_dense.py:86-91; get_score_fn :83,93) */
+int molsde_dense_edge_final(const float* raw, const float* flags, const float* scale, int32_t B, int32_t Nm, float* out,
+                            void* stream);
+
+/* perturbation prologue / loss epilogue of SDEModel3Dto2D_node_adj_dense.forward (:134-152,160-179) and the elementwise
+ * steps of the 3D->2D PC sampler (examples/pretrain_MoleculeSDE_inference_3D_to_2D_VE_VP.py:167-252) */
+int molsde_dense_sym_noise(const float* raw, const float* flags, int32_t B, int32_t Nm, float* z, void* stream);
+int molsde_dense_perturb_adj(const float* x, const float* z, const float* flags, const float* coef, const float* stdv, int32_t B,
+                             int32_t Nm, float* out, void* stream);
+int molsde_dense_perturb_onehot(const int64_t* zidx, const float* raw, const float* flags, const float* coef, const float* stdv,
+                                int32_t B, int32_t Nm, int32_t K, float* zx, float* px, void* stream);
+/* per-graph reductions over M contiguous floats: mode 0 Frobenius norm of a; mode 1 mean((a+b)^2) * w[g] */
+int molsde_graph_reduce(const float* a, const float* b, const float* w, int32_t B, int64_t M, int32_t mode, float* out,
+                        void* stream);
+int molsde_langevin_step(const float* gnorm, const float* nnorm, const float* alpha, int32_t B, float snr, float* step,
+                         void* stream);
+int molsde_langevin_update(const float* x, const float* grad, const float* noise, const float* step, int32_t B, int64_t M,
+                           float seps, float* x_new, float* x_mean, void* stream);
+int molsde_reverse_update(const float* x, const float* score, const float* z, const float* sqrt_alpha, const float* G, int32_t B,
+                          int64_t M, float* x_new, float* x_mean, void* stream);
+int molsde_mask_rows(const float* x, const float* flags, int64_t rows, int32_t cols, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,10 @@ EXPORTS = [
     "molsde_edge2d_emb_eval", "molsde_sde2d3d_score", "molsde_sde2d3d_scratch_floats", "molsde_tile_floats",
     "molsde_sde2d3d_pc_sample",
     "molsde_schnet_cfconv", "molsde_gather_rows", "molsde_segment_reduce", "molsde_ebm_node_dot",
+    "molsde_to_dense_batch", "molsde_to_dense_adj", "molsde_node_flags", "molsde_grouped_linear", "molsde_dense_pow2",
+    "molsde_dense_gcn", "molsde_dense_attn", "molsde_dense_pair_post", "molsde_dense_edge_final",
+    "molsde_dense_sym_noise", "molsde_dense_perturb_adj", "molsde_dense_perturb_onehot", "molsde_graph_reduce",
+    "molsde_langevin_step", "molsde_langevin_update", "molsde_reverse_update", "molsde_mask_rows",
 ]
 
 
@@ -85,7 +89,32 @@ def lib() -> ctypes.CDLL:
     L.molsde_csr_by_target_fill.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                             c_void_p, c_void_p]
     L.molsde_linear.argtypes = [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_void_p,
-                                c_int64, c_int32, c_void_p, c_int64, c_void_p]
+                                c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p]
+    L.molsde_to_dense_batch.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p]
+    L.molsde_to_dense_adj.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_int32, c_void_p,
+                                      c_void_p]
+    L.molsde_node_flags.argtypes = [c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p]
+    L.molsde_grouped_linear.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                        c_int64, c_int32, c_void_p]
+    L.molsde_dense_pow2.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
+    L.molsde_dense_gcn.argtypes = [c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_int32,
+                                   c_void_p, c_int64, c_int32, c_int32, c_void_p]
+    L.molsde_dense_attn.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32,
+                                    c_void_p, c_void_p]
+    L.molsde_dense_pair_post.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32,
+                                         c_void_p]
+    L.molsde_dense_edge_final.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
+    L.molsde_dense_sym_noise.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
+    L.molsde_dense_perturb_adj.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
+    L.molsde_dense_perturb_onehot.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                              c_void_p, c_void_p, c_void_p]
+    L.molsde_graph_reduce.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]
+    L.molsde_langevin_step.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p]
+    L.molsde_langevin_update.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_float, c_void_p, c_void_p,
+                                         c_void_p]
+    L.molsde_reverse_update.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p,
+                                        c_void_p]
+    L.molsde_mask_rows.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
     L.molsde_schnet_cfconv.argtypes = [POINTER(Plan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int32, c_float, c_float, c_void_p, c_void_p]
     L.molsde_gather_rows.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]

@@ -13,6 +13,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
         case 1: return fmaxf(v, 0.0f);
         case 2: return silu_f(v);
         case 3: return softplus_f(v) - 0.69314718246459961f;  // float32(log 2), schnet.py:213
+        case 4: return tanhf(v);
+        case 5: return v > 0.0f ? v : expm1f(v);  // F.elu
         default: return v;
     }
 }
@@ -20,7 +22,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 __global__ void __launch_bounds__(256)
 linear_kernel(const float* __restrict__ X, int64_t M, int K, int64_t ldx, const float* __restrict__ W,
               const float* __restrict__ bias, int N, float* __restrict__ Y, int64_t ldy, int act,
-              const float* __restrict__ R, int64_t ldr) {
+              const float* __restrict__ R, int64_t ldr, const float* __restrict__ rowscale) {
     __shared__ float Xs[BK][BM + 4];
     __shared__ float Ws[BK][BN + 4];
     const int tid = threadIdx.x;
@@ -66,7 +68,9 @@ linear_kernel(const float* __restrict__ X, int64_t M, int K, int64_t ldx, const 
         for (int j = 0; j < 4; ++j) {
             int gn = n0 + tx * 4 + j;
             if (gn >= N) continue;
-            float v = apply_act(acc[i][j] + (bias ? bias[gn] : 0.0f), act);
+            float v = acc[i][j] + (bias ? bias[gn] : 0.0f);
+            if (rowscale) v *= rowscale[gm];  // mask_x before the activation (edge_network_dense.py:117-118)
+            v = apply_act(v, act);
             if (R) v += R[gm * ldr + gn];  // residual (h = h + interaction(h), schnet.py:97)
             Y[gm * ldy + gn] = v;
         }
@@ -78,10 +82,11 @@ linear_kernel(const float* __restrict__ X, int64_t M, int K, int64_t ldx, const 
 using namespace molsde;
 
 extern "C" int molsde_linear(const float* X, int64_t M, int32_t K, int64_t ldx, const float* W, const float* b,
-                             int32_t N, float* Y, int64_t ldy, int32_t act, const float* R, int64_t ldr, void* stream) {
+                             int32_t N, float* Y, int64_t ldy, int32_t act, const float* R, int64_t ldr, const float* rowscale,
+                             void* stream) {
     if (!X || !W || !Y || M < 0 || K <= 0 || N <= 0) return MOLSDE_ERR_INVALID;
     if (M == 0) return MOLSDE_OK;
     dim3 grid((N + BN - 1) / BN, static_cast<unsigned>((M + BM - 1) / BM));
-    linear_kernel<<<grid, 256, 0, as_stream(stream)>>>(X, M, K, ldx, W, b, N, Y, ldy, act, R, ldr);
+    linear_kernel<<<grid, 256, 0, as_stream(stream)>>>(X, M, K, ldx, W, b, N, Y, ldy, act, R, ldr, rowscale);
     return check_launch("linear");
 }

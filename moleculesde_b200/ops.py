@@ -7,24 +7,40 @@ import torch
 
 from ._abi import check, lib, ptr, require_device, stream_ptr
 
-ACT = {None: 0, "none": 0, "relu": 1, "silu": 2, "ssp": 3}
+ACT = {None: 0, "none": 0, "relu": 1, "silu": 2, "ssp": 3, "tanh": 4, "elu": 5}
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
-           residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Y = act(x @ weight.T + bias) (+ residual) through `molsde_linear` (fp32)."""
+           residual: Optional[torch.Tensor] = None, rowscale: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Y = act((x @ weight.T + bias) * rowscale[:,None]) (+ residual) through `molsde_linear` (fp32).
+    `x` may be any tensor whose last dim is K with unit stride and uniform row stride (views into wider
+    buffers are fine); `out` may be such a view too."""
     require_device(x)
-    x = x.detach().float().contiguous()
+    K = x.size(-1)
+    assert x.stride(-1) == 1
+    x2 = x if x.dim() == 2 else x.reshape(-1, K) if x.is_contiguous() else x.flatten(0, -2)
+    M, ldx = x2.size(0), x2.stride(0)
     w = weight.detach().float().contiguous()
     b = None if bias is None else bias.detach().float().contiguous()
-    M, K = x.shape
     N = w.size(0)
-    assert w.size(1) == K
-    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
-    r = None if residual is None else residual.detach().float().contiguous()
-    check(lib().molsde_linear(ptr(x), M, K, K, ptr(w), ptr(b), N, ptr(y), N, ACT[act], ptr(r), N if r is not None else 0,
-                              stream_ptr(x)), "linear")
-    return y
+    assert w.size(1) == K and x2.dtype == torch.float32
+    if out is None:
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    else:
+        y = out if out.dim() == 2 else out.flatten(0, -2)
+        assert y.size(0) == M and y.size(1) == N and y.stride(1) == 1
+    r2, ldr = None, 0
+    if residual is not None:
+        r2 = residual if residual.dim() == 2 else residual.flatten(0, -2)
+        assert r2.stride(1) == 1
+        ldr = r2.stride(0)
+    rs = None if rowscale is None else rowscale.reshape(-1).contiguous()
+    check(lib().molsde_linear(x2.data_ptr(), M, K, ldx, ptr(w), ptr(b), N, y.data_ptr(), y.stride(0), ACT[act],
+                              None if r2 is None else r2.data_ptr(), ldr, ptr(rs), stream_ptr(x)), "linear")
+    if out is not None:
+        return out
+    return y if x.dim() == 2 else y.view(*x.shape[:-1], N)
 
 
 def gather_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:

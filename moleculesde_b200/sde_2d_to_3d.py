@@ -273,10 +273,10 @@ class SDEModel2Dto3D_02(nn.Module):
         N, dev, s = h.size(0), h.device, stream_ptr(h)
         nattr = torch.empty(N, _abi.HID, dtype=torch.float32, device=dev)
         check(lib().molsde_linear(ptr(h), N, self.emb_dim, self.emb_dim, ptr(pk["w_node"]), ptr(pk["b_node"]), _abi.HID,
-                                  ptr(nattr), _abi.HID, 0, None, 0, s), "node_emb")
+                                  ptr(nattr), _abi.HID, 0, None, 0, None, s), "node_emb")
         uv = torch.empty(N, 2 * self.emb_dim, dtype=torch.float32, device=dev)
         check(lib().molsde_linear(ptr(h), N, self.emb_dim, self.emb_dim, ptr(pk["w_uv"]), ptr(pk["b_uv"]),
-                                  2 * self.emb_dim, ptr(uv), 2 * self.emb_dim, 0, None, 0, s), "edge_2D_emb.0")
+                                  2 * self.emb_dim, ptr(uv), 2 * self.emb_dim, 0, None, 0, None, s), "edge_2D_emb.0")
         e2d = torch.empty(max(prep.plan.num_tiles, 1) * _abi.TILE_FLOATS, dtype=torch.float32, device=dev)
         st = prep.plan.as_struct()
         check(lib().molsde_edge2d_emb_eval(ctypes.byref(st), ptr(uv), ptr(pk["w3t"]), ptr(pk["b3"]), ptr(e2d), s),

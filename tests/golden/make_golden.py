@@ -191,6 +191,53 @@ def main():
                      "calls": calls}
         out["sde2d3d_" + sde_type] = sec
 
+    # ---------------- dense 3D -> 2D (VE and VP): score networks, DSM losses, 2 PC sampler steps ----------------
+    h3d = out["schnet"]["h"]
+    for sde_type in ("VE", "VP"):
+        _, _, _, m32 = build_reference_models(R, sde_type)
+        m32.train()
+        log = []
+        with record_rng(log, NOISE_SEED + 5):
+            lx, la = m32(h3d, batch, continuous=True, train=True, reduce_mean=True, anneal_power=0)
+        sec = {"loss_x": lx.detach(), "loss_adj": la.detach(), "draws": [v for _, v in log]}
+        # score networks on a fixed perturbed state
+        from torch_geometric.utils import to_dense_adj, to_dense_batch
+        import Geom3D.models.MoleculeSDE.SDE_model_3D_to_2D_node_adj_dense as M32
+        m32.eval()
+        edge_attr = batch.edge_attr[:, 0].float() + 1
+        nmax = int(torch.bincount(batch.batch).max())
+        adj = to_dense_adj(batch.edge_index, batch.batch, edge_attr=edge_attr, max_num_nodes=nmax)
+        rep, _ = to_dense_batch(h3d, batch.batch, max_num_nodes=nmax)
+        flags = M32.node_flags(adj)
+        g = torch.Generator().manual_seed(NOISE_SEED + 6)
+        Bg = adj.size(0)
+        xs = M32.mask_x(torch.randn(Bg, nmax, 119, generator=g), flags)
+        za = torch.randn(Bg, nmax, nmax, generator=g).triu(1)
+        pa = M32.mask_adjs(adj + 0.5 * (za + za.transpose(-1, -2)), flags)
+        tt = torch.rand(Bg, generator=g) * 0.9 + 0.05
+        with torch.no_grad():
+            emb = m32.embedding_3D(rep) + m32.embedding_X(xs)
+            s_adj = m32.get_score_fn(m32.sde_adj, m32.edge_score_network, train=False)(emb, pa, flags, tt)
+            s_x = m32.get_score_fn(m32.sde_x, m32.node_score_network, train=False)(emb, pa, flags, tt)
+        sec.update({"x": xs, "adj": pa, "t": tt, "flags": flags, "score_adj": s_adj, "score_x": s_x, "nmax": nmax})
+        # sampler: lift node_adj_PC_generation + classes from the inference script (lines 95-252)
+        import abc
+        glb = {"torch": torch, "abc": abc, "trange": lambda a, b, **kw: range(a, min(b, 2)), "device": "cpu",
+               "args": types.SimpleNamespace(device="cpu"), "print": lambda *a, **k: None,
+               "to_dense_adj": to_dense_adj, "node_flags": M32.node_flags, "mask_x": M32.mask_x, "mask_adjs": M32.mask_adjs,
+               "gen_noise": M32.gen_noise}
+        from Geom3D.models.MoleculeSDE.SDE_sparse import VPSDE, VESDE, subVPSDE
+        glb.update(VPSDE=VPSDE, VESDE=VESDE, subVPSDE=subVPSDE)
+        refload._exec_slice(os.path.join(refload.REFERENCE_ROOT, "examples", "pretrain_MoleculeSDE_inference_3D_to_2D_VE_VP.py"),
+                            95, 252, glb)
+        log = []
+        with record_rng(log, NOISE_SEED + 7):
+            with torch.no_grad():
+                x, a, xm, am = glb["node_adj_PC_generation"](representation=rep, data=batch, SDE_model=m32, B=Bg, max_num_nodes=nmax,
+                                                             num_class_X=119, n_steps=1)
+        sec["pc"] = {"steps": 2, "draws": [v for _, v in log], "x": x, "adj": a, "x_mean": xm, "adj_mean": am}
+        out["sde3d2d_" + sde_type] = sec
+
     path = os.path.join(HERE, "golden_pcqm8.pt")
     torch.save(out, path)
     print("wrote", path, os.path.getsize(path) / 1e6, "MB")

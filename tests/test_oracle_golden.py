@@ -90,3 +90,22 @@ def test_pc_sampler_2d3d(golden, golden_batch):
             torch.testing.assert_close(sp, calls[2 * i + 1][2], rtol=1e-4, atol=1e-5)
         # free-running trajectory of the oracle stays on the reference's
         torch.testing.assert_close(pos_mean, pc["pos_mean"], rtol=1e-3, atol=1e-3)
+
+
+def test_dense_3d2d_oracle(golden, golden_batch):
+    _, batch = golden_batch
+    h3d = golden["schnet"]["h"]
+    for kind in ("VE", "VP"):
+        sec = golden["sde3d2d_" + kind]
+        sd = sd_from_manifest(golden["manifest"]["sde3d2d"], golden["meta"]["weight_seed"])
+        bmin = 0.1 if kind == "VE" else 0.2
+        sx, sa = O.make_dense_sde(kind, bmin, 1.0, 1000), O.make_dense_sde(kind, bmin, 1.0, 1000)
+        d = sec["draws"]
+        lx, la = O.loss_3d2d(sd, sx, sa, h3d, batch.x[:, 0], batch.edge_index, batch.edge_attr[:, 0], batch.batch, d[0], d[1], d[2])
+        torch.testing.assert_close(lx, sec["loss_x"], **TOL)
+        torch.testing.assert_close(la, sec["loss_adj"], **TOL)
+        adj0, rep, _, flags = O.dense_inputs(h3d, batch.x[:, 0], batch.edge_index, batch.edge_attr[:, 0], batch.batch)
+        assert torch.equal(flags, sec["flags"])
+        emb = O.embed_3d2d(sd, rep, sec["x"])
+        torch.testing.assert_close(O.score_3d2d(sd, sa, "adj", emb, sec["adj"], flags, sec["t"]), sec["score_adj"], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(O.score_3d2d(sd, sx, "x", emb, sec["adj"], flags, sec["t"]), sec["score_x"], rtol=1e-4, atol=1e-5)
