@@ -64,16 +64,25 @@ constexpr int SI_ROWL = 0;                   // [MAXN+1] edge offsets local to t
 constexpr int SI_TTGT = SI_ROWL + MAXN + 1;  // [MAXT+1] tile target boundaries local to the chunk
 constexpr int SI_ESRC = SI_TTGT + MAXT + 1;  // [GROUPS][TE]
 constexpr int SI_ETGT = SI_ESRC + GROUPS * TE;  // [GROUPS][TE]
-constexpr int SI_MISC = SI_ETGT + GROUPS * TE;  // [4]
-constexpr int S_INTS = SI_MISC + 4;
+constexpr int SI_MISC = SI_ETGT + GROUPS * TE;  // [4]  (0: work item, 1: TMEM base address)
+constexpr int SI_BAR = ((S_FLOATS + SI_MISC + 4 + 1) & ~1) - S_FLOATS;  // [2] mbarrier (8-byte aligned)
+constexpr int S_INTS = SI_BAR + 2;
 constexpr size_t SMEM_BYTES = sizeof(float) * S_FLOATS + sizeof(int) * S_INTS;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 static_assert(MOLSDE_P_E0_END <= 3 * 32 * MAXN, "E0 weights are staged in the q/k/v region");
-static_assert(MOLSDE_P_BASIS_SZ <= 3 * 32 * MAXN, "basis weights are staged in the q/k/v region");
+static_assert(MOLSDE_P_BASIS_SZ <= 3 * 32 * MAXN, "basis weights (tcgen05 B tiles + small vectors) are staged in the q/k/v region");
 static_assert(32 * LDX <= GROUPS * TILE_FLOATS, "node staging aliases the A region");
 static_assert(TE * LDM <= TILE_FLOATS, "message tile aliases the group's A region");
 static_assert(LDX >= MAXN && LDX % 32 == 8 && LDA % 32 == 8, "padded leading dimensions");
 static_assert(S_A % 4 == 0 && S_WG % 4 == 0 && S_Q % 4 == 0 && TILE_FLOATS % 4 == 0, "16B alignment for cp.async");
+// tcgen05 operand tiles of the basis MLP: A hi/lo [128 x 64] over the (dead) GAT-weight + A regions, B hi/lo in the q/k/v region
+constexpr int UMMA_TILE = 128 * 64;          // floats per operand tile
+constexpr int S_UA_HI = S_WG, S_UA_LO = S_WG + UMMA_TILE;
+static_assert(S_UA_LO + UMMA_TILE <= S_L, "tcgen05 A tiles must fit before the logits region");
+static_assert((S_WG * 4) % 128 == 0 && (S_Q * 4) % 128 == 0, "operand tiles are 128B aligned");
+static_assert(GROUPS * TE * 8 >= 4 * TE * 4, "partial dyn buffer [4][TE][4]");
+constexpr uint32_t UMMA_LBO = 2048, UMMA_SBO = 128;  // bytes: next 16B K-chunk / next 8-row group (K-major, no swizzle)
+constexpr uint32_t TMEM_COLS = 128;
 
 struct Chunk {
     float* sm;
@@ -550,88 +559,165 @@ __device__ __noinline__ void node_update(const Chunk c, bool silu_after) {
 }
 
 // ---------------------------------------------------------------------------------------
-// basis MLP + equivariant mean aggregation  (equivariant_scorenetwork.py:154-164)
+// tcgen05 helpers (descriptor formats: cute/arch/mma_sm100_desc.hpp; bring-up test tools/ubench/tcgen05_gemm.cu)
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void phase_basis(const Chunk c, const float* __restrict__ blob, const int32_t* __restrict__ src_g,
-                                         const float* __restrict__ scratch, int module) {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return static_cast<uint64_t>((saddr & 0x3FFFF) >> 4)                   // start address  [0,14)
+           | (static_cast<uint64_t>(UMMA_LBO >> 4) << 16)                   // leading byte offset [16,30)
+           | (static_cast<uint64_t>(UMMA_SBO >> 4) << 32)                   // stride byte offset  [32,46)
+           | (static_cast<uint64_t>(1) << 46);                              // version 1 (Blackwell), layout = no swizzle
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, M = 128, N = 128, K = 8 (tf32), issued by ONE thread
+__device__ __forceinline__ void umma_tf32_128x128(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    // instruction descriptor: D = F32 (1<<4), A = B = TF32 (2<<7, 2<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int it = 0; it < (1 << 24) && !done; ++it)  // bounded: a descriptor bug must not hang the GPU
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// basis MLP + equivariant mean aggregation  (equivariant_scorenetwork.py:154-164)
+//   hidden[128 edges x 128] = [h_row + h_col | edge_attr][128 x 64] . W1^T on tcgen05 (M=128, N=128, 8 K-steps x 3 split
+//   terms, accumulator in TMEM); epilogue TMEM -> registers: +bias, SiLU, 128 -> 3 projection; frame mix; per-target mean.
+// All 16 warps work on one tile at a time; returns the updated mbarrier phase.
+// ---------------------------------------------------------------------------------------
+__device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restrict__ blob, const int32_t* __restrict__ src_g,
+                                             const float* __restrict__ scratch, int module, uint32_t tmem_base, uint32_t phase,
+                                             int32_t* status_flag) {
     float* sm = c.sm;
     float* Wb = sm + S_Q;  // staged over q/k/v (dead between GAT blocks)
+    float* AH = sm + S_UA_HI;
+    float* AL = sm + S_UA_LO;
+    float* dynp = sm + S_L;   // [4][TE][4] partial dyn coefficients of the four column blocks
+    float* mix = sm + S_MS;   // [TE][4]
     const float* XT = sm + S_XT;
     const float* pos = sm + S_POS;
     float* grad = sm + S_GRAD;
     const int* rowl = c.si + SI_ROWL;
+    int* esrc = c.si + SI_ESRC;
+    int* etgt = c.si + SI_ETGT;
+    const uint32_t bar = smem_u32(c.si + SI_BAR);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int grp = warp >> 3, slab = warp & 7, gt = tid & (GTHREADS - 1);
-    const int g = lane >> 2, t4 = lane & 3;
-    float* stripe = sm + S_A + grp * TILE_FLOATS + slab * 16;
-    float* mix = sm + S_MS + grp * (2 * TE * 8);  // [TE][4]
-    int* esrc = c.si + SI_ESRC + grp * TE;
-    int* etgt = c.si + SI_ETGT + grp * TE;
     stage_async(Wb, blob + MOLSDE_P_BASIS0 + module * MOLSDE_P_BASIS_SZ, MOLSDE_P_BASIS_SZ);
     cp_async_wait<0>();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    for (int t = grp; t < c.ntiles; t += GROUPS) {
+    for (int t = 0; t < c.ntiles; ++t) {
         const TileInfo ti = tile_info(c, t);
-        slot_edges(c, src_g, ti, slab, lane, esrc, etgt);
-        {   // K rows 0..31 of edge_feature: h_row + h_col   (:154-155)
-            const int fe = lane & 15, kb = (lane >> 4) * 16;
-            const int slot = slab * 16 + fe;
-            const int sj = esrc[slot], tg = etgt[slot];
-            const bool live = slot < ti.ne;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                stripe[(kb + i) * LDA + fe] = live ? XT[(kb + i) * LDX + sj] + XT[(kb + i) * LDX + tg] : 0.0f;
+        if (tid < TE) {  // (source, target) of every slot
+            int sj = 0, tg = ti.ta;
+            if (tid < ti.ne) {
+                const int e = ti.ea + tid;
+                int lo = ti.ta, hi = ti.tb;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (rowl[mid] <= e) lo = mid; else hi = mid;
+                }
+                tg = lo;
+                sj = src_g[c.edge0 + e] - c.node0;
+            }
+            esrc[tid] = sj;
+            etgt[tid] = tg;
         }
-        __syncwarp();
-        float acc[16][4];
-        zero_frag(acc);
-        mma_gemm<16, LDA, LD128>(stripe, Wb + MOLSDE_B_W1, 32, lane, acc);
-        __syncwarp();
-        // K rows 32..63: edge_attr stripe
-        load_stripe_async(stripe, scratch + static_cast<size_t>(t) * TILE_FLOATS + slab * 16, lane);
-        cp_async_wait<0>();
-        __syncwarp();
-        mma_gemm<16, LDA, LD128>(stripe, Wb + MOLSDE_B_W1 + 32 * LD128, 32, lane, acc);
-        float part[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+        __syncthreads();
+        // A operand [128 x 64], K-major canonical core-matrix layout, split into tf32 hi + exact lo:
+        //   k < 32: h_row + h_col (:154-155),  k >= 32: edge_attr (scratch tile)
+        const float* sc_t = scratch + static_cast<size_t>(t) * TILE_FLOATS;
 #pragma unroll
-        for (int nb = 0; nb < 16; ++nb)
+        for (int i = 0; i < 4; ++i) {
+            const int item = tid + NTHREADS * i;
+            const int e = item & (TE - 1), kc = item >> 7, k0 = kc * 4;
+            float v[4];
+            if (kc < 8) {
+                const int sj = esrc[e], tg = etgt[e];
+                const bool live = e < ti.ne;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int col = nb * 8 + 2 * t4 + j;
-                const float b1 = Wb[MOLSDE_B_B1 + col];
-                const float w0 = Wb[MOLSDE_B_W2 + col], w1 = Wb[MOLSDE_B_W2 + 128 + col], w2 = Wb[MOLSDE_B_W2 + 256 + col];
+                for (int q = 0; q < 4; ++q) v[q] = live ? XT[(k0 + q) * LDX + sj] + XT[(k0 + q) * LDX + tg] : 0.0f;
+            } else {
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const float hv = silu_fast(acc[nb][2 * rr + j] + b1);
-                    part[rr][0] = fmaf(hv, w0, part[rr][0]);
-                    part[rr][1] = fmaf(hv, w1, part[rr][1]);
-                    part[rr][2] = fmaf(hv, w2, part[rr][2]);
+                for (int q = 0; q < 4; ++q) v[q] = sc_t[(k0 - 32 + q) * LDA + e];
+            }
+            float4 h4, l4;
+            h4.x = __uint_as_float(tf32_hi(v[0])); h4.y = __uint_as_float(tf32_hi(v[1]));
+            h4.z = __uint_as_float(tf32_hi(v[2])); h4.w = __uint_as_float(tf32_hi(v[3]));
+            l4.x = v[0] - h4.x; l4.y = v[1] - h4.y; l4.z = v[2] - h4.z; l4.w = v[3] - h4.w;
+            const int idx = kc * 512 + (e >> 3) * 32 + (e & 7) * 4;
+            *reinterpret_cast<float4*>(AH + idx) = h4;
+            *reinterpret_cast<float4*>(AL + idx) = l4;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ah = smem_u32(AH), al = smem_u32(AL);
+            const uint32_t bh = smem_u32(Wb + MOLSDE_B_W1C_HI), bl = smem_u32(Wb + MOLSDE_B_W1C_LO);
+            uint32_t accumulate = 0;
+#pragma unroll 1
+            for (int term = 0; term < 3; ++term) {  // lo*hi, hi*lo, hi*hi (small terms first)
+                const uint32_t pa = (term == 0) ? al : ah, pb = (term == 1) ? bl : bh;
+#pragma unroll 1
+                for (int kb = 0; kb < 8; ++kb) {
+                    umma_tf32_128x128(tmem_base, umma_desc(pa + kb * 2 * UMMA_LBO), umma_desc(pb + kb * 2 * UMMA_LBO), accumulate);
+                    accumulate = 1;
                 }
             }
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-            for (int o = 0; o < 3; ++o) {
-                float v = part[rr][o];
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                part[rr][o] = v;
-            }
-        if (t4 < 2) {  // quad lane 0 finishes slot g, lane 1 slot g+8
-            const int slot = slab * 16 + g + 8 * t4;
-            if (slot < ti.ne) {
-                const Frame f = coord2basis(pos + 3 * esrc[slot], pos + 3 * etgt[slot]);
-                const float d0 = (t4 ? part[1][0] : part[0][0]) + Wb[MOLSDE_B_B2];
-                const float d1 = (t4 ? part[1][1] : part[0][1]) + Wb[MOLSDE_B_B2 + 1];
-                const float d2 = (t4 ? part[1][2] : part[0][2]) + Wb[MOLSDE_B_B2 + 2];
-                mix[slot * 4 + 0] = d0 * f.dx + d1 * f.cx + d2 * f.vx;
-                mix[slot * 4 + 1] = d0 * f.dy + d1 * f.cy + d2 * f.vy;
-                mix[slot * 4 + 2] = d0 * f.dz + d1 * f.cz + d2 * f.vz;
-            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
         }
-        group_sync(grp);
+        if (!mbar_wait(bar, phase) && tid == 0 && status_flag) atomicExch(status_flag, -7);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {   // epilogue: warp -> TMEM lane quarter (edge slots 32*lq..) x column block cb (hidden units 32*cb..)
+            const int lq = warp & 3, cb = warp >> 2;
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + cb * 32;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = cb * 32 + j;
+                const float hv = silu_fast(__uint_as_float(v[j]) + Wb[MOLSDE_B_B1 + col]);
+                p0 = fmaf(hv, Wb[MOLSDE_B_W2 + col], p0);
+                p1 = fmaf(hv, Wb[MOLSDE_B_W2 + 128 + col], p1);
+                p2 = fmaf(hv, Wb[MOLSDE_B_W2 + 256 + col], p2);
+            }
+            float* dp = dynp + (cb * TE + lq * 32 + lane) * 4;
+            dp[0] = p0; dp[1] = p1; dp[2] = p2;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < ti.ne) {
+            const Frame f = coord2basis(pos + 3 * esrc[tid], pos + 3 * etgt[tid]);
+            float d[3];
+#pragma unroll
+            for (int o = 0; o < 3; ++o)
+                d[o] = ((dynp[tid * 4 + o] + dynp[(TE + tid) * 4 + o]) + (dynp[(2 * TE + tid) * 4 + o] + dynp[(3 * TE + tid) * 4 + o])) +
+                       Wb[MOLSDE_B_B2 + o];
+            mix[tid * 4 + 0] = d[0] * f.dx + d[1] * f.cx + d[2] * f.vx;
+            mix[tid * 4 + 1] = d[0] * f.dy + d[1] * f.cy + d[2] * f.vy;
+            mix[tid * 4 + 2] = d[0] * f.dz + d[1] * f.cz + d[2] * f.vz;
+        }
+        __syncthreads();
         const int ntg = ti.tb - ti.ta;
-        for (int p = gt; p < ntg * 3; p += GTHREADS) {
+        for (int p = tid; p < ntg * 3; p += NTHREADS) {
             const int i = ti.ta + p / 3, ax = p % 3;
             const int s0 = rowl[i] - ti.ea, s1 = rowl[i + 1] - ti.ea;
             float sacc = 0.0f;
@@ -639,17 +725,18 @@ __device__ __noinline__ void phase_basis(const Chunk c, const float* __restrict_
             sacc = __fdiv_rn(sacc, static_cast<float>(max(s1 - s0, 1)));  // aggr='mean'
             grad[i * 3 + ax] = (module == 0) ? sacc : grad[i * 3 + ax] + sacc;
         }
-        group_sync(grp);
+        __syncthreads();
     }
-    __syncthreads();
+    return phase;
 }
 
 // ---------------------------------------------------------------------------------------
 // one full network evaluation on the chunk: positions in smem -> "gradient" in smem
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void score_eval(const Chunk c, const float* __restrict__ blob, const int32_t* __restrict__ src_g,
-                                        const float* __restrict__ nattr, const float* __restrict__ e2d_tiles,
-                                        float* __restrict__ scratch) {
+__device__ __noinline__ uint32_t score_eval(const Chunk c, const float* __restrict__ blob, const int32_t* __restrict__ src_g,
+                                            const float* __restrict__ nattr, const float* __restrict__ e2d_tiles,
+                                            float* __restrict__ scratch, uint32_t tmem_base, uint32_t phase,
+                                            int32_t* status_flag) {
     float* sm = c.sm;
     phase_edge_features(c, blob, src_g, e2d_tiles, scratch);
     // conv_input = node_attr (loop-invariant node_emb output), k-major
@@ -670,8 +757,30 @@ __device__ __noinline__ void score_eval(const Chunk c, const float* __restrict__
             node_update(c, conv == 0);
             __syncthreads();
         }
-        phase_basis(c, blob, src_g, scratch, module);
+        phase = phase_basis(c, blob, src_g, scratch, module, tmem_base, phase, status_flag);
     }
+    return phase;
+}
+
+// TMEM accumulator (128 columns) + mbarrier for the tcgen05 basis GEMM; call with all threads of the CTA
+__device__ __forceinline__ uint32_t tmem_setup(int* si) {
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(si + SI_BAR)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(si + SI_MISC + 1)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return static_cast<uint32_t>(si[SI_MISC + 1]);
+}
+__device__ __forceinline__ void tmem_teardown(uint32_t tmem_base) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
 }
 
 __device__ __forceinline__ bool load_chunk(Chunk& c, const molsde_plan& plan, int chunk, int32_t* status_flag) {
@@ -705,22 +814,25 @@ sde2d3d_score_kernel(molsde_plan plan, const float* __restrict__ blob, const flo
                      const float* __restrict__ e2d_tiles, const float* __restrict__ pos,
                      const float* __restrict__ stdv, float* __restrict__ score, float* __restrict__ scratch,
                      int64_t scratch_stride, int32_t* status_flag) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     Chunk c;
     c.sm = smem;
     c.si = reinterpret_cast<int*>(smem + S_FLOATS);
     float* my_scratch = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
+    const uint32_t tmem_base = tmem_setup(c.si);
+    uint32_t phase = 0;
     for (int chunk = blockIdx.x; chunk < plan.num_chunks; chunk += gridDim.x) {
         __syncthreads();
         if (!load_chunk(c, plan, chunk, status_flag)) continue;
         for (int i = threadIdx.x; i < c.n * 3; i += NTHREADS) smem[S_POS + i] = pos[static_cast<size_t>(c.node0) * 3 + i];
         __syncthreads();
-        score_eval(c, blob, plan.src, nattr, e2d_tiles, my_scratch);
+        phase = score_eval(c, blob, plan.src, nattr, e2d_tiles, my_scratch, tmem_base, phase, status_flag);
         for (int i = threadIdx.x; i < c.n * 3; i += NTHREADS) {
             // scores = -output / std  (:440-443)
             score[static_cast<size_t>(c.node0) * 3 + i] = __fdiv_rn(-smem[S_GRAD + i], stdv[c.node0 + i / 3]);
         }
     }
+    tmem_teardown(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -773,11 +885,13 @@ sde2d3d_pc_kernel(molsde_plan plan, const float* __restrict__ blob, const float*
                   const float* __restrict__ step_table, molsde_pc_config cfg, const float* __restrict__ noise_corr,
                   const float* __restrict__ noise_pred, float* __restrict__ pos_out, float* __restrict__ pos_mean_out,
                   float* __restrict__ scratch, int64_t scratch_stride, int32_t* work_counter, int32_t* status_flag) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     Chunk c;
     c.sm = smem;
     c.si = reinterpret_cast<int*>(smem + S_FLOATS);
     int* misc = c.si + SI_MISC;
+    const uint32_t tmem_base = tmem_setup(c.si);
+    uint32_t phase = 0;
     float* my_scratch = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
     float* P = smem + S_POS;
     float* G = smem + S_GRAD;
@@ -801,7 +915,7 @@ sde2d3d_pc_kernel(molsde_plan plan, const float* __restrict__ blob, const float*
             const float stdv = step_table[step * 8 + 0], Gd = step_table[step * 8 + 1];
             const float sqrt_alpha = step_table[step * 8 + 2], calpha = step_table[step * 8 + 3];
             // ---------------- corrector (LangevinCorrector.update_fn :191-212) ----------------
-            score_eval(c, blob, plan.src, nattr, e2d_tiles, my_scratch);
+            phase = score_eval(c, blob, plan.src, nattr, e2d_tiles, my_scratch, tmem_base, phase, status_flag);
             for (int i = tid; i < n3; i += NTHREADS) SC[i] = __fdiv_rn(-G[i], stdv);
             if (noise_corr) {
                 for (int i = tid; i < n3; i += NTHREADS) NZ[i] = noise_corr[static_cast<size_t>(step) * N3 + g3 + i];
@@ -826,7 +940,7 @@ sde2d3d_pc_kernel(molsde_plan plan, const float* __restrict__ blob, const float*
             }
             __syncthreads();
             // ---------------- predictor (ReverseDiffusionPredictor.update_fn :163-168) ----------------
-            score_eval(c, blob, plan.src, nattr, e2d_tiles, my_scratch);
+            phase = score_eval(c, blob, plan.src, nattr, e2d_tiles, my_scratch, tmem_base, phase, status_flag);
             const bool last = (step == cfg.steps - 1);
             for (int i = tid; i < c.n; i += NTHREADS) {
                 float nz[3];
@@ -852,6 +966,7 @@ sde2d3d_pc_kernel(molsde_plan plan, const float* __restrict__ blob, const float*
         }
         for (int i = tid; i < n3; i += NTHREADS) pos_out[g3 + i] = P[i];
     }
+    tmem_teardown(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -42,14 +42,19 @@
 #define MOLSDE_G_LN2_B 8736
 #define MOLSDE_P_GAT_SZ 8768
 
-/* ---- one basis MLP (score_network.basis_mlp_modules.{m}), base = P_BASIS0 + m*P_BASIS_SZ ---- */
+/* ---- one basis MLP (score_network.basis_mlp_modules.{m}), base = P_BASIS0 + m*P_BASIS_SZ ----
+ * The first layer (64 -> 128; input rows 0..31 = h_row+h_col, 32..63 = edge_attr) runs on tcgen05: its weight is
+ * stored as the B operand tile [N=128][K=64], K-major, in the canonical no-swizzle core-matrix layout
+ *   float index(n, k) = (k/4)*512 + (n/8)*32 + (n%8)*4 + (k%4)        (LBO = 2048 B, SBO = 128 B)
+ * twice: the tf32 "hi" part (top 19 bits) and the exact remainder "lo" (3xTF32 split done on the host). */
 #define MOLSDE_P_BASIS0 49376
-#define MOLSDE_B_W1 0      /* .0.weight^T [64][136]: rows 0..31 act on h_row+h_col, 32..63 on edge_attr */
-#define MOLSDE_B_B1 8704   /* [128] */
-#define MOLSDE_B_W2 8832   /* .2.weight [3][128] */
-#define MOLSDE_B_B2 9216   /* [3] + 1 pad */
-#define MOLSDE_P_BASIS_SZ 9220
+#define MOLSDE_B_W1C_HI 0      /* [8192] */
+#define MOLSDE_B_W1C_LO 8192   /* [8192] */
+#define MOLSDE_B_B1 16384      /* .0.bias [128] */
+#define MOLSDE_B_W2 16512      /* .2.weight [3][128] */
+#define MOLSDE_B_B2 16896      /* .2.bias [3] + 1 pad */
+#define MOLSDE_P_BASIS_SZ 16900
 
-#define MOLSDE_P_TOTAL 67816
+#define MOLSDE_P_TOTAL 83176
 
 #endif

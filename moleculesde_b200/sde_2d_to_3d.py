@@ -23,11 +23,20 @@ P_GFP_DIST_W, P_GFP_COFF_W = 0, 32
 P_IN_B, P_H_B, P_H_WSIN, P_H_WCOS, P_P1_B = 64, 96, 128, 160, 192
 P_IN_W, P_H_W, P_P1_W, P_E0_END = 224, 2784, 13024, 14304
 P_GAT0, P_GAT_SZ = 14304, 8768
-P_BASIS0, P_BASIS_SZ = 49376, 9220
-P_TOTAL = 67816
+P_BASIS0, P_BASIS_SZ = 49376, 16900
+P_TOTAL = 83176
 _G = dict(WQKV=0, WS=3328, WE=4608, F0=5888, F3=7168, BQKV=8448, BS=8544, LN1_W=8576, LN1_B=8608, F0_B=8640,
           F3_B=8672, LN2_W=8704, LN2_B=8736)
-_B = dict(W1=0, B1=8704, W2=8832, B2=9216)
+_B = dict(W1C_HI=0, W1C_LO=8192, B1=16384, W2=16512, B2=16896)
+
+
+def _umma_kmajor_tile(w: torch.Tensor) -> torch.Tensor:
+    """[R, K] matrix -> flat tcgen05 operand tile, K-major canonical no-swizzle core-matrix layout:
+    index(r, k) = (k//4)*(R//8)*32 + (r//8)*32 + (r%8)*4 + (k%4)   (8 rows x 16 B core matrices, csrc/sde2d3d_params.h)."""
+    R, K = w.shape
+    assert R % 8 == 0 and K % 4 == 0
+    t = w.reshape(R // 8, 8, K // 4, 4).permute(2, 0, 1, 3).contiguous()  # [K/4][R/8][8][4]
+    return t.reshape(-1)
 
 
 class MultiLayerPerceptron(nn.Module):
@@ -225,7 +234,10 @@ class SDEModel2Dto3D_02(nn.Module):
                 put(base + _G["LN2_B"], sd[p + "norm2.bias"])
             base = P_BASIS0 + m * P_BASIS_SZ
             p = f"score_network.basis_mlp_modules.{m}."
-            put_kmajor(base + _B["W1"], sd[p + "0.weight"], LD128)
+            w1 = sd[p + "0.weight"]                                   # [128 out (n), 64 in (k)]
+            w1_hi = (w1.contiguous().view(torch.int32) & -8192).view(torch.float32)   # top 19 bits = tf32 operand
+            put(base + _B["W1C_HI"], _umma_kmajor_tile(w1_hi))
+            put(base + _B["W1C_LO"], _umma_kmajor_tile(w1 - w1_hi))
             put(base + _B["B1"], sd[p + "0.bias"])
             put(base + _B["W2"], sd[p + "2.weight"])
             put(base + _B["B2"], sd[p + "2.bias"])

@@ -54,7 +54,7 @@ def test_param_offsets_match_header():
     # blocks do not overlap
     assert M.P_IN_W + 64 * M.LD32 == M.P_H_W and M.P_H_W + 256 * M.LD32 == M.P_P1_W and M.P_P1_W + 32 * M.LD32 == M.P_E0_END
     assert M._G["WQKV"] + 32 * M.LD96 == M._G["WS"] and M._G["F3"] + 32 * M.LD32 == M._G["BQKV"]
-    assert M._B["W1"] + 64 * M.LD128 == M._B["B1"]
+    assert M._B["W1C_HI"] + 8192 == M._B["W1C_LO"] and M._B["W1C_LO"] + 8192 == M._B["B1"]
     api = open(os.path.join(REPO, "include", "molsde_b200.h")).read()
     assert int(re.search(r"#define MOLSDE_TILE_LD (\d+)", api).group(1)) == _abi.TILE_LD
 
@@ -93,8 +93,15 @@ def test_packed_blob_roundtrip(golden):
     base = M.P_BASIS0 + M.P_BASIS_SZ
     assert torch.equal(blob[base + M._B["W2"]:base + M._B["W2"] + 384].view(3, 128),
                        sd["score_network.basis_mlp_modules.1.2.weight"])
-    w1 = blob[base + M._B["W1"]:base + M._B["W1"] + 64 * M.LD128].view(64, M.LD128)
-    assert torch.equal(w1[:, :128], sd["score_network.basis_mlp_modules.1.0.weight"].t())
+    # tcgen05 B-operand tiles of the basis MLP: canonical K-major core-matrix layout, hi + lo == weight exactly
+    w1 = sd["score_network.basis_mlp_modules.1.0.weight"]  # [128 (n), 64 (k)]
+    hi = blob[base + M._B["W1C_HI"]:base + M._B["W1C_HI"] + 8192]
+    lo = blob[base + M._B["W1C_LO"]:base + M._B["W1C_LO"] + 8192]
+    for n, k in ((0, 0), (5, 3), (8, 4), (77, 41), (127, 63)):
+        idx = (k // 4) * 512 + (n // 8) * 32 + (n % 8) * 4 + (k % 4)
+        assert (hi[idx] + lo[idx]).item() == w1[n, k].item()
+        assert hi[idx].view(torch.int32).item() & 0x1FFF == 0  # low 13 mantissa bits clear: a tf32 value
+    assert (lo.abs() <= hi.abs() * 2.0 ** -10 + 1e-30).all()
     # BN-folded, node-factored first layer of edge_2D_emb equals the reference layer in eval mode
     h = torch.randn(7, 300)
     row, col = torch.tensor([0, 3, 5]), torch.tensor([1, 2, 6])
