@@ -37,6 +37,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
                "-Xcompiler", "-fPIC", "-c", src, "-o", obj]
         if verbose:
             cmd += ["-Xptxas", "-v"]
+        if os.environ.get("MOLSDE_PROF") == "1":
+            cmd += ["-DMOLSDE_PROF"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()

@@ -82,7 +82,17 @@ static_assert(S_UA_LO + UMMA_TILE <= S_L, "tcgen05 A tiles must fit before the l
 static_assert((S_WG * 4) % 128 == 0 && (S_Q * 4) % 128 == 0, "operand tiles are 128B aligned");
 static_assert(GROUPS * TE * 8 >= 4 * TE * 4, "partial dyn buffer [4][TE][4]");
 constexpr uint32_t UMMA_LBO = 2048, UMMA_SBO = 128;  // bytes: next 16B K-chunk / next 8-row group (K-major, no swizzle)
-constexpr uint32_t TMEM_COLS = 128;
+constexpr uint32_t TMEM_COLS = 256;  // two 128-column accumulators (tile t / t+1 of the basis GEMM pipeline)
+
+// optional per-phase cycle accounting (build with MOLSDE_PROF=1; read back with molsde_debug_read_prof)
+#ifdef MOLSDE_PROF
+__device__ unsigned long long g_prof[kNumSMs][8];
+#define PROF_T0() long long prof_t0 = clock64()
+#define PROF_ADD(slot) do { __syncthreads(); if (threadIdx.x == 0) { long long prof_t1 = clock64(); g_prof[blockIdx.x][slot] += prof_t1 - prof_t0; prof_t0 = prof_t1; } } while (0)
+#else
+#define PROF_T0()
+#define PROF_ADD(slot)
+#endif
 
 struct Chunk {
     float* sm;
@@ -143,6 +153,10 @@ __device__ __forceinline__ Frame coord2basis(const float* pr, const float* pc) {
     f.vz = __fsub_rn(__fmul_rn(dx, cy), __fmul_rn(dy, cx));
     return f;
 }
+
+// q / k / v rows are [node][32] with the column XOR-swizzled by the node index (4-float granules): the per-edge gathers
+// k[src], v[src] of 8 consecutive slots then hit 8 different bank groups instead of one (profiles/r1_pc_v4_conflicts.txt)
+__device__ __forceinline__ int qkv_idx(int node, int col) { return node * 32 + (col ^ ((node & 7) << 2)); }
 
 // ---- group / tile helpers -------------------------------------------------------------------
 // The 16 warps form two groups of 8; group g walks tiles g, g+2, ... of the chunk.  Inside a group
@@ -267,26 +281,29 @@ __device__ __noinline__ void phase_edge_features(const Chunk c, const float* __r
         // hidden layer of `project` (:427-430).  Each block: sin half -> GEMM(K=32), cos half -> GEMM(K=32).
         float inv[4][4], acc[4][4];
         zero_frag(acc);
-        const int fe = lane & 15, wbase = (lane >> 4) * 16;
+        // lane -> (edge fe, half hf); frequency of step i is w(i) = 4*(i/2) + 2*hf + (i&1): at every step the two half-warps
+        // write A rows 2 apart = 16 banks apart (conflict-free), profiles/r1_pc_v4_conflicts.txt
+        const int fe = lane & 15, hf = lane >> 4;
 #pragma unroll 1
         for (int blk = 0; blk < 5; ++blk) {
             const float x = geo[blk * 16 + fe];
-            const float* Wf = W + (blk == 0 ? MOLSDE_P_GFP_DIST_W : MOLSDE_P_GFP_COFF_W) + wbase;
+            const float* Wf = W + (blk == 0 ? MOLSDE_P_GFP_DIST_W : MOLSDE_P_GFP_COFF_W);
             const float* Wm = (blk == 0) ? W + MOLSDE_P_IN_W : W + MOLSDE_P_H_W + (blk - 1) * 64 * LD32;
             float cs[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 // GaussianFourierProjection.forward, :64-66  (x * W * 2 * pi, fp32, in that order)
-                const float arg = __fmul_rn(__fmul_rn(__fmul_rn(x, Wf[i]), 2.0f), 3.14159274101257324f);
+                const int w = 4 * (i >> 1) + 2 * hf + (i & 1);
+                const float arg = __fmul_rn(__fmul_rn(__fmul_rn(x, Wf[w]), 2.0f), 3.14159274101257324f);
                 float sn;
                 sincos_reduced(arg, sn, cs[i]);
-                A[(wbase + i) * LDA + fe] = sn;
+                A[w * LDA + fe] = sn;
             }
             __syncwarp();
             mma_gemm<4, LDA, LD32>(A, Wm, 32, lane, acc);
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) A[(wbase + i) * LDA + fe] = cs[i];
+            for (int i = 0; i < 16; ++i) A[(4 * (i >> 1) + 2 * hf + (i & 1)) * LDA + fe] = cs[i];
             __syncwarp();
             mma_gemm<4, LDA, LD32>(A, Wm + 32 * LD32, 32, lane, acc);
             __syncwarp();
@@ -347,12 +364,12 @@ __device__ __noinline__ void node_qkv(const Chunk c) {
     for (int nb = 0; nb < 12; ++nb) {
         const int col = nb * 8 + 2 * t4;  // 0..95: q | k | v
         const float b0 = Wg[MOLSDE_G_BQKV + col], b1 = Wg[MOLSDE_G_BQKV + col + 1];
-        float* dst = sm + S_Q + (col >> 5) * (32 * MAXN) + (col & 31);
+        float* dst = sm + S_Q + (col >> 5) * (32 * MAXN);
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const int node = m0 + g + 8 * rr;
             if (node < c.n)
-                *reinterpret_cast<float2*>(dst + node * 32) = make_float2(acc[nb][2 * rr] + b0, acc[nb][2 * rr + 1] + b1);
+                *reinterpret_cast<float2*>(dst + qkv_idx(node, col & 31)) = make_float2(acc[nb][2 * rr] + b0, acc[nb][2 * rr + 1] + b1);
         }
     }
 }
@@ -396,9 +413,9 @@ __device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __rest
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
                 const int col = nb * 8 + 2 * t4;
-                const float2 k2 = *reinterpret_cast<const float2*>(Kk + sj * 32 + col);
-                const float2 q2 = *reinterpret_cast<const float2*>(Q + tg * 32 + col);
-                const float2 v2 = *reinterpret_cast<const float2*>(V + sj * 32 + col);
+                const float2 k2 = *reinterpret_cast<const float2*>(Kk + qkv_idx(sj, col));
+                const float2 q2 = *reinterpret_cast<const float2*>(Q + qkv_idx(tg, col));
+                const float2 v2 = *reinterpret_cast<const float2*>(V + qkv_idx(sj, col));
                 // alpha = (q_i . (k_j + e)) / sqrt(C): a head (4 columns) is split over the lane pair (t4, t4^1)
                 float part = fmaf(q2.y, k2.y + e[nb][2 * rr + 1], q2.x * (k2.x + e[nb][2 * rr]));
                 part += __shfl_xor_sync(0xffffffffu, part, 1);
@@ -441,7 +458,7 @@ __device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __rest
             const int s0 = rowl[i] - ti.ea, s1 = rowl[i + 1] - ti.ea;
             float acc = 0.0f;
             for (int s = s0; s < s1; ++s) acc += Mm[s * LDM + col];
-            Q[i * 32 + col] = acc;
+            Q[qkv_idx(i, col)] = acc;
         }
         group_sync(grp);
     }
@@ -499,7 +516,7 @@ __device__ __noinline__ void node_update(const Chunk c, bool silu_after) {
         for (int rr = 0; rr < 2; ++rr) {
             const int node = m0 + g + 8 * rr;
             float2 ag = make_float2(0.f, 0.f);
-            if (node < c.n) ag = *reinterpret_cast<const float2*>(Q + node * 32 + col);
+            if (node < c.n) ag = *reinterpret_cast<const float2*>(Q + qkv_idx(node, col));
             acc[nb][2 * rr] += b0 + ag.x;
             acc[nb][2 * rr + 1] += b1 + ag.y;
         }
@@ -560,23 +577,29 @@ __device__ __noinline__ void node_update(const Chunk c, bool silu_after) {
 
 // ---------------------------------------------------------------------------------------
 // tcgen05 helpers (descriptor formats: cute/arch/mma_sm100_desc.hpp; bring-up test tools/ubench/tcgen05_gemm.cu)
+// Operand tiles are K-major in the canonical no-swizzle core-matrix layout (8 rows x 16 B):
+//   float index(r, k) = (k/4)*(R/8)*32 + (r/8)*32 + (r%8)*4 + (k%4),  LBO = (R/8)*128 B, SBO = 128 B.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
     return static_cast<uint64_t>((saddr & 0x3FFFF) >> 4)                   // start address  [0,14)
-           | (static_cast<uint64_t>(UMMA_LBO >> 4) << 16)                   // leading byte offset [16,30)
+           | (static_cast<uint64_t>(lbo_bytes >> 4) << 16)                  // leading byte offset [16,30)
            | (static_cast<uint64_t>(UMMA_SBO >> 4) << 32)                   // stride byte offset  [32,46)
            | (static_cast<uint64_t>(1) << 46);                              // version 1 (Blackwell), layout = no swizzle
 }
-// D[tmem] (+)= A[smem] . B[smem]^T, M = 128, N = 128, K = 8 (tf32), issued by ONE thread
-__device__ __forceinline__ void umma_tf32_128x128(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] . B[smem]^T, M = 128, K = 8 (tf32), issued by ONE thread
+template <int N>
+__device__ __forceinline__ void umma_tf32_m128(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
     // instruction descriptor: D = F32 (1<<4), A = B = TF32 (2<<7, 2<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((static_cast<uint32_t>(N) >> 3) << 17) | ((128u >> 4) << 24);
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -584,6 +607,39 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
+}
+// 3xTF32: three passes (lo*hi, hi*lo, hi*hi) over `ksteps` K=8 steps of an A tile [128 x 8*ksteps] and a B tile [N x ...]
+template <int N>
+__device__ __forceinline__ void umma_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int ksteps,
+                                            uint32_t lbo_a, uint32_t lbo_b, uint32_t accumulate) {
+#pragma unroll 1
+    for (int term = 0; term < 3; ++term) {
+        const uint32_t pa = (term == 0) ? a_lo : a_hi, pb = (term == 1) ? b_lo : b_hi;
+#pragma unroll 1
+        for (int kb = 0; kb < ksteps; ++kb) {
+            umma_tf32_m128<N>(tmem_d, umma_desc(pa + kb * 2 * lbo_a, lbo_a), umma_desc(pb + kb * 2 * lbo_b, lbo_b), accumulate);
+            accumulate = 1;
+        }
+    }
+}
+// 8 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// write 4 consecutive-k values of row `r` (k-chunk kc) of a [128 x K] A tile as tf32 hi + exact lo
+__device__ __forceinline__ void store_a_chunk(float* AH, float* AL, int r, int kc, const float (&v)[4]) {
+    float4 h4, l4;
+    h4.x = __uint_as_float(tf32_hi(v[0])); h4.y = __uint_as_float(tf32_hi(v[1]));
+    h4.z = __uint_as_float(tf32_hi(v[2])); h4.w = __uint_as_float(tf32_hi(v[3]));
+    l4.x = v[0] - h4.x; l4.y = v[1] - h4.y; l4.z = v[2] - h4.z; l4.w = v[3] - h4.w;
+    const int idx = kc * 512 + (r >> 3) * 32 + (r & 7) * 4;
+    *reinterpret_cast<float4*>(AH + idx) = h4;
+    *reinterpret_cast<float4*>(AL + idx) = l4;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -605,16 +661,18 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
     const float* pos = sm + S_POS;
     float* grad = sm + S_GRAD;
     const int* rowl = c.si + SI_ROWL;
-    int* esrc = c.si + SI_ESRC;
-    int* etgt = c.si + SI_ETGT;
     const uint32_t bar = smem_u32(c.si + SI_BAR);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     stage_async(Wb, blob + MOLSDE_P_BASIS0 + module * MOLSDE_P_BASIS_SZ, MOLSDE_P_BASIS_SZ);
     cp_async_wait<0>();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    for (int t = 0; t < c.ntiles; ++t) {
+
+    // stage 1 of the software pipeline: slot bookkeeping + A operand of tile t + MMA issue (asynchronous)
+    auto produce_and_issue = [&](int t) {
         const TileInfo ti = tile_info(c, t);
+        int* esrc = c.si + SI_ESRC + (t & 1) * TE;
+        int* etgt = c.si + SI_ETGT + (t & 1) * TE;
         if (tid < TE) {  // (source, target) of every slot
             int sj = 0, tg = ti.ta;
             if (tid < ti.ne) {
@@ -648,40 +706,33 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
 #pragma unroll
                 for (int q = 0; q < 4; ++q) v[q] = sc_t[(k0 - 32 + q) * LDA + e];
             }
-            float4 h4, l4;
-            h4.x = __uint_as_float(tf32_hi(v[0])); h4.y = __uint_as_float(tf32_hi(v[1]));
-            h4.z = __uint_as_float(tf32_hi(v[2])); h4.w = __uint_as_float(tf32_hi(v[3]));
-            l4.x = v[0] - h4.x; l4.y = v[1] - h4.y; l4.z = v[2] - h4.z; l4.w = v[3] - h4.w;
-            const int idx = kc * 512 + (e >> 3) * 32 + (e & 7) * 4;
-            *reinterpret_cast<float4*>(AH + idx) = h4;
-            *reinterpret_cast<float4*>(AL + idx) = l4;
+            store_a_chunk(AH, AL, e, kc, v);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ah = smem_u32(AH), al = smem_u32(AL);
-            const uint32_t bh = smem_u32(Wb + MOLSDE_B_W1C_HI), bl = smem_u32(Wb + MOLSDE_B_W1C_LO);
-            uint32_t accumulate = 0;
-#pragma unroll 1
-            for (int term = 0; term < 3; ++term) {  // lo*hi, hi*lo, hi*hi (small terms first)
-                const uint32_t pa = (term == 0) ? al : ah, pb = (term == 1) ? bl : bh;
-#pragma unroll 1
-                for (int kb = 0; kb < 8; ++kb) {
-                    umma_tf32_128x128(tmem_base, umma_desc(pa + kb * 2 * UMMA_LBO), umma_desc(pb + kb * 2 * UMMA_LBO), accumulate);
-                    accumulate = 1;
-                }
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            umma_3xtf32<128>(tmem_base + (t & 1) * 128, smem_u32(AH), smem_u32(AL), smem_u32(Wb + MOLSDE_B_W1C_HI),
+                             smem_u32(Wb + MOLSDE_B_W1C_LO), 8, UMMA_LBO, UMMA_LBO, 0u);
+            umma_commit(bar);
         }
-        if (!mbar_wait(bar, phase) && tid == 0 && status_flag) atomicExch(status_flag, -7);
+    };
+
+    bool ok = true;
+    if (c.ntiles > 0) produce_and_issue(0);
+    for (int t = 0; t < c.ntiles; ++t) {
+        const TileInfo ti = tile_info(c, t);
+        const int* esrc = c.si + SI_ESRC + (t & 1) * TE;
+        const int* etgt = c.si + SI_ETGT + (t & 1) * TE;
+        ok &= mbar_wait(bar, phase);  // MMAs of tile t complete: accumulator (t&1) ready, A buffer free
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (t + 1 < c.ntiles) produce_and_issue(t + 1);  // its MMAs overlap the epilogue below
         {   // epilogue: warp -> TMEM lane quarter (edge slots 32*lq..) x column block cb (hidden units 32*cb..)
             const int lq = warp & 3, cb = warp >> 2;
             uint32_t v[32];
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + cb * 32;
+            const uint32_t taddr = tmem_base + (t & 1) * 128 + (static_cast<uint32_t>(lq * 32) << 16) + cb * 32;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
@@ -727,6 +778,7 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
         }
         __syncthreads();
     }
+    if (!ok && tid == 0 && status_flag) atomicExch(status_flag, -7);
     return phase;
 }
 
@@ -738,7 +790,9 @@ __device__ __noinline__ uint32_t score_eval(const Chunk c, const float* __restri
                                             float* __restrict__ scratch, uint32_t tmem_base, uint32_t phase,
                                             int32_t* status_flag) {
     float* sm = c.sm;
+    PROF_T0();
     phase_edge_features(c, blob, src_g, e2d_tiles, scratch);
+    PROF_ADD(0);
     // conv_input = node_attr (loop-invariant node_emb output), k-major
     for (int idx = threadIdx.x; idx < c.n * 32; idx += NTHREADS) {
         const int node = idx >> 5, k = idx & 31;
@@ -750,14 +804,19 @@ __device__ __noinline__ uint32_t score_eval(const Chunk c, const float* __restri
             stage_async(sm + S_WG, blob + MOLSDE_P_GAT0 + (2 * module + conv) * MOLSDE_P_GAT_SZ, MOLSDE_P_GAT_SZ);
             cp_async_wait<0>();
             __syncthreads();
+            PROF_ADD(1);
             node_qkv(c);
             __syncthreads();
+            PROF_ADD(2);
             gat_edge_phase(c, src_g, scratch);
             __syncthreads();
+            PROF_ADD(3);
             node_update(c, conv == 0);
             __syncthreads();
+            PROF_ADD(4);
         }
         phase = phase_basis(c, blob, src_g, scratch, module, tmem_base, phase, status_flag);
+        PROF_ADD(5);
     }
     return phase;
 }
@@ -1051,6 +1110,17 @@ static int plan_ok(const molsde_plan* p) {
 }
 
 extern "C" {
+
+#ifdef MOLSDE_PROF
+// debug: copy the per-CTA phase cycle counters (148 x 8 uint64) to the host and reset them
+int molsde_debug_read_prof(unsigned long long* host_out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_out, g_prof, sizeof(unsigned long long) * kNumSMs * 8);
+    static unsigned long long zeros[kNumSMs * 8];
+    cudaMemcpyToSymbol(g_prof, zeros, sizeof(zeros));
+    return 0;
+}
+#endif
 
 int64_t molsde_tile_floats(void) { return TILE_FLOATS; }
 
