@@ -38,6 +38,8 @@ constexpr int MAXT = 64;                      // tiles per chunk
 constexpr int LDA = MOLSDE_TILE_LD;           // 136: leading dim of a k-major edge tile
 constexpr int LDX = 232;                      // leading dim of the k-major node matrix (>= MAXN, == 8 mod 32)
 constexpr int TILE_FLOATS = 32 * LDA;         // one [32][136] per-edge attribute tile
+constexpr int FRAME_FLOATS = 9 * TE;          // per-edge SE(3) frame (diff, cross, vertical) cached by E0 for the basis phases
+constexpr int SCR_TILE = TILE_FLOATS + FRAME_FLOATS;  // per-tile scratch record: edge_attr [32][136] | frame [9][128]
 constexpr int LDM = 33;                       // padded row of the slot-major message tile [TE][33]
 constexpr int LD32 = MOLSDE_LD32, LD96 = MOLSDE_LD96, LD128 = MOLSDE_LD128;
 constexpr float EPS = 1e-6f;                  // SDE_model_2D_to_3D.py:10
@@ -256,6 +258,12 @@ __device__ __noinline__ void phase_edge_features(const Chunk c, const float* __r
                 const float* pr = pos + 3 * esrc[slot];  // row = source j
                 const float* pc = pos + 3 * etgt[slot];  // col = target i
                 const Frame f = coord2basis(pr, pc);
+                {   // cache the equivariant basis of this edge for the two basis phases (equivariant_scorenetwork.py:159)
+                    float* fr_t = scratch + static_cast<size_t>(t) * SCR_TILE + TILE_FLOATS + slot;
+                    fr_t[0 * TE] = f.dx; fr_t[1 * TE] = f.dy; fr_t[2 * TE] = f.dz;
+                    fr_t[3 * TE] = f.cx; fr_t[4 * TE] = f.cy; fr_t[5 * TE] = f.cz;
+                    fr_t[6 * TE] = f.vx; fr_t[7 * TE] = f.vy; fr_t[8 * TE] = f.vz;
+                }
                 // coff = edge_basis @ r  (:417-418), |.| on component 1 (:419-420)
                 const float ci0 = dot3_rn(f.dx, f.dy, f.dz, pr[0], pr[1], pr[2]);
                 const float ci1 = fabsf(dot3_rn(f.cx, f.cy, f.cz, pr[0], pr[1], pr[2]));
@@ -331,7 +339,7 @@ __device__ __noinline__ void phase_edge_features(const Chunk c, const float* __r
         zero_frag(acc);
         mma_gemm<4, LDA, LD32>(A, W + MOLSDE_P_P1_W, 32, lane, acc);
         // ---- edge_attr = inv3d * e2d + frame  (:432) -> scratch tile (own stripe) ----
-        float* sc_t = scratch + static_cast<size_t>(t) * TILE_FLOATS + slab * 16;
+        float* sc_t = scratch + static_cast<size_t>(t) * SCR_TILE + slab * 16;
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb)
 #pragma unroll
@@ -397,7 +405,7 @@ __device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __rest
     int* etgt = c.si + SI_ETGT + grp * TE;
     for (int t = grp; t < c.ntiles; t += GROUPS) {
         const TileInfo ti = tile_info(c, t);
-        load_stripe_async(stripe, scratch + static_cast<size_t>(t) * TILE_FLOATS + slab * 16, lane);
+        load_stripe_async(stripe, scratch + static_cast<size_t>(t) * SCR_TILE + slab * 16, lane);
         slot_edges(c, src_g, ti, slab, lane, esrc, etgt);
         cp_async_wait<0>();
         __syncwarp();
@@ -656,9 +664,9 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
     float* AH = sm + S_UA_HI;
     float* AL = sm + S_UA_LO;
     float* dynp = sm + S_L;   // [4][TE][4] partial dyn coefficients of the four column blocks
-    float* mix = sm + S_MS;   // [TE][4]
+    float* frames = sm + S_MS;  // [2][9][TE] cached edge frames of tile t / t+1
+    float* mix = sm + S_MS + 2 * FRAME_FLOATS;  // [3][TE]
     const float* XT = sm + S_XT;
-    const float* pos = sm + S_POS;
     float* grad = sm + S_GRAD;
     const int* rowl = c.si + SI_ROWL;
     const uint32_t bar = smem_u32(c.si + SI_BAR);
@@ -691,7 +699,8 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
         __syncthreads();
         // A operand [128 x 64], K-major canonical core-matrix layout, split into tf32 hi + exact lo:
         //   k < 32: h_row + h_col (:154-155),  k >= 32: edge_attr (scratch tile)
-        const float* sc_t = scratch + static_cast<size_t>(t) * TILE_FLOATS;
+        const float* sc_t = scratch + static_cast<size_t>(t) * SCR_TILE;
+        stage_async(frames + (t & 1) * FRAME_FLOATS, sc_t + TILE_FLOATS, FRAME_FLOATS);  // consumed by the epilogue of tile t
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int item = tid + NTHREADS * i;
@@ -708,6 +717,7 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
             }
             store_a_chunk(AH, AL, e, kc, v);
         }
+        cp_async_wait<0>();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -755,24 +765,27 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (tid < ti.ne) {
-            const Frame f = coord2basis(pos + 3 * esrc[tid], pos + 3 * etgt[tid]);
-            float d[3];
+        // basis_mix = dyn0 * coord_diff + dyn1 * coord_cross + dyn2 * coord_vertical  (:159), frames cached by E0
+        const float* F = frames + (t & 1) * FRAME_FLOATS;
+        if (tid < 3 * TE) {
+            const int q = tid & (TE - 1), ax = tid >> 7;
+            if (q < ti.ne) {
+                float d[3];
 #pragma unroll
-            for (int o = 0; o < 3; ++o)
-                d[o] = ((dynp[tid * 4 + o] + dynp[(TE + tid) * 4 + o]) + (dynp[(2 * TE + tid) * 4 + o] + dynp[(3 * TE + tid) * 4 + o])) +
-                       Wb[MOLSDE_B_B2 + o];
-            mix[tid * 4 + 0] = d[0] * f.dx + d[1] * f.cx + d[2] * f.vx;
-            mix[tid * 4 + 1] = d[0] * f.dy + d[1] * f.cy + d[2] * f.vy;
-            mix[tid * 4 + 2] = d[0] * f.dz + d[1] * f.cz + d[2] * f.vz;
+                for (int o = 0; o < 3; ++o)
+                    d[o] = ((dynp[q * 4 + o] + dynp[(TE + q) * 4 + o]) + (dynp[(2 * TE + q) * 4 + o] + dynp[(3 * TE + q) * 4 + o])) +
+                           Wb[MOLSDE_B_B2 + o];
+                mix[ax * TE + q] = d[0] * F[ax * TE + q] + d[1] * F[(3 + ax) * TE + q] + d[2] * F[(6 + ax) * TE + q];
+            }
         }
         __syncthreads();
+        // gradient_i (+)= mean over the incoming edges (:162-164), ascending-source order
         const int ntg = ti.tb - ti.ta;
         for (int p = tid; p < ntg * 3; p += NTHREADS) {
             const int i = ti.ta + p / 3, ax = p % 3;
             const int s0 = rowl[i] - ti.ea, s1 = rowl[i + 1] - ti.ea;
             float sacc = 0.0f;
-            for (int q = s0; q < s1; ++q) sacc += mix[q * 4 + ax];
+            for (int q = s0; q < s1; ++q) sacc += mix[ax * TE + q];
             sacc = __fdiv_rn(sacc, static_cast<float>(max(s1 - s0, 1)));  // aggr='mean'
             grad[i * 3 + ax] = (module == 0) ? sacc : grad[i * 3 + ax] + sacc;
         }
@@ -1129,7 +1142,7 @@ int64_t molsde_sde2d3d_scratch_floats(const molsde_plan* plan, int32_t max_chunk
     int ctas = plan->num_chunks < kNumSMs ? plan->num_chunks : kNumSMs;
     if (ctas < 1) ctas = 1;
     if (num_ctas_out) *num_ctas_out = ctas;
-    return static_cast<int64_t>(ctas) * max_chunk_tiles * TILE_FLOATS;
+    return static_cast<int64_t>(ctas) * max_chunk_tiles * SCR_TILE;
 }
 
 int molsde_edge2d_emb_eval(const molsde_plan* plan, const float* uv, const float* w3t, const float* b3,
@@ -1152,8 +1165,8 @@ int molsde_sde2d3d_score(const molsde_plan* plan, const molsde_sde2d3d_params* p
     if (params->blob_floats < MOLSDE_P_TOTAL) return MOLSDE_ERR_INVALID;
     if (plan->num_chunks == 0) return MOLSDE_OK;
     int ctas = plan->num_chunks < kNumSMs ? plan->num_chunks : kNumSMs;
-    const int64_t stride = (scratch_floats / ctas) / TILE_FLOATS * TILE_FLOATS;
-    if (stride < TILE_FLOATS) return MOLSDE_ERR_WORKSPACE;
+    const int64_t stride = (scratch_floats / ctas) / SCR_TILE * SCR_TILE;
+    if (stride < SCR_TILE) return MOLSDE_ERR_WORKSPACE;
     cudaError_t err = cudaFuncSetAttribute(sde2d3d_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (err != cudaSuccess) { set_last_error(cudaGetErrorString(err)); return MOLSDE_ERR_CUDA; }
     sde2d3d_score_kernel<<<ctas, NTHREADS, SMEM_BYTES, as_stream(stream)>>>(*plan, params->blob, nattr, e2d_tiles, pos,
@@ -1173,8 +1186,8 @@ int molsde_sde2d3d_pc_sample(const molsde_plan* plan, const molsde_sde2d3d_param
     if ((noise_corr == nullptr) != (noise_pred == nullptr)) return MOLSDE_ERR_INVALID;
     if (plan->num_chunks == 0) return MOLSDE_OK;
     int ctas = plan->num_chunks < kNumSMs ? plan->num_chunks : kNumSMs;
-    const int64_t stride = (scratch_floats / ctas) / TILE_FLOATS * TILE_FLOATS;
-    if (stride < TILE_FLOATS) return MOLSDE_ERR_WORKSPACE;
+    const int64_t stride = (scratch_floats / ctas) / SCR_TILE * SCR_TILE;
+    if (stride < SCR_TILE) return MOLSDE_ERR_WORKSPACE;
     cudaError_t err = cudaFuncSetAttribute(sde2d3d_pc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (err != cudaSuccess) { set_last_error(cudaGetErrorString(err)); return MOLSDE_ERR_CUDA; }
     err = cudaMemsetAsync(work_counter, 0, sizeof(int32_t), as_stream(stream));
