@@ -22,6 +22,9 @@ import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
+if "reference" in sys.argv:  # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -344,7 +347,7 @@ def run_b200(args):
                               "note": "same algorithmic FLOPs against the derived fp32 FFMA peak 148 SM x 128 lanes x 2 x max clock"},
             "atoms": N, "edges": Ex, "groups": int(group_ptr.numel() - 1),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
             rate, per_step, sample = cpu_reference_rate(mols, args.repeat, args.cpu_pc_steps, args.pc_steps, model.state_dict())
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
         print(json.dumps(line))

@@ -247,6 +247,7 @@ int molsde_extend_graph_count(const int64_t* edge_index, int64_t E_b, const int3
 int molsde_extend_graph_fill(const int64_t* edge_index, int64_t E_b, const int32_t* node_ptr,
                              const int32_t* edge_ptr, int32_t B, const int32_t* rowptr, int64_t E_x,
                              int32_t* col, int64_t* ext_edge_index, void* stream) {
+    if (E_x == 0) return MOLSDE_OK;  // nothing to emit (e.g. a batch of isolated atoms)
     if (!node_ptr || !edge_ptr || !rowptr || !col || B < 0) return MOLSDE_ERR_INVALID;
     if (B == 0) return MOLSDE_OK;
     int blocks = (B + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -269,6 +270,7 @@ int molsde_radius_graph_count(const float* pos, const int32_t* node_ptr, int32_t
 int molsde_radius_graph_fill(const float* pos, const int32_t* node_ptr, int32_t B, float r,
                              int32_t max_num_neighbors, const int32_t* rowptr, int64_t E_r, int32_t* col,
                              int64_t* edge_index, void* stream) {
+    if (E_r == 0) return MOLSDE_OK;
     if (!pos || !node_ptr || !rowptr || !col || B < 0) return MOLSDE_ERR_INVALID;
     if (B == 0) return MOLSDE_OK;
     int blocks = (B + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -292,8 +294,8 @@ int molsde_csr_by_target_count(const int64_t* edge_index, int64_t E, int64_t N, 
 int molsde_csr_by_target_fill(const int64_t* edge_index, int64_t E, const int32_t* node_ptr,
                               const int32_t* edge_ptr, int32_t B, const int32_t* rowptr, int32_t* src,
                               int32_t* perm, void* stream) {
-    if (!node_ptr || !edge_ptr || !rowptr || !src || B < 0) return MOLSDE_ERR_INVALID;
     if (B == 0 || E == 0) return MOLSDE_OK;
+    if (!node_ptr || !edge_ptr || !rowptr || !src || B < 0) return MOLSDE_ERR_INVALID;
     int blocks = (B + kWarpsPerCta - 1) / kWarpsPerCta;
     csr_fill_kernel<<<blocks, kWarpsPerCta * 32, 0, as_stream(stream)>>>(edge_index, E, node_ptr, edge_ptr, B,
                                                                        rowptr, src, perm);
