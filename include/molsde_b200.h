@@ -144,6 +144,26 @@ int molsde_edge2d_emb_eval(const molsde_plan* plan, const float* uv, const float
 int molsde_sde2d3d_score(const molsde_plan* plan, const molsde_sde2d3d_params* params, const float* nattr,
                          const float* e2d_tiles, const float* pos, const float* std, float* score,
                          float* scratch, int64_t scratch_floats, int32_t* status_flag, void* stream);
+/* SDEModel2Dto3D_02.forward pieces (train mode, SDE_model_2D_to_3D.py:306-391; forward values):
+ *  - molsde_edge2d_bn_train: BatchNorm1d(300) of edge_2D_emb with BATCH statistics over the E pre-activations
+ *    uv[src,:F] + uv[tgt,F:]; folds the normalisation into uv in place (then molsde_edge2d_emb_eval applies), returns the
+ *    batch mean / biased variance and updates the running statistics (momentum, unbiased variance) when given;
+ *  - molsde_sde2d3d_forward_net: raw network output ("gradient", :379) at perturbed positions; attn_keep [4][E][8] (CSR
+ *    edge order) / ffn_keep [4][N][32] are the 0/1 keep-masks of the two dropouts of every GATLayer (NULL = eval);
+ *  - molsde_dsm_pos_loss: out[g] = mean_{i in g} sum_xyz (score-noise)^2 * w[i], mean_out[0] = mean_g out[g] (:380-390;
+ *    w NULL = 1, mean_out optional). */
+int molsde_edge2d_bn_train(const molsde_plan* plan, float* uv, int32_t F, const float* gamma, const float* beta, float eps,
+                           float momentum, float* running_mean, float* running_var, float* batch_mean, float* batch_var,
+                           void* stream);
+int molsde_sde2d3d_forward_net(const molsde_plan* plan, const molsde_sde2d3d_params* params, const float* nattr,
+                               const float* e2d_tiles, const float* pos, const float* attn_keep, const float* ffn_keep,
+                               float dropout_p, float* gradient, float* scratch, int64_t scratch_floats, int32_t* status_flag,
+                               void* stream);
+/* out[i,:] = mean_coeff[i] * x[i,:] + stdv[i] * noise[i,:]  (forward perturbation, :331-332; mean_coeff NULL = 1) */
+int molsde_perturb_rows(const float* x, const float* mean_coeff, const float* stdv, const float* noise, int64_t N, int32_t D,
+                        float* out, void* stream);
+int molsde_dsm_pos_loss(const float* score, const float* noise, const float* w, const int32_t* node_ptr, int32_t B, float* out,
+                        float* mean_out, void* stream);
 int64_t molsde_sde2d3d_scratch_floats(const molsde_plan* plan, int32_t max_chunk_tiles, int32_t* num_ctas_out);
 int64_t molsde_tile_floats(void);
 

@@ -34,7 +34,7 @@ EXPORTS = [
     "molsde_csr_by_target_count", "molsde_csr_by_target_fill",
     "molsde_linear",
     "molsde_edge2d_emb_eval", "molsde_sde2d3d_score", "molsde_sde2d3d_scratch_floats", "molsde_tile_floats",
-    "molsde_sde2d3d_pc_sample",
+    "molsde_sde2d3d_pc_sample", "molsde_edge2d_bn_train", "molsde_sde2d3d_forward_net", "molsde_dsm_pos_loss", "molsde_perturb_rows",
     "molsde_schnet_cfconv", "molsde_gather_rows", "molsde_segment_reduce", "molsde_ebm_node_dot",
     "molsde_to_dense_batch", "molsde_to_dense_adj", "molsde_node_flags", "molsde_grouped_linear", "molsde_dense_pow2",
     "molsde_dense_gcn", "molsde_dense_attn", "molsde_dense_pair_post", "molsde_dense_edge_final",
@@ -127,6 +127,12 @@ def lib() -> ctypes.CDLL:
     L.molsde_sde2d3d_scratch_floats.argtypes = [POINTER(Plan), c_int32, POINTER(c_int32)]
     L.molsde_sde2d3d_scratch_floats.restype = c_int64
     L.molsde_tile_floats.restype = c_int64
+    L.molsde_edge2d_bn_train.argtypes = [POINTER(Plan), c_void_p, c_int32, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]
+    L.molsde_sde2d3d_forward_net.argtypes = [POINTER(Plan), POINTER(Params), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_float, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+    L.molsde_perturb_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    L.molsde_dsm_pos_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
     L.molsde_sde2d3d_pc_sample.argtypes = [POINTER(Plan), POINTER(Params), c_void_p, c_void_p, c_void_p, c_void_p,
                                            POINTER(PCConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_int64, c_void_p, c_void_p, c_void_p]

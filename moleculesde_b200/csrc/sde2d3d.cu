@@ -104,6 +104,11 @@ struct Chunk {
     int edge0;   // first global CSR edge
     int tile0;   // first global tile
     int ntiles;
+    // train mode (SDEModel2Dto3D_02.forward): keep-masks of the attention / FFN dropouts, NULL in eval mode
+    const float* attn_keep;  // [4 layers][E][8] in CSR edge order (0 or 1)
+    const float* ffn_keep;   // [4 layers][N][32]
+    float inv_keep;          // 1 / (1 - p)
+    int64_t E_total, N_total;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -385,7 +390,7 @@ __device__ __noinline__ void node_qkv(const Chunk c) {
 // attention over the incoming edges of every target: logits, segment softmax (+1e-16), weighted
 // messages, deterministic ascending-source sum; the aggregate overwrites q[target].
 __device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __restrict__ src_g,
-                                            const float* __restrict__ scratch) {
+                                            const float* __restrict__ scratch, int layer) {
     float* sm = c.sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = warp >> 3, slab = warp & 7, gt = tid & (GTHREADS - 1);
@@ -454,7 +459,9 @@ __device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __rest
 #pragma unroll
                 for (int nb = 0; nb < 4; ++nb) {
                     const int col = nb * 8 + 2 * t4, hd = col >> 2;
-                    const float a = __fdividef(__expf(L[s * 8 + hd] - smax[pb + hd]), ssum[pb + hd] + 1e-16f);
+                    float a = __fdividef(__expf(L[s * 8 + hd] - smax[pb + hd]), ssum[pb + hd] + 1e-16f);
+                    if (c.attn_keep)  // F.dropout(alpha, p) in train mode (TransformerConv.message)
+                        a *= c.attn_keep[(static_cast<size_t>(layer) * c.E_total + c.edge0 + ti.ea + s) * 8 + hd] * c.inv_keep;
                     Mm[s * LDM + col] = e[nb][2 * rr] * a;
                     Mm[s * LDM + col + 1] = e[nb][2 * rr + 1] * a;
                 }
@@ -504,7 +511,7 @@ __device__ __forceinline__ void layer_norm_quad(float (&v)[4][4], const float* _
 
 // x <- x + LN1(agg + skip(x));  x <- x + LN2(FFN(x));  optional SiLU  (equivariant_scorenetwork.py:35-38,140-141)
 // Each warp owns 16 nodes end to end (only __syncwarp between its GEMMs).
-__device__ __noinline__ void node_update(const Chunk c, bool silu_after) {
+__device__ __noinline__ void node_update(const Chunk c, bool silu_after, int layer) {
     float* sm = c.sm;
     float* XT = sm + S_XT;
     float* NT = sm + S_A;  // [32][LDX] staging of the FFN input / hidden, k-major
@@ -554,7 +561,13 @@ __device__ __noinline__ void node_update(const Chunk c, bool silu_after) {
             const int col = nb * 8 + 2 * t4 + j;
             const float bj = Wg[MOLSDE_G_F0_B + col];
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) NT[col * LDX + m0 + g + 8 * rr] = silu_fast(acc[nb][2 * rr + j] + bj);
+            for (int rr = 0; rr < 2; ++rr) {
+                const int node = m0 + g + 8 * rr;
+                float hv = silu_fast(acc[nb][2 * rr + j] + bj);
+                if (c.ffn_keep && node < c.n)  // nn.Dropout between FFN.1 (SiLU) and FFN.3 in train mode
+                    hv *= c.ffn_keep[(static_cast<size_t>(layer) * c.N_total + c.node0 + node) * 32 + col] * c.inv_keep;
+                NT[col * LDX + node] = hv;
+            }
         }
     __syncwarp();
     zero_frag(acc);
@@ -821,10 +834,10 @@ __device__ __noinline__ uint32_t score_eval(const Chunk c, const float* __restri
             node_qkv(c);
             __syncthreads();
             PROF_ADD(2);
-            gat_edge_phase(c, src_g, scratch);
+            gat_edge_phase(c, src_g, scratch, 2 * module + conv);
             __syncthreads();
             PROF_ADD(3);
-            node_update(c, conv == 0);
+            node_update(c, conv == 0, 2 * module + conv);
             __syncthreads();
             PROF_ADD(4);
         }
@@ -885,11 +898,14 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 sde2d3d_score_kernel(molsde_plan plan, const float* __restrict__ blob, const float* __restrict__ nattr,
                      const float* __restrict__ e2d_tiles, const float* __restrict__ pos,
                      const float* __restrict__ stdv, float* __restrict__ score, float* __restrict__ scratch,
-                     int64_t scratch_stride, int32_t* status_flag) {
+                     int64_t scratch_stride, int32_t* status_flag, const float* __restrict__ attn_keep,
+                     const float* __restrict__ ffn_keep, float inv_keep) {
     extern __shared__ __align__(128) float smem[];
     Chunk c;
     c.sm = smem;
     c.si = reinterpret_cast<int*>(smem + S_FLOATS);
+    c.attn_keep = attn_keep; c.ffn_keep = ffn_keep; c.inv_keep = inv_keep;
+    c.E_total = plan.E; c.N_total = plan.N;
     float* my_scratch = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
     const uint32_t tmem_base = tmem_setup(c.si);
     uint32_t phase = 0;
@@ -900,8 +916,8 @@ sde2d3d_score_kernel(molsde_plan plan, const float* __restrict__ blob, const flo
         __syncthreads();
         phase = score_eval(c, blob, plan.src, nattr, e2d_tiles, my_scratch, tmem_base, phase, status_flag);
         for (int i = threadIdx.x; i < c.n * 3; i += NTHREADS) {
-            // scores = -output / std  (:440-443)
-            score[static_cast<size_t>(c.node0) * 3 + i] = __fdiv_rn(-smem[S_GRAD + i], stdv[c.node0 + i / 3]);
+            // get_score: scores = -output / std  (:440-443);  forward (stdv == NULL): the raw network output (:379)
+            score[static_cast<size_t>(c.node0) * 3 + i] = stdv ? __fdiv_rn(-smem[S_GRAD + i], stdv[c.node0 + i / 3]) : smem[S_GRAD + i];
         }
     }
     tmem_teardown(tmem_base);
@@ -962,6 +978,7 @@ sde2d3d_pc_kernel(molsde_plan plan, const float* __restrict__ blob, const float*
     c.sm = smem;
     c.si = reinterpret_cast<int*>(smem + S_FLOATS);
     int* misc = c.si + SI_MISC;
+    c.attn_keep = nullptr; c.ffn_keep = nullptr; c.inv_keep = 1.0f; c.E_total = plan.E; c.N_total = plan.N;
     const uint32_t tmem_base = tmem_setup(c.si);
     uint32_t phase = 0;
     float* my_scratch = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
@@ -1113,6 +1130,108 @@ edge2d_emb_kernel(molsde_plan plan, const float* __restrict__ uv, const float* _
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// edge_2D_emb in TRAIN mode (SDE_model_2D_to_3D.py:265,345-347): BatchNorm1d(300) uses the batch statistics of the
+// E x 300 pre-activations  pre[e,f] = U[src_e,f] + V[tgt_e,f]  (uv = node-factored first layer incl. bias).
+// One CTA per feature; fp64 two-pass mean / biased variance in a fixed order (deterministic); then the affine
+// normalisation is folded into uv in place (U' = U*s + shift, V' = V*s) so that the eval-mode tile kernel applies, and
+// the running statistics are updated (momentum 0.1, unbiased variance) like nn.BatchNorm1d.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_edge_stats_kernel(const float* __restrict__ uv, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src, int64_t N,
+                     int64_t E, int F, float* __restrict__ mean_out, float* __restrict__ var_out) {
+    __shared__ double red[256];
+    __shared__ double s_mean;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    // pass 1: sum over edges = sum over targets i of (sum_{j in N(i)} U[j,f]) + deg(i) * V[i,f]
+    double acc = 0.0;
+    for (int64_t i = tid; i < N; i += 256) {
+        const int a = rowptr[i], b = rowptr[i + 1];
+        const double v = uv[i * 2 * F + F + f];
+        for (int e = a; e < b; ++e) acc += static_cast<double>(uv[static_cast<int64_t>(src[e]) * 2 * F + f]) + v;
+    }
+    red[tid] = acc;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int q = 0; q < 256; ++q) t += red[q]; s_mean = t / static_cast<double>(E); }
+    __syncthreads();
+    const double mu = s_mean;
+    acc = 0.0;
+    for (int64_t i = tid; i < N; i += 256) {
+        const int a = rowptr[i], b = rowptr[i + 1];
+        const double v = uv[i * 2 * F + F + f];
+        for (int e = a; e < b; ++e) {
+            const double d = static_cast<double>(uv[static_cast<int64_t>(src[e]) * 2 * F + f]) + v - mu;
+            acc += d * d;
+        }
+    }
+    red[tid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int q = 0; q < 256; ++q) t += red[q];
+        mean_out[f] = static_cast<float>(mu);
+        var_out[f] = static_cast<float>(t / static_cast<double>(E));  // biased (normalisation)
+    }
+}
+
+__global__ void bn_fold_uv_kernel(float* __restrict__ uv, int64_t N, int F, const float* __restrict__ mean,
+                                  const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  float eps) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= N * 2 * F) return;
+    const int c = static_cast<int>(idx % (2 * F)), f = c % F;
+    const float sc = gamma[f] / sqrtf(var[f] + eps);
+    uv[idx] = (c < F) ? fmaf(uv[idx], sc, beta[f] - mean[f] * sc) : uv[idx] * sc;
+}
+
+__global__ void bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict__ var, int F, int64_t E,
+                                         float momentum, float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const float unbiased = var[f] * (static_cast<float>(E) / static_cast<float>(E > 1 ? E - 1 : 1));
+    running_mean[f] = (1.0f - momentum) * running_mean[f] + momentum * mean[f];
+    running_var[f] = (1.0f - momentum) * running_var[f] + momentum * unbiased;
+}
+
+// pos_perturbed = mean_coeff[i] * pos + std[i] * noise   (SDE_model_2D_to_3D.py:331-332; mean_coeff NULL = 1, VE)
+__global__ void perturb_rows_kernel(const float* __restrict__ x, const float* __restrict__ mean_coeff, const float* __restrict__ stdv,
+                                    const float* __restrict__ noise, int64_t N, int D, float* __restrict__ out) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= N * D) return;
+    const int64_t i = idx / D;
+    const float m = mean_coeff ? __fmul_rn(mean_coeff[i], x[idx]) : x[idx];
+    out[idx] = __fadd_rn(m, __fmul_rn(stdv[i], noise[idx]));
+}
+
+// loss_pos[g] = mean_{i in g} sum_xyz (score - noise)^2 * w[i]   (SDE_model_2D_to_3D.py:380-386), one warp per graph
+__global__ void dsm_pos_loss_kernel(const float* __restrict__ score, const float* __restrict__ noise, const float* __restrict__ w,
+                                    const int32_t* __restrict__ node_ptr, int B, float* __restrict__ out) {
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (g >= B) return;
+    const int a = node_ptr[g], b = node_ptr[g + 1];
+    float acc = 0.0f;
+    for (int i = a + lane; i < b; i += 32) {
+        const float dx = score[3 * i] - noise[3 * i], dy = score[3 * i + 1] - noise[3 * i + 1], dz = score[3 * i + 2] - noise[3 * i + 2];
+        acc += (dx * dx + dy * dy + dz * dz) * (w ? w[i] : 1.0f);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[g] = acc / static_cast<float>(max(b - a, 1));
+}
+
+// fixed-order mean of B floats (one CTA): loss_pos.mean()
+__global__ void __launch_bounds__(256) mean_kernel(const float* __restrict__ v, int B, float* __restrict__ out) {
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < B; i += 256) acc += v[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int q = 0; q < 256; ++q) t += red[q];
+        out[0] = static_cast<float>(t / B);
+    }
+}
+
 }  // namespace molsde
 
 using namespace molsde;
@@ -1137,6 +1256,44 @@ int molsde_debug_read_prof(unsigned long long* host_out) {
 
 int64_t molsde_tile_floats(void) { return TILE_FLOATS; }
 
+int molsde_edge2d_bn_train(const molsde_plan* plan, float* uv, int32_t F, const float* gamma, const float* beta, float eps,
+                           float momentum, float* running_mean, float* running_var, float* batch_mean, float* batch_var,
+                           void* stream) {
+    if (!plan_ok(plan) || !uv || !gamma || !beta || !batch_mean || !batch_var || F <= 0 || plan->E <= 0) return MOLSDE_ERR_INVALID;
+    bn_edge_stats_kernel<<<F, 256, 0, as_stream(stream)>>>(uv, plan->rowptr, plan->src, plan->N, plan->E, F, batch_mean, batch_var);
+    int st = check_launch("bn_edge_stats");
+    if (st != MOLSDE_OK) return st;
+    const int64_t total = plan->N * 2 * F;
+    bn_fold_uv_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(uv, plan->N, F, batch_mean, batch_var,
+                                                                                            gamma, beta, eps);
+    st = check_launch("bn_fold_uv");
+    if (st != MOLSDE_OK) return st;
+    if (running_mean && running_var) {
+        bn_running_update_kernel<<<(F + 127) / 128, 128, 0, as_stream(stream)>>>(batch_mean, batch_var, F, plan->E, momentum,
+                                                                               running_mean, running_var);
+        st = check_launch("bn_running_update");
+    }
+    return st;
+}
+
+int molsde_perturb_rows(const float* x, const float* mean_coeff, const float* stdv, const float* noise, int64_t N, int32_t D,
+                        float* out, void* stream) {
+    if (!x || !stdv || !noise || !out || N < 0 || D <= 0) return MOLSDE_ERR_INVALID;
+    if (N == 0) return MOLSDE_OK;
+    perturb_rows_kernel<<<static_cast<unsigned>((N * D + 255) / 256), 256, 0, as_stream(stream)>>>(x, mean_coeff, stdv, noise, N, D, out);
+    return check_launch("perturb_rows");
+}
+
+int molsde_dsm_pos_loss(const float* score, const float* noise, const float* w, const int32_t* node_ptr, int32_t B, float* out,
+                        float* mean_out, void* stream) {
+    if (!score || !noise || !node_ptr || !out || B <= 0) return MOLSDE_ERR_INVALID;
+    dsm_pos_loss_kernel<<<(B + 3) / 4, 128, 0, as_stream(stream)>>>(score, noise, w, node_ptr, B, out);
+    int st = check_launch("dsm_pos_loss");
+    if (st != MOLSDE_OK || !mean_out) return st;
+    mean_kernel<<<1, 256, 0, as_stream(stream)>>>(out, B, mean_out);
+    return check_launch("dsm_pos_loss.mean");
+}
+
 int64_t molsde_sde2d3d_scratch_floats(const molsde_plan* plan, int32_t max_chunk_tiles, int32_t* num_ctas_out) {
     if (!plan || max_chunk_tiles < 0) return MOLSDE_ERR_INVALID;
     int ctas = plan->num_chunks < kNumSMs ? plan->num_chunks : kNumSMs;
@@ -1157,10 +1314,10 @@ int molsde_edge2d_emb_eval(const molsde_plan* plan, const float* uv, const float
     return check_launch("edge2d_emb");
 }
 
-int molsde_sde2d3d_score(const molsde_plan* plan, const molsde_sde2d3d_params* params, const float* nattr,
-                         const float* e2d_tiles, const float* pos, const float* stdv, float* score, float* scratch,
-                         int64_t scratch_floats, int32_t* status_flag, void* stream) {
-    if (!plan_ok(plan) || !params || !params->blob || !nattr || !e2d_tiles || !pos || !stdv || !score || !scratch)
+static int launch_score(const molsde_plan* plan, const molsde_sde2d3d_params* params, const float* nattr, const float* e2d_tiles,
+                        const float* pos, const float* stdv, float* score, float* scratch, int64_t scratch_floats,
+                        int32_t* status_flag, const float* attn_keep, const float* ffn_keep, float inv_keep, void* stream) {
+    if (!plan_ok(plan) || !params || !params->blob || !nattr || !e2d_tiles || !pos || !score || !scratch)
         return MOLSDE_ERR_INVALID;
     if (params->blob_floats < MOLSDE_P_TOTAL) return MOLSDE_ERR_INVALID;
     if (plan->num_chunks == 0) return MOLSDE_OK;
@@ -1170,8 +1327,26 @@ int molsde_sde2d3d_score(const molsde_plan* plan, const molsde_sde2d3d_params* p
     cudaError_t err = cudaFuncSetAttribute(sde2d3d_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (err != cudaSuccess) { set_last_error(cudaGetErrorString(err)); return MOLSDE_ERR_CUDA; }
     sde2d3d_score_kernel<<<ctas, NTHREADS, SMEM_BYTES, as_stream(stream)>>>(*plan, params->blob, nattr, e2d_tiles, pos,
-                                                                          stdv, score, scratch, stride, status_flag);
+                                                                          stdv, score, scratch, stride, status_flag,
+                                                                          attn_keep, ffn_keep, inv_keep);
     return check_launch("sde2d3d_score");
+}
+
+int molsde_sde2d3d_score(const molsde_plan* plan, const molsde_sde2d3d_params* params, const float* nattr,
+                         const float* e2d_tiles, const float* pos, const float* stdv, float* score, float* scratch,
+                         int64_t scratch_floats, int32_t* status_flag, void* stream) {
+    if (!stdv) return MOLSDE_ERR_INVALID;
+    return launch_score(plan, params, nattr, e2d_tiles, pos, stdv, score, scratch, scratch_floats, status_flag, nullptr, nullptr,
+                        1.0f, stream);
+}
+
+int molsde_sde2d3d_forward_net(const molsde_plan* plan, const molsde_sde2d3d_params* params, const float* nattr,
+                               const float* e2d_tiles, const float* pos, const float* attn_keep, const float* ffn_keep,
+                               float dropout_p, float* gradient, float* scratch, int64_t scratch_floats, int32_t* status_flag,
+                               void* stream) {
+    if ((attn_keep == nullptr) != (ffn_keep == nullptr) || dropout_p < 0.0f || dropout_p >= 1.0f) return MOLSDE_ERR_INVALID;
+    return launch_score(plan, params, nattr, e2d_tiles, pos, nullptr, gradient, scratch, scratch_floats, status_flag, attn_keep,
+                        ffn_keep, 1.0f / (1.0f - dropout_p), stream);
 }
 
 int molsde_sde2d3d_pc_sample(const molsde_plan* plan, const molsde_sde2d3d_params* params, const float* nattr,

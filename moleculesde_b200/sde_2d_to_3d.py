@@ -249,8 +249,11 @@ class SDEModel2Dto3D_02(nn.Module):
         E = self.emb_dim
         w_uv = torch.cat([W0[:, :E] * s[:, None], W0[:, E:] * s[:, None]], dim=0).contiguous()  # [2E, E]
         b_uv = torch.cat([b0 * s + shift, torch.zeros_like(b0)]).contiguous()
+        w_uv_raw = torch.cat([W0[:, :E], W0[:, E:]], dim=0).contiguous()   # train mode: BN uses batch statistics
+        b_uv_raw = torch.cat([b0, torch.zeros_like(b0)]).contiguous()
         packed = {
-            "blob": blob, "w_uv": w_uv, "b_uv": b_uv,
+            "blob": blob, "w_uv": w_uv, "b_uv": b_uv, "w_uv_raw": w_uv_raw, "b_uv_raw": b_uv_raw,
+            "bn_w": sd["edge_2D_emb.1.weight"].contiguous(), "bn_b": sd["edge_2D_emb.1.bias"].contiguous(),
             "w3t": sd["edge_2D_emb.3.weight"].t().contiguous(), "b3": sd["edge_2D_emb.3.bias"].contiguous(),
             "w_node": sd["node_emb.layers.0.weight"].contiguous(), "b_node": sd["node_emb.layers.0.bias"].contiguous(),
         }
@@ -299,9 +302,87 @@ class SDEModel2Dto3D_02(nn.Module):
         return nattr, e2d
 
     # ------------------------------------------------------------------ reference API
-    def forward(self, node_2D_repr, data, anneal_power):
-        raise NotImplementedError(
-            "training loss of SDEModel2Dto3D_02 (backward kernels) is not built yet; see DESIGN.md, scope table row a6/a13")
+    def _train_invariants(self, node_2D_repr: torch.Tensor, prep: PreparedGraph):
+        """`node_emb(h)` and `edge_2D_emb(cat(h[row], h[col]))` with BatchNorm in TRAIN mode: batch statistics over the
+        E edges, running statistics updated in place (`SDE_model_2D_to_3D.py:265,345-347`)."""
+        pk = self.packed_params()
+        h = node_2D_repr.detach().float().contiguous()
+        N, dev, s = h.size(0), h.device, stream_ptr(h)
+        F = self.emb_dim
+        nattr = torch.empty(N, _abi.HID, dtype=torch.float32, device=dev)
+        check(lib().molsde_linear(ptr(h), N, F, F, ptr(pk["w_node"]), ptr(pk["b_node"]), _abi.HID,
+                                  ptr(nattr), _abi.HID, 0, None, 0, None, s), "node_emb")
+        uv = torch.empty(N, 2 * F, dtype=torch.float32, device=dev)
+        check(lib().molsde_linear(ptr(h), N, F, F, ptr(pk["w_uv_raw"]), ptr(pk["b_uv_raw"]), 2 * F, ptr(uv), 2 * F,
+                                  0, None, 0, None, s), "edge_2D_emb.0")
+        bn = self.edge_2D_emb[1]
+        mean, var = torch.empty(F, dtype=torch.float32, device=dev), torch.empty(F, dtype=torch.float32, device=dev)
+        st = prep.plan.as_struct()
+        check(lib().molsde_edge2d_bn_train(ctypes.byref(st), ptr(uv), F, ptr(pk["bn_w"]), ptr(pk["bn_b"]), bn.eps, bn.momentum,
+                                           ptr(bn.running_mean), ptr(bn.running_var), ptr(mean), ptr(var), s), "edge2d_bn_train")
+        bn.num_batches_tracked += 1
+        e2d = torch.empty(max(prep.plan.num_tiles, 1) * _abi.TILE_FLOATS, dtype=torch.float32, device=dev)
+        check(lib().molsde_edge2d_emb_eval(ctypes.byref(st), ptr(uv), ptr(pk["w3t"]), ptr(pk["b3"]), ptr(e2d), s),
+              "edge2d_emb_eval")
+        return nattr, e2d, pk["blob"]
+
+    @torch.no_grad()
+    def forward(self, node_2D_repr, data, anneal_power, draws: Optional[dict] = None):
+        """Denoising score-matching loss of `SDE_model_2D_to_3D.py:306-391` (forward VALUE; the backward kernels are not
+        built yet, so the returned loss carries no autograd graph).  `draws` injects the random draws for parity tests:
+        `noise` [N,3], `time_step` (the `randint` of :322, [B//2+1]), `dropout` = 4 x (attn_mask [E,8] in
+        `extended_edge_index` order, ffn_mask [N,32]) in GATLayer call order; missing entries are drawn with torch's RNG."""
+        draws = draws or {}
+        pos = data.positions.detach().float().contiguous()
+        require_device(pos)
+        prep = self.prepared(data)
+        N, dev, s, B = pos.size(0), pos.device, stream_ptr(pos), data.num_graphs
+        E = prep.csr.num_edges
+        noise = draws.get("noise")
+        noise = torch.randn_like(pos) if noise is None else noise.to(dev).float().contiguous()
+        ts = draws.get("time_step")
+        T = self.num_diffusion_timesteps
+        ts = torch.randint(0, T, size=(B // 2 + 1,), device=dev) if ts is None else ts.to(dev)
+        ts = torch.cat([ts, T - ts - 1], dim=0)[:B]
+        if self.SDE_type in ("VE", "VP"):
+            ts = ts / T * (1 - 1e-6) + 1e-6
+        t_pos = ts.index_select(0, data.batch)
+        # schedule scalars per node ([N]-sized bookkeeping on the SDE object); the perturbation itself is a kernel
+        coeff, std = self.sde_pos.marGINal_prob(torch.ones(N, 1, device=dev), t_pos)
+        coeff = coeff.reshape(-1).float().contiguous() if isinstance(self.sde_pos, VPSDE) else None
+        std = std.float().contiguous()
+        pos_p = torch.empty_like(pos)
+        check(lib().molsde_perturb_rows(ptr(pos), ptr(coeff), ptr(std), ptr(noise), N, 3, ptr(pos_p), s), "perturb_rows")
+
+        p_drop = self.score_network.dropout
+        attn_keep = ffn_keep = None
+        if self.training:
+            nattr, e2d, blob = self._train_invariants(node_2D_repr, prep)
+            masks = draws.get("dropout")
+            if masks is None:
+                attn_keep = (torch.rand(4, E, 8, device=dev) >= p_drop).float()       # already CSR order: i.i.d.
+                ffn_keep = (torch.rand(4, N, _abi.HID, device=dev) >= p_drop).float()
+            else:
+                perm = prep.csr.perm.long()
+                attn_keep = torch.stack([m[0].to(dev).float()[perm] for m in masks]).contiguous()
+                ffn_keep = torch.stack([m[1].to(dev).float() for m in masks]).contiguous()
+        else:
+            nattr, e2d = self.invariants(node_2D_repr, prep)
+            blob = self.packed_params()["blob"]
+        grad = torch.empty_like(pos)
+        scratch = prep.get_scratch()
+        st = prep.plan.as_struct()
+        prm = _abi.Params(blob.data_ptr(), blob.numel())
+        prep.status.zero_()
+        check(lib().molsde_sde2d3d_forward_net(ctypes.byref(st), ctypes.byref(prm), ptr(nattr), ptr(e2d), ptr(pos_p),
+                                               ptr(attn_keep), ptr(ffn_keep), p_drop if self.training else 0.0, ptr(grad),
+                                               ptr(scratch), scratch.numel(), ptr(prep.status), s), "sde2d3d_forward_net")
+        w = None if anneal_power == 0 else (std ** anneal_power).contiguous()
+        per_graph = torch.empty(B, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        check(lib().molsde_dsm_pos_loss(ptr(grad), ptr(noise), ptr(w), ptr(prep.node_ptr), B, ptr(per_graph), ptr(loss), s),
+              "dsm_pos_loss")
+        return {"position": loss[0]}
 
     @torch.no_grad()
     def get_score(self, node_2D_repr, data, pos_perturbed, sigma, t_pos):

@@ -204,3 +204,57 @@ def test_pc_sampler_philox_mode(golden):
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1])
     assert not torch.equal(outs[0], outs[2])
+
+
+def _train_draws(sec):
+    draws = sec["train_draws"]
+    assert [k for k, _ in draws] == ["randn", "randint"] + ["dropout"] * 8
+    masks = [v for _, v in draws[2:]]
+    return {"noise": draws[0][1], "time_step": draws[1][1],
+            "dropout": [(masks[2 * i], masks[2 * i + 1]) for i in range(4)]}
+
+
+@pytest.mark.parametrize("kind", ["VE", "VP"])
+def test_train_loss_vs_golden(kind, golden, golden_batch):
+    """SDEModel2Dto3D_02.forward in train mode (dropout masks + BatchNorm batch statistics) against the loss the
+    reference produced with the same recorded draws, incl. the running-statistic update of edge_2D_emb.1."""
+    dev = _dev()
+    _, batch = golden_batch
+    model, _ = _model(golden, kind, dev)
+    model.train()
+    sec = golden["sde2d3d_" + kind]
+    b = _gpu_batch(batch, dev)
+    h2d = golden["gnn"]["h_eval"].to(dev)
+    out = model(h2d, b, 0, draws=_train_draws(sec))
+    assert_parity(out["position"].reshape(1), sec["train_loss"].reshape(1), f"train loss[{kind}]")
+    assert_parity(model.edge_2D_emb[1].running_mean, sec["bn_running_mean"], "BN running_mean")
+    assert_parity(model.edge_2D_emb[1].running_var, sec["bn_running_var"], "BN running_var")
+    assert int(model.edge_2D_emb[1].num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("anneal_power", [0.0, 2.0])
+def test_eval_loss_vs_oracle(anneal_power, golden, golden_batch):
+    """forward() in eval mode (no dropout, BN running statistics) and the annealed weighting vs the oracle."""
+    dev = _dev()
+    _, batch = golden_batch
+    model, sd = _model(golden, "VP", dev)
+    sec = golden["sde2d3d_VP"]
+    d = _train_draws(sec)
+    b = _gpu_batch(batch, dev)
+    h2d = golden["gnn"]["h_eval"]
+    out = model(h2d.to(dev), b, anneal_power, draws={"noise": d["noise"], "time_step": d["time_step"]})
+    ref = O.loss_2d3d(sd, O.make_sde("VP", 0.2, 1.0, 1000), h2d, batch.extended_edge_index, batch.positions, batch.batch,
+                      batch.num_graphs, d["noise"], d["time_step"], 1000, anneal_power, None, False)
+    assert_parity(out["position"].reshape(1), ref.reshape(1), f"eval loss anneal={anneal_power}")
+
+
+def test_train_loss_random_draws_finite(golden, golden_batch):
+    """Without injected draws the step draws its own noise / timesteps / dropout masks."""
+    dev = _dev()
+    _, batch = golden_batch
+    model, _ = _model(golden, "VE", dev)
+    model.train()
+    b = _gpu_batch(batch, dev)
+    torch.manual_seed(0)
+    out = model(golden["gnn"]["h_eval"].to(dev), b, 0)
+    assert torch.isfinite(out["position"]) and out["position"].item() > 0
