@@ -266,6 +266,77 @@ int molsde_reverse_update(const float* x, const float* score, const float* z, co
                           int64_t M, float* x_new, float* x_mean, void* stream);
 int molsde_mask_rows(const float* x, const float* flags, int64_t rows, int32_t cols, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Pretraining step (examples/pretrain_MoleculeSDE.py:105-152): layer-granular forward ops that keep their
+ * intermediates, and the backward kernel of every op on the path (csrc/train*.cu).  fp32, deterministic.
+ * The reference gets these from torch.autograd; a maintainer binds them as autograd.Function pairs.
+ * ---------------------------------------------------------------------------------- */
+
+/* C[M,N] (+)= op(A)[M,K] . op(B)[K,N];  transA: A stored [K][lda];  transB: B stored [N][ldb].
+ * Backward of nn.Linear y = x W^T:  dx = dy . W (0,0);  dW = dy^T . x (1,0; split-K over the rows, workspace
+ * molsde_gemm_ws_floats, may be NULL = no split). */
+int64_t molsde_gemm_ws_floats(int64_t M, int64_t N, int64_t K);
+int molsde_gemm(int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                int64_t ldb, float* C, int64_t ldc, int32_t accumulate, float* ws, int64_t ws_floats, void* stream);
+/* out[n] (+)= sum_m X[m,n]  (bias gradients) */
+int64_t molsde_colsum_ws_floats(int64_t M, int32_t N);
+int molsde_colsum(const float* X, int64_t M, int32_t N, int64_t ldx, float* out, int32_t accumulate, float* ws, int64_t ws_floats,
+                  void* stream);
+/* y = act(x);  dx = dy * act'(x) with x the pre-activation (act codes of molsde_linear) */
+int molsde_act_fwd(const float* x, int64_t n, int32_t act, float* y, void* stream);
+int molsde_act_bwd(const float* x, const float* dy, int64_t n, int32_t act, float* dx, void* stream);
+/* op 0: out = a + alpha*b (b NULL: alpha*a);  op 1: out = a*b (+c);  op 2: out[r,:] = a[r,:] * alpha * b[r];  op 3: out[r,c] = a[r,c] + b[c]  (cols per row).
+ * out may alias a. */
+int molsde_ew(int32_t op, const float* a, const float* b, const float* c, float alpha, int64_t n, int64_t cols, float* out,
+              void* stream);
+/* out[r,:] = A[ia[r],:] (+ B[ib[r],:]);  NULL index = identity  (x_j / x_i gathers of MessagePassing) */
+int molsde_gather_pair(const float* A, const int32_t* ia, const float* B, const int32_t* ib, int64_t rows, int32_t cols, float* out,
+                       void* stream);
+/* out[s,:] (+)= scale[s] * sum_{p in [ptr[s],ptr[s+1])} X[perm ? perm[p] : p, :]  (scatter-add / backward of a gather,
+ * as a deterministic gather-reduce over a CSR of the index) */
+int molsde_seg_gather_sum(const float* X, const int32_t* ptr, const int32_t* perm, int64_t segments, int32_t cols, const float* scale,
+                          int32_t accumulate, float* out, void* stream);
+/* stable counting sort of n int64 keys in [0,buckets): count[b]; then (after an exclusive scan -> rowptr) perm */
+int molsde_bucket_count(const int64_t* keys, int64_t n, int32_t buckets, int32_t* count, void* stream);
+int molsde_bucket_fill(const int64_t* keys, int64_t n, int32_t buckets, const int32_t* rowptr, int32_t* perm, void* stream);
+int molsde_expand_rowptr(const int32_t* rowptr, int64_t N, int32_t* row, void* stream);
+/* nn.LayerNorm over the last dim; bwd returns dx and dyx = dy * xhat (dgamma = colsum(dyx), dbeta = colsum(dy)) */
+int molsde_layernorm_fwd(const float* x, int64_t M, int32_t D, const float* g, const float* b, float eps, float* y, float* mean,
+                         float* rstd, void* stream);
+int molsde_layernorm_bwd(const float* x, const float* dy, int64_t M, int32_t D, const float* g, const float* mean, const float* rstd,
+                         float* dx, float* dyx, void* stream);
+/* nn.BatchNorm1d in train mode over rows [M,F] (+ optional fused ReLU, act = 1); running stats updated when given */
+int64_t molsde_bn_ws_doubles(int64_t M, int32_t F);
+int molsde_bn_train_fwd(const float* x, int64_t M, int32_t F, const float* gamma, const float* beta, float eps, float momentum,
+                        float* running_mean, float* running_var, int32_t act, float* y, float* mean, float* rstd, double* ws,
+                        void* stream);
+int molsde_bn_train_bwd(const float* x, const float* dy, int64_t M, int32_t F, const float* gamma, const float* mean,
+                        const float* rstd, float* dx, float* dgamma, float* dbeta, double* ws, void* stream);
+/* torch.optim.Adam step over one flat buffer (pretrain_MoleculeSDE.py:337); g is scaled by grad_scale first (1/world) */
+int molsde_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, int32_t step, float grad_scale, void* stream);
+
+/* SDEModel2Dto3D_02 training ops; edges in CSR-by-target order (tgt = expanded rowptr, src = plan src):
+ *  edge_geom: Fourier features of distance / frame coefficients, pseudo angle (emb[:,0:2], ld 66), frame basis [E,9]
+ *             (SDE_model_2D_to_3D.py:342-366);
+ *  tconv_fwd/bwd: TransformerConv 8x4 message passing on qkvs [N,128] = [q|k|v|skip], eproj [E,32]; keep [E,8] or NULL;
+ *             bwd fills dqkvs [N,128], dkvE [E,64] (scratch) and deproj [E,32]; sptr/sperm = CSR by source;
+ *  equi_fwd/bwd: EquiLayer mean aggregation of sum_k dyn_k basis_k (equivariant_scorenetwork.py:43-78);
+ *  dsm_pos_loss_bwd: gradient of molsde_dsm_pos_loss's mean_out w.r.t. score. */
+int molsde_sde2d3d_edge_geom(const float* pos, const int32_t* src, const int32_t* tgt, int64_t E, const float* w_dist,
+                             const float* w_coff, float* gfd, float* gfi, float* gfj, float* emb, float* basis, void* stream);
+int molsde_tconv_fwd(const float* qkvs, const float* eproj, const int32_t* rowptr, const int32_t* src, int64_t N, const float* keep,
+                     float dropout_p, float* alpha, float* out, void* stream);
+int molsde_tconv_bwd(const float* qkvs, const float* eproj, const int32_t* rowptr, const int32_t* src, const int32_t* sptr,
+                     const int32_t* sperm, int64_t N, const float* keep, float dropout_p, const float* alpha, const float* dout,
+                     float* dqkvs, float* dkvE, float* deproj, void* stream);
+int molsde_equi_fwd(const float* dyn, const float* basis, const int32_t* rowptr, int64_t N, int32_t accumulate, float* grad,
+                    void* stream);
+int molsde_equi_bwd(const float* dgrad, const float* basis, const int32_t* rowptr, const int32_t* tgt, int64_t E, float* ddyn,
+                    void* stream);
+int molsde_dsm_pos_loss_bwd(const float* score, const float* noise, const float* w, const int32_t* node_ptr, const int32_t* node2graph,
+                            int64_t N, int32_t B, float upstream, float* dscore, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

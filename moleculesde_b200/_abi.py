@@ -35,6 +35,11 @@ EXPORTS = [
     "molsde_linear",
     "molsde_edge2d_emb_eval", "molsde_sde2d3d_score", "molsde_sde2d3d_scratch_floats", "molsde_tile_floats",
     "molsde_sde2d3d_pc_sample", "molsde_edge2d_bn_train", "molsde_sde2d3d_forward_net", "molsde_dsm_pos_loss", "molsde_perturb_rows",
+    "molsde_gemm_ws_floats", "molsde_gemm", "molsde_colsum_ws_floats", "molsde_colsum", "molsde_act_fwd", "molsde_act_bwd",
+    "molsde_ew", "molsde_gather_pair", "molsde_seg_gather_sum", "molsde_bucket_count", "molsde_bucket_fill",
+    "molsde_expand_rowptr", "molsde_layernorm_fwd", "molsde_layernorm_bwd", "molsde_bn_ws_doubles", "molsde_bn_train_fwd",
+    "molsde_bn_train_bwd", "molsde_adam_step", "molsde_sde2d3d_edge_geom", "molsde_tconv_fwd", "molsde_tconv_bwd",
+    "molsde_equi_fwd", "molsde_equi_bwd", "molsde_dsm_pos_loss_bwd",
     "molsde_schnet_cfconv", "molsde_gather_rows", "molsde_segment_reduce", "molsde_ebm_node_dot",
     "molsde_to_dense_batch", "molsde_to_dense_adj", "molsde_node_flags", "molsde_grouped_linear", "molsde_dense_pow2",
     "molsde_dense_gcn", "molsde_dense_attn", "molsde_dense_pair_post", "molsde_dense_edge_final",
@@ -127,6 +132,34 @@ def lib() -> ctypes.CDLL:
     L.molsde_sde2d3d_scratch_floats.argtypes = [POINTER(Plan), c_int32, POINTER(c_int32)]
     L.molsde_sde2d3d_scratch_floats.restype = c_int64
     L.molsde_tile_floats.restype = c_int64
+    P = c_void_p
+    L.molsde_gemm_ws_floats.restype = c_int64
+    L.molsde_gemm_ws_floats.argtypes = [c_int64, c_int64, c_int64]
+    L.molsde_gemm.argtypes = [c_int32, c_int32, c_int64, c_int64, c_int64, P, c_int64, P, c_int64, P, c_int64, c_int32, P, c_int64, P]
+    L.molsde_colsum_ws_floats.restype = c_int64
+    L.molsde_colsum_ws_floats.argtypes = [c_int64, c_int32]
+    L.molsde_colsum.argtypes = [P, c_int64, c_int32, c_int64, P, c_int32, P, c_int64, P]
+    L.molsde_act_fwd.argtypes = [P, c_int64, c_int32, P, P]
+    L.molsde_act_bwd.argtypes = [P, P, c_int64, c_int32, P, P]
+    L.molsde_ew.argtypes = [c_int32, P, P, P, c_float, c_int64, c_int64, P, P]
+    L.molsde_gather_pair.argtypes = [P, P, P, P, c_int64, c_int32, P, P]
+    L.molsde_seg_gather_sum.argtypes = [P, P, P, c_int64, c_int32, P, c_int32, P, P]
+    L.molsde_bucket_count.argtypes = [P, c_int64, c_int32, P, P]
+    L.molsde_bucket_fill.argtypes = [P, c_int64, c_int32, P, P, P]
+    L.molsde_expand_rowptr.argtypes = [P, c_int64, P, P]
+    L.molsde_layernorm_fwd.argtypes = [P, c_int64, c_int32, P, P, c_float, P, P, P, P]
+    L.molsde_layernorm_bwd.argtypes = [P, P, c_int64, c_int32, P, P, P, P, P, P]
+    L.molsde_bn_ws_doubles.restype = c_int64
+    L.molsde_bn_ws_doubles.argtypes = [c_int64, c_int32]
+    L.molsde_bn_train_fwd.argtypes = [P, c_int64, c_int32, P, P, c_float, c_float, P, P, c_int32, P, P, P, P, P]
+    L.molsde_bn_train_bwd.argtypes = [P, P, c_int64, c_int32, P, P, P, P, P, P, P, P]
+    L.molsde_adam_step.argtypes = [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int32, c_float, P]
+    L.molsde_sde2d3d_edge_geom.argtypes = [P, P, P, c_int64, P, P, P, P, P, P, P, P]
+    L.molsde_tconv_fwd.argtypes = [P, P, P, P, c_int64, P, c_float, P, P, P]
+    L.molsde_tconv_bwd.argtypes = [P, P, P, P, P, P, c_int64, P, c_float, P, P, P, P, P, P]
+    L.molsde_equi_fwd.argtypes = [P, P, P, c_int64, c_int32, P, P]
+    L.molsde_equi_bwd.argtypes = [P, P, P, P, c_int64, P, P]
+    L.molsde_dsm_pos_loss_bwd.argtypes = [P, P, P, P, P, c_int64, c_int32, c_float, P, P]
     L.molsde_edge2d_bn_train.argtypes = [POINTER(Plan), c_void_p, c_int32, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p]
     L.molsde_sde2d3d_forward_net.argtypes = [POINTER(Plan), POINTER(Params), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

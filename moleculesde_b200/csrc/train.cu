@@ -1,0 +1,522 @@
+// Building blocks of the PRETRAINING step (pretrain_MoleculeSDE.py:105-152): the layer-granular forward ops that keep
+// their intermediates, and the backward kernels of every op on the path.  All fp32 FFMA, deterministic (no atomics:
+// every reduction has a fixed order), so gradients are bit-reproducible and comparable to the reference's autograd at
+// 1e-4.  The sampling path never uses these; it runs the fused kernels of sde2d3d.cu / schnet.cu / dense.cu.
+#include "common.cuh"
+
+namespace molsde {
+
+// =====================================================================================================
+// GEMM  C[M,N] (+)= op(A)[M,K] . op(B)[K,N]     (64x64x16 tile, 256 threads, 4x4 micro-tile, optional split-K)
+//   TA = 0: A stored [M][lda] (k contiguous)      TA = 1: A stored [K][lda] (m contiguous)
+//   TB = 0: B stored [K][ldb] (n contiguous)      TB = 1: B stored [N][ldb] (k contiguous)
+// Backward of y = x W^T:  dx = dy . W  (TA=0,TB=0),   dW = dy^T . x  (TA=1,TB=0; K = #rows -> split-K).
+// =====================================================================================================
+constexpr int GM = 64, GN = 64, GK = 16;
+
+template <int TA, int TB>
+__global__ void __launch_bounds__(256)
+gemm_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
+            float* __restrict__ C, int64_t ldc, int accumulate, int64_t k_per_split, float* __restrict__ ws) {
+    __shared__ float As[GK][GM + 4];
+    __shared__ float Bs[GK][GN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = static_cast<int64_t>(blockIdx.y) * GM, n0 = static_cast<int64_t>(blockIdx.x) * GN;
+    const int64_t kb = static_cast<int64_t>(blockIdx.z) * k_per_split;
+    const int64_t ke = min(K, kb + k_per_split);
+    float acc[4][4] = {};
+    for (int64_t k0 = kb; k0 < ke; k0 += GK) {
+        for (int idx = tid; idx < GM * GK; idx += 256) {
+            int r, c;
+            if (TA) { c = idx / GM; r = idx % GM; } else { r = idx / GK; c = idx % GK; }
+            const int64_t gm = m0 + r, gk = k0 + c;
+            float v = 0.0f;
+            if (gm < M && gk < ke) v = TA ? A[gk * lda + gm] : A[gm * lda + gk];
+            As[c][r] = v;
+        }
+        for (int idx = tid; idx < GN * GK; idx += 256) {
+            int r, c;
+            if (TB) { r = idx / GK; c = idx % GK; } else { c = idx / GN; r = idx % GN; }
+            const int64_t gn = n0 + r, gk = k0 + c;
+            float v = 0.0f;
+            if (gn < N && gk < ke) v = TB ? B[gn * ldb + gk] : B[gk * ldb + gn];
+            Bs[c][r] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* out = ws ? ws + static_cast<size_t>(blockIdx.z) * M * N : C;
+    const int64_t ldo = ws ? N : ldc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j];
+            if (!ws && accumulate) v += out[gm * ldo + gn];
+            out[gm * ldo + gn] = v;
+        }
+    }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t M, int64_t N, float* __restrict__ C,
+                                     int64_t ldc, int accumulate) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= M * N) return;
+    float v = 0.0f;
+    for (int s = 0; s < splits; ++s) v += ws[static_cast<size_t>(s) * M * N + idx];
+    float* c = C + (idx / N) * ldc + idx % N;
+    *c = accumulate ? *c + v : v;
+}
+
+// out[n] (+)= sum_m X[m,n]: CTA = 32 columns x 8 row lanes over one row chunk; partials [chunks][N], fixed-order finish
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ X, int64_t M, int N, int64_t ldx, int64_t rows_per_chunk, float* __restrict__ part) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+    float acc = 0.0f;
+    if (n < N)
+        for (int64_t r = r0 + ty; r < r1; r += 8) acc += X[r * ldx + n];
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        float t = 0.0f;
+        for (int q = 0; q < 8; ++q) t += red[q][tx];
+        part[static_cast<size_t>(blockIdx.y) * N + n] = t;
+    }
+}
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int chunks, int N, float* __restrict__ out, int accumulate) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float t = 0.0f;
+    for (int c = 0; c < chunks; ++c) t += part[static_cast<size_t>(c) * N + n];
+    out[n] = accumulate ? out[n] + t : t;
+}
+
+// ---- activations (act codes of molsde_linear): y = f(x); dx = dy * f'(x) with x the PRE-activation ----
+__device__ __forceinline__ float act_f(float v, int act) {
+    switch (act) {
+        case 1: return fmaxf(v, 0.0f);
+        case 2: return silu_f(v);
+        case 3: return softplus_f(v) - 0.69314718246459961f;
+        case 4: return tanhf(v);
+        case 5: return v > 0.0f ? v : expm1f(v);
+        default: return v;
+    }
+}
+__device__ __forceinline__ float act_df(float x, int act) {
+    switch (act) {
+        case 1: return x > 0.0f ? 1.0f : 0.0f;
+        case 2: { const float s = 1.0f / (1.0f + expf(-x)); return s * (1.0f + x * (1.0f - s)); }
+        case 3: return 1.0f / (1.0f + expf(-x));
+        case 4: { const float t = tanhf(x); return 1.0f - t * t; }
+        case 5: return x > 0.0f ? 1.0f : expf(x);
+        default: return 1.0f;
+    }
+}
+__global__ void act_fwd_kernel(const float* __restrict__ x, int64_t n, int act, float* __restrict__ y) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) y[i] = act_f(x[i], act);
+}
+__global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t n, int act, float* __restrict__ dx) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) dx[i] = dy[i] * act_df(x[i], act);
+}
+
+// ---- elementwise: op 0: out = a + alpha*b (b NULL: alpha*a);  op 1: out = a*b (+ c);  op 2: out = a * alpha * b[row];  op 3: out = a + b[col] ----
+__global__ void ew_kernel(int op, const float* a, const float* b, const float* c, float alpha, int64_t n, int64_t cols, float* out) {
+    // no __restrict__: `out` may alias an input (in-place accumulation)
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    float v;
+    if (op == 0) v = b ? fmaf(alpha, b[i], a[i]) : alpha * a[i];
+    else if (op == 1) v = c ? fmaf(a[i], b[i], c[i]) : a[i] * b[i];
+    else if (op == 2) v = a[i] * alpha * b[i / cols];
+    else v = a[i] + b[i % cols];
+    out[i] = v;
+}
+
+// out[r,:] = A[ia[r],:] (+ B[ib[r],:])      (x_j / x_i gathers of message passing; int32 indices, NULL index = r)
+__global__ void gather_pair_kernel(const float* __restrict__ A, const int32_t* __restrict__ ia, const float* __restrict__ B,
+                                   const int32_t* __restrict__ ib, int64_t rows, int cols, float* __restrict__ out) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const int64_t r = idx / cols;
+    const int c = static_cast<int>(idx % cols);
+    float v = A[static_cast<int64_t>(ia ? ia[r] : r) * cols + c];
+    if (B) v += B[static_cast<int64_t>(ib ? ib[r] : r) * cols + c];
+    out[idx] = v;
+}
+
+// out[s,:] (+)= scale[s] * sum_{p in [ptr[s],ptr[s+1])} X[perm ? perm[p] : p, :]   in ascending p   (backward of a gather)
+__global__ void seg_gather_sum_kernel(const float* __restrict__ X, const int32_t* __restrict__ ptr, const int32_t* __restrict__ perm,
+                                      int64_t segments, int cols, const float* __restrict__ scale, int accumulate,
+                                      float* __restrict__ out) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= segments * cols) return;
+    const int64_t s = idx / cols;
+    const int c = static_cast<int>(idx % cols);
+    float acc = 0.0f;
+    for (int p = ptr[s]; p < ptr[s + 1]; ++p) acc += X[static_cast<int64_t>(perm ? perm[p] : p) * cols + c];
+    if (scale) acc *= scale[s];
+    out[idx] = accumulate ? out[idx] + acc : acc;
+}
+
+// stable bucket sort: rowptr[b], perm = element ids ordered by (key, id).  One CTA per bucket, ascending scan.
+__global__ void bucket_count_kernel(const int64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ count) {
+    __shared__ int red[256];
+    const int b = blockIdx.x;
+    int c = 0;
+    for (int64_t i = threadIdx.x; i < n; i += 256) c += (keys[i] == b);
+    red[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) count[b] = red[0];
+}
+__global__ void bucket_fill_kernel(const int64_t* __restrict__ keys, int64_t n, const int32_t* __restrict__ rowptr,
+                                   int32_t* __restrict__ perm) {
+    // one warp per bucket: ballot-scan in ascending element order
+    const int b = blockIdx.x, lane = threadIdx.x;
+    int pos = rowptr[b];
+    for (int64_t base = 0; base < n; base += 32) {
+        const int64_t i = base + lane;
+        const bool hit = i < n && keys[i] == b;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) perm[pos + __popc(m & ((1u << lane) - 1u))] = static_cast<int32_t>(i);
+        pos += __popc(m);
+    }
+}
+
+// ---- LayerNorm over the last dim (D <= 1024), one warp per row ----
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, int64_t M, int D, const float* __restrict__ g,
+                                     const float* __restrict__ b, float eps, float* __restrict__ y, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out) {
+    const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= M) return;
+    const float* xr = x + r * D;
+    float s = 0.0f;
+    for (int c = lane; c < D; c += 32) s += xr[c];
+    const float mu = warp_sum(s) / D;
+    float v = 0.0f;
+    for (int c = lane; c < D; c += 32) { const float d = xr[c] - mu; v += d * d; }
+    const float rstd = rsqrtf(warp_sum(v) / D + eps);
+    for (int c = lane; c < D; c += 32) y[r * D + c] = (xr[c] - mu) * rstd * g[c] + b[c];
+    if (lane == 0) { mean_out[r] = mu; rstd_out[r] = rstd; }
+}
+// dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat));   dyx = dy * xhat (column-summed by the caller for dgamma)
+__global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t M, int D,
+                                     const float* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     float* __restrict__ dx, float* __restrict__ dyx) {
+    const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= M) return;
+    const float mu = mean[r], rs = rstd[r];
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int c = lane; c < D; c += 32) {
+        const float xh = (x[r * D + c] - mu) * rs, dg = dy[r * D + c] * g[c];
+        s1 += dg;
+        s2 += dg * xh;
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+    for (int c = lane; c < D; c += 32) {
+        const float xh = (x[r * D + c] - mu) * rs, d = dy[r * D + c];
+        dx[r * D + c] = rs * (d * g[c] - s1 - xh * s2);
+        dyx[r * D + c] = d * xh;
+    }
+}
+
+// ---- BatchNorm1d in train mode over rows [M,F] ----
+// stats: fp64 sum / sum of squares per column in row chunks (fixed order) -> mean, biased var
+__global__ void __launch_bounds__(256)
+bn_partial_kernel(const float* __restrict__ X, const float* __restrict__ Y, int64_t M, int F, int64_t rows_per_chunk,
+                  const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ part) {
+    // mode A (Y == NULL): part0 = sum x, part1 = sum x^2.   mode B: part0 = sum dy, part1 = sum dy * xhat  (X = x, Y = dy)
+    __shared__ double red[2][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int f = blockIdx.x * 32 + tx;
+    const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+    double a0 = 0.0, a1 = 0.0;
+    if (f < F) {
+        const float mu = Y ? mean[f] : 0.0f, rs = Y ? rstd[f] : 0.0f;
+        for (int64_t r = r0 + ty; r < r1; r += 8) {
+            const float x = X[r * F + f];
+            if (Y) { const float d = Y[r * F + f]; a0 += d; a1 += static_cast<double>(d) * ((x - mu) * rs); }
+            else { a0 += x; a1 += static_cast<double>(x) * x; }
+        }
+    }
+    red[0][ty][tx] = a0;
+    red[1][ty][tx] = a1;
+    __syncthreads();
+    if (ty == 0 && f < F) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int q = 0; q < 8; ++q) { t0 += red[0][q][tx]; t1 += red[1][q][tx]; }
+        part[(static_cast<size_t>(blockIdx.y) * 2 + 0) * F + f] = t0;
+        part[(static_cast<size_t>(blockIdx.y) * 2 + 1) * F + f] = t1;
+    }
+}
+__global__ void bn_stats_finish_kernel(const double* __restrict__ part, int chunks, int F, int64_t M, float eps, float momentum,
+                                       float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ running_mean,
+                                       float* __restrict__ running_var) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    double s = 0.0, q = 0.0;
+    for (int c = 0; c < chunks; ++c) { s += part[(static_cast<size_t>(c) * 2) * F + f]; q += part[(static_cast<size_t>(c) * 2 + 1) * F + f]; }
+    const double mu = s / M;
+    double var = q / M - mu * mu;
+    if (var < 0.0) var = 0.0;
+    mean[f] = static_cast<float>(mu);
+    rstd[f] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    if (running_mean) {
+        const float unbiased = static_cast<float>(var * (static_cast<double>(M) / static_cast<double>(M > 1 ? M - 1 : 1)));
+        running_mean[f] = (1.0f - momentum) * running_mean[f] + momentum * static_cast<float>(mu);
+        running_var[f] = (1.0f - momentum) * running_var[f] + momentum * unbiased;
+    }
+}
+__global__ void bn_bwd_finish_kernel(const double* __restrict__ part, int chunks, int F, float* __restrict__ dbeta,
+                                     float* __restrict__ dgamma, int accumulate) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    double s = 0.0, q = 0.0;
+    for (int c = 0; c < chunks; ++c) { s += part[(static_cast<size_t>(c) * 2) * F + f]; q += part[(static_cast<size_t>(c) * 2 + 1) * F + f]; }
+    dbeta[f] = (accumulate ? dbeta[f] : 0.0f) + static_cast<float>(s);
+    dgamma[f] = (accumulate ? dgamma[f] : 0.0f) + static_cast<float>(q);
+}
+// y = act((x - mean) * rstd * gamma + beta)   (act: 0 none, 1 relu)
+__global__ void bn_apply_kernel(const float* __restrict__ x, int64_t M, int F, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                int act, float* __restrict__ y) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= M * F) return;
+    const int f = static_cast<int>(i % F);
+    float v = (x[i] - mean[f]) * rstd[f] * gamma[f] + beta[f];
+    if (act == 1) v = fmaxf(v, 0.0f);
+    y[i] = v;
+}
+// dx = gamma * rstd * (dy' - dbeta/M - xhat * dgamma/M), dy' = dy * [y > 0] for act == 1 (caller passes dy' already masked
+// in the reductions: the mask is applied here AND in bn_partial via the masked dy buffer the host builds with act_bwd).
+__global__ void bn_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t M, int F,
+                                 const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                 const float* __restrict__ dbeta, const float* __restrict__ dgamma, float* __restrict__ dx) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= M * F) return;
+    const int f = static_cast<int>(i % F);
+    const float xh = (x[i] - mean[f]) * rstd[f];
+    const float inv_m = 1.0f / static_cast<float>(M);
+    dx[i] = gamma[f] * rstd[f] * (dy[i] - dbeta[f] * inv_m - xh * dgamma[f] * inv_m);
+}
+
+// ---- flat Adam (torch.optim.Adam, amsgrad=False, weight_decay as L2):  one launch over the whole parameter buffer ----
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                            float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
+                            float grad_scale) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i] * grad_scale;
+    if (weight_decay != 0.0f) gi = fmaf(weight_decay, p[i], gi);
+    const float mi = m[i] + (1.0f - beta1) * (gi - m[i]);        // torch: exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - (lr / bc1) * (mi / denom);
+}
+
+}  // namespace molsde
+
+using namespace molsde;
+
+static inline unsigned blocks_for(int64_t n, int t = 256) { return static_cast<unsigned>((n + t - 1) / t); }
+
+static int gemm_splits(int64_t M, int64_t N, int64_t K) {
+    const int64_t tiles = ((M + GM - 1) / GM) * ((N + GN - 1) / GN);
+    int64_t s = (2 * kNumSMs + tiles - 1) / tiles;
+    const int64_t maxs = (K + 255) / 256;
+    if (s > maxs) s = maxs;
+    if (s > 64) s = 64;
+    return s < 1 ? 1 : static_cast<int>(s);
+}
+
+extern "C" {
+
+int64_t molsde_gemm_ws_floats(int64_t M, int64_t N, int64_t K) {
+    const int s = gemm_splits(M, N, K);
+    return s > 1 ? s * M * N : 0;
+}
+
+int molsde_gemm(int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                int64_t ldb, float* C, int64_t ldc, int32_t accumulate, float* ws, int64_t ws_floats, void* stream) {
+    if (!A || !B || !C || M < 0 || N < 0 || K < 0) return MOLSDE_ERR_INVALID;
+    if (M == 0 || N == 0) return MOLSDE_OK;
+    int splits = gemm_splits(M, N, K);
+    if (splits > 1 && (!ws || ws_floats < static_cast<int64_t>(splits) * M * N)) splits = 1;
+    int64_t kps = (K + splits - 1) / splits;
+    kps = (kps + GK - 1) / GK * GK;
+    if (kps < GK) kps = GK;
+    dim3 grid(static_cast<unsigned>((N + GN - 1) / GN), static_cast<unsigned>((M + GM - 1) / GM), splits);
+    float* w = splits > 1 ? ws : nullptr;
+    cudaStream_t s = as_stream(stream);
+    if (transA && transB) gemm_kernel<1, 1><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate, kps, w);
+    else if (transA) gemm_kernel<1, 0><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate, kps, w);
+    else if (transB) gemm_kernel<0, 1><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate, kps, w);
+    else gemm_kernel<0, 0><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate, kps, w);
+    int st = check_launch("gemm");
+    if (st != MOLSDE_OK || splits == 1) return st;
+    splitk_reduce_kernel<<<blocks_for(M * N), 256, 0, s>>>(ws, splits, M, N, C, ldc, accumulate);
+    return check_launch("gemm.splitk_reduce");
+}
+
+int64_t molsde_colsum_ws_floats(int64_t M, int32_t N) {
+    int64_t chunks = (M + 511) / 512;
+    if (chunks > 128) chunks = 128;
+    if (chunks < 1) chunks = 1;
+    return chunks * N;
+}
+
+int molsde_colsum(const float* X, int64_t M, int32_t N, int64_t ldx, float* out, int32_t accumulate, float* ws, int64_t ws_floats,
+                  void* stream) {
+    if (!X || !out || !ws || M < 0 || N <= 0) return MOLSDE_ERR_INVALID;
+    int64_t chunks = (M + 511) / 512;
+    if (chunks > 128) chunks = 128;
+    if (chunks < 1) chunks = 1;
+    if (ws_floats < chunks * N) return MOLSDE_ERR_INVALID;
+    const int64_t rpc = (M + chunks - 1) / chunks;
+    dim3 grid((N + 31) / 32, static_cast<unsigned>(chunks));
+    colsum_partial_kernel<<<grid, 256, 0, as_stream(stream)>>>(X, M, N, ldx, rpc > 0 ? rpc : 1, ws);
+    int st = check_launch("colsum");
+    if (st != MOLSDE_OK) return st;
+    colsum_finish_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(ws, static_cast<int>(chunks), N, out, accumulate);
+    return check_launch("colsum.finish");
+}
+
+int molsde_act_fwd(const float* x, int64_t n, int32_t act, float* y, void* stream) {
+    if (!x || !y || n < 0) return MOLSDE_ERR_INVALID;
+    if (n == 0) return MOLSDE_OK;
+    act_fwd_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(x, n, act, y);
+    return check_launch("act_fwd");
+}
+int molsde_act_bwd(const float* x, const float* dy, int64_t n, int32_t act, float* dx, void* stream) {
+    if (!x || !dy || !dx || n < 0) return MOLSDE_ERR_INVALID;
+    if (n == 0) return MOLSDE_OK;
+    act_bwd_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(x, dy, n, act, dx);
+    return check_launch("act_bwd");
+}
+int molsde_ew(int32_t op, const float* a, const float* b, const float* c, float alpha, int64_t n, int64_t cols, float* out,
+              void* stream) {
+    if (!a || !out || n < 0 || op < 0 || op > 3 || (op >= 1 && !b) || (op >= 2 && cols <= 0)) return MOLSDE_ERR_INVALID;
+    if (n == 0) return MOLSDE_OK;
+    ew_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(op, a, b, c, alpha, n, cols, out);
+    return check_launch("ew");
+}
+int molsde_gather_pair(const float* A, const int32_t* ia, const float* B, const int32_t* ib, int64_t rows, int32_t cols, float* out,
+                       void* stream) {
+    if (!A || !out || rows < 0 || cols <= 0) return MOLSDE_ERR_INVALID;
+    if (rows == 0) return MOLSDE_OK;
+    gather_pair_kernel<<<blocks_for(rows * cols), 256, 0, as_stream(stream)>>>(A, ia, B, ib, rows, cols, out);
+    return check_launch("gather_pair");
+}
+int molsde_seg_gather_sum(const float* X, const int32_t* ptr, const int32_t* perm, int64_t segments, int32_t cols, const float* scale,
+                          int32_t accumulate, float* out, void* stream) {
+    if (!X || !ptr || !out || segments < 0 || cols <= 0) return MOLSDE_ERR_INVALID;
+    if (segments == 0) return MOLSDE_OK;
+    seg_gather_sum_kernel<<<blocks_for(segments * cols), 256, 0, as_stream(stream)>>>(X, ptr, perm, segments, cols, scale, accumulate, out);
+    return check_launch("seg_gather_sum");
+}
+int molsde_bucket_count(const int64_t* keys, int64_t n, int32_t buckets, int32_t* count, void* stream) {
+    if (!keys || !count || n < 0 || buckets <= 0) return MOLSDE_ERR_INVALID;
+    bucket_count_kernel<<<buckets, 256, 0, as_stream(stream)>>>(keys, n, count);
+    return check_launch("bucket_count");
+}
+int molsde_bucket_fill(const int64_t* keys, int64_t n, int32_t buckets, const int32_t* rowptr, int32_t* perm, void* stream) {
+    if (!keys || !rowptr || !perm || n < 0 || buckets <= 0) return MOLSDE_ERR_INVALID;
+    if (n == 0) return MOLSDE_OK;
+    bucket_fill_kernel<<<buckets, 32, 0, as_stream(stream)>>>(keys, n, rowptr, perm);
+    return check_launch("bucket_fill");
+}
+int molsde_layernorm_fwd(const float* x, int64_t M, int32_t D, const float* g, const float* b, float eps, float* y, float* mean,
+                         float* rstd, void* stream) {
+    if (!x || !g || !b || !y || !mean || !rstd || M < 0 || D <= 0) return MOLSDE_ERR_INVALID;
+    if (M == 0) return MOLSDE_OK;
+    layernorm_fwd_kernel<<<blocks_for(M, 8), 256, 0, as_stream(stream)>>>(x, M, D, g, b, eps, y, mean, rstd);
+    return check_launch("layernorm_fwd");
+}
+int molsde_layernorm_bwd(const float* x, const float* dy, int64_t M, int32_t D, const float* g, const float* mean, const float* rstd,
+                         float* dx, float* dyx, void* stream) {
+    if (!x || !dy || !g || !mean || !rstd || !dx || !dyx || M < 0 || D <= 0) return MOLSDE_ERR_INVALID;
+    if (M == 0) return MOLSDE_OK;
+    layernorm_bwd_kernel<<<blocks_for(M, 8), 256, 0, as_stream(stream)>>>(x, dy, M, D, g, mean, rstd, dx, dyx);
+    return check_launch("layernorm_bwd");
+}
+
+static int bn_chunks(int64_t M) {
+    int64_t c = (M + 255) / 256;
+    if (c > 64) c = 64;
+    return c < 1 ? 1 : static_cast<int>(c);
+}
+int64_t molsde_bn_ws_doubles(int64_t M, int32_t F) { return static_cast<int64_t>(bn_chunks(M)) * 2 * F; }
+
+int molsde_bn_train_fwd(const float* x, int64_t M, int32_t F, const float* gamma, const float* beta, float eps, float momentum,
+                        float* running_mean, float* running_var, int32_t act, float* y, float* mean, float* rstd, double* ws,
+                        void* stream) {
+    if (!x || !gamma || !beta || !y || !mean || !rstd || !ws || M <= 0 || F <= 0) return MOLSDE_ERR_INVALID;
+    const int chunks = bn_chunks(M);
+    const int64_t rpc = (M + chunks - 1) / chunks;
+    dim3 grid((F + 31) / 32, chunks);
+    bn_partial_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, nullptr, M, F, rpc, nullptr, nullptr, ws);
+    int st = check_launch("bn_partial");
+    if (st != MOLSDE_OK) return st;
+    bn_stats_finish_kernel<<<(F + 127) / 128, 128, 0, as_stream(stream)>>>(ws, chunks, F, M, eps, momentum, mean, rstd, running_mean,
+                                                                         running_var);
+    st = check_launch("bn_stats_finish");
+    if (st != MOLSDE_OK) return st;
+    bn_apply_kernel<<<blocks_for(M * F), 256, 0, as_stream(stream)>>>(x, M, F, mean, rstd, gamma, beta, act, y);
+    return check_launch("bn_apply");
+}
+/* dy must already carry the activation mask (relu'); dgamma / dbeta are fresh outputs */
+int molsde_bn_train_bwd(const float* x, const float* dy, int64_t M, int32_t F, const float* gamma, const float* mean,
+                        const float* rstd, float* dx, float* dgamma, float* dbeta, double* ws, void* stream) {
+    if (!x || !dy || !gamma || !mean || !rstd || !dx || !dgamma || !dbeta || !ws || M <= 0 || F <= 0) return MOLSDE_ERR_INVALID;
+    const int chunks = bn_chunks(M);
+    const int64_t rpc = (M + chunks - 1) / chunks;
+    dim3 grid((F + 31) / 32, chunks);
+    bn_partial_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, dy, M, F, rpc, mean, rstd, ws);
+    int st = check_launch("bn_bwd_partial");
+    if (st != MOLSDE_OK) return st;
+    bn_bwd_finish_kernel<<<(F + 127) / 128, 128, 0, as_stream(stream)>>>(ws, chunks, F, dbeta, dgamma, 0);
+    st = check_launch("bn_bwd_finish");
+    if (st != MOLSDE_OK) return st;
+    bn_bwd_dx_kernel<<<blocks_for(M * F), 256, 0, as_stream(stream)>>>(x, dy, M, F, mean, rstd, gamma, dbeta, dgamma, dx);
+    return check_launch("bn_bwd_dx");
+}
+
+int molsde_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, int32_t step, float grad_scale, void* stream) {
+    if (!p || !g || !m || !v || n < 0 || step < 1) return MOLSDE_ERR_INVALID;
+    if (n == 0) return MOLSDE_OK;
+    const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, static_cast<float>(step)));
+    adam_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt,
+                                                            grad_scale);
+    return check_launch("adam_step");
+}
+
+}  // extern "C"

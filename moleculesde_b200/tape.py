@@ -1,0 +1,354 @@
+"""Reverse-mode tape over the C-ABI training kernels (`csrc/train*.cu`).
+
+The reference obtains gradients from torch.autograd over PyTorch/PyG ops (`pretrain_MoleculeSDE.py:150`).
+Here every forward op is one of our CUDA kernels and records a closure that launches the matching backward
+kernel(s); `Tape.backward` runs the closures in reverse.  torch only owns the memory (`torch.empty`) and the
+stream — no torch compute op, no torch.autograd.  Gradient accumulation is `molsde_ew` (a += b), parameter
+gradients land in views of one flat buffer (the unit of the NCCL all-reduce and of the flat Adam step).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import torch
+
+from ._abi import check, lib, ptr, require_device, stream_ptr
+
+ACT = {"none": 0, "relu": 1, "silu": 2, "ssp": 3, "tanh": 4, "elu": 5}
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    """data pointer of a contiguous tensor or of a 2-D row-strided view (stride(1) == 1)."""
+    if t is None:
+        return None
+    if t.dim() == 2 and not t.is_contiguous():
+        assert t.stride(1) == 1, "only row-strided views cross the C ABI"
+        return t.data_ptr()
+    return ptr(t)
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.dim() == 2 else t.numel()
+
+
+class Var:
+    """A tensor on the tape: `data`, its gradient `grad` (allocated lazily) and whether anything upstream needs it."""
+    __slots__ = ("data", "grad", "needs")
+
+    def __init__(self, data: torch.Tensor, needs: bool = False, grad: Optional[torch.Tensor] = None):
+        self.data, self.needs, self.grad = data, needs, grad
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+
+class Index:
+    """An int32 row-index vector together with the CSR of its inverse (`ptr`, `perm`): the backward of a gather
+    `out[r] = x[idx[r]]` is the deterministic gather-reduce `dx[s] = sum_{p in ptr[s]..ptr[s+1]} dout[perm[p]]`.
+    `perm=None` means the index is already grouped (ascending), i.e. perm = identity."""
+
+    def __init__(self, idx: torch.Tensor, ptr_: torch.Tensor, perm: Optional[torch.Tensor], size: int):
+        self.idx, self.ptr, self.perm, self.size = idx, ptr_, perm, size
+
+
+def bucket_index(keys: torch.Tensor, size: int) -> Index:
+    """Index for arbitrary int64 keys in [0,size) via the stable counting sort kernels."""
+    require_device(keys)
+    L, s = lib(), stream_ptr(keys)
+    n = keys.numel()
+    count = torch.empty(size, dtype=torch.int32, device=keys.device)
+    check(L.molsde_bucket_count(ptr(keys), n, size, ptr(count), s), "bucket_count")
+    rowptr = torch.empty(size + 1, dtype=torch.int32, device=keys.device)
+    check(L.molsde_exclusive_scan_i32(ptr(count), size, ptr(rowptr), s), "scan")
+    perm = torch.empty(max(n, 1), dtype=torch.int32, device=keys.device)
+    check(L.molsde_bucket_fill(ptr(keys), n, size, ptr(rowptr), ptr(perm), s), "bucket_fill")
+    return Index(keys.to(torch.int32), rowptr, perm, size)
+
+
+class Tape:
+    def __init__(self, device: torch.device):
+        self.dev = device
+        self.ops: List[Callable[[], None]] = []
+        self.L = lib()
+        self.launches = 0
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def s(self) -> int:
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def empty(self, *shape, dtype=torch.float32) -> torch.Tensor:
+        return torch.empty(*shape, dtype=dtype, device=self.dev)
+
+    def var(self, data: torch.Tensor, needs: bool = False) -> Var:
+        return Var(data, needs)
+
+    def param(self, data: torch.Tensor, grad_view: torch.Tensor) -> Var:
+        return Var(data, True, grad_view)
+
+    def _call(self, fn, *args, what=""):
+        self.launches += 1
+        check(fn(*args), what or fn.__name__)
+
+    def ew(self, op, a, b, c, alpha, out, cols=1):
+        self._call(self.L.molsde_ew, op, _p(a), _p(b), _p(c), float(alpha), out.numel(), cols, _p(out), self.s, what="ew")
+
+    def accum(self, v: Var, g: torch.Tensor) -> None:
+        """v.grad += g (g is a fresh contiguous tensor this op owns)."""
+        if not v.needs:
+            return
+        if v.grad is None:
+            v.grad = g if g.is_contiguous() and g.shape == v.data.shape else None
+            if v.grad is None:
+                v.grad = self.empty(v.data.shape)
+                self.ew(0, g.contiguous(), None, None, 1.0, v.grad)
+        else:
+            assert v.grad.is_contiguous()
+            self.ew(0, v.grad, g, None, 1.0, v.grad)
+
+    def grad_of(self, v: Var) -> torch.Tensor:
+        if v.grad is None:  # nothing flowed into it
+            v.grad = torch.zeros(v.data.shape, dtype=torch.float32, device=self.dev)
+        return v.grad
+
+    def backward(self) -> None:
+        for fn in reversed(self.ops):
+            fn()
+        self.ops.clear()
+
+    # ------------------------------------------------------------------ dense ops
+    def gemm(self, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, accumulate=False):
+        n = self.L.molsde_gemm_ws_floats(M, N, K)
+        ws = self.empty(n) if n > 0 else None
+        self._call(self.L.molsde_gemm, ta, tb, M, N, K, _p(A), lda, _p(B), ldb, _p(C), ldc, int(accumulate), _p(ws), n, self.s,
+                   what="gemm")
+
+    def colsum(self, X, M, N, ldx, out, accumulate=False):
+        n = self.L.molsde_colsum_ws_floats(M, N)
+        ws = self.empty(n)
+        self._call(self.L.molsde_colsum, _p(X), M, N, ldx, _p(out), int(accumulate), _p(ws), n, self.s, what="colsum")
+
+    def linear(self, x: Var, W: Var, b: Optional[Var], act: str = "none", into: Optional[Var] = None, col0: int = 0,
+               rowscale: Optional[torch.Tensor] = None) -> Var:
+        """y = act(rowscale * (x W^T + b)); W [out,in] as nn.Linear.  `into`/`col0`: write y into columns
+        [col0, col0+out) of the wider buffer Var `into` (a concat without a copy); its gradient is read from there."""
+        M, K = x.data.shape
+        Nout = W.data.shape[0]
+        a = ACT[act]
+        if into is not None:
+            assert a == 0 and rowscale is None
+            y = into.data[:, col0:col0 + Nout]
+        else:
+            y = self.empty(M, Nout)
+        pre = y if a == 0 else self.empty(M, Nout)
+        if W.data.is_contiguous():
+            self._call(self.L.molsde_linear, _p(x.data), M, K, _ld(x.data), _p(W.data), _p(b.data) if b is not None else None, Nout,
+                       _p(pre), _ld(pre), 0, None, 0, _p(rowscale), self.s, what="linear")
+        else:  # W is a column slice of a wider weight (split concat input): plain GEMM + bias
+            assert rowscale is None and pre.is_contiguous()
+            self.gemm(0, 1, M, Nout, K, x.data, _ld(x.data), W.data, _ld(W.data), pre, Nout)
+            if b is not None:
+                self.ew(3, pre, b.data, None, 1.0, pre, cols=Nout)
+        if a:
+            self._call(self.L.molsde_act_fwd, _p(pre), pre.numel(), a, _p(y), self.s, what="act_fwd")
+        needs = x.needs or W.needs or (b is not None and b.needs)
+        out = into if into is not None else Var(y, needs)
+        if into is not None:
+            into.needs = into.needs or needs
+        if needs:
+            def bwd():
+                if into is not None:
+                    dy = self.grad_of(into)[:, col0:col0 + Nout]
+                else:
+                    if out.grad is None:
+                        return
+                    dy = out.grad
+                if a:
+                    dpre = self.empty(M, Nout)
+                    self._call(self.L.molsde_act_bwd, _p(pre), _p(dy), dpre.numel(), a, _p(dpre), self.s, what="act_bwd")
+                else:
+                    dpre = dy
+                if rowscale is not None:
+                    t = self.empty(M, Nout)
+                    self.ew(2, dpre, rowscale, None, 1.0, t, cols=Nout)
+                    dpre = t
+                if W.needs:
+                    self.gemm(1, 0, Nout, K, M, dpre, _ld(dpre), x.data, _ld(x.data), W.grad, _ld(W.grad), accumulate=True)
+                if b is not None and b.needs:
+                    self.colsum(dpre, M, Nout, _ld(dpre), b.grad, accumulate=True)
+                if x.needs:
+                    dx = self.empty(M, K)
+                    self.gemm(0, 0, M, K, Nout, dpre, _ld(dpre), W.data, _ld(W.data), dx, K)
+                    self.accum(x, dx)
+            self.ops.append(bwd)
+        return out
+
+    def act(self, x: Var, act: str) -> Var:
+        a = ACT[act]
+        y = self.empty(x.data.shape)
+        self._call(self.L.molsde_act_fwd, _p(x.data), y.numel(), a, _p(y), self.s, what="act_fwd")
+        out = Var(y, x.needs)
+        if x.needs:
+            def bwd():
+                if out.grad is None:
+                    return
+                dx = self.empty(x.data.shape)
+                self._call(self.L.molsde_act_bwd, _p(x.data), _p(out.grad), dx.numel(), a, _p(dx), self.s, what="act_bwd")
+                self.accum(x, dx)
+            self.ops.append(bwd)
+        return out
+
+    def add(self, a: Var, b: Var, alpha: float = 1.0) -> Var:
+        y = self.empty(a.data.shape)
+        self.ew(0, a.data, b.data, None, alpha, y)
+        out = Var(y, a.needs or b.needs)
+        if out.needs:
+            def bwd():
+                if out.grad is None:
+                    return
+                if a.needs:
+                    g = self.empty(y.shape)
+                    self.ew(0, out.grad, None, None, 1.0, g)
+                    self.accum(a, g)
+                if b.needs:
+                    g = self.empty(y.shape)
+                    self.ew(0, out.grad, None, None, alpha, g)
+                    self.accum(b, g)
+            self.ops.append(bwd)
+        return out
+
+    def mul(self, a: Var, b: Var, c: Optional[Var] = None) -> Var:
+        """a*b (+c)"""
+        y = self.empty(a.data.shape)
+        self.ew(1, a.data, b.data, c.data if c is not None else None, 1.0, y)
+        out = Var(y, a.needs or b.needs or (c is not None and c.needs))
+        if out.needs:
+            def bwd():
+                if out.grad is None:
+                    return
+                if a.needs:
+                    g = self.empty(y.shape)
+                    self.ew(1, out.grad, b.data, None, 1.0, g)
+                    self.accum(a, g)
+                if b.needs:
+                    g = self.empty(y.shape)
+                    self.ew(1, out.grad, a.data, None, 1.0, g)
+                    self.accum(b, g)
+                if c is not None and c.needs:
+                    g = self.empty(y.shape)
+                    self.ew(0, out.grad, None, None, 1.0, g)
+                    self.accum(c, g)
+            self.ops.append(bwd)
+        return out
+
+    def scale_mask(self, x: Var, mask: torch.Tensor, alpha: float) -> Var:
+        """x * mask * alpha (dropout with a given keep mask)."""
+        y = self.empty(x.data.shape)
+        self.ew(1, x.data, mask, None, 1.0, y)
+        self.ew(0, y, None, None, alpha, y)
+        out = Var(y, x.needs)
+        if x.needs:
+            def bwd():
+                if out.grad is None:
+                    return
+                g = self.empty(y.shape)
+                self.ew(1, out.grad, mask, None, 1.0, g)
+                self.ew(0, g, None, None, alpha, g)
+                self.accum(x, g)
+            self.ops.append(bwd)
+        return out
+
+    # ------------------------------------------------------------------ gather / scatter
+    def gather_pair(self, A: Var, ia: Optional[Index], B: Optional[Var] = None, ib: Optional[Index] = None,
+                    rows: Optional[int] = None) -> Var:
+        """out[r] = A[ia[r]] (+ B[ib[r]])"""
+        cols = A.data.shape[1]
+        rows = rows if rows is not None else (ia.idx.numel() if ia is not None else A.data.shape[0])
+        y = self.empty(rows, cols)
+        self._call(self.L.molsde_gather_pair, _p(A.data), _p(ia.idx) if ia else None, _p(B.data) if B is not None else None,
+                   _p(ib.idx) if ib else None, rows, cols, _p(y), self.s, what="gather_pair")
+        out = Var(y, A.needs or (B is not None and B.needs))
+        if out.needs:
+            def bwd():
+                if out.grad is None:
+                    return
+                for V, ix in ((A, ia), (B, ib)):
+                    if V is None or not V.needs:
+                        continue
+                    g = self.empty(V.data.shape)
+                    self.seg_sum(out.grad, ix, cols, g)
+                    self.accum(V, g)
+            self.ops.append(bwd)
+        return out
+
+    def seg_sum(self, X: torch.Tensor, ix: Index, cols: int, out: torch.Tensor, scale: Optional[torch.Tensor] = None,
+                accumulate: bool = False):
+        self._call(self.L.molsde_seg_gather_sum, _p(X), _p(ix.ptr), _p(ix.perm), ix.size, cols, _p(scale), int(accumulate),
+                   _p(out), self.s, what="seg_gather_sum")
+
+    def scatter_sum(self, X: Var, ix: Index) -> Var:
+        """out[s] = sum_{r: idx[r] == s} X[r]   (scatter-add as a gather-reduce); backward is a gather."""
+        cols = X.data.shape[1]
+        y = self.empty(ix.size, cols)
+        self.seg_sum(X.data, ix, cols, y)
+        out = Var(y, X.needs)
+        if X.needs:
+            def bwd():
+                if out.grad is None:
+                    return
+                g = self.empty(X.data.shape)
+                self._call(self.L.molsde_gather_pair, _p(out.grad), _p(ix.idx), None, None, g.shape[0], cols, _p(g), self.s,
+                           what="gather_pair")
+                self.accum(X, g)
+            self.ops.append(bwd)
+        return out
+
+    # ------------------------------------------------------------------ normalisation
+    def layernorm(self, x: Var, g: Var, b: Var, eps: float = 1e-5) -> Var:
+        M, D = x.data.shape
+        y, mean, rstd = self.empty(M, D), self.empty(M), self.empty(M)
+        self._call(self.L.molsde_layernorm_fwd, _p(x.data), M, D, _p(g.data), _p(b.data), eps, _p(y), _p(mean), _p(rstd), self.s,
+                   what="layernorm_fwd")
+        out = Var(y, True)
+
+        def bwd():
+            if out.grad is None:
+                return
+            dx, dyx = self.empty(M, D), self.empty(M, D)
+            self._call(self.L.molsde_layernorm_bwd, _p(x.data), _p(out.grad), M, D, _p(g.data), _p(mean), _p(rstd), _p(dx), _p(dyx),
+                       self.s, what="layernorm_bwd")
+            if g.needs:
+                self.colsum(dyx, M, D, D, g.grad, accumulate=True)
+            if b.needs:
+                self.colsum(out.grad, M, D, D, b.grad, accumulate=True)
+            self.accum(x, dx)
+        self.ops.append(bwd)
+        return out
+
+    def batchnorm(self, x: Var, g: Var, b: Var, running_mean: torch.Tensor, running_var: torch.Tensor, eps: float = 1e-5,
+                  momentum: float = 0.1, relu: bool = False) -> Var:
+        """nn.BatchNorm1d in train mode (+ fused ReLU)."""
+        M, F = x.data.shape
+        y, mean, rstd = self.empty(M, F), self.empty(F), self.empty(F)
+        ws = self.empty(self.L.molsde_bn_ws_doubles(M, F), dtype=torch.float64)
+        self._call(self.L.molsde_bn_train_fwd, _p(x.data), M, F, _p(g.data), _p(b.data), eps, momentum, _p(running_mean),
+                   _p(running_var), int(relu), _p(y), _p(mean), _p(rstd), _p(ws), self.s, what="bn_train_fwd")
+        out = Var(y, True)
+
+        def bwd():
+            if out.grad is None:
+                return
+            dy = out.grad
+            if relu:
+                dy = self.empty(M, F)
+                self._call(self.L.molsde_act_bwd, _p(y), _p(out.grad), dy.numel(), 1, _p(dy), self.s, what="act_bwd")  # y>0 <=> pre>0
+            dx, dg, db = self.empty(M, F), self.empty(F), self.empty(F)
+            ws2 = self.empty(self.L.molsde_bn_ws_doubles(M, F), dtype=torch.float64)
+            self._call(self.L.molsde_bn_train_bwd, _p(x.data), _p(dy), M, F, _p(g.data), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db),
+                       _p(ws2), self.s, what="bn_train_bwd")
+            self.accum(g, dg)
+            self.accum(b, db)
+            self.accum(x, dx)
+        self.ops.append(bwd)
+        return out
