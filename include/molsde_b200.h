@@ -285,7 +285,8 @@ int molsde_colsum(const float* X, int64_t M, int32_t N, int64_t ldx, float* out,
 /* y = act(x);  dx = dy * act'(x) with x the pre-activation (act codes of molsde_linear) */
 int molsde_act_fwd(const float* x, int64_t n, int32_t act, float* y, void* stream);
 int molsde_act_bwd(const float* x, const float* dy, int64_t n, int32_t act, float* dx, void* stream);
-/* op 0: out = a + alpha*b (b NULL: alpha*a);  op 1: out = a*b (+c);  op 2: out[r,:] = a[r,:] * alpha * b[r];  op 3: out[r,c] = a[r,c] + b[c]  (cols per row).
+/* op 0: out = a + alpha*b (b NULL: alpha*a);  op 1: out = a*b (+c);  op 2: out[r,:] = a[r,:] * alpha * b[r];  op 3: out[r,c] = a[r,c] + b[c]  (cols per row);
+ * op 4: out = a * (1 + b[0]) (+c).
  * out may alias a. */
 int molsde_ew(int32_t op, const float* a, const float* b, const float* c, float alpha, int64_t n, int64_t cols, float* out,
               void* stream);
@@ -295,7 +296,29 @@ int molsde_gather_pair(const float* A, const int32_t* ia, const float* B, const 
 /* out[s,:] (+)= scale[s] * sum_{p in [ptr[s],ptr[s+1])} X[perm ? perm[p] : p, :]  (scatter-add / backward of a gather,
  * as a deterministic gather-reduce over a CSR of the index) */
 int molsde_seg_gather_sum(const float* X, const int32_t* ptr, const int32_t* perm, int64_t segments, int32_t cols, const float* scale,
-                          int32_t accumulate, float* out, void* stream);
+                          int32_t accumulate, int32_t row_div, float* out, void* stream);  /* X row = perm[p] / row_div */
+/* out[r,:] = sum_f T[keys[r*F+f],:]  (AtomEncoder / BondEncoder / nn.Embedding; keys include the table offsets) */
+int molsde_embed_sum(const float* T, const int32_t* keys, int64_t rows, int32_t F, int32_t cols, float* out, void* stream);
+/* out[s,:] = sum_{p in ptr[s]..ptr[s+1]} A[ia[e],:] * W[e,:], e = perm ? perm[p] : p   (CFConv message+aggregate, and its dx) */
+int molsde_edge_mul_reduce(const float* A, const int32_t* ia, const float* W, const int32_t* ptr, const int32_t* perm, int64_t segments,
+                           int32_t cols, float* out, void* stream);
+/* out[e,:] = A[ia[e],:] * B[ib[e],:] */
+int molsde_edge_mul_gather(const float* A, const int32_t* ia, const float* B, const int32_t* ib, int64_t E, int32_t cols, float* out,
+                           void* stream);
+/* out[0] (+)= alpha <a,b> */
+int molsde_dot(const float* a, const float* b, int64_t n, float alpha, int32_t accumulate, float* out, void* stream);
+/* GINConv (molecule_gnn_model.py:13-32): pre = (1+eps) x + sum_{e->i} relu(x_src + BondEncoder(e)); dmsg = dpre[tgt] * relu' */
+int molsde_gin_aggregate_fwd(const float* x, const float* T, const int32_t* ekeys, int32_t F, const int32_t* rowptr, const int32_t* src,
+                             const float* eps, int64_t N, int32_t cols, float* pre, void* stream);
+int molsde_gin_message_bwd(const float* x, const float* T, const int32_t* ekeys, int32_t F, const int32_t* src, const int32_t* tgt,
+                           const float* dpre, int64_t E, int32_t cols, float* dmsg, void* stream);
+/* GaussianSmearing ea [E,ng] and cosine cutoff C [E] of the radius edges (schnet.py:93,186,205-207) */
+int molsde_schnet_edge_feat(const float* pos, const int32_t* src, const int32_t* tgt, int64_t E, const float* mu, int32_t ng,
+                            float coeff, float cutoff, float* ea, float* C, void* stream);
+/* backward of molsde_ebm_node_dot's loss_acc[0] scaled by coef; invperm = inverse permutation of perm */
+int molsde_ebm_node_dot_bwd(const float* X, const float* Y, const int64_t* perm, const int64_t* invperm, const float* pred_pos,
+                            const float* pred_neg, int64_t N, int32_t D, float T, float coef, int32_t accumulate, float* dX, float* dY,
+                            void* stream);
 /* stable counting sort of n int64 keys in [0,buckets): count[b]; then (after an exclusive scan -> rowptr) perm */
 int molsde_bucket_count(const int64_t* keys, int64_t n, int32_t buckets, int32_t* count, void* stream);
 int molsde_bucket_fill(const int64_t* keys, int64_t n, int32_t buckets, const int32_t* rowptr, int32_t* perm, void* stream);
@@ -310,6 +333,8 @@ int64_t molsde_bn_ws_doubles(int64_t M, int32_t F);
 int molsde_bn_train_fwd(const float* x, int64_t M, int32_t F, const float* gamma, const float* beta, float eps, float momentum,
                         float* running_mean, float* running_var, int32_t act, float* y, float* mean, float* rstd, double* ws,
                         void* stream);
+int molsde_bn_eval(const float* x, int64_t M, int32_t F, const float* gamma, const float* beta, const float* running_mean,
+                   const float* running_var, float eps, int32_t act, float* y, float* rstd_tmp, void* stream);
 int molsde_bn_train_bwd(const float* x, const float* dy, int64_t M, int32_t F, const float* gamma, const float* mean,
                         const float* rstd, float* dx, float* dgamma, float* dbeta, double* ws, void* stream);
 /* torch.optim.Adam step over one flat buffer (pretrain_MoleculeSDE.py:337); g is scaled by grad_scale first (1/world) */

@@ -138,7 +138,7 @@ __global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restr
     if (i < n) dx[i] = dy[i] * act_df(x[i], act);
 }
 
-// ---- elementwise: op 0: out = a + alpha*b (b NULL: alpha*a);  op 1: out = a*b (+ c);  op 2: out = a * alpha * b[row];  op 3: out = a + b[col] ----
+// ---- elementwise: op 0: out = a + alpha*b (b NULL: alpha*a);  op 1: out = a*b (+ c);  op 2: out = a * alpha * b[row];  op 3: out = a + b[col];  op 4: out = a*(1+b[0]) (+c) ----
 __global__ void ew_kernel(int op, const float* a, const float* b, const float* c, float alpha, int64_t n, int64_t cols, float* out) {
     // no __restrict__: `out` may alias an input (in-place accumulation)
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -147,7 +147,8 @@ __global__ void ew_kernel(int op, const float* a, const float* b, const float* c
     if (op == 0) v = b ? fmaf(alpha, b[i], a[i]) : alpha * a[i];
     else if (op == 1) v = c ? fmaf(a[i], b[i], c[i]) : a[i] * b[i];
     else if (op == 2) v = a[i] * alpha * b[i / cols];
-    else v = a[i] + b[i % cols];
+    else if (op == 3) v = a[i] + b[i % cols];
+    else v = c ? fmaf(a[i], 1.0f + b[0], c[i]) : a[i] * (1.0f + b[0]);
     out[i] = v;
 }
 
@@ -165,14 +166,14 @@ __global__ void gather_pair_kernel(const float* __restrict__ A, const int32_t* _
 
 // out[s,:] (+)= scale[s] * sum_{p in [ptr[s],ptr[s+1])} X[perm ? perm[p] : p, :]   in ascending p   (backward of a gather)
 __global__ void seg_gather_sum_kernel(const float* __restrict__ X, const int32_t* __restrict__ ptr, const int32_t* __restrict__ perm,
-                                      int64_t segments, int cols, const float* __restrict__ scale, int accumulate,
+                                      int64_t segments, int cols, const float* __restrict__ scale, int accumulate, int row_div,
                                       float* __restrict__ out) {
     const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (idx >= segments * cols) return;
     const int64_t s = idx / cols;
     const int c = static_cast<int>(idx % cols);
     float acc = 0.0f;
-    for (int p = ptr[s]; p < ptr[s + 1]; ++p) acc += X[static_cast<int64_t>(perm ? perm[p] : p) * cols + c];
+    for (int p = ptr[s]; p < ptr[s + 1]; ++p) acc += X[static_cast<int64_t>((perm ? perm[p] : p) / row_div) * cols + c];
     if (scale) acc *= scale[s];
     out[idx] = accumulate ? out[idx] + acc : acc;
 }
@@ -203,6 +204,126 @@ __global__ void bucket_fill_kernel(const int64_t* __restrict__ keys, int64_t n, 
         if (hit) perm[pos + __popc(m & ((1u << lane) - 1u))] = static_cast<int32_t>(i);
         pos += __popc(m);
     }
+}
+
+// out[r,:] = sum_f T[keys[r*F + f], :]     (AtomEncoder / BondEncoder / nn.Embedding: keys carry the per-feature table offset)
+__global__ void embed_sum_kernel(const float* __restrict__ T, const int32_t* __restrict__ keys, int64_t rows, int F, int cols,
+                                 float* __restrict__ out) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const int64_t r = idx / cols;
+    const int c = static_cast<int>(idx % cols);
+    float acc = 0.0f;
+    for (int f = 0; f < F; ++f) acc += T[static_cast<int64_t>(keys[r * F + f]) * cols + c];
+    out[idx] = acc;
+}
+
+// out[s,c] = sum_{p in [ptr[s],ptr[s+1])} A[ia[e],c] * W[e,c],  e = perm ? perm[p] : p
+//   CFConv message + aggregation (schnet.py:186-195): s = target, ia = source;   its dx: s = source (CSR by source), ia = target
+__global__ void edge_mul_reduce_kernel(const float* __restrict__ A, const int32_t* __restrict__ ia, const float* __restrict__ W,
+                                       const int32_t* __restrict__ ptr, const int32_t* __restrict__ perm, int64_t segments, int cols,
+                                       float* __restrict__ out) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= segments * cols) return;
+    const int64_t s = idx / cols;
+    const int c = static_cast<int>(idx % cols);
+    float acc = 0.0f;
+    for (int p = ptr[s]; p < ptr[s + 1]; ++p) {
+        const int64_t e = perm ? perm[p] : p;
+        acc = fmaf(A[static_cast<int64_t>(ia[e]) * cols + c], W[e * cols + c], acc);
+    }
+    out[idx] = acc;
+}
+// out[e,c] = A[ia[e],c] * B[ib[e],c]      (dW of the CFConv message)
+__global__ void edge_mul_gather_kernel(const float* __restrict__ A, const int32_t* __restrict__ ia, const float* __restrict__ B,
+                                       const int32_t* __restrict__ ib, int64_t E, int cols, float* __restrict__ out) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= E * cols) return;
+    const int64_t e = idx / cols;
+    const int c = static_cast<int>(idx % cols);
+    out[idx] = A[static_cast<int64_t>(ia[e]) * cols + c] * B[static_cast<int64_t>(ib[e]) * cols + c];
+}
+
+// out[0] (+)= alpha * <a, b>   (fixed-order, one CTA)
+__global__ void __launch_bounds__(1024) dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float alpha,
+                                                   int accumulate, float* __restrict__ out) {
+    __shared__ double red[1024];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) acc += static_cast<double>(a[i]) * b[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.0f) + alpha * static_cast<float>(red[0]);
+}
+
+// ---- GINConv (molecule_gnn_model.py:13-32):  pre[i] = (1+eps) x_i + sum_{e->i} relu(x_src + bond_emb_e),
+//      bond_emb_e = sum_f T[ekeys[e*F+f]] (BondEncoder fused; its table is a few rows) ----
+__global__ void gin_aggregate_fwd_kernel(const float* __restrict__ x, const float* __restrict__ T, const int32_t* __restrict__ ekeys, int F,
+                                         const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src, const float* __restrict__ eps,
+                                         int64_t N, int cols, float* __restrict__ pre) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= N * cols) return;
+    const int64_t i = idx / cols;
+    const int c = static_cast<int>(idx % cols);
+    float acc = 0.0f;
+    for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+        float em = 0.0f;
+        for (int f = 0; f < F; ++f) em += T[static_cast<int64_t>(ekeys[static_cast<int64_t>(e) * F + f]) * cols + c];
+        acc += fmaxf(x[static_cast<int64_t>(src[e]) * cols + c] + em, 0.0f);
+    }
+    pre[idx] = (1.0f + eps[0]) * x[idx] + acc;
+}
+// dmsg[e,c] = dpre[tgt_e,c] * [x_src + bond_emb_e > 0]
+__global__ void gin_message_bwd_kernel(const float* __restrict__ x, const float* __restrict__ T, const int32_t* __restrict__ ekeys, int F,
+                                       const int32_t* __restrict__ src, const int32_t* __restrict__ tgt, const float* __restrict__ dpre,
+                                       int64_t E, int cols, float* __restrict__ dmsg) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= E * cols) return;
+    const int64_t e = idx / cols;
+    const int c = static_cast<int>(idx % cols);
+    float em = 0.0f;
+    for (int f = 0; f < F; ++f) em += T[static_cast<int64_t>(ekeys[e * F + f]) * cols + c];
+    dmsg[idx] = (x[static_cast<int64_t>(src[e]) * cols + c] + em > 0.0f) ? dpre[static_cast<int64_t>(tgt[e]) * cols + c] : 0.0f;
+}
+
+// ---- SchNet edge features: GaussianSmearing (schnet.py:205-207) and the cosine cutoff (:186) ----
+__global__ void schnet_edge_feat_kernel(const float* __restrict__ pos, const int32_t* __restrict__ src, const int32_t* __restrict__ tgt,
+                                        int64_t E, const float* __restrict__ mu, int ng, float coeff, float cutoff,
+                                        float* __restrict__ ea, float* __restrict__ C) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= E * ng) return;
+    const int64_t e = idx / ng;
+    const int k = static_cast<int>(idx % ng);
+    const int r = src[e], c = tgt[e];
+    const float dx = __fsub_rn(pos[3 * r], pos[3 * c]), dy = __fsub_rn(pos[3 * r + 1], pos[3 * c + 1]),
+                dz = __fsub_rn(pos[3 * r + 2], pos[3 * c + 2]);
+    const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float t = d - mu[k];
+    ea[idx] = expf(coeff * (t * t));
+    if (k == 0) C[e] = 0.5f * (cosf(d * 3.14159274101257324f / cutoff) + 1.0f);
+}
+
+// ---- EBM_node_dot_prod backward (examples/util.py:52-68): loss = mean softplus(-pp) + mean softplus(pn) ----
+//   dX[r] (+)= coef/(N T) * (-sigmoid(-pp_r) Y[r] + sigmoid(pn_r) Y[perm[r]])
+//   dY[r] (+)= coef/(N T) * (-sigmoid(-pp_r) X[r] + sigmoid(pn_q) X[q]),  q = invperm[r]
+__global__ void ebm_node_dot_bwd_kernel(const float* __restrict__ X, const float* __restrict__ Y, const int64_t* __restrict__ perm,
+                                        const int64_t* __restrict__ invperm, const float* __restrict__ pp, const float* __restrict__ pn,
+                                        int64_t N, int D, float scale, int accumulate, float* __restrict__ dX, float* __restrict__ dY) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= N * D) return;
+    const int64_t r = idx / D;
+    const int c = static_cast<int>(idx % D);
+    const float gp = -1.0f / (1.0f + expf(pp[r]));  // -sigmoid(-pp)
+    const float gn = 1.0f / (1.0f + expf(-pn[r]));
+    const int64_t q = invperm[r];
+    const float gq = 1.0f / (1.0f + expf(-pn[q]));
+    const float dx = scale * (gp * Y[idx] + gn * Y[perm[r] * D + c]);
+    const float dy = scale * (gp * X[idx] + gq * X[q * D + c]);
+    dX[idx] = accumulate ? dX[idx] + dx : dx;
+    dY[idx] = accumulate ? dY[idx] + dy : dy;
 }
 
 // ---- LayerNorm over the last dim (D <= 1024), one warp per row ----
@@ -311,6 +432,10 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, int64_t M, int F, c
     float v = (x[i] - mean[f]) * rstd[f] * gamma[f] + beta[f];
     if (act == 1) v = fmaxf(v, 0.0f);
     y[i] = v;
+}
+__global__ void rsqrt_eps_kernel(const float* __restrict__ v, int n, float eps, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = 1.0f / sqrtf(v[i] + eps);
 }
 // dx = gamma * rstd * (dy' - dbeta/M - xhat * dgamma/M), dy' = dy * [y > 0] for act == 1 (caller passes dy' already masked
 // in the reductions: the mask is applied here AND in bn_partial via the masked dy buffer the host builds with act_bwd).
@@ -422,7 +547,7 @@ int molsde_act_bwd(const float* x, const float* dy, int64_t n, int32_t act, floa
 }
 int molsde_ew(int32_t op, const float* a, const float* b, const float* c, float alpha, int64_t n, int64_t cols, float* out,
               void* stream) {
-    if (!a || !out || n < 0 || op < 0 || op > 3 || (op >= 1 && !b) || (op >= 2 && cols <= 0)) return MOLSDE_ERR_INVALID;
+    if (!a || !out || n < 0 || op < 0 || op > 4 || (op >= 1 && !b) || ((op == 2 || op == 3) && cols <= 0)) return MOLSDE_ERR_INVALID;
     if (n == 0) return MOLSDE_OK;
     ew_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(op, a, b, c, alpha, n, cols, out);
     return check_launch("ew");
@@ -435,11 +560,66 @@ int molsde_gather_pair(const float* A, const int32_t* ia, const float* B, const 
     return check_launch("gather_pair");
 }
 int molsde_seg_gather_sum(const float* X, const int32_t* ptr, const int32_t* perm, int64_t segments, int32_t cols, const float* scale,
-                          int32_t accumulate, float* out, void* stream) {
-    if (!X || !ptr || !out || segments < 0 || cols <= 0) return MOLSDE_ERR_INVALID;
+                          int32_t accumulate, int32_t row_div, float* out, void* stream) {
+    if (!X || !ptr || !out || segments < 0 || cols <= 0 || row_div <= 0) return MOLSDE_ERR_INVALID;
     if (segments == 0) return MOLSDE_OK;
-    seg_gather_sum_kernel<<<blocks_for(segments * cols), 256, 0, as_stream(stream)>>>(X, ptr, perm, segments, cols, scale, accumulate, out);
+    seg_gather_sum_kernel<<<blocks_for(segments * cols), 256, 0, as_stream(stream)>>>(X, ptr, perm, segments, cols, scale, accumulate,
+                                                                                   row_div, out);
     return check_launch("seg_gather_sum");
+}
+int molsde_embed_sum(const float* T, const int32_t* keys, int64_t rows, int32_t F, int32_t cols, float* out, void* stream) {
+    if (!T || !keys || !out || rows < 0 || F <= 0 || cols <= 0) return MOLSDE_ERR_INVALID;
+    if (rows == 0) return MOLSDE_OK;
+    embed_sum_kernel<<<blocks_for(rows * cols), 256, 0, as_stream(stream)>>>(T, keys, rows, F, cols, out);
+    return check_launch("embed_sum");
+}
+int molsde_edge_mul_reduce(const float* A, const int32_t* ia, const float* W, const int32_t* ptr, const int32_t* perm, int64_t segments,
+                           int32_t cols, float* out, void* stream) {
+    if (!A || !ia || !W || !ptr || !out || segments < 0 || cols <= 0) return MOLSDE_ERR_INVALID;
+    if (segments == 0) return MOLSDE_OK;
+    edge_mul_reduce_kernel<<<blocks_for(segments * cols), 256, 0, as_stream(stream)>>>(A, ia, W, ptr, perm, segments, cols, out);
+    return check_launch("edge_mul_reduce");
+}
+int molsde_edge_mul_gather(const float* A, const int32_t* ia, const float* B, const int32_t* ib, int64_t E, int32_t cols, float* out,
+                           void* stream) {
+    if (!A || !ia || !B || !ib || !out || E < 0 || cols <= 0) return MOLSDE_ERR_INVALID;
+    if (E == 0) return MOLSDE_OK;
+    edge_mul_gather_kernel<<<blocks_for(E * cols), 256, 0, as_stream(stream)>>>(A, ia, B, ib, E, cols, out);
+    return check_launch("edge_mul_gather");
+}
+int molsde_dot(const float* a, const float* b, int64_t n, float alpha, int32_t accumulate, float* out, void* stream) {
+    if (!a || !b || !out || n < 0) return MOLSDE_ERR_INVALID;
+    dot_kernel<<<1, 1024, 0, as_stream(stream)>>>(a, b, n, alpha, accumulate, out);
+    return check_launch("dot");
+}
+int molsde_gin_aggregate_fwd(const float* x, const float* T, const int32_t* ekeys, int32_t F, const int32_t* rowptr, const int32_t* src,
+                             const float* eps, int64_t N, int32_t cols, float* pre, void* stream) {
+    if (!x || !T || !ekeys || !rowptr || !src || !eps || !pre || N < 0 || F <= 0 || cols <= 0) return MOLSDE_ERR_INVALID;
+    if (N == 0) return MOLSDE_OK;
+    gin_aggregate_fwd_kernel<<<blocks_for(N * cols), 256, 0, as_stream(stream)>>>(x, T, ekeys, F, rowptr, src, eps, N, cols, pre);
+    return check_launch("gin_aggregate_fwd");
+}
+int molsde_gin_message_bwd(const float* x, const float* T, const int32_t* ekeys, int32_t F, const int32_t* src, const int32_t* tgt,
+                           const float* dpre, int64_t E, int32_t cols, float* dmsg, void* stream) {
+    if (!x || !T || !ekeys || !src || !tgt || !dpre || !dmsg || E < 0 || F <= 0 || cols <= 0) return MOLSDE_ERR_INVALID;
+    if (E == 0) return MOLSDE_OK;
+    gin_message_bwd_kernel<<<blocks_for(E * cols), 256, 0, as_stream(stream)>>>(x, T, ekeys, F, src, tgt, dpre, E, cols, dmsg);
+    return check_launch("gin_message_bwd");
+}
+int molsde_schnet_edge_feat(const float* pos, const int32_t* src, const int32_t* tgt, int64_t E, const float* mu, int32_t ng,
+                            float coeff, float cutoff, float* ea, float* C, void* stream) {
+    if (!pos || !src || !tgt || !mu || !ea || !C || E < 0 || ng <= 0) return MOLSDE_ERR_INVALID;
+    if (E == 0) return MOLSDE_OK;
+    schnet_edge_feat_kernel<<<blocks_for(E * ng), 256, 0, as_stream(stream)>>>(pos, src, tgt, E, mu, ng, coeff, cutoff, ea, C);
+    return check_launch("schnet_edge_feat");
+}
+int molsde_ebm_node_dot_bwd(const float* X, const float* Y, const int64_t* perm, const int64_t* invperm, const float* pred_pos,
+                            const float* pred_neg, int64_t N, int32_t D, float T, float coef, int32_t accumulate, float* dX, float* dY,
+                            void* stream) {
+    if (!X || !Y || !perm || !invperm || !pred_pos || !pred_neg || !dX || !dY || N <= 0 || D <= 0) return MOLSDE_ERR_INVALID;
+    ebm_node_dot_bwd_kernel<<<blocks_for(N * D), 256, 0, as_stream(stream)>>>(X, Y, perm, invperm, pred_pos, pred_neg, N, D,
+                                                                           coef / (static_cast<float>(N) * T), accumulate, dX, dY);
+    return check_launch("ebm_node_dot_bwd");
 }
 int molsde_bucket_count(const int64_t* keys, int64_t n, int32_t buckets, int32_t* count, void* stream) {
     if (!keys || !count || n < 0 || buckets <= 0) return MOLSDE_ERR_INVALID;
@@ -490,6 +670,15 @@ int molsde_bn_train_fwd(const float* x, int64_t M, int32_t F, const float* gamma
     if (st != MOLSDE_OK) return st;
     bn_apply_kernel<<<blocks_for(M * F), 256, 0, as_stream(stream)>>>(x, M, F, mean, rstd, gamma, beta, act, y);
     return check_launch("bn_apply");
+}
+/* eval-mode BatchNorm1d (+ReLU): y = act((x - running_mean) / sqrt(running_var + eps) * gamma + beta) */
+int molsde_bn_eval(const float* x, int64_t M, int32_t F, const float* gamma, const float* beta, const float* running_mean,
+                   const float* running_var, float eps, int32_t act, float* y, float* rstd_tmp, void* stream) {
+    if (!x || !gamma || !beta || !running_mean || !running_var || !y || !rstd_tmp || M < 0 || F <= 0) return MOLSDE_ERR_INVALID;
+    if (M == 0) return MOLSDE_OK;
+    rsqrt_eps_kernel<<<blocks_for(F), 256, 0, as_stream(stream)>>>(running_var, F, eps, rstd_tmp);
+    bn_apply_kernel<<<blocks_for(M * F), 256, 0, as_stream(stream)>>>(x, M, F, running_mean, rstd_tmp, gamma, beta, act, y);
+    return check_launch("bn_eval");
 }
 /* dy must already carry the activation mask (relu'); dgamma / dbeta are fresh outputs */
 int molsde_bn_train_bwd(const float* x, const float* dy, int64_t M, int32_t F, const float* gamma, const float* mean,

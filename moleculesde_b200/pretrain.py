@@ -256,3 +256,158 @@ def _gat_layer(tp: Tape, P: Dict[str, Var], pf: str, x: Var, edge_attr: Var, es:
         h = tp.scale_mask(h, ffn_keep, 1.0 / (1.0 - p_drop))
     h2 = tp.linear(h, P[pf + "FFN.3.weight"], P[pf + "FFN.3.bias"])
     return tp.add(x1, tp.layernorm(h2, P[pf + "norm2.weight"], P[pf + "norm2.bias"]))
+
+
+# ======================================================================================================
+# GIN 2D encoder (Geom3D/models/molecule_gnn_model.py:132-197)
+# ======================================================================================================
+def _concat_tables(tp: Tape, P: Dict[str, Var], names) -> Var:
+    """The embedding tables of one encoder as ONE [rows, emb] table.  Inside a ParamStore they are adjacent in the flat
+    buffer (a zero-copy view, gradient included); otherwise (inference) they are concatenated once."""
+    vs = [P[n] for n in names]
+    cols = vs[0].data.shape[1]
+    adjacent = all(vs[i].data.data_ptr() + vs[i].data.numel() * 4 == vs[i + 1].data.data_ptr() for i in range(len(vs) - 1))
+    rows = sum(v.data.shape[0] for v in vs)
+    if adjacent and vs[0].grad is not None:
+        base = vs[0].data
+        data = torch.as_strided(base, (rows, cols), (cols, 1))
+        grad = torch.as_strided(vs[0].grad, (rows, cols), (cols, 1))
+        return Var(data, True, grad)
+    assert not any(v.needs for v in vs), "trainable embedding tables must live in a ParamStore"
+    return Var(torch.cat([v.data for v in vs], dim=0).contiguous(), False)
+
+
+def _keys(idx: torch.Tensor, dims) -> torch.Tensor:
+    """int64 [R,F] categorical features -> int32 keys into the concatenated table."""
+    off = torch.tensor([0] + list(torch.tensor(dims).cumsum(0)[:-1]), dtype=torch.int64, device=idx.device)
+    return (idx + off[None, :]).to(torch.int32).contiguous()
+
+
+def tape_gin(tp: Tape, model, P: Dict[str, Var], x: torch.Tensor, edge_index: torch.Tensor, edge_attr: torch.Tensor,
+             cache: Optional[dict], batch: Optional[torch.Tensor] = None, num_graphs: int = 1) -> Var:
+    """GNN.forward, GIN / JK=last / dropout 0.  `cache` (a dict living on the batch) keeps the index structures;
+    `batch` (node -> graph, ascending) only speeds up the CSR build."""
+    from .gnn import ATOM_FEATURE_DIMS, BOND_FEATURE_DIMS
+    from .tape import bucket_index
+    dev = x.device
+    require_device(x)
+    train = any(v.needs for v in P.values())
+    cache = cache if cache is not None else {}
+    if "gin" not in cache:
+        N = x.size(0)
+        if batch is None:
+            batch, num_graphs = torch.zeros(N, dtype=torch.long, device=dev), 1
+        csr = csr_by_target(edge_index, batch, num_graphs)
+        es = EdgeSet(csr.rowptr, csr.col, batch, num_graphs) if train else None
+        akeys = _keys(x, ATOM_FEATURE_DIMS)
+        ekeys = _keys(edge_attr[csr.perm.long()], BOND_FEATURE_DIMS)   # CSR edge order
+        aidx = bucket_index(akeys.reshape(-1).long(), sum(ATOM_FEATURE_DIMS)) if train else None
+        eidx = bucket_index(ekeys.reshape(-1).long(), sum(BOND_FEATURE_DIMS)) if train else None
+        cache["gin"] = (csr, es, akeys, ekeys, aidx, eidx)
+    csr, es, akeys, ekeys, aidx, eidx = cache["gin"]
+    src = es.src if es is not None else Index(csr.col, None, None, x.size(0))
+    tgt = es.tgt if es is not None else None
+    T_atom = _concat_tables(tp, P, [f"atom_encoder.atom_embedding_list.{i}.weight" for i in range(len(ATOM_FEATURE_DIMS))])
+    h = tp.embed_sum(T_atom, akeys, aidx)
+    for l in range(model.num_layer):
+        pf = f"gnns.{l}."
+        T_bond = _concat_tables(tp, P, [pf + f"bond_encoder.bond_embedding_list.{i}.weight" for i in range(len(BOND_FEATURE_DIMS))])
+        pre = tp.gin_aggregate(h, T_bond, ekeys, eidx, csr.rowptr, src, tgt, P[pf + "eps"])
+        bn1, bn2 = model.gnns[l].mlp[1], model.batch_norms[l]
+        z = tp.linear(pre, P[pf + "mlp.0.weight"], P[pf + "mlp.0.bias"])
+        last = l == model.num_layer - 1
+        if model.training:
+            z = tp.batchnorm(z, P[pf + "mlp.1.weight"], P[pf + "mlp.1.bias"], bn1.running_mean, bn1.running_var, bn1.eps,
+                             bn1.momentum, relu=True)
+            bn1.num_batches_tracked += 1
+        else:
+            z = tp.batchnorm_eval(z, P[pf + "mlp.1.weight"], P[pf + "mlp.1.bias"], bn1.running_mean, bn1.running_var, bn1.eps, relu=True)
+        z = tp.linear(z, P[pf + "mlp.3.weight"], P[pf + "mlp.3.bias"])
+        if model.training:
+            h = tp.batchnorm(z, P[f"batch_norms.{l}.weight"], P[f"batch_norms.{l}.bias"], bn2.running_mean, bn2.running_var,
+                             bn2.eps, bn2.momentum, relu=not last)
+            bn2.num_batches_tracked += 1
+        else:
+            h = tp.batchnorm_eval(z, P[f"batch_norms.{l}.weight"], P[f"batch_norms.{l}.bias"], bn2.running_mean, bn2.running_var,
+                                  bn2.eps, relu=not last)
+    return h
+
+
+# ======================================================================================================
+# SchNet (Geom3D/models/schnet.py:85-125), return_latent representation
+# ======================================================================================================
+def tape_schnet(tp: Tape, model, P: Dict[str, Var], z: torch.Tensor, pos: torch.Tensor, batch: torch.Tensor, num_graphs: int,
+                cache: Optional[dict]) -> Var:
+    """Node representation h [N, hidden] of SchNet.forward(return_latent=True) with every intermediate kept."""
+    from .graph import radius_graph
+    from .tape import bucket_index
+    L, dev = tp.L, pos.device
+    require_device(pos)
+    pos = pos.detach().float().contiguous()
+    cache = cache if cache is not None else {}
+    if "schnet" not in cache:  # positions are static during pretraining: the radius graph is built once per batch
+        csr = radius_graph(pos, model.cutoff, batch, num_graphs, want_edge_index=False)
+        es = EdgeSet(csr.rowptr, csr.col, batch, num_graphs)
+        zkeys = z.to(torch.int32).reshape(-1, 1).contiguous()
+        zidx = bucket_index(z, model.embedding.weight.shape[0])
+        E = es.E
+        ng = model.num_gaussians
+        ea, C = torch.empty(E, ng, dtype=torch.float32, device=dev), torch.empty(max(E, 1), dtype=torch.float32, device=dev)
+        check(L.molsde_schnet_edge_feat(ptr(pos), ptr(es.src.idx), ptr(es.tgt.idx), E, ptr(model.distance_expansion.offset), ng,
+                                        float(model.distance_expansion.coeff), float(model.cutoff), ptr(ea), ptr(C), tp.s),
+              "schnet_edge_feat")
+        cache["schnet"] = (es, zkeys, zidx, ea, C)
+    es, zkeys, zidx, ea, C = cache["schnet"]
+    h = tp.embed_sum(P["embedding.weight"], zkeys, zidx)
+    ea_v = Var(ea)
+    for i in range(model.num_interactions):
+        pf = f"interactions.{i}."
+        f1 = tp.linear(ea_v, P[pf + "mlp.0.weight"], P[pf + "mlp.0.bias"], act="ssp")
+        f2 = tp.linear(f1, P[pf + "mlp.2.weight"], P[pf + "mlp.2.bias"])
+        Wf = tp.rowscale(f2, C)
+        x = tp.linear(h, P[pf + "conv.lin1.weight"], None)
+        agg = tp.edge_mul_reduce(x, Wf, es.rowptr, es.src, es.tgt)
+        t = tp.linear(agg, P[pf + "conv.lin2.weight"], P[pf + "conv.lin2.bias"], act="ssp")
+        u = tp.linear(t, P[pf + "lin.weight"], P[pf + "lin.bias"])
+        h = tp.add(h, u)
+    h = tp.linear(h, P["lin1.weight"], P["lin1.bias"], act="ssp")
+    return tp.linear(h, P["lin2.weight"], P["lin2.bias"])
+
+
+# ======================================================================================================
+# dual_CL, EBM_node_dot_prod (examples/util.py:52-79)
+# ======================================================================================================
+def tape_dual_cl(tp: Tape, X: Var, Y: Var, T: float, neg_index_1: Optional[torch.Tensor] = None,
+                 neg_index_2: Optional[torch.Tensor] = None, coef: float = 1.0):
+    """(loss [1], loss_acc pairs) of dual_CL(X, Y); backward seeds coef * d loss."""
+    L, dev, s = tp.L, tp.dev, tp.s
+    N, D = X.data.shape
+    outs = []
+    dX, dY = tp.empty(N, D), tp.empty(N, D)
+    saved = []
+    for k, (A, Bv, neg) in enumerate(((X, Y, neg_index_1), (Y, X, neg_index_2))):
+        neg = torch.randperm(N) if neg is None else neg   # CPU generator in the reference (util.py:55)
+        perm = neg.to(dev).long().contiguous()
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(N, device=dev)
+        pp, pn, out = tp.empty(N), tp.empty(N), tp.empty(2)
+        ws = tp.empty(4 * 592)
+        tp._call(L.molsde_ebm_node_dot, ptr(A.data), ptr(Bv.data), ptr(perm), N, D, float(T), ptr(pp), ptr(pn), ptr(out), ptr(ws),
+                 ws.numel(), s, what="ebm_node_dot")
+        outs.append(out)
+        saved.append((A, Bv, perm, inv, pp, pn))
+    loss = tp.empty(1)
+    tp.ew(0, outs[0][:1], outs[1][:1], None, 1.0, loss)
+    tp.ew(0, loss, None, None, 0.5, loss)
+
+    def bwd():
+        (A, Bv, perm, inv, pp, pn) = saved[0]
+        tp._call(L.molsde_ebm_node_dot_bwd, ptr(A.data), ptr(Bv.data), ptr(perm), ptr(inv), ptr(pp), ptr(pn), N, D, float(T),
+                 0.5 * coef, 0, ptr(dX), ptr(dY), s, what="ebm_node_dot_bwd")
+        (A, Bv, perm, inv, pp, pn) = saved[1]   # roles swapped: A = Y, B = X
+        tp._call(L.molsde_ebm_node_dot_bwd, ptr(A.data), ptr(Bv.data), ptr(perm), ptr(inv), ptr(pp), ptr(pn), N, D, float(T),
+                 0.5 * coef, 1, ptr(dY), ptr(dX), s, what="ebm_node_dot_bwd")
+        tp.accum(X, dX)
+        tp.accum(Y, dY)
+    tp.ops.append(bwd)
+    return loss, outs

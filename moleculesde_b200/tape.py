@@ -283,9 +283,9 @@ class Tape:
         return out
 
     def seg_sum(self, X: torch.Tensor, ix: Index, cols: int, out: torch.Tensor, scale: Optional[torch.Tensor] = None,
-                accumulate: bool = False):
+                accumulate: bool = False, row_div: int = 1):
         self._call(self.L.molsde_seg_gather_sum, _p(X), _p(ix.ptr), _p(ix.perm), ix.size, cols, _p(scale), int(accumulate),
-                   _p(out), self.s, what="seg_gather_sum")
+                   row_div, _p(out), self.s, what="seg_gather_sum")
 
     def scatter_sum(self, X: Var, ix: Index) -> Var:
         """out[s] = sum_{r: idx[r] == s} X[r]   (scatter-add as a gather-reduce); backward is a gather."""
@@ -351,4 +351,100 @@ class Tape:
             self.accum(b, db)
             self.accum(x, dx)
         self.ops.append(bwd)
+        return out
+
+    def batchnorm_eval(self, x: Var, g: Var, b: Var, running_mean: torch.Tensor, running_var: torch.Tensor, eps: float = 1e-5,
+                       relu: bool = False) -> Var:
+        """nn.BatchNorm1d in eval mode (running statistics); forward only."""
+        assert not x.needs, "eval-mode BatchNorm is on the inference path only"
+        M, F = x.data.shape
+        y, tmp = self.empty(M, F), self.empty(F)
+        self._call(self.L.molsde_bn_eval, _p(x.data), M, F, _p(g.data), _p(b.data), _p(running_mean), _p(running_var), eps,
+                   int(relu), _p(y), _p(tmp), self.s, what="bn_eval")
+        return Var(y, False)
+
+    # ------------------------------------------------------------------ message passing pieces
+    def embed_sum(self, T: Var, keys: torch.Tensor, index: Optional[Index]) -> Var:
+        """out[r] = sum_f T[keys[r,f]] (AtomEncoder / BondEncoder / nn.Embedding over one concatenated table).
+        `index`: bucket Index of keys.reshape(-1) for the backward (None on the inference path)."""
+        rows, F = keys.shape
+        cols = T.data.shape[1]
+        y = self.empty(rows, cols)
+        self._call(self.L.molsde_embed_sum, _p(T.data), _p(keys), rows, F, cols, _p(y), self.s, what="embed_sum")
+        out = Var(y, T.needs and index is not None)
+        if out.needs:
+            def bwd():
+                if out.grad is None:
+                    return
+                self.seg_sum(out.grad, index, cols, T.grad, accumulate=True, row_div=F)
+            self.ops.append(bwd)
+        return out
+
+    def gin_aggregate(self, x: Var, T: Var, ekeys: torch.Tensor, ekey_index: Optional[Index], rowptr: torch.Tensor, src: Index,
+                      tgt: Index, eps: Var) -> Var:
+        """GINConv pre-MLP: (1+eps) x + sum_{e->i} relu(x_src + BondEncoder(e))  (molecule_gnn_model.py:23-31)."""
+        N, cols = x.data.shape
+        E, F = ekeys.shape
+        pre = self.empty(N, cols)
+        self._call(self.L.molsde_gin_aggregate_fwd, _p(x.data), _p(T.data), _p(ekeys), F, _p(rowptr), _p(src.idx), _p(eps.data), N, cols,
+                   _p(pre), self.s, what="gin_aggregate_fwd")
+        out = Var(pre, x.needs or T.needs or eps.needs)
+        if out.needs:
+            def bwd():
+                if out.grad is None:
+                    return
+                dmsg = self.empty(E, cols)
+                self._call(self.L.molsde_gin_message_bwd, _p(x.data), _p(T.data), _p(ekeys), F, _p(src.idx), _p(tgt.idx), _p(out.grad),
+                           E, cols, _p(dmsg), self.s, what="gin_message_bwd")
+                if T.needs:
+                    self.seg_sum(dmsg, ekey_index, cols, T.grad, accumulate=True, row_div=F)
+                if eps.needs:
+                    self._call(self.L.molsde_dot, _p(out.grad), _p(x.data), out.grad.numel(), 1.0, 1, _p(eps.grad), self.s, what="dot")
+                if x.needs:
+                    dx = self.empty(N, cols)
+                    self.seg_sum(dmsg, src, cols, dx)
+                    self.ew(4, out.grad, eps.data, dx, 1.0, dx)
+                    self.accum(x, dx)
+            self.ops.append(bwd)
+        return out
+
+    def edge_mul_reduce(self, x: Var, W: Var, rowptr: torch.Tensor, src: Index, tgt: Index) -> Var:
+        """CFConv message + aggregation: out[i] = sum_{e->i} x[src_e] * W[e]  (schnet.py:186-195)."""
+        N, cols = x.data.shape
+        E = W.data.shape[0]
+        y = self.empty(N, cols)
+        self._call(self.L.molsde_edge_mul_reduce, _p(x.data), _p(src.idx), _p(W.data), _p(rowptr), None, N, cols, _p(y), self.s,
+                   what="edge_mul_reduce")
+        out = Var(y, x.needs or W.needs)
+        if out.needs:
+            def bwd():
+                if out.grad is None:
+                    return
+                if W.needs:
+                    dW = self.empty(E, cols)
+                    self._call(self.L.molsde_edge_mul_gather, _p(out.grad), _p(tgt.idx), _p(x.data), _p(src.idx), E, cols, _p(dW),
+                               self.s, what="edge_mul_gather")
+                    self.accum(W, dW)
+                if x.needs:
+                    dx = self.empty(N, cols)
+                    self._call(self.L.molsde_edge_mul_reduce, _p(out.grad), _p(tgt.idx), _p(W.data), _p(src.ptr), _p(src.perm), N, cols,
+                               _p(dx), self.s, what="edge_mul_reduce")
+                    self.accum(x, dx)
+            self.ops.append(bwd)
+        return out
+
+    def rowscale(self, x: Var, r: torch.Tensor) -> Var:
+        """y[row,:] = x[row,:] * r[row]"""
+        cols = x.data.shape[1]
+        y = self.empty(x.data.shape)
+        self.ew(2, x.data, r, None, 1.0, y, cols=cols)
+        out = Var(y, x.needs)
+        if x.needs:
+            def bwd():
+                if out.grad is None:
+                    return
+                g = self.empty(y.shape)
+                self.ew(2, out.grad, r, None, 1.0, g, cols=cols)
+                self.accum(x, g)
+            self.ops.append(bwd)
         return out

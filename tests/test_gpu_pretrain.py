@@ -89,3 +89,98 @@ def test_2d3d_loss_and_grads(kind, gg, golden, golden_batch):
     for n, want in sec["buffers"]["sde2d3d"].items():
         got = dict(model.named_buffers())[n]
         check_grad_summary(got, want, n)
+
+
+def _check_module_grads(store, mname, sec, skip_zero=()):
+    bad = []
+    gmax = max(float(w["norm"]) for w in sec["grads"][mname].values() if w is not None)
+    for name, want in sec["grads"][mname].items():
+        if want is None:
+            continue
+        got = store.grad_view(mname, name)
+        if any(name.endswith(z) or name == z for z in skip_zero):
+            assert float(want["norm"]) <= 1e-5 * gmax and float(got.norm()) <= 1e-5 * gmax, name
+            continue
+        try:
+            check_grad_summary(got, want, f"{mname}.{name}")
+        except AssertionError as e:
+            bad.append(str(e))
+    assert not bad, "\n".join(bad)
+
+
+def _encoders(golden, dev):
+    from moleculesde_b200.gnn import GNN
+    from moleculesde_b200.schnet import SchNet
+    gnn = GNN(5, 300, JK="last", drop_ratio=0.0, gnn_type="GIN")
+    gnn.load_state_dict(sd_from_manifest(golden["manifest"]["gnn"], golden["meta"]["weight_seed"]))
+    sch = SchNet(hidden_channels=300, num_filters=128, num_interactions=6, num_gaussians=51, cutoff=10, readout="mean",
+                 node_class=119)
+    sch.load_state_dict(sd_from_manifest(golden["manifest"]["schnet"], golden["meta"]["weight_seed"]))
+    return gnn.train(), sch.train()
+
+
+def test_gin_eval_forward(golden, golden_batch):
+    """GNN.forward in eval mode (the representation the samplers consume) vs the reference output."""
+    from test_gpu_sde2d3d import assert_parity
+    dev = _dev()
+    _, batch = golden_batch
+    gnn, _ = _encoders(golden, dev)
+    gnn = gnn.to(dev).eval()
+    b = batch.to(dev)
+    h = gnn(b.x, b.edge_index, b.edge_attr)
+    assert_parity(h, golden["gnn"]["h_eval"], "GIN eval forward (x, edge_index, edge_attr)")
+    assert torch.equal(h, gnn(b))
+
+
+def test_encoders_forward_and_grads(gg, golden, golden_batch):
+    """GIN and SchNet in train mode: representations vs the reference, then backward from the reference's total
+    d loss / d representation -> every encoder parameter gradient."""
+    from moleculesde_b200.pretrain import ParamStore, tape_gin, tape_schnet
+    from moleculesde_b200.tape import Tape
+    from test_gpu_sde2d3d import assert_parity
+    dev = _dev()
+    sec = gg["pretrain_VE"]
+    _, batch = golden_batch
+    gnn, sch = _encoders(golden, dev)
+    store = ParamStore({"gnn": gnn, "schnet": sch}, dev)
+    b = batch.to(dev)
+    tp = Tape(dev)
+    cache = {}
+    h2d = tape_gin(tp, gnn, store.vars("gnn"), b.x, b.edge_index, b.edge_attr, cache, b.batch, b.num_graphs)
+    h3d = tape_schnet(tp, sch, store.vars("schnet"), b.x[:, 0].contiguous(), b.positions, b.batch, b.num_graphs, cache)
+    assert_parity(h2d.data, sec["h2d"], "GIN train-mode representation")
+    assert_parity(h3d.data, sec["h3d"], "SchNet representation")
+    h2d.grad = sec["d_h2d"].to(dev).contiguous()
+    h3d.grad = sec["d_h3d"].to(dev).contiguous()
+    tp.backward()
+    torch.cuda.synchronize()
+    # biases in front of a BatchNorm have analytically zero gradients
+    _check_module_grads(store, "gnn", sec, skip_zero=("mlp.0.bias", "mlp.3.bias"))
+    _check_module_grads(store, "schnet", sec)
+    bufs = dict(gnn.named_buffers())
+    for n, want in sec["buffers"]["gnn"].items():
+        check_grad_summary(bufs[n], want, "gnn." + n)
+
+
+def test_dual_cl_loss_and_backward(gg, golden):
+    """dual_CL (EBM_node_dot_prod): loss vs the reference, gradients vs autograd over the oracle restatement."""
+    from moleculesde_b200.pretrain import tape_dual_cl
+    from moleculesde_b200.tape import Tape, Var
+    from oracle import model as O
+    from test_gpu_sde2d3d import assert_parity
+    dev = _dev()
+    sec = gg["pretrain_VE"]
+    n1, n2 = sec["draws"][0][1], sec["draws"][1][1]
+    X, Y = sec["h2d"], sec["h3d"]
+    tp = Tape(dev)
+    Xv, Yv = Var(X.to(dev).contiguous(), True), Var(Y.to(dev).contiguous(), True)
+    loss, _ = tape_dual_cl(tp, Xv, Yv, 0.1, n1, n2, coef=1.0)
+    ref = float(sec["cl_loss"])
+    assert abs(float(loss) - ref) <= REL_TOL * abs(ref), (float(loss), ref)
+    tp.backward()
+    Xc, Yc = X.clone().requires_grad_(True), Y.clone().requires_grad_(True)
+    l1, _ = O.do_cl_ebm_node_dot_prod(Xc, Yc, 0.1, n1)
+    l2, _ = O.do_cl_ebm_node_dot_prod(Yc, Xc, 0.1, n2)
+    ((l1 + l2) / 2).backward()
+    assert_parity(Xv.grad, Xc.grad, "d CL / d X")
+    assert_parity(Yv.grad, Yc.grad, "d CL / d Y")
