@@ -362,6 +362,30 @@ int molsde_equi_bwd(const float* dgrad, const float* basis, const int32_t* rowpt
 int molsde_dsm_pos_loss_bwd(const float* score, const float* noise, const float* w, const int32_t* node_ptr, const int32_t* node2graph,
                             int64_t N, int32_t B, float upstream, float* dscore, void* stream);
 
+/* Backward kernels of the dense 3D->2D score networks (forward: molsde_dense_*):
+ *  dense_gcn_bwd: dpre [B*Nm, C*Fo] = dout * act'(out) (its column sum = dbias), dxw [B*Nm, lddx], and (dadj != NULL) the
+ *                 gradient w.r.t. the off-diagonal adjacency entries [B,C,Nm,Nm] (Fo <= 16; act none or tanh);
+ *  dense_attn_bwd: dQ/dK in the qk layout of the forward, dadjc = pass-through part of dpair (may be NULL);
+ *  dense_pair_post_bwd: dm [B*Nm*Nm, Co] from dadjc_next (NULL for the last layer) + the layer's slice of dallc;
+ *  dense_edge_final_bwd, graph_mse_bwd (mode-1 molsde_graph_reduce followed by the mean over graphs, times coef),
+ *  from_dense_batch (backward of molsde_to_dense_batch). */
+int molsde_dense_gcn_bwd(const float* adjc, int64_t adj_stride_b, int64_t adj_stride_c, int32_t B, int32_t C, int32_t Nm,
+                         const float* xw, int64_t ldxw, int32_t Fo, const float* out, const float* dout, int64_t ldo, int32_t out_off,
+                         int32_t act, float* dpre, float* dxw, int64_t lddx, float* dadj, int64_t dadj_stride_b, int32_t dadj_accumulate,
+                         void* stream);
+int molsde_dense_attn_bwd(const float* Q, const float* K, int64_t ldq, int32_t W, int32_t ds, int32_t B, int32_t C, int32_t Nm,
+                          const float* dpair, float* dQ, float* dK, float* dadjc, void* stream);
+int molsde_dense_pair_post_bwd(const float* dadjc_next, const float* dallc, int32_t ld_all, int32_t all_off, const float* flags,
+                               int32_t B, int32_t Nm, int32_t Co, float* dm, void* stream);
+int molsde_dense_edge_final_bwd(const float* dout, const float* flags, const float* scale, int32_t B, int32_t Nm, float* draw,
+                                void* stream);
+int molsde_graph_mse_bwd(const float* a, const float* b, const float* w, int32_t B, int64_t M, float coef, float* da, void* stream);
+/* dst[r,0:cols] (+)= src[r,0:cols] with independent row strides;  out[0] = mean(v[0:n]) */
+int molsde_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int32_t cols, int32_t accumulate, void* stream);
+int molsde_mean(const float* v, int64_t n, float* out, void* stream);
+int molsde_from_dense_batch(const float* dense, int64_t ldd, const int32_t* node_ptr, const int32_t* node2graph, int64_t N, int32_t Nm,
+                            int32_t F, float* x, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

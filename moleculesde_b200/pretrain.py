@@ -411,3 +411,214 @@ def tape_dual_cl(tp: Tape, X: Var, Y: Var, T: float, neg_index_1: Optional[torch
         tp.accum(Y, dY)
     tp.ops.append(bwd)
     return loss, outs
+
+
+# ======================================================================================================
+# SDEModel3Dto2D_node_adj_dense.forward (SDE_model_3D_to_2D_node_adj_dense.py:101-179), train=True, reduce_mean=True
+# ======================================================================================================
+def _dense_gcn(tp: Tape, adjc: Var, c: int, C: int, xw: Var, xw_col0: int, bias: Var, Fo: int, out: Var, out_off: int, act: str,
+               B: int, Nm: int) -> None:
+    """One channel of NodeNetwork_dense (dense GCN) writing act(Ahat . xw + bias) into out[:, out_off:out_off+Fo]."""
+    L, s = tp.L, tp.s
+    a = adjc.data
+    sb = a.stride(0)
+    a_ptr = a.data_ptr() + 4 * (c * Nm * Nm if a.dim() == 4 else 0)
+    code = {"none": 0, "tanh": 4}[act]
+    tp._call(L.molsde_dense_gcn, a_ptr, sb, 0, B, 1, Nm, xw.data.data_ptr() + 4 * xw_col0, xw.data.stride(0), ptr(bias.data), Fo,
+             out.data.data_ptr(), out.data.stride(0), out_off, code, s, what="dense_gcn")
+    out.needs = True
+
+    def bwd():
+        dout = tp.grad_of(out)
+        dpre = tp.empty(B * Nm, Fo)
+        dxw = tp.grad_of(xw)
+        want_dadj = adjc.needs
+        da_ptr = None
+        if want_dadj:
+            da = tp.grad_of(adjc)
+            da_ptr = da.data_ptr() + 4 * c * Nm * Nm
+        tp._call(L.molsde_dense_gcn_bwd, a_ptr, sb, 0, B, 1, Nm, xw.data.data_ptr() + 4 * xw_col0, xw.data.stride(0), Fo,
+                 out.data.data_ptr(), dout.data_ptr(), out.data.stride(0), out_off, code, ptr(dpre),
+                 dxw.data_ptr() + 4 * xw_col0, dxw.stride(0), da_ptr, C * Nm * Nm, 1, s, what="dense_gcn_bwd")
+        if bias.needs:
+            tp.colsum(dpre, B * Nm, Fo, Fo, bias.grad, accumulate=True)
+    tp.ops.append(bwd)
+
+
+def _mlp(tp: Tape, P: Dict[str, Var], prefix: str, x: Var, n_layers: int, act: str, last_rowscale=None, last_act: str = "none") -> Var:
+    for i in range(n_layers):
+        last = i == n_layers - 1
+        x = tp.linear(x, P[f"{prefix}.layers.{i}.weight"], P[f"{prefix}.layers.{i}.bias"], act=last_act if last else act,
+                      rowscale=last_rowscale if last else None)
+    return x
+
+
+def _edge_network(tp: Tape, P: Dict[str, Var], pf: str, lyr, x: Var, adjc: Var, flags: torch.Tensor, allc: Var, all_off: int,
+                  B: int, Nm: int, last: bool):
+    """EdgeNetwork_dense.forward (edge_network_dense.py:105-128) -> (x_out, adjc_next)."""
+    L, s = tp.L, tp.s
+    C, W, Fo, Co = lyr.in_ch, 2 * lyr.attn_dim, lyr.conv_out, lyr.out_ch
+    ds = lyr.attn_dim // lyr.num_heads
+    rows = B * Nm
+    # func_q / func_k (MLP in -> 2a -> 2a, tanh between) for every channel, written side by side: q_0..q_{C-1}, k_0..k_{C-1}
+    h1pre = Var(tp.empty(rows, 2 * C * W), False)
+    for c in range(C):
+        tp.linear(x, P[f"{pf}attn.{c}.func_q.layers.0.weight"], P[f"{pf}attn.{c}.func_q.layers.0.bias"], into=h1pre, col0=c * W)
+        tp.linear(x, P[f"{pf}attn.{c}.func_k.layers.0.weight"], P[f"{pf}attn.{c}.func_k.layers.0.bias"], into=h1pre, col0=(C + c) * W)
+    h1 = tp.act(h1pre, "tanh")
+    qk = Var(tp.empty(rows, 2 * C * W), False)
+    for c in range(C):
+        tp.linear(h1, P[f"{pf}attn.{c}.func_q.layers.1.weight"], P[f"{pf}attn.{c}.func_q.layers.1.bias"], into=qk, col0=c * W,
+                  x_cols=(c * W, (c + 1) * W))
+        tp.linear(h1, P[f"{pf}attn.{c}.func_k.layers.1.weight"], P[f"{pf}attn.{c}.func_k.layers.1.bias"], into=qk, col0=(C + c) * W,
+                  x_cols=((C + c) * W, (C + c + 1) * W))
+    # func_v: dense GCN per channel
+    xw = Var(tp.empty(rows, C * Fo), False)
+    V = Var(tp.empty(rows, C * Fo), False)
+    for c in range(C):
+        tp.matmul(x, P[f"{pf}attn.{c}.func_v.weight"], into=xw, col0=c * Fo)
+    for c in range(C):
+        _dense_gcn(tp, adjc, c, C, xw, c * Fo, P[f"{pf}attn.{c}.func_v.bias"], Fo, V, c * Fo, "none", B, Nm)
+    # attention scores + [A, adj] concat (recorded AFTER the GCNs: its backward overwrites d adjc, theirs accumulate)
+    pair = Var(tp.empty(B * Nm * Nm, 2 * C), True)
+    tp._call(L.molsde_dense_attn, qk.data.data_ptr(), qk.data.data_ptr() + 4 * C * W, qk.data.stride(0), W, ds, ptr(adjc.data), B, C, Nm,
+             ptr(pair.data), s, what="dense_attn")
+
+    def attn_bwd():
+        if pair.grad is None:
+            return
+        dqk = tp.grad_of(qk)
+        da = tp.grad_of(adjc) if adjc.needs else None
+        tp._call(L.molsde_dense_attn_bwd, qk.data.data_ptr(), qk.data.data_ptr() + 4 * C * W, qk.data.stride(0), W, ds, B, C, Nm,
+                 ptr(pair.grad), dqk.data_ptr(), dqk.data_ptr() + 4 * C * W, _p(da), s, what="dense_attn_bwd")
+    tp.ops.append(attn_bwd)
+    x_out = None
+    if not last:  # the last layer's node features are never used (invariant_scorenetwork_dense.py:80-83)
+        hmc = tp.linear(V, P[pf + "multi_channel.layers.0.weight"], P[pf + "multi_channel.layers.0.bias"], act="elu")
+        x_out = tp.linear(hmc, P[pf + "multi_channel.layers.1.weight"], P[pf + "multi_channel.layers.1.bias"], act="tanh",
+                          rowscale=flags.reshape(-1))
+    m = _mlp(tp, P, pf + "mlp", pair, len(lyr.mlp.layers), "elu")
+    adj_next = Var(tp.empty(B, Co, Nm, Nm), not last)
+    tp._call(L.molsde_dense_pair_post, ptr(m.data), ptr(flags), B, Nm, Co, ptr(adj_next.data), ptr(allc.data), allc.data.size(-1),
+             all_off, s, what="dense_pair_post")
+
+    def post_bwd():
+        dm = tp.empty(B * Nm * Nm, Co)
+        tp._call(L.molsde_dense_pair_post_bwd, _p(adj_next.grad), ptr(tp.grad_of(allc)), allc.data.size(-1), all_off, ptr(flags), B, Nm,
+                 Co, ptr(dm), s, what="dense_pair_post_bwd")
+        tp.accum(m, dm)
+    tp.ops.append(post_bwd)
+    return x_out, adj_next
+
+
+def tape_3d2d(tp: Tape, model, P: Dict[str, Var], h3d: Var, data, anneal_power: float = 0.0, draws=None, coef: float = 0.5):
+    """Records both DSM losses of the dense 3D->2D model; returns (loss_x [1], loss_adj [1]).  The backward seeds
+    d(total) = coef * (loss_x + loss_adj)  (pretrain_MoleculeSDE.py:146: (x + adj) * 0.5)."""
+    from .sde_3d_to_2d import EPSILON, gen_noise
+    L, dev, s = tp.L, tp.dev, tp.s
+    adj, rep, zd, flags, Nm = model.dense_inputs(h3d.data, data)
+    B, T, K, F = adj.size(0), model.num_diffusion_timesteps, model.num_class_X, model.nfeat
+    rows = B * Nm
+    N = h3d.data.size(0)
+    node_ptr = getattr(data, "_molsde_node_ptr", None)
+    if node_ptr is None:
+        from .graph import segment_ptr
+        node_ptr = data._molsde_node_ptr = segment_ptr(data.batch, B)
+    rep_v = Var(rep.view(rows, F), h3d.needs)
+    if h3d.needs:
+        node2graph = data.batch.to(torch.int32)
+
+        def rep_bwd():
+            if rep_v.grad is None:
+                return
+            g = tp.empty(N, F)
+            tp._call(L.molsde_from_dense_batch, ptr(rep_v.grad), F, ptr(node_ptr), ptr(node2graph), N, Nm, F, ptr(g), s,
+                     what="from_dense_batch")
+            tp.accum(h3d, g)
+        tp.ops.append(rep_bwd)
+    # ---- perturbation (no gradient) :111-152
+    th = torch.randint(0, T, size=(B // 2 + 1,), device=dev) if draws is None else draws[0].to(dev)
+    t = torch.cat([th, T - th - 1], dim=0)[:B]
+    t = t / T * (1 - EPSILON) + EPSILON
+    z_adj = gen_noise(adj, flags, sym=True, raw=None if draws is None else draws[1])
+    std_adj = model.sde_adj.marGINal_prob(torch.zeros(B, 1, 1, device=dev), t)[1].float().contiguous()
+    coef_adj = model.sde_adj.mean_coeff(t).float().contiguous()
+    p_adj = tp.empty(B, Nm, Nm)
+    tp._call(L.molsde_dense_perturb_adj, ptr(adj), ptr(z_adj), ptr(flags), ptr(coef_adj), ptr(std_adj), B, Nm, ptr(p_adj), s,
+             what="perturb_adj")
+    raw_x = torch.randn(B, Nm, K, device=dev) if draws is None else draws[2].to(dev).float().contiguous()
+    std_x = model.sde_x.marGINal_prob(torch.zeros(B, 1, 1, device=dev), t)[1].float().contiguous()
+    coef_x = model.sde_x.mean_coeff(t).float().contiguous()
+    z_x, p_x = tp.empty(B, Nm, K), tp.empty(B, Nm, K)
+    tp._call(L.molsde_dense_perturb_onehot, ptr(zd.contiguous()), ptr(raw_x), ptr(flags), ptr(coef_x), ptr(std_x), B, Nm, K, ptr(z_x),
+             ptr(p_x), s, what="perturb_onehot")
+    scale_adj = (-1.0 / std_adj).contiguous()
+    scale_x = (-1.0 / std_x).contiguous()
+    # ---- embedding :156
+    e3 = tp.linear(rep_v, P["embedding_3D.weight"], P["embedding_3D.bias"])
+    ex = tp.linear(Var(p_x.view(rows, K)), P["embedding_X.weight"], P["embedding_X.bias"])
+    emb = tp.add(e3, ex)
+
+    # ---- EdgeScoreNetwork_dense (invariant_scorenetwork_dense.py:74-93)
+    esn = model.edge_score_network
+    allc = Var(tp.empty(B * Nm * Nm, esn.fdim), False)
+    adjc0 = tp.empty(B, 2, Nm, Nm)
+    tp._call(L.molsde_dense_pow2, ptr(p_adj), B, Nm, ptr(adjc0), ptr(allc.data), esn.fdim, 0, s, what="dense_pow2")
+    x, adjc, off = emb, Var(adjc0, False), esn.c_init
+    for li, lyr in enumerate(esn.layers):
+        x, adjc = _edge_network(tp, P, f"edge_score_network.layers.{li}.", lyr, x, adjc, flags, allc, off, B, Nm,
+                                last=li == len(esn.layers) - 1)
+        off += lyr.out_ch
+    allc.needs = True
+    raw = _mlp(tp, P, "edge_score_network.final", allc, len(esn.final.layers), "silu")
+    score_adj = tp.empty(B, Nm, Nm)
+    tp._call(L.molsde_dense_edge_final, ptr(raw.data), ptr(flags), ptr(scale_adj), B, Nm, ptr(score_adj), s, what="dense_edge_final")
+
+    # ---- NodeScoreNetwork_dense (:118-131)
+    nsn = model.node_score_network
+    xs = Var(tp.empty(rows, nsn.fdim), False)
+    tp.copy_cols(emb, xs, 0)
+    adj_in = Var(p_adj, False)
+    cur_off, off = 0, nsn.nfeat
+    for li in range(nsn.depth):
+        width = nsn.nfeat if li == 0 else nsn.nhid
+        xw = Var(tp.empty(rows, nsn.nhid), False)
+        W = P[f"node_score_network.layers.{li}.weight"]
+        # x @ weight on the column slice of the concat buffer
+        xin = Var(xs.data[:, cur_off:cur_off + width], False)
+        tp.gemm(0, 0, rows, nsn.nhid, width, xin.data, xs.data.stride(0), W.data, nsn.nhid, xw.data, nsn.nhid)
+        xw.needs = True
+
+        def mm_bwd(xw=xw, W=W, width=width, cur_off=cur_off):
+            if xw.grad is None:
+                return
+            xv = xs.data[:, cur_off:cur_off + width]
+            tp.gemm(1, 0, width, nsn.nhid, rows, xv, xs.data.stride(0), xw.grad, nsn.nhid, W.grad, nsn.nhid, accumulate=True)
+            g = tp.grad_of(xs)[:, cur_off:cur_off + width]
+            tp.gemm(0, 1, rows, width, nsn.nhid, xw.grad, nsn.nhid, W.data, nsn.nhid, g, xs.data.stride(0), accumulate=True)
+        tp.ops.append(mm_bwd)
+        _dense_gcn(tp, adj_in, 0, 1, xw, 0, P[f"node_score_network.layers.{li}.bias"], nsn.nhid, xs, off, "tanh", B, Nm)
+        cur_off, off = off, off + nsn.nhid
+    rs = (flags * scale_x[:, None]).reshape(-1).contiguous()
+    score_x = _mlp(tp, P, "node_score_network.final", xs, len(nsn.final.layers), "silu", last_rowscale=rs)
+
+    # ---- losses :160-179
+    wx = None if anneal_power == 0 else (std_x ** anneal_power).contiguous()
+    wa = None if anneal_power == 0 else (std_adj ** anneal_power).contiguous()
+    lx_g, la_g, loss_x, loss_adj = tp.empty(B), tp.empty(B), tp.empty(1), tp.empty(1)
+    tp._call(L.molsde_graph_reduce, ptr(score_x.data), ptr(z_x), _p(wx), B, Nm * K, 1, ptr(lx_g), s, what="graph_reduce")
+    tp._call(L.molsde_graph_reduce, ptr(score_adj), ptr(z_adj), _p(wa), B, Nm * Nm, 1, ptr(la_g), s, what="graph_reduce")
+    tp._call(L.molsde_mean, ptr(lx_g), B, ptr(loss_x), s, what="mean")
+    tp._call(L.molsde_mean, ptr(la_g), B, ptr(loss_adj), s, what="mean")
+
+    def loss_bwd():
+        dsx = tp.empty(rows, K)
+        tp._call(L.molsde_graph_mse_bwd, ptr(score_x.data), ptr(z_x), _p(wx), B, Nm * K, float(coef), ptr(dsx), s, what="graph_mse_bwd")
+        tp.accum(score_x, dsx)
+        dsa = tp.empty(B, Nm, Nm)
+        tp._call(L.molsde_graph_mse_bwd, ptr(score_adj), ptr(z_adj), _p(wa), B, Nm * Nm, float(coef), ptr(dsa), s, what="graph_mse_bwd")
+        draw = tp.empty(B * Nm * Nm, 1)
+        tp._call(L.molsde_dense_edge_final_bwd, ptr(dsa), ptr(flags), ptr(scale_adj), B, Nm, ptr(draw), s, what="dense_edge_final_bwd")
+        tp.accum(raw, draw)
+    tp.ops.append(loss_bwd)
+    return loss_x, loss_adj

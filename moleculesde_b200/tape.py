@@ -130,9 +130,13 @@ class Tape:
         self._call(self.L.molsde_colsum, _p(X), M, N, ldx, _p(out), int(accumulate), _p(ws), n, self.s, what="colsum")
 
     def linear(self, x: Var, W: Var, b: Optional[Var], act: str = "none", into: Optional[Var] = None, col0: int = 0,
-               rowscale: Optional[torch.Tensor] = None) -> Var:
+               rowscale: Optional[torch.Tensor] = None, x_cols: Optional[tuple] = None) -> Var:
         """y = act(rowscale * (x W^T + b)); W [out,in] as nn.Linear.  `into`/`col0`: write y into columns
-        [col0, col0+out) of the wider buffer Var `into` (a concat without a copy); its gradient is read from there."""
+        [col0, col0+out) of the wider buffer Var `into` (a concat without a copy); its gradient is read from there.
+        `x_cols=(a,b)`: the input is the column slice x[:, a:b]; its gradient is accumulated into that slice of x.grad."""
+        if x_cols is not None:
+            full = x
+            x = Var(full.data[:, x_cols[0]:x_cols[1]], False)
         M, K = x.data.shape
         Nout = W.data.shape[0]
         a = ACT[act]
@@ -152,7 +156,8 @@ class Tape:
                 self.ew(3, pre, b.data, None, 1.0, pre, cols=Nout)
         if a:
             self._call(self.L.molsde_act_fwd, _p(pre), pre.numel(), a, _p(y), self.s, what="act_fwd")
-        needs = x.needs or W.needs or (b is not None and b.needs)
+        x_needs = full.needs if x_cols is not None else x.needs
+        needs = x_needs or W.needs or (b is not None and b.needs)
         out = into if into is not None else Var(y, needs)
         if into is not None:
             into.needs = into.needs or needs
@@ -177,12 +182,57 @@ class Tape:
                     self.gemm(1, 0, Nout, K, M, dpre, _ld(dpre), x.data, _ld(x.data), W.grad, _ld(W.grad), accumulate=True)
                 if b is not None and b.needs:
                     self.colsum(dpre, M, Nout, _ld(dpre), b.grad, accumulate=True)
-                if x.needs:
+                if x_cols is not None:
+                    if full.needs:
+                        g = self.grad_of(full)[:, x_cols[0]:x_cols[1]]
+                        self.gemm(0, 0, M, K, Nout, dpre, _ld(dpre), W.data, _ld(W.data), g, _ld(g), accumulate=True)
+                elif x.needs:
                     dx = self.empty(M, K)
                     self.gemm(0, 0, M, K, Nout, dpre, _ld(dpre), W.data, _ld(W.data), dx, K)
                     self.accum(x, dx)
             self.ops.append(bwd)
         return out
+
+    def matmul(self, x: Var, Wio: Var, into: Optional[Var] = None, col0: int = 0) -> Var:
+        """y = x @ W with W stored [in, out] (NodeNetwork_dense.weight, node_network_dense.py:33,73)."""
+        M, K = x.data.shape
+        Nout = Wio.data.shape[1]
+        y = into.data[:, col0:col0 + Nout] if into is not None else self.empty(M, Nout)
+        self.gemm(0, 0, M, Nout, K, x.data, _ld(x.data), Wio.data, _ld(Wio.data), y, _ld(y))
+        needs = x.needs or Wio.needs
+        out = into if into is not None else Var(y, needs)
+        if into is not None:
+            into.needs = into.needs or needs
+        if needs:
+            def bwd():
+                if into is not None:
+                    dy = self.grad_of(into)[:, col0:col0 + Nout]
+                else:
+                    if out.grad is None:
+                        return
+                    dy = out.grad
+                if Wio.needs:
+                    self.gemm(1, 0, K, Nout, M, x.data, _ld(x.data), dy, _ld(dy), Wio.grad, _ld(Wio.grad), accumulate=True)
+                if x.needs:
+                    dx = self.empty(M, K)
+                    self.gemm(0, 1, M, K, Nout, dy, _ld(dy), Wio.data, _ld(Wio.data), dx, K)
+                    self.accum(x, dx)
+            self.ops.append(bwd)
+        return out
+
+    def copy_cols(self, src: Var, dst: Var, col0: int) -> None:
+        """dst[:, col0:col0+w] = src (a concat slot); backward adds that slice of dst.grad to src.grad."""
+        rows, w = src.data.shape
+        d = dst.data[:, col0:col0 + w]
+        self._call(self.L.molsde_copy2d, _p(src.data), _ld(src.data), _p(d), _ld(d), rows, w, 0, self.s, what="copy2d")
+        dst.needs = dst.needs or src.needs
+        if src.needs:
+            def bwd():
+                g = self.empty(rows, w)
+                gs = self.grad_of(dst)[:, col0:col0 + w]
+                self._call(self.L.molsde_copy2d, _p(gs), _ld(gs), _p(g), w, rows, w, 0, self.s, what="copy2d")
+                self.accum(src, g)
+            self.ops.append(bwd)
 
     def act(self, x: Var, act: str) -> Var:
         a = ACT[act]

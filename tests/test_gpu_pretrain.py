@@ -184,3 +184,32 @@ def test_dual_cl_loss_and_backward(gg, golden):
     ((l1 + l2) / 2).backward()
     assert_parity(Xv.grad, Xc.grad, "d CL / d X")
     assert_parity(Yv.grad, Yc.grad, "d CL / d Y")
+
+
+@pytest.mark.parametrize("kind", ["VE", "VP"])
+def test_3d2d_losses_and_grads(kind, gg, golden, golden_batch):
+    """Dense 3D->2D model: both DSM losses and every parameter gradient of (loss_x + loss_adj) / 2."""
+    from moleculesde_b200.pretrain import ParamStore, tape_3d2d
+    from moleculesde_b200.sde_3d_to_2d import SDEModel3Dto2D_node_adj_dense
+    from moleculesde_b200.tape import Tape, Var
+    dev = _dev()
+    sec = gg["pretrain_" + kind]
+    _, batch = golden_batch
+    m32 = SDEModel3Dto2D_node_adj_dense(
+        dim3D=300, c_init=2, c_hid=8, c_final=4, num_heads=4, adim=16, nhid=16, num_layers=4, emb_dim=300, num_linears=3,
+        beta_min=0.1 if kind == "VE" else 0.2, beta_max=1.0, num_diffusion_timesteps=1000, SDE_type=kind, num_class_X=119,
+        noise_on_one_hot=True)
+    m32.load_state_dict(sd_from_manifest(golden["manifest"]["sde3d2d"], golden["meta"]["weight_seed"]))
+    m32.train()
+    store = ParamStore({"sde3d2d": m32}, dev)
+    b = batch.to(dev)
+    tp = Tape(dev)
+    h3d = Var(sec["h3d"].to(dev).contiguous(), True)
+    draws = [v for _, v in sec["draws"][12:15]]
+    lx, la = tape_3d2d(tp, m32, store.vars("sde3d2d"), h3d, b, 0.0, draws, coef=0.5)
+    for got, want, what in ((lx, sec["loss_x"], "loss_x"), (la, sec["loss_adj"], "loss_adj")):
+        assert abs(float(got) - float(want)) <= REL_TOL * abs(float(want)), (what, float(got), float(want))
+    tp.backward()
+    torch.cuda.synchronize()
+    _check_module_grads(store, "sde3d2d", sec)
+    assert torch.isfinite(h3d.grad).all()
