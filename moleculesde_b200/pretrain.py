@@ -622,3 +622,71 @@ def tape_3d2d(tp: Tape, model, P: Dict[str, Var], h3d: Var, data, anneal_power: 
         tp.accum(raw, draw)
     tp.ops.append(loss_bwd)
     return loss_x, loss_adj
+
+
+# ======================================================================================================
+# the training iteration (pretrain_MoleculeSDE.py:124-152)
+# ======================================================================================================
+class PretrainStep:
+    """`train()` loop body of the reference for one batch: four modules in train mode, loss =
+    c_CL * dual_CL + c_2D3D * loss_2Dto3D + c_3D2D * (loss_x + loss_adj)/2, backward, data-parallel all-reduce, Adam."""
+
+    def __init__(self, gnn, schnet, sde_2d3d, sde_3d2d, device, lr: float = 1e-4, T: float = 0.1, coeff_contrastive: float = 1.0,
+                 coeff_2Dto3D: float = 1.0, coeff_3Dto2D: float = 1.0, anneal_power: float = 0.0, gnn_2d_lr_scale: float = 1.0,
+                 gnn_3d_lr_scale: float = 1.0, weight_decay: float = 0.0):
+        self.gnn, self.schnet, self.m23, self.m32 = gnn, schnet, sde_2d3d, sde_3d2d
+        self.dev = device
+        self.store = ParamStore({"gnn": gnn, "schnet": schnet, "sde2d3d": sde_2d3d, "sde3d2d": sde_3d2d}, device)
+        self.lr, self.T, self.anneal_power, self.weight_decay = lr, T, anneal_power, weight_decay
+        self.c_cl, self.c_23, self.c_32 = coeff_contrastive, coeff_2Dto3D, coeff_3Dto2D
+        # pretrain_MoleculeSDE.py:331-335: 2D GNN and 2D->3D share gnn_2d_lr_scale; SchNet and 3D->2D share gnn_3d_lr_scale
+        self.lr_scale = {"gnn": gnn_2d_lr_scale, "sde2d3d": gnn_2d_lr_scale, "schnet": gnn_3d_lr_scale, "sde3d2d": gnn_3d_lr_scale}
+        self.launches = 0
+        for m in (gnn, schnet, sde_2d3d, sde_3d2d):
+            m.train()
+
+    def forward_backward(self, batch, draws: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+        """Forward + backward of one batch; gradients are left in `store.grad`.  `draws` (parity tests):
+        {"cl": (perm1, perm2), "sde2d3d": {...}, "sde3d2d": [randint, randn_adj, randn_x]}."""
+        draws = draws or {}
+        st = self.store
+        st.zero_grad()
+        tp = Tape(self.dev)
+        cache = batch.__dict__.setdefault("_molsde_train_cache", {})
+        h2d = tape_gin(tp, self.gnn, st.vars("gnn"), batch.x, batch.edge_index, batch.edge_attr, cache, batch.batch, batch.num_graphs)
+        z = cache.get("z")
+        if z is None:
+            z = cache["z"] = batch.x[:, 0].contiguous()
+        h3d = tape_schnet(tp, self.schnet, st.vars("schnet"), z, batch.positions, batch.batch, batch.num_graphs, cache)
+        out = {}
+        if self.c_cl > 0:
+            n1, n2 = draws.get("cl", (None, None))
+            out["cl_loss"], accs = tape_dual_cl(tp, h2d, h3d, self.T, n1, n2, coef=self.c_cl)
+            out["cl_acc_pair"] = accs
+        if self.c_23 > 0:
+            out["loss_2d3d"] = tape_2d3d(tp, self.m23, st.vars("sde2d3d"), h2d, batch, self.anneal_power, draws.get("sde2d3d"),
+                                         coef=self.c_23)
+        if self.c_32 > 0:
+            out["loss_x"], out["loss_adj"] = tape_3d2d(tp, self.m32, st.vars("sde3d2d"), h3d, batch, self.anneal_power,
+                                                       draws.get("sde3d2d"), coef=0.5 * self.c_32)
+        tp.backward()
+        self.launches = tp.launches
+        out["h2d"], out["h3d"] = h2d, h3d
+        return out
+
+    def step(self, batch, draws: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+        out = self.forward_backward(batch, draws)
+        scale = self.store.all_reduce()
+        self.store.adam_step(self.lr, self.lr_scale, weight_decay=self.weight_decay, grad_scale=scale)
+        return out
+
+    @staticmethod
+    def total_loss(out, c_cl=1.0, c_23=1.0, c_32=1.0) -> float:
+        t = 0.0
+        if "cl_loss" in out:
+            t += c_cl * float(out["cl_loss"])
+        if "loss_2d3d" in out:
+            t += c_23 * float(out["loss_2d3d"])
+        if "loss_x" in out:
+            t += c_32 * 0.5 * (float(out["loss_x"]) + float(out["loss_adj"]))
+        return t

@@ -213,3 +213,66 @@ def test_3d2d_losses_and_grads(kind, gg, golden, golden_batch):
     torch.cuda.synchronize()
     _check_module_grads(store, "sde3d2d", sec)
     assert torch.isfinite(h3d.grad).all()
+
+
+@pytest.mark.parametrize("kind", ["VE", "VP"])
+def test_full_pretrain_step(kind, gg, golden, golden_batch):
+    """The whole iteration: losses, d loss / d representations, every gradient, and the parameters after one Adam step."""
+    from moleculesde_b200.pretrain import PretrainStep
+    from moleculesde_b200.sde_2d_to_3d import SDEModel2Dto3D_02
+    from moleculesde_b200.sde_3d_to_2d import SDEModel3Dto2D_node_adj_dense
+    from test_gpu_sde2d3d import _gpu_batch, assert_parity
+    dev = _dev()
+    sec = gg["pretrain_" + kind]
+    _, batch = golden_batch
+    gnn, sch = _encoders(golden, dev)
+    m23 = SDEModel2Dto3D_02(emb_dim=300, hidden_dim=32, beta_schedule=None, beta_min=0.2, beta_max=1.0,
+                            num_diffusion_timesteps=1000, SDE_type=kind, use_extend_graph=True)
+    m23.load_state_dict(sd_from_manifest(golden["manifest"]["sde2d3d"], golden["meta"]["weight_seed"]))
+    m32 = SDEModel3Dto2D_node_adj_dense(
+        dim3D=300, c_init=2, c_hid=8, c_final=4, num_heads=4, adim=16, nhid=16, num_layers=4, emb_dim=300, num_linears=3,
+        beta_min=0.1 if kind == "VE" else 0.2, beta_max=1.0, num_diffusion_timesteps=1000, SDE_type=kind, num_class_X=119,
+        noise_on_one_hot=True)
+    m32.load_state_dict(sd_from_manifest(golden["manifest"]["sde3d2d"], golden["meta"]["weight_seed"]))
+    ps = PretrainStep(gnn, sch, m23, m32, dev, lr=1e-4, T=0.1)
+    b = _gpu_batch(batch, dev)
+    d = sec["draws"]
+    draws = {"cl": (d[0][1], d[1][1]), "sde2d3d": _draws_2d3d(sec), "sde3d2d": [v for _, v in d[12:15]]}
+    out = ps.forward_backward(b, draws)
+    torch.cuda.synchronize()
+    for key, want in (("cl_loss", "cl_loss"), ("loss_2d3d", "loss_2d3d"), ("loss_x", "loss_x"), ("loss_adj", "loss_adj")):
+        assert abs(float(out[key]) - float(sec[want])) <= REL_TOL * abs(float(sec[want])), key
+    assert abs(PretrainStep.total_loss(out) - float(sec["loss"])) <= REL_TOL * abs(float(sec["loss"]))
+    assert_parity(out["h2d"].grad, sec["d_h2d"], "d loss / d node_2D_repr")
+    assert_parity(out["h3d"].grad, sec["d_h3d"], "d loss / d node_3D_repr")
+    _check_module_grads(ps.store, "gnn", sec, skip_zero=("mlp.0.bias", "mlp.3.bias"))
+    _check_module_grads(ps.store, "schnet", sec)
+    _check_module_grads(ps.store, "sde3d2d", sec)
+    zero = ("edge_2D_emb.0.bias", "lin_key.bias")
+    _check_module_grads(ps.store, "sde2d3d", sec, skip_zero=zero)
+    assert ps.launches > 0
+    # Adam (lr 1e-4, first step => |update| ~ lr): compare the parameter samples after the step
+    ps.store.adam_step(ps.lr, ps.lr_scale)
+    torch.cuda.synchronize()
+    mods = {"gnn": gnn, "schnet": sch, "sde2d3d": m23, "sde3d2d": m32}
+    worst, n_bad, n_all = 0.0, 0, 0
+    for mname, m in mods.items():
+        params = dict(m.named_parameters())
+        for n, want in sec["after_step"][mname].items():
+            if sec["grads"][mname].get(n) is None:
+                continue
+            if any(n.endswith(zz) or n == zz for zz in zero + ("mlp.0.bias", "mlp.3.bias")):
+                continue  # sign of round-off noise decides the +-lr update of analytically-zero gradients
+            gn = float(sec["grads"][mname][n]["norm"]) / max(sec["grads"][mname][n]["numel"], 1) ** 0.5
+            if gn < 1e-6:
+                continue
+            f = params[n].detach().reshape(-1).float().cpu()
+            smp = f[::want["stride"]][:want["sample"].numel()]
+            diff = (smp - want["sample"]).abs()
+            worst = max(worst, float(diff.max()))
+            n_bad += int((diff > 2e-6).sum())
+            n_all += diff.numel()
+    # the first Adam step moves every element by ~lr * sign(g): elements whose gradient is ~0 may flip sign between
+    # implementations (error up to 2 lr); all others must agree to a small fraction of lr
+    assert worst <= 2.1e-4, worst
+    assert n_bad <= 0.01 * n_all, (n_bad, n_all)
