@@ -305,8 +305,8 @@ int molsde_edge_mul_reduce(const float* A, const int32_t* ia, const float* W, co
 /* out[e,:] = A[ia[e],:] * B[ib[e],:] */
 int molsde_edge_mul_gather(const float* A, const int32_t* ia, const float* B, const int32_t* ib, int64_t E, int32_t cols, float* out,
                            void* stream);
-/* out[0] (+)= alpha <a,b> */
-int molsde_dot(const float* a, const float* b, int64_t n, float alpha, int32_t accumulate, float* out, void* stream);
+/* out[0] (+)= alpha <a,b>;  ws: >= 128 doubles */
+int molsde_dot(const float* a, const float* b, int64_t n, float alpha, int32_t accumulate, float* out, double* ws, void* stream);
 /* GINConv (molecule_gnn_model.py:13-32): pre = (1+eps) x + sum_{e->i} relu(x_src + BondEncoder(e)); dmsg = dpre[tgt] * relu' */
 int molsde_gin_aggregate_fwd(const float* x, const float* T, const int32_t* ekeys, int32_t F, const int32_t* rowptr, const int32_t* src,
                              const float* eps, int64_t N, int32_t cols, float* pre, void* stream);

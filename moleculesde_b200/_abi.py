@@ -150,7 +150,7 @@ def lib() -> ctypes.CDLL:
     L.molsde_embed_sum.argtypes = [P, P, c_int64, c_int32, c_int32, P, P]
     L.molsde_edge_mul_reduce.argtypes = [P, P, P, P, P, c_int64, c_int32, P, P]
     L.molsde_edge_mul_gather.argtypes = [P, P, P, P, c_int64, c_int32, P, P]
-    L.molsde_dot.argtypes = [P, P, c_int64, c_float, c_int32, P, P]
+    L.molsde_dot.argtypes = [P, P, c_int64, c_float, c_int32, P, P, P]
     L.molsde_gin_aggregate_fwd.argtypes = [P, P, P, c_int32, P, P, P, c_int64, c_int32, P, P]
     L.molsde_gin_message_bwd.argtypes = [P, P, P, c_int32, P, P, P, c_int64, c_int32, P, P]
     L.molsde_schnet_edge_feat.argtypes = [P, P, P, c_int64, P, c_int32, c_float, c_float, P, P, P]

@@ -178,6 +178,28 @@ __global__ void seg_gather_sum_kernel(const float* __restrict__ X, const int32_t
     out[idx] = accumulate ? out[idx] + acc : acc;
 }
 
+// the same for FEW, LONG segments (embedding-table gradients: ~100 rows of the table, thousands of lookups each):
+// CTA (32 columns x 8 row lanes) per (segment, column block), fixed-order tree over the 8 lanes
+__global__ void __launch_bounds__(256)
+seg_gather_sum_wide_kernel(const float* __restrict__ X, const int32_t* __restrict__ ptr, const int32_t* __restrict__ perm, int cols,
+                           const float* __restrict__ scale, int accumulate, int row_div, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t s = blockIdx.x;
+    const int c = blockIdx.y * 32 + tx;
+    float acc = 0.0f;
+    if (c < cols)
+        for (int p = ptr[s] + ty; p < ptr[s + 1]; p += 8) acc += X[static_cast<int64_t>((perm ? perm[p] : p) / row_div) * cols + c];
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        float t = 0.0f;
+        for (int q = 0; q < 8; ++q) t += red[q][tx];
+        if (scale) t *= scale[s];
+        out[s * cols + c] = accumulate ? out[s * cols + c] + t : t;
+    }
+}
+
 // stable bucket sort: rowptr[b], perm = element ids ordered by (key, id).  One CTA per bucket, ascending scan.
 __global__ void bucket_count_kernel(const int64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ count) {
     __shared__ int red[256];
@@ -244,19 +266,26 @@ __global__ void edge_mul_gather_kernel(const float* __restrict__ A, const int32_
     out[idx] = A[static_cast<int64_t>(ia[e]) * cols + c] * B[static_cast<int64_t>(ib[e]) * cols + c];
 }
 
-// out[0] (+)= alpha * <a, b>   (fixed-order, one CTA)
-__global__ void __launch_bounds__(1024) dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float alpha,
-                                                   int accumulate, float* __restrict__ out) {
-    __shared__ double red[1024];
+// out[0] (+)= alpha * <a, b>: DOT_CTAS fp64 partial sums into the caller's workspace, then a fixed-order finish
+constexpr int DOT_CTAS = 128;
+__global__ void __launch_bounds__(256) dot_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                                          double* __restrict__ part) {
+    __shared__ double red[256];
     double acc = 0.0;
-    for (int64_t i = threadIdx.x; i < n; i += 1024) acc += static_cast<double>(a[i]) * b[i];
+    for (int64_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += static_cast<int64_t>(DOT_CTAS) * 256)
+        acc += static_cast<double>(a[i]) * b[i];
     red[threadIdx.x] = acc;
     __syncthreads();
-    for (int o = 512; o > 0; o >>= 1) {
+    for (int o = 128; o > 0; o >>= 1) {
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.0f) + alpha * static_cast<float>(red[0]);
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void dot_finish_kernel(const double* __restrict__ part, float alpha, int accumulate, float* __restrict__ out) {
+    double t = 0.0;
+    for (int q = 0; q < DOT_CTAS; ++q) t += part[q];
+    out[0] = (accumulate ? out[0] : 0.0f) + alpha * static_cast<float>(t);
 }
 
 // ---- GINConv (molecule_gnn_model.py:13-32):  pre[i] = (1+eps) x_i + sum_{e->i} relu(x_src + bond_emb_e),
@@ -473,11 +502,13 @@ using namespace molsde;
 static inline unsigned blocks_for(int64_t n, int t = 256) { return static_cast<unsigned>((n + t - 1) / t); }
 
 static int gemm_splits(int64_t M, int64_t N, int64_t K) {
+    // weight gradients are tall-skinny reductions (K = #rows >> M, N): split K until ~4 CTAs per SM are in flight, each
+    // with at least 2 k-steps; the partial buffer (splits x M x N) stays small because M x N is a weight matrix
     const int64_t tiles = ((M + GM - 1) / GM) * ((N + GN - 1) / GN);
-    int64_t s = (2 * kNumSMs + tiles - 1) / tiles;
-    const int64_t maxs = (K + 255) / 256;
+    int64_t s = (4 * kNumSMs + tiles - 1) / tiles;
+    const int64_t maxs = (K + 2 * GK - 1) / (2 * GK);
     if (s > maxs) s = maxs;
-    if (s > 64) s = 64;
+    if (s > 1024) s = 1024;
     return s < 1 ? 1 : static_cast<int>(s);
 }
 
@@ -563,6 +594,11 @@ int molsde_seg_gather_sum(const float* X, const int32_t* ptr, const int32_t* per
                           int32_t accumulate, int32_t row_div, float* out, void* stream) {
     if (!X || !ptr || !out || segments < 0 || cols <= 0 || row_div <= 0) return MOLSDE_ERR_INVALID;
     if (segments == 0) return MOLSDE_OK;
+    if (segments <= 1024) {  // few segments: one CTA per (segment, 32 columns) instead of one thread per output
+        seg_gather_sum_wide_kernel<<<dim3(static_cast<unsigned>(segments), (cols + 31) / 32), 256, 0, as_stream(stream)>>>(
+            X, ptr, perm, cols, scale, accumulate, row_div, out);
+        return check_launch("seg_gather_sum_wide");
+    }
     seg_gather_sum_kernel<<<blocks_for(segments * cols), 256, 0, as_stream(stream)>>>(X, ptr, perm, segments, cols, scale, accumulate,
                                                                                    row_div, out);
     return check_launch("seg_gather_sum");
@@ -587,9 +623,10 @@ int molsde_edge_mul_gather(const float* A, const int32_t* ia, const float* B, co
     edge_mul_gather_kernel<<<blocks_for(E * cols), 256, 0, as_stream(stream)>>>(A, ia, B, ib, E, cols, out);
     return check_launch("edge_mul_gather");
 }
-int molsde_dot(const float* a, const float* b, int64_t n, float alpha, int32_t accumulate, float* out, void* stream) {
-    if (!a || !b || !out || n < 0) return MOLSDE_ERR_INVALID;
-    dot_kernel<<<1, 1024, 0, as_stream(stream)>>>(a, b, n, alpha, accumulate, out);
+int molsde_dot(const float* a, const float* b, int64_t n, float alpha, int32_t accumulate, float* out, double* ws, void* stream) {
+    if (!a || !b || !out || !ws || n < 0) return MOLSDE_ERR_INVALID;  // ws: >= 128 doubles
+    dot_partial_kernel<<<DOT_CTAS, 256, 0, as_stream(stream)>>>(a, b, n, ws);
+    dot_finish_kernel<<<1, 1, 0, as_stream(stream)>>>(ws, alpha, accumulate, out);
     return check_launch("dot");
 }
 int molsde_gin_aggregate_fwd(const float* x, const float* T, const int32_t* ekeys, int32_t F, const int32_t* rowptr, const int32_t* src,

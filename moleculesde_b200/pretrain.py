@@ -386,7 +386,8 @@ def tape_dual_cl(tp: Tape, X: Var, Y: Var, T: float, neg_index_1: Optional[torch
     dX, dY = tp.empty(N, D), tp.empty(N, D)
     saved = []
     for k, (A, Bv, neg) in enumerate(((X, Y, neg_index_1), (Y, X, neg_index_2))):
-        neg = torch.randperm(N) if neg is None else neg   # CPU generator in the reference (util.py:55)
+        # the reference draws on the CPU generator (util.py:55); here on the device, so that the step stays capturable
+        neg = torch.randperm(N, device=dev) if neg is None else neg
         perm = neg.to(dev).long().contiguous()
         inv = torch.empty_like(perm)
         inv[perm] = torch.arange(N, device=dev)

@@ -314,9 +314,17 @@ class SDEModel3Dto2D_node_adj_dense(nn.Module):
         """to_dense_adj / to_dense_batch prologue (:118-134): (adj, rep_dense, z_dense, flags, Nm)."""
         require_device(node_3D_repr)
         batch = data.batch
-        B = int(batch.max().item()) + 1                                    # :124 (host sync, as the reference)
-        node_ptr = segment_ptr(batch, B)
-        Nm = int((node_ptr[1:] - node_ptr[:-1]).max().item())              # :127
+        cached = getattr(data, "_molsde_dense_dims", None)                 # static per batch: keeps replays sync-free
+        if cached is None:
+            B = int(batch.max().item()) + 1                                # :124 (host sync, as the reference)
+            node_ptr = segment_ptr(batch, B)
+            Nm = int((node_ptr[1:] - node_ptr[:-1]).max().item())          # :127
+            try:
+                data._molsde_dense_dims = (B, Nm, node_ptr)
+            except AttributeError:
+                pass
+        else:
+            B, Nm, node_ptr = cached
         if Nm > 64:
             raise _abi.MolsdeError("dense 3D->2D kernels support at most 64 atoms per graph")
         dev, s = node_3D_repr.device, stream_ptr(node_3D_repr)

@@ -449,7 +449,9 @@ class Tape:
                 if T.needs:
                     self.seg_sum(dmsg, ekey_index, cols, T.grad, accumulate=True, row_div=F)
                 if eps.needs:
-                    self._call(self.L.molsde_dot, _p(out.grad), _p(x.data), out.grad.numel(), 1.0, 1, _p(eps.grad), self.s, what="dot")
+                    ws = self.empty(128, dtype=torch.float64)
+                    self._call(self.L.molsde_dot, _p(out.grad), _p(x.data), out.grad.numel(), 1.0, 1, _p(eps.grad), _p(ws), self.s,
+                               what="dot")
                 if x.needs:
                     dx = self.empty(N, cols)
                     self.seg_sum(dmsg, src, cols, dx)
