@@ -362,6 +362,16 @@ int molsde_equi_bwd(const float* dgrad, const float* basis, const int32_t* rowpt
 int molsde_dsm_pos_loss_bwd(const float* score, const float* noise, const float* w, const int32_t* node_ptr, const int32_t* node2graph,
                             int64_t N, int32_t B, float upstream, float* dscore, void* stream);
 
+/* fp32-accurate GEMM on tcgen05 tensor cores (3xTF32 split, TMEM accumulator; csrc/tc_gemm.cu):
+ *   C[M,N] (+)= A . B^T (+ bias[n]) -> * rowscale[m] -> act (+ R),   A(m,k) = A[m*sam + k*sak],  B(n,k) = B[n*sbn + k*sbk]
+ * (one stride of each operand must be 1).  nn.Linear forward: A = x (sam = ldx, sak = 1), B = W [out,in] (sbn = in, sbk = 1);
+ * dx = dy . W: B = W with sbn = 1, sbk = in;  dW = dy^T . x: A = dy (sam = 1, sak = ldy), B = x (sbn = 1, sbk = ldx), split-K
+ * over the rows when `ws` (molsde_tc_gemm_ws_floats) is given.  status (optional): set to 1 on an internal wait time-out. */
+int64_t molsde_tc_gemm_ws_floats(int64_t M, int64_t N, int64_t K);
+int molsde_tc_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
+                   const float* bias, int32_t act, const float* rowscale, const float* R, int64_t ldr, float* C, int64_t ldc,
+                   int32_t accumulate, float* ws, int64_t ws_floats, int32_t* status, void* stream);
+
 /* Backward kernels of the dense 3D->2D score networks (forward: molsde_dense_*):
  *  dense_gcn_bwd: dpre [B*Nm, C*Fo] = dout * act'(out) (its column sum = dbias), dxw [B*Nm, lddx], and (dadj != NULL) the
  *                 gradient w.r.t. the off-diagonal adjacency entries [B,C,Nm,Nm] (Fo <= 16; act none or tanh);

@@ -1,0 +1,294 @@
+// fp32-accurate GEMM on the 5th-generation tensor cores (tcgen05, sm_100a):
+//     C[M,N] (+)= A[M,K] . B[N,K]^T  (+ bias[n]) -> rowscale -> activation (+ residual)
+// with arbitrary element strides for A and B (one of the two strides of each operand must be 1), so that the same
+// kernel serves  y = x W^T  (forward),  dx = dy . W  and  dW = dy^T . x  (backward, split-K over the rows).
+//
+// Arithmetic: 3xTF32.  Every fp32 operand value v is split into hi = top 19 bits (exactly a tf32 number) and the exact
+// remainder lo = v - hi; the accumulator receives lo_a*hi_b + hi_a*lo_b + hi_a*hi_b in fp32 (TMEM).  The dropped
+// lo*lo term is < 2^-22 relative, i.e. the result is fp32-class (measured ~1e-6 max-norm relative vs fp64), which keeps
+// the 1e-4 parity bar of scores, losses and gradients (BASELINE.json north_star).
+//
+// Structure (one CTA = one 128 x BN output tile, 256 threads):
+//   * all 8 warps stage a 32-deep K block of A and B from global memory: load -> split hi/lo in registers -> store into
+//     the canonical K-major no-swizzle core-matrix layout (8 rows x 16 B) that the UMMA shared-memory descriptors address;
+//   * one thread issues the 12 tcgen05.mma (3 terms x 4 K-steps, M=128, N=BN, K=8) of the block and commits them to an
+//     mbarrier; the two smem stages ping-pong, so staging of block k+1 overlaps the tensor-core work of block k;
+//   * the fp32 accumulator lives in TMEM (BN columns x 128 lanes).  Its adds truncate, so every TC_FLUSH K blocks it is
+//     drained with tcgen05.ld into fp32 registers (warp w owns lanes 32*(w%4).., warps 0-3 / 4-7 split the columns);
+//     the epilogue applies bias / rowscale / activation / residual and stores, or writes a raw split-K partial.
+#include "common.cuh"
+
+namespace molsde {
+
+constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 256;
+constexpr int TC_FLUSH = 8;  // K blocks (of 32) accumulated in TMEM between two drains into registers
+constexpr uint32_t TC_SBO = 128;  // bytes between consecutive 8-row core-matrix groups
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    return static_cast<uint64_t>((saddr & 0x3FFFF) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+           (static_cast<uint64_t>(TC_SBO >> 4) << 32) | (static_cast<uint64_t>(1) << 46);
+}
+template <int N>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((static_cast<uint32_t>(N) >> 3) << 17) | ((128u >> 4) << 24);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ bool tc_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int it = 0; it < (1 << 22) && !done; ++it)  // bounded: a descriptor bug must not hang the GPU
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+    switch (act) {
+        case 1: return fmaxf(v, 0.0f);
+        case 2: return silu_f(v);
+        case 3: return softplus_f(v) - 0.69314718246459961f;
+        case 4: return tanhf(v);
+        case 5: return v > 0.0f ? v : expm1f(v);
+        default: return v;
+    }
+}
+
+// Stage one [R x 32] K block of an operand:  element (r, k) = src[r * sr + k * sk], rows >= rvalid / k >= kvalid are zero.
+// Work item = (row r, k-chunk kc of 4): lanes run along r, so the 16-byte smem stores of a warp are contiguous (conflict
+// free) and, for r-contiguous operands, the global loads are coalesced; k-contiguous aligned operands use one float4 load.
+template <int R>
+__device__ __forceinline__ void tc_stage(float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ src, int64_t sr,
+                                         int64_t sk, int rvalid, int kvalid, bool vec4) {
+    for (int item = threadIdx.x; item < R * (TC_BK / 4); item += TC_THREADS) {
+        const int r = item % R, kc = item / R;
+        float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (r < rvalid) {
+            const float* p = src + r * sr + static_cast<int64_t>(kc) * 4 * sk;
+            if (vec4 && kc * 4 + 3 < kvalid) {
+                const float4 t = *reinterpret_cast<const float4*>(p);
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (kc * 4 + j < kvalid) v[j] = p[j * sk];
+            }
+        }
+        float4 h4, l4;
+        h4.x = __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u); h4.y = __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u);
+        h4.z = __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u); h4.w = __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u);
+        l4.x = v[0] - h4.x; l4.y = v[1] - h4.y; l4.z = v[2] - h4.z; l4.w = v[3] - h4.w;
+        const int idx = kc * (R / 8) * 32 + (r >> 3) * 32 + (r & 7) * 4;
+        *reinterpret_cast<float4*>(hi + idx) = h4;
+        *reinterpret_cast<float4*>(lo + idx) = l4;
+    }
+}
+
+struct TcArgs {
+    int64_t M, N, K;
+    const float* A; int64_t sam, sak;
+    const float* B; int64_t sbn, sbk;
+    const float* bias; const float* rowscale; const float* R; int64_t ldr;
+    float* C; int64_t ldc;
+    int act, accumulate;
+    int64_t k_per_split;   // multiple of TC_BK
+    float* ws;             // split-K partials [splits][M][N] or NULL
+    int vecA, vecB;
+    int32_t* status;       // set to 1 if an mbarrier wait timed out (never expected)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs a) {
+    extern __shared__ __align__(128) float tc_smem[];
+    constexpr int A_FLOATS = TC_BM * TC_BK, B_FLOATS = BN * TC_BK;
+    constexpr int STAGE = 2 * A_FLOATS + 2 * B_FLOATS;  // A hi | A lo | B hi | B lo
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t m0 = static_cast<int64_t>(blockIdx.y) * TC_BM, n0 = static_cast<int64_t>(blockIdx.x) * BN;
+    const int64_t kb0 = static_cast<int64_t>(blockIdx.z) * a.k_per_split;
+    const int64_t kend = min(a.K, kb0 + a.k_per_split);
+    const int nkb = static_cast<int>((kend - kb0 + TC_BK - 1) / TC_BK);
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)), "r"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    bool ok = true;
+    constexpr int HALF = BN / 2;                 // warps 0-3 own columns [0, HALF), warps 4-7 own [HALF, BN) of their 32 lanes
+    const int cbase = (warp >> 2) * HALF;
+    float accr[HALF];
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) accr[j] = 0.0f;
+
+    const int rvalidA = static_cast<int>(min(static_cast<int64_t>(TC_BM), a.M - m0));
+    const int rvalidB = static_cast<int>(min(static_cast<int64_t>(BN), a.N - n0));
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        float* st = tc_smem + s * STAGE;
+        if (kb >= 2) ok &= tc_wait(tc_smem_u32(&bars[s]), ((kb >> 1) - 1) & 1);  // tensor core finished reading stage s
+        const int64_t k0 = kb0 + static_cast<int64_t>(kb) * TC_BK;
+        const int kvalid = static_cast<int>(min(static_cast<int64_t>(TC_BK), kend - k0));
+        tc_stage<TC_BM>(st, st + A_FLOATS, a.A + m0 * a.sam + k0 * a.sak, a.sam, a.sak, rvalidA, kvalid, a.vecA != 0);
+        tc_stage<BN>(st + 2 * A_FLOATS, st + 2 * A_FLOATS + B_FLOATS, a.B + n0 * a.sbn + k0 * a.sbk, a.sbn, a.sbk, rvalidB, kvalid,
+                     a.vecB != 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ah = tc_smem_u32(st), al = ah + A_FLOATS * 4, bh = al + A_FLOATS * 4, bl = bh + B_FLOATS * 4;
+            constexpr uint32_t lbo_a = (TC_BM / 8) * 128, lbo_b = (BN / 8) * 128;
+            uint32_t acc = (kb % TC_FLUSH) > 0 ? 1u : 0u;
+#pragma unroll 1
+            for (int term = 0; term < 3; ++term) {
+                const uint32_t pa = (term == 0) ? al : ah, pb = (term == 1) ? bl : bh;
+#pragma unroll
+                for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                    tc_mma<BN>(tmem, tc_desc(pa + ks * 2 * lbo_a, lbo_a), tc_desc(pb + ks * 2 * lbo_b, lbo_b), acc);
+                    acc = 1u;
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&bars[s]))
+                         : "memory");
+        }
+        // The TMEM accumulator adds with truncation (measured: relative error grows ~7e-9 per unit of K), so every
+        // TC_FLUSH K blocks the partial sum is drained into fp32 registers (round-to-nearest adds) and TMEM restarts at 0.
+        if ((kb + 1) % TC_FLUSH == 0 || kb == nkb - 1) {
+            ok &= tc_wait(tc_smem_u32(&bars[s]), (kb >> 1) & 1);  // this commit covers every MMA issued so far
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < HALF; c0 += 16) {
+                uint32_t r[16];
+                const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(cbase + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) accr[c0 + j] += __uint_as_float(r[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // ordered before the next block's MMAs by its __syncthreads
+        }
+    }
+    if (!ok && a.status) *a.status = 1;
+
+    // ---- epilogue from the register accumulators
+    const int64_t gm = m0 + 32 * (warp & 3) + lane;
+    float* part = a.ws ? a.ws + static_cast<size_t>(blockIdx.z) * a.M * a.N : nullptr;
+    if (gm < a.M) {
+        const float rs = a.rowscale ? a.rowscale[gm] : 1.0f;
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) {
+            const int64_t gn = n0 + cbase + j;
+            if (gn >= a.N) continue;
+            float v = accr[j];
+            if (part) { part[gm * a.N + gn] = v; continue; }
+            if (a.bias) v += a.bias[gn];
+            if (a.rowscale) v *= rs;
+            v = tc_act(v, a.act);
+            if (a.R) v += a.R[gm * a.ldr + gn];
+            float* c = a.C + gm * a.ldc + gn;
+            *c = a.accumulate ? *c + v : v;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN));
+}
+
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t M, int64_t N, float* __restrict__ C,
+                                        int64_t ldc, int accumulate) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= M * N) return;
+    float v = 0.0f;
+    for (int s = 0; s < splits; ++s) v += ws[static_cast<size_t>(s) * M * N + idx];
+    float* c = C + (idx / N) * ldc + idx % N;
+    *c = accumulate ? *c + v : v;
+}
+
+template <int BN>
+static int tc_launch(const TcArgs& a, int splits, cudaStream_t s) {
+    constexpr size_t smem = 2 * (2 * TC_BM * TC_BK + 2 * BN * TC_BK) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return MOLSDE_ERR_CUDA; }
+        configured = true;
+    }
+    dim3 grid(static_cast<unsigned>((a.N + BN - 1) / BN), static_cast<unsigned>((a.M + TC_BM - 1) / TC_BM), splits);
+    tc_gemm_kernel<BN><<<grid, TC_THREADS, smem, s>>>(a);
+    return check_launch("tc_gemm");
+}
+
+}  // namespace molsde
+
+using namespace molsde;
+
+static int tc_bn(int64_t N) { return N <= 32 ? 32 : (N <= 64 || (N % 128 != 0 && N < 256 && (N + 63) / 64 * 64 < (N + 127) / 128 * 128) ? 64 : 128); }
+
+static int tc_splits(int64_t M, int64_t N, int64_t K) {
+    const int bn = tc_bn(N);
+    const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
+    int64_t s = (2 * kNumSMs + tiles - 1) / tiles;   // ~2 waves of CTAs
+    const int64_t maxs = (K + 4 * TC_BK - 1) / (4 * TC_BK);  // >= 4 K blocks per split
+    if (s > maxs) s = maxs;
+    if (s > 512) s = 512;
+    return s < 1 ? 1 : static_cast<int>(s);
+}
+
+extern "C" {
+
+int64_t molsde_tc_gemm_ws_floats(int64_t M, int64_t N, int64_t K) {
+    const int s = tc_splits(M, N, K);
+    return s > 1 ? s * M * N : 0;
+}
+
+/* element A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk]; for each operand one of its two strides must be 1.
+ * split-K (only when ws is given, bias/act/rowscale/R are all unset and K is large relative to the tile count). */
+int molsde_tc_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
+                   const float* bias, int32_t act, const float* rowscale, const float* R, int64_t ldr, float* C, int64_t ldc,
+                   int32_t accumulate, float* ws, int64_t ws_floats, int32_t* status, void* stream) {
+    if (!A || !B || !C || M < 0 || N < 0 || K < 0 || (sam != 1 && sak != 1) || (sbn != 1 && sbk != 1)) return MOLSDE_ERR_INVALID;
+    if (M == 0 || N == 0) return MOLSDE_OK;
+    TcArgs a;
+    a.M = M; a.N = N; a.K = K; a.A = A; a.sam = sam; a.sak = sak; a.B = B; a.sbn = sbn; a.sbk = sbk;
+    a.bias = bias; a.rowscale = rowscale; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc; a.act = act; a.accumulate = accumulate;
+    a.status = status;
+    const bool plain = !bias && !rowscale && !R && act == 0;
+    int splits = plain ? tc_splits(M, N, K) : 1;
+    if (splits > 1 && (!ws || ws_floats < static_cast<int64_t>(splits) * M * N)) splits = 1;
+    int64_t kps = (K + splits - 1) / splits;
+    kps = (kps + TC_BK - 1) / TC_BK * TC_BK;
+    if (kps < TC_BK) kps = TC_BK;
+    splits = static_cast<int>((K + kps - 1) / kps);
+    if (splits < 1) splits = 1;
+    a.k_per_split = kps;
+    a.ws = splits > 1 ? ws : nullptr;
+    // float4 global loads need k-contiguity, 16-byte aligned base and row stride, and split boundaries that keep alignment
+    a.vecA = (sak == 1 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && sam % 4 == 0) ? 1 : 0;
+    a.vecB = (sbk == 1 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && sbn % 4 == 0) ? 1 : 0;
+    cudaStream_t s = as_stream(stream);
+    const int bn = tc_bn(N);
+    int st = bn == 32 ? tc_launch<32>(a, splits, s) : bn == 64 ? tc_launch<64>(a, splits, s) : tc_launch<128>(a, splits, s);
+    if (st != MOLSDE_OK || splits == 1) return st;
+    tc_splitk_reduce_kernel<<<static_cast<unsigned>((M * N + 255) / 256), 256, 0, s>>>(ws, splits, M, N, C, ldc, accumulate);
+    return check_launch("tc_gemm.splitk_reduce");
+}
+
+}  // extern "C"

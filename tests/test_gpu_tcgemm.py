@@ -1,0 +1,83 @@
+"""tcgen05 3xTF32 GEMM (`molsde_tc_gemm`) against an fp64 reference: forward / dx / dW access patterns, ragged sizes,
+strided and misaligned views, epilogue (bias, rowscale, activation, residual), split-K, accumulate."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _tc(M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias=None, act=0, rowscale=None, R=None, accumulate=False, split=True):
+    from moleculesde_b200._abi import check, lib
+    L = lib()
+    n = L.molsde_tc_gemm_ws_floats(M, N, K) if split else 0
+    ws = torch.empty(max(n, 1), dtype=torch.float32, device=C.device)
+    status = torch.zeros(1, dtype=torch.int32, device=C.device)
+    p = lambda t: None if t is None else t.data_ptr()
+    check(L.molsde_tc_gemm(M, N, K, p(A), sam, sak, p(B), sbn, sbk, p(bias), act, p(rowscale), p(R), 0 if R is None else R.stride(0),
+                           p(C), ldc, int(accumulate), p(ws) if n else None, n, p(status), torch.cuda.current_stream().cuda_stream),
+          "tc_gemm")
+    torch.cuda.synchronize()
+    assert int(status) == 0, "mbarrier wait timed out"
+
+
+def _rel(a, b):
+    return float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (5120, 728, 364), (3585, 300, 300), (49000, 128, 51), (777, 119, 728),
+                                   (100, 32, 16), (38424, 32, 300), (1, 1, 1), (130, 65, 33)])
+def test_forward_linear_shapes(M, N, K):
+    dev = _dev()
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(dev)
+    w = torch.randn(N, K, generator=g).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    y = torch.empty(M, N, device=dev)
+    _tc(M, N, K, x, K, 1, w, K, 1, y, N, bias=b)
+    ref = x.double() @ w.double().t() + b.double()
+    assert _rel(y, ref) < 5e-6, _rel(y, ref)
+
+
+def test_epilogue_and_strided_views():
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 1000, 48, 70
+    xbig = torch.randn(M, K + 9, generator=g).to(dev)
+    x = xbig[:, 5:5 + K]                       # misaligned row-strided view
+    w = torch.randn(N, K, generator=g).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    rs = torch.rand(M, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev)
+    out_big = torch.zeros(M, N + 7, device=dev)
+    y = out_big[:, 3:3 + N]
+    _tc(M, N, K, x, x.stride(0), 1, w, K, 1, y, y.stride(0), bias=b, act=4, rowscale=rs, R=res)
+    ref = torch.tanh((x.double() @ w.double().t() + b.double()) * rs.double()[:, None]) + res.double()
+    assert _rel(y, ref) < 5e-6
+    assert float(out_big[:, :3].abs().max()) == 0 and float(out_big[:, 3 + N:].abs().max()) == 0
+
+
+def test_backward_patterns_split_k_and_accumulate():
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    rows, nin, nout = 40000, 51, 128
+    x = torch.randn(rows, nin, generator=g).to(dev)
+    dy = torch.randn(rows, nout, generator=g).to(dev)
+    w = torch.randn(nout, nin, generator=g).to(dev)
+    # dx = dy . W : A = dy [rows, nout], B(n = kin, k = nout) = W[k, n]
+    dx = torch.empty(rows, nin, device=dev)
+    _tc(rows, nin, nout, dy, nout, 1, w, 1, nin, dx, nin)
+    assert _rel(dx, dy.double() @ w.double()) < 5e-6
+    # dW = dy^T . x : A(m = nout, k = row) = dy[k, m], B(n = kin, k = row) = x[k, n]; split-K over the rows, accumulate
+    dw = torch.ones(nout, nin, device=dev)
+    _tc(nout, nin, rows, dy, 1, nout, x, 1, nin, dw, nin, accumulate=True)
+    ref = dy.double().t() @ x.double() + 1.0
+    assert _rel(dw, ref) < 5e-6
+    dw2 = torch.empty(nout, nin, device=dev)
+    _tc(nout, nin, rows, dy, 1, nout, x, 1, nin, dw2, nin, split=False)
+    assert _rel(dw2, ref - 1.0) < 5e-6
