@@ -17,6 +17,7 @@
 //     drained with tcgen05.ld into fp32 registers (warp w owns lanes 32*(w%4).., warps 0-3 / 4-7 split the columns);
 //     the epilogue applies bias / rowscale / activation / residual and stores, or writes a raw split-K partial.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace molsde {
 
@@ -58,30 +59,46 @@ __device__ __forceinline__ float tc_act(float v, int act) {
     }
 }
 
-// Stage one [R x 32] K block of an operand:  element (r, k) = src[r * sr + k * sk], rows >= rvalid / k >= kvalid are zero.
-// Work item = (row r, k-chunk kc of 4): lanes run along r, so the 16-byte smem stores of a warp are contiguous (conflict
-// free) and, for r-contiguous operands, the global loads are coalesced; k-contiguous aligned operands use one float4 load.
+// Staging of one [R x 32] K block of an operand in two phases so that the global-memory latency overlaps the tensor-core
+// work of the previous block:  tc_load (all loads of the block issued back to back into registers)  ->  ...  ->
+// tc_store (split hi/lo, store into the canonical core-matrix layout).   element (r, k) = src[r * sr + k * sk]; rows >=
+// rvalid / k >= kvalid read as zero.  Work item = (row r, k-chunk kc of 4): lanes run along r, so the 16-byte smem stores of
+// a warp are contiguous (conflict free) and, for r-contiguous operands, the global loads are coalesced; k-contiguous
+// aligned operands use one float4 load per item.
 template <int R>
-__device__ __forceinline__ void tc_stage(float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ src, int64_t sr,
-                                         int64_t sk, int rvalid, int kvalid, bool vec4) {
-    for (int item = threadIdx.x; item < R * (TC_BK / 4); item += TC_THREADS) {
+struct TcRegs { float v[R * (TC_BK / 4) / TC_THREADS][4]; };
+
+template <int R>
+__device__ __forceinline__ void tc_load(TcRegs<R>& g, const float* __restrict__ src, int64_t sr, int64_t sk, int rvalid, int kvalid,
+                                        bool vec4) {
+#pragma unroll
+    for (int i = 0; i < R * (TC_BK / 4) / TC_THREADS; ++i) {
+        const int item = threadIdx.x + i * TC_THREADS;
         const int r = item % R, kc = item / R;
-        float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        g.v[i][0] = g.v[i][1] = g.v[i][2] = g.v[i][3] = 0.0f;
         if (r < rvalid) {
             const float* p = src + r * sr + static_cast<int64_t>(kc) * 4 * sk;
             if (vec4 && kc * 4 + 3 < kvalid) {
-                const float4 t = *reinterpret_cast<const float4*>(p);
-                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+                g.v[i][0] = t.x; g.v[i][1] = t.y; g.v[i][2] = t.z; g.v[i][3] = t.w;
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (kc * 4 + j < kvalid) v[j] = p[j * sk];
+                    if (kc * 4 + j < kvalid) g.v[i][j] = __ldg(p + j * sk);
             }
         }
+    }
+}
+template <int R>
+__device__ __forceinline__ void tc_store(const TcRegs<R>& g, float* __restrict__ hi, float* __restrict__ lo) {
+#pragma unroll
+    for (int i = 0; i < R * (TC_BK / 4) / TC_THREADS; ++i) {
+        const int item = threadIdx.x + i * TC_THREADS;
+        const int r = item % R, kc = item / R;
         float4 h4, l4;
-        h4.x = __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u); h4.y = __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u);
-        h4.z = __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u); h4.w = __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u);
-        l4.x = v[0] - h4.x; l4.y = v[1] - h4.y; l4.z = v[2] - h4.z; l4.w = v[3] - h4.w;
+        h4.x = __uint_as_float(__float_as_uint(g.v[i][0]) & 0xFFFFE000u); h4.y = __uint_as_float(__float_as_uint(g.v[i][1]) & 0xFFFFE000u);
+        h4.z = __uint_as_float(__float_as_uint(g.v[i][2]) & 0xFFFFE000u); h4.w = __uint_as_float(__float_as_uint(g.v[i][3]) & 0xFFFFE000u);
+        l4.x = g.v[i][0] - h4.x; l4.y = g.v[i][1] - h4.y; l4.z = g.v[i][2] - h4.z; l4.w = g.v[i][3] - h4.w;
         const int idx = kc * (R / 8) * 32 + (r >> 3) * 32 + (r & 7) * 4;
         *reinterpret_cast<float4*>(hi + idx) = h4;
         *reinterpret_cast<float4*>(lo + idx) = l4;
@@ -97,12 +114,12 @@ struct TcArgs {
     int act, accumulate;
     int64_t k_per_split;   // multiple of TC_BK
     float* ws;             // split-K partials [splits][M][N] or NULL
-    int vecA, vecB;
+    int vecA, vecB, vecC;
     int32_t* status;       // set to 1 if an mbarrier wait timed out (never expected)
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(const TcArgs a) {
     extern __shared__ __align__(128) float tc_smem[];
     constexpr int A_FLOATS = TC_BM * TC_BK, B_FLOATS = BN * TC_BK;
     constexpr int STAGE = 2 * A_FLOATS + 2 * B_FLOATS;  // A hi | A lo | B hi | B lo
@@ -136,15 +153,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs a) 
 
     const int rvalidA = static_cast<int>(min(static_cast<int64_t>(TC_BM), a.M - m0));
     const int rvalidB = static_cast<int>(min(static_cast<int64_t>(BN), a.N - n0));
+    TcRegs<TC_BM> ga;
+    TcRegs<BN> gb;
+    const float* Abase = a.A + m0 * a.sam;
+    const float* Bbase = a.B + n0 * a.sbn;
+    if (nkb > 0) {
+        const int kv0 = static_cast<int>(min(static_cast<int64_t>(TC_BK), kend - kb0));
+        tc_load<TC_BM>(ga, Abase + kb0 * a.sak, a.sam, a.sak, rvalidA, kv0, a.vecA != 0);
+        tc_load<BN>(gb, Bbase + kb0 * a.sbk, a.sbn, a.sbk, rvalidB, kv0, a.vecB != 0);
+    }
     for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb & 1;
         float* st = tc_smem + s * STAGE;
         if (kb >= 2) ok &= tc_wait(tc_smem_u32(&bars[s]), ((kb >> 1) - 1) & 1);  // tensor core finished reading stage s
-        const int64_t k0 = kb0 + static_cast<int64_t>(kb) * TC_BK;
-        const int kvalid = static_cast<int>(min(static_cast<int64_t>(TC_BK), kend - k0));
-        tc_stage<TC_BM>(st, st + A_FLOATS, a.A + m0 * a.sam + k0 * a.sak, a.sam, a.sak, rvalidA, kvalid, a.vecA != 0);
-        tc_stage<BN>(st + 2 * A_FLOATS, st + 2 * A_FLOATS + B_FLOATS, a.B + n0 * a.sbn + k0 * a.sbk, a.sbn, a.sbk, rvalidB, kvalid,
-                     a.vecB != 0);
+        tc_store<TC_BM>(ga, st, st + A_FLOATS);
+        tc_store<BN>(gb, st + 2 * A_FLOATS, st + 2 * A_FLOATS + B_FLOATS);
+        if (kb + 1 < nkb) {  // next block's global loads fly while this block's MMAs run
+            const int64_t k1 = kb0 + static_cast<int64_t>(kb + 1) * TC_BK;
+            const int kv1 = static_cast<int>(min(static_cast<int64_t>(TC_BK), kend - k1));
+            tc_load<TC_BM>(ga, Abase + k1 * a.sak, a.sam, a.sak, rvalidA, kv1, a.vecA != 0);
+            tc_load<BN>(gb, Bbase + k1 * a.sbk, a.sbn, a.sbk, rvalidB, kv1, a.vecB != 0);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -191,7 +220,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs a) 
     // ---- epilogue from the register accumulators
     const int64_t gm = m0 + 32 * (warp & 3) + lane;
     float* part = a.ws ? a.ws + static_cast<size_t>(blockIdx.z) * a.M * a.N : nullptr;
-    if (gm < a.M) {
+    const bool fast = !part && !a.accumulate && !a.R && a.vecC && n0 + cbase + HALF <= a.N;
+    if (gm < a.M && fast) {  // full tile, 16-byte aligned rows: float4 stores
+        const float rs = a.rowscale ? a.rowscale[gm] : 1.0f;
+        float* c = a.C + gm * a.ldc + n0 + cbase;
+#pragma unroll
+        for (int j = 0; j < HALF; j += 4) {
+            float4 o;
+            float* ov = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v = accr[j + q];
+                if (a.bias) v += a.bias[n0 + cbase + j + q];
+                if (a.rowscale) v *= rs;
+                ov[q] = tc_act(v, a.act);
+            }
+            *reinterpret_cast<float4*>(c + j) = o;
+        }
+    } else if (gm < a.M) {
         const float rs = a.rowscale ? a.rowscale[gm] : 1.0f;
 #pragma unroll
         for (int j = 0; j < HALF; ++j) {
@@ -240,7 +286,14 @@ static int tc_launch(const TcArgs& a, int splits, cudaStream_t s) {
 
 using namespace molsde;
 
-static int tc_bn(int64_t N) { return N <= 32 ? 32 : (N <= 64 || (N % 128 != 0 && N < 256 && (N + 63) / 64 * 64 < (N + 127) / 128 * 128) ? 64 : 128); }
+static int tc_bn(int64_t N) {
+    // BN = 64 keeps a CTA at 96 KB of staging (2 CTAs per SM: one CTA's epilogue / prologue overlaps the other's main loop);
+    // MOLSDE_TC_BN=128 selects the wide tile (1 CTA per SM) for experiments
+    static const int forced = getenv("MOLSDE_TC_BN") ? atoi(getenv("MOLSDE_TC_BN")) : 0;
+    if (N <= 32) return 32;
+    if (forced == 128 && N > 64) return 128;
+    return 64;
+}
 
 static int tc_splits(int64_t M, int64_t N, int64_t K) {
     const int bn = tc_bn(N);
@@ -283,6 +336,7 @@ int molsde_tc_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t sam,
     // float4 global loads need k-contiguity, 16-byte aligned base and row stride, and split boundaries that keep alignment
     a.vecA = (sak == 1 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && sam % 4 == 0) ? 1 : 0;
     a.vecB = (sbk == 1 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && sbn % 4 == 0) ? 1 : 0;
+    a.vecC = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0) ? 1 : 0;
     cudaStream_t s = as_stream(stream);
     const int bn = tc_bn(N);
     int st = bn == 32 ? tc_launch<32>(a, splits, s) : bn == 64 ? tc_launch<64>(a, splits, s) : tc_launch<128>(a, splits, s);

@@ -8,6 +8,7 @@ import torch
 from ._abi import check, lib, ptr, require_device, stream_ptr
 
 ACT = {None: 0, "none": 0, "relu": 1, "silu": 2, "ssp": 3, "tanh": 4, "elu": 5}
+TC_MIN_ROWS = 256  # below this the 128-row tensor-core tile is mostly padding
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
@@ -36,8 +37,13 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         assert r2.stride(1) == 1
         ldr = r2.stride(0)
     rs = None if rowscale is None else rowscale.reshape(-1).contiguous()
-    check(lib().molsde_linear(x2.data_ptr(), M, K, ldx, ptr(w), ptr(b), N, y.data_ptr(), y.stride(0), ACT[act],
-                              None if r2 is None else r2.data_ptr(), ldr, ptr(rs), stream_ptr(x)), "linear")
+    if M >= TC_MIN_ROWS:   # tensor-core path (tcgen05, 3xTF32 = fp32-class accuracy); tiny problems stay on the FFMA kernel
+        check(lib().molsde_tc_gemm(M, N, K, x2.data_ptr(), ldx, 1, ptr(w), K, 1, ptr(b), ACT[act], ptr(rs),
+                                   None if r2 is None else r2.data_ptr(), ldr, y.data_ptr(), y.stride(0), 0, None, 0, None,
+                                   stream_ptr(x)), "tc_gemm")
+    else:
+        check(lib().molsde_linear(x2.data_ptr(), M, K, ldx, ptr(w), ptr(b), N, y.data_ptr(), y.stride(0), ACT[act],
+                                  None if r2 is None else r2.data_ptr(), ldr, ptr(rs), stream_ptr(x)), "linear")
     if out is not None:
         return out
     return y if x.dim() == 2 else y.view(*x.shape[:-1], N)

@@ -160,8 +160,8 @@ def tape_2d3d(tp: Tape, model, P: Dict[str, Var], h2d: Var, data, anneal_power: 
     # ---- edge_2D_emb: Linear(600,300) on cat[h[row], h[col]] factored per node, BatchNorm (batch stats) + ReLU, Linear(300,32)
     F = model.emb_dim
     W0, b0 = P["edge_2D_emb.0.weight"], P["edge_2D_emb.0.bias"]
-    U = tp.linear(h2d, _slice_cols(W0, 0, F), b0)
-    V = tp.linear(h2d, _slice_cols(W0, F, 2 * F), None)
+    U = tp.linear(h2d, _slice_cols(W0, 0, F), b0, exact=True)      # feeds BatchNorm + ReLU
+    V = tp.linear(h2d, _slice_cols(W0, F, 2 * F), None, exact=True)
     pre = tp.gather_pair(U, es.src, V, es.tgt)
     bn = model.edge_2D_emb[1]
     if model.training:
@@ -314,7 +314,7 @@ def tape_gin(tp: Tape, model, P: Dict[str, Var], x: torch.Tensor, edge_index: to
         T_bond = _concat_tables(tp, P, [pf + f"bond_encoder.bond_embedding_list.{i}.weight" for i in range(len(BOND_FEATURE_DIMS))])
         pre = tp.gin_aggregate(h, T_bond, ekeys, eidx, csr.rowptr, src, tgt, P[pf + "eps"])
         bn1, bn2 = model.gnns[l].mlp[1], model.batch_norms[l]
-        z = tp.linear(pre, P[pf + "mlp.0.weight"], P[pf + "mlp.0.bias"])
+        z = tp.linear(pre, P[pf + "mlp.0.weight"], P[pf + "mlp.0.bias"], exact=True)   # feeds BatchNorm + ReLU
         last = l == model.num_layer - 1
         if model.training:
             z = tp.batchnorm(z, P[pf + "mlp.1.weight"], P[pf + "mlp.1.bias"], bn1.running_mean, bn1.running_var, bn1.eps,
@@ -322,7 +322,7 @@ def tape_gin(tp: Tape, model, P: Dict[str, Var], x: torch.Tensor, edge_index: to
             bn1.num_batches_tracked += 1
         else:
             z = tp.batchnorm_eval(z, P[pf + "mlp.1.weight"], P[pf + "mlp.1.bias"], bn1.running_mean, bn1.running_var, bn1.eps, relu=True)
-        z = tp.linear(z, P[pf + "mlp.3.weight"], P[pf + "mlp.3.bias"])
+        z = tp.linear(z, P[pf + "mlp.3.weight"], P[pf + "mlp.3.bias"], exact=True)
         if model.training:
             h = tp.batchnorm(z, P[f"batch_norms.{l}.weight"], P[f"batch_norms.{l}.bias"], bn2.running_mean, bn2.running_var,
                              bn2.eps, bn2.momentum, relu=not last)

@@ -15,6 +15,9 @@ import torch
 from ._abi import check, lib, ptr, require_device, stream_ptr
 
 ACT = {"none": 0, "relu": 1, "silu": 2, "ssp": 3, "tanh": 4, "elu": 5}
+import os as _os
+# M*N*K below which a GEMM stays on the FFMA kernels (tensor-core tiles would be mostly padding); MOLSDE_NO_TC=1 disables
+TC_MIN_WORK = (1 << 62) if _os.environ.get("MOLSDE_NO_TC") == "1" else (1 << 20)
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -119,6 +122,15 @@ class Tape:
 
     # ------------------------------------------------------------------ dense ops
     def gemm(self, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, accumulate=False):
+        """C[M,N] (+)= op(A) op(B);  ta: A stored [K][lda];  tb: B stored [N][ldb].  tcgen05 (3xTF32) unless the problem is tiny."""
+        if M * N * K >= TC_MIN_WORK:
+            n = self.L.molsde_tc_gemm_ws_floats(M, N, K)
+            ws = self.empty(n) if n > 0 else None
+            sam, sak = (1, lda) if ta else (lda, 1)
+            sbn, sbk = (ldb, 1) if tb else (1, ldb)
+            self._call(self.L.molsde_tc_gemm, M, N, K, _p(A), sam, sak, _p(B), sbn, sbk, None, 0, None, None, 0, _p(C), ldc,
+                       int(accumulate), _p(ws), n, None, self.s, what="tc_gemm")
+            return
         n = self.L.molsde_gemm_ws_floats(M, N, K)
         ws = self.empty(n) if n > 0 else None
         self._call(self.L.molsde_gemm, ta, tb, M, N, K, _p(A), lda, _p(B), ldb, _p(C), ldc, int(accumulate), _p(ws), n, self.s,
@@ -130,10 +142,13 @@ class Tape:
         self._call(self.L.molsde_colsum, _p(X), M, N, ldx, _p(out), int(accumulate), _p(ws), n, self.s, what="colsum")
 
     def linear(self, x: Var, W: Var, b: Optional[Var], act: str = "none", into: Optional[Var] = None, col0: int = 0,
-               rowscale: Optional[torch.Tensor] = None, x_cols: Optional[tuple] = None) -> Var:
+               rowscale: Optional[torch.Tensor] = None, x_cols: Optional[tuple] = None, exact: bool = False) -> Var:
         """y = act(rowscale * (x W^T + b)); W [out,in] as nn.Linear.  `into`/`col0`: write y into columns
         [col0, col0+out) of the wider buffer Var `into` (a concat without a copy); its gradient is read from there.
-        `x_cols=(a,b)`: the input is the column slice x[:, a:b]; its gradient is accumulated into that slice of x.grad."""
+        `x_cols=(a,b)`: the input is the column slice x[:, a:b]; its gradient is accumulated into that slice of x.grad.
+        `exact`: forward on the fp32 FFMA kernel (round-to-nearest adds) instead of tcgen05 3xTF32 — used where the output
+        feeds BatchNorm + ReLU, whose sign decisions near zero amplify the ~1e-6 tensor-core error into O(1/rows) gradient
+        changes (the backward GEMMs are continuous and stay on the tensor cores)."""
         if x_cols is not None:
             full = x
             x = Var(full.data[:, x_cols[0]:x_cols[1]], False)
@@ -146,12 +161,19 @@ class Tape:
         else:
             y = self.empty(M, Nout)
         pre = y if a == 0 else self.empty(M, Nout)
-        if W.data.is_contiguous():
+        if M * Nout * K >= TC_MIN_WORK and not exact:  # tensor cores; W may be a column slice of a wider weight (ld = its row stride)
+            self._call(self.L.molsde_tc_gemm, M, Nout, K, _p(x.data), _ld(x.data), 1, _p(W.data), _ld(W.data), 1,
+                       _p(b.data) if b is not None else None, 0, _p(rowscale), None, 0, _p(pre), _ld(pre), 0, None, 0, None, self.s,
+                       what="tc_gemm")
+        elif W.data.is_contiguous():
             self._call(self.L.molsde_linear, _p(x.data), M, K, _ld(x.data), _p(W.data), _p(b.data) if b is not None else None, Nout,
                        _p(pre), _ld(pre), 0, None, 0, _p(rowscale), self.s, what="linear")
-        else:  # W is a column slice of a wider weight (split concat input): plain GEMM + bias
+        else:
             assert rowscale is None and pre.is_contiguous()
-            self.gemm(0, 1, M, Nout, K, x.data, _ld(x.data), W.data, _ld(W.data), pre, Nout)
+            n = self.L.molsde_gemm_ws_floats(M, Nout, K)
+            ws = self.empty(n) if n > 0 else None
+            self._call(self.L.molsde_gemm, 0, 1, M, Nout, K, _p(x.data), _ld(x.data), _p(W.data), _ld(W.data), _p(pre), Nout, 0,
+                       _p(ws), n, self.s, what="gemm")
             if b is not None:
                 self.ew(3, pre, b.data, None, 1.0, pre, cols=Nout)
         if a:

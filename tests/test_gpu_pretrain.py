@@ -25,7 +25,7 @@ def _dev():
     return torch.device("cuda:0")
 
 
-def check_grad_summary(got: torch.Tensor, want: dict, what: str, scale_floor: float = 0.0):
+def check_grad_summary(got: torch.Tensor, want: dict, what: str, scale_floor: float = 0.0, tol: float = REL_TOL):
     """Compare a gradient tensor with its fixture summary (norm, sum, strided sample)."""
     f = got.detach().reshape(-1).float().cpu()
     assert f.numel() == want["numel"], what
@@ -34,9 +34,9 @@ def check_grad_summary(got: torch.Tensor, want: dict, what: str, scale_floor: fl
     smp = f[::want["stride"]][:ref.numel()]
     scale = max(float(want["norm"]) / max(f.numel(), 1) ** 0.5, float(ref.abs().max()), scale_floor, 1e-30)
     err = float((smp - ref).abs().max()) / scale
-    assert err <= REL_TOL * 10, f"{what}: sample error {err:.3e} (relative to {scale:.3e})"
+    assert err <= tol * 10, f"{what}: sample error {err:.3e} (relative to {scale:.3e})"
     nerr = abs(float(f.double().norm()) - float(want["norm"])) / max(float(want["norm"]), scale_floor, 1e-30)
-    assert nerr <= REL_TOL, f"{what}: norm {float(f.double().norm()):.6e} vs {float(want['norm']):.6e} ({nerr:.3e})"
+    assert nerr <= tol, f"{what}: norm {float(f.double().norm()):.6e} vs {float(want['norm']):.6e} ({nerr:.3e})"
 
 
 def _draws_2d3d(sec):
@@ -102,7 +102,9 @@ def _check_module_grads(store, mname, sec, skip_zero=()):
             assert float(want["norm"]) <= 1e-5 * gmax and float(got.norm()) <= 1e-5 * gmax, name
             continue
         try:
-            check_grad_summary(got, want, f"{mname}.{name}")
+            # GINConv.eps is a scalar whose gradient <d pre, x> is a heavily cancelling dot product of ~3e4 terms:
+            # its relative error is the summands' 1e-6 times the cancellation factor
+            check_grad_summary(got, want, f"{mname}.{name}", tol=REL_TOL * (10 if name.endswith(".eps") else 1))
         except AssertionError as e:
             bad.append(str(e))
     assert not bad, "\n".join(bad)

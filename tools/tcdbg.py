@@ -2,21 +2,21 @@ import sys, os, torch
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 from test_gpu_tcgemm import _tc, _rel
 dev = torch.device("cuda:0")
-def run_t(nout, nin, rows, split):
+def run_t(nout, nin, rows, split, ldy=None, ldx=None):
     g = torch.Generator().manual_seed(5)
-    x = torch.randn(rows, nin, generator=g).to(dev); dy = torch.randn(rows, nout, generator=g).to(dev)
+    ldy = ldy or nout; ldx = ldx or nin
+    xb = torch.randn(rows, ldx, generator=g).to(dev); dyb = torch.randn(rows, ldy, generator=g).to(dev)
+    x, dy = xb[:, :nin], dyb[:, :nout]
     dw = torch.empty(nout, nin, device=dev)
-    _tc(nout, nin, rows, dy, 1, nout, x, 1, nin, dw, nin, split=split)
+    _tc(nout, nin, rows, dy, 1, ldy, x, 1, ldx, dw, nin, split=split)
     ref = dy.double().t() @ x.double()
-    print("TN", nout, nin, rows, split, "rel %.2e" % _rel(dw, ref))
-def run_n(M, N, K):
+    print("TN", nout, nin, rows, split, ldy, ldx, "rel %.2e" % _rel(dw, ref))
+def run_nn(M, N, K):
     g = torch.Generator().manual_seed(5)
-    x = torch.randn(M, K, generator=g).to(dev); w = torch.randn(N, K, generator=g).to(dev)
+    dy = torch.randn(M, K, generator=g).to(dev); w = torch.randn(K, N, generator=g).to(dev)
     y = torch.empty(M, N, device=dev)
-    _tc(M, N, K, x, K, 1, w, K, 1, y, N, split=False)
-    print("NT", M, N, K, "rel %.2e" % _rel(y, x.double() @ w.double().t()))
-for rows in (512, 4096, 40000):
-    for nin in (51, 64, 128):
-        run_t(128, nin, rows, False)
-run_t(128, 51, 40000, True)
-run_n(128, 51, 40000); run_n(128, 64, 40000); run_n(128, 128, 40000); run_n(128, 52, 40000)
+    _tc(M, N, K, dy, K, 1, w, 1, N, y, N, split=True)
+    print("NN", M, N, K, "rel %.2e" % _rel(y, dy.double() @ w.double()))
+for rows in (109, 113, 1126, 13):
+    run_t(600, 300, rows, True); run_t(300, 600, rows, True); run_t(300, 600, rows, False); run_t(32, 32, rows, True, 512, 64)
+run_nn(109, 300, 600); run_nn(109, 600, 300); run_nn(1126, 32, 300)
