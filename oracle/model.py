@@ -546,3 +546,63 @@ def loss_3d2d(sd, sde_x, sde_adj, h3d: Tensor, z: Tensor, edge_index: Tensor, bo
     lx = torch.mean(lx.reshape(B, -1), dim=-1)
     la = torch.mean(la.reshape(B, -1), dim=-1)
     return torch.mean(lx), torch.mean(la)
+
+
+# ----------------------------------------------------------------------------
+# GIN 2D encoder: Geom3D/models/molecule_gnn_model.py
+# ----------------------------------------------------------------------------
+def gin_forward(sd, x: Tensor, edge_index: Tensor, edge_attr: Tensor, num_layer: int = 5, training: bool = False,
+                stats: Optional[dict] = None) -> Tensor:
+    """GNN.forward, gnn_type="GIN", JK="last", drop_ratio=0 (`molecule_gnn_model.py:160-184`) with GINConv
+    (`:13-32`: out = mlp((1+eps) x + sum_{j->i} relu(x_j + BondEncoder(e)))) and the ogb Atom/BondEncoder (sum of the
+    per-column embeddings).  `training`: BatchNorm batch statistics; updated running stats go into `stats[key]`."""
+    def bn(prefix, v):
+        rm, rv = sd[prefix + ".running_mean"], sd[prefix + ".running_var"]
+        if training:
+            rm, rv = rm.clone(), rv.clone()
+            out = F.batch_norm(v, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], True, 0.1, 1e-5)
+            if stats is not None:
+                stats[prefix + ".running_mean"], stats[prefix + ".running_var"] = rm, rv
+            return out
+        return F.batch_norm(v, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], False, 0.1, 1e-5)
+
+    h = 0
+    for i in range(x.shape[1]):
+        h = h + sd[f"atom_encoder.atom_embedding_list.{i}.weight"][x[:, i]]
+    n = x.size(0)
+    row, col = edge_index
+    for l in range(num_layer):
+        p = f"gnns.{l}"
+        e = 0
+        for i in range(edge_attr.shape[1]):
+            e = e + sd[f"{p}.bond_encoder.bond_embedding_list.{i}.weight"][edge_attr[:, i]]
+        agg = R.propagate(edge_index, F.relu(h[row] + e), n, "add")  # message x_j + edge_attr, aggr add (:28-29)
+        z = (1 + sd[p + ".eps"]) * h + agg
+        z = _lin(sd, p + ".mlp.0", z)
+        z = F.relu(bn(p + ".mlp.1", z))
+        z = _lin(sd, p + ".mlp.3", z)
+        z = bn(f"batch_norms.{l}", z)
+        h = z if l == num_layer - 1 else F.relu(z)  # :176-180 (dropout p = 0)
+    return h
+
+
+# ----------------------------------------------------------------------------
+# one pretraining iteration: examples/pretrain_MoleculeSDE.py:124-152
+# ----------------------------------------------------------------------------
+def pretrain_losses(sds, sde_kind: str, batch, draws: dict, T: float = 0.1, anneal_power: float = 0.0):
+    """Forward of the reference `train()` body with injected draws.  `sds`: {"gnn","schnet","sde2d3d","sde3d2d"} state
+    dicts (tensors may require grad); `draws`: {"cl": (perm1, perm2), "sde2d3d": {noise, time_step, dropout}, "sde3d2d":
+    [randint, randn_adj, randn_x]}.  Returns dict(loss, cl_loss, loss_2d3d, loss_x, loss_adj, h2d, h3d)."""
+    h2d = gin_forward(sds["gnn"], batch.x, batch.edge_index, batch.edge_attr, training=True)
+    _, h3d, _ = schnet_forward(sds["schnet"], batch.x[:, 0], batch.positions, batch.batch, batch.num_graphs)
+    cl, _ = dual_cl(h2d, h3d, T, draws["cl"][0], draws["cl"][1])
+    d23 = draws["sde2d3d"]
+    l23 = loss_2d3d(sds["sde2d3d"], make_sde(sde_kind, 0.2, 1.0, 1000), h2d, batch.extended_edge_index, batch.positions,
+                    batch.batch, batch.num_graphs, d23["noise"], d23["time_step"], 1000, anneal_power, d23["dropout"], True)
+    bmin = 0.1 if sde_kind == "VE" else 0.2
+    d32 = draws["sde3d2d"]
+    lx, la = loss_3d2d(sds["sde3d2d"], make_dense_sde(sde_kind, bmin, 1.0, 1000), make_dense_sde(sde_kind, bmin, 1.0, 1000), h3d,
+                       batch.x[:, 0], batch.edge_index, batch.edge_attr[:, 0], batch.batch, d32[0], d32[1], d32[2], 1000, 119,
+                       anneal_power)
+    loss = cl + l23 + (lx + la) * 0.5
+    return {"loss": loss, "cl_loss": cl, "loss_2d3d": l23, "loss_x": lx, "loss_adj": la, "h2d": h2d, "h3d": h3d}
