@@ -45,6 +45,10 @@ def parse():
     p.add_argument("--cpu-pc-steps", type=int, default=10, help="PC steps of the bounded CPU sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--pretrain-batch", type=int, default=256, help="molecules per GPU of the pretraining step (configs[2])")
+    p.add_argument("--pretrain-steps", type=int, default=50)
+    p.add_argument("--cpu-pretrain-batch", type=int, default=32, help="molecules of the bounded CPU pretraining sample (configs[0])")
+    p.add_argument("--skip-pretrain", action="store_true")
     return p.parse_args()
 
 
@@ -292,6 +296,7 @@ def run_b200(args):
     h2d = rep_h.numel() * 4 + pos0_h.numel() * 4 + ei_h.numel() * 8 + batch_h.numel() * 8
     d2h = out_h.numel() * 4
 
+    plan_E, n_groups = prep.plan.E, int(group_ptr.numel() - 1)
     # ---------------- reduce over ranks (max time) ----------------
     from moleculesde_b200.dist_util import max_over_ranks
     elapsed_ms, pc_ms, e2e_s = max_over_ranks([elapsed_ms, pc_ms, e2e_s], dev)
@@ -299,9 +304,15 @@ def run_b200(args):
     value = world * n_conf / (ms_per_step * 1e-3)
     e2e_value = world * n_conf / e2e_s
 
+    pretrain = None
+    if not args.skip_pretrain:
+        del d, rep, pos0, prep, pm, pm2, d2, rep2, pos2
+        torch.cuda.empty_cache()
+        pretrain = bench_pretrain(args, dev, rank, world)
+
     if rank == 0:
         # roofline of the dominant kernel (sde2d3d_pc_kernel): SURVEY section 8(d) algorithmic work per launch
-        N, Ex = n_atoms, prep.plan.E
+        N, Ex = n_atoms, plan_E
         evals = 2 * args.pc_steps
         k3_bytes = 156 * N + 132 * Ex + 4 * (N + 1) + 266_000
         bytes_launch = evals * k3_bytes + args.pc_steps * 48 * N
@@ -345,14 +356,187 @@ def run_b200(args):
                                      "(156 N + 132 E_x + 4(N+1) + 266k) per eval + 48 N per step; small by construction (fused)"},
             "roofline_fp32": {"bound": "fp32_ffma", "achieved": tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tflops / fp32_peak,
                               "note": "same algorithmic FLOPs against the derived fp32 FFMA peak 148 SM x 128 lanes x 2 x max clock"},
-            "atoms": N, "edges": Ex, "groups": int(group_ptr.numel() - 1),
+            "atoms": N, "edges": Ex, "groups": n_groups,
         }
+        if pretrain is not None:
+            line["pretrain"] = pretrain
         if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
             rate, per_step, sample = cpu_reference_rate(mols, args.repeat, args.cpu_pc_steps, args.pc_steps, model.state_dict())
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# second metric of BASELINE.json: full pretraining step (configs[2]), molecules/s
+# ------------------------------------------------------------------------------------------------
+def build_pretrain_models(seed=1):
+    from moleculesde_b200.gnn import GNN
+    from moleculesde_b200.schnet import SchNet
+    from moleculesde_b200.sde_2d_to_3d import SDEModel2Dto3D_02
+    from moleculesde_b200.sde_3d_to_2d import SDEModel3Dto2D_node_adj_dense
+    torch.manual_seed(seed)
+    gnn = GNN(5, 300, JK="last", drop_ratio=0.0, gnn_type="GIN")
+    sch = SchNet(hidden_channels=300, num_filters=128, num_interactions=6, num_gaussians=51, cutoff=10, readout="mean", node_class=119)
+    m23 = SDEModel2Dto3D_02(emb_dim=300, hidden_dim=32, beta_schedule=None, beta_min=0.2, beta_max=1.0, num_diffusion_timesteps=1000,
+                            SDE_type="VE", use_extend_graph=True)
+    m32 = SDEModel3Dto2D_node_adj_dense(dim3D=300, c_init=2, c_hid=8, c_final=4, num_heads=4, adim=16, nhid=16, num_layers=4,
+                                        emb_dim=300, num_linears=3, beta_min=0.1, beta_max=1.0, num_diffusion_timesteps=1000,
+                                        SDE_type="VE", num_class_X=119, noise_on_one_hot=True)
+    return gnn, sch, m23, m32
+
+
+def cpu_pretrain_rate(batch_mols: int, seed: int):
+    """molecules/s of one reference pretraining iteration (forward, autograd backward, torch.optim.Adam) on the host cores:
+    the oracle restatement (`oracle.model.pretrain_losses`) on `batch_mols` synthetic molecules (BASELINE configs[0])."""
+    from moleculesde_b200.data import Batch, synth_molecules
+    from oracle import model as O
+    from oracle.ref_ops import extend_graph_index
+    torch.set_num_threads(os.cpu_count() or 1)
+    mols = synth_molecules(batch_mols, seed, "pcqm")
+    for m in mols:
+        m.extended_edge_index = extend_graph_index(m.edge_index, m.num_nodes)
+    b = Batch.from_data_list(mols)
+    mods = dict(zip(("gnn", "schnet", "sde2d3d", "sde3d2d"), build_pretrain_models()))
+    sds = {}
+    params = []
+    for k, m in mods.items():
+        trainable = {n for n, p_ in m.named_parameters() if p_.requires_grad}
+        sd = {}
+        for n, v in m.state_dict().items():
+            if n in trainable:
+                v = v.clone().float().requires_grad_(True)
+                params.append(v)
+            sd[n] = v
+        sds[k] = sd
+    opt = torch.optim.Adam(params, lr=1e-4)
+    N, E = b.positions.size(0), b.extended_edge_index.size(1)
+    g = torch.Generator().manual_seed(seed + 1)
+    Bn = b.num_graphs
+    nmax = int(torch.bincount(b.batch).max())
+
+    def draws():
+        return {"cl": (torch.randperm(N, generator=g), torch.randperm(N, generator=g)),
+                "sde2d3d": {"noise": torch.randn(N, 3, generator=g), "time_step": torch.randint(0, 1000, (Bn // 2 + 1,), generator=g),
+                            "dropout": [((torch.rand(E, 8, generator=g) >= 0.1).float(), (torch.rand(N, 32, generator=g) >= 0.1).float())
+                                        for _ in range(4)]},
+                "sde3d2d": [torch.randint(0, 1000, (Bn // 2 + 1,), generator=g), torch.randn(Bn, nmax, nmax, generator=g),
+                            torch.randn(Bn, nmax, 119, generator=g)]}
+
+    def one():
+        out = O.pretrain_losses(sds, "VE", b, draws())
+        opt.zero_grad()
+        out["loss"].backward()
+        opt.step()
+        return float(out["loss"].detach())
+
+    one()  # warm-up
+    t0 = time.perf_counter()
+    one()
+    dt = time.perf_counter() - t0
+    sample = (f"1 full iteration (GIN + SchNet + dual_CL + 2D->3D + 3D->2D forward, autograd backward, Adam) on {batch_mols} synthetic "
+              f"molecules ({N} atoms, {E} extended edges) after 1 warm-up; oracle port (pure-torch restatement), fp32")
+    return batch_mols / dt, dt, sample
+
+
+def bench_pretrain(args, dev, rank, world):
+    """One process per GPU, `--pretrain-batch` molecules each (distinct shards), data-parallel: forward+backward (one CUDA graph
+    replay over the static synthetic batch), NCCL all-reduce of the flat gradient buffer, flat Adam.  Returns the dict stored
+    under "pretrain" in the JSON line (rank 0) or None."""
+    import torch.distributed as dist
+    from moleculesde_b200 import graph as G
+    from moleculesde_b200.data import Batch, synth_molecules
+    from moleculesde_b200.dist_util import max_over_ranks
+    from moleculesde_b200.pretrain import PretrainStep
+    B = args.pretrain_batch
+    ps = PretrainStep(*build_pretrain_models(), dev)
+    if world > 1:  # identical replicas: rank 0's parameters everywhere
+        dist.broadcast(ps.store.flat, src=0)
+    hb = Batch.from_data_list(synth_molecules(B, 7000 + args.seed + rank, "pcqm"))
+    host = {k: getattr(hb, k).pin_memory() for k in ("x", "edge_index", "edge_attr", "positions", "batch")}
+
+    def stage():
+        b = hb.__class__()
+        for k, v in host.items():
+            setattr(b, k, v.to(dev, non_blocking=True))
+        b.num_graphs = hb.num_graphs
+        csr = G.extend_graph(b.edge_index, b.batch, b.num_graphs)
+        b.extended_edge_index = csr.edge_index
+        return b
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    b = stage()
+    out = None
+    for _ in range(max(args.warmup, 3)):
+        out = ps.step(b)
+    torch.cuda.synchronize()
+    launches = ps.launches + 1
+    losses = {k: float(v) for k, v in out.items() if k in ("cl_loss", "loss_2d3d", "loss_x", "loss_adj")}
+    if not all(np.isfinite(list(losses.values()))):
+        raise SystemExit(f"non-finite pretraining loss {losses}")
+    # forward+backward captured once; the all-reduce and Adam stay eager on the same stream
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ps.forward_backward(b)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            ps.forward_backward(b)
+    torch.cuda.synchronize()
+
+    def replay_step():
+        graph.replay()
+        scale = ps.store.all_reduce()
+        ps.store.adam_step(ps.lr, ps.lr_scale, grad_scale=scale)
+
+    for _ in range(3):
+        replay_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.pretrain_steps):
+        replay_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.pretrain_steps
+    # end to end: host batch in (pinned H2D), graph construction + index structures rebuilt, eager step, loss read back
+    e2e_steps = 5
+    loss_h = torch.empty(1).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        b2 = stage()
+        o = ps.step(b2)
+        loss_h.copy_(o["loss_2d3d"].reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    ms, e2e_s = max_over_ranks([ms, e2e_s], dev)
+    if rank != 0:
+        return None
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    res = {"metric": "pretrain molecules/sec", "value": world * B / (ms * 1e-3), "unit": "molecules/s", "ms_per_step": ms,
+           "steps": args.pretrain_steps, "batch_per_gpu": B, "n_gpus": world, "scaling": "weak", "dtype": "f32",
+           "e2e": {"value": world * B / e2e_s, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                   "includes": "pinned-host H2D of the PyG batch, extended/radius graph + CSR/bucket indices, eager forward+backward, "
+                               "all-reduce, Adam, D2H of one loss"},
+           "gpu_launches_per_step": launches, "parameters": ps.store.numel,
+           "atoms": int(hb.positions.size(0)), "bonds": int(hb.edge_index.size(1)), "extended_edges": int(b.extended_edge_index.size(1)),
+           "losses_last_warmup": losses,
+           "config": "BASELINE configs[2]: GIN(5x300) + SchNet(6 interactions) + dual_CL(EBM_node_dot_prod) + SDEModel2Dto3D_02 VE "
+                     "(extended graph) + SDEModel3Dto2D_node_adj_dense VE, forward+backward+Adam(lr 1e-4); forward+backward replayed as "
+                     "one CUDA graph over a static synthetic batch, gradient all-reduce = one NCCL call over the flat fp32 buffer",
+           "gemm": "tcgen05 3xTF32 (fp32-class) for GEMMs with M*N*K >= 2^20, FFMA otherwise"}
+    if not args.no_cpu_baseline and world == 1:
+        rate, dt, sample = cpu_pretrain_rate(args.cpu_pretrain_batch, args.seed)
+        res["cpu_baseline"] = {"value": rate, "unit": "molecules/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+    return res
 
 
 def hot_path_pc_only(model, d, rep, pos0, group_ptr, seed, pc_steps):

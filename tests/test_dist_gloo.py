@@ -57,3 +57,42 @@ def test_shard_groups_balanced():
         assert all(ranges[i][1] == ranges[i + 1][0] for i in range(w - 1))
         sizes = [b - a for a, b in ranges]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _dp_worker(rank, world, port, out):
+    """Data-parallel gradient exchange of the pretraining step: flat buffer layout, one all-reduce (sum), 1/world for Adam."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from moleculesde_b200.pretrain import ParamStore
+    torch.manual_seed(0)  # identical replicas
+    mods = {"a": torch.nn.Linear(5, 3), "b": torch.nn.Sequential(torch.nn.Linear(3, 2), torch.nn.BatchNorm1d(2))}
+    store = ParamStore(mods, torch.device("cpu"))
+    # parameters are views of the flat buffer, state_dict keys unchanged
+    assert mods["a"].weight.data_ptr() == store.flat.data_ptr()
+    assert set(mods["b"].state_dict()) == {"0.weight", "0.bias", "1.weight", "1.bias", "1.running_mean", "1.running_var",
+                                           "1.num_batches_tracked"}
+    store.zero_grad()
+    store.grad_view("a", "weight").fill_(float(rank + 1))      # rank-dependent gradients
+    store.grad_view("b", "1.bias").fill_(10.0 * (rank + 1))
+    scale = store.all_reduce()
+    res = (scale, store.grad_view("a", "weight").clone(), store.grad_view("b", "1.bias").clone(), store.numel)
+    if rank == 0:
+        out.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_flat_gradient_allreduce():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    scale, gw, gb, numel = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert scale == 0.5
+    assert torch.all(gw == 3.0) and torch.all(gb == 30.0)   # sum over ranks; Adam multiplies by 1/world
+    assert numel % 4 == 0 and numel >= 15 + 3 + 6 + 2 + 2 + 2
