@@ -8,7 +8,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(REPO, "moleculesde_b200", "libmolsde_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-cub = os.path.join(tmp, "sde2d3d.sm_100a.cubin")
+cub = os.path.join(tmp, os.environ.get("NCU_CUBIN", "sde2d3d") + ".sm_100a.cubin")
 dis = subprocess.run(["nvdisasm", "-g", "-c", cub], stdout=subprocess.PIPE, text=True).stdout
 cur, inside, off2line = None, False, {}
 for ln in dis.split("\n"):
@@ -24,7 +24,11 @@ for ln in dis.split("\n"):
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[1]; idx = {h: i for i, h in enumerate(hdr)}
-data = rows[2:]
+data = []
+for r in rows[2:]:   # a report with several launches repeats the two header rows: keep the first launch only
+    if not r or not re.match(r"^(0x)?[0-9a-fA-F]+$", r[0]):
+        break
+    data.append(r)
 base = int(data[0][0], 16)
 stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 agg, inst = collections.Counter(), collections.Counter()
