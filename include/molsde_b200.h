@@ -371,6 +371,14 @@ int64_t molsde_tc_gemm_ws_floats(int64_t M, int64_t N, int64_t K);
 int molsde_tc_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
                    const float* bias, int32_t act, const float* rowscale, const float* R, int64_t ldr, float* C, int64_t ldc,
                    int32_t accumulate, float* ws, int64_t ws_floats, int32_t* status, void* stream);
+/* `batch` independent GEMMs of one shape in ONE launch; pointers of batch b are offset by b*bsA / b*bsB / b*bsC / b*bsBias
+ * elements (0 = shared operand).  Instances: the per-channel func_q / func_k / func_v layers of EdgeNetwork_dense
+ * (layers/edge_network_dense.py:105-128) and their dx / dW. */
+int64_t molsde_tc_gemm_batched_ws_floats(int32_t batch, int64_t M, int64_t N, int64_t K);
+int molsde_tc_gemm_batched(int32_t batch, int64_t M, int64_t N, int64_t K, const float* A, int64_t sam, int64_t sak, int64_t bsA,
+                           const float* B, int64_t sbn, int64_t sbk, int64_t bsB, const float* bias, int64_t bsBias, int32_t act,
+                           float* C, int64_t ldc, int64_t bsC, int32_t accumulate, float* ws, int64_t ws_floats, int32_t* status,
+                           void* stream);
 
 /* Backward kernels of the dense 3D->2D score networks (forward: molsde_dense_*):
  *  dense_gcn_bwd: dpre [B*Nm, C*Fo] = dout * act'(out) (its column sum = dbias), dxw [B*Nm, lddx], and (dadj != NULL) the
@@ -393,6 +401,7 @@ int molsde_graph_mse_bwd(const float* a, const float* b, const float* w, int32_t
 /* dst[r,0:cols] (+)= src[r,0:cols] with independent row strides;  out[0] = mean(v[0:n]) */
 int molsde_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int32_t cols, int32_t accumulate, void* stream);
 int molsde_mean(const float* v, int64_t n, float* out, void* stream);
+int molsde_sum_slices(const float* X, int32_t slices, int64_t n, float* out, void* stream);  /* out[i] = sum_s X[s*n+i] */
 int molsde_from_dense_batch(const float* dense, int64_t ldd, const int32_t* node_ptr, const int32_t* node2graph, int64_t N, int32_t Nm,
                             int32_t F, float* x, void* stream);
 

@@ -113,6 +113,8 @@ struct TcArgs {
     float* C; int64_t ldc;
     int act, accumulate;
     int64_t k_per_split;   // multiple of TC_BK
+    int splits, batch;     // grid.z = batch * splits
+    int64_t bsA, bsB, bsC, bsBias, bsRow;  // element offsets between consecutive batches (A, B, C, bias, rowscale/R unused)
     float* ws;             // split-K partials [splits][M][N] or NULL
     int vecA, vecB, vecC;
     int32_t* status;       // set to 1 if an mbarrier wait timed out (never expected)
@@ -127,7 +129,8 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t m0 = static_cast<int64_t>(blockIdx.y) * TC_BM, n0 = static_cast<int64_t>(blockIdx.x) * BN;
-    const int64_t kb0 = static_cast<int64_t>(blockIdx.z) * a.k_per_split;
+    const int bz = static_cast<int>(blockIdx.z) / a.splits, sz = static_cast<int>(blockIdx.z) % a.splits;
+    const int64_t kb0 = static_cast<int64_t>(sz) * a.k_per_split;
     const int64_t kend = min(a.K, kb0 + a.k_per_split);
     const int nkb = static_cast<int>((kend - kb0 + TC_BK - 1) / TC_BK);
 
@@ -155,8 +158,8 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
     const int rvalidB = static_cast<int>(min(static_cast<int64_t>(BN), a.N - n0));
     TcRegs<TC_BM> ga;
     TcRegs<BN> gb;
-    const float* Abase = a.A + m0 * a.sam;
-    const float* Bbase = a.B + n0 * a.sbn;
+    const float* Abase = a.A + bz * a.bsA + m0 * a.sam;
+    const float* Bbase = a.B + bz * a.bsB + n0 * a.sbn;
     if (nkb > 0) {
         const int kv0 = static_cast<int>(min(static_cast<int64_t>(TC_BK), kend - kb0));
         tc_load<TC_BM>(ga, Abase + kb0 * a.sak, a.sam, a.sak, rvalidA, kv0, a.vecA != 0);
@@ -219,11 +222,13 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
 
     // ---- epilogue from the register accumulators
     const int64_t gm = m0 + 32 * (warp & 3) + lane;
-    float* part = a.ws ? a.ws + static_cast<size_t>(blockIdx.z) * a.M * a.N : nullptr;
+    float* part = a.ws ? a.ws + static_cast<size_t>(blockIdx.z) * a.M * a.N : nullptr;   // [batch][split][M][N]
+    float* Cb = a.C + bz * a.bsC;
+    const float* biasb = a.bias ? a.bias + bz * a.bsBias : nullptr;
     const bool fast = !part && !a.accumulate && !a.R && a.vecC && n0 + cbase + HALF <= a.N;
     if (gm < a.M && fast) {  // full tile, 16-byte aligned rows: float4 stores
         const float rs = a.rowscale ? a.rowscale[gm] : 1.0f;
-        float* c = a.C + gm * a.ldc + n0 + cbase;
+        float* c = Cb + gm * a.ldc + n0 + cbase;
 #pragma unroll
         for (int j = 0; j < HALF; j += 4) {
             float4 o;
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float v = accr[j + q];
-                if (a.bias) v += a.bias[n0 + cbase + j + q];
+                if (biasb) v += biasb[n0 + cbase + j + q];
                 if (a.rowscale) v *= rs;
                 ov[q] = tc_act(v, a.act);
             }
@@ -245,11 +250,11 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
             if (gn >= a.N) continue;
             float v = accr[j];
             if (part) { part[gm * a.N + gn] = v; continue; }
-            if (a.bias) v += a.bias[gn];
+            if (biasb) v += biasb[gn];
             if (a.rowscale) v *= rs;
             v = tc_act(v, a.act);
             if (a.R) v += a.R[gm * a.ldr + gn];
-            float* c = a.C + gm * a.ldc + gn;
+            float* c = Cb + gm * a.ldc + gn;
             *c = a.accumulate ? *c + v : v;
         }
     }
@@ -258,13 +263,14 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN));
 }
 
-__global__ void tc_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t M, int64_t N, float* __restrict__ C,
-                                        int64_t ldc, int accumulate) {
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int batch, int64_t M, int64_t N, float* __restrict__ C,
+                                        int64_t ldc, int64_t bsC, int accumulate) {
     const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (idx >= M * N) return;
+    if (idx >= batch * M * N) return;
+    const int64_t b = idx / (M * N), e = idx % (M * N);
     float v = 0.0f;
-    for (int s = 0; s < splits; ++s) v += ws[static_cast<size_t>(s) * M * N + idx];
-    float* c = C + (idx / N) * ldc + idx % N;
+    for (int s = 0; s < splits; ++s) v += ws[(static_cast<size_t>(b) * splits + s) * M * N + e];
+    float* c = C + b * bsC + (e / N) * ldc + e % N;
     *c = accumulate ? *c + v : v;
 }
 
@@ -277,7 +283,7 @@ static int tc_launch(const TcArgs& a, int splits, cudaStream_t s) {
         if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return MOLSDE_ERR_CUDA; }
         configured = true;
     }
-    dim3 grid(static_cast<unsigned>((a.N + BN - 1) / BN), static_cast<unsigned>((a.M + TC_BM - 1) / TC_BM), splits);
+    dim3 grid(static_cast<unsigned>((a.N + BN - 1) / BN), static_cast<unsigned>((a.M + TC_BM - 1) / TC_BM), splits * a.batch);
     tc_gemm_kernel<BN><<<grid, TC_THREADS, smem, s>>>(a);
     return check_launch("tc_gemm");
 }
@@ -295,9 +301,9 @@ static int tc_bn(int64_t N) {
     return 64;
 }
 
-static int tc_splits(int64_t M, int64_t N, int64_t K) {
+static int tc_splits(int64_t M, int64_t N, int64_t K, int batch) {
     const int bn = tc_bn(N);
-    const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
+    const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn) * batch;
     int64_t s = (2 * kNumSMs + tiles - 1) / tiles;   // ~2 waves of CTAs
     const int64_t maxs = (K + 4 * TC_BK - 1) / (4 * TC_BK);  // >= 4 K blocks per split
     if (s > maxs) s = maxs;
@@ -305,11 +311,50 @@ static int tc_splits(int64_t M, int64_t N, int64_t K) {
     return s < 1 ? 1 : static_cast<int>(s);
 }
 
+static int tc_run(int32_t batch, int64_t M, int64_t N, int64_t K, const float* A, int64_t sam, int64_t sak, int64_t bsA, const float* B,
+                  int64_t sbn, int64_t sbk, int64_t bsB, const float* bias, int64_t bsBias, int32_t act, const float* rowscale,
+                  const float* R, int64_t ldr, float* C, int64_t ldc, int64_t bsC, int32_t accumulate, float* ws, int64_t ws_floats,
+                  int32_t* status, void* stream) {
+    if (!A || !B || !C || M < 0 || N < 0 || K < 0 || batch < 1 || (sam != 1 && sak != 1) || (sbn != 1 && sbk != 1)) return MOLSDE_ERR_INVALID;
+    if (batch > 1 && (rowscale || R)) return MOLSDE_ERR_UNSUPPORTED;
+    if (M == 0 || N == 0) return MOLSDE_OK;
+    TcArgs a;
+    a.M = M; a.N = N; a.K = K; a.A = A; a.sam = sam; a.sak = sak; a.B = B; a.sbn = sbn; a.sbk = sbk;
+    a.bias = bias; a.rowscale = rowscale; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc; a.act = act; a.accumulate = accumulate;
+    a.status = status; a.batch = batch; a.bsA = bsA; a.bsB = bsB; a.bsC = bsC; a.bsBias = bsBias; a.bsRow = 0;
+    const bool plain = !bias && !rowscale && !R && act == 0;
+    int splits = plain ? tc_splits(M, N, K, batch) : 1;
+    if (splits > 1 && (!ws || ws_floats < static_cast<int64_t>(splits) * batch * M * N)) splits = 1;
+    int64_t kps = (K + splits - 1) / splits;
+    kps = (kps + TC_BK - 1) / TC_BK * TC_BK;
+    if (kps < TC_BK) kps = TC_BK;
+    splits = static_cast<int>((K + kps - 1) / kps);
+    if (splits < 1) splits = 1;
+    a.k_per_split = kps;
+    a.splits = splits;
+    a.ws = splits > 1 ? ws : nullptr;
+    // float4 global loads need k-contiguity and 16-byte aligned base, row stride and batch stride
+    a.vecA = (sak == 1 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && sam % 4 == 0 && bsA % 4 == 0) ? 1 : 0;
+    a.vecB = (sbk == 1 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && sbn % 4 == 0 && bsB % 4 == 0) ? 1 : 0;
+    a.vecC = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0 && bsC % 4 == 0) ? 1 : 0;
+    cudaStream_t s = as_stream(stream);
+    const int bn = tc_bn(N);
+    int st = bn == 32 ? tc_launch<32>(a, splits, s) : bn == 64 ? tc_launch<64>(a, splits, s) : tc_launch<128>(a, splits, s);
+    if (st != MOLSDE_OK || splits == 1) return st;
+    tc_splitk_reduce_kernel<<<static_cast<unsigned>((batch * M * N + 255) / 256), 256, 0, s>>>(ws, splits, batch, M, N, C, ldc, bsC,
+                                                                                           accumulate);
+    return check_launch("tc_gemm.splitk_reduce");
+}
+
 extern "C" {
 
 int64_t molsde_tc_gemm_ws_floats(int64_t M, int64_t N, int64_t K) {
-    const int s = tc_splits(M, N, K);
+    const int s = tc_splits(M, N, K, 1);
     return s > 1 ? s * M * N : 0;
+}
+int64_t molsde_tc_gemm_batched_ws_floats(int32_t batch, int64_t M, int64_t N, int64_t K) {
+    const int s = tc_splits(M, N, K, batch);
+    return s > 1 ? static_cast<int64_t>(s) * batch * M * N : 0;
 }
 
 /* element A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk]; for each operand one of its two strides must be 1.
@@ -317,32 +362,19 @@ int64_t molsde_tc_gemm_ws_floats(int64_t M, int64_t N, int64_t K) {
 int molsde_tc_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
                    const float* bias, int32_t act, const float* rowscale, const float* R, int64_t ldr, float* C, int64_t ldc,
                    int32_t accumulate, float* ws, int64_t ws_floats, int32_t* status, void* stream) {
-    if (!A || !B || !C || M < 0 || N < 0 || K < 0 || (sam != 1 && sak != 1) || (sbn != 1 && sbk != 1)) return MOLSDE_ERR_INVALID;
-    if (M == 0 || N == 0) return MOLSDE_OK;
-    TcArgs a;
-    a.M = M; a.N = N; a.K = K; a.A = A; a.sam = sam; a.sak = sak; a.B = B; a.sbn = sbn; a.sbk = sbk;
-    a.bias = bias; a.rowscale = rowscale; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc; a.act = act; a.accumulate = accumulate;
-    a.status = status;
-    const bool plain = !bias && !rowscale && !R && act == 0;
-    int splits = plain ? tc_splits(M, N, K) : 1;
-    if (splits > 1 && (!ws || ws_floats < static_cast<int64_t>(splits) * M * N)) splits = 1;
-    int64_t kps = (K + splits - 1) / splits;
-    kps = (kps + TC_BK - 1) / TC_BK * TC_BK;
-    if (kps < TC_BK) kps = TC_BK;
-    splits = static_cast<int>((K + kps - 1) / kps);
-    if (splits < 1) splits = 1;
-    a.k_per_split = kps;
-    a.ws = splits > 1 ? ws : nullptr;
-    // float4 global loads need k-contiguity, 16-byte aligned base and row stride, and split boundaries that keep alignment
-    a.vecA = (sak == 1 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && sam % 4 == 0) ? 1 : 0;
-    a.vecB = (sbk == 1 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && sbn % 4 == 0) ? 1 : 0;
-    a.vecC = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0) ? 1 : 0;
-    cudaStream_t s = as_stream(stream);
-    const int bn = tc_bn(N);
-    int st = bn == 32 ? tc_launch<32>(a, splits, s) : bn == 64 ? tc_launch<64>(a, splits, s) : tc_launch<128>(a, splits, s);
-    if (st != MOLSDE_OK || splits == 1) return st;
-    tc_splitk_reduce_kernel<<<static_cast<unsigned>((M * N + 255) / 256), 256, 0, s>>>(ws, splits, M, N, C, ldc, accumulate);
-    return check_launch("tc_gemm.splitk_reduce");
+    return tc_run(1, M, N, K, A, sam, sak, 0, B, sbn, sbk, 0, bias, 0, act, rowscale, R, ldr, C, ldc, 0, accumulate, ws, ws_floats, status,
+                  stream);
+}
+
+/* `batch` independent GEMMs of the same shape in one launch: operand / output / bias pointers of batch b are offset by
+ * b*bsA, b*bsB, b*bsC, b*bsBias elements (0 = shared).  The per-channel layers of EdgeNetwork_dense (edge_network_dense.py:
+ * 105-128) and their backward are instances. */
+int molsde_tc_gemm_batched(int32_t batch, int64_t M, int64_t N, int64_t K, const float* A, int64_t sam, int64_t sak, int64_t bsA,
+                           const float* B, int64_t sbn, int64_t sbk, int64_t bsB, const float* bias, int64_t bsBias, int32_t act,
+                           float* C, int64_t ldc, int64_t bsC, int32_t accumulate, float* ws, int64_t ws_floats, int32_t* status,
+                           void* stream) {
+    return tc_run(batch, M, N, K, A, sam, sak, bsA, B, sbn, sbk, bsB, bias, bsBias, act, nullptr, nullptr, 0, C, ldc, bsC, accumulate, ws,
+                  ws_floats, status, stream);
 }
 
 }  // extern "C"

@@ -193,6 +193,15 @@ __global__ void __launch_bounds__(256) mean1_kernel(const float* __restrict__ v,
     }
 }
 
+// out[i] = sum_s X[s*n + i] in ascending s
+__global__ void sum_slices_kernel(const float* __restrict__ X, int slices, int64_t n, float* __restrict__ out) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    float v = 0.0f;
+    for (int s = 0; s < slices; ++s) v += X[static_cast<size_t>(s) * n + i];
+    out[i] = v;
+}
+
 }  // namespace molsde
 
 using namespace molsde;
@@ -246,6 +255,12 @@ int molsde_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_
     if (rows == 0) return MOLSDE_OK;
     copy2d_kernel<<<nb(rows * cols), 256, 0, as_stream(stream)>>>(src, lds, dst, ldd, rows, cols, accumulate);
     return check_launch("copy2d");
+}
+int molsde_sum_slices(const float* X, int32_t slices, int64_t n, float* out, void* stream) {
+    if (!X || !out || slices <= 0 || n < 0) return MOLSDE_ERR_INVALID;
+    if (n == 0) return MOLSDE_OK;
+    sum_slices_kernel<<<nb(n), 256, 0, as_stream(stream)>>>(X, slices, n, out);
+    return check_launch("sum_slices");
 }
 int molsde_mean(const float* v, int64_t n, float* out, void* stream) {
     if (!v || !out || n <= 0) return MOLSDE_ERR_INVALID;

@@ -8,6 +8,7 @@ NCCL all-reduce and of the single-launch Adam step.  The per-model `tape_*` func
 from __future__ import annotations
 
 import ctypes
+import re
 from typing import Dict, Optional
 
 import torch
@@ -19,6 +20,41 @@ from .graph import csr_by_target
 from .tape import Index, Tape, Var, _p
 
 
+_CH = re.compile(r"^edge_score_network\.layers\.(\d+)\.attn\.(\d+)\.(func_q|func_k)\.layers\.(\d)\.(weight|bias)$")
+_CV = re.compile(r"^edge_score_network\.layers\.(\d+)\.attn\.(\d+)\.func_v\.(weight|bias)$")
+
+
+def _layout_key(pname: str):
+    """Placement of a parameter in the flat buffer.  The per-channel MLPs of EdgeNetwork_dense (`attn.{c}.func_q/func_k/func_v`,
+    edge_network_dense.py:33-53) are laid out channel after channel per (layer, tensor kind), so that the stack of all
+    channels is ONE contiguous [G, ...] array: the batched GEMM kernels then run all channels of a layer in one launch and
+    their weight gradients land directly in the flat gradient buffer.  Everything else keeps registration order."""
+    m = _CH.match(pname)
+    if m:
+        l, c, qk, li, kind = int(m.group(1)), int(m.group(2)), m.group(3), int(m.group(4)), m.group(5)
+        return (0, l, li * 2 + (kind == "bias"), qk == "func_k", c)
+    m = _CV.match(pname)
+    if m:
+        return (0, int(m.group(1)), 4 + (m.group(3) == "bias"), 0, int(m.group(2)))
+    return (1,)
+
+
+def _stacked(P: Dict[str, "Var"], names, shape) -> Optional["Var"]:
+    """Zero-copy [G, ...] view over parameters that are adjacent in a ParamStore (data and gradient), else None."""
+    vs = [P[n] for n in names]
+    if any(v.grad is None for v in vs):
+        return None
+    for a, b in zip(vs[:-1], vs[1:]):
+        if a.data.data_ptr() + a.data.numel() * 4 != b.data.data_ptr() or a.grad.data_ptr() + a.grad.numel() * 4 != b.grad.data_ptr():
+            return None
+    strides = []
+    acc = 1
+    for d in reversed(shape):
+        strides.insert(0, acc)
+        acc *= d
+    return Var(torch.as_strided(vs[0].data, shape, strides), True, torch.as_strided(vs[0].grad, shape, strides))
+
+
 class ParamStore:
     def __init__(self, modules: Dict[str, nn.Module], device: torch.device):
         self.modules, self.dev = modules, device
@@ -26,7 +62,9 @@ class ParamStore:
         total = 0
         for mname, m in modules.items():
             self.index[mname] = {}
-            for pname, p in m.named_parameters():
+            named = [(pn, p) for pn, p in m.named_parameters() if p.requires_grad]
+            named.sort(key=lambda kv: _layout_key(kv[0]))  # stable: only the per-channel dense layers move (see _layout_key)
+            for pname, p in named:
                 if not p.requires_grad:
                     continue
                 n = p.numel()
@@ -461,6 +499,24 @@ def _edge_network(tp: Tape, P: Dict[str, Var], pf: str, lyr, x: Var, adjc: Var, 
     C, W, Fo, Co = lyr.in_ch, 2 * lyr.attn_dim, lyr.conv_out, lyr.out_ch
     ds = lyr.attn_dim // lyr.num_heads
     rows = B * Nm
+    Fin = x.data.shape[1]
+    qk_names = lambda li, kind: ([f"{pf}attn.{c}.func_q.layers.{li}.{kind}" for c in range(C)] +
+                                 [f"{pf}attn.{c}.func_k.layers.{li}.{kind}" for c in range(C)])
+    W0p = _stacked(P, qk_names(0, "weight"), (2 * C * W, Fin))
+    b0p = _stacked(P, qk_names(0, "bias"), (2 * C * W,))
+    W1p = _stacked(P, qk_names(1, "weight"), (2 * C, W, W))
+    b1p = _stacked(P, qk_names(1, "bias"), (2 * C * W,))
+    Wvp = _stacked(P, [f"{pf}attn.{c}.func_v.weight" for c in range(C)], (C, Fin, Fo))
+    bvp = _stacked(P, [f"{pf}attn.{c}.func_v.bias" for c in range(C)], (C * Fo,))
+    if all(v is not None for v in (W0p, b0p, W1p, b1p, Wvp, bvp)):
+        # all channels of the layer per launch (parameters are stacked in the ParamStore, see _layout_key)
+        h1 = tp.linear(x, W0p, b0p, act="tanh")                     # func_q/func_k layer 0 of every channel: one GEMM
+        qk = tp.grouped_linear(h1, W1p, b1p, 2 * C)                 # layer 1: 2C independent 32x32 GEMMs, one launch
+        xw = tp.grouped_matmul_shared(x, Wvp, C)                    # x @ func_v.weight for every channel
+        V = Var(tp.empty(rows, C * Fo), False)
+        _dense_gcn_all(tp, adjc, C, xw, bvp, Fo, V, B, Nm)
+        return _edge_network_tail(tp, P, pf, lyr, adjc, flags, allc, all_off, B, Nm, last, qk, V, C, W, ds, Fo, Co)
+    # fallback: parameters not stacked (not owned by a ParamStore) -> one launch per channel
     # func_q / func_k (MLP in -> 2a -> 2a, tanh between) for every channel, written side by side: q_0..q_{C-1}, k_0..k_{C-1}
     h1pre = Var(tp.empty(rows, 2 * C * W), False)
     for c in range(C):
@@ -480,6 +536,33 @@ def _edge_network(tp: Tape, P: Dict[str, Var], pf: str, lyr, x: Var, adjc: Var, 
         tp.matmul(x, P[f"{pf}attn.{c}.func_v.weight"], into=xw, col0=c * Fo)
     for c in range(C):
         _dense_gcn(tp, adjc, c, C, xw, c * Fo, P[f"{pf}attn.{c}.func_v.bias"], Fo, V, c * Fo, "none", B, Nm)
+    return _edge_network_tail(tp, P, pf, lyr, adjc, flags, allc, all_off, B, Nm, last, qk, V, C, W, ds, Fo, Co)
+
+
+def _dense_gcn_all(tp: Tape, adjc: Var, C: int, xw: Var, bias: Var, Fo: int, out: Var, B: int, Nm: int) -> None:
+    """All C channels of func_v (dense GCN, no activation) in one launch; bias [C*Fo] stacked."""
+    L, s = tp.L, tp.s
+    a = adjc.data
+    sb, sc = a.stride(0), a.stride(1)
+    tp._call(L.molsde_dense_gcn, ptr(a), sb, sc, B, C, Nm, ptr(xw.data), xw.data.stride(0), ptr(bias.data), Fo, ptr(out.data),
+             out.data.stride(0), 0, 0, s, what="dense_gcn")
+    out.needs = True
+
+    def bwd():
+        dout = tp.grad_of(out)
+        dpre = tp.empty(B * Nm, C * Fo)
+        dxw = tp.empty(B * Nm, C * Fo)
+        da = tp.grad_of(adjc) if adjc.needs else None
+        tp._call(L.molsde_dense_gcn_bwd, ptr(a), sb, sc, B, C, Nm, ptr(xw.data), xw.data.stride(0), Fo, ptr(out.data), ptr(dout),
+                 out.data.stride(0), 0, 0, ptr(dpre), ptr(dxw), C * Fo, _p(da), C * Nm * Nm, 1, s, what="dense_gcn_bwd")
+        if bias.needs:
+            tp.colsum(dpre, B * Nm, C * Fo, C * Fo, bias.grad, accumulate=True)
+        tp.accum(xw, dxw)
+    tp.ops.append(bwd)
+
+
+def _edge_network_tail(tp: Tape, P, pf, lyr, adjc, flags, allc, all_off, B, Nm, last, qk, V, C, W, ds, Fo, Co):
+    L, s = tp.L, tp.s
     # attention scores + [A, adj] concat (recorded AFTER the GCNs: its backward overwrites d adjc, theirs accumulate)
     pair = Var(tp.empty(B * Nm * Nm, 2 * C), True)
     tp._call(L.molsde_dense_attn, qk.data.data_ptr(), qk.data.data_ptr() + 4 * C * W, qk.data.stride(0), W, ds, ptr(adjc.data), B, C, Nm,

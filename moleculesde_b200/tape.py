@@ -522,3 +522,59 @@ class Tape:
                 self.accum(x, g)
             self.ops.append(bwd)
         return out
+
+    # ------------------------------------------------------------------ batched small GEMMs (per-channel layers)
+    def gemm_batched(self, batch, M, N, K, A, sam, sak, bsA, B, sbn, sbk, bsB, C, ldc, bsC, bias=None, bsBias=0, accumulate=False):
+        n = self.L.molsde_tc_gemm_batched_ws_floats(batch, M, N, K)
+        ws = self.empty(n) if n > 0 else None
+        self._call(self.L.molsde_tc_gemm_batched, batch, M, N, K, _p(A), sam, sak, bsA, _p(B), sbn, sbk, bsB, _p(bias), bsBias, 0,
+                   _p(C), ldc, bsC, int(accumulate), _p(ws), n, None, self.s, what="tc_gemm_batched")
+
+    def grouped_linear(self, x: Var, Wp: Var, bp: Var, G: int) -> Var:
+        """G independent nn.Linear layers in one launch: y[:, g*No:(g+1)*No] = x[:, g*Ki:(g+1)*Ki] W_g^T + b_g with the weights
+        stacked as Wp [G, No, Ki] (adjacent parameters of a ParamStore) and bp [G*No]."""
+        rows = x.data.shape[0]
+        _, No, Ki = Wp.data.shape
+        ldx = _ld(x.data)
+        y = self.empty(rows, G * No)
+        self.gemm_batched(G, rows, No, Ki, x.data, ldx, 1, Ki, Wp.data, Ki, 1, No * Ki, y, G * No, No, bias=bp.data, bsBias=No)
+        out = Var(y, True)
+
+        def bwd():
+            if out.grad is None:
+                return
+            dy = out.grad
+            if Wp.needs:   # dW_g = dy_g^T x_g
+                self.gemm_batched(G, No, Ki, rows, dy, 1, G * No, No, x.data, 1, ldx, Ki, Wp.grad, Ki, No * Ki, accumulate=True)
+            if bp.needs:
+                self.colsum(dy, rows, G * No, G * No, bp.grad, accumulate=True)
+            if x.needs:    # dx_g = dy_g W_g
+                dx = self.empty(rows, G * Ki)
+                self.gemm_batched(G, rows, Ki, No, dy, G * No, 1, No, Wp.data, 1, Ki, No * Ki, dx, G * Ki, Ki)
+                self.accum(x, dx)
+        self.ops.append(bwd)
+        return out
+
+    def grouped_matmul_shared(self, x: Var, Wp: Var, G: int) -> Var:
+        """y[:, g*Fo:(g+1)*Fo] = x @ W_g for G weights stacked as Wp [G, Fin, Fo] (NodeNetwork_dense.weight layout), shared x."""
+        rows, Fin = x.data.shape
+        Fo = Wp.data.shape[2]
+        ldx = _ld(x.data)
+        y = self.empty(rows, G * Fo)
+        self.gemm_batched(G, rows, Fo, Fin, x.data, ldx, 1, 0, Wp.data, 1, Fo, Fin * Fo, y, G * Fo, Fo)
+        out = Var(y, True)
+
+        def bwd():
+            if out.grad is None:
+                return
+            dy = out.grad
+            if Wp.needs:   # dW_g [Fin,Fo] = x^T dy_g
+                self.gemm_batched(G, Fin, Fo, rows, x.data, 1, ldx, 0, dy, 1, G * Fo, Fo, Wp.grad, Fo, Fin * Fo, accumulate=True)
+            if x.needs:    # dx = sum_g dy_g W_g^T : per-group products into a scratch, then a fixed-order sum over the groups
+                tmp = self.empty(G, rows, Fin)
+                self.gemm_batched(G, rows, Fin, Fo, dy, G * Fo, 1, Fo, Wp.data, Fo, 1, Fin * Fo, tmp, Fin, rows * Fin)
+                dx = self.empty(rows, Fin)
+                self._call(self.L.molsde_sum_slices, _p(tmp), G, rows * Fin, _p(dx), self.s, what="sum_slices")
+                self.accum(x, dx)
+        self.ops.append(bwd)
+        return out
