@@ -278,3 +278,45 @@ def test_full_pretrain_step(kind, gg, golden, golden_batch):
     # implementations (error up to 2 lr); all others must agree to a small fraction of lr
     assert worst <= 2.1e-4, worst
     assert n_bad <= 0.01 * n_all, (n_bad, n_all)
+
+
+@pytest.mark.parametrize("num_mols,seed", [(1, 3), (3, 4), (17, 5)])
+def test_pretrain_step_small_and_odd_batches(num_mols, seed, golden):
+    """Batch sizes the antithetic time sampling treats specially (B = 1, odd B): losses vs the oracle with the same draws,
+    gradients finite and non-trivial, one Adam step keeps the parameters finite."""
+    import bench
+    from moleculesde_b200 import graph as G
+    from moleculesde_b200.data import Batch, synth_molecules
+    from moleculesde_b200.pretrain import PretrainStep
+    from oracle import model as O
+    from oracle.ref_ops import extend_graph_index
+    from oracle.weights import fill_state_dict
+    dev = _dev()
+    mods = bench.build_pretrain_models()
+    sds = {}
+    for k, m in zip(("gnn", "schnet", "sde2d3d", "sde3d2d"), mods):
+        m.load_state_dict(fill_state_dict(m.state_dict(), 1))
+        sds[k] = {n: v.clone() for n, v in m.state_dict().items()}
+    mols = synth_molecules(num_mols, seed, "pcqm")
+    for m in mols:
+        m.extended_edge_index = extend_graph_index(m.edge_index, m.num_nodes)
+    hb = Batch.from_data_list(mols)
+    N, E, B = hb.positions.size(0), hb.extended_edge_index.size(1), hb.num_graphs
+    nmax = int(torch.bincount(hb.batch).max())
+    g = torch.Generator().manual_seed(seed)
+    draws = {"cl": (torch.randperm(N, generator=g), torch.randperm(N, generator=g)),
+             "sde2d3d": {"noise": torch.randn(N, 3, generator=g), "time_step": torch.randint(0, 1000, (B // 2 + 1,), generator=g),
+                         "dropout": [((torch.rand(E, 8, generator=g) >= 0.1).float(), (torch.rand(N, 32, generator=g) >= 0.1).float())
+                                     for _ in range(4)]},
+             "sde3d2d": [torch.randint(0, 1000, (B // 2 + 1,), generator=g), torch.randn(B, nmax, nmax, generator=g),
+                         torch.randn(B, nmax, 119, generator=g)]}
+    with torch.no_grad():
+        ref = O.pretrain_losses(sds, "VE", hb, draws)
+    ps = PretrainStep(*mods, dev)
+    b = hb.to(dev)
+    b.extended_edge_index = G.extend_graph(b.edge_index, b.batch, b.num_graphs).edge_index
+    out = ps.step(b, draws)
+    for k in ("cl_loss", "loss_2d3d", "loss_x", "loss_adj"):
+        assert abs(float(out[k]) - float(ref[k])) <= REL_TOL * max(abs(float(ref[k])), 1e-3), (k, float(out[k]), float(ref[k]))
+    assert torch.isfinite(ps.store.grad).all() and float(ps.store.grad.abs().max()) > 0
+    assert torch.isfinite(ps.store.flat).all()
