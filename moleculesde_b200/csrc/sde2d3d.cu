@@ -67,8 +67,9 @@ constexpr int SI_TTGT = SI_ROWL + MAXN + 1;  // [MAXT+1] tile target boundaries 
 constexpr int SI_ESRC = SI_TTGT + MAXT + 1;  // [GROUPS][TE]
 constexpr int SI_ETGT = SI_ESRC + GROUPS * TE;  // [GROUPS][TE]
 constexpr int SI_MISC = SI_ETGT + GROUPS * TE;  // [4]  (0: work item, 1: TMEM base address)
-constexpr int SI_BAR = ((S_FLOATS + SI_MISC + 4 + 1) & ~1) - S_FLOATS;  // [2] mbarrier (8-byte aligned)
-constexpr int S_INTS = SI_BAR + 2;
+constexpr int SI_BAR = ((S_FLOATS + SI_MISC + 4 + 1) & ~1) - S_FLOATS;  // [2] mbarrier of the tcgen05 commits (8-byte aligned)
+constexpr int SI_TMABAR = SI_BAR + 2;        // [2] mbarrier of the TMA bulk weight copies (SI_MISC + 2 holds its phase)
+constexpr int S_INTS = SI_TMABAR + 2;
 constexpr size_t SMEM_BYTES = sizeof(float) * S_FLOATS + sizeof(int) * S_INTS;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 static_assert(MOLSDE_P_E0_END <= 3 * 32 * MAXN, "E0 weights are staged in the q/k/v region");
@@ -130,6 +131,29 @@ __device__ __forceinline__ void sincos_reduced(float x, float& s, float& c) {
 __device__ __forceinline__ void stage_async(float* dst, const float* __restrict__ src, int nfloat) {
     for (int i = threadIdx.x * 4; i < nfloat; i += NTHREADS * 4) cp_async16(dst + i, src + i);
     cp_async_commit();
+}
+
+// Weight blocks of a phase (35-68 KB, contiguous in the parameter blob): ONE TMA bulk copy (cp.async.bulk, 1-D) issued by
+// thread 0 and tracked by an mbarrier (complete_tx) instead of ~8 cp.async per thread.  Call with all threads after a
+// __syncthreads() (the destination may still be read by the previous phase before that); returns when the data is
+// visible to every thread.  The barrier's phase bit lives in shared memory (si[SI_MISC + 2]) because the number of copies
+// per score evaluation is odd.
+__device__ __forceinline__ void stage_bulk(int* si, float* dst, const float* __restrict__ src, int nfloat) {
+    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(si + SI_TMABAR));
+    const uint32_t phase = static_cast<uint32_t>(si[SI_MISC + 2]);
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(nfloat) * 4u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of dst before the async-proxy write
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    }
+    uint32_t done = 0;
+    for (int it = 0; it < (1 << 24) && !done; ++it)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) si[SI_MISC + 2] = static_cast<int>(phase ^ 1u);  // read again only after several more barriers
 }
 
 // ---------------------------------------------------------------------------------------
@@ -240,9 +264,8 @@ __device__ __noinline__ void phase_edge_features(const Chunk c, const float* __r
     float* geo = sm + S_L + grp * (TE * 8) + slab * 112;    // [7][16]: d, ci0, ci2, cj0, cj2, psin, pcos
     int* esrc = c.si + SI_ESRC + grp * TE;
     int* etgt = c.si + SI_ETGT + grp * TE;
-    stage_async(W, blob, MOLSDE_P_E0_END);
-    cp_async_wait<0>();
-    __syncthreads();
+    __syncthreads();  // the q/k/v region may still be read by the tail of the previous evaluation
+    stage_bulk(c.si, W, blob, MOLSDE_P_E0_END);
     for (int t = grp; t < c.ntiles; t += GROUPS) {
         const TileInfo ti = tile_info(c, t);
         slot_edges(c, src_g, ti, slab, lane, esrc, etgt);
@@ -684,10 +707,7 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
     const int* rowl = c.si + SI_ROWL;
     const uint32_t bar = smem_u32(c.si + SI_BAR);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    stage_async(Wb, blob + MOLSDE_P_BASIS0 + module * MOLSDE_P_BASIS_SZ, MOLSDE_P_BASIS_SZ);
-    cp_async_wait<0>();
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
+    stage_bulk(c.si, Wb, blob + MOLSDE_P_BASIS0 + module * MOLSDE_P_BASIS_SZ, MOLSDE_P_BASIS_SZ);
 
     // stage 1 of the software pipeline: slot bookkeeping + A operand of tile t + MMA issue (asynchronous)
     auto produce_and_issue = [&](int t) {
@@ -827,9 +847,7 @@ __device__ __noinline__ uint32_t score_eval(const Chunk c, const float* __restri
     __syncthreads();
     for (int module = 0; module < 2; ++module) {
         for (int conv = 0; conv < 2; ++conv) {
-            stage_async(sm + S_WG, blob + MOLSDE_P_GAT0 + (2 * module + conv) * MOLSDE_P_GAT_SZ, MOLSDE_P_GAT_SZ);
-            cp_async_wait<0>();
-            __syncthreads();
+            stage_bulk(c.si, sm + S_WG, blob + MOLSDE_P_GAT0 + (2 * module + conv) * MOLSDE_P_GAT_SZ, MOLSDE_P_GAT_SZ);
             PROF_ADD(1);
             node_qkv(c);
             __syncthreads();
@@ -851,6 +869,8 @@ __device__ __noinline__ uint32_t score_eval(const Chunk c, const float* __restri
 __device__ __forceinline__ uint32_t tmem_setup(int* si) {
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(si + SI_BAR)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(si + SI_TMABAR)));
+        si[SI_MISC + 2] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) {
