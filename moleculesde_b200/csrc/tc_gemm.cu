@@ -23,14 +23,21 @@ namespace molsde {
 
 constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 256;
 constexpr int TC_FLUSH = 8;  // K blocks (of 32) accumulated in TMEM between two drains into registers
-constexpr uint32_t TC_SBO = 128;  // bytes between consecutive 8-row core-matrix groups
+// Shared-memory operand layout (K-major, no swizzle): 8 rows x 16 B core matrices; consecutive K chunks of a row group are
+// TC_LBO = 144 B apart (128 + 16 B of padding: the eight 16-byte stores of a quarter warp that walks along K then hit 32
+// distinct banks), consecutive 8-row groups TC_SBO = 8 * 144 B apart.   byte(r, kc) = (r / 8) * TC_SBO + kc * TC_LBO + (r % 8) * 16
+constexpr uint32_t TC_LBO = 144;
+constexpr uint32_t TC_SBO = (TC_BK / 4) * TC_LBO;
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes) {
-    return static_cast<uint64_t>((saddr & 0x3FFFF) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
+    return static_cast<uint64_t>((saddr & 0x3FFFF) >> 4) | (static_cast<uint64_t>(TC_LBO >> 4) << 16) |
            (static_cast<uint64_t>(TC_SBO >> 4) << 32) | (static_cast<uint64_t>(1) << 46);
 }
+template <int R>
+__host__ __device__ constexpr int tc_tile_floats() { return (R / 8) * static_cast<int>(TC_SBO) / 4; }
+__device__ __forceinline__ int tc_idx(int r, int kc) { return (r >> 3) * static_cast<int>(TC_SBO / 4) + kc * static_cast<int>(TC_LBO / 4) + (r & 7) * 4; }
 template <int N>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
@@ -68,13 +75,21 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 template <int R>
 struct TcRegs { float v[R * (TC_BK / 4) / TC_THREADS][4]; };
 
+// item -> (row, k-chunk): lanes run along K for k-contiguous operands (a warp reads 4 rows x 128 contiguous bytes) and along
+// the rows for row-contiguous operands (each of the 4 scalar loads of a warp is one contiguous 128-byte line)
+template <int R>
+__device__ __forceinline__ void tc_item(int item, bool kfast, int& r, int& kc) {
+    if (kfast) { r = item / (TC_BK / 4); kc = item % (TC_BK / 4); } else { r = item % R; kc = item / R; }
+}
+
 template <int R>
 __device__ __forceinline__ void tc_load(TcRegs<R>& g, const float* __restrict__ src, int64_t sr, int64_t sk, int rvalid, int kvalid,
                                         bool vec4) {
+    const bool kfast = sk == 1;
 #pragma unroll
     for (int i = 0; i < R * (TC_BK / 4) / TC_THREADS; ++i) {
-        const int item = threadIdx.x + i * TC_THREADS;
-        const int r = item % R, kc = item / R;
+        int r, kc;
+        tc_item<R>(threadIdx.x + i * TC_THREADS, kfast, r, kc);
         g.v[i][0] = g.v[i][1] = g.v[i][2] = g.v[i][3] = 0.0f;
         if (r < rvalid) {
             const float* p = src + r * sr + static_cast<int64_t>(kc) * 4 * sk;
@@ -90,16 +105,16 @@ __device__ __forceinline__ void tc_load(TcRegs<R>& g, const float* __restrict__ 
     }
 }
 template <int R>
-__device__ __forceinline__ void tc_store(const TcRegs<R>& g, float* __restrict__ hi, float* __restrict__ lo) {
+__device__ __forceinline__ void tc_store(const TcRegs<R>& g, float* __restrict__ hi, float* __restrict__ lo, bool kfast) {
 #pragma unroll
     for (int i = 0; i < R * (TC_BK / 4) / TC_THREADS; ++i) {
-        const int item = threadIdx.x + i * TC_THREADS;
-        const int r = item % R, kc = item / R;
+        int r, kc;
+        tc_item<R>(threadIdx.x + i * TC_THREADS, kfast, r, kc);
         float4 h4, l4;
         h4.x = __uint_as_float(__float_as_uint(g.v[i][0]) & 0xFFFFE000u); h4.y = __uint_as_float(__float_as_uint(g.v[i][1]) & 0xFFFFE000u);
         h4.z = __uint_as_float(__float_as_uint(g.v[i][2]) & 0xFFFFE000u); h4.w = __uint_as_float(__float_as_uint(g.v[i][3]) & 0xFFFFE000u);
         l4.x = g.v[i][0] - h4.x; l4.y = g.v[i][1] - h4.y; l4.z = g.v[i][2] - h4.z; l4.w = g.v[i][3] - h4.w;
-        const int idx = kc * (R / 8) * 32 + (r >> 3) * 32 + (r & 7) * 4;
+        const int idx = tc_idx(r, kc);
         *reinterpret_cast<float4*>(hi + idx) = h4;
         *reinterpret_cast<float4*>(lo + idx) = l4;
     }
@@ -123,7 +138,7 @@ struct TcArgs {
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(const TcArgs a) {
     extern __shared__ __align__(128) float tc_smem[];
-    constexpr int A_FLOATS = TC_BM * TC_BK, B_FLOATS = BN * TC_BK;
+    constexpr int A_FLOATS = tc_tile_floats<TC_BM>(), B_FLOATS = tc_tile_floats<BN>();
     constexpr int STAGE = 2 * A_FLOATS + 2 * B_FLOATS;  // A hi | A lo | B hi | B lo
     __shared__ uint64_t bars[2];
     __shared__ uint32_t tmem_slot;
@@ -169,8 +184,8 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
         const int s = kb & 1;
         float* st = tc_smem + s * STAGE;
         if (kb >= 2) ok &= tc_wait(tc_smem_u32(&bars[s]), ((kb >> 1) - 1) & 1);  // tensor core finished reading stage s
-        tc_store<TC_BM>(ga, st, st + A_FLOATS);
-        tc_store<BN>(gb, st + 2 * A_FLOATS, st + 2 * A_FLOATS + B_FLOATS);
+        tc_store<TC_BM>(ga, st, st + A_FLOATS, a.sak == 1);
+        tc_store<BN>(gb, st + 2 * A_FLOATS, st + 2 * A_FLOATS + B_FLOATS, a.sbk == 1);
         if (kb + 1 < nkb) {  // next block's global loads fly while this block's MMAs run
             const int64_t k1 = kb0 + static_cast<int64_t>(kb + 1) * TC_BK;
             const int kv1 = static_cast<int>(min(static_cast<int64_t>(TC_BK), kend - k1));
@@ -183,14 +198,13 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t ah = tc_smem_u32(st), al = ah + A_FLOATS * 4, bh = al + A_FLOATS * 4, bl = bh + B_FLOATS * 4;
-            constexpr uint32_t lbo_a = (TC_BM / 8) * 128, lbo_b = (BN / 8) * 128;
             uint32_t acc = (kb % TC_FLUSH) > 0 ? 1u : 0u;
 #pragma unroll 1
             for (int term = 0; term < 3; ++term) {
                 const uint32_t pa = (term == 0) ? al : ah, pb = (term == 1) ? bl : bh;
 #pragma unroll
                 for (int ks = 0; ks < TC_BK / 8; ++ks) {
-                    tc_mma<BN>(tmem, tc_desc(pa + ks * 2 * lbo_a, lbo_a), tc_desc(pb + ks * 2 * lbo_b, lbo_b), acc);
+                    tc_mma<BN>(tmem, tc_desc(pa + ks * 2 * TC_LBO), tc_desc(pb + ks * 2 * TC_LBO), acc);
                     acc = 1u;
                 }
             }
@@ -276,7 +290,7 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ ws, int splits
 
 template <int BN>
 static int tc_launch(const TcArgs& a, int splits, cudaStream_t s) {
-    constexpr size_t smem = 2 * (2 * TC_BM * TC_BK + 2 * BN * TC_BK) * sizeof(float);
+    constexpr size_t smem = 2 * (2 * tc_tile_floats<TC_BM>() + 2 * tc_tile_floats<BN>()) * sizeof(float);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
