@@ -135,11 +135,106 @@ struct TcArgs {
     int32_t* status;       // set to 1 if an mbarrier wait timed out (never expected)
 };
 
-// epilogue from the register accumulators: thread (warp % 4, lane) owns output row m0 + 32*(warp%4) + lane, columns cbase..
 template <int BN>
-__device__ __forceinline__ void tc_epilogue(const TcArgs& a, const float (&accr)[BN / 2], int64_t m0, int64_t n0, int bz, int warp, int lane,
-                                            int cbase) {
-    constexpr int HALF = BN / 2;
+__global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(const TcArgs a) {
+    extern __shared__ __align__(128) float tc_smem[];
+    constexpr int A_FLOATS = tc_tile_floats<TC_BM>(), B_FLOATS = tc_tile_floats<BN>();
+    constexpr int STAGE = 2 * A_FLOATS + 2 * B_FLOATS;  // A hi | A lo | B hi | B lo
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t m0 = static_cast<int64_t>(blockIdx.y) * TC_BM, n0 = static_cast<int64_t>(blockIdx.x) * BN;
+    const int bz = static_cast<int>(blockIdx.z) / a.splits, sz = static_cast<int>(blockIdx.z) % a.splits;
+    const int64_t kb0 = static_cast<int64_t>(sz) * a.k_per_split;
+    const int64_t kend = min(a.K, kb0 + a.k_per_split);
+    const int nkb = static_cast<int>((kend - kb0 + TC_BK - 1) / TC_BK);
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)), "r"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    bool ok = true;
+    constexpr int HALF = BN / 2;                 // warps 0-3 own columns [0, HALF), warps 4-7 own [HALF, BN) of their 32 lanes
+    const int cbase = (warp >> 2) * HALF;
+    float accr[HALF];
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) accr[j] = 0.0f;
+
+    const int rvalidA = static_cast<int>(min(static_cast<int64_t>(TC_BM), a.M - m0));
+    const int rvalidB = static_cast<int>(min(static_cast<int64_t>(BN), a.N - n0));
+    TcRegs<TC_BM> ga;
+    TcRegs<BN> gb;
+    const float* Abase = a.A + bz * a.bsA + m0 * a.sam;
+    const float* Bbase = a.B + bz * a.bsB + n0 * a.sbn;
+    if (nkb > 0) {
+        const int kv0 = static_cast<int>(min(static_cast<int64_t>(TC_BK), kend - kb0));
+        tc_load<TC_BM>(ga, Abase + kb0 * a.sak, a.sam, a.sak, rvalidA, kv0, a.vecA != 0);
+        tc_load<BN>(gb, Bbase + kb0 * a.sbk, a.sbn, a.sbk, rvalidB, kv0, a.vecB != 0);
+    }
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        float* st = tc_smem + s * STAGE;
+        if (kb >= 2) ok &= tc_wait(tc_smem_u32(&bars[s]), ((kb >> 1) - 1) & 1);  // tensor core finished reading stage s
+        tc_store<TC_BM>(ga, st, st + A_FLOATS, a.sak == 1);
+        tc_store<BN>(gb, st + 2 * A_FLOATS, st + 2 * A_FLOATS + B_FLOATS, a.sbk == 1);
+        if (kb + 1 < nkb) {  // next block's global loads fly while this block's MMAs run
+            const int64_t k1 = kb0 + static_cast<int64_t>(kb + 1) * TC_BK;
+            const int kv1 = static_cast<int>(min(static_cast<int64_t>(TC_BK), kend - k1));
+            tc_load<TC_BM>(ga, Abase + k1 * a.sak, a.sam, a.sak, rvalidA, kv1, a.vecA != 0);
+            tc_load<BN>(gb, Bbase + k1 * a.sbk, a.sbn, a.sbk, rvalidB, kv1, a.vecB != 0);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ah = tc_smem_u32(st), al = ah + A_FLOATS * 4, bh = al + A_FLOATS * 4, bl = bh + B_FLOATS * 4;
+            uint32_t acc = (kb % TC_FLUSH) > 0 ? 1u : 0u;
+#pragma unroll 1
+            for (int term = 0; term < 3; ++term) {
+                const uint32_t pa = (term == 0) ? al : ah, pb = (term == 1) ? bl : bh;
+#pragma unroll
+                for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                    tc_mma<BN>(tmem, tc_desc(pa + ks * 2 * TC_LBO), tc_desc(pb + ks * 2 * TC_LBO), acc);
+                    acc = 1u;
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&bars[s]))
+                         : "memory");
+        }
+        // The TMEM accumulator adds with truncation (measured: relative error grows ~7e-9 per unit of K), so every
+        // TC_FLUSH K blocks the partial sum is drained into fp32 registers (round-to-nearest adds) and TMEM restarts at 0.
+        if ((kb + 1) % TC_FLUSH == 0 || kb == nkb - 1) {
+            ok &= tc_wait(tc_smem_u32(&bars[s]), (kb >> 1) & 1);  // this commit covers every MMA issued so far
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < HALF; c0 += 16) {
+                uint32_t r[16];
+                const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(cbase + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) accr[c0 + j] += __uint_as_float(r[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // ordered before the next block's MMAs by its __syncthreads
+        }
+    }
+    if (!ok && a.status) *a.status = 1;
+
+    // ---- epilogue from the register accumulators
     const int64_t gm = m0 + 32 * (warp & 3) + lane;
     float* part = a.ws ? a.ws + static_cast<size_t>(blockIdx.z) * a.M * a.N : nullptr;   // [batch][split][M][N]
     float* Cb = a.C + bz * a.bsC;
@@ -177,131 +272,6 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, const float (&accr)
             *c = a.accumulate ? *c + v : v;
         }
     }
-}
-
-__device__ __forceinline__ void tc_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
-// Warp-specialised main loop: warps 0-7 (256 threads) are PRODUCERS (stage operands, own the register accumulators, run the
-// epilogue); warp 8 lane 0 is the MMA ISSUER.  No CTA-wide barrier inside the K loop — hand-offs go through mbarriers:
-//   full[s]   (256 arrivals)  producers -> issuer : operand stage s is written and fenced to the async proxy
-//   empty[s]  (tcgen05.commit) issuer -> producers : the MMAs that read stage s (and all earlier ones) have completed
-//   drained   (256 arrivals)  producers -> issuer : TMEM has been drained into registers, it may be overwritten (acc = 0)
-// so the issuer can sit in the (blocking) tcgen05.mma issue of block k while the producers already stage block k+1.
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS + 32, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(const TcArgs a) {
-    extern __shared__ __align__(128) float tc_smem[];
-    constexpr int A_FLOATS = tc_tile_floats<TC_BM>(), B_FLOATS = tc_tile_floats<BN>();
-    constexpr int STAGE = 2 * A_FLOATS + 2 * B_FLOATS;  // A hi | A lo | B hi | B lo
-    __shared__ uint64_t bars[5];                         // full[2], empty[2], drained
-    __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t m0 = static_cast<int64_t>(blockIdx.y) * TC_BM, n0 = static_cast<int64_t>(blockIdx.x) * BN;
-    const int bz = static_cast<int>(blockIdx.z) / a.splits, sz = static_cast<int>(blockIdx.z) % a.splits;
-    const int64_t kb0 = static_cast<int64_t>(sz) * a.k_per_split;
-    const int64_t kend = min(a.K, kb0 + a.k_per_split);
-    const int nkb = static_cast<int>((kend - kb0 + TC_BK - 1) / TC_BK);
-    const uint32_t full0 = tc_smem_u32(&bars[0]), empty0 = tc_smem_u32(&bars[2]), drained = tc_smem_u32(&bars[4]);
-
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0), "r"(TC_THREADS));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8), "r"(TC_THREADS));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty0));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty0 + 8));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(drained), "r"(TC_THREADS));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)), "r"(BN));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = tmem_slot;
-    bool ok = true;
-
-    if (warp == TC_THREADS / 32) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb & 1;
-                ok &= tc_wait(full0 + 8 * s, (kb >> 1) & 1);
-                if (kb > 0 && kb % TC_FLUSH == 0) ok &= tc_wait(drained, ((kb / TC_FLUSH) - 1) & 1);  // TMEM may restart at 0
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t ah = tc_smem_u32(tc_smem + s * STAGE), al = ah + A_FLOATS * 4, bh = al + A_FLOATS * 4, bl = bh + B_FLOATS * 4;
-                uint32_t acc = (kb % TC_FLUSH) > 0 ? 1u : 0u;
-#pragma unroll 1
-                for (int term = 0; term < 3; ++term) {
-                    const uint32_t pa = (term == 0) ? al : ah, pb = (term == 1) ? bl : bh;
-#pragma unroll
-                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
-                        tc_mma<BN>(tmem, tc_desc(pa + ks * 2 * TC_LBO), tc_desc(pb + ks * 2 * TC_LBO), acc);
-                        acc = 1u;
-                    }
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s) : "memory");
-            }
-            if (!ok && a.status) *a.status = 1;
-        }
-    } else {
-        // ------------------------------------------------------------------ producers / accumulator owners
-        constexpr int HALF = BN / 2;                 // warps 0-3 own columns [0, HALF), warps 4-7 own [HALF, BN) of their 32 lanes
-        const int cbase = (warp >> 2) * HALF;
-        float accr[HALF];
-#pragma unroll
-        for (int j = 0; j < HALF; ++j) accr[j] = 0.0f;
-        const int rvalidA = static_cast<int>(min(static_cast<int64_t>(TC_BM), a.M - m0));
-        const int rvalidB = static_cast<int>(min(static_cast<int64_t>(BN), a.N - n0));
-        TcRegs<TC_BM> ga;
-        TcRegs<BN> gb;
-        const float* Abase = a.A + bz * a.bsA + m0 * a.sam;
-        const float* Bbase = a.B + bz * a.bsB + n0 * a.sbn;
-        if (nkb > 0) {
-            const int kv0 = static_cast<int>(min(static_cast<int64_t>(TC_BK), kend - kb0));
-            tc_load<TC_BM>(ga, Abase + kb0 * a.sak, a.sam, a.sak, rvalidA, kv0, a.vecA != 0);
-            tc_load<BN>(gb, Bbase + kb0 * a.sbk, a.sbn, a.sbk, rvalidB, kv0, a.vecB != 0);
-        }
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb & 1;
-            float* st = tc_smem + s * STAGE;
-            if (kb >= 2) ok &= tc_wait(empty0 + 8 * s, ((kb >> 1) - 1) & 1);  // tensor core finished reading stage s
-            tc_store<TC_BM>(ga, st, st + A_FLOATS, a.sak == 1);
-            tc_store<BN>(gb, st + 2 * A_FLOATS, st + 2 * A_FLOATS + B_FLOATS, a.sbk == 1);
-            if (kb + 1 < nkb) {  // next block's global loads fly while this block's MMAs run
-                const int64_t k1 = kb0 + static_cast<int64_t>(kb + 1) * TC_BK;
-                const int kv1 = static_cast<int>(min(static_cast<int64_t>(TC_BK), kend - k1));
-                tc_load<TC_BM>(ga, Abase + k1 * a.sak, a.sam, a.sak, rvalidA, kv1, a.vecA != 0);
-                tc_load<BN>(gb, Bbase + k1 * a.sbk, a.sbn, a.sbk, rvalidB, kv1, a.vecB != 0);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
-            tc_arrive(full0 + 8 * s);
-            // The TMEM accumulator adds with truncation (measured: relative error grows ~7e-9 per unit of K), so every
-            // TC_FLUSH K blocks the partial sum is drained into fp32 registers (round-to-nearest adds) and TMEM restarts at 0.
-            if ((kb + 1) % TC_FLUSH == 0 || kb == nkb - 1) {
-                ok &= tc_wait(empty0 + 8 * s, (kb >> 1) & 1);  // this commit covers every MMA issued so far
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (int c0 = 0; c0 < HALF; c0 += 16) {
-                    uint32_t r[16];
-                    const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(cbase + c0);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) accr[c0 + j] += __uint_as_float(r[j]);
-                }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                if (kb != nkb - 1) tc_arrive(drained);
-            }
-        }
-        if (!ok && a.status) *a.status = 1;
-        tc_epilogue<BN>(a, accr, m0, n0, bz, warp, lane, cbase);
-    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN));
@@ -328,7 +298,7 @@ static int tc_launch(const TcArgs& a, int splits, cudaStream_t s) {
         configured = true;
     }
     dim3 grid(static_cast<unsigned>((a.N + BN - 1) / BN), static_cast<unsigned>((a.M + TC_BM - 1) / TC_BM), splits * a.batch);
-    tc_gemm_kernel<BN><<<grid, TC_THREADS + 32, smem, s>>>(a);
+    tc_gemm_kernel<BN><<<grid, TC_THREADS, smem, s>>>(a);
     return check_launch("tc_gemm");
 }
 
