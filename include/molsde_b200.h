@@ -371,6 +371,12 @@ int64_t molsde_tc_gemm_ws_floats(int64_t M, int64_t N, int64_t K);
 int molsde_tc_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
                    const float* bias, int32_t act, const float* rowscale, const float* R, int64_t ldr, float* C, int64_t ldc,
                    int32_t accumulate, float* ws, int64_t ws_floats, int32_t* status, void* stream);
+/* nn.Linear backward, weight and bias gradient in one GEMM: dW[M=out,N=in] (+)= dy^T x (A = dy: sam = 1, sak = ldy; B = x:
+ * sbn = 1, sbk = ldx; K = rows) and db[m] (+)= sum_rows dy[row,m] via an all-ones extra operand row.
+ * Workspace: molsde_tc_gemm_ws_floats(M, N + 1, K). */
+int molsde_tc_gemm_dw_db(int64_t M, int64_t N, int64_t K, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn,
+                         int64_t sbk, float* dW, int64_t ldc, float* db, int32_t accumulate, float* ws, int64_t ws_floats,
+                         int32_t* status, void* stream);
 /* `batch` independent GEMMs of one shape in ONE launch; pointers of batch b are offset by b*bsA / b*bsB / b*bsC / b*bsBias
  * elements (0 = shared operand).  Instances: the per-channel func_q / func_k / func_v layers of EdgeNetwork_dense
  * (layers/edge_network_dense.py:105-128) and their dx / dW. */

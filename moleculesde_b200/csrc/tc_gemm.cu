@@ -84,13 +84,18 @@ __device__ __forceinline__ void tc_item(int item, bool kfast, int& r, int& kc) {
 
 template <int R>
 __device__ __forceinline__ void tc_load(TcRegs<R>& g, const float* __restrict__ src, int64_t sr, int64_t sk, int rvalid, int kvalid,
-                                        bool vec4) {
+                                        bool vec4, int ones_row = -1) {
     const bool kfast = sk == 1;
 #pragma unroll
     for (int i = 0; i < R * (TC_BK / 4) / TC_THREADS; ++i) {
         int r, kc;
         tc_item<R>(threadIdx.x + i * TC_THREADS, kfast, r, kc);
         g.v[i][0] = g.v[i][1] = g.v[i][2] = g.v[i][3] = 0.0f;
+        if (r == ones_row) {  // the extra all-ones B row: output column N = sum_k A(m,k) (bias gradient of a dW GEMM)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g.v[i][j] = (kc * 4 + j < kvalid) ? 1.0f : 0.0f;
+            continue;
+        }
         if (r < rvalid) {
             const float* p = src + r * sr + static_cast<int64_t>(kc) * 4 * sk;
             if (vec4 && kc * 4 + 3 < kvalid) {
@@ -130,7 +135,9 @@ struct TcArgs {
     int64_t k_per_split;   // multiple of TC_BK
     int splits, batch;     // grid.z = batch * splits
     int64_t bsA, bsB, bsC, bsBias, bsRow;  // element offsets between consecutive batches (A, B, C, bias, rowscale/R unused)
-    float* ws;             // split-K partials [splits][M][N] or NULL
+    float* ws;             // split-K partials [batch][splits][M][Nx] or NULL
+    float* colsum;         // optional: colsum[m] (+)= sum_k A(m,k) through an all-ones B row at n == N
+    int64_t Nx;            // N + (colsum ? 1 : 0): number of output columns incl. the ones column
     int vecA, vecB, vecC;
     int32_t* status;       // set to 1 if an mbarrier wait timed out (never expected)
 };
@@ -170,7 +177,8 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
     for (int j = 0; j < HALF; ++j) accr[j] = 0.0f;
 
     const int rvalidA = static_cast<int>(min(static_cast<int64_t>(TC_BM), a.M - m0));
-    const int rvalidB = static_cast<int>(min(static_cast<int64_t>(BN), a.N - n0));
+    const int rvalidB = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(BN), a.N - n0)));
+    const int ones_row = (a.colsum && a.N >= n0 && a.N < n0 + BN) ? static_cast<int>(a.N - n0) : -1;
     TcRegs<TC_BM> ga;
     TcRegs<BN> gb;
     const float* Abase = a.A + bz * a.bsA + m0 * a.sam;
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
     if (nkb > 0) {
         const int kv0 = static_cast<int>(min(static_cast<int64_t>(TC_BK), kend - kb0));
         tc_load<TC_BM>(ga, Abase + kb0 * a.sak, a.sam, a.sak, rvalidA, kv0, a.vecA != 0);
-        tc_load<BN>(gb, Bbase + kb0 * a.sbk, a.sbn, a.sbk, rvalidB, kv0, a.vecB != 0);
+        tc_load<BN>(gb, Bbase + kb0 * a.sbk, a.sbn, a.sbk, rvalidB, kv0, a.vecB != 0, ones_row);
     }
     for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb & 1;
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
             const int64_t k1 = kb0 + static_cast<int64_t>(kb + 1) * TC_BK;
             const int kv1 = static_cast<int>(min(static_cast<int64_t>(TC_BK), kend - k1));
             tc_load<TC_BM>(ga, Abase + k1 * a.sak, a.sam, a.sak, rvalidA, kv1, a.vecA != 0);
-            tc_load<BN>(gb, Bbase + k1 * a.sbk, a.sbn, a.sbk, rvalidB, kv1, a.vecB != 0);
+            tc_load<BN>(gb, Bbase + k1 * a.sbk, a.sbn, a.sbk, rvalidB, kv1, a.vecB != 0, ones_row);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -236,10 +244,10 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
 
     // ---- epilogue from the register accumulators
     const int64_t gm = m0 + 32 * (warp & 3) + lane;
-    float* part = a.ws ? a.ws + static_cast<size_t>(blockIdx.z) * a.M * a.N : nullptr;   // [batch][split][M][N]
+    float* part = a.ws ? a.ws + static_cast<size_t>(blockIdx.z) * a.M * a.Nx : nullptr;   // [batch][split][M][Nx]
     float* Cb = a.C + bz * a.bsC;
     const float* biasb = a.bias ? a.bias + bz * a.bsBias : nullptr;
-    const bool fast = !part && !a.accumulate && !a.R && a.vecC && n0 + cbase + HALF <= a.N;
+    const bool fast = !part && !a.accumulate && !a.R && a.vecC && n0 + cbase + HALF <= a.N;  // (never contains the ones column)
     if (gm < a.M && fast) {  // full tile, 16-byte aligned rows: float4 stores
         const float rs = a.rowscale ? a.rowscale[gm] : 1.0f;
         float* c = Cb + gm * a.ldc + n0 + cbase;
@@ -261,9 +269,10 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
 #pragma unroll
         for (int j = 0; j < HALF; ++j) {
             const int64_t gn = n0 + cbase + j;
-            if (gn >= a.N) continue;
+            if (gn >= a.Nx) continue;
             float v = accr[j];
-            if (part) { part[gm * a.N + gn] = v; continue; }
+            if (part) { part[gm * a.Nx + gn] = v; continue; }
+            if (gn == a.N) { a.colsum[gm] = a.accumulate ? a.colsum[gm] + v : v; continue; }  // the ones column
             if (biasb) v += biasb[gn];
             if (a.rowscale) v *= rs;
             v = tc_act(v, a.act);
@@ -277,15 +286,46 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN));
 }
 
-__global__ void tc_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int batch, int64_t M, int64_t N, float* __restrict__ C,
-                                        int64_t ldc, int64_t bsC, int accumulate) {
-    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (idx >= batch * M * N) return;
-    const int64_t b = idx / (M * N), e = idx % (M * N);
+// C[b] (+)= sum over the split-K partials ws[b][s] in ascending s.  CTA = 32 outputs x 8 split lanes: lane l adds the
+// partials s = l, l+8, ... (fixed order), then the 8 lane sums are added in lane order -> deterministic, and the long
+// dependent chain of the tall-skinny weight gradients (hundreds of splits, a few hundred outputs) is 8x shorter.
+__global__ void __launch_bounds__(256)
+tc_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int batch, int64_t M, int64_t N, int64_t Nreal, float* __restrict__ C,
+                        int64_t ldc, int64_t bsC, int accumulate, float* __restrict__ colsum) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * 32 + tx;
+    const int64_t MN = M * N;
     float v = 0.0f;
-    for (int s = 0; s < splits; ++s) v += ws[(static_cast<size_t>(b) * splits + s) * M * N + e];
-    float* c = C + b * bsC + (e / N) * ldc + e % N;
-    *c = accumulate ? *c + v : v;
+    if (idx < batch * MN) {
+        const int64_t b = idx / MN, e = idx % MN;
+        const float* p = ws + static_cast<size_t>(b) * splits * MN + e;
+        for (int s = sl; s < splits; s += 8) v += p[static_cast<size_t>(s) * MN];
+    }
+    red[sl][tx] = v;
+    __syncthreads();
+    if (sl == 0 && idx < batch * MN) {
+        float t = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += red[q][tx];
+        const int64_t b = idx / MN, e = idx % MN;
+        float* c = (e % N < Nreal) ? C + b * bsC + (e / N) * ldc + e % N : colsum + e / N;   // column Nreal = the ones column
+        *c = accumulate ? *c + t : t;
+    }
+}
+
+// few splits: one thread per output
+__global__ void tc_splitk_reduce_simple_kernel(const float* __restrict__ ws, int splits, int batch, int64_t M, int64_t N, int64_t Nreal,
+                                               float* __restrict__ C, int64_t ldc, int64_t bsC, int accumulate, float* __restrict__ colsum) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t MN = M * N;
+    if (idx >= batch * MN) return;
+    const int64_t b = idx / MN, e = idx % MN;
+    const float* p = ws + static_cast<size_t>(b) * splits * MN + e;
+    float t = 0.0f;
+    for (int s = 0; s < splits; ++s) t += p[static_cast<size_t>(s) * MN];
+    float* c = (e % N < Nreal) ? C + b * bsC + (e / N) * ldc + e % N : colsum + e / N;
+    *c = accumulate ? *c + t : t;
 }
 
 template <int BN>
@@ -297,7 +337,7 @@ static int tc_launch(const TcArgs& a, int splits, cudaStream_t s) {
         if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return MOLSDE_ERR_CUDA; }
         configured = true;
     }
-    dim3 grid(static_cast<unsigned>((a.N + BN - 1) / BN), static_cast<unsigned>((a.M + TC_BM - 1) / TC_BM), splits * a.batch);
+    dim3 grid(static_cast<unsigned>((a.Nx + BN - 1) / BN), static_cast<unsigned>((a.M + TC_BM - 1) / TC_BM), splits * a.batch);
     tc_gemm_kernel<BN><<<grid, TC_THREADS, smem, s>>>(a);
     return check_launch("tc_gemm");
 }
@@ -328,17 +368,19 @@ static int tc_splits(int64_t M, int64_t N, int64_t K, int batch) {
 static int tc_run(int32_t batch, int64_t M, int64_t N, int64_t K, const float* A, int64_t sam, int64_t sak, int64_t bsA, const float* B,
                   int64_t sbn, int64_t sbk, int64_t bsB, const float* bias, int64_t bsBias, int32_t act, const float* rowscale,
                   const float* R, int64_t ldr, float* C, int64_t ldc, int64_t bsC, int32_t accumulate, float* ws, int64_t ws_floats,
-                  int32_t* status, void* stream) {
+                  int32_t* status, void* stream, float* colsum = nullptr) {
+    if (colsum && (batch != 1 || bias || rowscale || R || act != 0)) return MOLSDE_ERR_UNSUPPORTED;
     if (!A || !B || !C || M < 0 || N < 0 || K < 0 || batch < 1 || (sam != 1 && sak != 1) || (sbn != 1 && sbk != 1)) return MOLSDE_ERR_INVALID;
     if (batch > 1 && (rowscale || R)) return MOLSDE_ERR_UNSUPPORTED;
     if (M == 0 || N == 0) return MOLSDE_OK;
     TcArgs a;
     a.M = M; a.N = N; a.K = K; a.A = A; a.sam = sam; a.sak = sak; a.B = B; a.sbn = sbn; a.sbk = sbk;
     a.bias = bias; a.rowscale = rowscale; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc; a.act = act; a.accumulate = accumulate;
+    a.colsum = colsum; a.Nx = N + (colsum ? 1 : 0);
     a.status = status; a.batch = batch; a.bsA = bsA; a.bsB = bsB; a.bsC = bsC; a.bsBias = bsBias; a.bsRow = 0;
     const bool plain = !bias && !rowscale && !R && act == 0;
-    int splits = plain ? tc_splits(M, N, K, batch) : 1;
-    if (splits > 1 && (!ws || ws_floats < static_cast<int64_t>(splits) * batch * M * N)) splits = 1;
+    int splits = plain ? tc_splits(M, a.Nx, K, batch) : 1;
+    if (splits > 1 && (!ws || ws_floats < static_cast<int64_t>(splits) * batch * M * a.Nx)) splits = 1;
     int64_t kps = (K + splits - 1) / splits;
     kps = (kps + TC_BK - 1) / TC_BK * TC_BK;
     if (kps < TC_BK) kps = TC_BK;
@@ -352,11 +394,15 @@ static int tc_run(int32_t batch, int64_t M, int64_t N, int64_t K, const float* A
     a.vecB = (sbk == 1 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && sbn % 4 == 0 && bsB % 4 == 0) ? 1 : 0;
     a.vecC = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0 && bsC % 4 == 0) ? 1 : 0;
     cudaStream_t s = as_stream(stream);
-    const int bn = tc_bn(N);
+    const int bn = tc_bn(a.Nx);
     int st = bn == 32 ? tc_launch<32>(a, splits, s) : bn == 64 ? tc_launch<64>(a, splits, s) : tc_launch<128>(a, splits, s);
     if (st != MOLSDE_OK || splits == 1) return st;
-    tc_splitk_reduce_kernel<<<static_cast<unsigned>((batch * M * N + 255) / 256), 256, 0, s>>>(ws, splits, batch, M, N, C, ldc, bsC,
-                                                                                           accumulate);
+    if (splits <= 16)
+        tc_splitk_reduce_simple_kernel<<<static_cast<unsigned>((batch * M * a.Nx + 255) / 256), 256, 0, s>>>(ws, splits, batch, M, a.Nx, N, C,
+                                                                                                         ldc, bsC, accumulate, colsum);
+    else
+        tc_splitk_reduce_kernel<<<static_cast<unsigned>((batch * M * a.Nx + 31) / 32), 256, 0, s>>>(ws, splits, batch, M, a.Nx, N, C, ldc,
+                                                                                                bsC, accumulate, colsum);
     return check_launch("tc_gemm.splitk_reduce");
 }
 
@@ -378,6 +424,16 @@ int molsde_tc_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t sam,
                    int32_t accumulate, float* ws, int64_t ws_floats, int32_t* status, void* stream) {
     return tc_run(1, M, N, K, A, sam, sak, 0, B, sbn, sbk, 0, bias, 0, act, rowscale, R, ldr, C, ldc, 0, accumulate, ws, ws_floats, status,
                   stream);
+}
+
+/* Weight + bias gradient of nn.Linear in ONE GEMM: dW[M=out, N=in] (+)= dy^T . x and db[m] (+)= sum_rows dy[row, m], the
+ * latter through an all-ones extra operand row (workspace: molsde_tc_gemm_ws_floats(M, N + 1, K)). */
+int molsde_tc_gemm_dw_db(int64_t M, int64_t N, int64_t K, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn,
+                         int64_t sbk, float* dW, int64_t ldc, float* db, int32_t accumulate, float* ws, int64_t ws_floats,
+                         int32_t* status, void* stream) {
+    if (!db) return MOLSDE_ERR_INVALID;
+    return tc_run(1, M, N, K, A, sam, sak, 0, B, sbn, sbk, 0, nullptr, 0, 0, nullptr, nullptr, 0, dW, ldc, 0, accumulate, ws, ws_floats,
+                  status, stream, db);
 }
 
 /* `batch` independent GEMMs of the same shape in one launch: operand / output / bias pointers of batch b are offset by

@@ -18,6 +18,7 @@ ACT = {"none": 0, "relu": 1, "silu": 2, "ssp": 3, "tanh": 4, "elu": 5}
 import os as _os
 # M*N*K below which a GEMM stays on the FFMA kernels (tensor-core tiles would be mostly padding); MOLSDE_NO_TC=1 disables
 TC_MIN_WORK = (1 << 62) if _os.environ.get("MOLSDE_NO_TC") == "1" else (1 << 20)
+FUSED_DB = _os.environ.get("MOLSDE_NO_FUSED_DB") != "1"   # bias gradient through the all-ones row of the dW GEMM
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -200,10 +201,17 @@ class Tape:
                     t = self.empty(M, Nout)
                     self.ew(2, dpre, rowscale, None, 1.0, t, cols=Nout)
                     dpre = t
-                if W.needs:
-                    self.gemm(1, 0, Nout, K, M, dpre, _ld(dpre), x.data, _ld(x.data), W.grad, _ld(W.grad), accumulate=True)
-                if b is not None and b.needs:
-                    self.colsum(dpre, M, Nout, _ld(dpre), b.grad, accumulate=True)
+                if FUSED_DB and W.needs and b is not None and b.needs and Nout * K * M >= TC_MIN_WORK:
+                    # dW and db in one tensor-core GEMM (db = the product with an all-ones extra row)
+                    n = self.L.molsde_tc_gemm_ws_floats(Nout, K + 1, M)
+                    ws = self.empty(n) if n > 0 else None
+                    self._call(self.L.molsde_tc_gemm_dw_db, Nout, K, M, _p(dpre), 1, _ld(dpre), _p(x.data), 1, _ld(x.data), _p(W.grad),
+                               _ld(W.grad), _p(b.grad), 1, _p(ws), n, None, self.s, what="tc_gemm_dw_db")
+                else:
+                    if W.needs:
+                        self.gemm(1, 0, Nout, K, M, dpre, _ld(dpre), x.data, _ld(x.data), W.grad, _ld(W.grad), accumulate=True)
+                    if b is not None and b.needs:
+                        self.colsum(dpre, M, Nout, _ld(dpre), b.grad, accumulate=True)
                 if x_cols is not None:
                     if full.needs:
                         g = self.grad_of(full)[:, x_cols[0]:x_cols[1]]

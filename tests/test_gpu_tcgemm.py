@@ -81,3 +81,23 @@ def test_backward_patterns_split_k_and_accumulate():
     dw2 = torch.empty(nout, nin, device=dev)
     _tc(nout, nin, rows, dy, 1, nout, x, 1, nin, dw2, nin, split=False)
     assert _rel(dw2, ref - 1.0) < 5e-6
+
+
+@pytest.mark.parametrize("rows,nin,nout", [(40000, 51, 128), (5120, 32, 32), (3585, 300, 600), (777, 64, 64), (102400, 16, 16)])
+def test_fused_weight_and_bias_gradient(rows, nin, nout):
+    """dW = dy^T x and db = colsum(dy) from one GEMM (all-ones extra operand row), accumulate semantics, split-K."""
+    from moleculesde_b200._abi import check, lib
+    dev = _dev()
+    L = lib()
+    g = torch.Generator().manual_seed(rows + nin)
+    x = torch.randn(rows, nin, generator=g).to(dev)
+    dy = torch.randn(rows, nout, generator=g).to(dev)
+    dw = torch.full((nout, nin), 2.0, device=dev)
+    db = torch.full((nout,), -1.0, device=dev)
+    n = L.molsde_tc_gemm_ws_floats(nout, nin + 1, rows)
+    ws = torch.empty(max(n, 1), device=dev)
+    check(L.molsde_tc_gemm_dw_db(nout, nin, rows, dy.data_ptr(), 1, nout, x.data_ptr(), 1, nin, dw.data_ptr(), nin, db.data_ptr(), 1,
+                                 ws.data_ptr() if n else None, n, None, torch.cuda.current_stream().cuda_stream), "dw_db")
+    torch.cuda.synchronize()
+    assert _rel(dw, dy.double().t() @ x.double() + 2.0) < 5e-6
+    assert _rel(db, dy.double().sum(0) - 1.0) < 5e-6
