@@ -362,6 +362,13 @@ int molsde_equi_bwd(const float* dgrad, const float* basis, const int32_t* rowpt
 int molsde_dsm_pos_loss_bwd(const float* score, const float* noise, const float* w, const int32_t* node_ptr, const int32_t* node2graph,
                             int64_t N, int32_t B, float upstream, float* dscore, void* stream);
 
+/* Fused row-wise 3-layer MLP  Y = W2 act(W1 act(W0 x + b0) + b1) + b2  (nn.Linear weights [out,in]; K0 <= 32, H1,H2 <= 64,
+ * NO <= 8; act 2 silu / 4 tanh / 5 elu) for the B*Nm^2-row per-pair MLPs of EdgeNetwork_dense (edge_network_dense.py:120-123) and
+ * the final head of EdgeScoreNetwork_dense (invariant_scorenetwork_dense.py:84-86): one pass over HBM instead of three. */
+int molsde_mlp3_rows(const float* X, int64_t rows, int64_t ldx, int32_t K0, const float* W0, const float* b0, int32_t H1,
+                     const float* W1, const float* b1, int32_t H2, const float* W2, const float* b2, int32_t NO, int32_t act,
+                     float* Y, int64_t ldy, void* stream);
+
 /* fp32-accurate GEMM on tcgen05 tensor cores (3xTF32 split, TMEM accumulator; csrc/tc_gemm.cu):
  *   C[M,N] (+)= A . B^T (+ bias[n]) -> * rowscale[m] -> act (+ R),   A(m,k) = A[m*sam + k*sak],  B(n,k) = B[n*sbn + k*sbk]
  * (one stride of each operand must be 1).  nn.Linear forward: A = x (sam = ldx, sak = 1), B = W [out,in] (sbn = in, sbk = 1);

@@ -28,10 +28,15 @@ ACT = {"none": 0, "relu": 1, "silu": 2, "tanh": 4, "elu": 5}
 # thin wrappers of the dense kernels
 # ----------------------------------------------------------------------------------------------
 def _grouped_linear(x2: torch.Tensor, W: torch.Tensor, b: torch.Tensor, G: int, Ki: int, No: int, act: str) -> torch.Tensor:
+    """y[:, g*No:(g+1)*No] = act(x[:, g*Ki:(g+1)*Ki] W_g^T + b_g): G small GEMMs in one batched tensor-core launch."""
     rows = x2.size(0)
     y = torch.empty(rows, G * No, dtype=torch.float32, device=x2.device)
-    check(lib().molsde_grouped_linear(x2.data_ptr(), rows, x2.stride(0), ptr(W), ptr(b), G, Ki, No, ptr(y), G * No, ACT[act],
-                                      stream_ptr(x2)), "grouped_linear")
+    if rows >= 256:
+        check(lib().molsde_tc_gemm_batched(G, rows, No, Ki, x2.data_ptr(), x2.stride(0), 1, Ki, ptr(W), Ki, 1, No * Ki, ptr(b), No,
+                                           ACT[act], ptr(y), G * No, No, 0, None, 0, None, stream_ptr(x2)), "tc_gemm_batched")
+    else:
+        check(lib().molsde_grouped_linear(x2.data_ptr(), rows, x2.stride(0), ptr(W), ptr(b), G, Ki, No, ptr(y), G * No, ACT[act],
+                                          stream_ptr(x2)), "grouped_linear")
     return y
 
 
@@ -43,6 +48,26 @@ def _dense_gcn(adjc: torch.Tensor, C: int, xw: torch.Tensor, bias: torch.Tensor,
     sc = adjc.stride(1) if adjc.dim() == 4 else 0
     check(lib().molsde_dense_gcn(adjc.data_ptr(), sb, sc, B, C, Nm, xw.data_ptr(), xw.stride(0), ptr(bias), Fo, out.data_ptr(),
                                  out.stride(0), out_off, ACT[act], stream_ptr(xw)), "dense_gcn")
+
+
+def _mlp_rows(x2: torch.Tensor, mlp: "MultiLayerPerceptron", act: str) -> torch.Tensor:
+    """MultiLayerPerceptron over very many rows.  3 layers with narrow widths run as ONE fused kernel (`molsde_mlp3_rows`);
+    anything else layer by layer."""
+    layers = list(mlp.layers)
+    if len(layers) == 3 and layers[0].in_features <= 32 and layers[0].out_features <= 64 and layers[1].out_features <= 64 \
+            and layers[2].out_features <= 8 and x2.stride(1) == 1:
+        rows = x2.size(0)
+        w = [l.weight.detach().float().contiguous() for l in layers]
+        b = [l.bias.detach().float().contiguous() for l in layers]
+        y = torch.empty(rows, w[2].size(0), dtype=torch.float32, device=x2.device)
+        check(lib().molsde_mlp3_rows(x2.data_ptr(), rows, x2.stride(0), w[0].size(1), ptr(w[0]), ptr(b[0]), w[0].size(0), ptr(w[1]),
+                                     ptr(b[1]), w[1].size(0), ptr(w[2]), ptr(b[2]), w[2].size(0), ACT[act], ptr(y), y.stride(0),
+                                     stream_ptr(x2)), "mlp3_rows")
+        return y
+    m = x2
+    for i, lyr in enumerate(layers):
+        m = linear(m, lyr.weight, lyr.bias, act=act if i < len(layers) - 1 else None)
+    return m
 
 
 def node_flags(adj: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
@@ -174,10 +199,7 @@ class EdgeNetwork_dense(nn.Module):
               "dense_attn")                                                                # tanh attention + [A, adj] concat
         mc = self.multi_channel.layers
         xo = linear(linear(V, mc[0].weight, mc[0].bias, act="elu"), mc[1].weight, mc[1].bias, act="tanh", rowscale=flags)
-        m = pair.view(-1, 2 * C)
-        n_l = len(self.mlp.layers)
-        for i, lyr in enumerate(self.mlp.layers):
-            m = linear(m, lyr.weight, lyr.bias, act="elu" if i < n_l - 1 else None)
+        m = _mlp_rows(pair.view(-1, 2 * C), self.mlp, "elu")
         adj_out = torch.empty(B, self.out_ch, Nm, Nm, dtype=torch.float32, device=adjc.device)
         if allc is None:
             allc, all_off = torch.empty(B, Nm, Nm, self.out_ch, dtype=torch.float32, device=adjc.device), 0
@@ -220,10 +242,7 @@ class EdgeScoreNetwork_dense(nn.Module):
         for lyr in self.layers:
             x, adjc = lyr(x, adjc, flags, allc, off)
             off += lyr.out_ch
-        m = allc.view(-1, self.fdim)
-        n_l = len(self.final.layers)
-        for i, lyr in enumerate(self.final.layers):
-            m = linear(m, lyr.weight, lyr.bias, act="silu" if i < n_l - 1 else None)
+        m = _mlp_rows(allc.view(-1, self.fdim), self.final, "silu")
         out = torch.empty(B, Nm, Nm, dtype=torch.float32, device=adj.device)
         check(lib().molsde_dense_edge_final(ptr(m), ptr(flags), None if scale is None else ptr(scale.contiguous()), B, Nm, ptr(out), s),
               "edge_final")
