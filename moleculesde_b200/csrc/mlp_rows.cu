@@ -10,11 +10,18 @@ namespace molsde {
 
 constexpr int MR_WARPS = 8, MR_LDA = 24;  // stripe: [k][24] floats, rows 0..15 (24 = conflict-free for the A fragment loads)
 
+// Activations on the SFU fast path (the epilogues evaluate 64 of them per lane and stripe, which would otherwise outweigh the
+// MMAs): __expf / __fdividef are accurate to ~2 ulp; expm1 switches to its 4-term series for |v| < 0.1 so that small
+// arguments keep full relative accuracy.  Parity with the reference stays within the 1e-4 bar (tests/test_gpu_dense.py).
 __device__ __forceinline__ float mr_act(float v, int act) {
     switch (act) {
-        case 2: return silu_f(v);
-        case 4: return tanhf(v);
-        case 5: return v > 0.0f ? v : expm1f(v);
+        case 2: return __fdividef(v, 1.0f + __expf(-v));
+        case 4: { const float e = __expf(-2.0f * fabsf(v)); return copysignf(__fdividef(1.0f - e, 1.0f + e), v); }
+        case 5: {
+            const float series = v * fmaf(v, fmaf(v, fmaf(v, 1.0f / 24.0f, 1.0f / 6.0f), 0.5f), 1.0f);
+            const float em1 = v > -0.1f ? series : __expf(v) - 1.0f;
+            return v > 0.0f ? v : em1;
+        }
         default: return v;
     }
 }
@@ -54,10 +61,18 @@ mlp3_rows_kernel(const float* __restrict__ X, int64_t rows, int64_t ldx, int K0,
     const int64_t nstripes = (rows + 15) / 16;
     for (int64_t sidx = static_cast<int64_t>(blockIdx.x) * MR_WARPS + warp; sidx < nstripes; sidx += static_cast<int64_t>(gridDim.x) * MR_WARPS) {
         const int64_t r0 = sidx * 16;
-        // stage the stripe transposed: A[k][row]  (lanes along k: coalesced row reads)
-        for (int r = 0; r < 16; ++r) {
-            const int64_t gr = r0 + r;
-            if (lane < K0p) A[lane * MR_LDA + r] = (gr < rows && lane < K0) ? X[gr * ldx + lane] : 0.0f;
+        // stage the stripe transposed: A[k][row]  (lanes along k: coalesced row reads; all 16 loads in flight before the stores)
+        {
+            float v[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int64_t gr = r0 + r;
+                v[r] = (gr < rows && lane < K0) ? __ldg(X + gr * ldx + lane) : 0.0f;
+            }
+            if (lane < K0p) {
+#pragma unroll
+                for (int r = 0; r < 16; r += 4) *reinterpret_cast<float4*>(A + lane * MR_LDA + r) = make_float4(v[r], v[r + 1], v[r + 2], v[r + 3]);
+            }
         }
         __syncwarp();
         float acc[NB][4];
