@@ -41,7 +41,7 @@ constexpr int TILE_FLOATS = 32 * LDA;         // one [32][136] per-edge attribut
 constexpr int FRAME_FLOATS = 9 * TE;          // per-edge SE(3) frame (diff, cross, vertical) cached by E0 for the basis phases
 constexpr int SCR_TILE = TILE_FLOATS + FRAME_FLOATS;  // per-tile scratch record: edge_attr [32][136] | frame [9][128]
 constexpr int LDM = 33;                       // padded row of the slot-major message tile [TE][33]
-constexpr int LD32 = MOLSDE_LD32, LD96 = MOLSDE_LD96, LD128 = MOLSDE_LD128;
+constexpr int LD32 = MOLSDE_LD32, LD96 = MOLSDE_LD96;
 constexpr float EPS = 1e-6f;                  // SDE_model_2D_to_3D.py:10
 constexpr float LN_EPS = 1e-5f;
 
@@ -766,8 +766,6 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
     if (c.ntiles > 0) produce_and_issue(0);
     for (int t = 0; t < c.ntiles; ++t) {
         const TileInfo ti = tile_info(c, t);
-        const int* esrc = c.si + SI_ESRC + (t & 1) * TE;
-        const int* etgt = c.si + SI_ETGT + (t & 1) * TE;
         ok &= mbar_wait(bar, phase);  // MMAs of tile t complete: accumulator (t&1) ready, A buffer free
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1088,7 +1086,7 @@ constexpr int E2D_THREADS = 256;
 __global__ void __launch_bounds__(E2D_THREADS, 1)
 edge2d_emb_kernel(molsde_plan plan, const float* __restrict__ uv, const float* __restrict__ w3t,
                   const float* __restrict__ b3, float* __restrict__ e2d_tiles) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* A = smem;             // [64][TE]
     float* W = smem + 64 * TE;   // [320][32] (rows >= 300 zero)
     __shared__ int s_src[TE], s_tgt[TE];
