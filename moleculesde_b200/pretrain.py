@@ -90,10 +90,12 @@ class ParamStore:
                 assert params[pname].data.data_ptr() == self.flat[off:off + n].data_ptr(), "module.to() re-allocated a parameter"
 
     def vars(self, mname: str) -> Dict[str, Var]:
-        out = {}
-        for pname, (off, n, shape) in self.index[mname].items():
-            out[pname] = Var(self.flat[off:off + n].view(shape), True, self.grad[off:off + n].view(shape))
-        return out
+        """name -> Var(parameter view, gradient view); the views never change, so the dict is built once."""
+        cache = self.__dict__.setdefault("_vars", {})
+        if mname not in cache:
+            cache[mname] = {pname: Var(self.flat[off:off + n].view(shape), True, self.grad[off:off + n].view(shape))
+                            for pname, (off, n, shape) in self.index[mname].items()}
+        return cache[mname]
 
     def grad_view(self, mname: str, pname: str) -> torch.Tensor:
         off, n, shape = self.index[mname][pname]

@@ -76,11 +76,12 @@ class Tape:
         self.ops: List[Callable[[], None]] = []
         self.L = lib()
         self.launches = 0
+        self._s = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0  # one stream per tape
 
     # ------------------------------------------------------------------ helpers
     @property
     def s(self) -> int:
-        return torch.cuda.current_stream(self.dev).cuda_stream
+        return self._s
 
     def empty(self, *shape, dtype=torch.float32) -> torch.Tensor:
         return torch.empty(*shape, dtype=dtype, device=self.dev)
