@@ -179,22 +179,22 @@ __global__ void seg_gather_sum_kernel(const float* __restrict__ X, const int32_t
 }
 
 // the same for FEW, LONG segments (embedding-table gradients: ~100 rows of the table, thousands of lookups each):
-// CTA (32 columns x 8 row lanes) per (segment, column block), fixed-order tree over the 8 lanes
-__global__ void __launch_bounds__(256)
+// CTA (32 columns x 32 row lanes) per (segment, column block), fixed-order sum over the 32 lanes
+__global__ void __launch_bounds__(1024)
 seg_gather_sum_wide_kernel(const float* __restrict__ X, const int32_t* __restrict__ ptr, const int32_t* __restrict__ perm, int cols,
                            const float* __restrict__ scale, int accumulate, int row_div, float* __restrict__ out) {
-    __shared__ float red[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int64_t s = blockIdx.x;
+    __shared__ float red[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 columns x 32 row lanes (the carbon row of an atom table holds
+    const int64_t s = blockIdx.x;                              // most of the batch: long segments need the parallelism)
     const int c = blockIdx.y * 32 + tx;
     float acc = 0.0f;
     if (c < cols)
-        for (int p = ptr[s] + ty; p < ptr[s + 1]; p += 8) acc += X[static_cast<int64_t>((perm ? perm[p] : p) / row_div) * cols + c];
+        for (int p = ptr[s] + ty; p < ptr[s + 1]; p += 32) acc += X[static_cast<int64_t>((perm ? perm[p] : p) / row_div) * cols + c];
     red[ty][tx] = acc;
     __syncthreads();
     if (ty == 0 && c < cols) {
         float t = 0.0f;
-        for (int q = 0; q < 8; ++q) t += red[q][tx];
+        for (int q = 0; q < 32; ++q) t += red[q][tx];
         if (scale) t *= scale[s];
         out[s * cols + c] = accumulate ? out[s * cols + c] + t : t;
     }
@@ -595,7 +595,7 @@ int molsde_seg_gather_sum(const float* X, const int32_t* ptr, const int32_t* per
     if (!X || !ptr || !out || segments < 0 || cols <= 0 || row_div <= 0) return MOLSDE_ERR_INVALID;
     if (segments == 0) return MOLSDE_OK;
     if (segments <= 1024) {  // few segments: one CTA per (segment, 32 columns) instead of one thread per output
-        seg_gather_sum_wide_kernel<<<dim3(static_cast<unsigned>(segments), (cols + 31) / 32), 256, 0, as_stream(stream)>>>(
+        seg_gather_sum_wide_kernel<<<dim3(static_cast<unsigned>(segments), (cols + 31) / 32), 1024, 0, as_stream(stream)>>>(
             X, ptr, perm, cols, scale, accumulate, row_div, out);
         return check_launch("seg_gather_sum_wide");
     }

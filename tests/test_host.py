@@ -67,6 +67,40 @@ def test_state_dict_layout_matches_reference(golden):
     assert mine == golden["manifest"]["sde2d3d"]
 
 
+def test_all_module_state_dicts_match_reference_manifest(golden):
+    """GIN, SchNet and the dense 3D->2D model expose exactly the reference's state_dict keys, shapes and dtypes (the manifest
+    was recorded from the unmodified reference classes), so `model_complete.pth` checkpoints move in both directions; a
+    ParamStore re-homing the parameters into its flat buffer does not change that."""
+    import torch
+    from moleculesde_b200.gnn import GNN
+    from moleculesde_b200.pretrain import ParamStore
+    from moleculesde_b200.schnet import SchNet
+    from moleculesde_b200.sde_3d_to_2d import SDEModel3Dto2D_node_adj_dense
+    gnn = GNN(5, 300, JK="last", drop_ratio=0.0, gnn_type="GIN")
+    sch = SchNet(hidden_channels=300, num_filters=128, num_interactions=6, num_gaussians=51, cutoff=10, readout="mean", node_class=119)
+    m32 = SDEModel3Dto2D_node_adj_dense(dim3D=300, c_init=2, c_hid=8, c_final=4, num_heads=4, adim=16, nhid=16, num_layers=4,
+                                        emb_dim=300, num_linears=3, beta_min=0.1, beta_max=1.0, num_diffusion_timesteps=1000,
+                                        SDE_type="VE", num_class_X=119, noise_on_one_hot=True)
+    mods = {"gnn": gnn, "schnet": sch, "sde3d2d": m32}
+
+    def manifest(m):
+        return {k: (tuple(v.shape), str(v.dtype)) for k, v in m.state_dict().items()}
+
+    for name, m in mods.items():
+        assert manifest(m) == golden["manifest"][name], name
+    before = {n: {k: v.clone() for k, v in m.state_dict().items()} for n, m in mods.items()}
+    store = ParamStore(mods, torch.device("cpu"))
+    for name, m in mods.items():
+        assert manifest(m) == golden["manifest"][name], name + " (after ParamStore)"
+        for k, v in m.state_dict().items():
+            assert torch.equal(v, before[name][k]), (name, k)
+    # the channel-stacked layout: per-channel q/k/v parameters of a dense edge layer are adjacent in the flat buffer
+    idx = store.index["sde3d2d"]
+    a = idx["edge_score_network.layers.1.attn.0.func_q.layers.1.weight"]
+    b = idx["edge_score_network.layers.1.attn.1.func_q.layers.1.weight"]
+    assert b[0] == a[0] + a[1]
+
+
 def test_packed_blob_roundtrip(golden):
     from conftest import sd_from_manifest
     from moleculesde_b200 import sde_2d_to_3d as M
