@@ -15,6 +15,22 @@ def do_CL(X: torch.Tensor, Y: torch.Tensor, args, neg_index: Optional[torch.Tens
     if args.CL_similarity_metric != "EBM_node_dot_prod":
         raise NotImplementedError("only EBM_node_dot_prod (the pretraining metric, README.md:86-94) is built")
     require_device(X)
+    if torch.is_grad_enabled() and (X.requires_grad or Y.requires_grad):   # differentiable call (training loop)
+        from . import autograd as AG
+        from .pretrain import tape_cl
+        T = float(args.T)
+        holder = {}
+
+        def build(tp, ins, P):
+            c = [1.0]
+            out = tape_cl(tp, ins[0], ins[1], T, neg_index, c)
+
+            def seed(gouts):
+                c[0] = float(gouts[0].reshape(-1)[0].item()) if gouts[0] is not None else 0.0
+            holder["acc"] = out
+            return [out[:1].reshape(())], seed
+        loss = AG.apply(torch.nn.Module(), build, [X, Y])
+        return loss, float(holder["acc"][1].item())
     X = X.detach().float().contiguous()
     Y = Y.detach().float().contiguous()
     N, D = X.shape

@@ -49,19 +49,33 @@ class GNN(nn.Module):
         self.gnns = nn.ModuleList(GINConv(emb_dim) for _ in range(num_layer))
         self.batch_norms = nn.ModuleList(nn.BatchNorm1d(emb_dim) for _ in range(num_layer))
 
-    @torch.no_grad()
     def forward(self, *argv):
-        """`forward(x, edge_index, edge_attr)` or `forward(data)` (`molecule_gnn_model.py:160-167`) -> [N, emb_dim]."""
+        """`forward(x, edge_index, edge_attr)` or `forward(data)` (`molecule_gnn_model.py:160-167`) -> [N, emb_dim].
+        With autograd enabled and trainable parameters the call is one autograd node (`autograd.py`): `.backward()` runs our
+        backward kernels; otherwise it is a plain inference call."""
+        from . import autograd as AG
         from .pretrain import tape_gin
         from .tape import Tape, Var
-        batch, num_graphs = None, 1
+        batch, num_graphs, cache = None, 1, None
         if len(argv) == 3:
             x, edge_index, edge_attr = argv
         elif len(argv) == 1:
             x, edge_index, edge_attr = argv[0].x, argv[0].edge_index, argv[0].edge_attr
             batch, num_graphs = getattr(argv[0], "batch", None), getattr(argv[0], "num_graphs", 1)
+            cache = argv[0].__dict__.setdefault("_molsde_train_cache", {})
         else:
             raise ValueError("unmatched number of arguments.")
-        tp = Tape(x.device)
-        P = {n: Var(p.data, False) for n, p in self.named_parameters()}
-        return tape_gin(tp, self, P, x, edge_index, edge_attr, None, batch, num_graphs).data
+        if self.training and AG.grad_mode(self):
+            cache = cache if cache is not None else {}
+
+            def build(tp, ins, P):
+                h = tape_gin(tp, self, P, x, edge_index, edge_attr, cache, batch, num_graphs)
+
+                def seed(gouts):
+                    h.grad = gouts[0]
+                return [h.data], seed
+            return AG.apply(self, build, [])
+        with torch.no_grad():
+            tp = Tape(x.device)
+            P = {n: Var(p.data, False) for n, p in self.named_parameters()}
+            return tape_gin(tp, self, P, x, edge_index, edge_attr, None, batch, num_graphs).data

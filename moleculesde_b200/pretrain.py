@@ -152,6 +152,14 @@ class EdgeSet:
 # ======================================================================================================
 # SDEModel2Dto3D_02.forward (SDE_model_2D_to_3D.py:306-391)
 # ======================================================================================================
+def _coef(c, i: int = 0) -> float:
+    """Loss weight seeding a backward sweep: a float fixed at record time, or a mutable list filled in right before
+    `Tape.backward()` (the autograd bridge passes torch's grad_output this way; two entries = (loss_x, loss_adj))."""
+    if isinstance(c, (list, tuple)):
+        return float(c[min(i, len(c) - 1)])
+    return float(c)
+
+
 def _slice_cols(v: Var, a: int, b: int) -> Var:
     return Var(v.data[:, a:b], v.needs, v.grad[:, a:b] if v.grad is not None else None)
 
@@ -255,7 +263,7 @@ def tape_2d3d(tp: Tape, model, P: Dict[str, Var], h2d: Var, data, anneal_power: 
 
     def bwd():
         dgrad = tp.empty(N, 3)
-        tp._call(L.molsde_dsm_pos_loss_bwd, ptr(grad), ptr(noise), ptr(w), ptr(prep.node_ptr), ptr(node2graph), N, B, float(coef),
+        tp._call(L.molsde_dsm_pos_loss_bwd, ptr(grad), ptr(noise), ptr(w), ptr(prep.node_ptr), ptr(node2graph), N, B, _coef(coef),
                  ptr(dgrad), s, what="dsm_pos_loss_bwd")
         for dyn in dyn_list:
             dd = tp.empty(E, 3)
@@ -417,41 +425,52 @@ def tape_schnet(tp: Tape, model, P: Dict[str, Var], z: torch.Tensor, pos: torch.
 # ======================================================================================================
 # dual_CL, EBM_node_dot_prod (examples/util.py:52-79)
 # ======================================================================================================
-def tape_dual_cl(tp: Tape, X: Var, Y: Var, T: float, neg_index_1: Optional[torch.Tensor] = None,
-                 neg_index_2: Optional[torch.Tensor] = None, coef: float = 1.0):
-    """(loss [1], loss_acc pairs) of dual_CL(X, Y); backward seeds coef * d loss."""
+def tape_cl(tp: Tape, X: Var, Y: Var, T: float, neg_index: Optional[torch.Tensor] = None, coef=1.0):
+    """do_CL(X, Y) with metric EBM_node_dot_prod (`examples/util.py:52-68`): returns the [loss, acc] tensor; the backward seeds
+    coef * d loss into X.grad and Y.grad."""
     L, dev, s = tp.L, tp.dev, tp.s
     N, D = X.data.shape
-    outs = []
-    dX, dY = tp.empty(N, D), tp.empty(N, D)
-    saved = []
-    for k, (A, Bv, neg) in enumerate(((X, Y, neg_index_1), (Y, X, neg_index_2))):
-        # the reference draws on the CPU generator (util.py:55); here on the device, so that the step stays capturable
-        neg = torch.randperm(N, device=dev) if neg is None else neg
-        perm = neg.to(dev).long().contiguous()
-        inv = torch.empty_like(perm)
-        inv[perm] = torch.arange(N, device=dev)
-        pp, pn, out = tp.empty(N), tp.empty(N), tp.empty(2)
-        ws = tp.empty(4 * 592)
-        tp._call(L.molsde_ebm_node_dot, ptr(A.data), ptr(Bv.data), ptr(perm), N, D, float(T), ptr(pp), ptr(pn), ptr(out), ptr(ws),
-                 ws.numel(), s, what="ebm_node_dot")
-        outs.append(out)
-        saved.append((A, Bv, perm, inv, pp, pn))
-    loss = tp.empty(1)
-    tp.ew(0, outs[0][:1], outs[1][:1], None, 1.0, loss)
-    tp.ew(0, loss, None, None, 0.5, loss)
+    # the reference draws the permutation on the CPU generator (util.py:55); here on the device, so that the step stays capturable
+    neg = torch.randperm(N, device=dev) if neg_index is None else neg_index
+    perm = neg.to(dev).long().contiguous()
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(N, device=dev)
+    pp, pn, out = tp.empty(N), tp.empty(N), tp.empty(2)
+    ws = tp.empty(4 * 592)
+    tp._call(L.molsde_ebm_node_dot, ptr(X.data), ptr(Y.data), ptr(perm), N, D, float(T), ptr(pp), ptr(pn), ptr(out), ptr(ws),
+             ws.numel(), s, what="ebm_node_dot")
 
     def bwd():
-        (A, Bv, perm, inv, pp, pn) = saved[0]
-        tp._call(L.molsde_ebm_node_dot_bwd, ptr(A.data), ptr(Bv.data), ptr(perm), ptr(inv), ptr(pp), ptr(pn), N, D, float(T),
-                 0.5 * coef, 0, ptr(dX), ptr(dY), s, what="ebm_node_dot_bwd")
-        (A, Bv, perm, inv, pp, pn) = saved[1]   # roles swapped: A = Y, B = X
-        tp._call(L.molsde_ebm_node_dot_bwd, ptr(A.data), ptr(Bv.data), ptr(perm), ptr(inv), ptr(pp), ptr(pn), N, D, float(T),
-                 0.5 * coef, 1, ptr(dY), ptr(dX), s, what="ebm_node_dot_bwd")
+        dX, dY = tp.empty(N, D), tp.empty(N, D)
+        tp._call(L.molsde_ebm_node_dot_bwd, ptr(X.data), ptr(Y.data), ptr(perm), ptr(inv), ptr(pp), ptr(pn), N, D, float(T),
+                 _coef(coef), 0, ptr(dX), ptr(dY), s, what="ebm_node_dot_bwd")
         tp.accum(X, dX)
         tp.accum(Y, dY)
     tp.ops.append(bwd)
-    return loss, outs
+    return out
+
+
+def tape_dual_cl(tp: Tape, X: Var, Y: Var, T: float, neg_index_1: Optional[torch.Tensor] = None,
+                 neg_index_2: Optional[torch.Tensor] = None, coef=1.0):
+    """(loss [1], [loss, acc] pairs) of dual_CL(X, Y) = (do_CL(X,Y) + do_CL(Y,X)) / 2 (`util.py:76-79`)."""
+    half = [0.5 * _coef(coef)] if not isinstance(coef, list) else _Half(coef)
+    o1 = tape_cl(tp, X, Y, T, neg_index_1, half)
+    o2 = tape_cl(tp, Y, X, T, neg_index_2, half)
+    loss = tp.empty(1)
+    tp.ew(0, o1[:1], o2[:1], None, 1.0, loss)
+    tp.ew(0, loss, None, None, 0.5, loss)
+    return loss, [o1, o2]
+
+
+class _Half(list):
+    """view of a mutable coefficient list scaled by 1/2 (read at backward time)"""
+
+    def __init__(self, src):
+        super().__init__([0.0])
+        self.src = src
+
+    def __getitem__(self, i):
+        return 0.5 * float(self.src[0])
 
 
 # ======================================================================================================
@@ -699,10 +718,10 @@ def tape_3d2d(tp: Tape, model, P: Dict[str, Var], h3d: Var, data, anneal_power: 
 
     def loss_bwd():
         dsx = tp.empty(rows, K)
-        tp._call(L.molsde_graph_mse_bwd, ptr(score_x.data), ptr(z_x), _p(wx), B, Nm * K, float(coef), ptr(dsx), s, what="graph_mse_bwd")
+        tp._call(L.molsde_graph_mse_bwd, ptr(score_x.data), ptr(z_x), _p(wx), B, Nm * K, _coef(coef, 0), ptr(dsx), s, what="graph_mse_bwd")
         tp.accum(score_x, dsx)
         dsa = tp.empty(B, Nm, Nm)
-        tp._call(L.molsde_graph_mse_bwd, ptr(score_adj), ptr(z_adj), _p(wa), B, Nm * Nm, float(coef), ptr(dsa), s, what="graph_mse_bwd")
+        tp._call(L.molsde_graph_mse_bwd, ptr(score_adj), ptr(z_adj), _p(wa), B, Nm * Nm, _coef(coef, 1), ptr(dsa), s, what="graph_mse_bwd")
         draw = tp.empty(B * Nm * Nm, 1)
         tp._call(L.molsde_dense_edge_final_bwd, ptr(dsa), ptr(flags), ptr(scale_adj), B, Nm, ptr(draw), s, what="dense_edge_final_bwd")
         tp.accum(raw, draw)

@@ -119,12 +119,31 @@ class SchNet(nn.Module):
         self._packed = (ver, (mu, packed))
         return self._packed[1]
 
-    @torch.no_grad()
     def forward(self, z, pos, batch=None, return_latent=False):
+        """Reference signature (`schnet.py:85`).  Inference: the fused edge-kernel path below.  With autograd enabled and
+        trainable parameters: one autograd node over the layer-granular training kernels (`autograd.py`, `pretrain.tape_schnet`);
+        gradients flow to the parameters (positions are inputs of the pretraining step, not differentiated)."""
         assert z.dim() == 1 and z.dtype == torch.long
         require_device(pos)
         batch = torch.zeros_like(z) if batch is None else batch
         num_graphs = int(batch[-1].item()) + 1 if batch.numel() else 0
+        from . import autograd as AG
+        if self.training and AG.grad_mode(self):
+            from .pretrain import tape_schnet
+
+            def build(tp, ins, P):
+                h = tape_schnet(tp, self, P, z.contiguous(), pos, batch, num_graphs, {})
+
+                def seed(gouts):
+                    h.grad = gouts[0]
+                return [h.data], seed
+            h = AG.apply(self, build, [])
+            out = segment_reduce(h.detach(), segment_ptr(batch, num_graphs), mean=(self.readout == "mean"))   # :115 (not differentiated)
+            return (out, h) if return_latent else out
+        with torch.no_grad():
+            return self._forward_inference(z, pos, batch, num_graphs, return_latent)
+
+    def _forward_inference(self, z, pos, batch, num_graphs, return_latent):
         pos = pos.detach().float().contiguous()
         csr = radius_graph(pos, self.cutoff, batch, num_graphs, want_edge_index=False)   # schnet.py:91
         node_ptr = segment_ptr(batch, num_graphs)

@@ -326,12 +326,29 @@ class SDEModel2Dto3D_02(nn.Module):
               "edge2d_emb_eval")
         return nattr, e2d, pk["blob"]
 
-    @torch.no_grad()
     def forward(self, node_2D_repr, data, anneal_power, draws: Optional[dict] = None):
-        """Denoising score-matching loss of `SDE_model_2D_to_3D.py:306-391` (forward VALUE; the backward kernels are not
-        built yet, so the returned loss carries no autograd graph).  `draws` injects the random draws for parity tests:
-        `noise` [N,3], `time_step` (the `randint` of :322, [B//2+1]), `dropout` = 4 x (attn_mask [E,8] in
-        `extended_edge_index` order, ffn_mask [N,32]) in GATLayer call order; missing entries are drawn with torch's RNG."""
+        """Denoising score-matching loss of `SDE_model_2D_to_3D.py:306-391` -> {"position": loss}.  In train mode with autograd
+        enabled the call is one autograd node (`autograd.py`, `pretrain.tape_2d3d`): `loss.backward()` yields the gradients of
+        every parameter and of `node_2D_repr`.  Otherwise (eval / no_grad) the fused persistent kernel computes the value.
+        `draws` injects the random draws for parity tests: `noise` [N,3], `time_step` (the `randint` of :322, [B//2+1]),
+        `dropout` = 4 x (attn_mask [E,8] in `extended_edge_index` order, ffn_mask [N,32]) in GATLayer call order; missing
+        entries are drawn with torch's RNG."""
+        from . import autograd as AG
+        if self.training and AG.grad_mode(self, node_2D_repr):
+            from .pretrain import tape_2d3d
+
+            def build(tp, ins, P):
+                c = [1.0]
+                loss = tape_2d3d(tp, self, P, ins[0], data, anneal_power, draws, coef=c)
+
+                def seed(gouts):
+                    c[0] = float(gouts[0].reshape(-1)[0].item()) if gouts[0] is not None else 0.0
+                return [loss.reshape(())], seed
+            return {"position": AG.apply(self, build, [node_2D_repr])}
+        with torch.no_grad():
+            return self._forward_value(node_2D_repr, data, anneal_power, draws)
+
+    def _forward_value(self, node_2D_repr, data, anneal_power, draws: Optional[dict] = None):
         draws = draws or {}
         pos = data.positions.detach().float().contiguous()
         require_device(pos)

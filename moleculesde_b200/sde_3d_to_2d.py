@@ -359,12 +359,31 @@ class SDEModel3Dto2D_node_adj_dense(nn.Module):
         check(lib().molsde_to_dense_batch(ptr(zf), ptr(node_ptr), B, Nm, 1, ptr(zd), 1, s), "to_dense_batch(z)")
         return adj, rep, zd.view(B, Nm).long(), node_flags(adj), Nm
 
-    @torch.no_grad()
     def forward(self, node_3D_repr, data, continuous, train, reduce_mean, anneal_power, *, draws=None):
-        """DSM losses (loss_x, loss_adj), `:101-179` (forward values; `draws` = (randint, randn adj, randn one-hot)
-        injects the three random draws in reference order)."""
+        """DSM losses (loss_x, loss_adj), `:101-179`; `draws` = (randint, randn adj, randn one-hot) injects the three random
+        draws in reference order.  With autograd enabled (training loop) the call is one autograd node (`autograd.py`,
+        `pretrain.tape_3d2d`); under no_grad the forward kernels compute the values."""
         if not reduce_mean:
             raise NotImplementedError("reduce_mean=False only pairs with noise_on_one_hot=False")
+        from . import autograd as AG
+        if train and AG.grad_mode(self, node_3D_repr):
+            if not continuous:
+                raise NotImplementedError("Discrete not supported")
+            from .pretrain import tape_3d2d
+
+            def build(tp, ins, P):
+                c = [1.0, 1.0]
+                lx, la = tape_3d2d(tp, self, P, ins[0], data, anneal_power, draws, coef=c)
+
+                def seed(gouts):
+                    for i in range(2):
+                        c[i] = float(gouts[i].reshape(-1)[0].item()) if gouts[i] is not None else 0.0
+                return [lx.reshape(()), la.reshape(())], seed
+            return AG.apply(self, build, [node_3D_repr])
+        with torch.no_grad():
+            return self._forward_value(node_3D_repr, data, continuous, train, reduce_mean, anneal_power, draws=draws)
+
+    def _forward_value(self, node_3D_repr, data, continuous, train, reduce_mean, anneal_power, *, draws=None):
         adj, rep, zd, flags, Nm = self.dense_inputs(node_3D_repr, data)
         dev, B, N, s = adj.device, adj.size(0), self.num_diffusion_timesteps, stream_ptr(adj)
         if self.noise_mode == "discrete":

@@ -320,3 +320,57 @@ def test_pretrain_step_small_and_odd_batches(num_mols, seed, golden):
         assert abs(float(out[k]) - float(ref[k])) <= REL_TOL * max(abs(float(ref[k])), 1e-3), (k, float(out[k]), float(ref[k]))
     assert torch.isfinite(ps.store.grad).all() and float(ps.store.grad.abs().max()) > 0
     assert torch.isfinite(ps.store.flat).all()
+
+
+def test_reference_training_loop_through_autograd(gg, golden, golden_batch):
+    """The reference's own loop body (`pretrain_MoleculeSDE.py:124-152`): module calls, `loss.backward()`, torch.optim.Adam —
+    unchanged, on our modules through the autograd bridge.  Losses and gradients match the reference step fixture."""
+    import types
+    from moleculesde_b200.contrastive import dual_CL
+    from moleculesde_b200.sde_2d_to_3d import SDEModel2Dto3D_02
+    from moleculesde_b200.sde_3d_to_2d import SDEModel3Dto2D_node_adj_dense
+    from test_gpu_sde2d3d import _gpu_batch
+    dev = _dev()
+    sec = gg["pretrain_VE"]
+    _, batch = golden_batch
+    molecule_model_2D, molecule_model_3D = _encoders(golden, dev)
+    SDE_2Dto3D_model = SDEModel2Dto3D_02(emb_dim=300, hidden_dim=32, beta_schedule=None, beta_min=0.2, beta_max=1.0,
+                                         num_diffusion_timesteps=1000, SDE_type="VE", use_extend_graph=True)
+    SDE_2Dto3D_model.load_state_dict(sd_from_manifest(golden["manifest"]["sde2d3d"], golden["meta"]["weight_seed"]))
+    SDE_3Dto2D_model = SDEModel3Dto2D_node_adj_dense(
+        dim3D=300, c_init=2, c_hid=8, c_final=4, num_heads=4, adim=16, nhid=16, num_layers=4, emb_dim=300, num_linears=3,
+        beta_min=0.1, beta_max=1.0, num_diffusion_timesteps=1000, SDE_type="VE", num_class_X=119, noise_on_one_hot=True)
+    SDE_3Dto2D_model.load_state_dict(sd_from_manifest(golden["manifest"]["sde3d2d"], golden["meta"]["weight_seed"]))
+    mods = {"gnn": molecule_model_2D, "schnet": molecule_model_3D, "sde2d3d": SDE_2Dto3D_model, "sde3d2d": SDE_3Dto2D_model}
+    for m in mods.values():
+        m.to(dev).train()
+    optimizer = torch.optim.Adam([{"params": m.parameters(), "lr": 1e-4} for m in mods.values()], lr=1e-4, weight_decay=0)
+    args = types.SimpleNamespace(CL_similarity_metric="EBM_node_dot_prod", T=0.1)
+    b = _gpu_batch(batch, dev)
+    d = sec["draws"]
+    # ---- the reference loop body, with the recorded draws injected through the keyword-only extensions ----
+    node_2D_repr = molecule_model_2D(b.x, b.edge_index, b.edge_attr)
+    _, node_3D_repr = molecule_model_3D(b.x[:, 0].contiguous(), b.positions, b.batch, return_latent=True)
+    CL_loss, CL_acc = dual_CL(node_2D_repr, node_3D_repr, args, d[0][1], d[1][1])
+    loss = CL_loss * 1.0
+    SDE_loss_2Dto3D = SDE_2Dto3D_model(node_2D_repr, b, anneal_power=0, draws=_draws_2d3d(sec))["position"]
+    loss = loss + SDE_loss_2Dto3D * 1.0
+    lx, la = SDE_3Dto2D_model(node_3D_repr, b, reduce_mean=True, continuous=True, train=True, anneal_power=0,
+                              draws=[v for _, v in d[12:15]])
+    loss = loss + (lx + la) * 0.5 * 1.0
+    optimizer.zero_grad()
+    loss.backward()
+    # ----
+    assert abs(float(loss.detach()) - float(sec["loss"])) <= REL_TOL * abs(float(sec["loss"]))
+    assert abs(float(CL_loss.detach()) - float(sec["cl_loss"])) <= REL_TOL * abs(float(sec["cl_loss"]))
+
+    class _S:  # adapter: _check_module_grads reads store.grad_view(module, name)
+        def grad_view(self, mname, pname):
+            return dict(mods[mname].named_parameters())[pname].grad
+    zero = ("edge_2D_emb.0.bias", "lin_key.bias")
+    _check_module_grads(_S(), "gnn", sec, skip_zero=("mlp.0.bias", "mlp.3.bias"))
+    _check_module_grads(_S(), "schnet", sec)
+    _check_module_grads(_S(), "sde2d3d", sec, skip_zero=zero)
+    _check_module_grads(_S(), "sde3d2d", sec)
+    optimizer.step()
+    assert all(torch.isfinite(p).all() for m in mods.values() for p in m.parameters())
