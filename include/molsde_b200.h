@@ -307,6 +307,11 @@ int molsde_edge_mul_gather(const float* A, const int32_t* ia, const float* B, co
                            void* stream);
 /* out[0] (+)= alpha <a,b>;  ws: >= 128 doubles */
 int molsde_dot(const float* a, const float* b, int64_t n, float alpha, int32_t accumulate, float* out, double* ws, void* stream);
+/* do_CL, metric InfoNCE_dot_prod (examples/util.py:23-32): rows of logits [B,B] = X Y^T / T (a molsde_tc_gemm):
+ * loss_row[r] = logsumexp(logits[r,:]) - logits[r,r], correct_row[r] = (argmax == r); with write_grad the logits are replaced
+ * in place by (softmax - onehot) * grad_scale, from which dX = dlogits . Y and dY = dlogits^T . X are two more GEMMs. */
+int molsde_infonce_rows(float* logits, int64_t B, int64_t ld, float grad_scale, int32_t write_grad, float* loss_row, float* correct_row,
+                        void* stream);
 /* GINConv (molecule_gnn_model.py:13-32): pre = (1+eps) x + sum_{e->i} relu(x_src + BondEncoder(e)); dmsg = dpre[tgt] * relu' */
 int molsde_gin_aggregate_fwd(const float* x, const float* T, const int32_t* ekeys, int32_t F, const int32_t* rowptr, const int32_t* src,
                              const float* eps, int64_t N, int32_t cols, float* pre, void* stream);

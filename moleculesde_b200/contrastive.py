@@ -1,5 +1,6 @@
-"""`do_CL` / `dual_CL` of `examples/util.py:22-79` for the pretraining metric `EBM_node_dot_prod`
-(forward: loss and accuracy) through `molsde_ebm_node_dot`."""
+"""`do_CL` / `dual_CL` of `examples/util.py:22-79`: the pretraining metric `EBM_node_dot_prod` (row-wise dots, HBM-bound,
+`molsde_ebm_node_dot`) and `InfoNCE_dot_prod` (a dense B x B contraction on the tcgen05 GEMM + a row-softmax kernel).
+Differentiable through the autograd bridge when an input requires grad."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -12,18 +13,19 @@ from ._abi import check, lib, ptr, require_device, stream_ptr
 def do_CL(X: torch.Tensor, Y: torch.Tensor, args, neg_index: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, float]:
     """Reference signature `do_CL(X, Y, args)`; `neg_index` injects the `torch.randperm(len(Y))` draw
     (`util.py:55`, CPU generator in the reference)."""
-    if args.CL_similarity_metric != "EBM_node_dot_prod":
-        raise NotImplementedError("only EBM_node_dot_prod (the pretraining metric, README.md:86-94) is built")
+    if args.CL_similarity_metric not in ("EBM_node_dot_prod", "InfoNCE_dot_prod"):
+        raise NotImplementedError("built: EBM_node_dot_prod (the pretraining metric, README.md:86-94) and InfoNCE_dot_prod")
     require_device(X)
-    if torch.is_grad_enabled() and (X.requires_grad or Y.requires_grad):   # differentiable call (training loop)
+    infonce = args.CL_similarity_metric == "InfoNCE_dot_prod"
+    if infonce or (torch.is_grad_enabled() and (X.requires_grad or Y.requires_grad)):   # tape path (differentiable when asked)
         from . import autograd as AG
-        from .pretrain import tape_cl
+        from .pretrain import tape_cl, tape_infonce
         T = float(args.T)
         holder = {}
 
         def build(tp, ins, P):
             c = [1.0]
-            out = tape_cl(tp, ins[0], ins[1], T, neg_index, c)
+            out = tape_infonce(tp, ins[0], ins[1], T, c) if infonce else tape_cl(tp, ins[0], ins[1], T, neg_index, c)
 
             def seed(gouts):
                 c[0] = float(gouts[0].reshape(-1)[0].item()) if gouts[0] is not None else 0.0

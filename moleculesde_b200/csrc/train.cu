@@ -355,6 +355,44 @@ __global__ void ebm_node_dot_bwd_kernel(const float* __restrict__ X, const float
     dY[idx] = accumulate ? dY[idx] + dy : dy;
 }
 
+// ---- InfoNCE_dot_prod (examples/util.py:23-32): CrossEntropy(logits, arange) over the rows of logits [B,B] = X Y^T / T ----
+// one warp per row: loss_row = logsumexp(row) - row[r], correct_row = (argmax(row) == r);  optionally the gradient
+// dlogits = (softmax(row) - onehot(r)) * scale in place of the logits (scale = coef / B).
+__global__ void __launch_bounds__(256)
+infonce_rows_kernel(float* __restrict__ logits, int64_t B, int64_t ld, float grad_scale, int write_grad, float* __restrict__ loss_row,
+                    float* __restrict__ correct_row) {
+    const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= B) return;
+    float* row = logits + r * ld;
+    float mx = -INFINITY;
+    int64_t arg = 0;
+    for (int64_t c = lane; c < B; c += 32) {
+        const float v = row[c];
+        if (v > mx) { mx = v; arg = c; }   // first maximum per lane (ascending c)
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int64_t oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }   // torch.argmax: first index of the maximum
+    }
+    float s = 0.0f;
+    for (int64_t c = lane; c < B; c += 32) s += expf(row[c] - mx);
+    s = warp_sum(s);
+    const float lse = mx + logf(s);
+    if (lane == 0) {
+        if (loss_row) loss_row[r] = lse - row[r];
+        if (correct_row) correct_row[r] = (arg == r) ? 1.0f : 0.0f;
+    }
+    if (write_grad) {
+        __syncwarp();
+        for (int64_t c = lane; c < B; c += 32) {
+            const float p = expf(row[c] - lse);
+            row[c] = (p - (c == r ? 1.0f : 0.0f)) * grad_scale;
+        }
+    }
+}
+
 // ---- LayerNorm over the last dim (D <= 1024), one warp per row ----
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, int64_t M, int D, const float* __restrict__ g,
                                      const float* __restrict__ b, float eps, float* __restrict__ y, float* __restrict__ mean_out,
@@ -657,6 +695,12 @@ int molsde_ebm_node_dot_bwd(const float* X, const float* Y, const int64_t* perm,
     ebm_node_dot_bwd_kernel<<<blocks_for(N * D), 256, 0, as_stream(stream)>>>(X, Y, perm, invperm, pred_pos, pred_neg, N, D,
                                                                            coef / (static_cast<float>(N) * T), accumulate, dX, dY);
     return check_launch("ebm_node_dot_bwd");
+}
+int molsde_infonce_rows(float* logits, int64_t B, int64_t ld, float grad_scale, int32_t write_grad, float* loss_row, float* correct_row,
+                        void* stream) {
+    if (!logits || B <= 0 || ld < B) return MOLSDE_ERR_INVALID;
+    infonce_rows_kernel<<<blocks_for(B, 8), 256, 0, as_stream(stream)>>>(logits, B, ld, grad_scale, write_grad, loss_row, correct_row);
+    return check_launch("infonce_rows");
 }
 int molsde_bucket_count(const int64_t* keys, int64_t n, int32_t buckets, int32_t* count, void* stream) {
     if (!keys || !count || n < 0 || buckets <= 0) return MOLSDE_ERR_INVALID;

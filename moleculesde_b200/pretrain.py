@@ -450,6 +450,35 @@ def tape_cl(tp: Tape, X: Var, Y: Var, T: float, neg_index: Optional[torch.Tensor
     return out
 
 
+def tape_infonce(tp: Tape, X: Var, Y: Var, T: float, coef=1.0):
+    """do_CL(X, Y) with metric InfoNCE_dot_prod (`examples/util.py:23-32`): logits = X Y^T / T on the tensor cores (tcgen05
+    3xTF32), CrossEntropy against the diagonal.  Returns the [loss, acc] tensor; backward: d logits = (softmax - I) coef / B, then
+    dX = d logits . Y / T and dY = d logits^T . X / T as two more tensor-core GEMMs."""
+    L, s = tp.L, tp.s
+    B, D = X.data.shape
+    inv_t = torch.full((B,), 1.0 / float(T), dtype=torch.float32, device=tp.dev)
+    logits = tp.empty(B, B)
+    tp._call(L.molsde_tc_gemm, B, B, D, ptr(X.data), D, 1, ptr(Y.data), D, 1, None, 0, ptr(inv_t), None, 0, ptr(logits), B, 0, None, 0,
+             None, s, what="tc_gemm")
+    loss_row, correct_row, out = tp.empty(B), tp.empty(B), tp.empty(2)
+    tp._call(L.molsde_infonce_rows, ptr(logits), B, B, 0.0, 0, ptr(loss_row), ptr(correct_row), s, what="infonce_rows")
+    tp._call(L.molsde_mean, ptr(loss_row), B, out.data_ptr(), s, what="mean")
+    tp._call(L.molsde_mean, ptr(correct_row), B, out.data_ptr() + 4, s, what="mean")
+
+    def bwd():
+        tp._call(L.molsde_infonce_rows, ptr(logits), B, B, _coef(coef) / (B * float(T)), 1, None, None, s, what="infonce_rows")
+        if X.needs:
+            dX = tp.empty(B, D)
+            tp.gemm(0, 0, B, D, B, logits, B, Y.data, D, dX, D)          # d logits . Y
+            tp.accum(X, dX)
+        if Y.needs:
+            dY = tp.empty(B, D)
+            tp.gemm(1, 0, B, D, B, logits, B, X.data, D, dY, D)          # d logits^T . X
+            tp.accum(Y, dY)
+    tp.ops.append(bwd)
+    return out
+
+
 def tape_dual_cl(tp: Tape, X: Var, Y: Var, T: float, neg_index_1: Optional[torch.Tensor] = None,
                  neg_index_2: Optional[torch.Tensor] = None, coef=1.0):
     """(loss [1], [loss, acc] pairs) of dual_CL(X, Y) = (do_CL(X,Y) + do_CL(Y,X)) / 2 (`util.py:76-79`)."""

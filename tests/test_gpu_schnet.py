@@ -75,3 +75,33 @@ def test_cl_edge_cases():
         loss, acc = do_CL(X.to(dev), Y.to(dev), args, perm)
         assert rel_err(loss.cpu().reshape(1), ref_loss.reshape(1)) < 2e-5
         assert abs(acc - ref_acc) < 1e-6
+
+
+@pytest.mark.parametrize("B,D", [(109, 300), (700, 300), (33, 64)])
+def test_infonce_dot_prod_loss_acc_and_grads(B, D):
+    """do_CL with metric InfoNCE_dot_prod (`examples/util.py:23-32`): logits on the tcgen05 GEMM, CrossEntropy vs the diagonal;
+    loss, accuracy and both input gradients against torch (fp64) restating the reference lines."""
+    import types
+    import torch.nn.functional as F
+    from moleculesde_b200.contrastive import do_CL
+    dev = _dev()
+    g = torch.Generator().manual_seed(B)
+    X = (0.2 * torch.randn(B, D, generator=g)).to(dev).requires_grad_(True)
+    Y = (0.2 * torch.randn(B, D, generator=g)).to(dev).requires_grad_(True)
+    args = types.SimpleNamespace(CL_similarity_metric="InfoNCE_dot_prod", T=0.1)
+    loss, acc = do_CL(X, Y, args)
+    (loss * 3.0).backward()
+    Xr, Yr = X.detach().double().cpu().requires_grad_(True), Y.detach().double().cpu().requires_grad_(True)
+    logits = torch.mm(Xr, Yr.t()) / 0.1
+    labels = torch.arange(B)
+    ref = F.cross_entropy(logits, labels)
+    ref_acc = float((logits.argmax(dim=1) == labels).sum()) / B
+    (ref * 3.0).backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
+    assert abs(acc - ref_acc) < 1e-6
+    for got, want in ((X.grad, Xr.grad), (Y.grad, Yr.grad)):
+        err = float((got.double().cpu() - want).abs().max() / want.abs().max())
+        assert err < 1e-4, err
+    with torch.no_grad():
+        l2, a2 = do_CL(X.detach(), Y.detach(), args)
+    assert float(l2) == float(loss.detach()) and a2 == acc
