@@ -218,9 +218,13 @@ class Tape:
                         g = self.grad_of(full)[:, x_cols[0]:x_cols[1]]
                         self.gemm(0, 0, M, K, Nout, dpre, _ld(dpre), W.data, _ld(W.data), g, _ld(g), accumulate=True)
                 elif x.needs:
-                    dx = self.empty(M, K)
-                    self.gemm(0, 0, M, K, Nout, dpre, _ld(dpre), W.data, _ld(W.data), dx, K)
-                    self.accum(x, dx)
+                    if x.grad is not None and x.grad.is_contiguous() and x.grad.shape == x.data.shape:
+                        # another consumer already produced a gradient: accumulate in the GEMM epilogue (no extra add pass)
+                        self.gemm(0, 0, M, K, Nout, dpre, _ld(dpre), W.data, _ld(W.data), x.grad, K, accumulate=True)
+                    else:
+                        dx = self.empty(M, K)
+                        self.gemm(0, 0, M, K, Nout, dpre, _ld(dpre), W.data, _ld(W.data), dx, K)
+                        self.accum(x, dx)
             self.ops.append(bwd)
         return out
 
