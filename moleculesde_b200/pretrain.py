@@ -19,6 +19,9 @@ from ._abi import check, lib, ptr, require_device, stream_ptr
 from .graph import csr_by_target
 from .tape import Index, Tape, Var, _p
 
+import os as _os
+_SINGLE_STREAM = _os.environ.get("MOLSDE_SINGLE_STREAM") == "1"   # A/B switch: issue the whole iteration on one stream
+
 
 _CH = re.compile(r"^edge_score_network\.layers\.(\d+)\.attn\.(\d+)\.(func_q|func_k)\.layers\.(\d)\.(weight|bias)$")
 _CV = re.compile(r"^edge_score_network\.layers\.(\d+)\.attn\.(\d+)\.func_v\.(weight|bias)$")
@@ -776,36 +779,109 @@ class PretrainStep:
         # pretrain_MoleculeSDE.py:331-335: 2D GNN and 2D->3D share gnn_2d_lr_scale; SchNet and 3D->2D share gnn_3d_lr_scale
         self.lr_scale = {"gnn": gnn_2d_lr_scale, "sde2d3d": gnn_2d_lr_scale, "schnet": gnn_3d_lr_scale, "sde3d2d": gnn_3d_lr_scale}
         self.launches = 0
+        self._streams = None
         for m in (gnn, schnet, sde_2d3d, sde_3d2d):
             m.train()
 
     def forward_backward(self, batch, draws: Optional[dict] = None) -> Dict[str, torch.Tensor]:
         """Forward + backward of one batch; gradients are left in `store.grad`.  `draws` (parity tests):
-        {"cl": (perm1, perm2), "sde2d3d": {...}, "sde3d2d": [randint, randn_adj, randn_x]}."""
+        {"cl": (perm1, perm2), "sde2d3d": {...}, "sde3d2d": [randint, randn_adj, randn_x]}.
+
+        The iteration is a fork/join graph, not a chain (pretrain_MoleculeSDE.py:131-147: the two encoders are independent, and
+        each of the three loss terms depends only on the encoder outputs), so it is issued on three streams:
+
+            main:  GIN forward ........ | 3D->2D forward+backward | d h2d = d_23 + d_CL -> GIN backward    |
+            s1:    SchNet forward ..... | 2D->3D forward+backward | d h3d = d_32 + d_CL -> SchNet backward | join
+            s2:                         | dual_CL forward+backward|
+
+        Under CUDA-graph replay the branches overlap on the GPU (most kernels of this step are far smaller than 148 SMs).  Every
+        branch owns its tape and its own gradient tensor for the shared representations, the two contributions are added after
+        the join in a fixed order, and each branch writes a disjoint slice of the flat gradient buffer — results are
+        bit-identical to the single-stream order (`MOLSDE_SINGLE_STREAM=1`)."""
         draws = draws or {}
         st = self.store
         st.zero_grad()
-        tp = Tape(self.dev)
+        multi = self.dev.type == "cuda" and not _SINGLE_STREAM
+        main = torch.cuda.current_stream(self.dev)
+        if multi:
+            if self._streams is None:
+                self._streams = (torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev))
+            s1, s2 = self._streams
+        else:
+            s1 = s2 = main
         cache = batch.__dict__.setdefault("_molsde_train_cache", {})
-        h2d = tape_gin(tp, self.gnn, st.vars("gnn"), batch.x, batch.edge_index, batch.edge_attr, cache, batch.batch, batch.num_graphs)
         z = cache.get("z")
         if z is None:
             z = cache["z"] = batch.x[:, 0].contiguous()
-        h3d = tape_schnet(tp, self.schnet, st.vars("schnet"), z, batch.positions, batch.batch, batch.num_graphs, cache)
+
+        def fork(dst, *srcs):
+            for src in srcs:
+                if dst is not src:
+                    dst.wait_stream(src)
+
+        # ---- encoders: GIN on main, SchNet on s1
+        fork(s1, main)
+        tp_g = Tape(self.dev)
+        h2d = tape_gin(tp_g, self.gnn, st.vars("gnn"), batch.x, batch.edge_index, batch.edge_attr, cache, batch.batch, batch.num_graphs)
+        with torch.cuda.stream(s1):
+            tp_s = Tape(self.dev)
+            h3d = tape_schnet(tp_s, self.schnet, st.vars("schnet"), z, batch.positions, batch.batch, batch.num_graphs, cache)
+        # ---- loss branches, each forward + backward on its own stream with private gradient tensors for h2d / h3d
         out = {}
+        keep = []   # cross-stream tensors stay referenced until the final join (the caching allocator reuses per stream)
+        g2d, g3d = [], []
+        fork(s2, main, s1)
+        fork(s1, main)
+        fork(main, s1)
         if self.c_cl > 0:
-            n1, n2 = draws.get("cl", (None, None))
-            out["cl_loss"], accs = tape_dual_cl(tp, h2d, h3d, self.T, n1, n2, coef=self.c_cl)
-            out["cl_acc_pair"] = accs
+            with torch.cuda.stream(s2):
+                tp = Tape(self.dev)
+                x2, x3 = Var(h2d.data, h2d.needs), Var(h3d.data, h3d.needs)
+                n1, n2 = draws.get("cl", (None, None))
+                out["cl_loss"], accs = tape_dual_cl(tp, x2, x3, self.T, n1, n2, coef=self.c_cl)
+                out["cl_acc_pair"] = accs
+                tp.backward()
+                keep += [tp, x2, x3]
+                cl2, cl3 = x2, x3
+        else:
+            cl2 = cl3 = None
         if self.c_23 > 0:
-            out["loss_2d3d"] = tape_2d3d(tp, self.m23, st.vars("sde2d3d"), h2d, batch, self.anneal_power, draws.get("sde2d3d"),
-                                         coef=self.c_23)
+            with torch.cuda.stream(s1):
+                tp = Tape(self.dev)
+                x2 = Var(h2d.data, h2d.needs)
+                out["loss_2d3d"] = tape_2d3d(tp, self.m23, st.vars("sde2d3d"), x2, batch, self.anneal_power, draws.get("sde2d3d"),
+                                             coef=self.c_23)
+                tp.backward()
+                keep += [tp, x2]
+                g2d.append(x2)
         if self.c_32 > 0:
-            out["loss_x"], out["loss_adj"] = tape_3d2d(tp, self.m32, st.vars("sde3d2d"), h3d, batch, self.anneal_power,
+            tp = Tape(self.dev)
+            x3 = Var(h3d.data, h3d.needs)
+            out["loss_x"], out["loss_adj"] = tape_3d2d(tp, self.m32, st.vars("sde3d2d"), x3, batch, self.anneal_power,
                                                        draws.get("sde3d2d"), coef=0.5 * self.c_32)
-        tp.backward()
-        self.launches = tp.launches
+            tp.backward()
+            keep += [tp, x3]
+            g3d.append(x3)
+        if cl2 is not None:
+            g2d.append(cl2)
+            g3d.append(cl3)
+        launches = sum(t.launches for t in keep if isinstance(t, Tape))
+        # ---- join, add the branch gradients (fixed order: SDE branch, then CL), encoder backwards on main / s1
+        fork(main, s1, s2)
+        fork(s1, main, s2)
+        for v in g2d:
+            if v.grad is not None:
+                tp_g.accum(h2d, v.grad)
+        tp_g.backward()
+        with torch.cuda.stream(s1):
+            for v in g3d:
+                if v.grad is not None:
+                    tp_s.accum(h3d, v.grad)
+            tp_s.backward()
+        fork(main, s1)
+        self.launches = launches + tp_g.launches + tp_s.launches
         out["h2d"], out["h3d"] = h2d, h3d
+        out["_keep"] = keep
         return out
 
     def step(self, batch, draws: Optional[dict] = None) -> Dict[str, torch.Tensor]:
