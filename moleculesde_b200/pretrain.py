@@ -21,6 +21,9 @@ from .tape import Index, Tape, Var, _p
 
 import os as _os
 _SINGLE_STREAM = _os.environ.get("MOLSDE_SINGLE_STREAM") == "1"   # A/B switch: issue the whole iteration on one stream
+# parameter gradients on side streams (Tape.wgrad): "capture" = only while a CUDA graph is being captured (the eager step is
+# bound by host launch time, where the extra event calls cost more than the overlap returns), "1" always, "0" never
+_WGRAD_STREAMS = _os.environ.get("MOLSDE_WGRAD_STREAMS", "capture")
 
 
 _CH = re.compile(r"^edge_score_network\.layers\.(\d+)\.attn\.(\d+)\.(func_q|func_k)\.layers\.(\d)\.(weight|bias)$")
@@ -533,7 +536,8 @@ def _dense_gcn(tp: Tape, adjc: Var, c: int, C: int, xw: Var, xw_col0: int, bias:
                  out.data.data_ptr(), dout.data_ptr(), out.data.stride(0), out_off, code, ptr(dpre),
                  dxw.data_ptr() + 4 * xw_col0, dxw.stride(0), da_ptr, C * Nm * Nm, 1, s, what="dense_gcn_bwd")
         if bias.needs:
-            tp.colsum(dpre, B * Nm, Fo, Fo, bias.grad, accumulate=True)
+            with tp.wgrad(dpre):
+                tp.colsum(dpre, B * Nm, Fo, Fo, bias.grad, accumulate=True)
     tp.ops.append(bwd)
 
 
@@ -609,7 +613,8 @@ def _dense_gcn_all(tp: Tape, adjc: Var, C: int, xw: Var, bias: Var, Fo: int, out
         tp._call(L.molsde_dense_gcn_bwd, ptr(a), sb, sc, B, C, Nm, ptr(xw.data), xw.data.stride(0), Fo, ptr(out.data), ptr(dout),
                  out.data.stride(0), 0, 0, ptr(dpre), ptr(dxw), C * Fo, _p(da), C * Nm * Nm, 1, s, what="dense_gcn_bwd")
         if bias.needs:
-            tp.colsum(dpre, B * Nm, C * Fo, C * Fo, bias.grad, accumulate=True)
+            with tp.wgrad(dpre):
+                tp.colsum(dpre, B * Nm, C * Fo, C * Fo, bias.grad, accumulate=True)
         tp.accum(xw, dxw)
     tp.ops.append(bwd)
 
@@ -730,7 +735,8 @@ def tape_3d2d(tp: Tape, model, P: Dict[str, Var], h3d: Var, data, anneal_power: 
             if xw.grad is None:
                 return
             xv = xs.data[:, cur_off:cur_off + width]
-            tp.gemm(1, 0, width, nsn.nhid, rows, xv, xs.data.stride(0), xw.grad, nsn.nhid, W.grad, nsn.nhid, accumulate=True)
+            with tp.wgrad(xw.grad, xs.data):
+                tp.gemm(1, 0, width, nsn.nhid, rows, xv, xs.data.stride(0), xw.grad, nsn.nhid, W.grad, nsn.nhid, accumulate=True)
             g = tp.grad_of(xs)[:, cur_off:cur_off + width]
             tp.gemm(0, 1, rows, width, nsn.nhid, xw.grad, nsn.nhid, W.data, nsn.nhid, g, xs.data.stride(0), accumulate=True)
         tp.ops.append(mm_bwd)
@@ -803,10 +809,13 @@ class PretrainStep:
         st.zero_grad()
         multi = self.dev.type == "cuda" and not _SINGLE_STREAM
         main = torch.cuda.current_stream(self.dev)
+        w0 = w1 = None
         if multi:
             if self._streams is None:
-                self._streams = (torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev))
-            s1, s2 = self._streams
+                self._streams = tuple(torch.cuda.Stream(self.dev) for _ in range(4))
+            s1, s2 = self._streams[:2]
+            if _WGRAD_STREAMS == "1" or (_WGRAD_STREAMS == "capture" and torch.cuda.is_current_stream_capturing()):
+                w0, w1 = self._streams[2:]   # weight-gradient side streams of the tapes on main / s1
         else:
             s1 = s2 = main
         cache = batch.__dict__.setdefault("_molsde_train_cache", {})
@@ -821,10 +830,10 @@ class PretrainStep:
 
         # ---- encoders: GIN on main, SchNet on s1
         fork(s1, main)
-        tp_g = Tape(self.dev)
+        tp_g = Tape(self.dev, w0)
         h2d = tape_gin(tp_g, self.gnn, st.vars("gnn"), batch.x, batch.edge_index, batch.edge_attr, cache, batch.batch, batch.num_graphs)
         with torch.cuda.stream(s1):
-            tp_s = Tape(self.dev)
+            tp_s = Tape(self.dev, w1)
             h3d = tape_schnet(tp_s, self.schnet, st.vars("schnet"), z, batch.positions, batch.batch, batch.num_graphs, cache)
         # ---- loss branches, each forward + backward on its own stream with private gradient tensors for h2d / h3d
         out = {}
@@ -847,7 +856,7 @@ class PretrainStep:
             cl2 = cl3 = None
         if self.c_23 > 0:
             with torch.cuda.stream(s1):
-                tp = Tape(self.dev)
+                tp = Tape(self.dev, w1)
                 x2 = Var(h2d.data, h2d.needs)
                 out["loss_2d3d"] = tape_2d3d(tp, self.m23, st.vars("sde2d3d"), x2, batch, self.anneal_power, draws.get("sde2d3d"),
                                              coef=self.c_23)
@@ -855,7 +864,7 @@ class PretrainStep:
                 keep += [tp, x2]
                 g2d.append(x2)
         if self.c_32 > 0:
-            tp = Tape(self.dev)
+            tp = Tape(self.dev, w0)
             x3 = Var(h3d.data, h3d.needs)
             out["loss_x"], out["loss_adj"] = tape_3d2d(tp, self.m32, st.vars("sde3d2d"), x3, batch, self.anneal_power,
                                                        draws.get("sde3d2d"), coef=0.5 * self.c_32)

@@ -8,6 +8,7 @@ gradients land in views of one flat buffer (the unit of the NCCL all-reduce and 
 """
 from __future__ import annotations
 
+from contextlib import contextmanager
 from typing import Callable, List, Optional
 
 import torch
@@ -71,12 +72,20 @@ def bucket_index(keys: torch.Tensor, size: int) -> Index:
 
 
 class Tape:
-    def __init__(self, device: torch.device):
+    def __init__(self, device: torch.device, wstream: Optional["torch.cuda.Stream"] = None):
+        """`wstream`: optional side stream for PARAMETER gradients.  In the backward pass only the input-gradient chain is
+        sequential; dW / db / table gradients are leaves of the dependency graph, so they are forked onto `wstream` (after the
+        main stream produced dy) and joined once at the end of `backward()` — under CUDA-graph replay they fill the SMs the
+        short dx kernels leave idle.  Operands the side kernels read are kept referenced until the join."""
         self.dev = device
         self.ops: List[Callable[[], None]] = []
         self.L = lib()
         self.launches = 0
-        self._s = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0  # one stream per tape
+        self._main = torch.cuda.current_stream(device) if device.type == "cuda" else None
+        self._s = self._main.cuda_stream if self._main is not None else 0  # one stream per tape (+ the optional wstream)
+        self._w = wstream if (wstream is not None and self._main is not None and wstream != self._main) else None
+        self._hold: list = []
+        self._w_used = False
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -117,9 +126,32 @@ class Tape:
             v.grad = torch.zeros(v.data.shape, dtype=torch.float32, device=self.dev)
         return v.grad
 
+    @contextmanager
+    def wgrad(self, *operands):
+        """Run the enclosed launches (a parameter-gradient leaf) on the side stream, ordered after everything issued so far on
+        the tape's stream.  `operands`: tensors read by those launches that could otherwise be freed before the join."""
+        if self._w is None:
+            yield
+            return
+        self._hold.extend(t for t in operands if t is not None)
+        self._w.wait_stream(self._main)
+        prev, self._s, self._w_used = self._s, self._w.cuda_stream, True
+        try:
+            with torch.cuda.stream(self._w):   # workspaces allocated inside come from the side stream's pool
+                yield
+        finally:
+            self._s = prev
+
+    def join(self) -> None:
+        if self._w_used:
+            self._main.wait_stream(self._w)
+            self._w_used = False
+        self._hold.clear()
+
     def backward(self) -> None:
         for fn in reversed(self.ops):
             fn()
+        self.join()
         self.ops.clear()
 
     # ------------------------------------------------------------------ dense ops
@@ -202,17 +234,18 @@ class Tape:
                     t = self.empty(M, Nout)
                     self.ew(2, dpre, rowscale, None, 1.0, t, cols=Nout)
                     dpre = t
-                if FUSED_DB and W.needs and b is not None and b.needs and Nout * K * M >= TC_MIN_WORK:
-                    # dW and db in one tensor-core GEMM (db = the product with an all-ones extra row)
-                    n = self.L.molsde_tc_gemm_ws_floats(Nout, K + 1, M)
-                    ws = self.empty(n) if n > 0 else None
-                    self._call(self.L.molsde_tc_gemm_dw_db, Nout, K, M, _p(dpre), 1, _ld(dpre), _p(x.data), 1, _ld(x.data), _p(W.grad),
-                               _ld(W.grad), _p(b.grad), 1, _p(ws), n, None, self.s, what="tc_gemm_dw_db")
-                else:
-                    if W.needs:
-                        self.gemm(1, 0, Nout, K, M, dpre, _ld(dpre), x.data, _ld(x.data), W.grad, _ld(W.grad), accumulate=True)
-                    if b is not None and b.needs:
-                        self.colsum(dpre, M, Nout, _ld(dpre), b.grad, accumulate=True)
+                with self.wgrad(dpre, x.data):
+                    if FUSED_DB and W.needs and b is not None and b.needs and Nout * K * M >= TC_MIN_WORK:
+                        # dW and db in one tensor-core GEMM (db = the product with an all-ones extra row)
+                        n = self.L.molsde_tc_gemm_ws_floats(Nout, K + 1, M)
+                        ws = self.empty(n) if n > 0 else None
+                        self._call(self.L.molsde_tc_gemm_dw_db, Nout, K, M, _p(dpre), 1, _ld(dpre), _p(x.data), 1, _ld(x.data),
+                                   _p(W.grad), _ld(W.grad), _p(b.grad), 1, _p(ws), n, None, self.s, what="tc_gemm_dw_db")
+                    else:
+                        if W.needs:
+                            self.gemm(1, 0, Nout, K, M, dpre, _ld(dpre), x.data, _ld(x.data), W.grad, _ld(W.grad), accumulate=True)
+                        if b is not None and b.needs:
+                            self.colsum(dpre, M, Nout, _ld(dpre), b.grad, accumulate=True)
                 if x_cols is not None:
                     if full.needs:
                         g = self.grad_of(full)[:, x_cols[0]:x_cols[1]]
@@ -247,7 +280,8 @@ class Tape:
                         return
                     dy = out.grad
                 if Wio.needs:
-                    self.gemm(1, 0, K, Nout, M, x.data, _ld(x.data), dy, _ld(dy), Wio.grad, _ld(Wio.grad), accumulate=True)
+                    with self.wgrad(dy, x.data):
+                        self.gemm(1, 0, K, Nout, M, x.data, _ld(x.data), dy, _ld(dy), Wio.grad, _ld(Wio.grad), accumulate=True)
                 if x.needs:
                     dx = self.empty(M, K)
                     self.gemm(0, 1, M, K, Nout, dy, _ld(dy), Wio.data, _ld(Wio.data), dx, K)
@@ -403,10 +437,11 @@ class Tape:
             dx, dyx = self.empty(M, D), self.empty(M, D)
             self._call(self.L.molsde_layernorm_bwd, _p(x.data), _p(out.grad), M, D, _p(g.data), _p(mean), _p(rstd), _p(dx), _p(dyx),
                        self.s, what="layernorm_bwd")
-            if g.needs:
-                self.colsum(dyx, M, D, D, g.grad, accumulate=True)
-            if b.needs:
-                self.colsum(out.grad, M, D, D, b.grad, accumulate=True)
+            with self.wgrad(dyx, out.grad):
+                if g.needs:
+                    self.colsum(dyx, M, D, D, g.grad, accumulate=True)
+                if b.needs:
+                    self.colsum(out.grad, M, D, D, b.grad, accumulate=True)
             self.accum(x, dx)
         self.ops.append(bwd)
         return out
@@ -461,7 +496,8 @@ class Tape:
             def bwd():
                 if out.grad is None:
                     return
-                self.seg_sum(out.grad, index, cols, T.grad, accumulate=True, row_div=F)
+                with self.wgrad(out.grad):
+                    self.seg_sum(out.grad, index, cols, T.grad, accumulate=True, row_div=F)
             self.ops.append(bwd)
         return out
 
@@ -481,12 +517,13 @@ class Tape:
                 dmsg = self.empty(E, cols)
                 self._call(self.L.molsde_gin_message_bwd, _p(x.data), _p(T.data), _p(ekeys), F, _p(src.idx), _p(tgt.idx), _p(out.grad),
                            E, cols, _p(dmsg), self.s, what="gin_message_bwd")
-                if T.needs:
-                    self.seg_sum(dmsg, ekey_index, cols, T.grad, accumulate=True, row_div=F)
-                if eps.needs:
-                    ws = self.empty(128, dtype=torch.float64)
-                    self._call(self.L.molsde_dot, _p(out.grad), _p(x.data), out.grad.numel(), 1.0, 1, _p(eps.grad), _p(ws), self.s,
-                               what="dot")
+                with self.wgrad(dmsg, out.grad, x.data):
+                    if T.needs:
+                        self.seg_sum(dmsg, ekey_index, cols, T.grad, accumulate=True, row_div=F)
+                    if eps.needs:
+                        ws = self.empty(128, dtype=torch.float64)
+                        self._call(self.L.molsde_dot, _p(out.grad), _p(x.data), out.grad.numel(), 1.0, 1, _p(eps.grad), _p(ws), self.s,
+                                   what="dot")
                 if x.needs:
                     dx = self.empty(N, cols)
                     self.seg_sum(dmsg, src, cols, dx)
@@ -557,10 +594,11 @@ class Tape:
             if out.grad is None:
                 return
             dy = out.grad
-            if Wp.needs:   # dW_g = dy_g^T x_g
-                self.gemm_batched(G, No, Ki, rows, dy, 1, G * No, No, x.data, 1, ldx, Ki, Wp.grad, Ki, No * Ki, accumulate=True)
-            if bp.needs:
-                self.colsum(dy, rows, G * No, G * No, bp.grad, accumulate=True)
+            with self.wgrad(dy, x.data):
+                if Wp.needs:   # dW_g = dy_g^T x_g
+                    self.gemm_batched(G, No, Ki, rows, dy, 1, G * No, No, x.data, 1, ldx, Ki, Wp.grad, Ki, No * Ki, accumulate=True)
+                if bp.needs:
+                    self.colsum(dy, rows, G * No, G * No, bp.grad, accumulate=True)
             if x.needs:    # dx_g = dy_g W_g
                 dx = self.empty(rows, G * Ki)
                 self.gemm_batched(G, rows, Ki, No, dy, G * No, 1, No, Wp.data, 1, Ki, No * Ki, dx, G * Ki, Ki)
@@ -582,7 +620,8 @@ class Tape:
                 return
             dy = out.grad
             if Wp.needs:   # dW_g [Fin,Fo] = x^T dy_g
-                self.gemm_batched(G, Fin, Fo, rows, x.data, 1, ldx, 0, dy, 1, G * Fo, Fo, Wp.grad, Fo, Fin * Fo, accumulate=True)
+                with self.wgrad(dy, x.data):
+                    self.gemm_batched(G, Fin, Fo, rows, x.data, 1, ldx, 0, dy, 1, G * Fo, Fo, Wp.grad, Fo, Fin * Fo, accumulate=True)
             if x.needs:    # dx = sum_g dy_g W_g^T : per-group products into a scratch, then a fixed-order sum over the groups
                 tmp = self.empty(G, rows, Fin)
                 self.gemm_batched(G, rows, Fin, Fo, dy, G * Fo, 1, Fo, Wp.data, Fo, 1, Fin * Fo, tmp, Fin, rows * Fin)

@@ -171,6 +171,32 @@ def test_fullsize_pretrain_step_properties():
     assert torch.equal(ps.store.grad, g1), "fixed draws -> bit-identical gradients (no atomics anywhere in the backward)"
     assert math.isfinite(l1) and abs(PretrainStep.total_loss(out) - l1) == 0.0
     assert any(not torch.equal(buf, running[n]) for n, buf in ps.gnn.named_buffers() if "running_mean" in n), "BN stats advance"
+
+    # the schedule bench.py replays -- the iteration captured as ONE CUDA graph, branches on three streams and the parameter
+    # gradients on their side streams (Tape.wgrad) -- must give the same bits as the eager launch order
+    def on_dev(x):
+        if torch.is_tensor(x):
+            return x.to(dev)
+        if isinstance(x, dict):
+            return {k: on_dev(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return type(x)(on_dev(v) for v in x)
+        return x
+    ddraws = on_dev(draws)
+    ps.forward_backward(b, ddraws)
+    torch.cuda.synchronize()
+    graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            ps.forward_backward(b, ddraws)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        ps.store.grad.fill_(float("nan"))
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(ps.store.grad, g1), "graph replay (multi-stream, side-stream weight gradients) == eager gradients"
+    del graph
     losses = []
     for _ in range(8):   # a fixed batch with fixed draws: Adam must drive the loss down
         o = ps.step(b, draws)
