@@ -230,14 +230,16 @@ def tape_2d3d(tp: Tape, model, P: Dict[str, Var], h2d: Var, data, anneal_power: 
     gfd, gfi, gfj = tp.empty(E, 64), tp.empty(E, 128), tp.empty(E, 128)
     emb = Var(tp.empty(E, 66), False)
     basis = tp.empty(E, 9)
-    tp._call(L.molsde_sde2d3d_edge_geom, ptr(pos_p), ptr(es.src.idx), ptr(es.tgt.idx), E, ptr(model.dist_gaussian_fourier.W.data),
+    has_dist = getattr(model, "has_distance_branch", True)
+    w_dist = model.dist_gaussian_fourier.W.data if has_dist else torch.zeros(32, dtype=torch.float32, device=dev)
+    tp._call(L.molsde_sde2d3d_edge_geom, ptr(pos_p), ptr(es.src.idx), ptr(es.tgt.idx), E, ptr(w_dist),
              ptr(model.coff_gaussian_fourier.W.data), ptr(gfd), ptr(gfi), ptr(gfj), ptr(emb.data), ptr(basis), s, what="edge_geom")
-    inv3d = tp.linear(Var(gfd), P["input_mlp.layers.0.weight"], P["input_mlp.layers.0.bias"])
+    inv3d = tp.linear(Var(gfd), P["input_mlp.layers.0.weight"], P["input_mlp.layers.0.bias"]) if has_dist else None
     tp.linear(Var(gfi), P["coff_mlp.weight"], P["coff_mlp.bias"], into=emb, col0=2)
     tp.linear(Var(gfj), P["coff_mlp.weight"], P["coff_mlp.bias"], into=emb, col0=2 + 32)
     hid = tp.linear(emb, P["project.layers.0.weight"], P["project.layers.0.bias"], act="silu")
     frame = tp.linear(hid, P["project.layers.1.weight"], P["project.layers.1.bias"])
-    edge_attr = tp.mul(inv3d, e2d, frame)
+    edge_attr = tp.mul(inv3d, e2d, frame) if has_dist else tp.add(e2d, frame)   # :372 (_02) / :181 (SDEModel2Dto3D_01)
     x = tp.linear(h2d, P["node_emb.layers.0.weight"], P["node_emb.layers.0.bias"])
 
     # ---- EquivariantScoreNetwork (equivariant_scorenetwork.py:121-169)

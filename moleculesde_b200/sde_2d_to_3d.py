@@ -143,6 +143,8 @@ def prepare_graph(edge_index: torch.Tensor, batch: torch.Tensor, num_graphs: int
 
 
 class SDEModel2Dto3D_02(nn.Module):
+    has_distance_branch = True   # dist_gaussian_fourier + input_mlp (`SDE_model_2D_to_3D.py:267-268`); False in SDEModel2Dto3D_01
+
     def __init__(self, emb_dim, hidden_dim, beta_schedule, beta_min, beta_max, num_diffusion_timesteps,
                  SDE_type="VE", short_cut=False, concat_hidden=False, use_extend_graph=False):
         super().__init__()
@@ -194,10 +196,16 @@ class SDEModel2Dto3D_02(nn.Module):
             blk[:, :out_f] = w.t()
             put(off, blk)
 
-        put(P_GFP_DIST_W, sd["dist_gaussian_fourier.W"])
         put(P_GFP_COFF_W, sd["coff_gaussian_fourier.W"])
-        put(P_IN_B, sd["input_mlp.layers.0.bias"])
-        put_kmajor(P_IN_W, sd["input_mlp.layers.0.weight"], LD32)
+        if self.has_distance_branch:
+            put(P_GFP_DIST_W, sd["dist_gaussian_fourier.W"])
+            put(P_IN_B, sd["input_mlp.layers.0.bias"])
+            put_kmajor(P_IN_W, sd["input_mlp.layers.0.weight"], LD32)
+        else:
+            # SDEModel2Dto3D_01: edge_attr = edge_attr_2D + frame (:181).  The kernels compute (W_in gfp(d) + b_in) * e2d + frame
+            # with one fused multiply-add; zero frequencies / weights and a unit bias make the factor exactly 1.0f, so the
+            # result is the same single-rounded sum.
+            put(P_IN_B, torch.ones(self.hidden_dim, dtype=torch.float32, device=dev))
         # coff_mlp is a bare Linear feeding project.layers.0 (SDE_model_2D_to_3D.py:297-304,429-430): fold it in
         # (float64 products, rounded once) so the hidden layer accumulates straight from the Fourier features.
         H = self.hidden_dim
@@ -420,3 +428,16 @@ class SDEModel2Dto3D_02(nn.Module):
                                          ptr(score), ptr(scratch), scratch.numel(), ptr(prep.status), stream_ptr(pos)),
               "sde2d3d_score")
         return score
+
+
+class SDEModel2Dto3D_01(SDEModel2Dto3D_02):
+    """`SDE_model_2D_to_3D.py:69-250`: the variant without the distance branch (`edge_attr = edge_attr_2D + frame`, :181) that
+    several published checkpoints were trained with (`README_checkpoints.md`).  Same constructor, `forward` / `get_score`
+    signatures and state_dict keys as the reference class (no `dist_gaussian_fourier.*` / `input_mlp.*` entries); runs on the
+    same kernels as `_02` with the multiplicative factor pinned to 1."""
+    has_distance_branch = False
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        del self.dist_gaussian_fourier
+        del self.input_mlp

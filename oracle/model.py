@@ -153,9 +153,11 @@ def edge_features_2d3d(sd, e2d: Tensor, ei: Tensor, pos: Tensor):
     """Per-edge geometric pipeline shared by forward and get_score,
     `SDE_model_2D_to_3D.py:342-372` == `:402-432`.  Returns (edge_attr [E,32], basis 3x[E,3])."""
     row, col = ei
-    d = (pos[row] - pos[col]).norm(dim=-1).unsqueeze(-1)  # get_perturb_distance :50-54
-    d_emb = gaussian_fourier(sd["dist_gaussian_fourier.W"], d)  # :349
-    inv3d = mlp(sd, "input_mlp", d_emb, F.silu)  # :350 (single layer)
+    has_dist = "input_mlp.layers.0.weight" in sd  # SDEModel2Dto3D_01 (:69-250) has no distance branch
+    if has_dist:
+        d = (pos[row] - pos[col]).norm(dim=-1).unsqueeze(-1)  # get_perturb_distance :50-54
+        d_emb = gaussian_fourier(sd["dist_gaussian_fourier.W"], d)  # :349
+        inv3d = mlp(sd, "input_mlp", d_emb, F.silu)  # :350 (single layer)
     coord_diff, coord_cross, coord_vertical = coord2basis(pos, row, col)  # :353
     edge_basis = torch.cat([coord_diff.unsqueeze(1), coord_cross.unsqueeze(1), coord_vertical.unsqueeze(1)], dim=1)
     r_i, r_j = pos[row], pos[col]
@@ -176,7 +178,7 @@ def edge_features_2d3d(sd, e2d: Tensor, ei: Tensor, pos: Tensor):
 
     edge_embed = torch.cat([pseudo_angle, get_embedding(coff_i), get_embedding(coff_j)], dim=-1)  # :369
     frame_inv = mlp(sd, "project", edge_embed, F.silu)  # :370
-    edge_attr = inv3d * e2d + frame_inv  # :372
+    edge_attr = inv3d * e2d + frame_inv if has_dist else e2d + frame_inv  # :372 (_02) / :181 (_01)
     return edge_attr, (coord_diff, coord_cross, coord_vertical)
 
 

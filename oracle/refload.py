@@ -38,10 +38,12 @@ def load():
     ns = types.SimpleNamespace()
     from Geom3D.models import SchNet, GNN
     from Geom3D.models.MoleculeSDE import SDEModel2Dto3D_02, SDEModel3Dto2D_node_adj_dense
+    from Geom3D.models.MoleculeSDE.SDE_model_2D_to_3D import SDEModel2Dto3D_01
     from Geom3D.models.MoleculeSDE import SDE_sparse, SDE_dense
     from Geom3D.datasets.dataset_3D import extend_graph
     ns.SchNet, ns.GNN = SchNet, GNN
     ns.SDEModel2Dto3D_02 = SDEModel2Dto3D_02
+    ns.SDEModel2Dto3D_01 = SDEModel2Dto3D_01
     ns.SDEModel3Dto2D_node_adj_dense = SDEModel3Dto2D_node_adj_dense
     ns.SDE_sparse, ns.SDE_dense = SDE_sparse, SDE_dense
     ns.extend_graph = extend_graph

@@ -1,0 +1,216 @@
+"""the `SDEModel2Dto3D_01` sibling, the noise-schedule presets (VE02 / VP02 / VE03 / VP03) and the
+reference checkpoint layout -- oracle and host checks on the CPU, the CUDA path (`-m gpu`) against the outputs of the
+unmodified reference (`tests/golden/make_golden_variants.py` -> `golden_variants.pt`)."""
+import os
+
+import pytest
+import torch
+
+from conftest import sd_from_manifest
+from oracle import model as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REL_TOL = 1e-4   # north_star: fp32, max-norm relative
+
+
+@pytest.fixture(scope="module")
+def gv():
+    return torch.load(os.path.join(HERE, "golden", "golden_variants.pt"), weights_only=False)
+
+
+def _draws(sec):
+    d = sec["train_draws"]
+    assert [k for k, _ in d] == ["randn", "randint"] + ["dropout"] * 8
+    masks = [v for _, v in d[2:]]
+    return {"noise": d[0][1], "time_step": d[1][1], "dropout": [(masks[2 * i], masks[2 * i + 1]) for i in range(4)]}
+
+
+# ----------------------------------------------------------------------------------------------- CPU: oracle + host
+def test_oracle_01_score_and_loss(gv, golden, golden_batch):
+    _, batch = golden_batch
+    h2d = golden["gnn"]["h_eval"]
+    for kind in ("VE", "VP"):
+        sec = gv["sde2d3d_01_" + kind]
+        assert not any(k.startswith(("input_mlp", "dist_gaussian_fourier")) for k in sec["manifest"])
+        sd = sd_from_manifest(sec["manifest"], gv["meta"]["weight_seed"])
+        sde = O.make_sde(kind, 0.2, 1.0, 1000)
+        s = O.get_score_2d3d(sd, sde, h2d, batch.extended_edge_index, gv["inputs"]["pos_perturbed"], gv["inputs"]["t"])
+        torch.testing.assert_close(s, sec["score"], rtol=1e-4, atol=1e-5)
+        dr = _draws(sec)
+        stats = {}
+        loss = O.loss_2d3d(sd, sde, sec["train_h2d"], batch.extended_edge_index, batch.positions, batch.batch, batch.num_graphs,
+                           dr["noise"], dr["time_step"], 1000, 0.0, dr["dropout"], True, stats)
+        torch.testing.assert_close(loss, sec["train_loss"], rtol=2e-5, atol=2e-6)
+        torch.testing.assert_close(stats["running_mean"], sec["bn_running_mean"], rtol=2e-5, atol=2e-6)
+
+
+def test_oracle_schedule_presets(gv, golden, golden_batch):
+    from moleculesde_b200.checkpoint import resolve_sde_type
+    _, batch = golden_batch
+    sd = sd_from_manifest(golden["manifest"]["sde2d3d"], golden["meta"]["weight_seed"])
+    for name in ("VE02", "VP02", "VE03", "VP03"):
+        sec = gv["preset_" + name]
+        kind, lo, hi, n = resolve_sde_type(name, "2Dto3D")
+        assert (kind, lo, hi, n) == (sec["kind"], sec["beta_min"], sec["beta_max"], 1000)
+        s = O.get_score_2d3d(sd, O.make_sde(kind, lo, hi, n), golden["gnn"]["h_eval"], batch.extended_edge_index,
+                             sec["pos_perturbed"], gv["inputs"]["t"])
+        err = float((s - sec["score"]).abs().max() / sec["score"].abs().max())
+        assert err <= 1e-5, (name, err)   # same fp32 op order as the reference on the same CPU: agrees to rounding
+
+
+def test_preset_tables_match_reference_script():
+    """pretrain_MoleculeSDE.py:226-256 (2D->3D) and :272-302 (3D->2D)."""
+    from moleculesde_b200.checkpoint import resolve_sde_type
+    want23 = {"VE": ("VE", 0.2, 1.0), "VP": ("VP", 0.2, 1.0), "VE02": ("VE", 0.1, 10.0), "VP02": ("VP", 0.2, 30.0),
+              "VE03": ("VE", 0.1, 1000.0), "VP03": ("VP", 0.2, 1000.0)}
+    want32 = {"VE": ("VE", 0.1, 1.0), "VP": ("VP", 0.2, 1.0), "VE02": ("VE", 0.1, 10.0), "VP02": ("VP", 0.1, 30.0),
+              "VE03": ("VE", 0.1, 1000.0), "VP03": ("VP", 0.1, 1000.0)}
+    for k, v in want23.items():
+        assert resolve_sde_type(k, "2Dto3D") == v + (1000,)
+    for k, v in want32.items():
+        assert resolve_sde_type(k, "3Dto2D") == v + (1000,)
+    with pytest.raises(NotImplementedError):
+        resolve_sde_type("discrete_VE", "2Dto3D")
+
+
+def test_01_state_dict_and_checkpoint_roundtrip(gv, golden, tmp_path):
+    from moleculesde_b200 import checkpoint as C
+    models = C.build_models(SDE_2Dto3D_model="SDEModel2Dto3D_01", SDE_type_2Dto3D="VP02", SDE_type_3Dto2D="VE02")
+    sd = models["SDE_2Dto3D_model"].state_dict()
+    man = gv["sde2d3d_01_VE"]["manifest"]
+    assert list(sd.keys()) == list(man.keys()), "same keys in the same order as the reference class"
+    assert all(tuple(sd[k].shape) == man[k][0] for k in man)
+    assert models["SDE_2Dto3D_model"].sde_pos.beta_1 == 30.0 and models["SDE_3Dto2D_model"].sde_adj.sigma_max == 10.0
+    for key, mname in (("model_2D", "gnn"), ("model_3D", "schnet"), ("SDE_3Dto2D_model", "sde3d2d")):
+        assert list(models[key].state_dict().keys()) == list(golden["manifest"][mname].keys())
+    path = C.save_model(models, str(tmp_path), save_best=True)
+    assert path.endswith("model_complete.pth")
+    assert C.save_model(models, str(tmp_path), save_best=False).endswith("model_complete_final.pth")
+    blob = torch.load(path, weights_only=True)
+    assert tuple(blob.keys()) == C.KEYS
+    loaded = C.load_model(path, SDE_type_2Dto3D="VP02", SDE_type_3Dto2D="VE02")   # variant picked from the keys in the file
+    assert type(loaded["SDE_2Dto3D_model"]).__name__ == "SDEModel2Dto3D_01"
+    for k in C.KEYS:
+        a, b = models[k].state_dict(), loaded[k].state_dict()
+        assert all(torch.equal(a[n], b[n]) for n in a)
+    # a _02 file builds the _02 class; loading it into _01 is a key error (strict, as torch's load_state_dict in the reference)
+    m02 = C.build_models()
+    p02 = C.save_model(m02, str(tmp_path / "b"))
+    assert type(C.load_model(p02)["SDE_2Dto3D_model"]).__name__ == "SDEModel2Dto3D_02"
+    with pytest.raises(RuntimeError):
+        C.load_model(p02, models=models)
+
+
+@pytest.mark.reference
+def test_checkpoint_loads_into_reference_classes(tmp_path):
+    """A checkpoint written here loads (strict) into the unmodified reference modules, and back."""
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("needs /root/reference (build container only)")
+    from moleculesde_b200 import checkpoint as C
+    R = refload.load()
+    ours = C.build_models(SDE_2Dto3D_model="SDEModel2Dto3D_01")
+    blob = torch.load(C.save_model(ours, str(tmp_path)), weights_only=True)
+    ref23 = R.SDEModel2Dto3D_01(emb_dim=300, hidden_dim=32, beta_schedule=None, beta_min=0.2, beta_max=1.0,
+                                num_diffusion_timesteps=1000, SDE_type="VE", use_extend_graph=True)
+    ref23.load_state_dict(blob["SDE_2Dto3D_model"], strict=True)
+    R.GNN(5, 300, JK="last", drop_ratio=0.0, gnn_type="GIN").load_state_dict(blob["model_2D"], strict=True)
+    R.SchNet(hidden_channels=300, num_filters=128, num_interactions=6, num_gaussians=51, cutoff=10, readout="mean",
+             node_class=119).load_state_dict(blob["model_3D"], strict=True)
+    ours["SDE_2Dto3D_model"].load_state_dict(ref23.state_dict(), strict=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU: CUDA path
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _model01(gv, kind, dev):
+    from moleculesde_b200.sde_2d_to_3d import SDEModel2Dto3D_01
+    m = SDEModel2Dto3D_01(emb_dim=300, hidden_dim=32, beta_schedule=None, beta_min=0.2, beta_max=1.0,
+                          num_diffusion_timesteps=1000, SDE_type=kind, use_extend_graph=True)
+    m.load_state_dict(sd_from_manifest(gv["sde2d3d_01_" + kind]["manifest"], gv["meta"]["weight_seed"]))
+    return m.to(dev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["VE", "VP"])
+def test_gpu_01_get_score_and_eval_loss(kind, gv, golden, golden_batch):
+    from test_gpu_sde2d3d import _gpu_batch, assert_parity
+    dev = _dev()
+    _, batch = golden_batch
+    sec = gv["sde2d3d_01_" + kind]
+    m = _model01(gv, kind, dev).eval()
+    b = _gpu_batch(batch, dev)
+    h2d = golden["gnn"]["h_eval"].to(dev)
+    score = m.get_score(h2d, b, gv["inputs"]["pos_perturbed"].to(dev), None, gv["inputs"]["t"].to(dev))
+    assert_parity(score, sec["score"], f"SDEModel2Dto3D_01.get_score[{kind}] vs reference")
+    # train-mode loss value through the fused persistent kernel (no autograd), recorded draws
+    m.train()
+    with torch.no_grad():
+        loss = m(sec["train_h2d"].to(dev), b, 0, draws=_draws(sec))["position"]
+    ref = float(sec["train_loss"])
+    assert abs(float(loss) - ref) <= REL_TOL * abs(ref), (float(loss), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["VE", "VP"])
+def test_gpu_01_training_gradients(kind, gv, golden, golden_batch):
+    from moleculesde_b200.pretrain import ParamStore, tape_2d3d
+    from moleculesde_b200.tape import Tape, Var
+    from test_gpu_pretrain import check_grad_summary
+    from test_gpu_sde2d3d import _gpu_batch, assert_parity
+    dev = _dev()
+    _, batch = golden_batch
+    sec = gv["sde2d3d_01_" + kind]
+    m = _model01(gv, kind, dev).train()
+    store = ParamStore({"sde2d3d": m}, dev)
+    b = _gpu_batch(batch, dev)
+    tp = Tape(dev)
+    h2d = Var(sec["train_h2d"].to(dev).contiguous(), True)
+    loss = tape_2d3d(tp, m, store.vars("sde2d3d"), h2d, b, 0.0, _draws(sec))
+    ref = float(sec["train_loss"])
+    assert abs(float(loss) - ref) <= REL_TOL * abs(ref), (float(loss), ref)
+    tp.backward()
+    torch.cuda.synchronize()
+    assert_parity(h2d.grad, sec["d_h2d"], "d loss / d node_2D_repr")
+    gmax = max(float(w["norm"]) for w in sec["grads"].values() if w is not None)
+    bad = []
+    for name, want in sec["grads"].items():
+        if want is None:
+            continue
+        got = store.grad_view("sde2d3d", name)
+        if name == "edge_2D_emb.0.bias" or name.endswith("lin_key.bias"):   # analytically zero (see test_gpu_pretrain)
+            assert float(want["norm"]) <= 1e-6 * gmax and float(got.norm()) <= 1e-6 * gmax, name
+            continue
+        try:
+            check_grad_summary(got, want, name)
+        except AssertionError as e:
+            bad.append(str(e))
+    assert not bad, "\n".join(bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["VE02", "VP02", "VE03", "VP03"])
+def test_gpu_schedule_presets(name, gv, golden, golden_batch):
+    from moleculesde_b200.checkpoint import resolve_sde_type
+    from moleculesde_b200.sde_2d_to_3d import SDEModel2Dto3D_02
+    from test_gpu_sde2d3d import _gpu_batch
+    dev = _dev()
+    _, batch = golden_batch
+    sec = gv["preset_" + name]
+    kind, lo, hi, n = resolve_sde_type(name, "2Dto3D")
+    m = SDEModel2Dto3D_02(emb_dim=300, hidden_dim=32, beta_schedule=None, beta_min=lo, beta_max=hi, num_diffusion_timesteps=n,
+                          SDE_type=kind, use_extend_graph=True)
+    m.load_state_dict(sd_from_manifest(golden["manifest"]["sde2d3d"], golden["meta"]["weight_seed"]))
+    m = m.to(dev).eval()
+    b = _gpu_batch(batch, dev)
+    score = m.get_score(golden["gnn"]["h_eval"].to(dev), b, sec["pos_perturbed"].to(dev), None, gv["inputs"]["t"].to(dev))
+    assert torch.isfinite(score).all()
+    err = float((score.cpu() - sec["score"]).abs().max() / sec["score"].abs().max())
+    # VE03 (sigma up to 1000): |pos| ~ 1e3 A puts the Fourier arguments at ~1e4 rad, where ONE fp32 ulp of the argument is
+    # ~1e-3 rad -- any two fp32 implementations (torch CPU vs CUDA included) differ at that level; stated, not hidden
+    tol = 2e-3 if name == "VE03" else REL_TOL
+    assert err <= tol, (name, err)
