@@ -320,6 +320,12 @@ int molsde_gin_message_bwd(const float* x, const float* T, const int32_t* ekeys,
 /* GaussianSmearing ea [E,ng] and cosine cutoff C [E] of the radius edges (schnet.py:93,186,205-207) */
 int molsde_schnet_edge_feat(const float* pos, const int32_t* src, const int32_t* tgt, int64_t E, const float* mu, int32_t ng,
                             float coeff, float cutoff, float* ea, float* C, void* stream);
+/* Backward of molsde_schnet_edge_feat towards the positions (the reference obtains forces as -dE/dpos through autograd,
+ * examples/finetune_MD17.py:66): g[e,:] = (sum_k dea[e,k] d ea[e,k]/dd + dC[e] dC/dd) * (pos[src]-pos[tgt]) / d, the contribution
+ * of edge e to d loss / d pos[src] (and, negated, to d pos[tgt]); dC may be NULL.  molsde_rowdot: out[r] (+)= <a[r,:], b[r,:]>. */
+int molsde_schnet_edge_feat_bwd(const float* pos, const int32_t* src, const int32_t* tgt, int64_t E, const float* mu, int32_t ng,
+                                float coeff, float cutoff, const float* ea, const float* dea, const float* dC, float* g, void* stream);
+int molsde_rowdot(const float* a, const float* b, int64_t rows, int32_t cols, int32_t accumulate, float* out, void* stream);
 /* backward of molsde_ebm_node_dot's loss_acc[0] scaled by coef; invperm = inverse permutation of perm */
 int molsde_ebm_node_dot_bwd(const float* X, const float* Y, const int64_t* perm, const int64_t* invperm, const float* pred_pos,
                             const float* pred_neg, int64_t N, int32_t D, float T, float coef, int32_t accumulate, float* dX, float* dY,

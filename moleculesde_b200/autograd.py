@@ -50,6 +50,11 @@ class _TapeFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *gouts):
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("moleculesde_b200: this forward was already back-propagated once; the kernel tape frees its "
+                               "intermediates in the reverse sweep (retain_graph / double backward are not supported -- run the "
+                               "forward again)")
+        ctx.consumed = True
         ctx.seed([None if g is None else g.detach().float().contiguous() for g in gouts])
         ctx.tp.backward()
         gin = []

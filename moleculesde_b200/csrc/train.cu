@@ -335,6 +335,48 @@ __global__ void schnet_edge_feat_kernel(const float* __restrict__ pos, const int
     if (k == 0) C[e] = 0.5f * (cosf(d * 3.14159274101257324f / cutoff) + 1.0f);
 }
 
+// ---- d/d pos of the SchNet edge features (finetune_MD17.py:66: force = -dE/dpos) ----
+// row-wise dot, one warp per row, fixed shuffle order:  out[r] (+)= sum_c a[r,c] * b[r,c]      (d C[e] = <dWf[e,:], f2[e,:]>)
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t rows, int cols, int accumulate, float* __restrict__ out) {
+    const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float* ar = a + r * cols;
+    const float* br = b + r * cols;
+    float acc = 0.0f;
+    for (int c = lane; c < cols; c += 32) acc = fmaf(ar[c], br[c], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[r] = accumulate ? out[r] + acc : acc;
+}
+// per edge e = (src -> tgt), d = |pos[src] - pos[tgt]|:
+//   dd = sum_k dea[e,k] * ea[e,k] * 2 coeff (d - mu_k)  +  dC[e] * (-pi / (2 cutoff)) sin(pi d / cutoff)
+//   g[e,:] = dd * (pos[src] - pos[tgt]) / d      (= d loss / d pos[src] of this edge; d pos[tgt] gets -g)
+// one warp per edge; the k-sum is a fixed-order shuffle reduction (deterministic).
+__global__ void __launch_bounds__(256)
+schnet_edge_feat_bwd_kernel(const float* __restrict__ pos, const int32_t* __restrict__ src, const int32_t* __restrict__ tgt, int64_t E,
+                            const float* __restrict__ mu, int ng, float coeff, float cutoff, const float* __restrict__ ea,
+                            const float* __restrict__ dea, const float* __restrict__ dC, float* __restrict__ g) {
+    const int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= E) return;
+    const int r = src[e], c = tgt[e];
+    const float dx = __fsub_rn(pos[3 * r], pos[3 * c]), dy = __fsub_rn(pos[3 * r + 1], pos[3 * c + 1]),
+                dz = __fsub_rn(pos[3 * r + 2], pos[3 * c + 2]);
+    const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    float acc = 0.0f;
+    for (int k = lane; k < ng; k += 32) acc = fmaf(dea[e * ng + k] * ea[e * ng + k], 2.0f * coeff * (d - mu[k]), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        const float w = 3.14159274101257324f / cutoff;
+        const float dd = acc + (dC ? dC[e] * (-0.5f * w * sinf(d * w)) : 0.0f);
+        const float s = d > 0.0f ? dd / d : 0.0f;   // coincident atoms: the norm's subgradient 0, as torch's norm backward
+        g[3 * e] = s * dx; g[3 * e + 1] = s * dy; g[3 * e + 2] = s * dz;
+    }
+}
+
 // ---- EBM_node_dot_prod backward (examples/util.py:52-68): loss = mean softplus(-pp) + mean softplus(pn) ----
 //   dX[r] (+)= coef/(N T) * (-sigmoid(-pp_r) Y[r] + sigmoid(pn_r) Y[perm[r]])
 //   dY[r] (+)= coef/(N T) * (-sigmoid(-pp_r) X[r] + sigmoid(pn_q) X[q]),  q = invperm[r]
@@ -687,6 +729,19 @@ int molsde_schnet_edge_feat(const float* pos, const int32_t* src, const int32_t*
     if (E == 0) return MOLSDE_OK;
     schnet_edge_feat_kernel<<<blocks_for(E * ng), 256, 0, as_stream(stream)>>>(pos, src, tgt, E, mu, ng, coeff, cutoff, ea, C);
     return check_launch("schnet_edge_feat");
+}
+int molsde_rowdot(const float* a, const float* b, int64_t rows, int32_t cols, int32_t accumulate, float* out, void* stream) {
+    if (!a || !b || !out || rows < 0 || cols <= 0) return MOLSDE_ERR_INVALID;
+    if (rows == 0) return MOLSDE_OK;
+    rowdot_kernel<<<blocks_for(rows, 8), 256, 0, as_stream(stream)>>>(a, b, rows, cols, accumulate, out);
+    return check_launch("rowdot");
+}
+int molsde_schnet_edge_feat_bwd(const float* pos, const int32_t* src, const int32_t* tgt, int64_t E, const float* mu, int32_t ng,
+                                float coeff, float cutoff, const float* ea, const float* dea, const float* dC, float* g, void* stream) {
+    if (!pos || !src || !tgt || !mu || !ea || !dea || !g || E < 0 || ng <= 0) return MOLSDE_ERR_INVALID;
+    if (E == 0) return MOLSDE_OK;
+    schnet_edge_feat_bwd_kernel<<<blocks_for(E, 8), 256, 0, as_stream(stream)>>>(pos, src, tgt, E, mu, ng, coeff, cutoff, ea, dea, dC, g);
+    return check_launch("schnet_edge_feat_bwd");
 }
 int molsde_ebm_node_dot_bwd(const float* X, const float* Y, const int64_t* perm, const int64_t* invperm, const float* pred_pos,
                             const float* pred_neg, int64_t N, int32_t D, float T, float coef, int32_t accumulate, float* dX, float* dY,

@@ -393,13 +393,16 @@ def tape_gin(tp: Tape, model, P: Dict[str, Var], x: torch.Tensor, edge_index: to
 # SchNet (Geom3D/models/schnet.py:85-125), return_latent representation
 # ======================================================================================================
 def tape_schnet(tp: Tape, model, P: Dict[str, Var], z: torch.Tensor, pos: torch.Tensor, batch: torch.Tensor, num_graphs: int,
-                cache: Optional[dict]) -> Var:
-    """Node representation h [N, hidden] of SchNet.forward(return_latent=True) with every intermediate kept."""
+                cache: Optional[dict], pos_var: Optional[Var] = None) -> Var:
+    """Node representation h [N, hidden] of SchNet.forward(return_latent=True) with every intermediate kept.
+    `pos_var` (a Var over `pos` with needs=True): also differentiate with respect to the positions -- GaussianSmearing and the
+    cosine cutoff are functions of the edge length -- which is how the reference obtains forces (`finetune_MD17.py:66`)."""
     from .graph import radius_graph
     from .tape import bucket_index
     L, dev = tp.L, pos.device
     require_device(pos)
     pos = pos.detach().float().contiguous()
+    need_pos = pos_var is not None and pos_var.needs
     cache = cache if cache is not None else {}
     if "schnet" not in cache:  # positions are static during pretraining: the radius graph is built once per batch
         csr = radius_graph(pos, model.cutoff, batch, num_graphs, want_edge_index=False)
@@ -415,12 +418,29 @@ def tape_schnet(tp: Tape, model, P: Dict[str, Var], z: torch.Tensor, pos: torch.
         cache["schnet"] = (es, zkeys, zidx, ea, C)
     es, zkeys, zidx, ea, C = cache["schnet"]
     h = tp.embed_sum(P["embedding.weight"], zkeys, zidx)
-    ea_v = Var(ea)
+    ea_v = Var(ea, need_pos)
+    C_v = Var(C[:es.E], need_pos)
+    if need_pos:
+        N, E = es.N, es.E
+
+        def pos_bwd():   # recorded first => runs last, after every interaction added its share to d ea / d C
+            if ea_v.grad is None or E == 0:
+                return
+            g = tp.empty(E, 3)
+            tp._call(L.molsde_schnet_edge_feat_bwd, ptr(pos), ptr(es.src.idx), ptr(es.tgt.idx), E, ptr(model.distance_expansion.offset),
+                     model.num_gaussians, float(model.distance_expansion.coeff), float(model.cutoff), ptr(ea), ptr(ea_v.grad),
+                     _p(C_v.grad), ptr(g), tp.s, what="schnet_edge_feat_bwd")
+            dpos, dneg = tp.empty(N, 3), tp.empty(N, 3)
+            tp.seg_sum(g, es.src, 3, dpos)                    # edges leaving the atom: + g
+            tp.seg_sum(g, es.tgt, 3, dneg)                    # edges arriving at the atom: - g
+            tp.ew(0, dpos, dneg, None, -1.0, dpos)
+            tp.accum(pos_var, dpos)
+        tp.ops.append(pos_bwd)
     for i in range(model.num_interactions):
         pf = f"interactions.{i}."
         f1 = tp.linear(ea_v, P[pf + "mlp.0.weight"], P[pf + "mlp.0.bias"], act="ssp")
         f2 = tp.linear(f1, P[pf + "mlp.2.weight"], P[pf + "mlp.2.bias"])
-        Wf = tp.rowscale(f2, C)
+        Wf = tp.rowscale_var(f2, C_v) if need_pos else tp.rowscale(f2, C)
         x = tp.linear(h, P[pf + "conv.lin1.weight"], None)
         agg = tp.edge_mul_reduce(x, Wf, es.rowptr, es.src, es.tgt)
         t = tp.linear(agg, P[pf + "conv.lin2.weight"], P[pf + "conv.lin2.bias"], act="ssp")

@@ -128,17 +128,26 @@ class SchNet(nn.Module):
         batch = torch.zeros_like(z) if batch is None else batch
         num_graphs = int(batch[-1].item()) + 1 if batch.numel() else 0
         from . import autograd as AG
-        if self.training and AG.grad_mode(self):
+        if (self.training and AG.grad_mode(self)) or (torch.is_grad_enabled() and pos.requires_grad):
             from .pretrain import tape_schnet
+            node_ptr = segment_ptr(batch, num_graphs)
+            row2seg = batch.to(torch.int32).contiguous()
+            mean = self.readout == "mean"
 
             def build(tp, ins, P):
-                h = tape_schnet(tp, self, P, z.contiguous(), pos, batch, num_graphs, {})
+                pv = ins[0] if ins else None
+                h = tape_schnet(tp, self, P, z.contiguous(), pos, batch, num_graphs, {}, pos_var=pv)
+                out = tp.segment_readout(h, node_ptr, row2seg, mean)                   # :115, differentiable
+                if self.scale is not None:
+                    raise NotImplementedError("SchNet.scale with gradients (unused by the reference scripts)")
 
-                def seed(gouts):
-                    h.grad = gouts[0]
-                return [h.data], seed
-            h = AG.apply(self, build, [])
-            out = segment_reduce(h.detach(), segment_ptr(batch, num_graphs), mean=(self.readout == "mean"))   # :115 (not differentiated)
+                def seed(gouts):   # torch's grad_outputs for (out, h); either may be absent
+                    out.grad = gouts[0]
+                    h.grad = None if gouts[1] is None else gouts[1].clone()   # the readout backward accumulates into it in place
+                return [out.data, h.data], seed
+            # positions take part in autograd only when the caller asked for it (`positions.requires_grad_()`, finetune_MD17.py:49):
+            # first-order forces -dE/dpos; `create_graph=True` (a force term inside the training loss) is not supported
+            out, h = AG.apply(self, build, [pos] if pos.requires_grad else [])
             return (out, h) if return_latent else out
         with torch.no_grad():
             return self._forward_inference(z, pos, batch, num_graphs, return_latent)

@@ -573,6 +573,52 @@ class Tape:
             self.ops.append(bwd)
         return out
 
+    def rowscale_var(self, x: Var, r: Var) -> Var:
+        """y[row,:] = x[row,:] * r[row] where the per-row factor is differentiable too: d r[row] = <dy[row,:], x[row,:]>
+        (the cosine cutoff C(d) of CFConv when forces are wanted, schnet.py:187-188)."""
+        rows, cols = x.data.shape
+        y = self.empty(rows, cols)
+        self.ew(2, x.data, r.data, None, 1.0, y, cols=cols)
+        out = Var(y, x.needs or r.needs)
+        if out.needs:
+            def bwd():
+                if out.grad is None:
+                    return
+                if r.needs:
+                    if r.grad is None:
+                        r.grad = self.empty(rows)
+                        acc = 0
+                    else:
+                        acc = 1
+                    self._call(self.L.molsde_rowdot, _p(out.grad), _p(x.data), rows, cols, acc, _p(r.grad), self.s, what="rowdot")
+                if x.needs:
+                    g = self.empty(rows, cols)
+                    self.ew(2, out.grad, r.data, None, 1.0, g, cols=cols)
+                    self.accum(x, g)
+            self.ops.append(bwd)
+        return out
+
+    def segment_readout(self, x: Var, seg_ptr: torch.Tensor, row2seg: torch.Tensor, mean: bool) -> Var:
+        """out[g,:] = sum (or mean) of the rows of segment g (`scatter(h, batch, reduce=readout)`, schnet.py:115); `row2seg` int32 [rows]."""
+        rows, cols = x.data.shape
+        segs = seg_ptr.numel() - 1
+        y = self.empty(segs, cols)
+        self._call(self.L.molsde_segment_reduce, _p(x.data), _p(seg_ptr), segs, cols, int(mean), _p(y), self.s, what="segment_reduce")
+        out = Var(y, x.needs)
+        if x.needs:
+            def bwd():
+                if out.grad is None:
+                    return
+                g = self.empty(rows, cols)
+                self._call(self.L.molsde_gather_pair, _p(out.grad), _p(row2seg), None, None, rows, cols, _p(g), self.s, what="gather_pair")
+                if mean:
+                    cnt = (seg_ptr[1:] - seg_ptr[:-1]).clamp_min(1).float()
+                    inv = (1.0 / cnt)[row2seg.long()].contiguous()   # [rows] bookkeeping
+                    self.ew(2, g, inv, None, 1.0, g, cols=cols)
+                self.accum(x, g)
+            self.ops.append(bwd)
+        return out
+
     # ------------------------------------------------------------------ batched small GEMMs (per-channel layers)
     def gemm_batched(self, batch, M, N, K, A, sam, sak, bsA, B, sbn, sbk, bsB, C, ldc, bsC, bias=None, bsBias=0, accumulate=False):
         n = self.L.molsde_tc_gemm_batched_ws_floats(batch, M, N, K)

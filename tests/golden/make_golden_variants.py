@@ -86,6 +86,25 @@ def main():
         out["preset_" + name] = {"kind": kind, "beta_min": bmin, "beta_max": bmax, "pos_perturbed": pp,
                                  "score": m.get_score(h2d, batch, pp, None, t).detach()}
         print(name, "|score|", float(out["preset_" + name]["score"].norm()), "max |pos|", float(pp.abs().max()))
+    # ---- SchNet energy head + forces (finetune_MD17.py:49-66): E_g = <readout(h)_g, w>, F = -dE/dpos through torch.autograd
+    sch = R.SchNet(hidden_channels=300, num_filters=128, num_interactions=6, num_gaussians=51, cutoff=10, readout="mean",
+                   node_class=119)
+    sch.load_state_dict(fill_state_dict(sch.state_dict(), WEIGHT_SEED))
+    sch.train()
+    gw = torch.Generator().manual_seed(NOISE_SEED + 43)
+    w = torch.randn(300, generator=gw) / 17.0
+    pos = batch.positions.clone().requires_grad_(True)
+    out_g = sch(batch.x[:, 0], pos, batch.batch)
+    energy = out_g @ w
+    force = -torch.autograd.grad(energy, pos, torch.ones_like(energy), retain_graph=True)[0]
+    # a fine-tuning style scalar loss on the energies: parameter gradients through the differentiable readout
+    target = torch.linspace(-0.05, 0.05, NUM_MOLS)
+    loss = ((energy - target) ** 2).mean()
+    loss.backward()
+    out["schnet_force"] = {"w": w, "out": out_g.detach(), "energy": energy.detach(), "force": force.detach(), "target": target,
+                           "loss": loss.detach(), "d_pos": pos.grad.clone(),
+                           "grads": {n: summarize(p.grad) for n, p in sch.named_parameters() if p.grad is not None}}
+    print("SchNet energy", energy.detach()[:3], "|F|", float(force.norm()), "loss", float(loss))
     path = os.path.join(HERE, "golden_variants.pt")
     torch.save(out, path)
     print("wrote", path, os.path.getsize(path) / 1e6, "MB")

@@ -120,6 +120,19 @@ def test_checkpoint_loads_into_reference_classes(tmp_path):
     ours["SDE_2Dto3D_model"].load_state_dict(ref23.state_dict(), strict=True)
 
 
+def test_oracle_schnet_energy_and_forces(gv, golden, golden_batch):
+    """forces as -dE/dpos (finetune_MD17.py:66); the oracle restatement under torch.autograd vs the reference."""
+    _, batch = golden_batch
+    sec = gv["schnet_force"]
+    sd = sd_from_manifest(golden["manifest"]["schnet"], golden["meta"]["weight_seed"])
+    pos = batch.positions.clone().requires_grad_(True)
+    out, _, _ = O.schnet_forward(sd, batch.x[:, 0], pos, batch.batch, batch.num_graphs)
+    energy = out @ sec["w"]
+    force = -torch.autograd.grad(energy, pos, torch.ones_like(energy))[0]
+    torch.testing.assert_close(energy, sec["energy"], rtol=2e-5, atol=2e-6)
+    assert float((force - sec["force"]).abs().max() / sec["force"].abs().max()) <= 1e-4
+
+
 # ----------------------------------------------------------------------------------------------- GPU: CUDA path
 def _dev():
     if not torch.cuda.is_available():
@@ -214,3 +227,57 @@ def test_gpu_schedule_presets(name, gv, golden, golden_batch):
     # ~1e-3 rad -- any two fp32 implementations (torch CPU vs CUDA included) differ at that level; stated, not hidden
     tol = 2e-3 if name == "VE03" else REL_TOL
     assert err <= tol, (name, err)
+
+
+@pytest.mark.gpu
+def test_gpu_schnet_forces_and_finetune_gradients(gv, golden, golden_batch):
+    """`positions.requires_grad_(); E = head(model(x, positions, batch)); F = -grad(E, positions)` (finetune_MD17.py:49-66) and a
+    fine-tuning loss on the energies (finetune_QM9.py:133-160): energies, forces, d loss / d pos and every SchNet parameter
+    gradient vs the unmodified reference."""
+    from moleculesde_b200.schnet import SchNet
+    from test_gpu_pretrain import check_grad_summary
+    from test_gpu_sde2d3d import assert_parity
+    dev = _dev()
+    _, batch = golden_batch
+    sec = gv["schnet_force"]
+    m = SchNet(hidden_channels=300, num_filters=128, num_interactions=6, num_gaussians=51, cutoff=10, readout="mean", node_class=119)
+    m.load_state_dict(sd_from_manifest(golden["manifest"]["schnet"], golden["meta"]["weight_seed"]))
+    m = m.to(dev).train()
+    b = batch.to(dev)
+    w = sec["w"].to(dev)
+    pos = b.positions.clone().requires_grad_(True)
+    out = m(b.x[:, 0].contiguous(), pos, b.batch)
+    assert out.requires_grad
+    assert_parity(out, sec["out"], "SchNet graph-level output")
+    energy = out @ w
+    force = -torch.autograd.grad(energy, pos, torch.ones_like(energy), retain_graph=True)[0]
+    assert_parity(energy, sec["energy"], "energy")
+    assert_parity(force, sec["force"], "force = -dE/dpos")
+    with pytest.raises(RuntimeError, match="already back-propagated"):   # one reverse sweep per forward, stated loudly
+        torch.autograd.grad(energy, pos, torch.ones_like(energy))
+    for p in m.parameters():
+        p.grad = None
+    pos = b.positions.clone().requires_grad_(True)
+    energy = m(b.x[:, 0].contiguous(), pos, b.batch) @ w
+    loss = ((energy - sec["target"].to(dev)) ** 2).mean()
+    loss.backward()
+    assert abs(float(loss.detach()) - float(sec["loss"])) <= REL_TOL * abs(float(sec["loss"]))
+    assert_parity(pos.grad, sec["d_pos"], "d loss / d pos")
+    bad = []
+    for n, p in m.named_parameters():
+        if n in sec["grads"]:
+            try:
+                check_grad_summary(p.grad, sec["grads"][n], n)
+            except AssertionError as e:
+                bad.append(str(e))
+    assert not bad, "\n".join(bad)
+    # eval mode: forces only (the MD17 evaluation loop, finetune_MD17.py:101-125)
+    m.eval()
+    pos2 = b.positions.clone().requires_grad_(True)
+    e2 = m(b.x[:, 0].contiguous(), pos2, b.batch) @ w
+    f2 = -torch.autograd.grad(e2, pos2, torch.ones_like(e2))[0]
+    assert torch.equal(f2, force), "deterministic kernels: same bits in eval mode"
+    # without requires_grad on the positions and under no_grad the fused inference path answers (no tape)
+    with torch.no_grad():
+        out3 = m(b.x[:, 0].contiguous(), b.positions, b.batch)
+    assert_parity(out3, sec["out"], "inference path")
