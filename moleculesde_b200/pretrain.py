@@ -339,6 +339,26 @@ def _keys(idx: torch.Tensor, dims) -> torch.Tensor:
     return (idx + off[None, :]).to(torch.int32).contiguous()
 
 
+def prepare_gin(cache: dict, x: torch.Tensor, edge_index: torch.Tensor, edge_attr: torch.Tensor, batch: Optional[torch.Tensor],
+                num_graphs: int, train: bool) -> None:
+    """Per-batch index structures of the GIN tape (bond CSR by target, its by-source inverse, feature keys and their bucket
+    indices), on the current stream; idempotent.  Static for a batch, so an input pipeline can build them ahead of the step."""
+    if "gin" in cache:
+        return
+    from .gnn import ATOM_FEATURE_DIMS, BOND_FEATURE_DIMS
+    from .tape import bucket_index
+    dev = x.device
+    if batch is None:
+        batch, num_graphs = torch.zeros(x.size(0), dtype=torch.long, device=dev), 1
+    csr = csr_by_target(edge_index, batch, num_graphs)
+    es = EdgeSet(csr.rowptr, csr.col, batch, num_graphs) if train else None
+    akeys = _keys(x, ATOM_FEATURE_DIMS)
+    ekeys = _keys(edge_attr[csr.perm.long()], BOND_FEATURE_DIMS)   # CSR edge order
+    aidx = bucket_index(akeys.reshape(-1).long(), sum(ATOM_FEATURE_DIMS)) if train else None
+    eidx = bucket_index(ekeys.reshape(-1).long(), sum(BOND_FEATURE_DIMS)) if train else None
+    cache["gin"] = (csr, es, akeys, ekeys, aidx, eidx)
+
+
 def tape_gin(tp: Tape, model, P: Dict[str, Var], x: torch.Tensor, edge_index: torch.Tensor, edge_attr: torch.Tensor,
              cache: Optional[dict], batch: Optional[torch.Tensor] = None, num_graphs: int = 1) -> Var:
     """GNN.forward, GIN / JK=last / dropout 0.  `cache` (a dict living on the batch) keeps the index structures;
@@ -349,17 +369,7 @@ def tape_gin(tp: Tape, model, P: Dict[str, Var], x: torch.Tensor, edge_index: to
     require_device(x)
     train = any(v.needs for v in P.values())
     cache = cache if cache is not None else {}
-    if "gin" not in cache:
-        N = x.size(0)
-        if batch is None:
-            batch, num_graphs = torch.zeros(N, dtype=torch.long, device=dev), 1
-        csr = csr_by_target(edge_index, batch, num_graphs)
-        es = EdgeSet(csr.rowptr, csr.col, batch, num_graphs) if train else None
-        akeys = _keys(x, ATOM_FEATURE_DIMS)
-        ekeys = _keys(edge_attr[csr.perm.long()], BOND_FEATURE_DIMS)   # CSR edge order
-        aidx = bucket_index(akeys.reshape(-1).long(), sum(ATOM_FEATURE_DIMS)) if train else None
-        eidx = bucket_index(ekeys.reshape(-1).long(), sum(BOND_FEATURE_DIMS)) if train else None
-        cache["gin"] = (csr, es, akeys, ekeys, aidx, eidx)
+    prepare_gin(cache, x, edge_index, edge_attr, batch, num_graphs, train)
     csr, es, akeys, ekeys, aidx, eidx = cache["gin"]
     src = es.src if es is not None else Index(csr.col, None, None, x.size(0))
     tgt = es.tgt if es is not None else None
@@ -392,6 +402,28 @@ def tape_gin(tp: Tape, model, P: Dict[str, Var], x: torch.Tensor, edge_index: to
 # ======================================================================================================
 # SchNet (Geom3D/models/schnet.py:85-125), return_latent representation
 # ======================================================================================================
+def prepare_schnet(cache: dict, model, z: torch.Tensor, pos: torch.Tensor, batch: torch.Tensor, num_graphs: int) -> None:
+    """Radius graph (CSR + by-source inverse), atomic-number bucket index, GaussianSmearing features and cosine cutoff of the
+    edges, on the current stream; idempotent.  Depends on the positions only, i.e. static for a pretraining batch."""
+    if "schnet" in cache:
+        return
+    from .graph import radius_graph
+    from .tape import bucket_index
+    L, dev = lib(), pos.device
+    pos = pos.detach().float().contiguous()
+    csr = radius_graph(pos, model.cutoff, batch, num_graphs, want_edge_index=False)
+    es = EdgeSet(csr.rowptr, csr.col, batch, num_graphs)
+    zkeys = z.to(torch.int32).reshape(-1, 1).contiguous()
+    zidx = bucket_index(z, model.embedding.weight.shape[0])
+    E = es.E
+    ng = model.num_gaussians
+    ea, C = torch.empty(E, ng, dtype=torch.float32, device=dev), torch.empty(max(E, 1), dtype=torch.float32, device=dev)
+    check(L.molsde_schnet_edge_feat(ptr(pos), ptr(es.src.idx), ptr(es.tgt.idx), E, ptr(model.distance_expansion.offset), ng,
+                                    float(model.distance_expansion.coeff), float(model.cutoff), ptr(ea), ptr(C), stream_ptr(pos)),
+          "schnet_edge_feat")
+    cache["schnet"] = (es, zkeys, zidx, ea, C)
+
+
 def tape_schnet(tp: Tape, model, P: Dict[str, Var], z: torch.Tensor, pos: torch.Tensor, batch: torch.Tensor, num_graphs: int,
                 cache: Optional[dict], pos_var: Optional[Var] = None) -> Var:
     """Node representation h [N, hidden] of SchNet.forward(return_latent=True) with every intermediate kept.
@@ -404,18 +436,7 @@ def tape_schnet(tp: Tape, model, P: Dict[str, Var], z: torch.Tensor, pos: torch.
     pos = pos.detach().float().contiguous()
     need_pos = pos_var is not None and pos_var.needs
     cache = cache if cache is not None else {}
-    if "schnet" not in cache:  # positions are static during pretraining: the radius graph is built once per batch
-        csr = radius_graph(pos, model.cutoff, batch, num_graphs, want_edge_index=False)
-        es = EdgeSet(csr.rowptr, csr.col, batch, num_graphs)
-        zkeys = z.to(torch.int32).reshape(-1, 1).contiguous()
-        zidx = bucket_index(z, model.embedding.weight.shape[0])
-        E = es.E
-        ng = model.num_gaussians
-        ea, C = torch.empty(E, ng, dtype=torch.float32, device=dev), torch.empty(max(E, 1), dtype=torch.float32, device=dev)
-        check(L.molsde_schnet_edge_feat(ptr(pos), ptr(es.src.idx), ptr(es.tgt.idx), E, ptr(model.distance_expansion.offset), ng,
-                                        float(model.distance_expansion.coeff), float(model.cutoff), ptr(ea), ptr(C), tp.s),
-              "schnet_edge_feat")
-        cache["schnet"] = (es, zkeys, zidx, ea, C)
+    prepare_schnet(cache, model, z, pos, batch, num_graphs)   # positions are static during pretraining: once per batch
     es, zkeys, zidx, ea, C = cache["schnet"]
     h = tp.embed_sum(P["embedding.weight"], zkeys, zidx)
     ea_v = Var(ea, need_pos)
@@ -810,6 +831,34 @@ class PretrainStep:
         self._streams = None
         for m in (gnn, schnet, sde_2d3d, sde_3d2d):
             m.train()
+
+    def prepare(self, batch, max_nodes: Optional[int] = None):
+        """Build, on the CURRENT stream, every per-batch index structure the iteration needs and attach it to `batch`: extended
+        graph (`dataset_3D.py:12-35`) with its CSR / tile plan / by-source inverse, bond CSR and feature bucket indices of the GIN,
+        radius graph + edge features of SchNet, dense-batch pointers.  The step itself then launches no graph construction and
+        makes no host sync.  `max_nodes` (largest molecule, known on the host from `batch.ptr`) avoids the one device read the
+        dense 3D->2D prologue would otherwise make.  Used by `loader.DeviceLoader` one batch ahead of the step."""
+        from . import graph as G
+        from .graph import segment_ptr
+        cache = batch.__dict__.setdefault("_molsde_train_cache", {})
+        if "z" not in cache:
+            cache["z"] = batch.x[:, 0].contiguous()
+        prepare_gin(cache, batch.x, batch.edge_index, batch.edge_attr, batch.batch, batch.num_graphs, True)
+        prepare_schnet(cache, self.schnet, cache["z"], batch.positions, batch.batch, batch.num_graphs)
+        if self.c_23 > 0:
+            if self.m23.use_extend_graph and getattr(batch, "extended_edge_index", None) is None:
+                csr = G.extend_graph(batch.edge_index, batch.batch, batch.num_graphs)
+                batch.extended_edge_index, batch._molsde_ext_csr = csr.edge_index, csr
+            prep = self.m23.prepared(batch)
+            if getattr(prep, "_edge_set", None) is None:
+                prep._edge_set = EdgeSet(prep.csr.rowptr, prep.csr.col, batch.batch, batch.num_graphs)
+        if self.c_32 > 0:
+            node_ptr = getattr(batch, "_molsde_node_ptr", None)
+            if node_ptr is None:
+                node_ptr = batch._molsde_node_ptr = segment_ptr(batch.batch, batch.num_graphs)
+            if getattr(batch, "_molsde_dense_dims", None) is None and max_nodes is not None:
+                batch._molsde_dense_dims = (batch.num_graphs, int(max_nodes), node_ptr)
+        return batch
 
     def forward_backward(self, batch, draws: Optional[dict] = None) -> Dict[str, torch.Tensor]:
         """Forward + backward of one batch; gradients are left in `store.grad`.  `draws` (parity tests):
