@@ -82,42 +82,58 @@ dense_gcn_bwd_kernel(const float* __restrict__ adjc, int64_t adj_stride_b, int64
 //   dpair [B,Nm,Nm,2C]: column c is dS, column C+c is the pass-through gradient of adjc[b,c].
 // Outputs dQ/dK in the layout of the forward's qk buffer and dadjc (pass-through part, overwrite).
 // -----------------------------------------------------------------------------------------------------
+// Per head h the factor  dU_ij = dA_ij / H * (1 - tanh^2(<Q_i[h],K_j[h]>/sqrt(ds))) / sqrt(ds)  is shared by the ds columns of
+// that head, so it is tabulated once per head in shared memory (Nm^2 tanh per head instead of Nm^2 * ds per output row pass);
+// the output sums run over o in ascending order with the same fmaf sequence as before (bit-identical, deterministic).
+// Dynamic shared memory: sQ, sK [Nm][33] | dA, dU [Nm][Nm+1].
 __global__ void __launch_bounds__(256)
 dense_attn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, int64_t ldq, int W, int ds, int C, int Nm,
                       const float* __restrict__ dpair, float* __restrict__ dQ, float* __restrict__ dK, float* __restrict__ dadjc) {
-    __shared__ float sQ[TDN][33], sK[TDN][33];
-    __shared__ float dA[TDN][TDN + 1];
+    extern __shared__ float smem_attn[];
+    const int ldp = Nm + 1;
+    float* sQ = smem_attn;              // [Nm][33]
+    float* sK = sQ + Nm * 33;           // [Nm][33]
+    float* dA = sK + Nm * 33;           // [Nm][Nm+1]
+    float* dU = dA + Nm * ldp;          // [Nm][Nm+1]
     const int b = blockIdx.x, c = blockIdx.y;
     for (int i = threadIdx.x; i < Nm * W; i += blockDim.x) {
         const int r = i / W, k = i % W;
-        sQ[r][k] = Q[(static_cast<int64_t>(b) * Nm + r) * ldq + c * W + k];
-        sK[r][k] = K[(static_cast<int64_t>(b) * Nm + r) * ldq + c * W + k];
+        sQ[r * 33 + k] = Q[(static_cast<int64_t>(b) * Nm + r) * ldq + c * W + k];
+        sK[r * 33 + k] = K[(static_cast<int64_t>(b) * Nm + r) * ldq + c * W + k];
     }
     const float* pb = dpair + static_cast<int64_t>(b) * Nm * Nm * (2 * C);
     float* da = dadjc ? dadjc + (static_cast<int64_t>(b) * C + c) * Nm * Nm : nullptr;
     for (int p = threadIdx.x; p < Nm * Nm; p += blockDim.x) {
         const int i = p / Nm, j = p % Nm;
-        dA[i][j] = 0.5f * (pb[static_cast<int64_t>(p) * (2 * C) + c] + pb[static_cast<int64_t>(j * Nm + i) * (2 * C) + c]);
+        dA[i * ldp + j] = 0.5f * (pb[static_cast<int64_t>(p) * (2 * C) + c] + pb[static_cast<int64_t>(j * Nm + i) * (2 * C) + c]);
         if (da) da[p] = pb[static_cast<int64_t>(p) * (2 * C) + C + c];
     }
     __syncthreads();
     const int H = W / ds;
     const float inv_sqrt = 1.0f / sqrtf(static_cast<float>(ds)), inv_h = 1.0f / static_cast<float>(H);
-    for (int p = threadIdx.x; p < 2 * Nm * W; p += blockDim.x) {
-        const bool forK = p >= Nm * W;
-        const int q = forK ? p - Nm * W : p;
-        const int r = q / W, col = q % W, h = col / ds;
-        float acc = 0.0f;
-        for (int o = 0; o < Nm; ++o) {
-            const int i = forK ? o : r, j = forK ? r : o;
+    for (int h = 0; h < H; ++h) {
+        for (int p = threadIdx.x; p < Nm * Nm; p += blockDim.x) {
+            const int i = p / Nm, j = p % Nm;
             float d = 0.0f;
-            for (int k = 0; k < ds; ++k) d = fmaf(sQ[i][h * ds + k], sK[j][h * ds + k], d);
+            for (int k = 0; k < ds; ++k) d = fmaf(sQ[i * 33 + h * ds + k], sK[j * 33 + h * ds + k], d);
             const float t = tanhf(d * inv_sqrt);
-            const float du = dA[i][j] * inv_h * (1.0f - t * t) * inv_sqrt;
-            acc = fmaf(du, forK ? sQ[i][col] : sK[j][col], acc);
+            dU[i * ldp + j] = dA[i * ldp + j] * inv_h * (1.0f - t * t) * inv_sqrt;
         }
-        float* dst = forK ? dK : dQ;
-        dst[(static_cast<int64_t>(b) * Nm + r) * ldq + c * W + col] = acc;
+        __syncthreads();
+        for (int p = threadIdx.x; p < 2 * Nm * ds; p += blockDim.x) {
+            const bool forK = p >= Nm * ds;
+            const int q = forK ? p - Nm * ds : p;
+            const int r = q / ds, col = h * ds + q % ds;
+            float acc = 0.0f;
+            if (forK) {
+                for (int o = 0; o < Nm; ++o) acc = fmaf(dU[o * ldp + r], sQ[o * 33 + col], acc);
+            } else {
+                for (int o = 0; o < Nm; ++o) acc = fmaf(dU[r * ldp + o], sK[o * 33 + col], acc);
+            }
+            float* dst = forK ? dK : dQ;
+            dst[(static_cast<int64_t>(b) * Nm + r) * ldq + c * W + col] = acc;
+        }
+        __syncthreads();
     }
 }
 
@@ -225,7 +241,15 @@ int molsde_dense_attn_bwd(const float* Q, const float* K, int64_t ldq, int32_t W
                           const float* dpair, float* dQ, float* dK, float* dadjc, void* stream) {
     if (!Q || !K || !dpair || !dQ || !dK || B <= 0 || C <= 0 || Nm <= 0 || W <= 0 || ds <= 0 || W % ds) return MOLSDE_ERR_INVALID;
     if (Nm > TDN || W > 32) return MOLSDE_ERR_UNSUPPORTED;
-    dense_attn_bwd_kernel<<<dim3(B, C), 256, 0, as_stream(stream)>>>(Q, K, ldq, W, ds, C, Nm, dpair, dQ, dK, dadjc);
+    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(Nm) * 33 + 2 * static_cast<size_t>(Nm) * (Nm + 1));
+    static bool attr_set = false;   // 50.2 KB at Nm = 64: above the 48 KB default, opt in once
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(dense_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(sizeof(float) * (2 * TDN * 33 + 2 * TDN * (TDN + 1)))) != cudaSuccess)
+            return check_launch("dense_attn_bwd(attr)");
+        attr_set = true;
+    }
+    dense_attn_bwd_kernel<<<dim3(B, C), 256, smem, as_stream(stream)>>>(Q, K, ldq, W, ds, C, Nm, dpair, dQ, dK, dadjc);
     return check_launch("dense_attn_bwd");
 }
 
