@@ -552,8 +552,18 @@ def hot_path_pc_only(model, d, rep, pos0, group_ptr, seed, pc_steps):
     return pos_mean
 
 
+def _json_only_stdout():
+    """The contract is ONE JSON line on stdout: libraries that write to fd 1 (NCCL prints its version banner there) are sent to
+    stderr for the whole run; `print(json.dumps(...))` goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
+
+
 def main():
     args = parse()
+    _json_only_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
