@@ -13,6 +13,7 @@ from typing import Callable, List, Optional
 
 import torch
 
+from . import _abi
 from ._abi import check, lib, ptr, require_device, stream_ptr
 
 ACT = {"none": 0, "relu": 1, "silu": 2, "ssp": 3, "tanh": 4, "elu": 5}
@@ -26,10 +27,9 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
     """data pointer of a contiguous tensor or of a 2-D row-strided view (stride(1) == 1)."""
     if t is None:
         return None
-    if t.dim() == 2 and not t.is_contiguous():
-        assert t.stride(1) == 1, "only row-strided views cross the C ABI"
-        return t.data_ptr()
-    return ptr(t)
+    if _abi.CHECK_ABI and not t.is_contiguous():
+        assert t.dim() == 2 and t.stride(1) == 1, "only contiguous tensors and row-strided 2-D views cross the C ABI"
+    return t.data_ptr()
 
 
 def _ld(t: torch.Tensor) -> int:

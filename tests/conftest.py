@@ -3,6 +3,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("MOLSDE_CHECK_ABI", "1")   # layout assertions on every pointer handed to the C ABI (off in production)
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)

@@ -281,3 +281,34 @@ def test_gpu_schnet_forces_and_finetune_gradients(gv, golden, golden_batch):
     with torch.no_grad():
         out3 = m(b.x[:, 0].contiguous(), b.positions, b.batch)
     assert_parity(out3, sec["out"], "inference path")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["VE", "VP02"])
+def test_gpu_01_pc_sampler_vs_oracle(preset, gv):
+    """The fused predictor-corrector loop with the `_01` variant (and a preset schedule): 4 reverse steps with injected noise,
+    one 5-conformer group, vs the oracle's restatement of `position_PC_generation` step by step."""
+    from moleculesde_b200.checkpoint import resolve_sde_type
+    from moleculesde_b200.data import repeat_data, synth_molecules
+    from moleculesde_b200.sampler import position_PC_generation
+    from moleculesde_b200.sde_2d_to_3d import SDEModel2Dto3D_01
+    from test_gpu_sde2d3d import _gpu_batch, rel_err
+    dev = _dev()
+    kind, lo, hi, n = resolve_sde_type(preset, "2Dto3D")
+    sd = sd_from_manifest(gv["sde2d3d_01_VE"]["manifest"], gv["meta"]["weight_seed"])
+    m = SDEModel2Dto3D_01(emb_dim=300, hidden_dim=32, beta_schedule=None, beta_min=lo, beta_max=hi, num_diffusion_timesteps=n,
+                          SDE_type=kind, use_extend_graph=True)
+    m.load_state_dict(sd)
+    m = m.to(dev).eval()
+    rb = repeat_data(synth_molecules(1, 52, "pcqm")[0], 5)
+    b = _gpu_batch(rb, dev)
+    g = torch.Generator().manual_seed(8)
+    N, steps = rb.positions.size(0), 4
+    rep, pos0 = torch.randn(N, 300, generator=g), torch.randn(N, 3, generator=g)
+    nc, npd = torch.randn(steps, N, 3, generator=g), torch.randn(steps, N, 3, generator=g)
+    _, pos_mean = position_PC_generation(rep.to(dev), b, pos0.to(dev), m, m.sde_pos, noise_corr=nc.to(dev), noise_pred=npd.to(dev),
+                                         diffusion_steps=steps)
+    assert int(m.prepared(b).status.item()) == 0
+    _, ref = O.pc_sample_2d3d(sd, O.make_sde(kind, lo, hi, n), rep, b.extended_edge_index.cpu(), rb.batch, rb.num_graphs, pos0,
+                              nc, npd, n_diff_steps=steps)
+    assert rel_err(pos_mean.cpu(), ref) < 2e-3, preset   # free-running trajectory: rounding differences amplify step by step
