@@ -18,9 +18,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from moleculesde_b200 import graph as G  # noqa: E402
+from moleculesde_b200 import graph as G  # noqa: E402,F401
 from moleculesde_b200.data import Batch, synth_molecules  # noqa: E402
 from moleculesde_b200.gnn import GNN  # noqa: E402
+from moleculesde_b200.loader import DeviceLoader, pin_batch  # noqa: E402
 from moleculesde_b200.pretrain import PretrainStep  # noqa: E402
 from moleculesde_b200.schnet import SchNet  # noqa: E402
 from moleculesde_b200.sde_2d_to_3d import SDEModel2Dto3D_02  # noqa: E402
@@ -74,13 +75,13 @@ def main():
                         gnn_2d_lr_scale=args.gnn_2d_lr_scale, gnn_3d_lr_scale=args.gnn_3d_lr_scale, weight_decay=args.decay)
     if world > 1:
         dist.broadcast(step.store.flat, src=0)
-    # "dataset": every rank its own shard of synthetic molecules, batched once (the reference re-collates every epoch)
+    # "dataset": every rank its own shard of synthetic molecules, collated once into pinned HOST batches (the reference
+    # re-collates every epoch); the DeviceLoader copies each batch and builds its graph structures (extended graph of
+    # dataset_3D.py:114-115, CSRs, radius graph, ...) on the GPU one batch ahead of the step, every epoch
     mols = synth_molecules(args.num_molecules // world, args.seed + 1000 * rank, "pcqm")
-    loader = []
-    for i in range(0, len(mols) - args.batch_size + 1, args.batch_size):
-        b = Batch.from_data_list(mols[i:i + args.batch_size]).to(dev)
-        b.extended_edge_index = G.extend_graph(b.edge_index, b.batch, b.num_graphs).edge_index   # dataset_3D.py:114-115 on the GPU
-        loader.append(b)
+    host_batches = [pin_batch(Batch.from_data_list(mols[i:i + args.batch_size]))
+                    for i in range(0, len(mols) - args.batch_size + 1, args.batch_size)]
+    loader = DeviceLoader(host_batches, dev, prepare=step.prepare)
     optimal_loss = 1e10
     for epoch in range(1, args.epochs + 1):
         if rank == 0:

@@ -24,6 +24,7 @@ _SINGLE_STREAM = _os.environ.get("MOLSDE_SINGLE_STREAM") == "1"   # A/B switch: 
 # parameter gradients on side streams (Tape.wgrad): "capture" = only while a CUDA graph is being captured (the eager step is
 # bound by host launch time, where the extra event calls cost more than the overlap returns), "1" always, "0" never
 _WGRAD_STREAMS = _os.environ.get("MOLSDE_WGRAD_STREAMS", "capture")
+_STREAM_PRIORITY = _os.environ.get("MOLSDE_STREAM_PRIORITY", "1") == "1"   # A/B switch for the high-priority branch streams
 
 
 _CH = re.compile(r"^edge_score_network\.layers\.(\d+)\.attn\.(\d+)\.(func_q|func_k)\.layers\.(\d)\.(weight|bias)$")
@@ -875,20 +876,26 @@ class PretrainStep:
         branch owns its tape and its own gradient tensor for the shared representations, the two contributions are added after
         the join in a fixed order, and each branch writes a disjoint slice of the flat gradient buffer — results are
         bit-identical to the single-stream order (`MOLSDE_SINGLE_STREAM=1`)."""
-        draws = draws or {}
+        caller = torch.cuda.current_stream(self.dev) if self.dev.type == "cuda" else None
+        if caller is None or _SINGLE_STREAM:
+            return self._forward_backward(batch, draws or {}, caller, caller, caller, None, None)
+        if self._streams is None:
+            # the dependent chains (branch streams) get the high priority, the weight-gradient side streams the low one: a
+            # pending CTA of the critical path is scheduled before the leaves that only have to finish by the end of the step
+            hi = -1 if _STREAM_PRIORITY else 0
+            self._streams = tuple(torch.cuda.Stream(self.dev, priority=p) for p in (hi, hi, hi, 0, 0))
+        s0, s1, s2, w0, w1 = self._streams
+        if not (_WGRAD_STREAMS == "1" or (_WGRAD_STREAMS == "capture" and torch.cuda.is_current_stream_capturing())):
+            w0 = w1 = None
+        s0.wait_stream(caller)
+        with torch.cuda.stream(s0):
+            out = self._forward_backward(batch, draws or {}, s0, s1, s2, w0, w1)
+        caller.wait_stream(s0)
+        return out
+
+    def _forward_backward(self, batch, draws, main, s1, s2, w0, w1) -> Dict[str, torch.Tensor]:
         st = self.store
         st.zero_grad()
-        multi = self.dev.type == "cuda" and not _SINGLE_STREAM
-        main = torch.cuda.current_stream(self.dev)
-        w0 = w1 = None
-        if multi:
-            if self._streams is None:
-                self._streams = tuple(torch.cuda.Stream(self.dev) for _ in range(4))
-            s1, s2 = self._streams[:2]
-            if _WGRAD_STREAMS == "1" or (_WGRAD_STREAMS == "capture" and torch.cuda.is_current_stream_capturing()):
-                w0, w1 = self._streams[2:]   # weight-gradient side streams of the tapes on main / s1
-        else:
-            s1 = s2 = main
         cache = batch.__dict__.setdefault("_molsde_train_cache", {})
         z = cache.get("z")
         if z is None:

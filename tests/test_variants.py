@@ -312,3 +312,36 @@ def test_gpu_01_pc_sampler_vs_oracle(preset, gv):
     _, ref = O.pc_sample_2d3d(sd, O.make_sde(kind, lo, hi, n), rep, b.extended_edge_index.cpu(), rb.batch, rb.num_graphs, pos0,
                               nc, npd, n_diff_steps=steps)
     assert rel_err(pos_mean.cpu(), ref) < 2e-3, preset   # free-running trajectory: rounding differences amplify step by step
+
+
+@pytest.mark.gpu
+def test_gpu_schnet_forces_capped_radius_graph_vs_oracle(golden):
+    """Drug-sized molecules at the 10 A cutoff: the 32-neighbour cap binds, so the radius graph is NOT symmetric and the two
+    ends of an edge collect different position gradients.  Forces vs torch.autograd over the oracle restatement (same edges)."""
+    from moleculesde_b200.data import Batch, synth_molecules
+    from moleculesde_b200.schnet import SchNet
+    from test_gpu_sde2d3d import assert_parity
+    dev = _dev()
+    hb = Batch.from_data_list(synth_molecules(6, 91, "drug"))
+    sd = sd_from_manifest(golden["manifest"]["schnet"], golden["meta"]["weight_seed"])
+    m = SchNet(hidden_channels=300, num_filters=128, num_interactions=6, num_gaussians=51, cutoff=10, readout="mean", node_class=119)
+    m.load_state_dict(sd)
+    m = m.to(dev).eval()
+    g = torch.Generator().manual_seed(17)
+    w = torch.randn(300, generator=g) / 17.0
+    # oracle (CPU, autograd)
+    pos_c = hb.positions.clone().requires_grad_(True)
+    out_c, _, ei = O.schnet_forward(sd, hb.x[:, 0], pos_c, hb.batch, hb.num_graphs)
+    deg = torch.bincount(ei[1], minlength=hb.positions.size(0))
+    assert 32 <= int(deg.max()) <= 33 and int(torch.bincount(hb.batch).max()) > 60, "the neighbour cap binds (torch_cluster keeps 32, or 33 when the centre itself is not among the first 33 hits)"
+    flipped = set(map(tuple, ei.flip(0).t().tolist()))
+    assert any(tuple(e) not in flipped for e in ei.t().tolist()), "asymmetric edge set"
+    e_c = out_c @ w
+    f_c = -torch.autograd.grad(e_c, pos_c, torch.ones_like(e_c))[0]
+    # CUDA path
+    b = hb.to(dev)
+    pos = b.positions.clone().requires_grad_(True)
+    e_g = m(b.x[:, 0].contiguous(), pos, b.batch) @ w.to(dev)
+    f_g = -torch.autograd.grad(e_g, pos, torch.ones_like(e_g))[0]
+    assert_parity(e_g, e_c.detach(), "energy (drug-sized)")
+    assert_parity(f_g, f_c, "forces (drug-sized, capped radius graph)")
