@@ -345,3 +345,54 @@ def test_gpu_schnet_forces_capped_radius_graph_vs_oracle(golden):
     f_g = -torch.autograd.grad(e_g, pos, torch.ones_like(e_g))[0]
     assert_parity(e_g, e_c.detach(), "energy (drug-sized)")
     assert_parity(f_g, f_c, "forces (drug-sized, capped radius graph)")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("per_launch", [3, 1])
+def test_gpu_generate_samples_from_testset_vs_oracle(per_launch, golden):
+    """The reference's inference driver (`..._inference_2D_to_3D_VE_VP.py:41-91`): GIN encoding of the repeated copies, prior,
+    PC loop, per-molecule records -- several molecules per launch as independent groups -- vs the oracle molecule by molecule."""
+    import types
+    from moleculesde_b200.data import repeat_data, synth_molecules
+    from moleculesde_b200.gnn import GNN
+    from moleculesde_b200.inference import generate_samples_from_testset
+    from moleculesde_b200.sde_2d_to_3d import SDEModel2Dto3D_02
+    from oracle.ref_ops import extend_graph_index
+    from test_gpu_sde2d3d import rel_err
+    dev = _dev()
+    sd23 = sd_from_manifest(golden["manifest"]["sde2d3d"], golden["meta"]["weight_seed"])
+    sdg = sd_from_manifest(golden["manifest"]["gnn"], golden["meta"]["weight_seed"])
+    m23 = SDEModel2Dto3D_02(emb_dim=300, hidden_dim=32, beta_schedule=None, beta_min=0.2, beta_max=1.0, num_diffusion_timesteps=1000,
+                            SDE_type="VE", use_extend_graph=True)
+    m23.load_state_dict(sd23)
+    gnn = GNN(5, 300, JK="last", drop_ratio=0.0, gnn_type="GIN")
+    gnn.load_state_dict(sdg)
+    m23, gnn = m23.to(dev), gnn.to(dev)
+    mols = synth_molecules(3, 61, "pcqm")
+    R, steps = 2, 3
+    args = types.SimpleNamespace(start=0, end=10, num_repeat_SDE_inference=R, steps_pos=1, device=str(dev))
+
+    def injected(N):
+        g = torch.Generator().manual_seed(1000 + N)
+        return torch.randn(N, 3, generator=g), torch.randn(steps, N, 3, generator=g), torch.randn(steps, N, 3, generator=g)
+
+    recs = generate_samples_from_testset(mols, gnn, m23, args, molecules_per_launch=per_launch, diffusion_steps=steps,
+                                         _injected=injected)
+    assert len(recs) == 3
+    sde = O.make_sde("VE", 0.2, 1.0, 1000)
+    for lo in range(0, 3, per_launch):
+        group = mols[lo:lo + per_launch]
+        N = sum(m.num_nodes for m in group) * R
+        pos0, nc, npd = injected(N)
+        off = 0
+        for k, m in enumerate(group):
+            rb = repeat_data(m, R)
+            n = rb.positions.size(0)
+            ext = torch.cat([extend_graph_index(m.edge_index, m.num_nodes) + r * m.num_nodes for r in range(R)], dim=1)
+            rep = O.gin_forward(sdg, rb.x, rb.edge_index, rb.edge_attr)
+            _, ref = O.pc_sample_2d3d(sd23, sde, rep, ext, rb.batch, R, pos0[off:off + n], nc[:, off:off + n], npd[:, off:off + n],
+                                      n_diff_steps=steps)
+            rec = recs[lo + k]
+            assert tuple(rec.pos_gen.shape) == (n, 3) and int(rec.num_pos_gen) == R and torch.equal(rec.x, m.x)
+            assert rel_err(rec.pos_gen, ref) < 2e-3, (lo, k)
+            off += n
