@@ -70,7 +70,12 @@ constexpr int SI_MISC = SI_ETGT + GROUPS * TE;  // [4]  (0: work item, 1: TMEM b
 constexpr int SI_BAR = ((S_FLOATS + SI_MISC + 4 + 1) & ~1) - S_FLOATS;  // [2] mbarrier of the tcgen05 commits (8-byte aligned)
 constexpr int SI_TMABAR = SI_BAR + 2;        // [2] mbarrier of the TMA bulk weight copies (SI_MISC + 2 holds its phase)
 constexpr int S_INTS = SI_TMABAR + 2;
-constexpr size_t SMEM_BYTES = sizeof(float) * S_FLOATS + sizeof(int) * S_INTS;
+// (source, target) of every edge slot of the first SLOT_CACHE_TILES tiles of the chunk as chunk-local byte indices (< MAXN <= 255):
+// static per batch, resolved once per chunk (load_chunk) instead of by a dependent global load + bisection at each of the
+// 7 tile visits of every score evaluation.  [tile][0: src, 1: tgt][TE] uint8, behind the int region.
+constexpr int SLOT_CACHE_TILES = 31;
+constexpr size_t SMEM_BYTES = sizeof(float) * S_FLOATS + sizeof(int) * S_INTS + static_cast<size_t>(SLOT_CACHE_TILES) * 2 * TE;
+static_assert(MAXN <= 255, "slot cache stores chunk-local node indices as bytes");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 static_assert(MOLSDE_P_E0_END <= 3 * 32 * MAXN, "E0 weights are staged in the q/k/v region");
 static_assert(MOLSDE_P_BASIS_SZ <= 3 * 32 * MAXN, "basis weights (tcgen05 B tiles + small vectors) are staged in the q/k/v region");
@@ -212,22 +217,38 @@ __device__ __forceinline__ TileInfo tile_info(const Chunk& c, int t) {
     return ti;
 }
 
-// warp-private bookkeeping: lanes 0..15 resolve (source, target) of their slot by bisection on rowptr
-__device__ __forceinline__ void slot_edges(const Chunk& c, const int32_t* __restrict__ src_g, const TileInfo& ti,
+__device__ __forceinline__ uint8_t* slot_cache(const Chunk& c) { return reinterpret_cast<uint8_t*>(c.si + S_INTS); }
+
+// (source, target) of edge slot `slot` of tile t, chunk-local: bisection on the row pointer + one global load
+__device__ __forceinline__ void resolve_slot(const Chunk& c, const int32_t* __restrict__ src_g, const TileInfo& ti, int slot,
+                                             int& sj, int& tg) {
+    const int* rowl = c.si + SI_ROWL;
+    sj = 0;
+    tg = ti.ta;
+    if (slot < ti.ne) {
+        const int e = ti.ea + slot;
+        int lo = ti.ta, hi = ti.tb;  // largest i in [ta, tb) with rowl[i] <= e
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (rowl[mid] <= e) lo = mid; else hi = mid;
+        }
+        tg = lo;
+        sj = src_g[c.edge0 + e] - c.node0;
+    }
+}
+
+// warp-private bookkeeping: lanes 0..15 fetch (source, target) of their slot (dead slots: source 0, target = first of the tile)
+__device__ __forceinline__ void slot_edges(const Chunk& c, const int32_t* __restrict__ src_g, const TileInfo& ti, int t,
                                            int slab, int lane, int* esrc, int* etgt) {
     if (lane < 16) {
-        const int* rowl = c.si + SI_ROWL;
         const int slot = slab * 16 + lane;
-        int sj = 0, tg = 0;
-        if (slot < ti.ne) {
-            const int e = ti.ea + slot;
-            int lo = ti.ta, hi = ti.tb;  // largest i in [ta, tb) with rowl[i] <= e
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (rowl[mid] <= e) lo = mid; else hi = mid;
-            }
-            tg = lo;
-            sj = src_g[c.edge0 + e] - c.node0;
+        int sj, tg;
+        if (t < SLOT_CACHE_TILES) {
+            const uint8_t* sc = slot_cache(c) + t * 2 * TE;
+            sj = sc[slot];
+            tg = sc[TE + slot];
+        } else {
+            resolve_slot(c, src_g, ti, slot, sj, tg);
         }
         esrc[slot] = sj;
         etgt[slot] = tg;
@@ -268,7 +289,7 @@ __device__ __noinline__ void phase_edge_features(const Chunk c, const float* __r
     stage_bulk(c.si, W, blob, MOLSDE_P_E0_END);
     for (int t = grp; t < c.ntiles; t += GROUPS) {
         const TileInfo ti = tile_info(c, t);
-        slot_edges(c, src_g, ti, slab, lane, esrc, etgt);
+        slot_edges(c, src_g, ti, t, slab, lane, esrc, etgt);
         // this thread's 16 elements of the e2d tile (rows g, g+8; columns nb*8 + 2*t4 + j), fetched early
         const float* e2d_t = e2d_tiles + static_cast<size_t>(c.tile0 + t) * TILE_FLOATS + slab * 16;
         float e2[4][4];
@@ -434,7 +455,7 @@ __device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __rest
     for (int t = grp; t < c.ntiles; t += GROUPS) {
         const TileInfo ti = tile_info(c, t);
         load_stripe_async(stripe, scratch + static_cast<size_t>(t) * SCR_TILE + slab * 16, lane);
-        slot_edges(c, src_g, ti, slab, lane, esrc, etgt);
+        slot_edges(c, src_g, ti, t, slab, lane, esrc, etgt);
         cp_async_wait<0>();
         __syncwarp();
         // e = lin_edge(edge_attr); this thread: slots 16*slab + g, +8; columns nb*8 + 2*t4 + {0,1}
@@ -715,16 +736,13 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
         int* esrc = c.si + SI_ESRC + (t & 1) * TE;
         int* etgt = c.si + SI_ETGT + (t & 1) * TE;
         if (tid < TE) {  // (source, target) of every slot
-            int sj = 0, tg = ti.ta;
-            if (tid < ti.ne) {
-                const int e = ti.ea + tid;
-                int lo = ti.ta, hi = ti.tb;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (rowl[mid] <= e) lo = mid; else hi = mid;
-                }
-                tg = lo;
-                sj = src_g[c.edge0 + e] - c.node0;
+            int sj, tg;
+            if (t < SLOT_CACHE_TILES) {
+                const uint8_t* sc = slot_cache(c) + t * 2 * TE;
+                sj = sc[tid];
+                tg = sc[TE + tid];
+            } else {
+                resolve_slot(c, src_g, ti, tid, sj, tg);
             }
             esrc[tid] = sj;
             etgt[tid] = tg;
@@ -887,6 +905,7 @@ __device__ __forceinline__ void tmem_teardown(uint32_t tmem_base) {
 }
 
 __device__ __forceinline__ bool load_chunk(Chunk& c, const molsde_plan& plan, int chunk, int32_t* status_flag) {
+    // (also fills the slot cache of the chunk's first SLOT_CACHE_TILES tiles)
     const int tid = threadIdx.x;
     c.tile0 = plan.chunk_tile_ptr[chunk];
     c.ntiles = plan.chunk_tile_ptr[chunk + 1] - c.tile0;
@@ -904,6 +923,19 @@ __device__ __forceinline__ bool load_chunk(Chunk& c, const molsde_plan& plan, in
         for (int t = tid; t < c.ntiles; t += NTHREADS)
             if (rowl[ttgt[t + 1]] - rowl[ttgt[t]] > TE) bad = 1;
         ok = !__syncthreads_or(bad);
+        if (ok) {
+            uint8_t* sc = slot_cache(c);
+            const int nt = c.ntiles < SLOT_CACHE_TILES ? c.ntiles : SLOT_CACHE_TILES;
+            for (int item = tid; item < nt * TE; item += NTHREADS) {
+                const int t = item / TE, slot = item % TE;
+                const TileInfo ti = tile_info(c, t);
+                int sj, tg;
+                resolve_slot(c, plan.src, ti, slot, sj, tg);
+                sc[t * 2 * TE + slot] = static_cast<uint8_t>(sj);
+                sc[t * 2 * TE + TE + slot] = static_cast<uint8_t>(tg);
+            }
+            __syncthreads();
+        }
     }
     if (!ok && tid == 0 && status_flag) atomicExch(status_flag, 1 + chunk);
     return ok;
