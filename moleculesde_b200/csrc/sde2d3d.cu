@@ -443,8 +443,7 @@ __device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __rest
     float* stripe = Ag + slab * 16;
     float* Mm = Ag;  // [TE][LDM] slot-major messages, written only after the group's GEMMs are done
     float* L = sm + S_L + grp * (TE * 8);
-    float* smax = sm + S_MS + grp * (2 * TE * 8);
-    float* ssum = smax + TE * 8;
+    float* ssum = sm + S_MS + grp * (2 * TE * 8) + TE * 8;
     float* Q = sm + S_Q;
     const float* Kk = sm + S_K;
     const float* V = sm + S_V;
@@ -490,8 +489,11 @@ __device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __rest
             float m = -CUDART_INF_F;
             for (int s = s0; s < s1; ++s) m = fmaxf(m, L[s * 8 + hd]);
             float z = 0.0f;
-            for (int s = s0; s < s1; ++s) z += __expf(L[s * 8 + hd] - m);
-            smax[p] = m;
+            for (int s = s0; s < s1; ++s) {   // the exponentials are kept (in place of the logits) for the normalisation pass
+                const float ex = __expf(L[s * 8 + hd] - m);
+                L[s * 8 + hd] = ex;
+                z += ex;
+            }
             ssum[p] = z;
         }
         group_sync(grp);
@@ -503,7 +505,7 @@ __device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __rest
 #pragma unroll
                 for (int nb = 0; nb < 4; ++nb) {
                     const int col = nb * 8 + 2 * t4, hd = col >> 2;
-                    float a = __fdividef(__expf(L[s * 8 + hd] - smax[pb + hd]), ssum[pb + hd] + 1e-16f);
+                    float a = __fdividef(L[s * 8 + hd], ssum[pb + hd] + 1e-16f);
                     if (c.attn_keep)  // F.dropout(alpha, p) in train mode (TransformerConv.message)
                         a *= c.attn_keep[(static_cast<size_t>(layer) * c.E_total + c.edge0 + ti.ea + s) * 8 + hd] * c.inv_keep;
                     Mm[s * LDM + col] = e[nb][2 * rr] * a;
@@ -735,6 +737,17 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
         const TileInfo ti = tile_info(c, t);
         int* esrc = c.si + SI_ESRC + (t & 1) * TE;
         int* etgt = c.si + SI_ETGT + (t & 1) * TE;
+        // items (e, kc) of the A operand: kc = (tid >> 7) + 4 i.  i = 2, 3 (kc >= 8) are the edge_attr half, read straight from
+        // the L2-resident scratch record (written by E0): issued FIRST, their latency overlaps the slot bookkeeping, the
+        // barrier and the shared-memory gathers of i = 0, 1.
+        static_assert(NTHREADS == 4 * TE, "item mapping of the basis A operand");
+        const float* sc_t = scratch + static_cast<size_t>(t) * SCR_TILE;
+        const int e = tid & (TE - 1), kq = tid >> 7;
+        float va[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) va[i][q] = sc_t[((kq + 4 * i) * 4 + q) * LDA + e];
         if (tid < TE) {  // (source, target) of every slot
             int sj, tg;
             if (t < SLOT_CACHE_TILES) {
@@ -750,24 +763,21 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
         __syncthreads();
         // A operand [128 x 64], K-major canonical core-matrix layout, split into tf32 hi + exact lo:
         //   k < 32: h_row + h_col (:154-155),  k >= 32: edge_attr (scratch tile)
-        const float* sc_t = scratch + static_cast<size_t>(t) * SCR_TILE;
         stage_async(frames + (t & 1) * FRAME_FLOATS, sc_t + TILE_FLOATS, FRAME_FLOATS);  // consumed by the epilogue of tile t
+        {
+            const int sj = esrc[e], tg = etgt[e];
+            const bool live = e < ti.ne;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int item = tid + NTHREADS * i;
-            const int e = item & (TE - 1), kc = item >> 7, k0 = kc * 4;
-            float v[4];
-            if (kc < 8) {
-                const int sj = esrc[e], tg = etgt[e];
-                const bool live = e < ti.ne;
+            for (int i = 0; i < 2; ++i) {
+                const int kc = kq + 4 * i, k0 = kc * 4;
+                float v[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) v[q] = live ? XT[(k0 + q) * LDX + sj] + XT[(k0 + q) * LDX + tg] : 0.0f;
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) v[q] = sc_t[(k0 - 32 + q) * LDA + e];
+                store_a_chunk(AH, AL, e, kc, v);
             }
-            store_a_chunk(AH, AL, e, kc, v);
         }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) store_a_chunk(AH, AL, e, kq + 4 * i + 8, va[i]);
         cp_async_wait<0>();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
