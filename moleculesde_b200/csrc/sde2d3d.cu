@@ -747,7 +747,8 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) va[i][q] = sc_t[((kq + 4 * i) * 4 + q) * LDA + e];
+            for (int q = 0; q < 4; ++q)   // the record is rewritten by E0 of every evaluation of this launch: L2-coherent load, never .nc
+                va[i][q] = __ldcg(sc_t + ((kq + 4 * i) * 4 + q) * LDA + e);
         if (tid < TE) {  // (source, target) of every slot
             int sj, tg;
             if (t < SLOT_CACHE_TILES) {
