@@ -348,6 +348,12 @@ int molsde_bn_eval(const float* x, int64_t M, int32_t F, const float* gamma, con
                    const float* running_var, float eps, int32_t act, float* y, float* rstd_tmp, void* stream);
 int molsde_bn_train_bwd(const float* x, const float* dy, int64_t M, int32_t F, const float* gamma, const float* mean,
                         const float* rstd, float* dx, float* dgamma, float* dbeta, double* ws, void* stream);
+/* the same with the ReLU mask of a fused BatchNorm+ReLU applied in place (relu_y = the forward output; NULL = none) and the
+ * totals also ADDED to the parameter-gradient buffers grad_gamma / grad_beta (optional) -- one call instead of
+ * act_bwd + bn_train_bwd + two accumulation passes. */
+int molsde_bn_train_bwd_fused(const float* x, const float* dy, const float* relu_y, int64_t M, int32_t F, const float* gamma,
+                              const float* mean, const float* rstd, float* dx, float* dgamma, float* dbeta, float* grad_gamma,
+                              float* grad_beta, double* ws, void* stream);
 /* torch.optim.Adam step over one flat buffer (pretrain_MoleculeSDE.py:337); g is scaled by grad_scale first (1/world) */
 int molsde_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                      float weight_decay, int32_t step, float grad_scale, void* stream);

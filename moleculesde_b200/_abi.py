@@ -41,7 +41,7 @@ EXPORTS = [
     "molsde_bn_train_bwd", "molsde_adam_step", "molsde_sde2d3d_edge_geom", "molsde_tconv_fwd", "molsde_tconv_bwd",
     "molsde_equi_fwd", "molsde_equi_bwd", "molsde_dsm_pos_loss_bwd", "molsde_embed_sum", "molsde_edge_mul_reduce",
     "molsde_edge_mul_gather", "molsde_dot", "molsde_gin_aggregate_fwd", "molsde_gin_message_bwd", "molsde_schnet_edge_feat",
-    "molsde_schnet_edge_feat_bwd", "molsde_rowdot",
+    "molsde_schnet_edge_feat_bwd", "molsde_rowdot", "molsde_bn_train_bwd_fused",
     "molsde_ebm_node_dot_bwd", "molsde_infonce_rows", "molsde_bn_eval", "molsde_dense_gcn_bwd", "molsde_dense_attn_bwd",
     "molsde_dense_pair_post_bwd", "molsde_dense_edge_final_bwd", "molsde_graph_mse_bwd", "molsde_from_dense_batch", "molsde_copy2d", "molsde_mean", "molsde_sum_slices", "molsde_tc_gemm_ws_floats", "molsde_tc_gemm", "molsde_tc_gemm_batched_ws_floats", "molsde_tc_gemm_batched", "molsde_tc_gemm_dw_db", "molsde_mlp3_rows",
     "molsde_schnet_cfconv", "molsde_gather_rows", "molsde_segment_reduce", "molsde_ebm_node_dot",
@@ -190,6 +190,7 @@ def lib() -> ctypes.CDLL:
     L.molsde_infonce_rows.argtypes = [P, c_int64, c_int64, c_float, c_int32, P, P, P]
     L.molsde_bn_eval.argtypes = [P, c_int64, c_int32, P, P, P, P, c_float, c_int32, P, P, P]
     L.molsde_bn_train_bwd.argtypes = [P, P, c_int64, c_int32, P, P, P, P, P, P, P, P]
+    L.molsde_bn_train_bwd_fused.argtypes = [P, P, P, c_int64, c_int32, P, P, P, P, P, P, P, P, P, P]
     L.molsde_adam_step.argtypes = [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int32, c_float, P]
     L.molsde_sde2d3d_edge_geom.argtypes = [P, P, P, c_int64, P, P, P, P, P, P, P, P]
     L.molsde_tconv_fwd.argtypes = [P, P, P, P, c_int64, P, c_float, P, P, P]

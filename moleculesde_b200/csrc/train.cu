@@ -479,7 +479,9 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* _
 // stats: fp64 sum / sum of squares per column in row chunks (fixed order) -> mean, biased var
 __global__ void __launch_bounds__(256)
 bn_partial_kernel(const float* __restrict__ X, const float* __restrict__ Y, int64_t M, int F, int64_t rows_per_chunk,
-                  const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ part) {
+                  const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ part,
+                  const float* __restrict__ relu_y = nullptr) {
+    // relu_y (mode B only): output of the fused ReLU; dy counts only where relu_y > 0 (the mask of act_bwd, applied in place)
     // mode A (Y == NULL): part0 = sum x, part1 = sum x^2.   mode B: part0 = sum dy, part1 = sum dy * xhat  (X = x, Y = dy)
     __shared__ double red[2][8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -490,7 +492,11 @@ bn_partial_kernel(const float* __restrict__ X, const float* __restrict__ Y, int6
         const float mu = Y ? mean[f] : 0.0f, rs = Y ? rstd[f] : 0.0f;
         for (int64_t r = r0 + ty; r < r1; r += 8) {
             const float x = X[r * F + f];
-            if (Y) { const float d = Y[r * F + f]; a0 += d; a1 += static_cast<double>(d) * ((x - mu) * rs); }
+            if (Y) {
+                float d = Y[r * F + f];
+                if (relu_y && !(relu_y[r * F + f] > 0.0f)) d = 0.0f;
+                a0 += d; a1 += static_cast<double>(d) * ((x - mu) * rs);
+            }
             else { a0 += x; a1 += static_cast<double>(x) * x; }
         }
     }
@@ -523,13 +529,16 @@ __global__ void bn_stats_finish_kernel(const double* __restrict__ part, int chun
     }
 }
 __global__ void bn_bwd_finish_kernel(const double* __restrict__ part, int chunks, int F, float* __restrict__ dbeta,
-                                     float* __restrict__ dgamma, int accumulate) {
+                                     float* __restrict__ dgamma, int accumulate, float* __restrict__ gbeta = nullptr,
+                                     float* __restrict__ ggamma = nullptr) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     double s = 0.0, q = 0.0;
     for (int c = 0; c < chunks; ++c) { s += part[(static_cast<size_t>(c) * 2) * F + f]; q += part[(static_cast<size_t>(c) * 2 + 1) * F + f]; }
     dbeta[f] = (accumulate ? dbeta[f] : 0.0f) + static_cast<float>(s);
     dgamma[f] = (accumulate ? dgamma[f] : 0.0f) + static_cast<float>(q);
+    if (gbeta) gbeta[f] += static_cast<float>(s);     // parameter-gradient buffers: accumulate (same add as a separate a += b pass)
+    if (ggamma) ggamma[f] += static_cast<float>(q);
 }
 // y = act((x - mean) * rstd * gamma + beta)   (act: 0 none, 1 relu)
 __global__ void bn_apply_kernel(const float* __restrict__ x, int64_t M, int F, const float* __restrict__ mean,
@@ -550,13 +559,16 @@ __global__ void rsqrt_eps_kernel(const float* __restrict__ v, int n, float eps, 
 // in the reductions: the mask is applied here AND in bn_partial via the masked dy buffer the host builds with act_bwd).
 __global__ void bn_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t M, int F,
                                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                 const float* __restrict__ dbeta, const float* __restrict__ dgamma, float* __restrict__ dx) {
+                                 const float* __restrict__ dbeta, const float* __restrict__ dgamma, float* __restrict__ dx,
+                                 const float* __restrict__ relu_y = nullptr) {
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (i >= M * F) return;
     const int f = static_cast<int>(i % F);
     const float xh = (x[i] - mean[f]) * rstd[f];
     const float inv_m = 1.0f / static_cast<float>(M);
-    dx[i] = gamma[f] * rstd[f] * (dy[i] - dbeta[f] * inv_m - xh * dgamma[f] * inv_m);
+    float d = dy[i];
+    if (relu_y && !(relu_y[i] > 0.0f)) d = 0.0f;
+    dx[i] = gamma[f] * rstd[f] * (d - dbeta[f] * inv_m - xh * dgamma[f] * inv_m);
 }
 
 // ---- flat Adam (torch.optim.Adam, amsgrad=False, weight_decay as L2):  one launch over the whole parameter buffer ----
@@ -816,21 +828,28 @@ int molsde_bn_eval(const float* x, int64_t M, int32_t F, const float* gamma, con
     bn_apply_kernel<<<blocks_for(M * F), 256, 0, as_stream(stream)>>>(x, M, F, running_mean, rstd_tmp, gamma, beta, act, y);
     return check_launch("bn_eval");
 }
-/* dy must already carry the activation mask (relu'); dgamma / dbeta are fresh outputs */
-int molsde_bn_train_bwd(const float* x, const float* dy, int64_t M, int32_t F, const float* gamma, const float* mean,
-                        const float* rstd, float* dx, float* dgamma, float* dbeta, double* ws, void* stream) {
+/* relu_y: output of the fused ReLU (NULL: dy is used as is); dgamma / dbeta are fresh outputs (this layer's totals, needed by
+ * dx); grad_gamma / grad_beta (optional): parameter-gradient buffers the totals are ADDED to in the same launch. */
+int molsde_bn_train_bwd_fused(const float* x, const float* dy, const float* relu_y, int64_t M, int32_t F, const float* gamma,
+                              const float* mean, const float* rstd, float* dx, float* dgamma, float* dbeta, float* grad_gamma,
+                              float* grad_beta, double* ws, void* stream) {
     if (!x || !dy || !gamma || !mean || !rstd || !dx || !dgamma || !dbeta || !ws || M <= 0 || F <= 0) return MOLSDE_ERR_INVALID;
     const int chunks = bn_chunks(M);
     const int64_t rpc = (M + chunks - 1) / chunks;
     dim3 grid((F + 31) / 32, chunks);
-    bn_partial_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, dy, M, F, rpc, mean, rstd, ws);
+    bn_partial_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, dy, M, F, rpc, mean, rstd, ws, relu_y);
     int st = check_launch("bn_bwd_partial");
     if (st != MOLSDE_OK) return st;
-    bn_bwd_finish_kernel<<<(F + 127) / 128, 128, 0, as_stream(stream)>>>(ws, chunks, F, dbeta, dgamma, 0);
+    bn_bwd_finish_kernel<<<(F + 127) / 128, 128, 0, as_stream(stream)>>>(ws, chunks, F, dbeta, dgamma, 0, grad_beta, grad_gamma);
     st = check_launch("bn_bwd_finish");
     if (st != MOLSDE_OK) return st;
-    bn_bwd_dx_kernel<<<blocks_for(M * F), 256, 0, as_stream(stream)>>>(x, dy, M, F, mean, rstd, gamma, dbeta, dgamma, dx);
+    bn_bwd_dx_kernel<<<blocks_for(M * F), 256, 0, as_stream(stream)>>>(x, dy, M, F, mean, rstd, gamma, dbeta, dgamma, dx, relu_y);
     return check_launch("bn_bwd_dx");
+}
+/* dy must already carry the activation mask (relu'); dgamma / dbeta are fresh outputs */
+int molsde_bn_train_bwd(const float* x, const float* dy, int64_t M, int32_t F, const float* gamma, const float* mean,
+                        const float* rstd, float* dx, float* dgamma, float* dbeta, double* ws, void* stream) {
+    return molsde_bn_train_bwd_fused(x, dy, nullptr, M, F, gamma, mean, rstd, dx, dgamma, dbeta, nullptr, nullptr, ws, stream);
 }
 
 int molsde_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

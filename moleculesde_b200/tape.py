@@ -459,16 +459,18 @@ class Tape:
         def bwd():
             if out.grad is None:
                 return
-            dy = out.grad
-            if relu:
-                dy = self.empty(M, F)
-                self._call(self.L.molsde_act_bwd, _p(y), _p(out.grad), dy.numel(), 1, _p(dy), self.s, what="act_bwd")  # y>0 <=> pre>0
+            # one call: ReLU mask applied inside the reductions and the dx pass, gamma / beta totals added to the parameter
+            # gradients by the finish kernel (was act_bwd + bn_train_bwd + two accumulation launches)
             dx, dg, db = self.empty(M, F), self.empty(F), self.empty(F)
             ws2 = self.empty(self.L.molsde_bn_ws_doubles(M, F), dtype=torch.float64)
-            self._call(self.L.molsde_bn_train_bwd, _p(x.data), _p(dy), M, F, _p(g.data), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db),
-                       _p(ws2), self.s, what="bn_train_bwd")
-            self.accum(g, dg)
-            self.accum(b, db)
+            gg = g.grad if (g.needs and g.grad is not None) else None
+            gb = b.grad if (b.needs and b.grad is not None) else None
+            self._call(self.L.molsde_bn_train_bwd_fused, _p(x.data), _p(out.grad), _p(y) if relu else None, M, F, _p(g.data), _p(mean),
+                       _p(rstd), _p(dx), _p(dg), _p(db), _p(gg), _p(gb), _p(ws2), self.s, what="bn_train_bwd")
+            if g.needs and gg is None:
+                self.accum(g, dg)
+            if b.needs and gb is None:
+                self.accum(b, db)
             self.accum(x, dx)
         self.ops.append(bwd)
         return out
