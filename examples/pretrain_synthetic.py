@@ -18,14 +18,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from moleculesde_b200 import graph as G  # noqa: E402,F401
+from moleculesde_b200 import checkpoint  # noqa: E402
 from moleculesde_b200.data import Batch, synth_molecules  # noqa: E402
-from moleculesde_b200.gnn import GNN  # noqa: E402
 from moleculesde_b200.loader import DeviceLoader, pin_batch  # noqa: E402
 from moleculesde_b200.pretrain import PretrainStep  # noqa: E402
-from moleculesde_b200.schnet import SchNet  # noqa: E402
-from moleculesde_b200.sde_2d_to_3d import SDEModel2Dto3D_02  # noqa: E402
-from moleculesde_b200.sde_3d_to_2d import SDEModel3Dto2D_node_adj_dense  # noqa: E402
 
 
 def parse():
@@ -39,8 +35,9 @@ def parse():
     p.add_argument("--emb_dim", type=int, default=300)
     p.add_argument("--num_layer", type=int, default=5)
     p.add_argument("--T", type=float, default=0.1)
-    p.add_argument("--SDE_type_2Dto3D", default="VE", choices=["VE", "VP"])
-    p.add_argument("--SDE_type_3Dto2D", default="VE", choices=["VE", "VP"])
+    p.add_argument("--SDE_type_2Dto3D", default="VE", choices=["VE", "VP", "VE02", "VP02", "VE03", "VP03"])
+    p.add_argument("--SDE_type_3Dto2D", default="VE", choices=["VE", "VP", "VE02", "VP02", "VE03", "VP03"])
+    p.add_argument("--SDE_2Dto3D_model", default="SDEModel2Dto3D_02", choices=["SDEModel2Dto3D_01", "SDEModel2Dto3D_02"])
     p.add_argument("--SDE_coeff_contrastive", type=float, default=1.0)
     p.add_argument("--SDE_coeff_generative_2Dto3D", type=float, default=1.0)
     p.add_argument("--SDE_coeff_generative_3Dto2D", type=float, default=1.0)
@@ -60,15 +57,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(args.seed)
-    molecule_model_2D = GNN(args.num_layer, args.emb_dim, JK="last", drop_ratio=0.0, gnn_type="GIN")
-    molecule_model_3D = SchNet(hidden_channels=args.emb_dim, num_filters=128, num_interactions=6, num_gaussians=51, cutoff=10,
-                               readout="mean", node_class=119)
-    SDE_2Dto3D_model = SDEModel2Dto3D_02(emb_dim=args.emb_dim, hidden_dim=32, beta_schedule=None, beta_min=0.2, beta_max=1.0,
-                                         num_diffusion_timesteps=1000, SDE_type=args.SDE_type_2Dto3D, use_extend_graph=True)
-    SDE_3Dto2D_model = SDEModel3Dto2D_node_adj_dense(
-        dim3D=args.emb_dim, c_init=2, c_hid=8, c_final=4, num_heads=4, adim=16, nhid=16, num_layers=4, emb_dim=args.emb_dim,
-        num_linears=3, beta_min=0.1 if args.SDE_type_3Dto2D == "VE" else 0.2, beta_max=1.0, num_diffusion_timesteps=1000,
-        SDE_type=args.SDE_type_3Dto2D, num_class_X=119, noise_on_one_hot=True)
+    # the module set of pretrain_MoleculeSDE.py:181-315 (schedule presets VE/VP/VE02/VP02/VE03/VP03, _01 / _02 variants)
+    models = checkpoint.build_models(emb_dim=args.emb_dim, SDE_type_2Dto3D=args.SDE_type_2Dto3D, SDE_type_3Dto2D=args.SDE_type_3Dto2D,
+                                     SDE_2Dto3D_model=args.SDE_2Dto3D_model, num_layer=args.num_layer)
+    molecule_model_2D, molecule_model_3D = models["model_2D"], models["model_3D"]
+    SDE_2Dto3D_model, SDE_3Dto2D_model = models["SDE_2Dto3D_model"], models["SDE_3Dto2D_model"]
     step = PretrainStep(molecule_model_2D, molecule_model_3D, SDE_2Dto3D_model, SDE_3Dto2D_model, dev, lr=args.lr, T=args.T,
                         coeff_contrastive=args.SDE_coeff_contrastive, coeff_2Dto3D=args.SDE_coeff_generative_2Dto3D,
                         coeff_3Dto2D=args.SDE_coeff_generative_3Dto2D, anneal_power=args.SDE_anneal_power,
@@ -102,11 +95,8 @@ def main():
             if temp_loss < optimal_loss:
                 optimal_loss = temp_loss
                 if args.output_model_dir:
-                    os.makedirs(args.output_model_dir, exist_ok=True)
                     print("save model with loss: {:.5f}".format(optimal_loss))
-                    torch.save({"model_2D": molecule_model_2D.state_dict(), "model_3D": molecule_model_3D.state_dict(),
-                                "SDE_2Dto3D_model": SDE_2Dto3D_model.state_dict(), "SDE_3Dto2D_model": SDE_3Dto2D_model.state_dict()},
-                               os.path.join(args.output_model_dir, "model_complete.pth"))
+                    checkpoint.save_model(models, args.output_model_dir, save_best=True)   # model_complete.pth, reference keys
             print("CL Loss: {:.5f}\tCL Acc: {:.5f}\t\tSDE 2Dto3D Loss: {:.5f}\tSDE 3Dto2D Loss: {:.5f}".format(
                 acc["cl_loss"] / n, acc["cl_acc"] / n, acc["loss_2d3d"] / n, acc["loss_3d2d"] / n))
             dt = time.time() - start_time

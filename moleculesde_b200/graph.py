@@ -101,12 +101,44 @@ def radius_graph(pos: torch.Tensor, r: float, batch: torch.Tensor, num_graphs: i
     return CSR(rowptr, col, ei)
 
 
-def csr_by_target(edge_index: torch.Tensor, batch: torch.Tensor, num_graphs: int) -> CSR:
-    """CSR-by-target of an arbitrary collated `[2,E]` edge list, stable in input order."""
+def edge_segments(edge_index: torch.Tensor, num_nodes: int) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """(node_ptr, edge_ptr, G) of a collated `[2,E]` edge list WITHOUT the `batch` vector (the reference's
+    `GNN.forward(x, edge_index, edge_attr)` form, `molecule_gnn_model.py:160-163`): position e of the list is a cut when every
+    node referenced before it is smaller than every node referenced from it on (molecules are contiguous node blocks whose edges
+    are stored together), so each run between cuts is a self-contained sub-graph and the per-graph CSR kernels apply.  A few
+    [E]-sized prefix-max / suffix-min passes and one size read; nodes without edges join the preceding segment."""
+    E, dev = int(edge_index.size(1)), edge_index.device
+    if E == 0:
+        z = torch.tensor([0, num_nodes], dtype=torch.int32, device=dev)
+        return z, torch.zeros(2, dtype=torch.int32, device=dev), 1
+    lo, hi = torch.minimum(edge_index[0], edge_index[1]), torch.maximum(edge_index[0], edge_index[1])
+    pm = torch.cummax(hi, 0).values
+    sm = torch.flip(torch.cummin(torch.flip(lo, [0]), 0).values, [0])
+    cut = torch.ones(E + 1, dtype=torch.bool, device=dev)
+    cut[1:E] = pm[:-1] < sm[1:]
+    edge_ptr = torch.nonzero(cut).reshape(-1)                       # [G+1], ascending, first 0, last E
+    G = int(edge_ptr.numel()) - 1
+    node_ptr = torch.empty(G + 1, dtype=torch.int64, device=dev)
+    node_ptr[:G] = sm[edge_ptr[:G]]
+    node_ptr[0] = 0
+    node_ptr[G] = num_nodes
+    return node_ptr.to(torch.int32).contiguous(), edge_ptr.to(torch.int32).contiguous(), G
+
+
+def csr_by_target(edge_index: torch.Tensor, batch: Optional[torch.Tensor], num_graphs: int, num_nodes: Optional[int] = None) -> CSR:
+    """CSR-by-target of an arbitrary collated `[2,E]` edge list, stable in input order.  `batch=None` (with `num_nodes`): the
+    sub-graph boundaries are recovered from the edge list itself (`edge_segments`)."""
     require_device(edge_index)
     edge_index = edge_index.contiguous()
-    N, E = int(batch.numel()), int(edge_index.size(1))
-    node_ptr, edge_ptr = batch_ptrs(batch, edge_index, num_graphs)
+    E = int(edge_index.size(1))
+    if batch is None:
+        assert num_nodes is not None
+        N = int(num_nodes)
+        node_ptr, edge_ptr, num_graphs = edge_segments(edge_index, N)
+        batch = edge_index   # device / stream carrier below
+    else:
+        N = int(batch.numel())
+        node_ptr, edge_ptr = batch_ptrs(batch, edge_index, num_graphs)
     deg = torch.empty(N, dtype=torch.int32, device=batch.device)
     s = stream_ptr(batch)
     check(lib().molsde_csr_by_target_count(ptr(edge_index), E, N, ptr(deg), s), "csr_count")

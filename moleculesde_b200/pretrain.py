@@ -152,7 +152,7 @@ class EdgeSet:
         self.N, self.E, self.rowptr = N, E, rowptr
         self.tgt = Index(tgt, rowptr, None, N)
         flipped = torch.stack([tgt.long(), src.long()])  # [2,E]: "target" row of csr_by_target = our source
-        by_src = csr_by_target(flipped, batch, num_graphs)
+        by_src = csr_by_target(flipped, batch, num_graphs, num_nodes=N)
         self.src = Index(src, by_src.rowptr, by_src.perm, N)
 
 
@@ -348,10 +348,7 @@ def prepare_gin(cache: dict, x: torch.Tensor, edge_index: torch.Tensor, edge_att
         return
     from .gnn import ATOM_FEATURE_DIMS, BOND_FEATURE_DIMS
     from .tape import bucket_index
-    dev = x.device
-    if batch is None:
-        batch, num_graphs = torch.zeros(x.size(0), dtype=torch.long, device=dev), 1
-    csr = csr_by_target(edge_index, batch, num_graphs)
+    csr = csr_by_target(edge_index, batch, num_graphs, num_nodes=x.size(0))   # batch None: segments recovered from the edge list
     es = EdgeSet(csr.rowptr, csr.col, batch, num_graphs) if train else None
     akeys = _keys(x, ATOM_FEATURE_DIMS)
     ekeys = _keys(edge_attr[csr.perm.long()], BOND_FEATURE_DIMS)   # CSR edge order

@@ -204,3 +204,33 @@ def test_no_cpu_fallback():
     from moleculesde_b200.graph import radius_graph
     with pytest.raises(_abi.MolsdeError):
         radius_graph(torch.zeros(4, 3), 10.0, torch.zeros(4, dtype=torch.long), 1)
+
+
+def test_edge_segments_without_batch_vector():
+    """`GNN.forward(x, edge_index, edge_attr)` carries no `batch`: the sub-graph boundaries recovered from the collated edge list
+    (graph.edge_segments) must partition nodes and edges consistently (every edge inside its segment's node range)."""
+    import torch
+    from moleculesde_b200.data import Batch, synth_molecules
+    from moleculesde_b200.graph import edge_segments
+    mols = synth_molecules(40, 5, "pcqm")
+    mols[7].edge_index = mols[7].edge_index[:, :0]          # a molecule without bonds: its atoms join the preceding segment
+    mols[7].edge_attr = mols[7].edge_attr[:0]
+    b = Batch.from_data_list(mols)
+    N = b.x.size(0)
+    node_ptr, edge_ptr, G = edge_segments(b.edge_index, N)
+    assert node_ptr[0] == 0 and node_ptr[-1] == N and edge_ptr[0] == 0 and edge_ptr[-1] == b.edge_index.size(1)
+    assert torch.all(node_ptr[1:] > node_ptr[:-1]) and torch.all(edge_ptr[1:] > edge_ptr[:-1])
+    assert 39 <= G <= 2 * 40, "about one segment per molecule (more only for disconnected molecules)"
+    for g in range(G):
+        e = b.edge_index[:, int(edge_ptr[g]):int(edge_ptr[g + 1])]
+        assert int(e.min()) >= int(node_ptr[g]) and int(e.max()) < int(node_ptr[g + 1])
+    # flipped / by-target-sorted edge lists (what the by-source CSR is built from) segment the same way
+    order = torch.argsort(b.edge_index[1], stable=True)
+    flipped = torch.stack([b.edge_index[1][order], b.edge_index[0][order]])
+    n2, e2, G2 = edge_segments(flipped, N)
+    for g in range(G2):
+        e = flipped[:, int(e2[g]):int(e2[g + 1])]
+        assert int(e.min()) >= int(n2[g]) and int(e.max()) < int(n2[g + 1])
+    # no edges at all
+    n3, e3, G3 = edge_segments(b.edge_index[:, :0], N)
+    assert G3 == 1 and n3.tolist() == [0, N] and e3.tolist() == [0, 0]

@@ -396,3 +396,28 @@ def test_gpu_generate_samples_from_testset_vs_oracle(per_launch, golden):
             assert tuple(rec.pos_gen.shape) == (n, 3) and int(rec.num_pos_gen) == R and torch.equal(rec.x, m.x)
             assert rel_err(rec.pos_gen, ref) < 2e-3, (lo, k)
             off += n
+
+
+@pytest.mark.gpu
+def test_gpu_gnn_forward_without_batch_vector(golden):
+    """`GNN.forward(x, edge_index, edge_attr)` (no `batch`, the reference's call form in the inference driver) builds its CSR from
+    segments recovered from the edge list: same bits as the `forward(data)` form, and fast on a large collated batch (the one-
+    segment fallback is quadratic in the sub-graph size)."""
+    import time
+    from moleculesde_b200.data import Batch, synth_molecules
+    from moleculesde_b200.gnn import GNN
+    dev = _dev()
+    gnn = GNN(5, 300, JK="last", drop_ratio=0.0, gnn_type="GIN")
+    gnn.load_state_dict(sd_from_manifest(golden["manifest"]["gnn"], golden["meta"]["weight_seed"]))
+    gnn = gnn.to(dev).eval()
+    b = Batch.from_data_list(synth_molecules(3000, 77, "pcqm")).to(dev)
+    gnn(b)   # warm-up
+    torch.cuda.synchronize()
+    t0 = time.time()
+    h3 = gnn(b.x, b.edge_index, b.edge_attr)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    b2 = Batch.from_data_list(synth_molecules(3000, 77, "pcqm")).to(dev)
+    h1 = gnn(b2)
+    assert torch.equal(h1, h3)
+    assert dt < 1.0, f"3-argument GNN forward on {b.x.size(0)} atoms took {dt:.2f} s"
