@@ -26,6 +26,10 @@
 #include "mma_tile.cuh"
 #include "sde2d3d_params.h"
 
+// tile GEMMs of the score network: mma.m16n8k16 (f16, fp32 accumulate) with the two-way fp16 split of both operands
+// (mma_tile.cuh); every K here is 32 and the weight blocks of the parameter blob arrive pre-split from the host (pack_f16_pairs)
+#define MOLSDE_MMA_GEMM mma_gemm_hp
+
 namespace molsde {
 
 constexpr int TE = MOLSDE_TILE_EDGES;         // 128 edges per tile
@@ -357,12 +361,12 @@ __device__ __noinline__ void phase_edge_features(const Chunk c, const float* __r
                 A[w * LDA + fe] = sn;
             }
             __syncwarp();
-            mma_gemm<4, LDA, LD32>(A, Wm, 32, lane, acc);
+            MOLSDE_MMA_GEMM<4, LDA, LD32>(A, Wm, 32, lane, acc);
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 16; ++i) A[(4 * (i >> 1) + 2 * hf + (i & 1)) * LDA + fe] = cs[i];
             __syncwarp();
-            mma_gemm<4, LDA, LD32>(A, Wm + 32 * LD32, 32, lane, acc);
+            MOLSDE_MMA_GEMM<4, LDA, LD32>(A, Wm + 32 * LD32, 32, lane, acc);
             __syncwarp();
             if (blk == 0) {
 #pragma unroll
@@ -386,7 +390,7 @@ __device__ __noinline__ void phase_edge_features(const Chunk c, const float* __r
             }
         __syncwarp();
         zero_frag(acc);
-        mma_gemm<4, LDA, LD32>(A, W + MOLSDE_P_P1_W, 32, lane, acc);
+        MOLSDE_MMA_GEMM<4, LDA, LD32>(A, W + MOLSDE_P_P1_W, 32, lane, acc);
         // ---- edge_attr = inv3d * e2d + frame  (:432) -> scratch tile (own stripe) ----
         float* sc_t = scratch + static_cast<size_t>(t) * SCR_TILE + slab * 16;
 #pragma unroll
@@ -416,7 +420,7 @@ __device__ __noinline__ void node_qkv(const Chunk c) {
     if (m0 >= c.n) return;
     float acc[12][4];
     zero_frag(acc);
-    mma_gemm<12, LDX, LD96>(sm + S_XT + m0, Wg + MOLSDE_G_WQKV, 32, lane, acc);
+    MOLSDE_MMA_GEMM<12, LDX, LD96>(sm + S_XT + m0, Wg + MOLSDE_G_WQKV, 32, lane, acc);
 #pragma unroll
     for (int nb = 0; nb < 12; ++nb) {
         const int col = nb * 8 + 2 * t4;  // 0..95: q | k | v
@@ -460,7 +464,7 @@ __device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __rest
         // e = lin_edge(edge_attr); this thread: slots 16*slab + g, +8; columns nb*8 + 2*t4 + {0,1}
         float e[4][4];
         zero_frag(e);
-        mma_gemm<4, LDA, LD32>(stripe, Wg + MOLSDE_G_WE, 32, lane, e);
+        MOLSDE_MMA_GEMM<4, LDA, LD32>(stripe, Wg + MOLSDE_G_WE, 32, lane, e);
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const int s = slab * 16 + g + 8 * rr;
@@ -568,7 +572,7 @@ __device__ __noinline__ void node_update(const Chunk c, bool silu_after, int lay
     if (m0 >= c.n) return;
     float acc[4][4], x1[4][4];
     zero_frag(acc);
-    mma_gemm<4, LDX, LD32>(XT + m0, Wg + MOLSDE_G_WS, 32, lane, acc);
+    MOLSDE_MMA_GEMM<4, LDX, LD32>(XT + m0, Wg + MOLSDE_G_WS, 32, lane, acc);
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb) {
         const int col = nb * 8 + 2 * t4;
@@ -598,7 +602,7 @@ __device__ __noinline__ void node_update(const Chunk c, bool silu_after, int lay
         }
     __syncwarp();
     zero_frag(acc);
-    mma_gemm<4, LDX, LD32>(NT + m0, Wg + MOLSDE_G_F0, 32, lane, acc);
+    MOLSDE_MMA_GEMM<4, LDX, LD32>(NT + m0, Wg + MOLSDE_G_F0, 32, lane, acc);
     __syncwarp();
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb)
@@ -617,7 +621,7 @@ __device__ __noinline__ void node_update(const Chunk c, bool silu_after, int lay
         }
     __syncwarp();
     zero_frag(acc);
-    mma_gemm<4, LDX, LD32>(NT + m0, Wg + MOLSDE_G_F3, 32, lane, acc);
+    MOLSDE_MMA_GEMM<4, LDX, LD32>(NT + m0, Wg + MOLSDE_G_F3, 32, lane, acc);
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb)
 #pragma unroll

@@ -30,6 +30,35 @@ _G = dict(WQKV=0, WS=3328, WE=4608, F0=5888, F3=7168, BQKV=8448, BS=8544, LN1_W=
 _B = dict(W1C_HI=0, W1C_LO=8192, B1=16384, W2=16512, B2=16896)
 
 
+def pack_f16_pairs(blk: torch.Tensor) -> torch.Tensor:
+    """k-major fp32 weight block [K, LD] (K even) -> the same [K, LD] words holding the two-way fp16 split the `mma.m16n8k16`
+    tile GEMMs consume (csrc/mma_tile.cuh, `mma_gemm_hp`): row 2p = half2(hi[2p], hi[2p+1]), row 2p+1 = half2(lo[2p], lo[2p+1]) per
+    column, hi = fp16(w) (round to nearest), lo = fp16(w - hi); the even-k half sits in the low 16 bits.  Same footprint and the
+    same four addresses per B fragment as the fp32 block, but no conversion instructions in the kernel's inner loop."""
+    K, LD = blk.shape
+    assert K % 2 == 0
+    hi = blk.half()
+    lo = (blk - hi.float()).half()
+
+    def words(h):
+        u = h.view(torch.int16).to(torch.int32) & 0xFFFF
+        return u[0::2] | (u[1::2] << 16)
+    out = torch.stack([words(hi), words(lo)], dim=1).reshape(K, LD)
+    return out.contiguous().view(torch.float32)
+
+
+def unpack_f16_pairs(words: torch.Tensor) -> torch.Tensor:
+    """Inverse of `pack_f16_pairs` up to the split: returns hi + lo as fp32 [K, LD] (tests)."""
+    K, LD = words.shape
+    w = words.contiguous().view(torch.int32).reshape(K // 2, 2, LD)
+
+    def halves(u):
+        lo16 = (u & 0xFFFF).to(torch.int16).view(torch.float16).float()
+        hi16 = ((u >> 16) & 0xFFFF).to(torch.int16).view(torch.float16).float()
+        return torch.stack([lo16, hi16], dim=1).reshape(K, LD)    # interleave even / odd k
+    return halves(w[:, 0]) + halves(w[:, 1])
+
+
 def _umma_kmajor_tile(w: torch.Tensor) -> torch.Tensor:
     """[R, K] matrix -> flat tcgen05 operand tile, K-major canonical no-swizzle core-matrix layout:
     index(r, k) = (k//4)*(R//8)*32 + (r//8)*32 + (r%8)*4 + (k%4)   (8 rows x 16 B core matrices, csrc/sde2d3d_params.h)."""
@@ -190,11 +219,12 @@ class SDEModel2Dto3D_02(nn.Module):
             blob[off:off + t.numel()] = t.reshape(-1)
 
         def put_kmajor(off, w, ld):
-            """nn.Linear weight [out,in] -> k-major block [in][ld] (columns >= out stay zero)."""
+            """nn.Linear weight [out,in] -> k-major block [in][ld] (columns >= out stay zero), stored as the fp16 hi/lo pair
+            words of `pack_f16_pairs` (what the mma.sync tile GEMMs of csrc/sde2d3d.cu read)."""
             out_f, in_f = w.shape
             blk = torch.zeros(in_f, ld, dtype=torch.float32, device=dev)
             blk[:, :out_f] = w.t()
-            put(off, blk)
+            put(off, pack_f16_pairs(blk))
 
         put(P_GFP_COFF_W, sd["coff_gaussian_fourier.W"])
         if self.has_distance_branch:

@@ -115,15 +115,25 @@ def test_packed_blob_roundtrip(golden):
     emb_i = g_i @ sd["coff_mlp.weight"].t() + sd["coff_mlp.bias"]
     emb_j = g_j @ sd["coff_mlp.weight"].t() + sd["coff_mlp.bias"]
     ref = torch.cat([ang, emb_i, emb_j], -1) @ sd["project.layers.0.weight"].t() + sd["project.layers.0.bias"]
-    WH = blob[M.P_H_W:M.P_H_W + 256 * M.LD32].view(256, M.LD32)[:, :32]
+    # mma.sync weight blocks are stored as fp16 hi/lo pair words (pack_f16_pairs): hi + lo reproduces the weight to ~2^-22
+    WH = M.unpack_f16_pairs(blob[M.P_H_W:M.P_H_W + 256 * M.LD32].view(256, M.LD32))[:, :32]
     got = torch.cat([g_i, g_j], -1) @ WH + blob[M.P_H_B:M.P_H_B + 32] + ang[:, :1] * blob[M.P_H_WSIN:M.P_H_WSIN + 32] \
         + ang[:, 1:] * blob[M.P_H_WCOS:M.P_H_WCOS + 32]
     torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
     base = M.P_GAT0 + 3 * M.P_GAT_SZ
-    we = blob[base + M._G["WE"]:base + M._G["WE"] + 32 * M.LD32].view(32, M.LD32)
-    assert torch.equal(we[:, :32], sd["score_network.gnn_layers.1.1.MHA.lin_edge.weight"].t()) and torch.all(we[:, 32:] == 0)
-    wqkv = blob[base + M._G["WQKV"]:base + M._G["WQKV"] + 32 * M.LD96].view(32, M.LD96)
-    assert torch.equal(wqkv[:, 32:64], sd["score_network.gnn_layers.1.1.MHA.lin_key.weight"].t())
+    we = M.unpack_f16_pairs(blob[base + M._G["WE"]:base + M._G["WE"] + 32 * M.LD32].view(32, M.LD32))
+    ref_we = sd["score_network.gnn_layers.1.1.MHA.lin_edge.weight"].t()
+    assert float((we[:, :32] - ref_we).abs().max()) <= 2.0 ** -21 * float(ref_we.abs().max()) and torch.all(we[:, 32:] == 0)
+    wqkv = M.unpack_f16_pairs(blob[base + M._G["WQKV"]:base + M._G["WQKV"] + 32 * M.LD96].view(32, M.LD96))
+    ref_k = sd["score_network.gnn_layers.1.1.MHA.lin_key.weight"].t()
+    assert float((wqkv[:, 32:64] - ref_k).abs().max()) <= 2.0 ** -21 * float(ref_k.abs().max())
+    # the packing itself: even k in the low half, hi row then lo row
+    blk = torch.tensor([[1.0, -2.5], [3.0e-5, 0.1], [7.0, 0.0], [-0.33, 1e-3]])
+    pk2 = M.pack_f16_pairs(blk).view(torch.int32)
+    h = blk.half()
+    assert pk2[0, 0].item() & 0xFFFF == h[0, 0].view(torch.int16).item() & 0xFFFF
+    assert (pk2[0, 0].item() >> 16) & 0xFFFF == h[1, 0].view(torch.int16).item() & 0xFFFF
+    assert float((M.unpack_f16_pairs(pk2.view(torch.float32)) - blk).abs().max()) <= 2.0 ** -21
     base = M.P_BASIS0 + M.P_BASIS_SZ
     assert torch.equal(blob[base + M._B["W2"]:base + M._B["W2"] + 384].view(3, 128),
                        sd["score_network.basis_mlp_modules.1.2.weight"])
