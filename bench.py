@@ -348,9 +348,10 @@ def run_b200(args):
                          "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (derived dense TF32)" if peaks
                                          else "fallback 1400/2"),
                          "note": "achieved = ALGORITHMIC FLOPs 2*(34,624 E_x + 24,576 N) per score eval x 2000 evals / kernel time. "
-                                 "The kernel issues 3x that on the tensor pipe (3xTF32 split for fp32-grade accuracy) through "
-                                 "legacy mma.sync (measured 476 MAC/clk/SM, profiles/r1_ubench_mma_rate.txt). traffic = ncu dram "
-                                 "bytes of one launch: node/edge state stays in shared memory for all 1000 steps."},
+                                 "The kernel issues 3x that on the tensor pipe (two-way fp16 operand split, 3 product terms, for "
+                                 "fp32-grade accuracy): legacy mma.sync m16n8k16 for the edge/node tile GEMMs (measured 953 "
+                                 "MAC/clk/SM, profiles/r1_ubench_mma_rate.txt), tcgen05 3xTF32 for the basis MLP. traffic = ncu dram "
+                                 "bytes of one launch (v4 capture): node/edge state stays in shared memory for all 1000 steps."},
             "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                              "note": "north_star's HBM view with the layer-granular algorithmic bytes of SURVEY 8(d): "
                                      "(156 N + 132 E_x + 4(N+1) + 266k) per eval + 48 N per step; small by construction (fused)"},
