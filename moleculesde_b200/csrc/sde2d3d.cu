@@ -12,11 +12,11 @@
 //   * edges are processed in CSR-by-target order in tiles of <= 128 edges aligned to target nodes,
 //     so the segment softmax / mean aggregation of a tile is self-contained and runs in a fixed,
 //     atomic-free, ascending-source order (deterministic, same order as the reference scatter);
-//   * every per-edge / per-node MLP is a tile GEMM on the tensor cores: mma.sync m16n8k8 TF32 with
-//     the 3xTF32 error-compensated split (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate), which
-//     keeps fp32-grade accuracy (north_star: 1e-4) at ~3x the math rate the FFMA register tile reaches
-//     from shared memory (profiles/r1_ubench_mma_rate.txt).  A operands are k-major in smem with a
-//     padded leading dimension (== 8 mod 32) so fragment loads are bank-conflict free;
+//   * every per-edge / per-node MLP is a tile GEMM on the tensor cores: mma.sync m16n8k16 (f16 inputs, fp32 accumulate)
+//     with an error-compensated two-way fp16 split of both operands (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi; weights
+//     pre-split on the host), which keeps fp32-grade accuracy (north_star: 1e-4) at ~6x the math rate the FFMA
+//     register tile reaches from shared memory (profiles/r1_ubench_mma_rate.txt); the basis MLP runs on tcgen05
+//     (3xTF32, TMEM accumulator).  A operands are k-major in smem with a padded leading dimension (== 8 mod 32);
 //   * the per-edge attribute (32 floats) is the only per-edge state that survives between phases; it
 //     goes to an L2-resident per-CTA scratch in the smem tile layout [32][136], so re-loading it is
 //     a straight 17 KB cp.async copy.
