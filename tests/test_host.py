@@ -244,3 +244,42 @@ def test_edge_segments_without_batch_vector():
     # no edges at all
     n3, e3, G3 = edge_segments(b.edge_index[:, :0], N)
     assert G3 == 1 and n3.tolist() == [0, N] and e3.tolist() == [0, 0]
+
+
+def test_edge_segments_randomised_edge_orders():
+    """Segments stay valid when a molecule's edges are stored in any order and when a molecule has several components: a cut may
+    only appear where the node ranges before / after it are disjoint (coarser segments are fine, wrong ones are not)."""
+    import torch
+    from moleculesde_b200.data import Batch, synth_molecules
+    from moleculesde_b200.graph import edge_segments
+    g = torch.Generator().manual_seed(11)
+    for seed in range(6):
+        mols = synth_molecules(12, 100 + seed, "pcqm")
+        for m in mols:
+            E = m.edge_index.size(1)
+            keep = torch.rand(E // 2, generator=g) > 0.25            # drop ~25 % of the bonds (both directions): fragments appear
+            keep = keep.repeat_interleave(2)
+            perm = torch.randperm(int(keep.sum()), generator=g)      # and shuffle the edge order inside the molecule
+            m.edge_index = m.edge_index[:, keep][:, perm]
+            m.edge_attr = m.edge_attr[keep][perm]
+        b = Batch.from_data_list(mols)
+        N, E = b.x.size(0), b.edge_index.size(1)
+        node_ptr, edge_ptr, G = edge_segments(b.edge_index, N)
+        assert int(node_ptr[0]) == 0 and int(node_ptr[-1]) == N and int(edge_ptr[-1]) == E
+        seg_of_edge = torch.bucketize(torch.arange(E), edge_ptr[1:].long(), right=True)
+        lo, hi = node_ptr[seg_of_edge].long(), node_ptr[seg_of_edge + 1].long()
+        assert torch.all((b.edge_index >= lo) & (b.edge_index < hi)), "every edge lies inside the node range of its segment"
+        assert G <= E and G >= 1
+
+
+def test_pack_f16_pairs_randomised():
+    import torch
+    from moleculesde_b200.sde_2d_to_3d import pack_f16_pairs, unpack_f16_pairs
+    g = torch.Generator().manual_seed(3)
+    for scale in (1e-3, 1.0, 50.0):
+        blk = torch.randn(64, 40, generator=g) * scale
+        back = unpack_f16_pairs(pack_f16_pairs(blk))
+        # hi + lo keeps 22 significant bits, or 2^-25 absolutely where lo falls into fp16's subnormal range
+        tol = torch.maximum(blk.abs() * 2.0 ** -21, torch.full_like(blk, 2.0 ** -24))
+        assert torch.all((back - blk).abs() <= tol)
+    assert torch.equal(pack_f16_pairs(torch.zeros(4, 8)), torch.zeros(4, 8))
