@@ -20,8 +20,8 @@ LIB_PATH = os.path.join(_HERE, "libmolsde_b200.so")
 MAX_MOL_NODES = 128
 CHUNK_MAX_NODES = 224
 TILE_EDGES = 128
-TILE_LD = 136
-TILE_FLOATS = 32 * TILE_LD
+TILE_LD = 136                      # SchNet edge tiles (csrc/schnet.cu)
+TILE_FLOATS = 32 * TILE_EDGES      # edge_2D_emb tile [8 feature quads][128 slots][4] (molsde_tile_floats())
 HID = 32
 EMB = 300
 MAX_CHUNK_TILES = 64
@@ -71,6 +71,20 @@ class PCConfig(Structure):
 
 
 _lib: Optional[ctypes.CDLL] = None
+
+# Kernels that update parameters or buffers IN PLACE through raw pointers (the flat Adam step, the train-mode BatchNorm running
+# statistics) do not bump torch's per-tensor `_version`.  Every such wrapper calls `touch_params()`; every packed-weight cache
+# (SDEModel2Dto3D_02.packed_params, SchNet._filters, EdgeScoreNetwork_dense._pack) carries `param_epoch()` in its key.
+_param_epoch = 0
+
+
+def param_epoch() -> int:
+    return _param_epoch
+
+
+def touch_params() -> None:
+    global _param_epoch
+    _param_epoch += 1
 
 
 def lib() -> ctypes.CDLL:

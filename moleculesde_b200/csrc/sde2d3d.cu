@@ -5,29 +5,31 @@
 // examples/pretrain_MoleculeSDE_inference_2D_to_3D_VE_VP.py:92-212.
 //
 // Design (B200-first):
-//   * one persistent CTA (512 threads = 2 decoupled groups of 8 warps, 1 CTA/SM, ~219 KB smem) owns one "chunk" = a set of whole
-//     molecules with <= 224 atoms; node state (hidden features, q/k/v, positions, score) lives in
-//     shared memory for the WHOLE score evaluation -- and, in the PC kernel, for all 1000 reverse
-//     steps -- so HBM sees only the initial/final positions;
-//   * edges are processed in CSR-by-target order in tiles of <= 128 edges aligned to target nodes,
-//     so the segment softmax / mean aggregation of a tile is self-contained and runs in a fixed,
-//     atomic-free, ascending-source order (deterministic, same order as the reference scatter);
-//   * every per-edge / per-node MLP is a tile GEMM on the tensor cores: mma.sync m16n8k16 (f16 inputs, fp32 accumulate)
-//     with an error-compensated two-way fp16 split of both operands (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi; weights
-//     pre-split on the host), which keeps fp32-grade accuracy (north_star: 1e-4) at ~6x the math rate the FFMA
-//     register tile reaches from shared memory (profiles/r1_ubench_mma_rate.txt); the basis MLP runs on tcgen05
-//     (3xTF32, TMEM accumulator).  A operands are k-major in smem with a padded leading dimension (== 8 mod 32);
-//   * the per-edge attribute (32 floats) is the only per-edge state that survives between phases; it
-//     goes to an L2-resident per-CTA scratch in the smem tile layout [32][136], so re-loading it is
-//     a straight 17 KB cp.async copy.
+//   * one persistent CTA (512 threads, 1 CTA/SM, ~220 KB smem) owns one "chunk" = a set of whole molecules with <= 224 atoms;
+//     node state (hidden features, q/k/v, positions, score) lives in shared memory for the WHOLE score evaluation -- and, in
+//     the PC kernel, for all 1000 reverse steps -- so HBM sees only the initial/final positions;
+//   * edges are processed in CSR-by-target order in tiles of <= 128 edges aligned to target nodes, so the segment softmax /
+//     mean aggregation of a tile is self-contained and runs in a fixed, atomic-free, ascending-source order (deterministic,
+//     same order as the reference scatter);
+//   * the CTA is four decoupled QUADS of 128 threads.  A quad owns one edge tile at a time and THREAD = EDGE SLOT = TMEM LANE:
+//     every per-edge GEMM (Fourier-feature layers, project.1, lin_edge, basis MLP layer 0) is a tcgen05.mma kind::f16
+//     (M = 128 edges, fp32 accumulator in the quad's 128 TMEM columns) with an error-compensated two-way fp16 split of both
+//     operands (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi: 22-bit operands, north_star's 1e-4 holds with 3 orders of margin), issued
+//     by the quad's first thread and tracked by the quad's own mbarriers; epilogues read the accumulator row of their edge
+//     with tcgen05.ld and keep all 32 (or 128) columns in registers, so bias / SiLU / attention logits / the 128 -> 3
+//     projection need no cross-lane traffic.  Quads synchronise on named barriers only; four tiles are in flight per SM and
+//     hide each other's MMA / TMA / MUFU latencies;
+//   * the per-edge attribute is written ONCE per evaluation by the feature phase, already as the fp16 hi/lo A-operand tile
+//     (canonical K-major core-matrix layout) into an L2-resident per-CTA scratch record; the four GAT layers and the two
+//     basis modules fetch it with one TMA bulk copy per tile (cp.async.bulk + mbarrier complete_tx) straight into the
+//     operand slot -- no thread touches it again;
+//   * the per-node GEMMs (q|k|v, lin_skip, FFN: <= 224 rows) stay on warp-level mma.sync m16n8k16 with the same split.
 #include <math_constants.h>
 
 #include "common.cuh"
 #include "mma_tile.cuh"
 #include "sde2d3d_params.h"
 
-// tile GEMMs of the score network: mma.m16n8k16 (f16, fp32 accumulate) with the two-way fp16 split of both operands
-// (mma_tile.cuh); every K here is 32 and the weight blocks of the parameter blob arrive pre-split from the host (pack_f16_pairs)
 #define MOLSDE_MMA_GEMM mma_gemm_hp
 
 namespace molsde {
@@ -35,66 +37,67 @@ namespace molsde {
 constexpr int TE = MOLSDE_TILE_EDGES;         // 128 edges per tile
 constexpr int NTHREADS = 512;
 constexpr int NWARPS = NTHREADS / 32;
-constexpr int GROUPS = 2;                     // two 8-warp groups work on alternate tiles, decoupled
-constexpr int GTHREADS = NTHREADS / GROUPS;
+constexpr int QUADS = 4;                      // four 128-thread quads, one edge tile each
+constexpr int QT = NTHREADS / QUADS;
 constexpr int MAXN = MOLSDE_CHUNK_MAX_NODES;  // 224 atoms per chunk
 constexpr int MAXT = 64;                      // tiles per chunk
-constexpr int LDA = MOLSDE_TILE_LD;           // 136: leading dim of a k-major edge tile
 constexpr int LDX = 232;                      // leading dim of the k-major node matrix (>= MAXN, == 8 mod 32)
-constexpr int TILE_FLOATS = 32 * LDA;         // one [32][136] per-edge attribute tile
-constexpr int FRAME_FLOATS = 9 * TE;          // per-edge SE(3) frame (diff, cross, vertical) cached by E0 for the basis phases
-constexpr int SCR_TILE = TILE_FLOATS + FRAME_FLOATS;  // per-tile scratch record: edge_attr [32][136] | frame [9][128]
-constexpr int LDM = 33;                       // padded row of the slot-major message tile [TE][33]
 constexpr int LD32 = MOLSDE_LD32, LD96 = MOLSDE_LD96;
+constexpr int E2D_TILE_FLOATS = 32 * TE;      // edge_2D_emb output tile [8 feature quads][128 slots][4]
 constexpr float EPS = 1e-6f;                  // SDE_model_2D_to_3D.py:10
 constexpr float LN_EPS = 1e-5f;
+static_assert(QT == TE, "thread = edge slot inside a quad");
 
-// ---- shared memory carve-up (float offsets) ----
-constexpr int S_XT = 0;                      // [32][LDX]   node hidden, k-major
-constexpr int S_Q = S_XT + 32 * LDX;         // [MAXN][32]  query  (aggregate written in place)
-constexpr int S_K = S_Q + 32 * MAXN;         // [MAXN][32]
-constexpr int S_V = S_K + 32 * MAXN;         // [MAXN][32]
-constexpr int S_WG = S_V + 32 * MAXN;        // [P_GAT_SZ]  weights of the current GAT layer
-constexpr int S_A = S_WG + MOLSDE_P_GAT_SZ;  // [GROUPS][32][LDA] A operand per group (k-major); also the message tile
-                                             //                   [TE][33] of the group and the node staging [32][LDX]
-constexpr int S_L = S_A + GROUPS * TILE_FLOATS;  // [GROUPS][TE][8]    logits / per-warp geometry scalars
-constexpr int S_MS = S_L + GROUPS * TE * 8;      // [GROUPS][2][TE][8] softmax max, sum / basis mix
-constexpr int S_POS = S_MS + GROUPS * 2 * TE * 8;  // [MAXN*3]
-constexpr int S_GRAD = S_POS + MAXN * 3;     // [MAXN*3]  network output ("gradient")
-constexpr int S_SCORE = S_GRAD + MAXN * 3;   // [MAXN*3]
-constexpr int S_NOISE = S_SCORE + MAXN * 3;  // [MAXN*3]
-constexpr int S_RED = S_NOISE + MAXN * 3;    // [64]
-constexpr int S_FLOATS = S_RED + 64;
-// int region (after the floats)
-constexpr int SI_ROWL = 0;                   // [MAXN+1] edge offsets local to the chunk
-constexpr int SI_TTGT = SI_ROWL + MAXN + 1;  // [MAXT+1] tile target boundaries local to the chunk
-constexpr int SI_ESRC = SI_TTGT + MAXT + 1;  // [GROUPS][TE]
-constexpr int SI_ETGT = SI_ESRC + GROUPS * TE;  // [GROUPS][TE]
-constexpr int SI_MISC = SI_ETGT + GROUPS * TE;  // [4]  (0: work item, 1: TMEM base address)
-constexpr int SI_BAR = ((S_FLOATS + SI_MISC + 4 + 1) & ~1) - S_FLOATS;  // [2] mbarrier of the tcgen05 commits (8-byte aligned)
-constexpr int SI_TMABAR = SI_BAR + 2;        // [2] mbarrier of the TMA bulk weight copies (SI_MISC + 2 holds its phase)
-constexpr int S_INTS = SI_TMABAR + 2;
-// (source, target) of every edge slot of the first SLOT_CACHE_TILES tiles of the chunk as chunk-local byte indices (< MAXN <= 255):
-// static per batch, resolved once per chunk (load_chunk) instead of by a dependent global load + bisection at each of the
-// 7 tile visits of every score evaluation.  [tile][0: src, 1: tgt][TE] uint8, behind the int region.
-constexpr int SLOT_CACHE_TILES = 31;
-constexpr size_t SMEM_BYTES = sizeof(float) * S_FLOATS + sizeof(int) * S_INTS + static_cast<size_t>(SLOT_CACHE_TILES) * 2 * TE;
-static_assert(MAXN <= 255, "slot cache stores chunk-local node indices as bytes");
+// ---- per-tile scratch record (global memory, L2 resident), byte offsets ----
+constexpr int REC_EA_HI = 0;                  // edge_attr, fp16 hi part: A-operand tile [128 rows][32 k] = [4 k-chunks][128][8 halves]
+constexpr int REC_EA_LO = 8192;               // fp16 lo part
+constexpr int REC_FRAME = 16384;              // fp32 [9][128]: coord_diff | coord_cross | coord_vertical per slot
+constexpr int REC_SLOT = REC_FRAME + 9 * TE * 4;  // uint8 [2][128]: chunk-local source / target of every slot (static per chunk)
+constexpr int REC_BYTES = REC_SLOT + 2 * TE;  // 21,248
+constexpr int REC_FLOATS = REC_BYTES / 4;
+static_assert(REC_BYTES % 128 == 0 && MAXN <= 255, "record alignment / byte-sized node indices");
+
+// ---- shared memory carve-up (byte offsets) ----
+constexpr int SB_XT = 0;                                // f32 [32][LDX] node hidden, k-major
+constexpr int SB_BIG = SB_XT + 32 * LDX * 4;            // phase-dependent union
+//   GAT layers
+constexpr int SB_Q = SB_BIG;                            // f32 [MAXN][32] query (aggregate written in place), rows XOR-swizzled
+constexpr int SB_K = SB_Q + MAXN * 32 * 4;
+constexpr int SB_V = SB_K + MAXN * 32 * 4;
+constexpr int SB_WP = SB_V + MAXN * 32 * 4;             // resident weights of the current GAT layer [G_WP_SZ floats]
+constexpr int SB_R = SB_WP + MOLSDE_G_WP_SZ * 4;        // q|k|v weights / per-quad edge-phase slots / FFN staging
+constexpr int GAT_SLOT = 16384 + 4096;                  // per quad: A operand hi|lo (later the message tile [128][32] f32) + logits [128][8]
+constexpr int SB_BIG_END = SB_R + QUADS * GAT_SLOT;
+//   feature phase (E0)
+constexpr int SB_E0W = SB_BIG;                          // E0 section of the blob
+constexpr int SB_E0A = SB_E0W + MOLSDE_P_E0_END * 4;    // per quad: two A slots [hi 8 KB | lo 8 KB]
+constexpr int E0_SLOT = 16384;
+//   basis phase
+constexpr int SB_BW = SB_BIG;                           // basis section of the blob
+constexpr int SB_BA = SB_BW + MOLSDE_P_BASIS_STRIDE * 4;  // per quad: A operand [128 x 64] hi (16 KB) | lo (16 KB)
+constexpr int B_SLOT = 32768;
+constexpr int SB_MIX = SB_BA + QUADS * B_SLOT;          // per quad f32 [3][128]
+//   predictor / corrector update (between evaluations)
+constexpr int SB_SCORE = SB_BIG;                        // f32 [MAXN*3]
+constexpr int SB_NOISE = SB_SCORE + MAXN * 3 * 4;
+// persistent tail
+constexpr int SB_POS = SB_BIG_END;                      // f32 [MAXN*3]
+constexpr int SB_GRAD = SB_POS + MAXN * 3 * 4;          // f32 [MAXN*3] network output ("gradient")
+constexpr int SB_RED = SB_GRAD + MAXN * 3 * 4;          // f32 [64]
+constexpr int SB_INT = SB_RED + 256;
+constexpr int SI_ROWL = 0;                              // [MAXN+1] edge offsets local to the chunk
+constexpr int SI_TTGT = SI_ROWL + MAXN + 1;             // [MAXT+1] tile target boundaries local to the chunk
+constexpr int SI_MISC = SI_TTGT + MAXT + 1;             // [0] work item, [1] TMEM base, [2] phase of the CTA-wide TMA barrier
+constexpr int SB_BAR = SB_INT + ((SI_MISC + 6) * 4 + 127) / 128 * 128;  // mbarriers (8 B): quad MMA [q][2], quad TMA [q], CTA TMA
+constexpr int NUM_BARS = 3 * QUADS + 1;
+constexpr size_t SMEM_BYTES = SB_BAR + NUM_BARS * 8;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
-static_assert(MOLSDE_P_E0_END <= 3 * 32 * MAXN, "E0 weights are staged in the q/k/v region");
-static_assert(MOLSDE_P_BASIS_SZ <= 3 * 32 * MAXN, "basis weights (tcgen05 B tiles + small vectors) are staged in the q/k/v region");
-static_assert(32 * LDX <= GROUPS * TILE_FLOATS, "node staging aliases the A region");
-static_assert(TE * LDM <= TILE_FLOATS, "message tile aliases the group's A region");
-static_assert(LDX >= MAXN && LDX % 32 == 8 && LDA % 32 == 8, "padded leading dimensions");
-static_assert(S_A % 4 == 0 && S_WG % 4 == 0 && S_Q % 4 == 0 && TILE_FLOATS % 4 == 0, "16B alignment for cp.async");
-// tcgen05 operand tiles of the basis MLP: A hi/lo [128 x 64] over the (dead) GAT-weight + A regions, B hi/lo in the q/k/v region
-constexpr int UMMA_TILE = 128 * 64;          // floats per operand tile
-constexpr int S_UA_HI = S_WG, S_UA_LO = S_WG + UMMA_TILE;
-static_assert(S_UA_LO + UMMA_TILE <= S_L, "tcgen05 A tiles must fit before the logits region");
-static_assert((S_WG * 4) % 128 == 0 && (S_Q * 4) % 128 == 0, "operand tiles are 128B aligned");
-static_assert(GROUPS * TE * 8 >= 4 * TE * 4, "partial dyn buffer [4][TE][4]");
-constexpr uint32_t UMMA_LBO = 2048, UMMA_SBO = 128;  // bytes: next 16B K-chunk / next 8-row group (K-major, no swizzle)
-constexpr uint32_t TMEM_COLS = 256;  // two 128-column accumulators (tile t / t+1 of the basis GEMM pipeline)
+static_assert(SB_BIG % 128 == 0 && SB_WP % 128 == 0 && SB_R % 128 == 0 && SB_E0A % 128 == 0 && SB_BA % 128 == 0 && SB_BAR % 8 == 0,
+              "operand tiles / barriers alignment");
+static_assert(SB_E0A + QUADS * 2 * E0_SLOT <= SB_BIG_END && SB_MIX + QUADS * 3 * TE * 4 <= SB_BIG_END, "phase unions fit");
+static_assert(QUADS * GAT_SLOT >= 32 * LDX * 4 && QUADS * GAT_SLOT >= (MOLSDE_P_GAT_SZ - MOLSDE_G_WQKV) * 4, "R region uses");
+static_assert((MOLSDE_G_WEC * 4) % 128 == 0 && (MOLSDE_P_E0_BT * 4) % 128 == 0, "B tiles are 128B aligned inside their sections");
+constexpr uint32_t TMEM_COLS = 512;  // 128 accumulator columns per quad
 
 // optional per-phase cycle accounting (build with MOLSDE_PROF=1; read back with molsde_debug_read_prof)
 #ifdef MOLSDE_PROF
@@ -119,50 +122,156 @@ struct Chunk {
     const float* ffn_keep;   // [4 layers][N][32]
     float inv_keep;          // 1 / (1 - p)
     int64_t E_total, N_total;
+    int32_t* status_flag;
 };
+__device__ __forceinline__ uint8_t* smem_bytes(const Chunk& c) { return reinterpret_cast<uint8_t*>(c.sm); }
+template <typename T>
+__device__ __forceinline__ T* smem_at(const Chunk& c, int byte_off) { return reinterpret_cast<T*>(smem_bytes(c) + byte_off); }
+
+// Per-thread synchronisation state, carried through the phases in one register:
+//   bit 0 / 1: phase parity of the quad's two MMA barriers, bit 2: of the quad's TMA barrier, bit 3: a wait timed out (sticky)
+constexpr uint32_t QS_MMA0 = 1u, QS_MMA1 = 2u, QS_TMA = 4u, QS_DEAD = 8u;
 
 // ---------------------------------------------------------------------------------------
 // fast, accuracy-checked elementwise helpers (absolute / relative error ~1e-6, far below the 1e-4 bar)
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
-// sin/cos of an fp32 argument of magnitude up to ~1e5: 2-term Cody-Waite reduction by 2*pi (exact
-// products through FMA), then the SFU approximations on |r| <= pi (abs error < 1e-6).
+// sin/cos of an fp32 argument of magnitude up to ~1e5: 2-term Cody-Waite reduction by 2*pi (exact products through FMA; the
+// rounding to the nearest multiple uses the 1.5*2^23 magic constant, i.e. two FADDs instead of a conversion-pipe FRND), then
+// the SFU approximations on |r| <= pi (abs error < 1e-6).
 __device__ __forceinline__ void sincos_reduced(float x, float& s, float& c) {
-    const float k = rintf(x * 0.15915494309189535f);
+    const float k = __fsub_rn(__fadd_rn(x * 0.15915494309189535f, 12582912.0f), 12582912.0f);
     float r = fmaf(-k, 6.2831854820251465f, x);
     r = fmaf(-k, -1.7484555314695172e-7f, r);
     s = __sinf(r);
     c = __cosf(r);
 }
 
-// cooperative global->shared copy of `nfloat` floats (multiple of 4, 16B aligned both sides)
-__device__ __forceinline__ void stage_async(float* dst, const float* __restrict__ src, int nfloat) {
-    for (int i = threadIdx.x * 4; i < nfloat; i += NTHREADS * 4) cp_async16(dst + i, src + i);
-    cp_async_commit();
-}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-// Weight blocks of a phase (35-68 KB, contiguous in the parameter blob): ONE TMA bulk copy (cp.async.bulk, 1-D) issued by
-// thread 0 and tracked by an mbarrier (complete_tx) instead of ~8 cp.async per thread.  Call with all threads after a
-// __syncthreads() (the destination may still be read by the previous phase before that); returns when the data is
-// visible to every thread.  The barrier's phase bit lives in shared memory (si[SI_MISC + 2]) because the number of copies
-// per score evaluation is odd.
-__device__ __forceinline__ void stage_bulk(int* si, float* dst, const float* __restrict__ src, int nfloat) {
-    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(si + SI_TMABAR));
-    const uint32_t phase = static_cast<uint32_t>(si[SI_MISC + 2]);
+// ---- mbarrier / TMA bulk copy / tcgen05 primitives --------------------------------------------
+__device__ __forceinline__ uint32_t bar_addr(const Chunk& c, int idx) { return smem_u32(smem_bytes(c) + SB_BAR + idx * 8); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// Bounded parity wait: a descriptor / protocol bug must not hang the GPU.  After the first timeout the thread's state word
+// carries QS_DEAD, every later wait returns at once (the launch finishes quickly with garbage) and the status word is set.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t& qs, uint32_t which, int32_t* status_flag) {
+    if (!(qs & QS_DEAD)) {
+        const uint32_t parity = (qs & which) ? 1u : 0u;
+        uint32_t done = 0;
+        for (int it = 0; it < (1 << 22) && !done; ++it)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done) {
+            qs |= QS_DEAD;
+            if (status_flag) atomicExch(status_flag, -7);
+        }
+    }
+    qs ^= which;
+}
+__device__ __forceinline__ void quad_sync(int q) { asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(QT) : "memory"); }
+
+// Weight sections of a phase (13-46 KB each, contiguous in the parameter blob): TMA bulk copies (cp.async.bulk, 1-D) issued by
+// thread 0 and tracked by the CTA-wide mbarrier (complete_tx).  Call with all threads after a __syncthreads() (the destinations
+// may still be read by the previous phase before that); returns when the data is visible to every thread.
+__device__ __forceinline__ void stage_bulk2(const Chunk& c, void* dst0, const float* __restrict__ src0, int nfloat0, void* dst1,
+                                            const float* __restrict__ src1, int nfloat1) {
+    const uint32_t bar = bar_addr(c, 3 * QUADS);
+    const uint32_t parity = static_cast<uint32_t>(c.si[SI_MISC + 2]);
     if (threadIdx.x == 0) {
-        const uint32_t bytes = static_cast<uint32_t>(nfloat) * 4u;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of dst before the async-proxy write
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src), "r"(bytes), "r"(bar) : "memory");
+        fence_proxy_async_smem();  // earlier generic accesses of the destinations before the async-proxy writes
+        mbar_expect_tx(bar, static_cast<uint32_t>(nfloat0 + nfloat1) * 4u);
+        bulk_g2s(smem_u32(dst0), src0, static_cast<uint32_t>(nfloat0) * 4u, bar);
+        if (nfloat1 > 0) bulk_g2s(smem_u32(dst1), src1, static_cast<uint32_t>(nfloat1) * 4u, bar);
     }
     uint32_t done = 0;
-    for (int it = 0; it < (1 << 24) && !done; ++it)
+    for (int it = 0; it < (1 << 22) && !done; ++it)
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     __syncthreads();
-    if (threadIdx.x == 0) si[SI_MISC + 2] = static_cast<int>(phase ^ 1u);  // read again only after several more barriers
+    if (threadIdx.x == 0) c.si[SI_MISC + 2] = static_cast<int>(parity ^ 1u);  // read again only after several more barriers
+}
+
+// tcgen05 shared-memory matrix descriptor, K-major, no swizzle (cute/arch/mma_sm100_desc.hpp): core matrices of 8 rows x 16 B;
+// LBO = byte distance between core matrices adjacent in K, SBO = 128 B between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    return static_cast<uint64_t>((saddr & 0x3FFFF) >> 4)                   // start address  [0,14)
+           | (static_cast<uint64_t>(lbo_bytes >> 4) << 16)                  // leading byte offset [16,30)
+           | (static_cast<uint64_t>(128u >> 4) << 32)                       // stride byte offset  [32,46)
+           | (static_cast<uint64_t>(1) << 46);                              // version 1 (Blackwell), layout = no swizzle
+}
+// D[tmem, 128 lanes x N columns] (+)= A[smem, 128 x 16] . B[smem, N x 16]^T, fp16 inputs, fp32 accumulate; issued by ONE thread
+template <int N>
+__device__ __forceinline__ void umma_f16_m128(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    // instruction descriptor: D = F32 (1<<4), A = B = F16 (0<<7, 0<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    constexpr uint32_t idesc = (1u << 4) | ((static_cast<uint32_t>(N) >> 3) << 17) | ((128u >> 4) << 24);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Split-fp16 GEMM: three passes (lo*hi, hi*lo, hi*hi; small terms first) over `ksteps` K=16 steps of an A tile [128 x 16*ksteps]
+// (hi at a_hi, lo at a_lo; k-chunk stride 2048 B) and a B tile [N x 16*ksteps] (k-chunk stride N*16 B).
+template <int N>
+__device__ __forceinline__ void umma_split_f16(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int ksteps,
+                                               uint32_t accumulate) {
+    constexpr uint32_t LBO_A = 2048, LBO_B = N * 16;
+#pragma unroll 1
+    for (int term = 0; term < 3; ++term) {
+        const uint32_t pa = (term == 0) ? a_lo : a_hi, pb = (term == 1) ? b_lo : b_hi;
+#pragma unroll 1
+        for (int kb = 0; kb < ksteps; ++kb) {
+            umma_f16_m128<N>(tmem_d, umma_desc(pa + kb * 2 * LBO_A, LBO_A), umma_desc(pb + kb * 2 * LBO_B, LBO_B), accumulate);
+            accumulate = 1;
+        }
+    }
+}
+// accumulator columns [col, col+32) / [col, col+8) of this thread's TMEM lane (all 32 lanes of the warp must call)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&f)[32]) {
+    uint32_t v[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&f)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[i]);
+}
+// 8 consecutive-k values of row r -> fp16 hi / lo, one 16 B chunk each, into an operand tile (k-chunk stride 2048 B)
+__device__ __forceinline__ void split8(const float* v, uint4& h, uint4& l) {
+    split_f16x2(v[0], v[1], h.x, l.x);
+    split_f16x2(v[2], v[3], h.y, l.y);
+    split_f16x2(v[4], v[5], h.z, l.z);
+    split_f16x2(v[6], v[7], h.w, l.w);
+}
+__device__ __forceinline__ void store_a_chunk(uint8_t* hi, uint8_t* lo, int r, int kc, const float* v) {
+    uint4 h, l;
+    split8(v, h, l);
+    *reinterpret_cast<uint4*>(hi + kc * 2048 + r * 16) = h;
+    *reinterpret_cast<uint4*>(lo + kc * 2048 + r * 16) = l;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -194,18 +303,9 @@ __device__ __forceinline__ Frame coord2basis(const float* pr, const float* pc) {
     return f;
 }
 
-// q / k / v rows are [node][32] with the column XOR-swizzled by the node index (4-float granules): the per-edge gathers
-// k[src], v[src] of 8 consecutive slots then hit 8 different bank groups instead of one (profiles/r1_pc_v4_conflicts.txt)
+// q / k / v rows are [node][32] with the 16-byte granules XOR-swizzled by the node index: the per-edge row gathers
+// k[src], v[src] of 8 consecutive slots then hit 8 different bank groups instead of one.
 __device__ __forceinline__ int qkv_idx(int node, int col) { return node * 32 + (col ^ ((node & 7) << 2)); }
-
-// ---- group / tile helpers -------------------------------------------------------------------
-// The 16 warps form two groups of 8; group g walks tiles g, g+2, ... of the chunk.  Inside a group
-// warp `slab` owns edge slots [16*slab, 16*slab+16) of the current tile and the matching 16-column
-// stripe of the group's A buffer, so producer -> GEMM -> epilogue chains need only __syncwarp();
-// the group meets on a named barrier only where a target's edge segment may span stripes.
-__device__ __forceinline__ void group_sync(int grp) {
-    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(GTHREADS) : "memory");
-}
 
 struct TileInfo {
     int ta, tb, ea, ne;  // first / end target (chunk-local), first edge (chunk-local), #edges
@@ -221,211 +321,176 @@ __device__ __forceinline__ TileInfo tile_info(const Chunk& c, int t) {
     return ti;
 }
 
-__device__ __forceinline__ uint8_t* slot_cache(const Chunk& c) { return reinterpret_cast<uint8_t*>(c.si + S_INTS); }
-
-// (source, target) of edge slot `slot` of tile t, chunk-local: bisection on the row pointer + one global load
-__device__ __forceinline__ void resolve_slot(const Chunk& c, const int32_t* __restrict__ src_g, const TileInfo& ti, int slot,
-                                             int& sj, int& tg) {
-    const int* rowl = c.si + SI_ROWL;
-    sj = 0;
-    tg = ti.ta;
-    if (slot < ti.ne) {
-        const int e = ti.ea + slot;
-        int lo = ti.ta, hi = ti.tb;  // largest i in [ta, tb) with rowl[i] <= e
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (rowl[mid] <= e) lo = mid; else hi = mid;
-        }
-        tg = lo;
-        sj = src_g[c.edge0 + e] - c.node0;
-    }
-}
-
-// warp-private bookkeeping: lanes 0..15 fetch (source, target) of their slot (dead slots: source 0, target = first of the tile)
-__device__ __forceinline__ void slot_edges(const Chunk& c, const int32_t* __restrict__ src_g, const TileInfo& ti, int t,
-                                           int slab, int lane, int* esrc, int* etgt) {
-    if (lane < 16) {
-        const int slot = slab * 16 + lane;
-        int sj, tg;
-        if (t < SLOT_CACHE_TILES) {
-            const uint8_t* sc = slot_cache(c) + t * 2 * TE;
-            sj = sc[slot];
-            tg = sc[TE + slot];
-        } else {
-            resolve_slot(c, src_g, ti, slot, sj, tg);
-        }
-        esrc[slot] = sj;
-        etgt[slot] = tg;
-    }
-    __syncwarp();
-}
-
-// copy the warp's 16-column stripe of a [32][LDA] tile from global into its smem stripe (4 x 16 B per lane)
-__device__ __forceinline__ void load_stripe_async(float* stripe, const float* __restrict__ tile_stripe, int lane) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int chunk = lane + 32 * i, k = chunk >> 2, c4 = (chunk & 3) * 4;
-        cp_async16(stripe + k * LDA + c4, tile_stripe + k * LDA + c4);
-    }
-    cp_async_commit();
-}
-
 // ---------------------------------------------------------------------------------------
 // Phase E0: per-edge attribute  edge_attr = input_mlp(gfp(d)) * e2d + project([sin,cos,emb_i,emb_j])
-// SDE_model_2D_to_3D.py:402-432.  coff_mlp (a bare Linear) is folded into project.layers.0 on the
-// host (MOLSDE_P_H_W), so the hidden layer accumulates directly over the four Fourier blocks.
-// Entirely warp-private: no block- or group-level barrier inside the tile loop.
+// SDE_model_2D_to_3D.py:402-432.  coff_mlp (a bare Linear) is folded into project.layers.0 on the host, so the hidden layer
+// accumulates directly over the four Fourier blocks.
+//   Per tile (one quad): every thread builds the 5 x 64 Fourier features of ITS edge in ten K = 32 sub-blocks
+//   [sin f(16h..) | cos f(16h..)], writes them as fp16 hi/lo rows of the A operand (two ring slots), and the quad leader issues
+//   3 x 2 tcgen05.mma (N = 32) per sub-block into the TMEM accumulators "inv" (columns 0..31, block 0) and "hidden" (32..63,
+//   blocks 1..4) while the threads already compute the next sub-block.  Epilogue: hidden -> +bias, SiLU -> A operand ->
+//   project.1 on the tensor core (columns 64..95) -> edge_attr = (inv + b) * e2d + (proj + b) -> scratch record, already as
+//   the fp16 hi/lo operand tile of the later phases.
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void phase_edge_features(const Chunk c, const float* __restrict__ blob,
-                                                 const int32_t* __restrict__ src_g, const float* __restrict__ e2d_tiles,
-                                                 float* __restrict__ scratch) {
-    float* sm = c.sm;
-    float* W = sm + S_Q;  // E0 weights staged over the (currently dead) q/k/v region
-    const float* pos = sm + S_POS;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int grp = warp >> 3, slab = warp & 7;
-    const int g = lane >> 2, t4 = lane & 3;
-    float* A = sm + S_A + grp * TILE_FLOATS + slab * 16;   // stripe: element (k, r) at A[k*LDA + r]
-    float* geo = sm + S_L + grp * (TE * 8) + slab * 112;    // [7][16]: d, ci0, ci2, cj0, cj2, psin, pcos
-    int* esrc = c.si + SI_ESRC + grp * TE;
-    int* etgt = c.si + SI_ETGT + grp * TE;
-    __syncthreads();  // the q/k/v region may still be read by the tail of the previous evaluation
-    stage_bulk(c.si, W, blob, MOLSDE_P_E0_END);
-    for (int t = grp; t < c.ntiles; t += GROUPS) {
+__device__ __noinline__ uint32_t phase_edge_features(const Chunk c, const float* __restrict__ blob, const float* __restrict__ e2d_tiles,
+                                                     uint8_t* __restrict__ scratch, uint32_t tmem_base, uint32_t qs) {
+    const float* W = smem_at<const float>(c, SB_E0W);
+    const float* pos = smem_at<const float>(c, SB_POS);
+    const int tid = threadIdx.x, q = tid >> 7, e = tid & (QT - 1);
+    uint8_t* Aq = smem_bytes(c) + SB_E0A + q * (2 * E0_SLOT);
+    const uint32_t a_base = smem_u32(Aq);
+    const uint32_t w_bt = smem_u32(W + MOLSDE_P_E0_BT);
+    const uint32_t bar0 = bar_addr(c, 2 * q), bar1 = bar_addr(c, 2 * q + 1);
+    const uint32_t tq = tmem_base + q * 128;                                  // the quad's accumulator columns
+    const uint32_t tlane = tq + (static_cast<uint32_t>(e & ~31) << 16);       // + this warp's TMEM lane quarter
+    __syncthreads();  // the union region may still be read by the tail of the previous evaluation / the PC update
+    stage_bulk2(c, smem_bytes(c) + SB_E0W, blob, MOLSDE_P_E0_END, nullptr, nullptr, 0);
+    for (int t = q; t < c.ntiles; t += QUADS) {
         const TileInfo ti = tile_info(c, t);
-        slot_edges(c, src_g, ti, t, slab, lane, esrc, etgt);
-        // this thread's 16 elements of the e2d tile (rows g, g+8; columns nb*8 + 2*t4 + j), fetched early
-        const float* e2d_t = e2d_tiles + static_cast<size_t>(c.tile0 + t) * TILE_FLOATS + slab * 16;
-        float e2[4][4];
-#pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr)
-                    e2[nb][2 * rr + j] = __ldg(e2d_t + (nb * 8 + 2 * t4 + j) * LDA + g + 8 * rr);
-        if (lane < 16) {
-            const int slot = slab * 16 + lane;
-            float gq[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (slot < ti.ne) {
-                const float* pr = pos + 3 * esrc[slot];  // row = source j
-                const float* pc = pos + 3 * etgt[slot];  // col = target i
-                const Frame f = coord2basis(pr, pc);
-                {   // cache the equivariant basis of this edge for the two basis phases (equivariant_scorenetwork.py:159)
-                    float* fr_t = scratch + static_cast<size_t>(t) * SCR_TILE + TILE_FLOATS + slot;
-                    fr_t[0 * TE] = f.dx; fr_t[1 * TE] = f.dy; fr_t[2 * TE] = f.dz;
-                    fr_t[3 * TE] = f.cx; fr_t[4 * TE] = f.cy; fr_t[5 * TE] = f.cz;
-                    fr_t[6 * TE] = f.vx; fr_t[7 * TE] = f.vy; fr_t[8 * TE] = f.vz;
-                }
-                // coff = edge_basis @ r  (:417-418), |.| on component 1 (:419-420)
-                const float ci0 = dot3_rn(f.dx, f.dy, f.dz, pr[0], pr[1], pr[2]);
-                const float ci1 = fabsf(dot3_rn(f.cx, f.cy, f.cz, pr[0], pr[1], pr[2]));
-                const float ci2 = dot3_rn(f.vx, f.vy, f.vz, pr[0], pr[1], pr[2]);
-                const float cj0 = dot3_rn(f.dx, f.dy, f.dz, pc[0], pc[1], pc[2]);
-                const float cj1 = fabsf(dot3_rn(f.cx, f.cy, f.cz, pc[0], pc[1], pc[2]));
-                const float cj2 = dot3_rn(f.vx, f.vy, f.vz, pc[0], pc[1], pc[2]);
-                const float ni = sqrtf(dot3_rn(ci0, ci1, ci2, ci0, ci1, ci2));
-                const float nj = sqrtf(dot3_rn(cj0, cj1, cj2, cj0, cj1, cj2));
-                const float pcos = __fdiv_rn(__fdiv_rn(dot3_rn(ci0, ci1, ci2, cj0, cj1, cj2), __fadd_rn(ni, EPS)),
-                                             __fadd_rn(nj, EPS));
-                // :425  sqrt(1 - cos^2).  For (anti)parallel r_i, r_j rounding can make the argument a tiny negative
-                // number and the reference then returns NaN for the whole batch; the limit value 0 is used instead
-                // (only inputs on which the reference output is NaN are affected).
-                const float psin = sqrtf(fmaxf(__fsub_rn(1.0f, __fmul_rn(pcos, pcos)), 0.0f));
-                gq[0] = f.dist; gq[1] = ci0; gq[2] = ci2; gq[3] = cj0; gq[4] = cj2; gq[5] = psin; gq[6] = pcos;
+        uint8_t* rec = scratch + static_cast<size_t>(t) * REC_BYTES;
+        const bool live = e < ti.ne;
+        float x[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, psin = 0.f, pcos = 0.f;
+        if (live) {
+            const int sj = rec[REC_SLOT + e], tg = rec[REC_SLOT + TE + e];
+            const float* pr = pos + 3 * sj;  // row = source j
+            const float* pc = pos + 3 * tg;  // col = target i
+            const Frame f = coord2basis(pr, pc);
+            {   // cache the equivariant basis of this edge for the two basis phases (equivariant_scorenetwork.py:159)
+                float* fr = reinterpret_cast<float*>(rec + REC_FRAME) + e;
+                fr[0 * TE] = f.dx; fr[1 * TE] = f.dy; fr[2 * TE] = f.dz;
+                fr[3 * TE] = f.cx; fr[4 * TE] = f.cy; fr[5 * TE] = f.cz;
+                fr[6 * TE] = f.vx; fr[7 * TE] = f.vy; fr[8 * TE] = f.vz;
             }
-#pragma unroll
-            for (int q = 0; q < 7; ++q) geo[q * 16 + lane] = gq[q];
+            // coff = edge_basis @ r  (:417-418), |.| on component 1 (:419-420)
+            const float ci0 = dot3_rn(f.dx, f.dy, f.dz, pr[0], pr[1], pr[2]);
+            const float ci1 = fabsf(dot3_rn(f.cx, f.cy, f.cz, pr[0], pr[1], pr[2]));
+            const float ci2 = dot3_rn(f.vx, f.vy, f.vz, pr[0], pr[1], pr[2]);
+            const float cj0 = dot3_rn(f.dx, f.dy, f.dz, pc[0], pc[1], pc[2]);
+            const float cj1 = fabsf(dot3_rn(f.cx, f.cy, f.cz, pc[0], pc[1], pc[2]));
+            const float cj2 = dot3_rn(f.vx, f.vy, f.vz, pc[0], pc[1], pc[2]);
+            const float ni = sqrtf(dot3_rn(ci0, ci1, ci2, ci0, ci1, ci2));
+            const float nj = sqrtf(dot3_rn(cj0, cj1, cj2, cj0, cj1, cj2));
+            pcos = __fdiv_rn(__fdiv_rn(dot3_rn(ci0, ci1, ci2, cj0, cj1, cj2), __fadd_rn(ni, EPS)), __fadd_rn(nj, EPS));
+            // :425  sqrt(1 - cos^2).  For (anti)parallel r_i, r_j rounding can make the argument a tiny negative
+            // number and the reference then returns NaN for the whole batch; the limit value 0 is used instead
+            // (only inputs on which the reference output is NaN are affected).
+            psin = sqrtf(fmaxf(__fsub_rn(1.0f, __fmul_rn(pcos, pcos)), 0.0f));
+            x[0] = f.dist; x[1] = ci0; x[2] = ci2; x[3] = cj0; x[4] = cj2;
         }
-        __syncwarp();
-        // Fourier block 0 (distance) feeds input_mlp (:409-410); blocks 1..4 (ci0, ci2, cj0, cj2) feed the fused
-        // hidden layer of `project` (:427-430).  Each block: sin half -> GEMM(K=32), cos half -> GEMM(K=32).
-        float inv[4][4], acc[4][4];
-        zero_frag(acc);
-        // lane -> (edge fe, half hf); frequency of step i is w(i) = 4*(i/2) + 2*hf + (i&1): at every step the two half-warps
-        // write A rows 2 apart = 16 banks apart (conflict-free), profiles/r1_pc_v4_conflicts.txt
-        const int fe = lane & 15, hf = lane >> 4;
-#pragma unroll 1
+        // Fourier block 0 (distance) feeds input_mlp (:409-410); blocks 1..4 (ci0, ci2, cj0, cj2) feed the fused hidden layer
+        // of `project` (:427-430).
+#pragma unroll
         for (int blk = 0; blk < 5; ++blk) {
-            const float x = geo[blk * 16 + fe];
-            const float* Wf = W + (blk == 0 ? MOLSDE_P_GFP_DIST_W : MOLSDE_P_GFP_COFF_W);
-            const float* Wm = (blk == 0) ? W + MOLSDE_P_IN_W : W + MOLSDE_P_H_W + (blk - 1) * 64 * LD32;
-            float cs[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                // GaussianFourierProjection.forward, :64-66  (x * W * 2 * pi, fp32, in that order)
-                const int w = 4 * (i >> 1) + 2 * hf + (i & 1);
-                const float arg = __fmul_rn(__fmul_rn(__fmul_rn(x, Wf[w]), 2.0f), 3.14159274101257324f);
-                float sn;
-                sincos_reduced(arg, sn, cs[i]);
-                A[w * LDA + fe] = sn;
-            }
-            __syncwarp();
-            MOLSDE_MMA_GEMM<4, LDA, LD32>(A, Wm, 32, lane, acc);
-            __syncwarp();
+            for (int half = 0; half < 2; ++half) {
+                const float4* Wf = reinterpret_cast<const float4*>(W + (blk == 0 ? MOLSDE_P_GFP_DIST_W : MOLSDE_P_GFP_COFF_W) + half * 16);
+                float v[32];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) A[(4 * (i >> 1) + 2 * hf + (i & 1)) * LDA + fe] = cs[i];
-            __syncwarp();
-            MOLSDE_MMA_GEMM<4, LDA, LD32>(A, Wm + 32 * LD32, 32, lane, acc);
-            __syncwarp();
-            if (blk == 0) {
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const float4 w4 = Wf[i4];
+                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                for (int nb = 0; nb < 4; ++nb)
+                    for (int j = 0; j < 4; ++j) {
+                        // GaussianFourierProjection.forward, :64-66  (x * W * 2 * pi, fp32, in that order)
+                        const float arg = __fmul_rn(__fmul_rn(__fmul_rn(x[blk], wv[j]), 2.0f), 3.14159274101257324f);
+                        sincos_reduced(arg, v[4 * i4 + j], v[16 + 4 * i4 + j]);
+                    }
+                }
+                const uint32_t bar = half ? bar1 : bar0;
+                if (blk >= 1) mbar_wait(bar, qs, half ? QS_MMA1 : QS_MMA0, c.status_flag);  // MMAs of sub-block b-2 done: slot free
+                uint8_t* Ah = Aq + half * E0_SLOT;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { inv[nb][q] = acc[nb][q]; acc[nb][q] = 0.0f; }
-            }
-        }
-#pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int col = nb * 8 + 2 * t4 + j;
-                const float bh = W[MOLSDE_P_H_B + col], ws = W[MOLSDE_P_H_WSIN + col], wc = W[MOLSDE_P_H_WCOS + col];
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int r = g + 8 * rr;
-                    const float v = acc[nb][2 * rr + j] + bh + geo[5 * 16 + r] * ws + geo[6 * 16 + r] * wc;
-                    A[col * LDA + r] = silu_fast(v);
+                for (int kc = 0; kc < 4; ++kc) store_a_chunk(Ah, Ah + 8192, e, kc, v + 8 * kc);
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
+                tc_fence_before();
+                quad_sync(q);
+                if (e == 0) {
+                    tc_fence_after();
+                    const uint32_t ah = a_base + half * E0_SLOT, wb = w_bt + (2 * blk + half) * (MOLSDE_E0_BT_FLOATS * 4);
+                    umma_split_f16<32>(tq + (blk == 0 ? 0 : 32), ah, ah + 8192, wb, wb + 2048, 2, (blk <= 1 && half == 0) ? 0u : 1u);
+                    umma_commit(bar);
                 }
             }
-        __syncwarp();
-        zero_frag(acc);
-        MOLSDE_MMA_GEMM<4, LDA, LD32>(A, W + MOLSDE_P_P1_W, 32, lane, acc);
-        // ---- edge_attr = inv3d * e2d + frame  (:432) -> scratch tile (own stripe) ----
-        float* sc_t = scratch + static_cast<size_t>(t) * SCR_TILE + slab * 16;
+        }
+        mbar_wait(bar0, qs, QS_MMA0, c.status_flag);
+        mbar_wait(bar1, qs, QS_MMA1, c.status_flag);  // all Fourier MMAs of the tile are complete
+        tc_fence_after();
+        {
+            float hv[32];
+            tmem_ld32(tlane + 32, hv);
+            const float4* HV = reinterpret_cast<const float4*>(W + MOLSDE_P_E0_HV);
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int col = nb * 8 + 2 * t4 + j;
-                const float bi = W[MOLSDE_P_IN_B + col], bf = W[MOLSDE_P_P1_B + col];
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr)
-                    sc_t[col * LDA + g + 8 * rr] = fmaf(inv[nb][2 * rr + j] + bi, e2[nb][2 * rr + j], acc[nb][2 * rr + j] + bf);
+            for (int col = 0; col < 32; ++col) {
+                const float4 p = HV[col];  // {bias, w_sin, w_cos, 0}
+                hv[col] = silu_fast(hv[col] + p.x + psin * p.y + pcos * p.z);
             }
-        __syncwarp();
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) store_a_chunk(Aq, Aq + 8192, e, kc, hv + 8 * kc);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        quad_sync(q);
+        if (e == 0) {
+            tc_fence_after();
+            const uint32_t wb = w_bt + 10 * (MOLSDE_E0_BT_FLOATS * 4);
+            umma_split_f16<32>(tq + 64, a_base, a_base + 8192, wb, wb + 2048, 2, 0u);
+            umma_commit(bar0);
+        }
+        // edge_2D_emb tile of this edge (loop invariant, L2): [8 feature quads][128 slots][4]; in flight during project.1
+        float4 e2[8];
+        {
+            const float4* e2d_t = reinterpret_cast<const float4*>(e2d_tiles + static_cast<size_t>(c.tile0 + t) * E2D_TILE_FLOATS) + e;
+#pragma unroll
+            for (int fq = 0; fq < 8; ++fq) e2[fq] = __ldg(e2d_t + fq * TE);
+        }
+        mbar_wait(bar0, qs, QS_MMA0, c.status_flag);
+        tc_fence_after();
+        // ---- edge_attr = inv3d * e2d + frame  (:432) -> scratch record, as the fp16 hi/lo operand rows of the later phases ----
+        const float2* OB = reinterpret_cast<const float2*>(W + MOLSDE_P_E0_OB);
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+            float inv[8], pr[8], ea[8];
+            tmem_ld8(tlane + 8 * kc, inv);
+            tmem_ld8(tlane + 64 + 8 * kc, pr);
+            const float ev[8] = {e2[2 * kc].x, e2[2 * kc].y, e2[2 * kc].z, e2[2 * kc].w,
+                                 e2[2 * kc + 1].x, e2[2 * kc + 1].y, e2[2 * kc + 1].z, e2[2 * kc + 1].w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float2 ob = OB[8 * kc + j];  // {input_mlp bias, project.1 bias}
+                ea[j] = fmaf(inv[j] + ob.x, ev[j], pr[j] + ob.y);
+            }
+            uint4 h, l;
+            split8(ea, h, l);
+            *reinterpret_cast<uint4*>(rec + REC_EA_HI + kc * 2048 + e * 16) = h;
+            *reinterpret_cast<uint4*>(rec + REC_EA_LO + kc * 2048 + e * 16) = l;
+        }
+        tc_fence_before();  // TMEM reads of this tile are ordered before the next tile's MMAs by its first quad barrier
     }
+    asm volatile("fence.proxy.async;" ::: "memory");  // the records are read back by TMA bulk copies (async proxy)
     __syncthreads();
+    return qs;
 }
 
 // ---------------------------------------------------------------------------------------
 // GAT layer pieces  (equivariant_scorenetwork.py:34-40, TransformerConv heads=8 C=4)
 // ---------------------------------------------------------------------------------------
-// q|k|v = Linear(x): each warp owns 16 nodes and all 96 output columns
+// q|k|v = Linear(x): each warp owns 16 nodes and all 96 output columns (mma.sync; weights staged in the R region)
 __device__ __noinline__ void node_qkv(const Chunk c) {
     float* sm = c.sm;
-    const float* Wg = sm + S_WG;
+    const float* Wqkv = smem_at<const float>(c, SB_R);
+    const float* Wp = smem_at<const float>(c, SB_WP);
+    float* Qb = smem_at<float>(c, SB_Q);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m0 = warp * 16, g = lane >> 2, t4 = lane & 3;
     if (m0 >= c.n) return;
     float acc[12][4];
     zero_frag(acc);
-    MOLSDE_MMA_GEMM<12, LDX, LD96>(sm + S_XT + m0, Wg + MOLSDE_G_WQKV, 32, lane, acc);
+    MOLSDE_MMA_GEMM<12, LDX, LD96>(sm + SB_XT / 4 + m0, Wqkv, 32, lane, acc);
 #pragma unroll
     for (int nb = 0; nb < 12; ++nb) {
         const int col = nb * 8 + 2 * t4;  // 0..95: q | k | v
-        const float b0 = Wg[MOLSDE_G_BQKV + col], b1 = Wg[MOLSDE_G_BQKV + col + 1];
-        float* dst = sm + S_Q + (col >> 5) * (32 * MAXN);
+        const float b0 = Wp[MOLSDE_G_BQKV + col], b1 = Wp[MOLSDE_G_BQKV + col + 1];
+        float* dst = Qb + (col >> 5) * (32 * MAXN);
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const int node = m0 + g + 8 * rr;
@@ -435,98 +500,115 @@ __device__ __noinline__ void node_qkv(const Chunk c) {
     }
 }
 
-// attention over the incoming edges of every target: logits, segment softmax (+1e-16), weighted
-// messages, deterministic ascending-source sum; the aggregate overwrites q[target].
-__device__ __noinline__ void gat_edge_phase(const Chunk c, const int32_t* __restrict__ src_g,
-                                            const float* __restrict__ scratch, int layer) {
-    float* sm = c.sm;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int grp = warp >> 3, slab = warp & 7, gt = tid & (GTHREADS - 1);
-    const int g = lane >> 2, t4 = lane & 3;
-    float* Ag = sm + S_A + grp * TILE_FLOATS;
-    float* stripe = Ag + slab * 16;
-    float* Mm = Ag;  // [TE][LDM] slot-major messages, written only after the group's GEMMs are done
-    float* L = sm + S_L + grp * (TE * 8);
-    float* ssum = sm + S_MS + grp * (2 * TE * 8) + TE * 8;
-    float* Q = sm + S_Q;
-    const float* Kk = sm + S_K;
-    const float* V = sm + S_V;
-    const float* Wg = sm + S_WG;
+// attention over the incoming edges of every target: e = lin_edge(edge_attr) on the tensor core (A operand = the scratch record,
+// fetched by one TMA bulk copy), logits, segment softmax (+1e-16), weighted messages, deterministic ascending-source sum; the
+// aggregate overwrites q[target].  One quad per tile, thread = edge slot.
+__device__ __noinline__ uint32_t gat_edge_phase(const Chunk c, const uint8_t* __restrict__ scratch, int layer, uint32_t tmem_base,
+                                                uint32_t qs) {
+    const int tid = threadIdx.x, q = tid >> 7, e = tid & (QT - 1);
+    uint8_t* slot = smem_bytes(c) + SB_R + q * GAT_SLOT;
+    float* Mm = reinterpret_cast<float*>(slot);          // [TE][32] messages (granules swizzled by the slot), over the consumed operand
+    float* L = reinterpret_cast<float*>(slot + 16384);   // [TE][8] logits -> attention weights
+    float* Q = smem_at<float>(c, SB_Q);
+    const float* Kk = smem_at<const float>(c, SB_K);
+    const float* V = smem_at<const float>(c, SB_V);
     const int* rowl = c.si + SI_ROWL;
-    int* esrc = c.si + SI_ESRC + grp * TE;
-    int* etgt = c.si + SI_ETGT + grp * TE;
-    for (int t = grp; t < c.ntiles; t += GROUPS) {
+    const uint32_t a_addr = smem_u32(slot);
+    const uint32_t w_addr = smem_u32(smem_at<float>(c, SB_WP) + MOLSDE_G_WEC);
+    const uint32_t bar_mma = bar_addr(c, 2 * q), bar_tma = bar_addr(c, 2 * QUADS + q);
+    const uint32_t tq = tmem_base + q * 128;
+    const uint32_t tlane = tq + (static_cast<uint32_t>(e & ~31) << 16);
+    for (int t = q; t < c.ntiles; t += QUADS) {
         const TileInfo ti = tile_info(c, t);
-        load_stripe_async(stripe, scratch + static_cast<size_t>(t) * SCR_TILE + slab * 16, lane);
-        slot_edges(c, src_g, ti, t, slab, lane, esrc, etgt);
-        cp_async_wait<0>();
-        __syncwarp();
-        // e = lin_edge(edge_attr); this thread: slots 16*slab + g, +8; columns nb*8 + 2*t4 + {0,1}
-        float e[4][4];
-        zero_frag(e);
-        MOLSDE_MMA_GEMM<4, LDA, LD32>(stripe, Wg + MOLSDE_G_WE, 32, lane, e);
+        const uint8_t* rec = scratch + static_cast<size_t>(t) * REC_BYTES;
+        if (e == 0) {
+            fence_proxy_async_smem();  // the slot was last touched through the generic proxy (message tile of the previous tile)
+            mbar_expect_tx(bar_tma, 16384u);
+            bulk_g2s(a_addr, rec + REC_EA_HI, 16384u, bar_tma);
+        }
+        const bool live = e < ti.ne;
+        const int sj = live ? rec[REC_SLOT + e] : 0, tg = live ? rec[REC_SLOT + TE + e] : ti.ta;
+        if (e == 0) {
+            uint32_t qt = qs;  // (every thread flips its own copy below)
+            mbar_wait(bar_tma, qt, QS_TMA, c.status_flag);
+            qs |= (qt & QS_DEAD);
+            tc_fence_after();
+            umma_split_f16<32>(tq, a_addr, a_addr + 8192, w_addr, w_addr + 2048, 2, 0u);
+            umma_commit(bar_mma);
+        }
+        qs ^= QS_TMA;
+        mbar_wait(bar_mma, qs, QS_MMA0, c.status_flag);
+        tc_fence_after();
+        float ev[32], lg[8];
+        tmem_ld32(tlane, ev);
+        {
+            const float4* Q4 = reinterpret_cast<const float4*>(Q) + tg * 8;
+            const float4* K4 = reinterpret_cast<const float4*>(Kk) + sj * 8;
+            const float4* V4 = reinterpret_cast<const float4*>(V) + sj * 8;
+            const int sq = tg & 7, sk = sj & 7;
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int s = slab * 16 + g + 8 * rr;
-            const bool live = s < ti.ne;
-            const int sj = esrc[s], tg = etgt[s];
-#pragma unroll
-            for (int nb = 0; nb < 4; ++nb) {
-                const int col = nb * 8 + 2 * t4;
-                const float2 k2 = *reinterpret_cast<const float2*>(Kk + qkv_idx(sj, col));
-                const float2 q2 = *reinterpret_cast<const float2*>(Q + qkv_idx(tg, col));
-                const float2 v2 = *reinterpret_cast<const float2*>(V + qkv_idx(sj, col));
-                // alpha = (q_i . (k_j + e)) / sqrt(C): a head (4 columns) is split over the lane pair (t4, t4^1)
-                float part = fmaf(q2.y, k2.y + e[nb][2 * rr + 1], q2.x * (k2.x + e[nb][2 * rr]));
-                part += __shfl_xor_sync(0xffffffffu, part, 1);
-                if (live && (t4 & 1) == 0) L[s * 8 + (col >> 2)] = part * 0.5f;
-                e[nb][2 * rr] += v2.x;      // v_j + e
-                e[nb][2 * rr + 1] += v2.y;
+            for (int hd = 0; hd < 8; ++hd) {
+                const float4 q4 = Q4[hd ^ sq], k4 = K4[hd ^ sk], v4 = V4[hd ^ sk];
+                // alpha = (q_i . (k_j + e)) / sqrt(C)
+                float part = fmaf(q4.y, k4.y + ev[4 * hd + 1], q4.x * (k4.x + ev[4 * hd]));
+                part += fmaf(q4.w, k4.w + ev[4 * hd + 3], q4.z * (k4.z + ev[4 * hd + 2]));
+                lg[hd] = part * 0.5f;
+                ev[4 * hd] += v4.x;      // v_j + e
+                ev[4 * hd + 1] += v4.y;
+                ev[4 * hd + 2] += v4.z;
+                ev[4 * hd + 3] += v4.w;
             }
         }
-        group_sync(grp);
-        // per (target, head): max and sum(exp) over the target's contiguous edge segment
+        if (live) {
+            *reinterpret_cast<float4*>(L + e * 8) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+            *reinterpret_cast<float4*>(L + e * 8 + 4) = make_float4(lg[4], lg[5], lg[6], lg[7]);
+        }
+        tc_fence_before();
+        quad_sync(q);
+        // per (target, head): softmax over the target's contiguous edge segment, normalised in place
         const int ntg = ti.tb - ti.ta;
-        for (int p = gt; p < ntg * 8; p += GTHREADS) {
+        for (int p = e; p < ntg * 8; p += QT) {
             const int i = ti.ta + (p >> 3), hd = p & 7;
             const int s0 = rowl[i] - ti.ea, s1 = rowl[i + 1] - ti.ea;
             float m = -CUDART_INF_F;
             for (int s = s0; s < s1; ++s) m = fmaxf(m, L[s * 8 + hd]);
             float z = 0.0f;
-            for (int s = s0; s < s1; ++s) {   // the exponentials are kept (in place of the logits) for the normalisation pass
+            for (int s = s0; s < s1; ++s) {
                 const float ex = __expf(L[s * 8 + hd] - m);
                 L[s * 8 + hd] = ex;
                 z += ex;
             }
-            ssum[p] = z;
+            const float rz = __fdividef(1.0f, z + 1e-16f);
+            for (int s = s0; s < s1; ++s) L[s * 8 + hd] *= rz;
         }
-        group_sync(grp);
+        quad_sync(q);
+        if (live) {
+            const float4 a0 = *reinterpret_cast<const float4*>(L + e * 8), a1 = *reinterpret_cast<const float4*>(L + e * 8 + 4);
+            float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            if (c.attn_keep) {  // F.dropout(alpha, p) in train mode (TransformerConv.message)
+                const float* kp = c.attn_keep + (static_cast<size_t>(layer) * c.E_total + c.edge0 + ti.ea + e) * 8;
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int s = slab * 16 + g + 8 * rr;
-            if (s < ti.ne) {
-                const int pb = (etgt[s] - ti.ta) * 8;
-#pragma unroll
-                for (int nb = 0; nb < 4; ++nb) {
-                    const int col = nb * 8 + 2 * t4, hd = col >> 2;
-                    float a = __fdividef(L[s * 8 + hd], ssum[pb + hd] + 1e-16f);
-                    if (c.attn_keep)  // F.dropout(alpha, p) in train mode (TransformerConv.message)
-                        a *= c.attn_keep[(static_cast<size_t>(layer) * c.E_total + c.edge0 + ti.ea + s) * 8 + hd] * c.inv_keep;
-                    Mm[s * LDM + col] = e[nb][2 * rr] * a;
-                    Mm[s * LDM + col + 1] = e[nb][2 * rr + 1] * a;
-                }
+                for (int hd = 0; hd < 8; ++hd) al[hd] *= kp[hd] * c.inv_keep;
             }
+#pragma unroll
+            for (int hd = 0; hd < 8; ++hd)
+                *reinterpret_cast<float4*>(Mm + e * 32 + ((hd ^ (e & 7)) << 2)) =
+                    make_float4(ev[4 * hd] * al[hd], ev[4 * hd + 1] * al[hd], ev[4 * hd + 2] * al[hd], ev[4 * hd + 3] * al[hd]);
         }
-        group_sync(grp);
-        for (int p = gt; p < ntg * 32; p += GTHREADS) {
-            const int i = ti.ta + (p >> 5), col = p & 31;
+        quad_sync(q);
+        for (int p = e; p < ntg * 8; p += QT) {
+            const int i = ti.ta + (p >> 3), hd = p & 7;
             const int s0 = rowl[i] - ti.ea, s1 = rowl[i + 1] - ti.ea;
-            float acc = 0.0f;
-            for (int s = s0; s < s1; ++s) acc += Mm[s * LDM + col];
-            Q[qkv_idx(i, col)] = acc;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = s0; s < s1; ++s) {
+                const float4 mv = *reinterpret_cast<const float4*>(Mm + s * 32 + ((hd ^ (s & 7)) << 2));
+                acc.x += mv.x; acc.y += mv.y; acc.z += mv.z; acc.w += mv.w;
+            }
+            *reinterpret_cast<float4*>(Q + qkv_idx(i, 4 * hd)) = acc;
         }
-        group_sync(grp);
+        quad_sync(q);
     }
+    return qs;
 }
 
 // LayerNorm over the 32 columns of two rows held by a lane quad (8 columns per lane and row)
@@ -562,11 +644,10 @@ __device__ __forceinline__ void layer_norm_quad(float (&v)[4][4], const float* _
 // x <- x + LN1(agg + skip(x));  x <- x + LN2(FFN(x));  optional SiLU  (equivariant_scorenetwork.py:35-38,140-141)
 // Each warp owns 16 nodes end to end (only __syncwarp between its GEMMs).
 __device__ __noinline__ void node_update(const Chunk c, bool silu_after, int layer) {
-    float* sm = c.sm;
-    float* XT = sm + S_XT;
-    float* NT = sm + S_A;  // [32][LDX] staging of the FFN input / hidden, k-major
-    const float* Q = sm + S_Q;
-    const float* Wg = sm + S_WG;
+    float* XT = smem_at<float>(c, SB_XT);
+    float* NT = smem_at<float>(c, SB_R);  // [32][LDX] staging of the FFN input / hidden, k-major
+    const float* Q = smem_at<const float>(c, SB_Q);
+    const float* Wg = smem_at<const float>(c, SB_WP);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m0 = warp * 16, g = lane >> 2, t4 = lane & 3;
     if (m0 >= c.n) return;
@@ -647,287 +728,195 @@ __device__ __noinline__ void node_update(const Chunk c, bool silu_after, int lay
 }
 
 // ---------------------------------------------------------------------------------------
-// tcgen05 helpers (descriptor formats: cute/arch/mma_sm100_desc.hpp; bring-up test tools/ubench/tcgen05_gemm.cu)
-// Operand tiles are K-major in the canonical no-swizzle core-matrix layout (8 rows x 16 B):
-//   float index(r, k) = (k/4)*(R/8)*32 + (r/8)*32 + (r%8)*4 + (k%4),  LBO = (R/8)*128 B, SBO = 128 B.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
-    return static_cast<uint64_t>((saddr & 0x3FFFF) >> 4)                   // start address  [0,14)
-           | (static_cast<uint64_t>(lbo_bytes >> 4) << 16)                  // leading byte offset [16,30)
-           | (static_cast<uint64_t>(UMMA_SBO >> 4) << 32)                   // stride byte offset  [32,46)
-           | (static_cast<uint64_t>(1) << 46);                              // version 1 (Blackwell), layout = no swizzle
-}
-// D[tmem] (+)= A[smem] . B[smem]^T, M = 128, K = 8 (tf32), issued by ONE thread
-template <int N>
-__device__ __forceinline__ void umma_tf32_m128(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-    // instruction descriptor: D = F32 (1<<4), A = B = TF32 (2<<7, 2<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((static_cast<uint32_t>(N) >> 3) << 17) | ((128u >> 4) << 24);
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (int it = 0; it < (1 << 24) && !done; ++it)  // bounded: a descriptor bug must not hang the GPU
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    return done != 0;
-}
-// 3xTF32: three passes (lo*hi, hi*lo, hi*hi) over `ksteps` K=8 steps of an A tile [128 x 8*ksteps] and a B tile [N x ...]
-template <int N>
-__device__ __forceinline__ void umma_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int ksteps,
-                                            uint32_t lbo_a, uint32_t lbo_b, uint32_t accumulate) {
-#pragma unroll 1
-    for (int term = 0; term < 3; ++term) {
-        const uint32_t pa = (term == 0) ? a_lo : a_hi, pb = (term == 1) ? b_lo : b_hi;
-#pragma unroll 1
-        for (int kb = 0; kb < ksteps; ++kb) {
-            umma_tf32_m128<N>(tmem_d, umma_desc(pa + kb * 2 * lbo_a, lbo_a), umma_desc(pb + kb * 2 * lbo_b, lbo_b), accumulate);
-            accumulate = 1;
-        }
-    }
-}
-// 8 consecutive accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-// write 4 consecutive-k values of row `r` (k-chunk kc) of a [128 x K] A tile as tf32 hi + exact lo
-__device__ __forceinline__ void store_a_chunk(float* AH, float* AL, int r, int kc, const float (&v)[4]) {
-    float4 h4, l4;
-    h4.x = __uint_as_float(tf32_hi(v[0])); h4.y = __uint_as_float(tf32_hi(v[1]));
-    h4.z = __uint_as_float(tf32_hi(v[2])); h4.w = __uint_as_float(tf32_hi(v[3]));
-    l4.x = v[0] - h4.x; l4.y = v[1] - h4.y; l4.z = v[2] - h4.z; l4.w = v[3] - h4.w;
-    const int idx = kc * 512 + (r >> 3) * 32 + (r & 7) * 4;
-    *reinterpret_cast<float4*>(AH + idx) = h4;
-    *reinterpret_cast<float4*>(AL + idx) = l4;
-}
-
-// ---------------------------------------------------------------------------------------
 // basis MLP + equivariant mean aggregation  (equivariant_scorenetwork.py:154-164)
-//   hidden[128 edges x 128] = [h_row + h_col | edge_attr][128 x 64] . W1^T on tcgen05 (M=128, N=128, 8 K-steps x 3 split
-//   terms, accumulator in TMEM); epilogue TMEM -> registers: +bias, SiLU, 128 -> 3 projection; frame mix; per-target mean.
-// All 16 warps work on one tile at a time; returns the updated mbarrier phase.
+//   hidden[128 edges x 128] = [h_row + h_col | edge_attr][128 x 64] . W1^T on tcgen05 (M = 128, N = 128, 4 K-steps x 3 split
+//   terms, accumulator = the quad's 128 TMEM columns); the edge_attr half of the A operand arrives by TMA bulk copy from the
+//   scratch record, the node half is gathered and split by the edge's thread.  Epilogue: the thread reads the 128 hidden
+//   pre-activations of ITS edge (4 x tcgen05.ld x32): +bias, SiLU, 128 -> 3 projection in registers; frame mix; per-target mean.
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restrict__ blob, const int32_t* __restrict__ src_g,
-                                             const float* __restrict__ scratch, int module, uint32_t tmem_base, uint32_t phase,
-                                             int32_t* status_flag) {
-    float* sm = c.sm;
-    float* Wb = sm + S_Q;  // staged over q/k/v (dead between GAT blocks)
-    float* AH = sm + S_UA_HI;
-    float* AL = sm + S_UA_LO;
-    float* dynp = sm + S_L;   // [4][TE][4] partial dyn coefficients of the four column blocks
-    float* frames = sm + S_MS;  // [2][9][TE] cached edge frames of tile t / t+1
-    float* mix = sm + S_MS + 2 * FRAME_FLOATS;  // [3][TE]
-    const float* XT = sm + S_XT;
-    float* grad = sm + S_GRAD;
+__device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restrict__ blob, const uint8_t* __restrict__ scratch, int module,
+                                             uint32_t tmem_base, uint32_t qs) {
+    const float* Wb = smem_at<const float>(c, SB_BW);
+    const float* XT = smem_at<const float>(c, SB_XT);
+    float* grad = smem_at<float>(c, SB_GRAD);
     const int* rowl = c.si + SI_ROWL;
-    const uint32_t bar = smem_u32(c.si + SI_BAR);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    stage_bulk(c.si, Wb, blob + MOLSDE_P_BASIS0 + module * MOLSDE_P_BASIS_SZ, MOLSDE_P_BASIS_SZ);
-
-    // stage 1 of the software pipeline: slot bookkeeping + A operand of tile t + MMA issue (asynchronous)
-    auto produce_and_issue = [&](int t) {
+    const int tid = threadIdx.x, q = tid >> 7, e = tid & (QT - 1);
+    uint8_t* Ah = smem_bytes(c) + SB_BA + q * B_SLOT;
+    uint8_t* Al = Ah + 16384;
+    float* mix = smem_at<float>(c, SB_MIX) + q * (3 * TE);
+    const uint32_t a_addr = smem_u32(Ah);
+    const uint32_t w_addr = smem_u32(Wb);
+    const uint32_t bar_mma = bar_addr(c, 2 * q), bar_tma = bar_addr(c, 2 * QUADS + q);
+    const uint32_t tq = tmem_base + q * 128;
+    const uint32_t tlane = tq + (static_cast<uint32_t>(e & ~31) << 16);
+    __syncthreads();
+    stage_bulk2(c, smem_bytes(c) + SB_BW, blob + MOLSDE_P_BASIS0 + module * MOLSDE_P_BASIS_STRIDE, MOLSDE_P_BASIS_SZ, nullptr, nullptr, 0);
+    const float4* EPI = reinterpret_cast<const float4*>(Wb + MOLSDE_B_EPI);
+    for (int t = q; t < c.ntiles; t += QUADS) {
         const TileInfo ti = tile_info(c, t);
-        int* esrc = c.si + SI_ESRC + (t & 1) * TE;
-        int* etgt = c.si + SI_ETGT + (t & 1) * TE;
-        // items (e, kc) of the A operand: kc = (tid >> 7) + 4 i.  i = 2, 3 (kc >= 8) are the edge_attr half, read straight from
-        // the L2-resident scratch record (written by E0): issued FIRST, their latency overlaps the slot bookkeeping, the
-        // barrier and the shared-memory gathers of i = 0, 1.
-        static_assert(NTHREADS == 4 * TE, "item mapping of the basis A operand");
-        const float* sc_t = scratch + static_cast<size_t>(t) * SCR_TILE;
-        const int e = tid & (TE - 1), kq = tid >> 7;
-        float va[2][4];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int q = 0; q < 4; ++q)   // the record is rewritten by E0 of every evaluation of this launch: L2-coherent load, never .nc
-                va[i][q] = __ldcg(sc_t + ((kq + 4 * i) * 4 + q) * LDA + e);
-        if (tid < TE) {  // (source, target) of every slot
-            int sj, tg;
-            if (t < SLOT_CACHE_TILES) {
-                const uint8_t* sc = slot_cache(c) + t * 2 * TE;
-                sj = sc[tid];
-                tg = sc[TE + tid];
-            } else {
-                resolve_slot(c, src_g, ti, tid, sj, tg);
-            }
-            esrc[tid] = sj;
-            etgt[tid] = tg;
+        const uint8_t* rec = scratch + static_cast<size_t>(t) * REC_BYTES;
+        if (e == 0) {   // edge_attr half of the A operand: k-chunks 4..7 of the hi and the lo tile
+            mbar_expect_tx(bar_tma, 16384u);
+            bulk_g2s(a_addr + 4 * 2048, rec + REC_EA_HI, 8192u, bar_tma);
+            bulk_g2s(a_addr + 16384 + 4 * 2048, rec + REC_EA_LO, 8192u, bar_tma);
         }
-        __syncthreads();
-        // A operand [128 x 64], K-major canonical core-matrix layout, split into tf32 hi + exact lo:
-        //   k < 32: h_row + h_col (:154-155),  k >= 32: edge_attr (scratch tile)
-        stage_async(frames + (t & 1) * FRAME_FLOATS, sc_t + TILE_FLOATS, FRAME_FLOATS);  // consumed by the epilogue of tile t
+        const bool live = e < ti.ne;
+        const int sj = live ? rec[REC_SLOT + e] : 0, tg = live ? rec[REC_SLOT + TE + e] : 0;
+        float F[9];
         {
-            const int sj = esrc[e], tg = etgt[e];
-            const bool live = e < ti.ne;
+            const float* fr = reinterpret_cast<const float*>(rec + REC_FRAME) + e;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int kc = kq + 4 * i, k0 = kc * 4;
-                float v[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) v[q] = live ? XT[(k0 + q) * LDX + sj] + XT[(k0 + q) * LDX + tg] : 0.0f;
-                store_a_chunk(AH, AL, e, kc, v);
-            }
+            for (int i = 0; i < 9; ++i) F[i] = live ? fr[i * TE] : 0.0f;
         }
+        // node half: h_row + h_col (:154-155), k-chunks 0..3
 #pragma unroll
-        for (int i = 0; i < 2; ++i) store_a_chunk(AH, AL, e, kq + 4 * i + 8, va[i]);
-        cp_async_wait<0>();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            umma_3xtf32<128>(tmem_base + (t & 1) * 128, smem_u32(AH), smem_u32(AL), smem_u32(Wb + MOLSDE_B_W1C_HI),
-                             smem_u32(Wb + MOLSDE_B_W1C_LO), 8, UMMA_LBO, UMMA_LBO, 0u);
-            umma_commit(bar);
+        for (int kc = 0; kc < 4; ++kc) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = XT[(8 * kc + j) * LDX + sj] + XT[(8 * kc + j) * LDX + tg];
+            store_a_chunk(Ah, Al, e, kc, v);
         }
-    };
-
-    bool ok = true;
-    if (c.ntiles > 0) produce_and_issue(0);
-    for (int t = 0; t < c.ntiles; ++t) {
-        const TileInfo ti = tile_info(c, t);
-        ok &= mbar_wait(bar, phase);  // MMAs of tile t complete: accumulator (t&1) ready, A buffer free
-        phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (t + 1 < c.ntiles) produce_and_issue(t + 1);  // its MMAs overlap the epilogue below
-        {   // epilogue: warp -> TMEM lane quarter (edge slots 32*lq..) x column block cb (hidden units 32*cb..)
-            const int lq = warp & 3, cb = warp >> 2;
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + (t & 1) * 128 + (static_cast<uint32_t>(lq * 32) << 16) + cb * 32;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        quad_sync(q);
+        if (e == 0) {
+            uint32_t qt = qs;
+            mbar_wait(bar_tma, qt, QS_TMA, c.status_flag);
+            qs |= (qt & QS_DEAD);
+            tc_fence_after();
+            umma_split_f16<128>(tq, a_addr, a_addr + 16384, w_addr + MOLSDE_B_W1_HI * 4, w_addr + MOLSDE_B_W1_LO * 4, 4, 0u);
+            umma_commit(bar_mma);
+        }
+        qs ^= QS_TMA;
+        mbar_wait(bar_mma, qs, QS_MMA0, c.status_flag);
+        tc_fence_after();
+        float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+            float hv[32];
+            tmem_ld32(tlane + 32 * cb, hv);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const int col = cb * 32 + j;
-                const float hv = silu_fast(__uint_as_float(v[j]) + Wb[MOLSDE_B_B1 + col]);
-                p0 = fmaf(hv, Wb[MOLSDE_B_W2 + col], p0);
-                p1 = fmaf(hv, Wb[MOLSDE_B_W2 + 128 + col], p1);
-                p2 = fmaf(hv, Wb[MOLSDE_B_W2 + 256 + col], p2);
+                const float4 ep = EPI[32 * cb + j];  // {bias, w2[0], w2[1], w2[2]} of hidden unit 32*cb + j
+                const float h = silu_fast(hv[j] + ep.x);
+                p0 = fmaf(h, ep.y, p0);
+                p1 = fmaf(h, ep.z, p1);
+                p2 = fmaf(h, ep.w, p2);
             }
-            float* dp = dynp + (cb * TE + lq * 32 + lane) * 4;
-            dp[0] = p0; dp[1] = p1; dp[2] = p2;
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        tc_fence_before();
         // basis_mix = dyn0 * coord_diff + dyn1 * coord_cross + dyn2 * coord_vertical  (:159), frames cached by E0
-        const float* F = frames + (t & 1) * FRAME_FLOATS;
-        if (tid < 3 * TE) {
-            const int q = tid & (TE - 1), ax = tid >> 7;
-            if (q < ti.ne) {
-                float d[3];
+        if (live) {
+            const float d0 = p0 + Wb[MOLSDE_B_B2], d1 = p1 + Wb[MOLSDE_B_B2 + 1], d2 = p2 + Wb[MOLSDE_B_B2 + 2];
 #pragma unroll
-                for (int o = 0; o < 3; ++o)
-                    d[o] = ((dynp[q * 4 + o] + dynp[(TE + q) * 4 + o]) + (dynp[(2 * TE + q) * 4 + o] + dynp[(3 * TE + q) * 4 + o])) +
-                           Wb[MOLSDE_B_B2 + o];
-                mix[ax * TE + q] = d[0] * F[ax * TE + q] + d[1] * F[(3 + ax) * TE + q] + d[2] * F[(6 + ax) * TE + q];
-            }
+            for (int ax = 0; ax < 3; ++ax) mix[ax * TE + e] = d0 * F[ax] + d1 * F[3 + ax] + d2 * F[6 + ax];
         }
-        __syncthreads();
+        quad_sync(q);
         // gradient_i (+)= mean over the incoming edges (:162-164), ascending-source order
         const int ntg = ti.tb - ti.ta;
-        for (int p = tid; p < ntg * 3; p += NTHREADS) {
+        for (int p = e; p < ntg * 3; p += QT) {
             const int i = ti.ta + p / 3, ax = p % 3;
             const int s0 = rowl[i] - ti.ea, s1 = rowl[i + 1] - ti.ea;
             float sacc = 0.0f;
-            for (int q = s0; q < s1; ++q) sacc += mix[ax * TE + q];
+            for (int s = s0; s < s1; ++s) sacc += mix[ax * TE + s];
             sacc = __fdiv_rn(sacc, static_cast<float>(max(s1 - s0, 1)));  // aggr='mean'
             grad[i * 3 + ax] = (module == 0) ? sacc : grad[i * 3 + ax] + sacc;
         }
-        __syncthreads();
+        // (no trailing barrier: the next tile writes `mix` only after its own quad barrier, which every thread reaches after
+        //  this loop; the operand slot was released by the MMA completion waited for above)
     }
-    if (!ok && tid == 0 && status_flag) atomicExch(status_flag, -7);
-    return phase;
+    __syncthreads();
+    return qs;
 }
 
 // ---------------------------------------------------------------------------------------
 // one full network evaluation on the chunk: positions in smem -> "gradient" in smem
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ uint32_t score_eval(const Chunk c, const float* __restrict__ blob, const int32_t* __restrict__ src_g,
-                                            const float* __restrict__ nattr, const float* __restrict__ e2d_tiles,
-                                            float* __restrict__ scratch, uint32_t tmem_base, uint32_t phase,
-                                            int32_t* status_flag) {
-    float* sm = c.sm;
+__device__ __noinline__ uint32_t score_eval(const Chunk c, const float* __restrict__ blob, const float* __restrict__ nattr,
+                                            const float* __restrict__ e2d_tiles, uint8_t* __restrict__ scratch, uint32_t tmem_base,
+                                            uint32_t qs) {
     PROF_T0();
-    phase_edge_features(c, blob, src_g, e2d_tiles, scratch);
+    qs = phase_edge_features(c, blob, e2d_tiles, scratch, tmem_base, qs);
     PROF_ADD(0);
     // conv_input = node_attr (loop-invariant node_emb output), k-major
+    float* XT = smem_at<float>(c, SB_XT);
     for (int idx = threadIdx.x; idx < c.n * 32; idx += NTHREADS) {
         const int node = idx >> 5, k = idx & 31;
-        sm[S_XT + k * LDX + node] = __ldg(nattr + static_cast<size_t>(c.node0 + node) * 32 + k);
+        XT[k * LDX + node] = __ldg(nattr + static_cast<size_t>(c.node0 + node) * 32 + k);
     }
-    __syncthreads();
     for (int module = 0; module < 2; ++module) {
         for (int conv = 0; conv < 2; ++conv) {
-            stage_bulk(c.si, sm + S_WG, blob + MOLSDE_P_GAT0 + (2 * module + conv) * MOLSDE_P_GAT_SZ, MOLSDE_P_GAT_SZ);
+            const float* sec = blob + MOLSDE_P_GAT0 + (2 * module + conv) * MOLSDE_P_GAT_SZ;
+            __syncthreads();  // previous users of the WP / R regions (E0 operands, FFN staging, basis operands) are done
+            stage_bulk2(c, smem_bytes(c) + SB_WP, sec, MOLSDE_G_WP_SZ, smem_bytes(c) + SB_R, sec + MOLSDE_G_WQKV,
+                        MOLSDE_P_GAT_SZ - MOLSDE_G_WQKV);
             PROF_ADD(1);
             node_qkv(c);
             __syncthreads();
             PROF_ADD(2);
-            gat_edge_phase(c, src_g, scratch, 2 * module + conv);
+            qs = gat_edge_phase(c, scratch, 2 * module + conv, tmem_base, qs);
             __syncthreads();
             PROF_ADD(3);
             node_update(c, conv == 0, 2 * module + conv);
-            __syncthreads();
             PROF_ADD(4);
         }
-        phase = phase_basis(c, blob, src_g, scratch, module, tmem_base, phase, status_flag);
+        qs = phase_basis(c, blob, scratch, module, tmem_base, qs);
         PROF_ADD(5);
     }
-    return phase;
+    return qs;
 }
 
-// TMEM accumulator (128 columns) + mbarrier for the tcgen05 basis GEMM; call with all threads of the CTA
-__device__ __forceinline__ uint32_t tmem_setup(int* si) {
+// TMEM accumulators (128 columns per quad) + mbarriers; call with all threads of the CTA
+__device__ __forceinline__ uint32_t tmem_setup(const Chunk& c) {
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(si + SI_BAR)));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(si + SI_TMABAR)));
-        si[SI_MISC + 2] = 0;
+        for (int i = 0; i < NUM_BARS; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr(c, i)));
+        c.si[SI_MISC + 2] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(si + SI_MISC + 1)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(c.si + SI_MISC + 1)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_fence_before();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    return static_cast<uint32_t>(si[SI_MISC + 1]);
+    tc_fence_after();
+    return static_cast<uint32_t>(c.si[SI_MISC + 1]);
 }
 __device__ __forceinline__ void tmem_teardown(uint32_t tmem_base) {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
 }
 
-__device__ __forceinline__ bool load_chunk(Chunk& c, const molsde_plan& plan, int chunk, int32_t* status_flag) {
-    // (also fills the slot cache of the chunk's first SLOT_CACHE_TILES tiles)
+// (source, target) of edge slot `slot` of a tile, chunk-local: bisection on the row pointer + one global load
+__device__ __forceinline__ void resolve_slot(const Chunk& c, const int32_t* __restrict__ src_g, const TileInfo& ti, int slot,
+                                             int& sj, int& tg) {
+    const int* rowl = c.si + SI_ROWL;
+    sj = 0;
+    tg = ti.ta;
+    if (slot < ti.ne) {
+        const int e = ti.ea + slot;
+        int lo = ti.ta, hi = ti.tb;  // largest i in [ta, tb) with rowl[i] <= e
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (rowl[mid] <= e) lo = mid; else hi = mid;
+        }
+        tg = lo;
+        sj = src_g[c.edge0 + e] - c.node0;
+    }
+}
+
+// Chunk bookkeeping into shared memory + the static slot tables (chunk-local source / target bytes of every edge slot) into the
+// chunk's scratch records: resolved once per chunk instead of at each of the 7 tile visits of every score evaluation.
+__device__ __forceinline__ bool load_chunk(Chunk& c, const molsde_plan& plan, int chunk, uint8_t* __restrict__ scratch,
+                                           int64_t scratch_tiles) {
     const int tid = threadIdx.x;
     c.tile0 = plan.chunk_tile_ptr[chunk];
     c.ntiles = plan.chunk_tile_ptr[chunk + 1] - c.tile0;
     c.node0 = plan.tile_tgt_ptr[c.tile0];
     c.n = plan.tile_tgt_ptr[c.tile0 + c.ntiles] - c.node0;
     c.edge0 = plan.rowptr[c.node0];
-    bool ok = (c.n <= MAXN) && (c.ntiles <= MAXT) && (c.n >= 0);
+    bool ok = (c.n <= MAXN) && (c.ntiles <= MAXT) && (c.n >= 0) && (c.ntiles <= scratch_tiles);
     if (ok) {
         int* rowl = c.si + SI_ROWL;
         int* ttgt = c.si + SI_TTGT;
@@ -939,20 +928,19 @@ __device__ __forceinline__ bool load_chunk(Chunk& c, const molsde_plan& plan, in
             if (rowl[ttgt[t + 1]] - rowl[ttgt[t]] > TE) bad = 1;
         ok = !__syncthreads_or(bad);
         if (ok) {
-            uint8_t* sc = slot_cache(c);
-            const int nt = c.ntiles < SLOT_CACHE_TILES ? c.ntiles : SLOT_CACHE_TILES;
-            for (int item = tid; item < nt * TE; item += NTHREADS) {
+            for (int item = tid; item < c.ntiles * TE; item += NTHREADS) {
                 const int t = item / TE, slot = item % TE;
                 const TileInfo ti = tile_info(c, t);
                 int sj, tg;
                 resolve_slot(c, plan.src, ti, slot, sj, tg);
-                sc[t * 2 * TE + slot] = static_cast<uint8_t>(sj);
-                sc[t * 2 * TE + TE + slot] = static_cast<uint8_t>(tg);
+                uint8_t* rec = scratch + static_cast<size_t>(t) * REC_BYTES + REC_SLOT;
+                rec[slot] = static_cast<uint8_t>(sj);
+                rec[TE + slot] = static_cast<uint8_t>(tg);
             }
             __syncthreads();
         }
     }
-    if (!ok && tid == 0 && status_flag) atomicExch(status_flag, 1 + chunk);
+    if (!ok && tid == 0 && c.status_flag) atomicExch(c.status_flag, 1 + chunk);
     return ok;
 }
 
@@ -963,26 +951,29 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 sde2d3d_score_kernel(molsde_plan plan, const float* __restrict__ blob, const float* __restrict__ nattr,
                      const float* __restrict__ e2d_tiles, const float* __restrict__ pos,
                      const float* __restrict__ stdv, float* __restrict__ score, float* __restrict__ scratch,
-                     int64_t scratch_stride, int32_t* status_flag, const float* __restrict__ attn_keep,
+                     int64_t scratch_tiles, int32_t* status_flag, const float* __restrict__ attn_keep,
                      const float* __restrict__ ffn_keep, float inv_keep) {
     extern __shared__ __align__(128) float smem[];
     Chunk c;
     c.sm = smem;
-    c.si = reinterpret_cast<int*>(smem + S_FLOATS);
+    c.si = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(smem) + SB_INT);
     c.attn_keep = attn_keep; c.ffn_keep = ffn_keep; c.inv_keep = inv_keep;
     c.E_total = plan.E; c.N_total = plan.N;
-    float* my_scratch = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
-    const uint32_t tmem_base = tmem_setup(c.si);
-    uint32_t phase = 0;
+    c.status_flag = status_flag;
+    uint8_t* my_scratch = reinterpret_cast<uint8_t*>(scratch) + static_cast<size_t>(blockIdx.x) * scratch_tiles * REC_BYTES;
+    const uint32_t tmem_base = tmem_setup(c);
+    uint32_t qs = 0;
+    float* P = smem_at<float>(c, SB_POS);
+    const float* G = smem_at<const float>(c, SB_GRAD);
     for (int chunk = blockIdx.x; chunk < plan.num_chunks; chunk += gridDim.x) {
         __syncthreads();
-        if (!load_chunk(c, plan, chunk, status_flag)) continue;
-        for (int i = threadIdx.x; i < c.n * 3; i += NTHREADS) smem[S_POS + i] = pos[static_cast<size_t>(c.node0) * 3 + i];
+        if (!load_chunk(c, plan, chunk, my_scratch, scratch_tiles)) continue;
+        for (int i = threadIdx.x; i < c.n * 3; i += NTHREADS) P[i] = pos[static_cast<size_t>(c.node0) * 3 + i];
         __syncthreads();
-        phase = score_eval(c, blob, plan.src, nattr, e2d_tiles, my_scratch, tmem_base, phase, status_flag);
+        qs = score_eval(c, blob, nattr, e2d_tiles, my_scratch, tmem_base, qs);
         for (int i = threadIdx.x; i < c.n * 3; i += NTHREADS) {
             // get_score: scores = -output / std  (:440-443);  forward (stdv == NULL): the raw network output (:379)
-            score[static_cast<size_t>(c.node0) * 3 + i] = stdv ? __fdiv_rn(-smem[S_GRAD + i], stdv[c.node0 + i / 3]) : smem[S_GRAD + i];
+            score[static_cast<size_t>(c.node0) * 3 + i] = stdv ? __fdiv_rn(-G[i], stdv[c.node0 + i / 3]) : G[i];
         }
     }
     tmem_teardown(tmem_base);
@@ -1037,21 +1028,22 @@ sde2d3d_pc_kernel(molsde_plan plan, const float* __restrict__ blob, const float*
                   const float* __restrict__ e2d_tiles, const float* __restrict__ pos_init,
                   const float* __restrict__ step_table, molsde_pc_config cfg, const float* __restrict__ noise_corr,
                   const float* __restrict__ noise_pred, float* __restrict__ pos_out, float* __restrict__ pos_mean_out,
-                  float* __restrict__ scratch, int64_t scratch_stride, int32_t* work_counter, int32_t* status_flag) {
+                  float* __restrict__ scratch, int64_t scratch_tiles, int32_t* work_counter, int32_t* status_flag) {
     extern __shared__ __align__(128) float smem[];
     Chunk c;
     c.sm = smem;
-    c.si = reinterpret_cast<int*>(smem + S_FLOATS);
+    c.si = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(smem) + SB_INT);
     int* misc = c.si + SI_MISC;
     c.attn_keep = nullptr; c.ffn_keep = nullptr; c.inv_keep = 1.0f; c.E_total = plan.E; c.N_total = plan.N;
-    const uint32_t tmem_base = tmem_setup(c.si);
-    uint32_t phase = 0;
-    float* my_scratch = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
-    float* P = smem + S_POS;
-    float* G = smem + S_GRAD;
-    float* SC = smem + S_SCORE;
-    float* NZ = smem + S_NOISE;
-    float* red = smem + S_RED;
+    c.status_flag = status_flag;
+    const uint32_t tmem_base = tmem_setup(c);
+    uint32_t qs = 0;
+    uint8_t* my_scratch = reinterpret_cast<uint8_t*>(scratch) + static_cast<size_t>(blockIdx.x) * scratch_tiles * REC_BYTES;
+    float* P = smem_at<float>(c, SB_POS);
+    float* G = smem_at<float>(c, SB_GRAD);
+    float* SC = smem_at<float>(c, SB_SCORE);   // (score / noise alias the phase union: only live between two evaluations)
+    float* NZ = smem_at<float>(c, SB_NOISE);
+    float* red = smem_at<float>(c, SB_RED);
     const int tid = threadIdx.x;
     const size_t N3 = static_cast<size_t>(plan.N) * 3;
     while (true) {
@@ -1060,7 +1052,7 @@ sde2d3d_pc_kernel(molsde_plan plan, const float* __restrict__ blob, const float*
         __syncthreads();
         if (misc[0] >= plan.num_chunks) break;
         const int chunk = plan.chunk_order ? plan.chunk_order[misc[0]] : misc[0];  // longest groups first
-        if (!load_chunk(c, plan, chunk, status_flag)) continue;
+        if (!load_chunk(c, plan, chunk, my_scratch, scratch_tiles)) continue;
         const int n3 = c.n * 3;
         const size_t g3 = static_cast<size_t>(c.node0) * 3;
         for (int i = tid; i < n3; i += NTHREADS) P[i] = pos_init[g3 + i];
@@ -1069,7 +1061,7 @@ sde2d3d_pc_kernel(molsde_plan plan, const float* __restrict__ blob, const float*
             const float stdv = step_table[step * 8 + 0], Gd = step_table[step * 8 + 1];
             const float sqrt_alpha = step_table[step * 8 + 2], calpha = step_table[step * 8 + 3];
             // ---------------- corrector (LangevinCorrector.update_fn :191-212) ----------------
-            phase = score_eval(c, blob, plan.src, nattr, e2d_tiles, my_scratch, tmem_base, phase, status_flag);
+            qs = score_eval(c, blob, nattr, e2d_tiles, my_scratch, tmem_base, qs);
             for (int i = tid; i < n3; i += NTHREADS) SC[i] = __fdiv_rn(-G[i], stdv);
             if (noise_corr) {
                 for (int i = tid; i < n3; i += NTHREADS) NZ[i] = noise_corr[static_cast<size_t>(step) * N3 + g3 + i];
@@ -1094,7 +1086,7 @@ sde2d3d_pc_kernel(molsde_plan plan, const float* __restrict__ blob, const float*
             }
             __syncthreads();
             // ---------------- predictor (ReverseDiffusionPredictor.update_fn :163-168) ----------------
-            phase = score_eval(c, blob, plan.src, nattr, e2d_tiles, my_scratch, tmem_base, phase, status_flag);
+            qs = score_eval(c, blob, nattr, e2d_tiles, my_scratch, tmem_base, qs);
             const bool last = (step == cfg.steps - 1);
             for (int i = tid; i < c.n; i += NTHREADS) {
                 float nz[3];
@@ -1126,7 +1118,7 @@ sde2d3d_pc_kernel(molsde_plan plan, const float* __restrict__ blob, const float*
 // ---------------------------------------------------------------------------------------
 // edge_2D_emb (eval): e2d tile = W3 . relu(U[src] + V[tgt]) + b3,  SDE_model_2D_to_3D.py:405-407
 // uv [N][600]: columns 0..299 = folded first layer applied to h[row], 300..599 to h[col].
-// One-time (loop-invariant) kernel: fp32 FFMA register tile, 256 threads, output in the [32][136] tile layout.
+// One-time (loop-invariant) kernel: fp32 FFMA register tile, 256 threads, output in the [8][128][4] tile layout.
 // ---------------------------------------------------------------------------------------
 constexpr int E2D_THREADS = 256;
 
@@ -1176,22 +1168,16 @@ edge2d_emb_kernel(molsde_plan plan, const float* __restrict__ uv, const float* _
             }
             __syncthreads();
         }
-        float* out = e2d_tiles + static_cast<size_t>(tile) * TILE_FLOATS;
+        // output tile [8 feature quads][128 slots][4]: the edge's thread of the score kernels reads its 32 values as 8 coalesced 16 B loads
+        float* out = e2d_tiles + static_cast<size_t>(tile) * E2D_TILE_FLOATS;
+        const float4 bq = *reinterpret_cast<const float4*>(b3 + to * 4);  // this thread: feature quad `to`, slots 4*te .. 4*te+3
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = to * 4 + j;
-            const float bj = b3[col];
-            float4 o = make_float4(acc[0][j] + bj, acc[1][j] + bj, acc[2][j] + bj, acc[3][j] + bj);
-            const int s = te * 4;
-            if (s >= ne) o = make_float4(0.f, 0.f, 0.f, 0.f);
-            else {
-                if (s + 1 >= ne) o.y = 0.f;
-                if (s + 2 >= ne) o.z = 0.f;
-                if (s + 3 >= ne) o.w = 0.f;
-            }
-            *reinterpret_cast<float4*>(out + col * LDA + s) = o;
+        for (int i = 0; i < 4; ++i) {
+            const int s = te * 4 + i;
+            float4 o = make_float4(acc[i][0] + bq.x, acc[i][1] + bq.y, acc[i][2] + bq.z, acc[i][3] + bq.w);
+            if (s >= ne) o = make_float4(0.f, 0.f, 0.f, 0.f);  // dead slots stay zero
+            *reinterpret_cast<float4*>(out + (to * TE + s) * 4) = o;
         }
-        if (tid < 32 * (LDA - TE)) out[(tid / (LDA - TE)) * LDA + TE + tid % (LDA - TE)] = 0.0f;  // pad columns
     }
 }
 
@@ -1319,7 +1305,7 @@ int molsde_debug_read_prof(unsigned long long* host_out) {
 }
 #endif
 
-int64_t molsde_tile_floats(void) { return TILE_FLOATS; }
+int64_t molsde_tile_floats(void) { return E2D_TILE_FLOATS; }
 
 int molsde_edge2d_bn_train(const molsde_plan* plan, float* uv, int32_t F, const float* gamma, const float* beta, float eps,
                            float momentum, float* running_mean, float* running_var, float* batch_mean, float* batch_var,
@@ -1364,7 +1350,7 @@ int64_t molsde_sde2d3d_scratch_floats(const molsde_plan* plan, int32_t max_chunk
     int ctas = plan->num_chunks < kNumSMs ? plan->num_chunks : kNumSMs;
     if (ctas < 1) ctas = 1;
     if (num_ctas_out) *num_ctas_out = ctas;
-    return static_cast<int64_t>(ctas) * max_chunk_tiles * SCR_TILE;
+    return static_cast<int64_t>(ctas) * max_chunk_tiles * REC_FLOATS;
 }
 
 int molsde_edge2d_emb_eval(const molsde_plan* plan, const float* uv, const float* w3t, const float* b3,
@@ -1387,8 +1373,8 @@ static int launch_score(const molsde_plan* plan, const molsde_sde2d3d_params* pa
     if (params->blob_floats < MOLSDE_P_TOTAL) return MOLSDE_ERR_INVALID;
     if (plan->num_chunks == 0) return MOLSDE_OK;
     int ctas = plan->num_chunks < kNumSMs ? plan->num_chunks : kNumSMs;
-    const int64_t stride = (scratch_floats / ctas) / SCR_TILE * SCR_TILE;
-    if (stride < SCR_TILE) return MOLSDE_ERR_WORKSPACE;
+    const int64_t stride = (scratch_floats / ctas) / REC_FLOATS;  // scratch records (tiles) per CTA
+    if (stride < 1) return MOLSDE_ERR_WORKSPACE;
     cudaError_t err = cudaFuncSetAttribute(sde2d3d_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (err != cudaSuccess) { set_last_error(cudaGetErrorString(err)); return MOLSDE_ERR_CUDA; }
     sde2d3d_score_kernel<<<ctas, NTHREADS, SMEM_BYTES, as_stream(stream)>>>(*plan, params->blob, nattr, e2d_tiles, pos,
@@ -1426,8 +1412,8 @@ int molsde_sde2d3d_pc_sample(const molsde_plan* plan, const molsde_sde2d3d_param
     if ((noise_corr == nullptr) != (noise_pred == nullptr)) return MOLSDE_ERR_INVALID;
     if (plan->num_chunks == 0) return MOLSDE_OK;
     int ctas = plan->num_chunks < kNumSMs ? plan->num_chunks : kNumSMs;
-    const int64_t stride = (scratch_floats / ctas) / SCR_TILE * SCR_TILE;
-    if (stride < SCR_TILE) return MOLSDE_ERR_WORKSPACE;
+    const int64_t stride = (scratch_floats / ctas) / REC_FLOATS;  // scratch records (tiles) per CTA
+    if (stride < 1) return MOLSDE_ERR_WORKSPACE;
     cudaError_t err = cudaFuncSetAttribute(sde2d3d_pc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (err != cudaSuccess) { set_last_error(cudaGetErrorString(err)); return MOLSDE_ERR_CUDA; }
     err = cudaMemsetAsync(work_counter, 0, sizeof(int32_t), as_stream(stream));

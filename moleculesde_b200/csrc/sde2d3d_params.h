@@ -1,60 +1,63 @@
 /* Float offsets inside the packed SDEModel2Dto3D_02 parameter blob (molsde_sde2d3d_params.blob).
  * The host (moleculesde_b200/sde_2d_to_3d.py::packed_params) builds it from the reference
- * state_dict keys.  Every `*_W` matrix is stored k-major (`[in][ld]`, i.e. the
- * nn.Linear weight transposed) with a padded leading dimension ld == 8 (mod 32) so that the
- * mma.sync B-fragment loads (lane -> (k = lane%4, n = lane/4)) are shared-memory bank-conflict free.
- * All offsets are multiples of 4 floats (16 B, cp.async granularity). */
+ * state_dict keys.
+ *
+ * Two weight formats live in the blob:
+ *  (a) tcgen05 B-operand tiles (every per-edge GEMM: Fourier-feature layers, project.1, lin_edge, basis MLP layer 0):
+ *      fp16, two-way split  w = hi + lo  (hi = fp16(w), lo = fp16(w - hi)), each part stored as an [N rows][K] K-major tile in
+ *      the canonical no-swizzle core-matrix layout (8 rows x 16 B = 8 halves):
+ *        byte offset(n, k) = (k/8)*(N*16) + (n/8)*128 + (n%8)*16 + (k%8)*2        (LBO = N*16 B, SBO = 128 B)
+ *  (b) mma.sync B blocks of the per-node GEMMs (q|k|v, lin_skip, FFN): k-major [in][ld] words with ld == 8 (mod 32), holding
+ *      fp16 hi/lo pair words (pack_f16_pairs; csrc/mma_tile.cuh mma_gemm_hp).
+ * All section offsets are multiples of 32 floats (128 B); every section is copied to shared memory by ONE TMA bulk copy. */
 #ifndef MOLSDE_SDE2D3D_PARAMS_H_
 #define MOLSDE_SDE2D3D_PARAMS_H_
 
-#define MOLSDE_LD32 40   /* leading dimension of a 32-column weight block  */
-#define MOLSDE_LD96 104  /* q|k|v block                                     */
-#define MOLSDE_LD128 136 /* 128-column weight block                         */
+#define MOLSDE_LD32 40   /* leading dimension of a 32-column mma.sync weight block */
+#define MOLSDE_LD96 104  /* q|k|v block                                            */
 
 /* ---- per-edge feature stage (SDE_model_2D_to_3D.py:402-432) ---- */
 #define MOLSDE_P_GFP_DIST_W 0   /* dist_gaussian_fourier.W [32] */
 #define MOLSDE_P_GFP_COFF_W 32  /* coff_gaussian_fourier.W [32] */
-#define MOLSDE_P_IN_B 64        /* input_mlp.layers.0.bias [32] */
-#define MOLSDE_P_H_B 96         /* fused bias: project.0.bias + P_i b_c + P_j b_c [32] */
-#define MOLSDE_P_H_WSIN 128     /* project.layers.0.weight[:,0] (pseudo_sin) [32] */
-#define MOLSDE_P_H_WCOS 160     /* project.layers.0.weight[:,1] (pseudo_cos) [32] */
-#define MOLSDE_P_P1_B 192       /* project.layers.1.bias [32] */
-#define MOLSDE_P_IN_W 224       /* input_mlp.layers.0.weight^T [64][40] */
-#define MOLSDE_P_H_W 2784       /* (project.0.weight[:,2:34] @ coff_mlp.weight)^T rows 0..127,
-                                   (project.0.weight[:,34:66] @ coff_mlp.weight)^T rows 128..255; [256][40] */
-#define MOLSDE_P_P1_W 13024     /* project.layers.1.weight^T [32][40] */
-#define MOLSDE_P_E0_END 14304
+#define MOLSDE_P_E0_HV 64       /* [32][4]: {fused hidden bias (project.0.bias + P_i b_c + P_j b_c), project.0.weight[:,0] (pseudo_sin),
+                                   project.0.weight[:,1] (pseudo_cos), 0} per hidden unit */
+#define MOLSDE_P_E0_OB 192      /* [32][2]: {input_mlp.layers.0.bias, project.layers.1.bias} per output column */
+#define MOLSDE_P_E0_BT 256      /* 11 B tiles of [32 n][32 k] fp16, each 1024 floats = hi (2048 B) | lo (2048 B):
+                                   tiles 0..9 = Fourier sub-blocks b = 2*blk + half (blk 0: input_mlp.layers.0.weight over gfp(d);
+                                   blk 1..4: (project.0.weight[:,2:] (.) coff_mlp.weight) over gfp(ci0, ci2, cj0, cj2)), K order inside a
+                                   sub-block = [sin f(16*half .. +15) | cos f(16*half .. +15)];  tile 10 = project.layers.1.weight */
+#define MOLSDE_E0_BT_FLOATS 1024
+#define MOLSDE_P_E0_END 11520
 
-/* ---- one GATLayer (score_network.gnn_layers.{m}.{c}), base = P_GAT0 + (2m+c)*P_GAT_SZ ---- */
-#define MOLSDE_P_GAT0 14304
-#define MOLSDE_G_WQKV 0     /* [lin_query | lin_key | lin_value].weight^T [32][104] */
-#define MOLSDE_G_WS 3328    /* MHA.lin_skip.weight^T [32][40] */
-#define MOLSDE_G_WE 4608    /* MHA.lin_edge.weight^T [32][40] (no bias) */
-#define MOLSDE_G_F0 5888    /* FFN.0.weight^T [32][40] */
-#define MOLSDE_G_F3 7168    /* FFN.3.weight^T [32][40] */
-#define MOLSDE_G_BQKV 8448  /* [96] */
-#define MOLSDE_G_BS 8544
-#define MOLSDE_G_LN1_W 8576
-#define MOLSDE_G_LN1_B 8608
-#define MOLSDE_G_F0_B 8640
-#define MOLSDE_G_F3_B 8672
-#define MOLSDE_G_LN2_W 8704
-#define MOLSDE_G_LN2_B 8736
-#define MOLSDE_P_GAT_SZ 8768
+/* ---- one GATLayer (score_network.gnn_layers.{m}.{c}), base = P_GAT0 + (2m+c)*P_GAT_SZ ----
+ * [0, G_WP_SZ): resident for the whole layer;  [G_WQKV, P_GAT_SZ): only needed by the q|k|v GEMM (staged over the edge-phase buffers) */
+#define MOLSDE_P_GAT0 11520
+#define MOLSDE_G_WS 0       /* MHA.lin_skip.weight^T [32][40] (pair words) */
+#define MOLSDE_G_F0 1280    /* FFN.0.weight^T [32][40] */
+#define MOLSDE_G_F3 2560    /* FFN.3.weight^T [32][40] */
+#define MOLSDE_G_BQKV 3840  /* [96] */
+#define MOLSDE_G_BS 3936
+#define MOLSDE_G_LN1_W 3968
+#define MOLSDE_G_LN1_B 4000
+#define MOLSDE_G_F0_B 4032
+#define MOLSDE_G_F3_B 4064
+#define MOLSDE_G_LN2_W 4096
+#define MOLSDE_G_LN2_B 4128
+#define MOLSDE_G_WEC 4160   /* MHA.lin_edge.weight (no bias) as a tcgen05 B tile [32 n][32 k]: hi (512 floats) | lo (512 floats) */
+#define MOLSDE_G_WP_SZ 5184
+#define MOLSDE_G_WQKV 5184  /* [lin_query | lin_key | lin_value].weight^T [32][104] (pair words) */
+#define MOLSDE_P_GAT_SZ 8512
 
 /* ---- one basis MLP (score_network.basis_mlp_modules.{m}), base = P_BASIS0 + m*P_BASIS_SZ ----
- * The first layer (64 -> 128; input rows 0..31 = h_row+h_col, 32..63 = edge_attr) runs on tcgen05: its weight is
- * stored as the B operand tile [N=128][K=64], K-major, in the canonical no-swizzle core-matrix layout
- *   float index(n, k) = (k/4)*512 + (n/8)*32 + (n%8)*4 + (k%4)        (LBO = 2048 B, SBO = 128 B)
- * twice: the tf32 "hi" part (top 19 bits) and the exact remainder "lo" (3xTF32 split done on the host). */
-#define MOLSDE_P_BASIS0 49376
-#define MOLSDE_B_W1C_HI 0      /* [8192] */
-#define MOLSDE_B_W1C_LO 8192   /* [8192] */
-#define MOLSDE_B_B1 16384      /* .0.bias [128] */
-#define MOLSDE_B_W2 16512      /* .2.weight [3][128] */
-#define MOLSDE_B_B2 16896      /* .2.bias [3] + 1 pad */
-#define MOLSDE_P_BASIS_SZ 16900
+ * layer 0 (64 -> 128; input k 0..31 = h_row+h_col, 32..63 = edge_attr) as a tcgen05 B tile [128 n][64 k] fp16 hi | lo. */
+#define MOLSDE_P_BASIS0 45568
+#define MOLSDE_B_W1_HI 0     /* 16384 B = 4096 floats */
+#define MOLSDE_B_W1_LO 4096
+#define MOLSDE_B_EPI 8192    /* [128][4]: {.0.bias[n], .2.weight[0][n], .2.weight[1][n], .2.weight[2][n]} */
+#define MOLSDE_B_B2 8704     /* .2.bias [3] + 1 pad */
+#define MOLSDE_P_BASIS_SZ 8708
+#define MOLSDE_P_BASIS_STRIDE 8736  /* section stride (multiple of 32 floats) */
 
-#define MOLSDE_P_TOTAL 83176
+#define MOLSDE_P_TOTAL 63040
 
 #endif

@@ -134,6 +134,7 @@ class ParamStore:
             check(lib().molsde_adam_step(self.flat[a:b].data_ptr(), self.grad[a:b].data_ptr(), self.exp_avg[a:b].data_ptr(),
                                          self.exp_avg_sq[a:b].data_ptr(), b - a, l, betas[0], betas[1], eps, weight_decay,
                                          self.step_count, grad_scale, s), "adam_step")
+        _abi.touch_params()   # raw-pointer update: torch's _version does not move, the packed-weight caches key on this epoch
 
 
 # ======================================================================================================

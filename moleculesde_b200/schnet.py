@@ -102,7 +102,7 @@ class SchNet(nn.Module):
 
     # filter-MLP weights in the kernel layout (k-major, ld 136, zero padded), rebuilt when parameters change
     def _filters(self):
-        ver = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        ver = (_abi.param_epoch(),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._packed is not None and self._packed[0] == ver:
             return self._packed[1]
         packed = []

@@ -18,16 +18,15 @@ from .plan import TilePlan, build_plan
 from .sde import VESDE, VPSDE
 
 # float offsets of csrc/sde2d3d_params.h
-LD32, LD96, LD128 = 40, 104, 136
+LD32, LD96 = 40, 104
 P_GFP_DIST_W, P_GFP_COFF_W = 0, 32
-P_IN_B, P_H_B, P_H_WSIN, P_H_WCOS, P_P1_B = 64, 96, 128, 160, 192
-P_IN_W, P_H_W, P_P1_W, P_E0_END = 224, 2784, 13024, 14304
-P_GAT0, P_GAT_SZ = 14304, 8768
-P_BASIS0, P_BASIS_SZ = 49376, 16900
-P_TOTAL = 83176
-_G = dict(WQKV=0, WS=3328, WE=4608, F0=5888, F3=7168, BQKV=8448, BS=8544, LN1_W=8576, LN1_B=8608, F0_B=8640,
-          F3_B=8672, LN2_W=8704, LN2_B=8736)
-_B = dict(W1C_HI=0, W1C_LO=8192, B1=16384, W2=16512, B2=16896)
+P_E0_HV, P_E0_OB, P_E0_BT, E0_BT_FLOATS, P_E0_END = 64, 192, 256, 1024, 11520
+P_GAT0, P_GAT_SZ = 11520, 8512
+P_BASIS0, P_BASIS_SZ, P_BASIS_STRIDE = 45568, 8708, 8736
+P_TOTAL = 63040
+_G = dict(WS=0, F0=1280, F3=2560, BQKV=3840, BS=3936, LN1_W=3968, LN1_B=4000, F0_B=4032, F3_B=4064, LN2_W=4096, LN2_B=4128,
+          WEC=4160, WP_SZ=5184, WQKV=5184)
+_B = dict(W1_HI=0, W1_LO=4096, EPI=8192, B2=8704)
 
 
 def pack_f16_pairs(blk: torch.Tensor) -> torch.Tensor:
@@ -59,13 +58,31 @@ def unpack_f16_pairs(words: torch.Tensor) -> torch.Tensor:
     return halves(w[:, 0]) + halves(w[:, 1])
 
 
-def _umma_kmajor_tile(w: torch.Tensor) -> torch.Tensor:
-    """[R, K] matrix -> flat tcgen05 operand tile, K-major canonical no-swizzle core-matrix layout:
-    index(r, k) = (k//4)*(R//8)*32 + (r//8)*32 + (r%8)*4 + (k%4)   (8 rows x 16 B core matrices, csrc/sde2d3d_params.h)."""
+def umma_tile_f16(w: torch.Tensor) -> torch.Tensor:
+    """[R, K] fp16 matrix -> flat tcgen05 operand tile, K-major canonical no-swizzle core-matrix layout (8 rows x 16 B):
+    half index(r, k) = (k//8)*(R*8) + (r//8)*64 + (r%8)*8 + (k%8)   (LBO = R*16 B, SBO = 128 B; csrc/sde2d3d_params.h)."""
     R, K = w.shape
-    assert R % 8 == 0 and K % 4 == 0
-    t = w.reshape(R // 8, 8, K // 4, 4).permute(2, 0, 1, 3).contiguous()  # [K/4][R/8][8][4]
-    return t.reshape(-1)
+    assert R % 8 == 0 and K % 8 == 0 and w.dtype == torch.float16
+    return w.reshape(R // 8, 8, K // 8, 8).permute(2, 0, 1, 3).contiguous().reshape(-1)   # [K/8][R/8][8][8]
+
+
+def split_f16(w: torch.Tensor):
+    """Two-way fp16 split of an fp32 tensor: hi = fp16(w), lo = fp16(w - hi); hi + lo carries 22 significant bits."""
+    hi = w.float().half()
+    lo = (w.float() - hi.float()).half()
+    return hi, lo
+
+
+def umma_tile_split_words(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] fp32 weight (nn.Linear layout: rows = outputs) -> float32 words of the B-operand tile pair hi | lo."""
+    hi, lo = split_f16(w)
+    return torch.cat([umma_tile_f16(hi), umma_tile_f16(lo)]).view(torch.float32)
+
+
+def unpack_umma_tile_f16(words: torch.Tensor, R: int, K: int) -> torch.Tensor:
+    """Inverse of `umma_tile_f16` on float32 words (tests): -> [R, K] fp32."""
+    h = words.contiguous().view(torch.float16).reshape(K // 8, R // 8, 8, 8).permute(1, 2, 0, 3).reshape(R, K)
+    return h.float()
 
 
 class MultiLayerPerceptron(nn.Module):
@@ -199,11 +216,10 @@ class SDEModel2Dto3D_02(nn.Module):
             raise NotImplementedError(f"SDE_type {SDE_type!r} (discrete_VE is not on the BASELINE path)")
         self.num_diffusion_timesteps = num_diffusion_timesteps
         self._packed: Optional[Tuple[tuple, Dict[str, torch.Tensor]]] = None
-        self._invariants: Dict[tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
 
     # ------------------------------------------------------------------ parameters -> kernel layout
     def _param_version(self) -> tuple:
-        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        return (_abi.param_epoch(),) + tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
 
     def packed_params(self) -> Dict[str, torch.Tensor]:
         """Parameter blob (csrc/sde2d3d_params.h) + BN-folded edge_2D_emb first layer; rebuilt only when
@@ -226,30 +242,39 @@ class SDEModel2Dto3D_02(nn.Module):
             blk[:, :out_f] = w.t()
             put(off, pack_f16_pairs(blk))
 
+        H = self.hidden_dim
         put(P_GFP_COFF_W, sd["coff_gaussian_fourier.W"])
+        ob = torch.zeros(H, 2, dtype=torch.float32, device=dev)            # {input_mlp bias, project.1 bias} per column
+        w_in = torch.zeros(H, 2 * H, dtype=torch.float32, device=dev)      # [out, 64 = sin f | cos f]
         if self.has_distance_branch:
             put(P_GFP_DIST_W, sd["dist_gaussian_fourier.W"])
-            put(P_IN_B, sd["input_mlp.layers.0.bias"])
-            put_kmajor(P_IN_W, sd["input_mlp.layers.0.weight"], LD32)
+            ob[:, 0] = sd["input_mlp.layers.0.bias"]
+            w_in = sd["input_mlp.layers.0.weight"]
         else:
             # SDEModel2Dto3D_01: edge_attr = edge_attr_2D + frame (:181).  The kernels compute (W_in gfp(d) + b_in) * e2d + frame
             # with one fused multiply-add; zero frequencies / weights and a unit bias make the factor exactly 1.0f, so the
             # result is the same single-rounded sum.
-            put(P_IN_B, torch.ones(self.hidden_dim, dtype=torch.float32, device=dev))
+            ob[:, 0] = 1.0
         # coff_mlp is a bare Linear feeding project.layers.0 (SDE_model_2D_to_3D.py:297-304,429-430): fold it in
         # (float64 products, rounded once) so the hidden layer accumulates straight from the Fourier features.
-        H = self.hidden_dim
         P0 = sd["project.layers.0.weight"].double()                     # [32, 66] = [psin, pcos, emb_i(32), emb_j(32)]
         Wc, bc = sd["coff_mlp.weight"].double(), sd["coff_mlp.bias"].double()  # [32,128], [32]
         Pi, Pj = P0[:, 2:2 + H], P0[:, 2 + H:2 + 2 * H]
-        w_h = torch.cat([Pi @ Wc, Pj @ Wc], dim=1)                       # [32, 256]
-        b_h = sd["project.layers.0.bias"].double() + Pi @ bc + Pj @ bc
-        put_kmajor(P_H_W, w_h.float(), LD32)
-        put(P_H_B, b_h.float())
-        put(P_H_WSIN, P0[:, 0].float())
-        put(P_H_WCOS, P0[:, 1].float())
-        put_kmajor(P_P1_W, sd["project.layers.1.weight"], LD32)
-        put(P_P1_B, sd["project.layers.1.bias"])
+        w_h = torch.cat([Pi @ Wc, Pj @ Wc], dim=1).float()               # [32, 256] over gfp(ci0) | gfp(ci2) | gfp(cj0) | gfp(cj2)
+        b_h = (sd["project.layers.0.bias"].double() + Pi @ bc + Pj @ bc).float()
+        hv = torch.zeros(H, 4, dtype=torch.float32, device=dev)           # {hidden bias, w_sin, w_cos, 0}
+        hv[:, 0], hv[:, 1], hv[:, 2] = b_h, P0[:, 0].float(), P0[:, 1].float()
+        put(P_E0_HV, hv)
+        ob[:, 1] = sd["project.layers.1.bias"]
+        put(P_E0_OB, ob)
+        # tcgen05 B tiles of the Fourier sub-blocks b = 2*blk + half: K order [sin f(16*half..+15) | cos f(16*half..+15)]
+        w_all = torch.cat([w_in, w_h], dim=1)                             # [32, 5 x 64]
+        for blk in range(5):
+            for half in range(2):
+                base_k = blk * 2 * H + half * 16
+                sub = torch.cat([w_all[:, base_k:base_k + 16], w_all[:, base_k + H:base_k + H + 16]], dim=1)   # [32 n, 32 k]
+                put(P_E0_BT + (2 * blk + half) * E0_BT_FLOATS, umma_tile_split_words(sub))
+        put(P_E0_BT + 10 * E0_BT_FLOATS, umma_tile_split_words(sd["project.layers.1.weight"]))
         for m in range(2):
             for c in range(2):
                 base = P_GAT0 + (2 * m + c) * P_GAT_SZ
@@ -261,7 +286,7 @@ class SDEModel2Dto3D_02(nn.Module):
                                                   sd[p + "MHA.lin_value.bias"]]))
                 put_kmajor(base + _G["WS"], sd[p + "MHA.lin_skip.weight"], LD32)
                 put(base + _G["BS"], sd[p + "MHA.lin_skip.bias"])
-                put_kmajor(base + _G["WE"], sd[p + "MHA.lin_edge.weight"], LD32)
+                put(base + _G["WEC"], umma_tile_split_words(sd[p + "MHA.lin_edge.weight"]))
                 put(base + _G["LN1_W"], sd[p + "norm1.weight"])
                 put(base + _G["LN1_B"], sd[p + "norm1.bias"])
                 put_kmajor(base + _G["F0"], sd[p + "FFN.0.weight"], LD32)
@@ -270,14 +295,11 @@ class SDEModel2Dto3D_02(nn.Module):
                 put(base + _G["F3_B"], sd[p + "FFN.3.bias"])
                 put(base + _G["LN2_W"], sd[p + "norm2.weight"])
                 put(base + _G["LN2_B"], sd[p + "norm2.bias"])
-            base = P_BASIS0 + m * P_BASIS_SZ
+            base = P_BASIS0 + m * P_BASIS_STRIDE
             p = f"score_network.basis_mlp_modules.{m}."
-            w1 = sd[p + "0.weight"]                                   # [128 out (n), 64 in (k)]
-            w1_hi = (w1.contiguous().view(torch.int32) & -8192).view(torch.float32)   # top 19 bits = tf32 operand
-            put(base + _B["W1C_HI"], _umma_kmajor_tile(w1_hi))
-            put(base + _B["W1C_LO"], _umma_kmajor_tile(w1 - w1_hi))
-            put(base + _B["B1"], sd[p + "0.bias"])
-            put(base + _B["W2"], sd[p + "2.weight"])
+            put(base + _B["W1_HI"], umma_tile_split_words(sd[p + "0.weight"]))   # [128 out (n), 64 in (k)] -> hi (4096) | lo (4096)
+            epi = torch.cat([sd[p + "0.bias"][:, None], sd[p + "2.weight"].t()], dim=1)   # [128, 4] = {b1, w2[0], w2[1], w2[2]}
+            put(base + _B["EPI"], epi.contiguous())
             put(base + _B["B2"], sd[p + "2.bias"])
         # edge_2D_emb, eval mode: y = relu(BN(W0 [h_row,h_col] + b0)); BN folded into W0/b0 and the
         # layer factored per node:  W0 [h_r, h_c] = Wa h_r + Wb h_c   (SDE_model_2D_to_3D.py:265,405-407)
@@ -296,7 +318,6 @@ class SDEModel2Dto3D_02(nn.Module):
             "w_node": sd["node_emb.layers.0.weight"].contiguous(), "b_node": sd["node_emb.layers.0.bias"].contiguous(),
         }
         self._packed = (ver, packed)
-        self._invariants.clear()
         return packed
 
     # ------------------------------------------------------------------ graph / invariants
@@ -318,10 +339,13 @@ class SDEModel2Dto3D_02(nn.Module):
         output in tile layout.  The reference recomputes both in every `get_score` call
         (`SDE_model_2D_to_3D.py:395,404-407,435`); they depend only on `node_2D_repr`."""
         pk = self.packed_params()
-        key = (id(prep), node_2D_repr.data_ptr(), node_2D_repr._version, tuple(node_2D_repr.shape))
-        hit = self._invariants.get(key)
-        if hit is not None:
-            return hit
+        # The cache lives ON the PreparedGraph (its lifetime = the batch's) and holds the representation alive, so neither a
+        # recycled object id nor a recycled device block can alias another batch's entry.
+        key = (id(self), self._packed[0], node_2D_repr.data_ptr(), node_2D_repr._version, tuple(node_2D_repr.shape))
+        hit = getattr(prep, "_invariants", None)
+        if hit is not None and hit[0] == key and hit[1] is node_2D_repr and \
+                hit[2][1].numel() == max(prep.plan.num_tiles, 1) * _abi.TILE_FLOATS:
+            return hit[2]
         h = node_2D_repr.detach().float().contiguous()
         N, dev, s = h.size(0), h.device, stream_ptr(h)
         nattr = torch.empty(N, _abi.HID, dtype=torch.float32, device=dev)
@@ -334,9 +358,7 @@ class SDEModel2Dto3D_02(nn.Module):
         st = prep.plan.as_struct()
         check(lib().molsde_edge2d_emb_eval(ctypes.byref(st), ptr(uv), ptr(pk["w3t"]), ptr(pk["b3"]), ptr(e2d), s),
               "edge2d_emb_eval")
-        if len(self._invariants) > 8:
-            self._invariants.clear()
-        self._invariants[key] = (nattr, e2d)
+        prep._invariants = (key, node_2D_repr, (nattr, e2d))
         return nattr, e2d
 
     # ------------------------------------------------------------------ reference API
@@ -359,6 +381,7 @@ class SDEModel2Dto3D_02(nn.Module):
         check(lib().molsde_edge2d_bn_train(ctypes.byref(st), ptr(uv), F, ptr(pk["bn_w"]), ptr(pk["bn_b"]), bn.eps, bn.momentum,
                                            ptr(bn.running_mean), ptr(bn.running_var), ptr(mean), ptr(var), s), "edge2d_bn_train")
         bn.num_batches_tracked += 1
+        _abi.touch_params()   # running statistics moved under the folded eval-mode weights cached by packed_params()
         e2d = torch.empty(max(prep.plan.num_tiles, 1) * _abi.TILE_FLOATS, dtype=torch.float32, device=dev)
         check(lib().molsde_edge2d_emb_eval(ctypes.byref(st), ptr(uv), ptr(pk["w3t"]), ptr(pk["b3"]), ptr(e2d), s),
               "edge2d_emb_eval")

@@ -164,7 +164,7 @@ class EdgeNetwork_dense(nn.Module):
         self._packed = None
 
     def _pack(self):
-        ver = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        ver = (_abi.param_epoch(),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._packed is not None and self._packed[0] == ver:
             return self._packed[1]
         q1 = [a.func_q.layers[0] for a in self.attn] + [a.func_k.layers[0] for a in self.attn]

@@ -454,6 +454,7 @@ class Tape:
         ws = self.empty(self.L.molsde_bn_ws_doubles(M, F), dtype=torch.float64)
         self._call(self.L.molsde_bn_train_fwd, _p(x.data), M, F, _p(g.data), _p(b.data), eps, momentum, _p(running_mean),
                    _p(running_var), int(relu), _p(y), _p(mean), _p(rstd), _p(ws), self.s, what="bn_train_fwd")
+        _abi.touch_params()   # running statistics updated in place through raw pointers (eval-mode BN folds are cached)
         out = Var(y, True)
 
         def bwd():

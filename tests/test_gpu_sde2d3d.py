@@ -78,17 +78,17 @@ def test_edge2d_and_node_invariants_vs_oracle(golden, golden_batch):
     prep = model.prepared(b)
     nattr, e2d = model.invariants(h2d.to(dev), prep)
     assert_parity(nattr, O.node_emb(sd, h2d), "node_emb")
-    # un-tile the kernel's [T][32][128] layout back to CSR edge order, then to the reference order
+    # un-tile the kernel's [T][8 feature quads][128 slots][4] layout back to CSR edge order, then to the reference order
     ei = batch.extended_edge_index
     ref = O.edge_2d_emb(sd, h2d, ei, training=False)  # reference order: sorted by (row, col); row=source
     tt = prep.plan.tile_tgt_ptr.cpu().long()
     rp = prep.csr.rowptr.cpu().long()
-    e2d = e2d.cpu().view(-1, 32, _abi.TILE_LD)
+    e2d = e2d.cpu().view(-1, 8, _abi.TILE_EDGES, 4).permute(0, 2, 1, 3).reshape(-1, _abi.TILE_EDGES, 32)   # [T][slot][feature]
     rows = []
     for t in range(prep.plan.num_tiles):
         ne = int(rp[tt[t + 1]] - rp[tt[t]])
-        rows.append(e2d[t, :, :ne].t())
-        assert torch.all(e2d[t, :, ne:] == 0)
+        rows.append(e2d[t, :ne])
+        assert torch.all(e2d[t, ne:] == 0)
     got = torch.cat(rows)  # CSR-by-target order: (target asc, source asc)
     perm = prep.csr.perm.cpu().long()  # position of each CSR edge in the reference list
     assert_parity(got, ref[perm], "edge_2D_emb (eval)")

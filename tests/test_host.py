@@ -38,23 +38,27 @@ def test_param_offsets_match_header():
     from moleculesde_b200 import sde_2d_to_3d as M
     hdr = open(os.path.join(REPO, "moleculesde_b200", "csrc", "sde2d3d_params.h")).read()
     defs = {k: int(v) for k, v in re.findall(r"#define\s+(MOLSDE_\w+)\s+(\d+)", hdr)}
-    assert defs["MOLSDE_P_TOTAL"] == M.P_TOTAL == defs["MOLSDE_P_BASIS0"] + 2 * defs["MOLSDE_P_BASIS_SZ"]
-    assert defs["MOLSDE_P_GAT0"] == M.P_GAT0 == defs["MOLSDE_P_E0_END"] and defs["MOLSDE_P_GAT_SZ"] == M.P_GAT_SZ
+    assert defs["MOLSDE_P_TOTAL"] == M.P_TOTAL == defs["MOLSDE_P_BASIS0"] + 2 * defs["MOLSDE_P_BASIS_STRIDE"]
+    assert defs["MOLSDE_P_GAT0"] == M.P_GAT0 == defs["MOLSDE_P_E0_END"] == M.P_E0_END and defs["MOLSDE_P_GAT_SZ"] == M.P_GAT_SZ
     assert defs["MOLSDE_P_BASIS0"] == M.P_BASIS0 == M.P_GAT0 + 4 * M.P_GAT_SZ
-    assert (defs["MOLSDE_LD32"], defs["MOLSDE_LD96"], defs["MOLSDE_LD128"]) == (M.LD32, M.LD96, M.LD128)
-    for ld in (M.LD32, M.LD96, M.LD128):
+    assert defs["MOLSDE_P_BASIS_SZ"] == M.P_BASIS_SZ <= defs["MOLSDE_P_BASIS_STRIDE"] == M.P_BASIS_STRIDE
+    assert (defs["MOLSDE_LD32"], defs["MOLSDE_LD96"]) == (M.LD32, M.LD96)
+    for ld in (M.LD32, M.LD96):
         assert ld % 32 == 8  # bank-conflict-free mma B-fragment loads
     for k, v in M._G.items():
         assert defs["MOLSDE_G_" + k] == v and v % 4 == 0
     for k, v in M._B.items():
         assert defs["MOLSDE_B_" + k] == v and v % 4 == 0
-    for name in ("IN_B", "H_B", "H_WSIN", "H_WCOS", "P1_B", "IN_W", "H_W", "P1_W", "E0_END"):
+    for name in ("GFP_DIST_W", "GFP_COFF_W", "E0_HV", "E0_OB", "E0_BT"):
         assert defs["MOLSDE_P_" + name] == getattr(M, "P_" + name)
-        assert defs["MOLSDE_P_" + name] % 4 == 0
-    # blocks do not overlap
-    assert M.P_IN_W + 64 * M.LD32 == M.P_H_W and M.P_H_W + 256 * M.LD32 == M.P_P1_W and M.P_P1_W + 32 * M.LD32 == M.P_E0_END
-    assert M._G["WQKV"] + 32 * M.LD96 == M._G["WS"] and M._G["F3"] + 32 * M.LD32 == M._G["BQKV"]
-    assert M._B["W1C_HI"] + 8192 == M._B["W1C_LO"] and M._B["W1C_LO"] + 8192 == M._B["B1"]
+    assert defs["MOLSDE_E0_BT_FLOATS"] == M.E0_BT_FLOATS == 2 * 32 * 32 * 2 // 4
+    # sections are whole numbers of 128-byte lines (TMA bulk copies, 128 B aligned operand tiles); blocks do not overlap
+    for v in (M.P_E0_BT, M.P_E0_END, M.P_GAT_SZ, M.P_BASIS_STRIDE, M._G["WEC"], M._G["WQKV"]):
+        assert v % 32 == 0
+    assert M.P_E0_BT + 11 * M.E0_BT_FLOATS == M.P_E0_END
+    assert M._G["F3"] + 32 * M.LD32 == M._G["BQKV"] and M._G["LN2_B"] + 32 == M._G["WEC"] and M._G["WEC"] + 1024 == M._G["WP_SZ"]
+    assert M._G["WQKV"] + 32 * M.LD96 == M.P_GAT_SZ
+    assert M._B["W1_LO"] == 128 * 64 * 2 // 4 and M._B["W1_LO"] + 4096 == M._B["EPI"] and M._B["EPI"] + 512 == M._B["B2"]
     api = open(os.path.join(REPO, "include", "molsde_b200.h")).read()
     assert int(re.search(r"#define MOLSDE_TILE_LD (\d+)", api).group(1)) == _abi.TILE_LD
 
@@ -110,23 +114,44 @@ def test_packed_blob_roundtrip(golden):
     pk = m.packed_params()
     blob = pk["blob"]
     assert blob.numel() == M.P_TOTAL
-    # fused project.0 o coff_mlp block reproduces the two-layer reference expression
-    g_i, g_j, ang = torch.randn(5, 128), torch.randn(5, 128), torch.randn(5, 2)
+
+    def tile(off, R, K):   # hi + lo of a tcgen05 B tile pair stored at float offset `off`
+        n = R * K // 2
+        return M.unpack_umma_tile_f16(blob[off:off + n], R, K) + M.unpack_umma_tile_f16(blob[off + n:off + 2 * n], R, K)
+
+    # Fourier sub-block tiles: the fused project.0 o coff_mlp hidden layer reproduces the two-layer reference expression when the
+    # features are fed in the kernel's K order [sin f(16h..) | cos f(16h..)] per sub-block
+    g_i, g_j, ang = torch.randn(5, 128), torch.randn(5, 128), torch.randn(5, 2)   # gfp features [sin 32 | cos 32] x 2 per node
     emb_i = g_i @ sd["coff_mlp.weight"].t() + sd["coff_mlp.bias"]
     emb_j = g_j @ sd["coff_mlp.weight"].t() + sd["coff_mlp.bias"]
     ref = torch.cat([ang, emb_i, emb_j], -1) @ sd["project.layers.0.weight"].t() + sd["project.layers.0.bias"]
-    # mma.sync weight blocks are stored as fp16 hi/lo pair words (pack_f16_pairs): hi + lo reproduces the weight to ~2^-22
-    WH = M.unpack_f16_pairs(blob[M.P_H_W:M.P_H_W + 256 * M.LD32].view(256, M.LD32))[:, :32]
-    got = torch.cat([g_i, g_j], -1) @ WH + blob[M.P_H_B:M.P_H_B + 32] + ang[:, :1] * blob[M.P_H_WSIN:M.P_H_WSIN + 32] \
-        + ang[:, 1:] * blob[M.P_H_WCOS:M.P_H_WCOS + 32]
+    feats = torch.cat([g_i, g_j], -1)                     # [5, 256] = blocks 1..4, each [sin 32 | cos 32]
+    got = torch.zeros(5, 32)
+    for blk in range(1, 5):
+        for half in range(2):
+            k0 = (blk - 1) * 64 + half * 16
+            a = torch.cat([feats[:, k0:k0 + 16], feats[:, k0 + 32:k0 + 48]], dim=1)
+            got += a @ tile(M.P_E0_BT + (2 * blk + half) * M.E0_BT_FLOATS, 32, 32).t()
+    hv = blob[M.P_E0_HV:M.P_E0_HV + 128].view(32, 4)
+    got = got + hv[:, 0] + ang[:, :1] * hv[:, 1] + ang[:, 1:] * hv[:, 2]
     torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+    assert torch.all(hv[:, 3] == 0)
+    # input_mlp over gfp(d) (sub-blocks 0, 1) and project.1 (tile 10)
+    w_in = sd["input_mlp.layers.0.weight"]
+    t0, t1 = tile(M.P_E0_BT, 32, 32), tile(M.P_E0_BT + M.E0_BT_FLOATS, 32, 32)
+    assert float((torch.cat([t0[:, :16], t1[:, :16], t0[:, 16:], t1[:, 16:]], 1) - w_in).abs().max()) <= 2.0 ** -21 * float(w_in.abs().max())
+    w_p1 = sd["project.layers.1.weight"]
+    assert float((tile(M.P_E0_BT + 10 * M.E0_BT_FLOATS, 32, 32) - w_p1).abs().max()) <= 2.0 ** -21 * float(w_p1.abs().max())
+    ob = blob[M.P_E0_OB:M.P_E0_OB + 64].view(32, 2)
+    assert torch.equal(ob[:, 0], sd["input_mlp.layers.0.bias"]) and torch.equal(ob[:, 1], sd["project.layers.1.bias"])
     base = M.P_GAT0 + 3 * M.P_GAT_SZ
-    we = M.unpack_f16_pairs(blob[base + M._G["WE"]:base + M._G["WE"] + 32 * M.LD32].view(32, M.LD32))
-    ref_we = sd["score_network.gnn_layers.1.1.MHA.lin_edge.weight"].t()
-    assert float((we[:, :32] - ref_we).abs().max()) <= 2.0 ** -21 * float(ref_we.abs().max()) and torch.all(we[:, 32:] == 0)
+    we = tile(base + M._G["WEC"], 32, 32)
+    ref_we = sd["score_network.gnn_layers.1.1.MHA.lin_edge.weight"]
+    assert float((we - ref_we).abs().max()) <= 2.0 ** -21 * float(ref_we.abs().max())
+    # mma.sync weight blocks of the node GEMMs are stored as fp16 hi/lo pair words (pack_f16_pairs)
     wqkv = M.unpack_f16_pairs(blob[base + M._G["WQKV"]:base + M._G["WQKV"] + 32 * M.LD96].view(32, M.LD96))
     ref_k = sd["score_network.gnn_layers.1.1.MHA.lin_key.weight"].t()
-    assert float((wqkv[:, 32:64] - ref_k).abs().max()) <= 2.0 ** -21 * float(ref_k.abs().max())
+    assert float((wqkv[:, 32:64] - ref_k).abs().max()) <= 2.0 ** -21 * float(ref_k.abs().max()) and torch.all(wqkv[:, 96:] == 0)
     # the packing itself: even k in the low half, hi row then lo row
     blk = torch.tensor([[1.0, -2.5], [3.0e-5, 0.1], [7.0, 0.0], [-0.33, 1e-3]])
     pk2 = M.pack_f16_pairs(blk).view(torch.int32)
@@ -134,31 +159,18 @@ def test_packed_blob_roundtrip(golden):
     assert pk2[0, 0].item() & 0xFFFF == h[0, 0].view(torch.int16).item() & 0xFFFF
     assert (pk2[0, 0].item() >> 16) & 0xFFFF == h[1, 0].view(torch.int16).item() & 0xFFFF
     assert float((M.unpack_f16_pairs(pk2.view(torch.float32)) - blk).abs().max()) <= 2.0 ** -21
-    base = M.P_BASIS0 + M.P_BASIS_SZ
-    assert torch.equal(blob[base + M._B["W2"]:base + M._B["W2"] + 384].view(3, 128),
-                       sd["score_network.basis_mlp_modules.1.2.weight"])
-    # tcgen05 B-operand tiles of the basis MLP: canonical K-major core-matrix layout, hi + lo == weight exactly
+    # basis MLP: tcgen05 B tile [128 n][64 k] (hi + lo == weight to 2^-22) and the epilogue table {b1, w2[0..2]} per hidden unit
+    base = M.P_BASIS0 + M.P_BASIS_STRIDE
     w1 = sd["score_network.basis_mlp_modules.1.0.weight"]  # [128 (n), 64 (k)]
-    hi = blob[base + M._B["W1C_HI"]:base + M._B["W1C_HI"] + 8192]
-    lo = blob[base + M._B["W1C_LO"]:base + M._B["W1C_LO"] + 8192]
-    for n, k in ((0, 0), (5, 3), (8, 4), (77, 41), (127, 63)):
-        idx = (k // 4) * 512 + (n // 8) * 32 + (n % 8) * 4 + (k % 4)
-        assert (hi[idx] + lo[idx]).item() == w1[n, k].item()
-        assert hi[idx].view(torch.int32).item() & 0x1FFF == 0  # low 13 mantissa bits clear: a tf32 value
-    assert (lo.abs() <= hi.abs() * 2.0 ** -10 + 1e-30).all()
-    # BN-folded, node-factored first layer of edge_2D_emb equals the reference layer in eval mode
-    h = torch.randn(7, 300)
-    row, col = torch.tensor([0, 3, 5]), torch.tensor([1, 2, 6])
-    x = torch.cat([h[row], h[col]], -1) @ sd["edge_2D_emb.0.weight"].t() + sd["edge_2D_emb.0.bias"]
-    x = torch.nn.functional.batch_norm(x, sd["edge_2D_emb.1.running_mean"], sd["edge_2D_emb.1.running_var"],
-                                       sd["edge_2D_emb.1.weight"], sd["edge_2D_emb.1.bias"], False, 0.1, 1e-5)
-    uv = h @ pk["w_uv"].t() + pk["b_uv"]
-    torch.testing.assert_close(uv[row, :300] + uv[col, 300:], x, rtol=1e-4, atol=1e-5)
-    # cache: unchanged parameters -> same object; in-place change -> repack
-    assert m.packed_params() is pk
-    with torch.no_grad():
-        m.coff_mlp.bias.add_(1.0)
-    assert m.packed_params() is not pk
+    assert float((tile(base + M._B["W1_HI"], 128, 64) - w1).abs().max()) <= 2.0 ** -21 * float(w1.abs().max())
+    hi_words = blob[base + M._B["W1_HI"]:base + M._B["W1_HI"] + 4096].view(torch.float16)
+    for n, k in ((0, 0), (5, 3), (8, 4), (77, 41), (127, 63)):   # canonical K-major core-matrix addressing (csrc/sde2d3d_params.h)
+        idx = (k // 8) * (128 * 8) + (n // 8) * 64 + (n % 8) * 8 + (k % 8)
+        assert hi_words[idx] == w1[n, k].half()
+    epi = blob[base + M._B["EPI"]:base + M._B["EPI"] + 512].view(128, 4)
+    assert torch.equal(epi[:, 0], sd["score_network.basis_mlp_modules.1.0.bias"])
+    assert torch.equal(epi[:, 1:].t().contiguous(), sd["score_network.basis_mlp_modules.1.2.weight"])
+    assert torch.equal(blob[base + M._B["B2"]:base + M._B["B2"] + 3], sd["score_network.basis_mlp_modules.1.2.bias"])
 
 
 def test_sde_schedules_match_oracle():
