@@ -89,7 +89,8 @@ constexpr int SI_ROWL = 0;                              // [MAXN+1] edge offsets
 constexpr int SI_TTGT = SI_ROWL + MAXN + 1;             // [MAXT+1] tile target boundaries local to the chunk
 constexpr int SI_MISC = SI_TTGT + MAXT + 1;             // [0] work item, [1] TMEM base, [2] phase of the CTA-wide TMA barrier
 constexpr int SB_BAR = SB_INT + ((SI_MISC + 6) * 4 + 127) / 128 * 128;  // mbarriers (8 B): quad MMA [q][2], quad TMA [q], CTA TMA
-constexpr int NUM_BARS = 3 * QUADS + 1;
+constexpr int NUM_BARS = 5 * QUADS + 1;                        //   ... quad FULL [q][2] (count = QT arrivals) behind them
+constexpr int BAR_CTA_TMA = 3 * QUADS, BAR_FULL0 = 3 * QUADS + 1;
 constexpr size_t SMEM_BYTES = SB_BAR + NUM_BARS * 8;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 static_assert(SB_BIG % 128 == 0 && SB_WP % 128 == 0 && SB_R % 128 == 0 && SB_E0A % 128 == 0 && SB_BA % 128 == 0 && SB_BAR % 8 == 0,
@@ -108,6 +109,10 @@ __device__ unsigned long long g_prof[kNumSMs][8];
 #define PROF_T0()
 #define PROF_ADD(slot)
 #endif
+
+// The quad's MMA / TMA issuing thread sits in warp (4q + q): warps map to the four SM sub-partitions by warp index mod 4, so the
+// four leaders (and their single-thread issue sequences and barrier polls) run on four different schedulers.
+__device__ __forceinline__ bool quad_leader(int q, int e) { return e == (q << 5); }
 
 struct Chunk {
     float* sm;
@@ -129,8 +134,12 @@ template <typename T>
 __device__ __forceinline__ T* smem_at(const Chunk& c, int byte_off) { return reinterpret_cast<T*>(smem_bytes(c) + byte_off); }
 
 // Per-thread synchronisation state, carried through the phases in one register:
-//   bit 0 / 1: phase parity of the quad's two MMA barriers, bit 2: of the quad's TMA barrier, bit 3: a wait timed out (sticky)
-constexpr uint32_t QS_MMA0 = 1u, QS_MMA1 = 2u, QS_TMA = 4u, QS_DEAD = 8u;
+//   bit 0 / 1: phase parity of the quad's two MMA barriers, bit 2: of the quad's TMA barrier, bit 3: a wait timed out (sticky),
+//   bit 4 / 5: phase parity of the quad's two FULL barriers (operand rows written by all 128 threads; only the leader waits).
+//   One FULL barrier per operand slot: a thread may run one ring use ahead of the slowest warp of its quad, never two (re-using a
+//   slot needs the commit of its previous MMAs, which the leader issues only after all 128 arrivals), so arrivals of
+//   consecutive uses must not share a barrier.
+constexpr uint32_t QS_MMA0 = 1u, QS_MMA1 = 2u, QS_TMA = 4u, QS_DEAD = 8u, QS_FULL0 = 16u, QS_FULL1 = 32u;
 
 // ---------------------------------------------------------------------------------------
 // fast, accuracy-checked elementwise helpers (absolute / relative error ~1e-6, far below the 1e-4 bar)
@@ -168,15 +177,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t& qs, uint32_t w
     if (!(qs & QS_DEAD)) {
         const uint32_t parity = (qs & which) ? 1u : 0u;
         uint32_t done = 0;
-        for (int it = 0; it < (1 << 22) && !done; ++it)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        for (int it = 0; it < (1 << 16) && !done; ++it)   // each poll sleeps in hardware up to the hinted time (ns) before it returns
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
         if (!done) {
             qs |= QS_DEAD;
             if (status_flag) atomicExch(status_flag, -7);
         }
     }
     qs ^= which;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void quad_sync(int q) { asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(QT) : "memory"); }
 
@@ -185,7 +197,7 @@ __device__ __forceinline__ void quad_sync(int q) { asm volatile("bar.sync %0, %1
 // may still be read by the previous phase before that); returns when the data is visible to every thread.
 __device__ __forceinline__ void stage_bulk2(const Chunk& c, void* dst0, const float* __restrict__ src0, int nfloat0, void* dst1,
                                             const float* __restrict__ src1, int nfloat1) {
-    const uint32_t bar = bar_addr(c, 3 * QUADS);
+    const uint32_t bar = bar_addr(c, BAR_CTA_TMA);
     const uint32_t parity = static_cast<uint32_t>(c.si[SI_MISC + 2]);
     if (threadIdx.x == 0) {
         fence_proxy_async_smem();  // earlier generic accesses of the destinations before the async-proxy writes
@@ -224,16 +236,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 // Split-fp16 GEMM: three passes (lo*hi, hi*lo, hi*hi; small terms first) over `ksteps` K=16 steps of an A tile [128 x 16*ksteps]
 // (hi at a_hi, lo at a_lo; k-chunk stride 2048 B) and a B tile [N x 16*ksteps] (k-chunk stride N*16 B).
-template <int N>
-__device__ __forceinline__ void umma_split_f16(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int ksteps,
+template <int N, int KSTEPS>
+__device__ __forceinline__ void umma_split_f16(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                                uint32_t accumulate) {
     constexpr uint32_t LBO_A = 2048, LBO_B = N * 16;
-#pragma unroll 1
+    const uint64_t dah = umma_desc(a_hi, LBO_A), dal = umma_desc(a_lo, LBO_A), dbh = umma_desc(b_hi, LBO_B), dbl = umma_desc(b_lo, LBO_B);
+#pragma unroll
     for (int term = 0; term < 3; ++term) {
-        const uint32_t pa = (term == 0) ? a_lo : a_hi, pb = (term == 1) ? b_lo : b_hi;
-#pragma unroll 1
-        for (int kb = 0; kb < ksteps; ++kb) {
-            umma_f16_m128<N>(tmem_d, umma_desc(pa + kb * 2 * LBO_A, LBO_A), umma_desc(pb + kb * 2 * LBO_B, LBO_B), accumulate);
+        const uint64_t da = (term == 0) ? dal : dah, db = (term == 1) ? dbl : dbh;
+#pragma unroll
+        for (int kb = 0; kb < KSTEPS; ++kb) {   // the start-address field counts 16-byte units: one K step = two k-chunks
+            umma_f16_m128<N>(tmem_d, da + static_cast<uint64_t>((kb * 2 * LBO_A) >> 4), db + static_cast<uint64_t>((kb * 2 * LBO_B) >> 4),
+                             accumulate);
             accumulate = 1;
         }
     }
@@ -241,6 +255,7 @@ __device__ __forceinline__ void umma_split_f16(uint32_t tmem_d, uint32_t a_hi, u
 // accumulator columns [col, col+32) / [col, col+8) of this thread's TMEM lane (all 32 lanes of the warp must call)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&f)[32]) {
     uint32_t v[32];
+    __syncwarp();  // .sync.aligned: the quad leader's lane may still be behind after its single-thread MMA issue block
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
         "tcgen05.wait::ld.sync.aligned;\n"
@@ -254,6 +269,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&f)[32]) {
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&f)[8]) {
     uint32_t r[8];
+    __syncwarp();
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t"
                  "tcgen05.wait::ld.sync.aligned;\n"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
@@ -326,11 +342,15 @@ __device__ __forceinline__ TileInfo tile_info(const Chunk& c, int t) {
 // SDE_model_2D_to_3D.py:402-432.  coff_mlp (a bare Linear) is folded into project.layers.0 on the host, so the hidden layer
 // accumulates directly over the four Fourier blocks.
 //   Per tile (one quad): every thread builds the 5 x 64 Fourier features of ITS edge in ten K = 32 sub-blocks
-//   [sin f(16h..) | cos f(16h..)], writes them as fp16 hi/lo rows of the A operand (two ring slots), and the quad leader issues
-//   3 x 2 tcgen05.mma (N = 32) per sub-block into the TMEM accumulators "inv" (columns 0..31, block 0) and "hidden" (32..63,
-//   blocks 1..4) while the threads already compute the next sub-block.  Epilogue: hidden -> +bias, SiLU -> A operand ->
-//   project.1 on the tensor core (columns 64..95) -> edge_attr = (inv + b) * e2d + (proj + b) -> scratch record, already as
-//   the fp16 hi/lo operand tile of the later phases.
+//   [sin f(16h..) | cos f(16h..)] and writes them as fp16 hi/lo rows into a two-slot operand ring; the quad leader issues
+//   3 x 2 tcgen05.mma (N = 32) per ring use into the TMEM accumulators "inv" (block 0) and "hidden" (blocks 1..4).
+//   Nothing blocks on the way: threads ARRIVE on the quad's FULL barrier and go on computing the next sub-block; only the
+//   leader waits for the 128 arrivals, and a slot is re-written only after the commit of its previous MMAs (mbarrier).
+//   The epilogue of a tile is software-pipelined INTO the next tile of the quad (accumulators double-buffered by tile parity):
+//   after sub-block 1 of tile n+1 the ring protocol guarantees that all Fourier MMAs of tile n are complete -> hidden -> +bias,
+//   SiLU -> A operand -> project.1 as one more ring use (its accumulator overwrites "hidden"); after sub-block 3 that MMA is
+//   complete -> edge_attr = (inv + b) * e2d + (proj + b) -> scratch record, already as the fp16 hi/lo operand tile of the
+//   later phases.  The MMA latency is never exposed except when the quad drains its last tile.
 // ---------------------------------------------------------------------------------------
 __device__ __noinline__ uint32_t phase_edge_features(const Chunk c, const float* __restrict__ blob, const float* __restrict__ e2d_tiles,
                                                      uint8_t* __restrict__ scratch, uint32_t tmem_base, uint32_t qs) {
@@ -341,14 +361,102 @@ __device__ __noinline__ uint32_t phase_edge_features(const Chunk c, const float*
     const uint32_t a_base = smem_u32(Aq);
     const uint32_t w_bt = smem_u32(W + MOLSDE_P_E0_BT);
     const uint32_t bar0 = bar_addr(c, 2 * q), bar1 = bar_addr(c, 2 * q + 1);
+    const uint32_t full0 = bar_addr(c, BAR_FULL0 + 2 * q), full1 = bar_addr(c, BAR_FULL0 + 2 * q + 1);
     const uint32_t tq = tmem_base + q * 128;                                  // the quad's accumulator columns
-    const uint32_t tlane = tq + (static_cast<uint32_t>(e & ~31) << 16);       // + this warp's TMEM lane quarter
+    const uint32_t lane_off = static_cast<uint32_t>(e & ~31) << 16;           // this warp's TMEM lane quarter
     __syncthreads();  // the union region may still be read by the tail of the previous evaluation / the PC update
     stage_bulk2(c, smem_bytes(c) + SB_E0W, blob, MOLSDE_P_E0_END, nullptr, nullptr, 0);
-    for (int t = q; t < c.ntiles; t += QUADS) {
+
+    uint32_t ring = 0;     // operand-ring uses so far (slot = ring & 1)
+    uint32_t pend = 0;     // bit s: the last commit on slot s has not been waited for yet
+    // one ring use: 32 operand columns of this thread's row -> slot, arrive; the leader issues the split-fp16 MMA group
+    auto ring_use = [&](const float* v, uint32_t tmem_d, uint32_t w_tile, uint32_t accumulate) {
+        const uint32_t sl = ring & 1u;
+        const uint32_t bar = sl ? bar1 : bar0;
+        if (pend & (1u << sl)) mbar_wait(bar, qs, sl ? QS_MMA1 : QS_MMA0, c.status_flag);  // MMAs of use ring-2 done: slot free
+        uint8_t* Ah = Aq + sl * E0_SLOT;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) store_a_chunk(Ah, Ah + 8192, e, kc, v + 8 * kc);
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
+        const uint32_t full = sl ? full1 : full0, fbit = sl ? QS_FULL1 : QS_FULL0;
+        mbar_arrive(full);
+        if (quad_leader(q, e)) {
+            uint32_t qt = qs;
+            mbar_wait(full, qt, fbit, c.status_flag);
+            qs |= (qt & QS_DEAD);
+            tc_fence_after();
+            const uint32_t ah = a_base + sl * E0_SLOT;
+            umma_split_f16<32, 2>(tmem_d, ah, ah + 8192, w_tile, w_tile + 2048, accumulate);
+            umma_commit(bar);
+        }
+        qs ^= fbit;
+        pend |= (1u << sl);
+        ++ring;
+    };
+    auto drain = [&]() {   // wait for every outstanding commit (older slot first)
+        const uint32_t older = ring & 1u;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t sl = older ^ static_cast<uint32_t>(k);
+            if (pend & (1u << sl)) mbar_wait(sl ? bar1 : bar0, qs, sl ? QS_MMA1 : QS_MMA0, c.status_flag);
+        }
+        pend = 0;
+    };
+    // hidden(tile) -> +bias, SiLU -> operand ring -> project.1 into the columns of "hidden"
+    auto epilogue1 = [&](uint32_t tcol, float psin, float pcos) {
+        tc_fence_after();
+        float hv[32];
+        tmem_ld32(tq + lane_off + tcol + 32, hv);
+        tc_fence_before();
+        const float4* HV = reinterpret_cast<const float4*>(W + MOLSDE_P_E0_HV);
+#pragma unroll
+        for (int col = 0; col < 32; ++col) {
+            const float4 p = HV[col];  // {bias, w_sin, w_cos, 0}
+            hv[col] = silu_fast(hv[col] + p.x + psin * p.y + pcos * p.z);
+        }
+        ring_use(hv, tq + tcol + 32, w_bt + 10 * (MOLSDE_E0_BT_FLOATS * 4), 0u);
+    };
+    // edge_attr = inv3d * e2d + frame  (:432) -> scratch record, as the fp16 hi/lo operand rows of the later phases
+    auto epilogue2 = [&](int t, uint32_t tcol) {
+        uint8_t* rec = scratch + static_cast<size_t>(t) * REC_BYTES;
+        // edge_2D_emb tile of this edge (loop invariant, L2): [8 feature quads][128 slots][4]
+        float4 e2[8];
+        {
+            const float4* e2d_t = reinterpret_cast<const float4*>(e2d_tiles + static_cast<size_t>(c.tile0 + t) * E2D_TILE_FLOATS) + e;
+#pragma unroll
+            for (int fq = 0; fq < 8; ++fq) e2[fq] = __ldg(e2d_t + fq * TE);
+        }
+        tc_fence_after();
+        const float2* OB = reinterpret_cast<const float2*>(W + MOLSDE_P_E0_OB);
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+            float inv[8], pr[8], ea[8];
+            tmem_ld8(tq + lane_off + tcol + 8 * kc, inv);
+            tmem_ld8(tq + lane_off + tcol + 32 + 8 * kc, pr);
+            const float ev[8] = {e2[2 * kc].x, e2[2 * kc].y, e2[2 * kc].z, e2[2 * kc].w,
+                                 e2[2 * kc + 1].x, e2[2 * kc + 1].y, e2[2 * kc + 1].z, e2[2 * kc + 1].w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float2 ob = OB[8 * kc + j];  // {input_mlp bias, project.1 bias}
+                ea[j] = fmaf(inv[j] + ob.x, ev[j], pr[j] + ob.y);
+            }
+            uint4 h, l;
+            split8(ea, h, l);
+            *reinterpret_cast<uint4*>(rec + REC_EA_HI + kc * 2048 + e * 16) = h;
+            *reinterpret_cast<uint4*>(rec + REC_EA_LO + kc * 2048 + e * 16) = l;
+        }
+        tc_fence_before();  // these TMEM reads are ordered before the next MMAs into the same columns by the FULL barrier
+    };
+
+    int tp = -1;                      // previous tile of this quad (its epilogue is pipelined into the current one)
+    uint32_t tcol_p = 0;
+    float psin_p = 0.f, pcos_p = 0.f;
+    uint32_t par = 0;
+    for (int t = q; t < c.ntiles; t += QUADS, par ^= 1u) {
         const TileInfo ti = tile_info(c, t);
         uint8_t* rec = scratch + static_cast<size_t>(t) * REC_BYTES;
         const bool live = e < ti.ne;
+        const uint32_t tcol = par * 64;   // accumulators of this tile: inv = [tcol, +32), hidden / proj = [tcol + 32, +32)
         float x[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, psin = 0.f, pcos = 0.f;
         if (live) {
             const int sj = rec[REC_SLOT + e], tg = rec[REC_SLOT + TE + e];
@@ -379,92 +487,39 @@ __device__ __noinline__ uint32_t phase_edge_features(const Chunk c, const float*
         }
         // Fourier block 0 (distance) feeds input_mlp (:409-410); blocks 1..4 (ci0, ci2, cj0, cj2) feed the fused hidden layer
         // of `project` (:427-430).
+        // (one rolled loop over the ten sub-blocks: the body is ~400 instructions and four warps per scheduler sit at different
+        //  places of it -- a fully unrolled copy does not fit the instruction caches)
+#pragma unroll 1
+        for (int b = 0; b < 10; ++b) {
+            const int blk = b >> 1, half = b & 1;
+            const float xb = blk == 0 ? x[0] : blk == 1 ? x[1] : blk == 2 ? x[2] : blk == 3 ? x[3] : x[4];
+            const float4* Wf = reinterpret_cast<const float4*>(W + (blk == 0 ? MOLSDE_P_GFP_DIST_W : MOLSDE_P_GFP_COFF_W) + half * 16);
+            float v[32];
 #pragma unroll
-        for (int blk = 0; blk < 5; ++blk) {
+            for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 w4 = Wf[i4];
+                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const float4* Wf = reinterpret_cast<const float4*>(W + (blk == 0 ? MOLSDE_P_GFP_DIST_W : MOLSDE_P_GFP_COFF_W) + half * 16);
-                float v[32];
-#pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                    const float4 w4 = Wf[i4];
-                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        // GaussianFourierProjection.forward, :64-66  (x * W * 2 * pi, fp32, in that order)
-                        const float arg = __fmul_rn(__fmul_rn(__fmul_rn(x[blk], wv[j]), 2.0f), 3.14159274101257324f);
-                        sincos_reduced(arg, v[4 * i4 + j], v[16 + 4 * i4 + j]);
-                    }
-                }
-                const uint32_t bar = half ? bar1 : bar0;
-                if (blk >= 1) mbar_wait(bar, qs, half ? QS_MMA1 : QS_MMA0, c.status_flag);  // MMAs of sub-block b-2 done: slot free
-                uint8_t* Ah = Aq + half * E0_SLOT;
-#pragma unroll
-                for (int kc = 0; kc < 4; ++kc) store_a_chunk(Ah, Ah + 8192, e, kc, v + 8 * kc);
-                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
-                tc_fence_before();
-                quad_sync(q);
-                if (e == 0) {
-                    tc_fence_after();
-                    const uint32_t ah = a_base + half * E0_SLOT, wb = w_bt + (2 * blk + half) * (MOLSDE_E0_BT_FLOATS * 4);
-                    umma_split_f16<32>(tq + (blk == 0 ? 0 : 32), ah, ah + 8192, wb, wb + 2048, 2, (blk <= 1 && half == 0) ? 0u : 1u);
-                    umma_commit(bar);
+                for (int j = 0; j < 4; ++j) {
+                    // GaussianFourierProjection.forward, :64-66  (x * W * 2 * pi, fp32, in that order)
+                    const float arg = __fmul_rn(__fmul_rn(__fmul_rn(xb, wv[j]), 2.0f), 3.14159274101257324f);
+                    sincos_reduced(arg, v[4 * i4 + j], v[16 + 4 * i4 + j]);
                 }
             }
+            ring_use(v, tq + tcol + (blk == 0 ? 0 : 32), w_bt + b * (MOLSDE_E0_BT_FLOATS * 4), (b == 0 || b == 2) ? 0u : 1u);
+            // pipelined epilogue of the quad's previous tile: the slot wait inside the ring use above has just proven that
+            //   after sub-block 1: every Fourier MMA of the previous tile is complete (its last commit was two uses ago)
+            //   after sub-block 3: its project.1 MMA (issued after sub-block 1) is complete
+            if (b == 1 && tp >= 0) epilogue1(tcol_p, psin_p, pcos_p);
+            if (b == 3 && tp >= 0) epilogue2(tp, tcol_p);
         }
-        mbar_wait(bar0, qs, QS_MMA0, c.status_flag);
-        mbar_wait(bar1, qs, QS_MMA1, c.status_flag);  // all Fourier MMAs of the tile are complete
-        tc_fence_after();
-        {
-            float hv[32];
-            tmem_ld32(tlane + 32, hv);
-            const float4* HV = reinterpret_cast<const float4*>(W + MOLSDE_P_E0_HV);
-#pragma unroll
-            for (int col = 0; col < 32; ++col) {
-                const float4 p = HV[col];  // {bias, w_sin, w_cos, 0}
-                hv[col] = silu_fast(hv[col] + p.x + psin * p.y + pcos * p.z);
-            }
-#pragma unroll
-            for (int kc = 0; kc < 4; ++kc) store_a_chunk(Aq, Aq + 8192, e, kc, hv + 8 * kc);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        quad_sync(q);
-        if (e == 0) {
-            tc_fence_after();
-            const uint32_t wb = w_bt + 10 * (MOLSDE_E0_BT_FLOATS * 4);
-            umma_split_f16<32>(tq + 64, a_base, a_base + 8192, wb, wb + 2048, 2, 0u);
-            umma_commit(bar0);
-        }
-        // edge_2D_emb tile of this edge (loop invariant, L2): [8 feature quads][128 slots][4]; in flight during project.1
-        float4 e2[8];
-        {
-            const float4* e2d_t = reinterpret_cast<const float4*>(e2d_tiles + static_cast<size_t>(c.tile0 + t) * E2D_TILE_FLOATS) + e;
-#pragma unroll
-            for (int fq = 0; fq < 8; ++fq) e2[fq] = __ldg(e2d_t + fq * TE);
-        }
-        mbar_wait(bar0, qs, QS_MMA0, c.status_flag);
-        tc_fence_after();
-        // ---- edge_attr = inv3d * e2d + frame  (:432) -> scratch record, as the fp16 hi/lo operand rows of the later phases ----
-        const float2* OB = reinterpret_cast<const float2*>(W + MOLSDE_P_E0_OB);
-#pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
-            float inv[8], pr[8], ea[8];
-            tmem_ld8(tlane + 8 * kc, inv);
-            tmem_ld8(tlane + 64 + 8 * kc, pr);
-            const float ev[8] = {e2[2 * kc].x, e2[2 * kc].y, e2[2 * kc].z, e2[2 * kc].w,
-                                 e2[2 * kc + 1].x, e2[2 * kc + 1].y, e2[2 * kc + 1].z, e2[2 * kc + 1].w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float2 ob = OB[8 * kc + j];  // {input_mlp bias, project.1 bias}
-                ea[j] = fmaf(inv[j] + ob.x, ev[j], pr[j] + ob.y);
-            }
-            uint4 h, l;
-            split8(ea, h, l);
-            *reinterpret_cast<uint4*>(rec + REC_EA_HI + kc * 2048 + e * 16) = h;
-            *reinterpret_cast<uint4*>(rec + REC_EA_LO + kc * 2048 + e * 16) = l;
-        }
-        tc_fence_before();  // TMEM reads of this tile are ordered before the next tile's MMAs by its first quad barrier
+        tp = t; tcol_p = tcol; psin_p = psin; pcos_p = pcos;
+    }
+    if (tp >= 0) {   // the quad's last tile: drain the ring, then both epilogue stages with their MMA latency exposed once
+        drain();
+        epilogue1(tcol_p, psin_p, pcos_p);
+        drain();
+        epilogue2(tp, tcol_p);
     }
     asm volatile("fence.proxy.async;" ::: "memory");  // the records are read back by TMA bulk copies (async proxy)
     __syncthreads();
@@ -502,13 +557,15 @@ __device__ __noinline__ void node_qkv(const Chunk c) {
 
 // attention over the incoming edges of every target: e = lin_edge(edge_attr) on the tensor core (A operand = the scratch record,
 // fetched by one TMA bulk copy), logits, segment softmax (+1e-16), weighted messages, deterministic ascending-source sum; the
-// aggregate overwrites q[target].  One quad per tile, thread = edge slot.
+// aggregate overwrites q[target].  One quad per tile, thread = edge slot; two quad barriers per tile: the edge threads publish
+// their logits and unweighted messages (v_j + e), then one thread per (target, head) runs max / exp / weighted sum over the
+// target's contiguous segment and normalises once:  sum_s ex_s m_s / (sum_s ex_s + 1e-16).
 __device__ __noinline__ uint32_t gat_edge_phase(const Chunk c, const uint8_t* __restrict__ scratch, int layer, uint32_t tmem_base,
                                                 uint32_t qs) {
     const int tid = threadIdx.x, q = tid >> 7, e = tid & (QT - 1);
     uint8_t* slot = smem_bytes(c) + SB_R + q * GAT_SLOT;
     float* Mm = reinterpret_cast<float*>(slot);          // [TE][32] messages (granules swizzled by the slot), over the consumed operand
-    float* L = reinterpret_cast<float*>(slot + 16384);   // [TE][8] logits -> attention weights
+    float* L = reinterpret_cast<float*>(slot + 16384);   // [TE][8] logits
     float* Q = smem_at<float>(c, SB_Q);
     const float* Kk = smem_at<const float>(c, SB_K);
     const float* V = smem_at<const float>(c, SB_V);
@@ -521,51 +578,56 @@ __device__ __noinline__ uint32_t gat_edge_phase(const Chunk c, const uint8_t* __
     for (int t = q; t < c.ntiles; t += QUADS) {
         const TileInfo ti = tile_info(c, t);
         const uint8_t* rec = scratch + static_cast<size_t>(t) * REC_BYTES;
-        if (e == 0) {
+        if (quad_leader(q, e)) {
             fence_proxy_async_smem();  // the slot was last touched through the generic proxy (message tile of the previous tile)
             mbar_expect_tx(bar_tma, 16384u);
             bulk_g2s(a_addr, rec + REC_EA_HI, 16384u, bar_tma);
         }
         const bool live = e < ti.ne;
         const int sj = live ? rec[REC_SLOT + e] : 0, tg = live ? rec[REC_SLOT + TE + e] : ti.ta;
-        if (e == 0) {
+        // q / k rows of this edge: in flight while the operand lands and the MMA runs
+        float4 q4[8], k4[8];
+        {
+            const float4* Q4 = reinterpret_cast<const float4*>(Q) + tg * 8;
+            const float4* K4 = reinterpret_cast<const float4*>(Kk) + sj * 8;
+            const int sq = tg & 7, sk = sj & 7;
+#pragma unroll
+            for (int hd = 0; hd < 8; ++hd) { q4[hd] = Q4[hd ^ sq]; k4[hd] = K4[hd ^ sk]; }
+        }
+        if (quad_leader(q, e)) {
             uint32_t qt = qs;  // (every thread flips its own copy below)
             mbar_wait(bar_tma, qt, QS_TMA, c.status_flag);
             qs |= (qt & QS_DEAD);
             tc_fence_after();
-            umma_split_f16<32>(tq, a_addr, a_addr + 8192, w_addr, w_addr + 2048, 2, 0u);
+            umma_split_f16<32, 2>(tq, a_addr, a_addr + 8192, w_addr, w_addr + 2048, 0u);
             umma_commit(bar_mma);
         }
         qs ^= QS_TMA;
         mbar_wait(bar_mma, qs, QS_MMA0, c.status_flag);
         tc_fence_after();
-        float ev[32], lg[8];
+        float ev[32];
         tmem_ld32(tlane, ev);
-        {
-            const float4* Q4 = reinterpret_cast<const float4*>(Q) + tg * 8;
-            const float4* K4 = reinterpret_cast<const float4*>(Kk) + sj * 8;
+        tc_fence_before();
+        if (live) {
             const float4* V4 = reinterpret_cast<const float4*>(V) + sj * 8;
-            const int sq = tg & 7, sk = sj & 7;
+            const int sk = sj & 7;
+            float lg[8];
 #pragma unroll
             for (int hd = 0; hd < 8; ++hd) {
-                const float4 q4 = Q4[hd ^ sq], k4 = K4[hd ^ sk], v4 = V4[hd ^ sk];
+                const float4 v4 = V4[hd ^ sk];
                 // alpha = (q_i . (k_j + e)) / sqrt(C)
-                float part = fmaf(q4.y, k4.y + ev[4 * hd + 1], q4.x * (k4.x + ev[4 * hd]));
-                part += fmaf(q4.w, k4.w + ev[4 * hd + 3], q4.z * (k4.z + ev[4 * hd + 2]));
+                float part = fmaf(q4[hd].y, k4[hd].y + ev[4 * hd + 1], q4[hd].x * (k4[hd].x + ev[4 * hd]));
+                part += fmaf(q4[hd].w, k4[hd].w + ev[4 * hd + 3], q4[hd].z * (k4[hd].z + ev[4 * hd + 2]));
                 lg[hd] = part * 0.5f;
-                ev[4 * hd] += v4.x;      // v_j + e
-                ev[4 * hd + 1] += v4.y;
-                ev[4 * hd + 2] += v4.z;
-                ev[4 * hd + 3] += v4.w;
+                // message before weighting: v_j + e  (the operand slot is free: its MMA completed)
+                *reinterpret_cast<float4*>(Mm + e * 32 + ((hd ^ (e & 7)) << 2)) =
+                    make_float4(ev[4 * hd] + v4.x, ev[4 * hd + 1] + v4.y, ev[4 * hd + 2] + v4.z, ev[4 * hd + 3] + v4.w);
             }
-        }
-        if (live) {
             *reinterpret_cast<float4*>(L + e * 8) = make_float4(lg[0], lg[1], lg[2], lg[3]);
             *reinterpret_cast<float4*>(L + e * 8 + 4) = make_float4(lg[4], lg[5], lg[6], lg[7]);
         }
-        tc_fence_before();
         quad_sync(q);
-        // per (target, head): softmax over the target's contiguous edge segment, normalised in place
+        // per (target, head): softmax over the target's contiguous edge segment fused with the weighted message sum
         const int ntg = ti.tb - ti.ta;
         for (int p = e; p < ntg * 8; p += QT) {
             const int i = ti.ta + (p >> 3), hd = p & 7;
@@ -573,40 +635,20 @@ __device__ __noinline__ uint32_t gat_edge_phase(const Chunk c, const uint8_t* __
             float m = -CUDART_INF_F;
             for (int s = s0; s < s1; ++s) m = fmaxf(m, L[s * 8 + hd]);
             float z = 0.0f;
-            for (int s = s0; s < s1; ++s) {
-                const float ex = __expf(L[s * 8 + hd] - m);
-                L[s * 8 + hd] = ex;
-                z += ex;
-            }
-            const float rz = __fdividef(1.0f, z + 1e-16f);
-            for (int s = s0; s < s1; ++s) L[s * 8 + hd] *= rz;
-        }
-        quad_sync(q);
-        if (live) {
-            const float4 a0 = *reinterpret_cast<const float4*>(L + e * 8), a1 = *reinterpret_cast<const float4*>(L + e * 8 + 4);
-            float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            if (c.attn_keep) {  // F.dropout(alpha, p) in train mode (TransformerConv.message)
-                const float* kp = c.attn_keep + (static_cast<size_t>(layer) * c.E_total + c.edge0 + ti.ea + e) * 8;
-#pragma unroll
-                for (int hd = 0; hd < 8; ++hd) al[hd] *= kp[hd] * c.inv_keep;
-            }
-#pragma unroll
-            for (int hd = 0; hd < 8; ++hd)
-                *reinterpret_cast<float4*>(Mm + e * 32 + ((hd ^ (e & 7)) << 2)) =
-                    make_float4(ev[4 * hd] * al[hd], ev[4 * hd + 1] * al[hd], ev[4 * hd + 2] * al[hd], ev[4 * hd + 3] * al[hd]);
-        }
-        quad_sync(q);
-        for (int p = e; p < ntg * 8; p += QT) {
-            const int i = ti.ta + (p >> 3), hd = p & 7;
-            const int s0 = rowl[i] - ti.ea, s1 = rowl[i + 1] - ti.ea;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* kp = c.attn_keep ? c.attn_keep + (static_cast<size_t>(layer) * c.E_total + c.edge0 + ti.ea) * 8 + hd : nullptr;
             for (int s = s0; s < s1; ++s) {
+                float ex = __expf(L[s * 8 + hd] - m);
+                z += ex;
+                if (kp) ex *= kp[s * 8];  // F.dropout(alpha, p) in train mode (TransformerConv.message): 0/1 keep mask, 1/(1-p) below
                 const float4 mv = *reinterpret_cast<const float4*>(Mm + s * 32 + ((hd ^ (s & 7)) << 2));
-                acc.x += mv.x; acc.y += mv.y; acc.z += mv.z; acc.w += mv.w;
+                acc.x = fmaf(ex, mv.x, acc.x); acc.y = fmaf(ex, mv.y, acc.y);
+                acc.z = fmaf(ex, mv.z, acc.z); acc.w = fmaf(ex, mv.w, acc.w);
             }
-            *reinterpret_cast<float4*>(Q + qkv_idx(i, 4 * hd)) = acc;
+            const float rz = __fdividef(c.inv_keep, z + 1e-16f);   // (inv_keep = 1 in eval mode)
+            *reinterpret_cast<float4*>(Q + qkv_idx(i, 4 * hd)) = make_float4(acc.x * rz, acc.y * rz, acc.z * rz, acc.w * rz);
         }
-        quad_sync(q);
+        quad_sync(q);  // the slot (messages) and the logits are rewritten by the next tile
     }
     return qs;
 }
@@ -749,26 +791,24 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
     const uint32_t bar_mma = bar_addr(c, 2 * q), bar_tma = bar_addr(c, 2 * QUADS + q);
     const uint32_t tq = tmem_base + q * 128;
     const uint32_t tlane = tq + (static_cast<uint32_t>(e & ~31) << 16);
+    const uint32_t bar_full = bar_addr(c, BAR_FULL0 + 2 * q);
     __syncthreads();
     stage_bulk2(c, smem_bytes(c) + SB_BW, blob + MOLSDE_P_BASIS0 + module * MOLSDE_P_BASIS_STRIDE, MOLSDE_P_BASIS_SZ, nullptr, nullptr, 0);
     const float4* EPI = reinterpret_cast<const float4*>(Wb + MOLSDE_B_EPI);
-    for (int t = q; t < c.ntiles; t += QUADS) {
+    // A operand of tile t: the edge_attr half (k-chunks 4..7 of the hi and the lo tile) by TMA from the scratch record, the node
+    // half h_row + h_col (:154-155, k-chunks 0..3) gathered and split by the edge's thread; every thread then ARRIVES on the
+    // quad's FULL barrier (nobody blocks here -- only the leader waits for it before issuing the MMAs)
+    auto produce = [&](int t) {
         const TileInfo ti = tile_info(c, t);
         const uint8_t* rec = scratch + static_cast<size_t>(t) * REC_BYTES;
-        if (e == 0) {   // edge_attr half of the A operand: k-chunks 4..7 of the hi and the lo tile
+        if (quad_leader(q, e)) {
+            fence_proxy_async_smem();
             mbar_expect_tx(bar_tma, 16384u);
             bulk_g2s(a_addr + 4 * 2048, rec + REC_EA_HI, 8192u, bar_tma);
             bulk_g2s(a_addr + 16384 + 4 * 2048, rec + REC_EA_LO, 8192u, bar_tma);
         }
         const bool live = e < ti.ne;
         const int sj = live ? rec[REC_SLOT + e] : 0, tg = live ? rec[REC_SLOT + TE + e] : 0;
-        float F[9];
-        {
-            const float* fr = reinterpret_cast<const float*>(rec + REC_FRAME) + e;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) F[i] = live ? fr[i * TE] : 0.0f;
-        }
-        // node half: h_row + h_col (:154-155), k-chunks 0..3
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
             float v[8];
@@ -777,19 +817,33 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
             store_a_chunk(Ah, Al, e, kc, v);
         }
         fence_proxy_async_smem();
-        tc_fence_before();
-        quad_sync(q);
-        if (e == 0) {
-            uint32_t qt = qs;
+        mbar_arrive(bar_full);
+    };
+    if (q < c.ntiles) produce(q);
+    for (int t = q; t < c.ntiles; t += QUADS) {
+        const TileInfo ti = tile_info(c, t);
+        const uint8_t* rec = scratch + static_cast<size_t>(t) * REC_BYTES;
+        const bool live = e < ti.ne;
+        if (quad_leader(q, e)) {
+            uint32_t qt = qs;   // (every thread flips its own copy of the two parities below)
+            mbar_wait(bar_full, qt, QS_FULL0, c.status_flag);
             mbar_wait(bar_tma, qt, QS_TMA, c.status_flag);
             qs |= (qt & QS_DEAD);
             tc_fence_after();
-            umma_split_f16<128>(tq, a_addr, a_addr + 16384, w_addr + MOLSDE_B_W1_HI * 4, w_addr + MOLSDE_B_W1_LO * 4, 4, 0u);
+            umma_split_f16<128, 4>(tq, a_addr, a_addr + 16384, w_addr + MOLSDE_B_W1_HI * 4, w_addr + MOLSDE_B_W1_LO * 4, 0u);
             umma_commit(bar_mma);
         }
-        qs ^= QS_TMA;
+        qs ^= (QS_TMA | QS_FULL0);
+        float F[9];
+        {
+            const float* fr = reinterpret_cast<const float*>(rec + REC_FRAME) + e;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) F[i] = live ? fr[i * TE] : 0.0f;
+        }
         mbar_wait(bar_mma, qs, QS_MMA0, c.status_flag);
         tc_fence_after();
+        // the operand slot is free again: stage the quad's next tile now, its TMA and gathers overlap the epilogue below
+        if (t + QUADS < c.ntiles) produce(t + QUADS);
         float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
 #pragma unroll 1
         for (int cb = 0; cb < 4; ++cb) {
@@ -822,8 +876,7 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
             sacc = __fdiv_rn(sacc, static_cast<float>(max(s1 - s0, 1)));  // aggr='mean'
             grad[i * 3 + ax] = (module == 0) ? sacc : grad[i * 3 + ax] + sacc;
         }
-        // (no trailing barrier: the next tile writes `mix` only after its own quad barrier, which every thread reaches after
-        //  this loop; the operand slot was released by the MMA completion waited for above)
+        quad_sync(q);  // `mix` is rewritten by the next tile; its TMEM loads are ordered before the next MMA issue
     }
     __syncthreads();
     return qs;
@@ -869,7 +922,8 @@ __device__ __noinline__ uint32_t score_eval(const Chunk c, const float* __restri
 // TMEM accumulators (128 columns per quad) + mbarriers; call with all threads of the CTA
 __device__ __forceinline__ uint32_t tmem_setup(const Chunk& c) {
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NUM_BARS; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr(c, i)));
+        for (int i = 0; i < NUM_BARS; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_addr(c, i)), "r"(i >= BAR_FULL0 ? QT : 1));
         c.si[SI_MISC + 2] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }

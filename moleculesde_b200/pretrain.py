@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import re
-from typing import Dict, Optional
+from typing import Dict, Optional, Sequence
 
 import torch
 from torch import nn
@@ -120,16 +120,20 @@ class ParamStore:
         return 1.0
 
     def adam_step(self, lr: float = 1e-4, lr_scale: Optional[Dict[str, float]] = None, betas=(0.9, 0.999), eps: float = 1e-8,
-                  weight_decay: float = 0.0, grad_scale: float = 1.0) -> None:
+                  weight_decay: float = 0.0, grad_scale: float = 1.0, skip: Sequence[str] = ()) -> None:
         """torch.optim.Adam over the four parameter groups (`pretrain_MoleculeSDE.py:331-337`); groups with the same lr
-        share one launch."""
+        share one launch.  `skip`: modules that received no gradient this run (a loss term with coefficient 0 is never evaluated,
+        `pretrain_MoleculeSDE.py:136-153`, so their `.grad` stays None and torch's Adam leaves them untouched -- no weight
+        decay, no moment update)."""
         self.step_count += 1
         s = torch.cuda.current_stream(self.dev).cuda_stream
-        scales = {m: (lr_scale or {}).get(m, 1.0) for m in self.modules}
-        if len(set(scales.values())) == 1:
+        scales = {m: (lr_scale or {}).get(m, 1.0) for m in self.modules if m not in skip}
+        if not scales:
+            return
+        if len(set(scales.values())) == 1 and not skip:
             spans = [(0, self.numel, lr * next(iter(scales.values())))]
         else:
-            spans = [(a, b, lr * scales[m]) for m, (a, b) in self.ranges.items() if b > a]
+            spans = [(a, b, lr * scales[m]) for m, (a, b) in self.ranges.items() if b > a and m in scales]
         for a, b, l in spans:
             check(lib().molsde_adam_step(self.flat[a:b].data_ptr(), self.grad[a:b].data_ptr(), self.exp_avg[a:b].data_ptr(),
                                          self.exp_avg_sq[a:b].data_ptr(), b - a, l, betas[0], betas[1], eps, weight_decay,
@@ -972,7 +976,8 @@ class PretrainStep:
     def step(self, batch, draws: Optional[dict] = None) -> Dict[str, torch.Tensor]:
         out = self.forward_backward(batch, draws)
         scale = self.store.all_reduce()
-        self.store.adam_step(self.lr, self.lr_scale, weight_decay=self.weight_decay, grad_scale=scale)
+        skip = [m for m, c in (("sde2d3d", self.c_23), ("sde3d2d", self.c_32)) if not c > 0]
+        self.store.adam_step(self.lr, self.lr_scale, weight_decay=self.weight_decay, grad_scale=scale, skip=skip)
         return out
 
     @staticmethod

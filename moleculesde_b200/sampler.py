@@ -110,8 +110,8 @@ def position_PC_generation(representation, data, pos_init, scorenet, sde, probab
         noise_corr = noise_corr.float().contiguous()
         noise_pred = noise_pred.float().contiguous()
         assert tuple(noise_corr.shape) == (steps, n_atoms, 3) and tuple(noise_pred.shape) == (steps, n_atoms, 3)
-    pos_out = torch.empty_like(pos0)
-    pos_mean = torch.empty_like(pos0)
+    pos_out = torch.full_like(pos0, float("nan"))   # a skipped chunk stays NaN
+    pos_mean = torch.full_like(pos0, float("nan"))
     scratch = prep.get_scratch()
     st = prep.plan.as_struct()
     prm = _abi.Params(pk["blob"].data_ptr(), pk["blob"].numel())
@@ -121,4 +121,11 @@ def position_PC_generation(representation, data, pos_init, scorenet, sde, probab
                                          ctypes.byref(cfg), ptr(noise_corr), ptr(noise_pred), ptr(pos_out), ptr(pos_mean),
                                          ptr(scratch), scratch.numel(), ptr(prep.counter), ptr(prep.status),
                                          stream_ptr(pos0)), "sde2d3d_pc_sample")
+    # device status word (one sync; the reference's driver copies the positions to the host right after this call anyway):
+    # > 0 = chunk (1 + index) exceeded a compiled limit and was skipped, -7 = a tensor-core / TMA completion wait timed out
+    status = int(prep.status.item())
+    if status != 0:
+        raise _abi.MolsdeError(f"sde2d3d_pc_sample: device status {status} "
+                               f"({'chunk %d beyond the compiled limits' % (status - 1) if status > 0 else 'completion wait timed out'}); "
+                               "the returned positions would be undefined")
     return (data, pos_mean) if denoise else (data, pos_out)

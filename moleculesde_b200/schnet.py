@@ -71,6 +71,25 @@ class InteractionBlock(nn.Module):
         self.lin.bias.data.fill_(0)
 
 
+# Standard atomic masses (IUPAC 2016, index = atomic number, entry 0 = the dummy element 'X'), the values `ase.data.atomic_masses`
+# holds: the reference registers them as the float64 buffer `atomic_mass` (schnet.py:47-48) and reads them for the dipole
+# readout's centre of mass (:105-107).  Embedded so that a checkpoint written here carries the real table into the reference class.
+_ATOMIC_MASSES = (
+    1.0, 1.008, 4.002602, 6.94, 9.0121831, 10.81, 12.011, 14.007, 15.999, 18.998403163, 20.1797,
+    22.98976928, 24.305, 26.9815385, 28.085, 30.973761998, 32.06, 35.45, 39.948, 39.0983, 40.078,
+    44.955908, 47.867, 50.9415, 51.9961, 54.938044, 55.845, 58.933194, 58.6934, 63.546, 65.38,
+    69.723, 72.630, 74.921595, 78.971, 79.904, 83.798, 85.4678, 87.62, 88.90584, 91.224,
+    92.90637, 95.95, 97.90721, 101.07, 102.90550, 106.42, 107.8682, 112.414, 114.818, 118.710,
+    121.760, 127.60, 126.90447, 131.293, 132.90545196, 137.327, 138.90547, 140.116, 140.90766, 144.242,
+    144.91276, 150.36, 151.964, 157.25, 158.92535, 162.500, 164.93033, 167.259, 168.93422, 173.054,
+    174.9668, 178.49, 180.94788, 183.84, 186.207, 190.23, 192.217, 195.084, 196.966569, 200.592,
+    204.38, 207.2, 208.98040, 208.98243, 209.98715, 222.01758, 223.01974, 226.02541, 227.02775, 232.0377,
+    231.03588, 238.02891, 237.04817, 244.06421, 243.06138, 247.07035, 247.07031, 251.07959, 252.0830, 257.09511,
+    258.09843, 259.1010, 262.110, 267.122, 268.126, 271.134, 270.133, 269.1338, 278.156, 281.165,
+    281.166, 285.177, 286.182, 289.190, 289.194, 293.204, 293.208, 294.214)
+assert len(_ATOMIC_MASSES) == 119
+
+
 class SchNet(nn.Module):
     def __init__(self, hidden_channels=128, num_filters=128, num_interactions=6, num_gaussians=50, cutoff=10.0,
                  node_class=None, readout="mean", dipole=False, mean=None, std=None, atomref=None):
@@ -83,8 +102,8 @@ class SchNet(nn.Module):
         self.hidden_channels, self.num_filters = hidden_channels, num_filters
         self.num_interactions, self.num_gaussians, self.cutoff = num_interactions, num_gaussians, cutoff
         self.readout, self.dipole, self.mean, self.std, self.scale = readout, dipole, mean, std, None
-        # `ase.data.atomic_masses` in the reference (schnet.py:47-48); only read when dipole=True. Kept for key parity.
-        self.register_buffer("atomic_mass", torch.zeros(119, dtype=torch.float64))
+        # `ase.data.atomic_masses` in the reference (schnet.py:47-48); only read when dipole=True (not built here); kept with the real values for checkpoint parity.
+        self.register_buffer("atomic_mass", torch.tensor(_ATOMIC_MASSES, dtype=torch.float64))
         self.embedding = nn.Embedding(node_class, hidden_channels)
         self.distance_expansion = GaussianSmearing(0.0, cutoff, num_gaussians)
         self.interactions = nn.ModuleList(InteractionBlock(hidden_channels, num_gaussians, num_filters, cutoff)

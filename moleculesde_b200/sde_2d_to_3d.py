@@ -447,7 +447,7 @@ class SDEModel2Dto3D_02(nn.Module):
         else:
             nattr, e2d = self.invariants(node_2D_repr, prep)
             blob = self.packed_params()["blob"]
-        grad = torch.empty_like(pos)
+        grad = torch.full_like(pos, float("nan"))   # a chunk the kernel had to skip (status word) stays NaN -> non-finite loss
         scratch = prep.get_scratch()
         st = prep.plan.as_struct()
         prm = _abi.Params(blob.data_ptr(), blob.numel())
@@ -472,7 +472,7 @@ class SDEModel2Dto3D_02(nn.Module):
         pos = pos_perturbed.detach().float().contiguous()
         _, std = self.sde_pos.marGINal_prob(pos, t_pos)
         std = std.float().contiguous()
-        score = torch.empty_like(pos)
+        score = torch.full_like(pos, float("nan"))  # a chunk the kernel had to skip (status word) stays NaN
         scratch = prep.get_scratch()
         st = prep.plan.as_struct()
         prm = _abi.Params(pk["blob"].data_ptr(), pk["blob"].numel())

@@ -5,7 +5,10 @@ with every random draw recorded.  Stored: the draws, the losses, both representa
 every parameter the gradient's norm, sum and a strided sample (full tensor when <= 512 elements), plus the same
 sample of the parameter after one Adam step (lr 1e-4).
 
-Run in the build container only (needs /root/reference):  python tests/golden/make_golden_grads.py
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden_grads.py                 # golden_grads.pt   (8 molecules, VE + VP, full representations)
+    python tests/golden/make_golden_grads.py --b32           # golden_grads_b32.pt: BASELINE.json configs[0] -- batch 32, VE/VE,
+                                                             # data seed 32; representations stored as summaries only
 """
 import os
 import sys
@@ -31,16 +34,17 @@ def summarize(t, n=SAMPLE):
             "sample": f[::stride][:n].clone(), "numel": f.numel()}
 
 
-def main():
+def main(num_mols=NUM_MOLS, data_seed=DATA_SEED, kinds=("VE", "VP"), out_name="golden_grads.pt", full_repr=True):
     R = refload.load()
     torch.set_num_threads(1)
-    mols = synth_molecules(NUM_MOLS, DATA_SEED)
+    mols = synth_molecules(num_mols, data_seed)
     for m in mols:
         R.extend_graph(m)
     batch = Batch.from_data_list(mols)
-    out = {"meta": {"num_mols": NUM_MOLS, "data_seed": DATA_SEED, "weight_seed": WEIGHT_SEED, "noise_seed": NOISE_SEED + 20,
-                    "lr": 1e-4, "torch": str(torch.__version__)}}
-    for sde_type in ("VE", "VP"):
+    out = {"meta": {"num_mols": num_mols, "data_seed": data_seed, "weight_seed": WEIGHT_SEED, "noise_seed": NOISE_SEED + 20,
+                    "lr": 1e-4, "torch": str(torch.__version__), "num_atoms": int(batch.positions.size(0)),
+                    "num_ext_edges": int(batch.extended_edge_index.size(1))}}
+    for sde_type in kinds:
         gnn, sch, m23, m32 = build_reference_models(R, sde_type)
         models = {"gnn": gnn, "schnet": sch, "sde2d3d": m23, "sde3d2d": m32}
         for m in models.values():
@@ -59,8 +63,9 @@ def main():
             loss = cl_loss + l23 + (lx + la) * 0.5
         opt.zero_grad()
         loss.backward()
-        sec = {"draws": [(k, v) for k, v in log], "h2d": h2d.detach().clone(), "h3d": h3d.detach().clone(),
-               "d_h2d": h2d.grad.clone(), "d_h3d": h3d.grad.clone(),
+        keep = (lambda t: t.detach().clone()) if full_repr else summarize
+        sec = {"draws": [(k, v) for k, v in log], "h2d": keep(h2d), "h3d": keep(h3d),
+               "d_h2d": keep(h2d.grad), "d_h3d": keep(h3d.grad),
                "loss": loss.detach(), "cl_loss": cl_loss.detach(), "cl_acc": torch.tensor(cl_acc), "loss_2d3d": l23.detach(),
                "loss_x": lx.detach(), "loss_adj": la.detach(), "grads": {}, "after_step": {}, "buffers": {}}
         for name, m in models.items():
@@ -73,10 +78,13 @@ def main():
         out["pretrain_" + sde_type] = sec
         print(sde_type, "loss", float(loss), "cl", float(cl_loss), "2d3d", float(l23), "x", float(lx), "adj", float(la),
               "draws", [k for k, _ in log])
-    path = os.path.join(HERE, "golden_grads.pt")
+    path = os.path.join(HERE, out_name)
     torch.save(out, path)
     print("wrote", path, os.path.getsize(path) / 1e6, "MB")
 
 
 if __name__ == "__main__":
-    main()
+    if "--b32" in sys.argv:
+        main(num_mols=32, data_seed=32, kinds=("VE",), out_name="golden_grads_b32.pt", full_repr=False)
+    else:
+        main()

@@ -11,6 +11,14 @@ pytestmark = pytest.mark.gpu
 from conftest import sd_from_manifest  # noqa: E402
 
 REL_TOL = 1e-4
+# Measured on a B200 (gpurun_out/grad_parity_errors.txt, 1044 gradient tensors): every tensor of the 8-molecule fixture is within
+# 5.6e-5 (sample, max-norm relative) / 5.4e-5 (norm, sum); at batch 32 all but 7 are within 1e-4.  The 7 are two documented families:
+#  (a) CANCELLATION-DOMINATED tensors -- gradient norm below 1e-3 of the largest gradient norm of their module (the q/k biases of one
+#      nearly saturated tanh-attention channel of the dense edge network, 1.5e-4 of the module scale; GINConv.eps, a scalar dot
+#      product of ~1e5 cancelling terms): measured <= 2.3e-4, allowed 3e-4 (eps: 1e-3 as before);
+#  (b) the GIN chain (gnn.* and d loss / d h2d): ReLU units sitting at ~0 behind a BatchNorm take the other branch under a
+#      different fp32 summation order and move single entries: measured <= 1.6e-4, allowed 2e-4.
+SMALL_GRAD = 1e-3
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -25,8 +33,16 @@ def _dev():
     return torch.device("cuda:0")
 
 
-def check_grad_summary(got: torch.Tensor, want: dict, what: str, scale_floor: float = 0.0, tol: float = REL_TOL):
-    """Compare a gradient tensor with its fixture summary (norm, sum, strided sample)."""
+ERR_LOG = {}   # what -> (sample error, norm error, sum error), max-norm relative; dumped by test_zz_error_report
+
+
+def check_grad_summary(got: torch.Tensor, want: dict, what: str, scale_floor: float = 0.0, tol: float = REL_TOL,
+                       sample_tol: float = None):
+    """Compare a gradient tensor with its fixture summary (norm, sum, strided sample).
+      sample: max |got - ref| over the strided sample, relative to the tensor's scale max(rms, max |ref|)  (max-norm relative);
+      norm:   | ||got|| - ||ref|| | / ||ref||;
+      sum:    | sum(got) - sum(ref) | relative to ||ref||_2 * sqrt(numel) (>= the L1 norm: the scale of a sum's rounding error)."""
+    sample_tol = tol if sample_tol is None else sample_tol
     f = got.detach().reshape(-1).float().cpu()
     assert f.numel() == want["numel"], what
     assert torch.isfinite(f).all(), f"{what}: non-finite"
@@ -34,9 +50,12 @@ def check_grad_summary(got: torch.Tensor, want: dict, what: str, scale_floor: fl
     smp = f[::want["stride"]][:ref.numel()]
     scale = max(float(want["norm"]) / max(f.numel(), 1) ** 0.5, float(ref.abs().max()), scale_floor, 1e-30)
     err = float((smp - ref).abs().max()) / scale
-    assert err <= tol * 10, f"{what}: sample error {err:.3e} (relative to {scale:.3e})"
     nerr = abs(float(f.double().norm()) - float(want["norm"])) / max(float(want["norm"]), scale_floor, 1e-30)
+    serr = abs(float(f.double().sum()) - float(want["sum"])) / max(float(want["norm"]) * max(f.numel(), 1) ** 0.5, scale_floor, 1e-30)
+    ERR_LOG[what] = (err, nerr, serr)
+    assert err <= sample_tol, f"{what}: sample error {err:.3e} (relative to {scale:.3e})"
     assert nerr <= tol, f"{what}: norm {float(f.double().norm()):.6e} vs {float(want['norm']):.6e} ({nerr:.3e})"
+    assert serr <= tol, f"{what}: sum {float(f.double().sum()):.6e} vs {float(want['sum']):.6e} ({serr:.3e})"
 
 
 def _draws_2d3d(sec):
@@ -91,7 +110,7 @@ def test_2d3d_loss_and_grads(kind, gg, golden, golden_batch):
         check_grad_summary(got, want, n)
 
 
-def _check_module_grads(store, mname, sec, skip_zero=()):
+def _check_module_grads(store, mname, sec, skip_zero=(), sample_tol=None, tag=""):
     bad = []
     gmax = max(float(w["norm"]) for w in sec["grads"][mname].values() if w is not None)
     for name, want in sec["grads"][mname].items():
@@ -104,7 +123,9 @@ def _check_module_grads(store, mname, sec, skip_zero=()):
         try:
             # GINConv.eps is a scalar whose gradient <d pre, x> is a heavily cancelling dot product of ~3e4 terms:
             # its relative error is the summands' 1e-6 times the cancellation factor
-            check_grad_summary(got, want, f"{mname}.{name}", tol=REL_TOL * (10 if name.endswith(".eps") else 1))
+            t = REL_TOL * (10 if name.endswith(".eps") else 3 if float(want["norm"]) < SMALL_GRAD * gmax else 1)
+            st = max(t, sample_tol or 0.0)
+            check_grad_summary(got, want, f"{tag}{mname}.{name}", tol=t, sample_tol=st)
         except AssertionError as e:
             bad.append(str(e))
     assert not bad, "\n".join(bad)
@@ -280,6 +301,57 @@ def test_full_pretrain_step(kind, gg, golden, golden_batch):
     assert n_bad <= 0.01 * n_all, (n_bad, n_all)
 
 
+def test_full_pretrain_step_b32(golden):
+    """BASELINE.json configs[0]: ONE pretrain_MoleculeSDE step at batch 32 (VE / VE, extended graph) against the unmodified
+    reference run on the same molecules with recorded draws (`tests/golden/golden_grads_b32.pt`, made by
+    `make_golden_grads.py --b32`): the four losses, both representations and d loss / d representation (summaries), every
+    parameter gradient (norm, sum, strided sample) and the BatchNorm running statistics."""
+    from moleculesde_b200.data import Batch, synth_molecules
+    from moleculesde_b200.pretrain import PretrainStep
+    from moleculesde_b200.sde_2d_to_3d import SDEModel2Dto3D_02
+    from moleculesde_b200.sde_3d_to_2d import SDEModel3Dto2D_node_adj_dense
+    from oracle.ref_ops import extend_graph_index
+    from test_gpu_sde2d3d import _gpu_batch
+    dev = _dev()
+    g32 = torch.load(os.path.join(HERE, "golden", "golden_grads_b32.pt"))
+    sec, meta = g32["pretrain_VE"], g32["meta"]
+    assert meta["num_mols"] == 32
+    mols = synth_molecules(meta["num_mols"], meta["data_seed"])
+    for m in mols:
+        m.extended_edge_index = extend_graph_index(m.edge_index, m.num_nodes)
+    batch = Batch.from_data_list(mols)
+    assert batch.positions.size(0) == meta["num_atoms"] and batch.extended_edge_index.size(1) == meta["num_ext_edges"]
+    gnn, sch = _encoders(golden, dev)
+    m23 = SDEModel2Dto3D_02(emb_dim=300, hidden_dim=32, beta_schedule=None, beta_min=0.2, beta_max=1.0,
+                            num_diffusion_timesteps=1000, SDE_type="VE", use_extend_graph=True)
+    m23.load_state_dict(sd_from_manifest(golden["manifest"]["sde2d3d"], meta["weight_seed"]))
+    m32 = SDEModel3Dto2D_node_adj_dense(
+        dim3D=300, c_init=2, c_hid=8, c_final=4, num_heads=4, adim=16, nhid=16, num_layers=4, emb_dim=300, num_linears=3,
+        beta_min=0.1, beta_max=1.0, num_diffusion_timesteps=1000, SDE_type="VE", num_class_X=119, noise_on_one_hot=True)
+    m32.load_state_dict(sd_from_manifest(golden["manifest"]["sde3d2d"], meta["weight_seed"]))
+    ps = PretrainStep(gnn, sch, m23, m32, dev, lr=1e-4, T=0.1)
+    b = _gpu_batch(batch, dev)
+    d = sec["draws"]
+    draws = {"cl": (d[0][1], d[1][1]), "sde2d3d": _draws_2d3d(sec), "sde3d2d": [v for _, v in d[12:15]]}
+    out = ps.forward_backward(b, draws)
+    torch.cuda.synchronize()
+    for key in ("cl_loss", "loss_2d3d", "loss_x", "loss_adj"):
+        assert abs(float(out[key]) - float(sec[key])) <= REL_TOL * abs(float(sec[key])), (key, float(out[key]), float(sec[key]))
+    assert abs(PretrainStep.total_loss(out) - float(sec["loss"])) <= REL_TOL * abs(float(sec["loss"]))
+    check_grad_summary(out["h2d"].data, sec["h2d"], "b32.h2d", sample_tol=REL_TOL)
+    check_grad_summary(out["h3d"].data, sec["h3d"], "b32.h3d", sample_tol=REL_TOL)
+    check_grad_summary(out["h2d"].grad, sec["d_h2d"], "b32.d_h2d", sample_tol=2 * REL_TOL)   # family (b)
+    check_grad_summary(out["h3d"].grad, sec["d_h3d"], "b32.d_h3d")
+    _check_module_grads(ps.store, "gnn", sec, skip_zero=("mlp.0.bias", "mlp.3.bias"), sample_tol=2 * REL_TOL, tag="b32.")   # (b)
+    _check_module_grads(ps.store, "schnet", sec, tag="b32.")
+    _check_module_grads(ps.store, "sde3d2d", sec, tag="b32.")
+    _check_module_grads(ps.store, "sde2d3d", sec, skip_zero=("edge_2D_emb.0.bias", "lin_key.bias"), tag="b32.")
+    for mname, m in (("gnn", gnn), ("sde2d3d", m23)):
+        bufs = dict(m.named_buffers())
+        for n, want in sec["buffers"][mname].items():
+            check_grad_summary(bufs[n], want, f"b32.{mname}.{n}", sample_tol=REL_TOL)
+
+
 @pytest.mark.parametrize("num_mols,seed", [(1, 3), (3, 4), (17, 5)])
 def test_pretrain_step_small_and_odd_batches(num_mols, seed, golden):
     """Batch sizes the antithetic time sampling treats specially (B = 1, odd B): losses vs the oracle with the same draws,
@@ -374,3 +446,19 @@ def test_reference_training_loop_through_autograd(gg, golden, golden_batch):
     _check_module_grads(_S(), "sde3d2d", sec)
     optimizer.step()
     assert all(torch.isfinite(p).all() for m in mods.values() for p in m.parameters())
+
+
+def test_zz_error_report():
+    """Not a check: writes the achieved max-norm relative errors of every gradient comparison of this module (sample / norm / sum)
+    to gpurun_out/ so that the tolerances above can be read against measurements."""
+    if not ERR_LOG:
+        pytest.skip("no gradient comparison ran")
+    out_dir = os.path.join(os.path.dirname(HERE), "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    rows = sorted(ERR_LOG.items(), key=lambda kv: -kv[1][0])
+    with open(os.path.join(out_dir, "grad_parity_errors.txt"), "w") as f:
+        f.write("# what  sample_err  norm_err  sum_err   (max-norm relative, see check_grad_summary)\n")
+        for k, (a, b_, c) in rows:
+            f.write(f"{k:70s} {a:.3e} {b_:.3e} {c:.3e}\n")
+        worst = [max(v[i] for v in ERR_LOG.values()) for i in range(3)]
+        f.write(f"# worst: sample {worst[0]:.3e} norm {worst[1]:.3e} sum {worst[2]:.3e} over {len(rows)} tensors\n")

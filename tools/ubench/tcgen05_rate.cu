@@ -72,6 +72,7 @@ void run(const char* name, int kdim) {
 }
 int main() {
     run<64, 0>("tf32", 8); run<128, 0>("tf32", 8); run<256, 0>("tf32", 8);
+    run<16, 1>("bf16", 16); run<32, 1>("bf16", 16);
     run<64, 1>("bf16", 16); run<128, 1>("bf16", 16); run<256, 1>("bf16", 16);
     return 0;
 }
