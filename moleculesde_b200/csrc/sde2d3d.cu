@@ -23,14 +23,14 @@
 //     (canonical K-major core-matrix layout) into an L2-resident per-CTA scratch record; the four GAT layers and the two
 //     basis modules fetch it with one TMA bulk copy per tile (cp.async.bulk + mbarrier complete_tx) straight into the
 //     operand slot -- no thread touches it again;
-//   * the per-node GEMMs (q|k|v, lin_skip, FFN: <= 224 rows) stay on warp-level mma.sync m16n8k16 with the same split.
+//   * the per-node GEMMs run the same way with THREAD = NODE (<= 224 nodes = two M = 128 tiles on quads 0 and 1): one N = 128
+//     GEMM gives q | k | v | lin_skip (the skip part stays in TMEM through the edge phase), FFN.0 / FFN.3 follow as N = 32
+//     GEMMs; both LayerNorms and the residuals are thread-local on the accumulator row.  No legacy mma.sync is left.
 #include <math_constants.h>
 
 #include "common.cuh"
-#include "mma_tile.cuh"
+#include "mma_tile.cuh"   // split_f16x2
 #include "sde2d3d_params.h"
-
-#define MOLSDE_MMA_GEMM mma_gemm_hp
 
 namespace molsde {
 
@@ -41,8 +41,6 @@ constexpr int QUADS = 4;                      // four 128-thread quads, one edge
 constexpr int QT = NTHREADS / QUADS;
 constexpr int MAXN = MOLSDE_CHUNK_MAX_NODES;  // 224 atoms per chunk
 constexpr int MAXT = 64;                      // tiles per chunk
-constexpr int LDX = 232;                      // leading dim of the k-major node matrix (>= MAXN, == 8 mod 32)
-constexpr int LD32 = MOLSDE_LD32, LD96 = MOLSDE_LD96;
 constexpr int E2D_TILE_FLOATS = 32 * TE;      // edge_2D_emb output tile [8 feature quads][128 slots][4]
 constexpr float EPS = 1e-6f;                  // SDE_model_2D_to_3D.py:10
 constexpr float LN_EPS = 1e-5f;
@@ -58,14 +56,16 @@ constexpr int REC_FLOATS = REC_BYTES / 4;
 static_assert(REC_BYTES % 128 == 0 && MAXN <= 255, "record alignment / byte-sized node indices");
 
 // ---- shared memory carve-up (byte offsets) ----
-constexpr int SB_XT = 0;                                // f32 [32][LDX] node hidden, k-major
-constexpr int SB_BIG = SB_XT + 32 * LDX * 4;            // phase-dependent union
+constexpr int SB_XT = 0;                                // f32 [MAXN][32] node hidden, node-major rows, 16-byte granules XOR-swizzled
+constexpr int SB_BIG = SB_XT + MAXN * 32 * 4;           // phase-dependent union
 //   GAT layers
 constexpr int SB_Q = SB_BIG;                            // f32 [MAXN][32] query (aggregate written in place), rows XOR-swizzled
 constexpr int SB_K = SB_Q + MAXN * 32 * 4;
 constexpr int SB_V = SB_K + MAXN * 32 * 4;
 constexpr int SB_WP = SB_V + MAXN * 32 * 4;             // resident weights of the current GAT layer [G_WP_SZ floats]
-constexpr int SB_R = SB_WP + MOLSDE_G_WP_SZ * 4;        // q|k|v weights / per-quad edge-phase slots / FFN staging
+constexpr int SB_R = SB_WP + MOLSDE_G_WP_SZ * 4;        // node phases: A operand of the two node tiles + q|k|v|skip weights; edge phase: per-quad slots
+constexpr int NODE_A = 16384;                           // per node tile (quad 0 / 1): [128 nodes][32 k] fp16 hi (8 KB) | lo (8 KB)
+constexpr int SB_WQ = SB_R + 2 * NODE_A;                // q|k|v|skip B tile [128 n][32 k] hi | lo (16 KB), dead once the edge phase starts
 constexpr int GAT_SLOT = 16384 + 4096;                  // per quad: A operand hi|lo (later the message tile [128][32] f32) + logits [128][8]
 constexpr int SB_BIG_END = SB_R + QUADS * GAT_SLOT;
 //   feature phase (E0)
@@ -96,7 +96,7 @@ static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of
 static_assert(SB_BIG % 128 == 0 && SB_WP % 128 == 0 && SB_R % 128 == 0 && SB_E0A % 128 == 0 && SB_BA % 128 == 0 && SB_BAR % 8 == 0,
               "operand tiles / barriers alignment");
 static_assert(SB_E0A + QUADS * 2 * E0_SLOT <= SB_BIG_END && SB_MIX + QUADS * 3 * TE * 4 <= SB_BIG_END, "phase unions fit");
-static_assert(QUADS * GAT_SLOT >= 32 * LDX * 4 && QUADS * GAT_SLOT >= (MOLSDE_P_GAT_SZ - MOLSDE_G_WQKV) * 4, "R region uses");
+static_assert(QUADS * GAT_SLOT >= 2 * NODE_A + (MOLSDE_P_GAT_SZ - MOLSDE_G_WQKVS) * 4 && MAXN <= 2 * QT, "R region uses / two node tiles");
 static_assert((MOLSDE_G_WEC * 4) % 128 == 0 && (MOLSDE_P_E0_BT * 4) % 128 == 0, "B tiles are 128B aligned inside their sections");
 constexpr uint32_t TMEM_COLS = 512;  // 128 accumulator columns per quad
 
@@ -529,30 +529,78 @@ __device__ __noinline__ uint32_t phase_edge_features(const Chunk c, const float*
 // ---------------------------------------------------------------------------------------
 // GAT layer pieces  (equivariant_scorenetwork.py:34-40, TransformerConv heads=8 C=4)
 // ---------------------------------------------------------------------------------------
-// q|k|v = Linear(x): each warp owns 16 nodes and all 96 output columns (mma.sync; weights staged in the R region)
-__device__ __noinline__ void node_qkv(const Chunk c) {
-    float* sm = c.sm;
-    const float* Wqkv = smem_at<const float>(c, SB_R);
+// node rows are [node][32] fp32 with the 16-byte granules XOR-swizzled by the node index (same scheme as q / k / v)
+__device__ __forceinline__ float4* row_granule(float* base, int node, int g) {
+    return reinterpret_cast<float4*>(base + node * 32) + (g ^ (node & 7));
+}
+// fp16 hi / lo operand row of a node tile from 32 fp32 values (4 k-chunks)
+__device__ __forceinline__ void store_node_operand(uint8_t* A, int e, const float* v) {
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) store_a_chunk(A, A + 8192, e, kc, v + 8 * kc);
+}
+
+// x of every node (thread = node; node tile m on quad m) -> XT row (from `src_rows` [N][32] in global memory when given) and the
+// fp16 hi/lo A operand of the layer's first GEMM.  Called after E0 (from nattr) and after a basis phase (from XT), whose
+// operand buffers overlay the node operand tiles.
+__device__ __forceinline__ void node_stage(const Chunk c, const float* __restrict__ src_rows) {
+    const int tid = threadIdx.x, q = tid >> 7, e = tid & (QT - 1), node = q * QT + e;
+    if (q * QT >= c.n) return;
+    float* XT = smem_at<float>(c, SB_XT);
+    float x[32];
+    if (node < c.n) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            float4 v4;
+            if (src_rows) {
+                v4 = __ldg(reinterpret_cast<const float4*>(src_rows + static_cast<size_t>(c.node0 + node) * 32) + g);
+                *row_granule(XT, node, g) = v4;
+            } else {
+                v4 = *row_granule(XT, node, g);
+            }
+            x[4 * g] = v4.x; x[4 * g + 1] = v4.y; x[4 * g + 2] = v4.z; x[4 * g + 3] = v4.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = 0.0f;
+    }
+    store_node_operand(smem_bytes(c) + SB_R + q * NODE_A, e, x);
+    fence_proxy_async_smem();
+}
+
+// q | k | v | skip = Linear(x) as ONE N = 128 GEMM per node tile (A operand staged by node_stage / the previous node_update);
+// q, k, v (+bias) go to their swizzled rows, the lin_skip part stays in TMEM columns [96, 128) for node_update.
+__device__ __noinline__ uint32_t node_qkvs(const Chunk c, uint32_t tmem_base, uint32_t qs) {
+    const int tid = threadIdx.x, q = tid >> 7, e = tid & (QT - 1), node = q * QT + e;
+    if (q * QT >= c.n) return qs;  // (whole quad: no node tile)
     const float* Wp = smem_at<const float>(c, SB_WP);
     float* Qb = smem_at<float>(c, SB_Q);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int m0 = warp * 16, g = lane >> 2, t4 = lane & 3;
-    if (m0 >= c.n) return;
-    float acc[12][4];
-    zero_frag(acc);
-    MOLSDE_MMA_GEMM<12, LDX, LD96>(sm + SB_XT / 4 + m0, Wqkv, 32, lane, acc);
+    const uint32_t a_addr = smem_u32(smem_bytes(c) + SB_R + q * NODE_A), w_addr = smem_u32(smem_bytes(c) + SB_WQ);
+    const uint32_t bar_mma = bar_addr(c, 2 * q);
+    const uint32_t tq = tmem_base + q * 128;
+    const uint32_t tlane = tq + (static_cast<uint32_t>(e & ~31) << 16);
+    if (quad_leader(q, e)) {
+        tc_fence_after();
+        umma_split_f16<128, 2>(tq, a_addr, a_addr + 8192, w_addr, w_addr + 8192, 0u);
+        umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, qs, QS_MMA0, c.status_flag);
+    tc_fence_after();
+#pragma unroll 1
+    for (int part = 0; part < 3; ++part) {   // q, k, v
+        float v[32];
+        tmem_ld32(tlane + 32 * part, v);
+        if (node < c.n) {
+            const float4* b4 = reinterpret_cast<const float4*>(Wp + MOLSDE_G_BQKVS + 32 * part);
+            float* dst = Qb + part * (32 * MAXN);
 #pragma unroll
-    for (int nb = 0; nb < 12; ++nb) {
-        const int col = nb * 8 + 2 * t4;  // 0..95: q | k | v
-        const float b0 = Wp[MOLSDE_G_BQKV + col], b1 = Wp[MOLSDE_G_BQKV + col + 1];
-        float* dst = Qb + (col >> 5) * (32 * MAXN);
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int node = m0 + g + 8 * rr;
-            if (node < c.n)
-                *reinterpret_cast<float2*>(dst + qkv_idx(node, col & 31)) = make_float2(acc[nb][2 * rr] + b0, acc[nb][2 * rr + 1] + b1);
+            for (int g = 0; g < 8; ++g) {
+                const float4 b = b4[g];
+                *row_granule(dst, node, g) = make_float4(v[4 * g] + b.x, v[4 * g + 1] + b.y, v[4 * g + 2] + b.z, v[4 * g + 3] + b.w);
+            }
         }
     }
+    tc_fence_before();
+    return qs;
 }
 
 // attention over the incoming edges of every target: e = lin_edge(edge_attr) on the tensor core (A operand = the scratch record,
@@ -653,120 +701,115 @@ __device__ __noinline__ uint32_t gat_edge_phase(const Chunk c, const uint8_t* __
     return qs;
 }
 
-// LayerNorm over the 32 columns of two rows held by a lane quad (8 columns per lane and row)
-__device__ __forceinline__ void layer_norm_quad(float (&v)[4][4], const float* __restrict__ w, const float* __restrict__ b,
-                                                int t4) {
+// LayerNorm over the 32 features of one node, all in this thread's registers (biased variance, eps 1e-5)
+__device__ __forceinline__ void layer_norm_row(float (&v)[32], const float* __restrict__ w, const float* __restrict__ b) {
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent partial sums: the node phases are latency-bound (one or two quads)
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        float s = 0.0f;
+    for (int i = 0; i < 32; ++i) s4[i & 3] += v[i];
+    const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / 32.0f);
+    float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) s += v[nb][2 * rr] + v[nb][2 * rr + 1];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        const float mean = s * (1.0f / 32.0f);
-        float q = 0.0f;
+    for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; q4[i & 3] = fmaf(d, d, q4[i & 3]); }
+    const float rstd = 1.0f / sqrtf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / 32.0f) + LN_EPS);
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) {
-            const float d0 = v[nb][2 * rr] - mean, d1 = v[nb][2 * rr + 1] - mean;
-            q += d0 * d0 + d1 * d1;
-        }
-        q += __shfl_xor_sync(0xffffffffu, q, 1);
-        q += __shfl_xor_sync(0xffffffffu, q, 2);
-        const float rstd = 1.0f / sqrtf(q * (1.0f / 32.0f) + LN_EPS);
-#pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int col = nb * 8 + 2 * t4 + j;
-                v[nb][2 * rr + j] = (v[nb][2 * rr + j] - mean) * rstd * w[col] + b[col];
-            }
+    for (int g = 0; g < 8; ++g) {
+        const float4 w4 = reinterpret_cast<const float4*>(w)[g], b4 = reinterpret_cast<const float4*>(b)[g];
+        v[4 * g] = (v[4 * g] - mean) * rstd * w4.x + b4.x;
+        v[4 * g + 1] = (v[4 * g + 1] - mean) * rstd * w4.y + b4.y;
+        v[4 * g + 2] = (v[4 * g + 2] - mean) * rstd * w4.z + b4.z;
+        v[4 * g + 3] = (v[4 * g + 3] - mean) * rstd * w4.w + b4.w;
     }
 }
 
 // x <- x + LN1(agg + skip(x));  x <- x + LN2(FFN(x));  optional SiLU  (equivariant_scorenetwork.py:35-38,140-141)
-// Each warp owns 16 nodes end to end (only __syncwarp between its GEMMs).
-__device__ __noinline__ void node_update(const Chunk c, bool silu_after, int layer) {
+// Thread = node: lin_skip(x) waits in TMEM (node_qkvs), the aggregate in q[node]; FFN.0 / FFN.3 are two N = 32 tcgen05 GEMMs on
+// the node tile (operand rows written by the node's thread, FULL barrier -> leader issue); the new x goes to XT and, as the
+// fp16 hi/lo operand, to the node tile for the next layer's q|k|v|skip GEMM.
+__device__ __noinline__ uint32_t node_update(const Chunk c, bool silu_after, int layer, uint32_t tmem_base, uint32_t qs) {
+    const int tid = threadIdx.x, q = tid >> 7, e = tid & (QT - 1), node = q * QT + e;
+    if (q * QT >= c.n) return qs;
+    const bool live = node < c.n;
     float* XT = smem_at<float>(c, SB_XT);
-    float* NT = smem_at<float>(c, SB_R);  // [32][LDX] staging of the FFN input / hidden, k-major
-    const float* Q = smem_at<const float>(c, SB_Q);
-    const float* Wg = smem_at<const float>(c, SB_WP);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int m0 = warp * 16, g = lane >> 2, t4 = lane & 3;
-    if (m0 >= c.n) return;
-    float acc[4][4], x1[4][4];
-    zero_frag(acc);
-    MOLSDE_MMA_GEMM<4, LDX, LD32>(XT + m0, Wg + MOLSDE_G_WS, 32, lane, acc);
+    float* Q = smem_at<float>(c, SB_Q);
+    const float* Wp = smem_at<const float>(c, SB_WP);
+    uint8_t* A = smem_bytes(c) + SB_R + q * NODE_A;
+    const uint32_t a_addr = smem_u32(A), w_addr = smem_u32(Wp);
+    const uint32_t bar_mma = bar_addr(c, 2 * q), bar_full = bar_addr(c, BAR_FULL0 + 2 * q);
+    const uint32_t tq = tmem_base + q * 128;
+    const uint32_t tlane = tq + (static_cast<uint32_t>(e & ~31) << 16);
+    auto gemm32 = [&](const float* rows, uint32_t w_off_floats, uint32_t tcol) {   // rows -> operand, D[tcol, +32) = rows . W^T
+        store_node_operand(A, e, rows);
+        fence_proxy_async_smem();
+        mbar_arrive(bar_full);
+        if (quad_leader(q, e)) {
+            uint32_t qt = qs;
+            mbar_wait(bar_full, qt, QS_FULL0, c.status_flag);
+            qs |= (qt & QS_DEAD);
+            tc_fence_after();
+            umma_split_f16<32, 2>(tq + tcol, a_addr, a_addr + 8192, w_addr + w_off_floats * 4, w_addr + w_off_floats * 4 + 2048, 0u);
+            umma_commit(bar_mma);
+        }
+        qs ^= QS_FULL0;
+        mbar_wait(bar_mma, qs, QS_MMA0, c.status_flag);
+        tc_fence_after();
+    };
+    float y[32], x1[32];
+    tc_fence_after();
+    tmem_ld32(tlane + 96, y);   // lin_skip(x) without bias
+    {
+        const float4* bs = reinterpret_cast<const float4*>(Wp + MOLSDE_G_BQKVS + 96);
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb) {
-        const int col = nb * 8 + 2 * t4;
-        const float b0 = Wg[MOLSDE_G_BS + col], b1 = Wg[MOLSDE_G_BS + col + 1];
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int node = m0 + g + 8 * rr;
-            float2 ag = make_float2(0.f, 0.f);
-            if (node < c.n) ag = *reinterpret_cast<const float2*>(Q + qkv_idx(node, col));
-            acc[nb][2 * rr] += b0 + ag.x;
-            acc[nb][2 * rr + 1] += b1 + ag.y;
+        for (int g = 0; g < 8; ++g) {
+            const float4 b = bs[g];
+            const float4 ag = live ? *row_granule(Q, node, g) : make_float4(0.f, 0.f, 0.f, 0.f);   // attention aggregate
+            y[4 * g] += b.x + ag.x; y[4 * g + 1] += b.y + ag.y; y[4 * g + 2] += b.z + ag.z; y[4 * g + 3] += b.w + ag.w;
         }
     }
-    layer_norm_quad(acc, Wg + MOLSDE_G_LN1_W, Wg + MOLSDE_G_LN1_B, t4);
+    layer_norm_row(y, Wp + MOLSDE_G_LN1_W, Wp + MOLSDE_G_LN1_B);
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb)
+    for (int g = 0; g < 8; ++g) {
+        const float4 xo = live ? *row_granule(XT, node, g) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x1[4 * g] = xo.x + y[4 * g]; x1[4 * g + 1] = xo.y + y[4 * g + 1]; x1[4 * g + 2] = xo.z + y[4 * g + 2]; x1[4 * g + 3] = xo.w + y[4 * g + 3];
+    }
+    gemm32(x1, MOLSDE_G_F0C, 0);
+    tmem_ld32(tlane, y);
+    tc_fence_before();
+    {
+        const float* kp = (c.ffn_keep && live) ? c.ffn_keep + (static_cast<size_t>(layer) * c.N_total + c.node0 + node) * 32 : nullptr;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int col = nb * 8 + 2 * t4 + j;
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int node = m0 + g + 8 * rr;
-                const float xo = (node < c.n) ? XT[col * LDX + node] : 0.0f;
-                x1[nb][2 * rr + j] = xo + acc[nb][2 * rr + j];
-                NT[col * LDX + node] = x1[nb][2 * rr + j];
+        for (int g = 0; g < 8; ++g) {
+            const float4 b = reinterpret_cast<const float4*>(Wp + MOLSDE_G_F0_B)[g];
+            float4 h = make_float4(silu_fast(y[4 * g] + b.x), silu_fast(y[4 * g + 1] + b.y), silu_fast(y[4 * g + 2] + b.z),
+                                   silu_fast(y[4 * g + 3] + b.w));
+            if (kp) {  // nn.Dropout between FFN.1 (SiLU) and FFN.3 in train mode
+                const float4 k4 = __ldg(reinterpret_cast<const float4*>(kp) + g);
+                h.x *= k4.x * c.inv_keep; h.y *= k4.y * c.inv_keep; h.z *= k4.z * c.inv_keep; h.w *= k4.w * c.inv_keep;
             }
+            y[4 * g] = h.x; y[4 * g + 1] = h.y; y[4 * g + 2] = h.z; y[4 * g + 3] = h.w;
         }
-    __syncwarp();
-    zero_frag(acc);
-    MOLSDE_MMA_GEMM<4, LDX, LD32>(NT + m0, Wg + MOLSDE_G_F0, 32, lane, acc);
-    __syncwarp();
+    }
+    gemm32(y, MOLSDE_G_F3C, 32);
+    tmem_ld32(tlane + 32, y);
+    tc_fence_before();
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb)
+    for (int g = 0; g < 8; ++g) {
+        const float4 b = reinterpret_cast<const float4*>(Wp + MOLSDE_G_F3_B)[g];
+        y[4 * g] += b.x; y[4 * g + 1] += b.y; y[4 * g + 2] += b.z; y[4 * g + 3] += b.w;
+    }
+    layer_norm_row(y, Wp + MOLSDE_G_LN2_W, Wp + MOLSDE_G_LN2_B);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int col = nb * 8 + 2 * t4 + j;
-            const float bj = Wg[MOLSDE_G_F0_B + col];
+    for (int i = 0; i < 32; ++i) {
+        float x2 = x1[i] + y[i];
+        if (silu_after) x2 = silu_fast(x2);
+        y[i] = live ? x2 : 0.0f;
+    }
+    if (live) {
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int node = m0 + g + 8 * rr;
-                float hv = silu_fast(acc[nb][2 * rr + j] + bj);
-                if (c.ffn_keep && node < c.n)  // nn.Dropout between FFN.1 (SiLU) and FFN.3 in train mode
-                    hv *= c.ffn_keep[(static_cast<size_t>(layer) * c.N_total + c.node0 + node) * 32 + col] * c.inv_keep;
-                NT[col * LDX + node] = hv;
-            }
-        }
-    __syncwarp();
-    zero_frag(acc);
-    MOLSDE_MMA_GEMM<4, LDX, LD32>(NT + m0, Wg + MOLSDE_G_F3, 32, lane, acc);
-#pragma unroll
-    for (int nb = 0; nb < 4; ++nb)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const float bj = Wg[MOLSDE_G_F3_B + nb * 8 + 2 * t4 + j];
-            acc[nb][j] += bj;
-            acc[nb][2 + j] += bj;
-        }
-    layer_norm_quad(acc, Wg + MOLSDE_G_LN2_W, Wg + MOLSDE_G_LN2_B, t4);
-#pragma unroll
-    for (int nb = 0; nb < 4; ++nb)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int col = nb * 8 + 2 * t4 + j;
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int node = m0 + g + 8 * rr;
-                float x2 = x1[nb][2 * rr + j] + acc[nb][2 * rr + j];
-                if (silu_after) x2 = silu_fast(x2);
-                if (node < c.n) XT[col * LDX + node] = x2;
-            }
-        }
+        for (int g = 0; g < 8; ++g) *row_granule(XT, node, g) = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
+    }
+    store_node_operand(A, e, y);   // A operand of the next layer's q|k|v|skip GEMM (its FFN.3 reader has completed)
+    fence_proxy_async_smem();
+    return qs;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -779,7 +822,7 @@ __device__ __noinline__ void node_update(const Chunk c, bool silu_after, int lay
 __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restrict__ blob, const uint8_t* __restrict__ scratch, int module,
                                              uint32_t tmem_base, uint32_t qs) {
     const float* Wb = smem_at<const float>(c, SB_BW);
-    const float* XT = smem_at<const float>(c, SB_XT);
+    float* XTm = smem_at<float>(c, SB_XT);
     float* grad = smem_at<float>(c, SB_GRAD);
     const int* rowl = c.si + SI_ROWL;
     const int tid = threadIdx.x, q = tid >> 7, e = tid & (QT - 1);
@@ -811,9 +854,9 @@ __device__ __noinline__ uint32_t phase_basis(const Chunk c, const float* __restr
         const int sj = live ? rec[REC_SLOT + e] : 0, tg = live ? rec[REC_SLOT + TE + e] : 0;
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = XT[(8 * kc + j) * LDX + sj] + XT[(8 * kc + j) * LDX + tg];
+            const float4 a0 = *row_granule(XTm, sj, 2 * kc), a1 = *row_granule(XTm, sj, 2 * kc + 1);
+            const float4 b0 = *row_granule(XTm, tg, 2 * kc), b1 = *row_granule(XTm, tg, 2 * kc + 1);
+            const float v[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
             store_a_chunk(Ah, Al, e, kc, v);
         }
         fence_proxy_async_smem();
@@ -891,30 +934,27 @@ __device__ __noinline__ uint32_t score_eval(const Chunk c, const float* __restri
     PROF_T0();
     qs = phase_edge_features(c, blob, e2d_tiles, scratch, tmem_base, qs);
     PROF_ADD(0);
-    // conv_input = node_attr (loop-invariant node_emb output), k-major
-    float* XT = smem_at<float>(c, SB_XT);
-    for (int idx = threadIdx.x; idx < c.n * 32; idx += NTHREADS) {
-        const int node = idx >> 5, k = idx & 31;
-        XT[k * LDX + node] = __ldg(nattr + static_cast<size_t>(c.node0 + node) * 32 + k);
-    }
+    // conv_input = node_attr (loop-invariant node_emb output): XT rows + the operand of the first q|k|v|skip GEMM
+    node_stage(c, nattr);
     for (int module = 0; module < 2; ++module) {
         for (int conv = 0; conv < 2; ++conv) {
             const float* sec = blob + MOLSDE_P_GAT0 + (2 * module + conv) * MOLSDE_P_GAT_SZ;
-            __syncthreads();  // previous users of the WP / R regions (E0 operands, FFN staging, basis operands) are done
-            stage_bulk2(c, smem_bytes(c) + SB_WP, sec, MOLSDE_G_WP_SZ, smem_bytes(c) + SB_R, sec + MOLSDE_G_WQKV,
-                        MOLSDE_P_GAT_SZ - MOLSDE_G_WQKV);
+            __syncthreads();  // previous users of the WP / SB_WQ regions are done; the node operand tiles are complete
+            stage_bulk2(c, smem_bytes(c) + SB_WP, sec, MOLSDE_G_WP_SZ, smem_bytes(c) + SB_WQ, sec + MOLSDE_G_WQKVS,
+                        MOLSDE_P_GAT_SZ - MOLSDE_G_WQKVS);
             PROF_ADD(1);
-            node_qkv(c);
+            qs = node_qkvs(c, tmem_base, qs);
             __syncthreads();
             PROF_ADD(2);
             qs = gat_edge_phase(c, scratch, 2 * module + conv, tmem_base, qs);
             __syncthreads();
             PROF_ADD(3);
-            node_update(c, conv == 0, 2 * module + conv);
+            qs = node_update(c, conv == 0, 2 * module + conv, tmem_base, qs);
             PROF_ADD(4);
         }
         qs = phase_basis(c, blob, scratch, module, tmem_base, qs);
         PROF_ADD(5);
+        if (module == 0) node_stage(c, nullptr);  // the basis operand buffers overlaid the node operand tiles
     }
     return qs;
 }

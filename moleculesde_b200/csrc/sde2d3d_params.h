@@ -2,19 +2,13 @@
  * The host (moleculesde_b200/sde_2d_to_3d.py::packed_params) builds it from the reference
  * state_dict keys.
  *
- * Two weight formats live in the blob:
- *  (a) tcgen05 B-operand tiles (every per-edge GEMM: Fourier-feature layers, project.1, lin_edge, basis MLP layer 0):
+ * Every GEMM of the score network runs on tcgen05; its weight is stored as a B-operand tile:
  *      fp16, two-way split  w = hi + lo  (hi = fp16(w), lo = fp16(w - hi)), each part stored as an [N rows][K] K-major tile in
  *      the canonical no-swizzle core-matrix layout (8 rows x 16 B = 8 halves):
  *        byte offset(n, k) = (k/8)*(N*16) + (n/8)*128 + (n%8)*16 + (k%8)*2        (LBO = N*16 B, SBO = 128 B)
- *  (b) mma.sync B blocks of the per-node GEMMs (q|k|v, lin_skip, FFN): k-major [in][ld] words with ld == 8 (mod 32), holding
- *      fp16 hi/lo pair words (pack_f16_pairs; csrc/mma_tile.cuh mma_gemm_hp).
  * All section offsets are multiples of 32 floats (128 B); every section is copied to shared memory by ONE TMA bulk copy. */
 #ifndef MOLSDE_SDE2D3D_PARAMS_H_
 #define MOLSDE_SDE2D3D_PARAMS_H_
-
-#define MOLSDE_LD32 40   /* leading dimension of a 32-column mma.sync weight block */
-#define MOLSDE_LD96 104  /* q|k|v block                                            */
 
 /* ---- per-edge feature stage (SDE_model_2D_to_3D.py:402-432) ---- */
 #define MOLSDE_P_GFP_DIST_W 0   /* dist_gaussian_fourier.W [32] */
@@ -30,27 +24,26 @@
 #define MOLSDE_P_E0_END 11520
 
 /* ---- one GATLayer (score_network.gnn_layers.{m}.{c}), base = P_GAT0 + (2m+c)*P_GAT_SZ ----
- * [0, G_WP_SZ): resident for the whole layer;  [G_WQKV, P_GAT_SZ): only needed by the q|k|v GEMM (staged over the edge-phase buffers) */
+ * All GEMMs of the layer run on tcgen05: B tiles [N rows][32 k] fp16, hi | lo.
+ * [0, G_WP_SZ): resident for the whole layer;  [G_WQKVS, P_GAT_SZ): only needed by the q|k|v|skip GEMM (staged over the edge-phase buffers) */
 #define MOLSDE_P_GAT0 11520
-#define MOLSDE_G_WS 0       /* MHA.lin_skip.weight^T [32][40] (pair words) */
-#define MOLSDE_G_F0 1280    /* FFN.0.weight^T [32][40] */
-#define MOLSDE_G_F3 2560    /* FFN.3.weight^T [32][40] */
-#define MOLSDE_G_BQKV 3840  /* [96] */
-#define MOLSDE_G_BS 3936
-#define MOLSDE_G_LN1_W 3968
-#define MOLSDE_G_LN1_B 4000
-#define MOLSDE_G_F0_B 4032
-#define MOLSDE_G_F3_B 4064
-#define MOLSDE_G_LN2_W 4096
-#define MOLSDE_G_LN2_B 4128
-#define MOLSDE_G_WEC 4160   /* MHA.lin_edge.weight (no bias) as a tcgen05 B tile [32 n][32 k]: hi (512 floats) | lo (512 floats) */
-#define MOLSDE_G_WP_SZ 5184
-#define MOLSDE_G_WQKV 5184  /* [lin_query | lin_key | lin_value].weight^T [32][104] (pair words) */
-#define MOLSDE_P_GAT_SZ 8512
+#define MOLSDE_G_F0C 0      /* FFN.0.weight [32 n][32 k]: hi (512 floats) | lo (512 floats) */
+#define MOLSDE_G_F3C 1024   /* FFN.3.weight */
+#define MOLSDE_G_WEC 2048   /* MHA.lin_edge.weight (no bias) */
+#define MOLSDE_G_BQKVS 3072 /* [128]: lin_query | lin_key | lin_value | lin_skip biases */
+#define MOLSDE_G_LN1_W 3200
+#define MOLSDE_G_LN1_B 3232
+#define MOLSDE_G_F0_B 3264
+#define MOLSDE_G_F3_B 3296
+#define MOLSDE_G_LN2_W 3328
+#define MOLSDE_G_LN2_B 3360
+#define MOLSDE_G_WP_SZ 3392
+#define MOLSDE_G_WQKVS 3392 /* [lin_query | lin_key | lin_value | lin_skip].weight as ONE B tile [128 n][32 k]: hi (2048 floats) | lo (2048) */
+#define MOLSDE_P_GAT_SZ 7488
 
 /* ---- one basis MLP (score_network.basis_mlp_modules.{m}), base = P_BASIS0 + m*P_BASIS_SZ ----
  * layer 0 (64 -> 128; input k 0..31 = h_row+h_col, 32..63 = edge_attr) as a tcgen05 B tile [128 n][64 k] fp16 hi | lo. */
-#define MOLSDE_P_BASIS0 45568
+#define MOLSDE_P_BASIS0 41472
 #define MOLSDE_B_W1_HI 0     /* 16384 B = 4096 floats */
 #define MOLSDE_B_W1_LO 4096
 #define MOLSDE_B_EPI 8192    /* [128][4]: {.0.bias[n], .2.weight[0][n], .2.weight[1][n], .2.weight[2][n]} */
@@ -58,6 +51,6 @@
 #define MOLSDE_P_BASIS_SZ 8708
 #define MOLSDE_P_BASIS_STRIDE 8736  /* section stride (multiple of 32 floats) */
 
-#define MOLSDE_P_TOTAL 63040
+#define MOLSDE_P_TOTAL 58944
 
 #endif

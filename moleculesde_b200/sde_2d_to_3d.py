@@ -18,44 +18,14 @@ from .plan import TilePlan, build_plan
 from .sde import VESDE, VPSDE
 
 # float offsets of csrc/sde2d3d_params.h
-LD32, LD96 = 40, 104
 P_GFP_DIST_W, P_GFP_COFF_W = 0, 32
 P_E0_HV, P_E0_OB, P_E0_BT, E0_BT_FLOATS, P_E0_END = 64, 192, 256, 1024, 11520
-P_GAT0, P_GAT_SZ = 11520, 8512
-P_BASIS0, P_BASIS_SZ, P_BASIS_STRIDE = 45568, 8708, 8736
-P_TOTAL = 63040
-_G = dict(WS=0, F0=1280, F3=2560, BQKV=3840, BS=3936, LN1_W=3968, LN1_B=4000, F0_B=4032, F3_B=4064, LN2_W=4096, LN2_B=4128,
-          WEC=4160, WP_SZ=5184, WQKV=5184)
+P_GAT0, P_GAT_SZ = 11520, 7488
+P_BASIS0, P_BASIS_SZ, P_BASIS_STRIDE = 41472, 8708, 8736
+P_TOTAL = 58944
+_G = dict(F0C=0, F3C=1024, WEC=2048, BQKVS=3072, LN1_W=3200, LN1_B=3232, F0_B=3264, F3_B=3296, LN2_W=3328, LN2_B=3360,
+          WP_SZ=3392, WQKVS=3392)
 _B = dict(W1_HI=0, W1_LO=4096, EPI=8192, B2=8704)
-
-
-def pack_f16_pairs(blk: torch.Tensor) -> torch.Tensor:
-    """k-major fp32 weight block [K, LD] (K even) -> the same [K, LD] words holding the two-way fp16 split the `mma.m16n8k16`
-    tile GEMMs consume (csrc/mma_tile.cuh, `mma_gemm_hp`): row 2p = half2(hi[2p], hi[2p+1]), row 2p+1 = half2(lo[2p], lo[2p+1]) per
-    column, hi = fp16(w) (round to nearest), lo = fp16(w - hi); the even-k half sits in the low 16 bits.  Same footprint and the
-    same four addresses per B fragment as the fp32 block, but no conversion instructions in the kernel's inner loop."""
-    K, LD = blk.shape
-    assert K % 2 == 0
-    hi = blk.half()
-    lo = (blk - hi.float()).half()
-
-    def words(h):
-        u = h.view(torch.int16).to(torch.int32) & 0xFFFF
-        return u[0::2] | (u[1::2] << 16)
-    out = torch.stack([words(hi), words(lo)], dim=1).reshape(K, LD)
-    return out.contiguous().view(torch.float32)
-
-
-def unpack_f16_pairs(words: torch.Tensor) -> torch.Tensor:
-    """Inverse of `pack_f16_pairs` up to the split: returns hi + lo as fp32 [K, LD] (tests)."""
-    K, LD = words.shape
-    w = words.contiguous().view(torch.int32).reshape(K // 2, 2, LD)
-
-    def halves(u):
-        lo16 = (u & 0xFFFF).to(torch.int16).view(torch.float16).float()
-        hi16 = ((u >> 16) & 0xFFFF).to(torch.int16).view(torch.float16).float()
-        return torch.stack([lo16, hi16], dim=1).reshape(K, LD)    # interleave even / odd k
-    return halves(w[:, 0]) + halves(w[:, 1])
 
 
 def umma_tile_f16(w: torch.Tensor) -> torch.Tensor:
@@ -234,14 +204,6 @@ class SDEModel2Dto3D_02(nn.Module):
         def put(off, t):
             blob[off:off + t.numel()] = t.reshape(-1)
 
-        def put_kmajor(off, w, ld):
-            """nn.Linear weight [out,in] -> k-major block [in][ld] (columns >= out stay zero), stored as the fp16 hi/lo pair
-            words of `pack_f16_pairs` (what the mma.sync tile GEMMs of csrc/sde2d3d.cu read)."""
-            out_f, in_f = w.shape
-            blk = torch.zeros(in_f, ld, dtype=torch.float32, device=dev)
-            blk[:, :out_f] = w.t()
-            put(off, pack_f16_pairs(blk))
-
         H = self.hidden_dim
         put(P_GFP_COFF_W, sd["coff_gaussian_fourier.W"])
         ob = torch.zeros(H, 2, dtype=torch.float32, device=dev)            # {input_mlp bias, project.1 bias} per column
@@ -279,19 +241,17 @@ class SDEModel2Dto3D_02(nn.Module):
             for c in range(2):
                 base = P_GAT0 + (2 * m + c) * P_GAT_SZ
                 p = f"score_network.gnn_layers.{m}.{c}."
-                wqkv = torch.cat([sd[p + "MHA.lin_query.weight"], sd[p + "MHA.lin_key.weight"],
-                                  sd[p + "MHA.lin_value.weight"]], dim=0)  # [96, 32]
-                put_kmajor(base + _G["WQKV"], wqkv, LD96)
-                put(base + _G["BQKV"], torch.cat([sd[p + "MHA.lin_query.bias"], sd[p + "MHA.lin_key.bias"],
-                                                  sd[p + "MHA.lin_value.bias"]]))
-                put_kmajor(base + _G["WS"], sd[p + "MHA.lin_skip.weight"], LD32)
-                put(base + _G["BS"], sd[p + "MHA.lin_skip.bias"])
+                wqkvs = torch.cat([sd[p + "MHA.lin_query.weight"], sd[p + "MHA.lin_key.weight"], sd[p + "MHA.lin_value.weight"],
+                                   sd[p + "MHA.lin_skip.weight"]], dim=0)  # [128, 32]: one N = 128 GEMM gives q | k | v | skip
+                put(base + _G["WQKVS"], umma_tile_split_words(wqkvs))
+                put(base + _G["BQKVS"], torch.cat([sd[p + "MHA.lin_query.bias"], sd[p + "MHA.lin_key.bias"],
+                                                   sd[p + "MHA.lin_value.bias"], sd[p + "MHA.lin_skip.bias"]]))
                 put(base + _G["WEC"], umma_tile_split_words(sd[p + "MHA.lin_edge.weight"]))
                 put(base + _G["LN1_W"], sd[p + "norm1.weight"])
                 put(base + _G["LN1_B"], sd[p + "norm1.bias"])
-                put_kmajor(base + _G["F0"], sd[p + "FFN.0.weight"], LD32)
+                put(base + _G["F0C"], umma_tile_split_words(sd[p + "FFN.0.weight"]))
                 put(base + _G["F0_B"], sd[p + "FFN.0.bias"])
-                put_kmajor(base + _G["F3"], sd[p + "FFN.3.weight"], LD32)
+                put(base + _G["F3C"], umma_tile_split_words(sd[p + "FFN.3.weight"]))
                 put(base + _G["F3_B"], sd[p + "FFN.3.bias"])
                 put(base + _G["LN2_W"], sd[p + "norm2.weight"])
                 put(base + _G["LN2_B"], sd[p + "norm2.bias"])

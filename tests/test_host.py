@@ -42,9 +42,6 @@ def test_param_offsets_match_header():
     assert defs["MOLSDE_P_GAT0"] == M.P_GAT0 == defs["MOLSDE_P_E0_END"] == M.P_E0_END and defs["MOLSDE_P_GAT_SZ"] == M.P_GAT_SZ
     assert defs["MOLSDE_P_BASIS0"] == M.P_BASIS0 == M.P_GAT0 + 4 * M.P_GAT_SZ
     assert defs["MOLSDE_P_BASIS_SZ"] == M.P_BASIS_SZ <= defs["MOLSDE_P_BASIS_STRIDE"] == M.P_BASIS_STRIDE
-    assert (defs["MOLSDE_LD32"], defs["MOLSDE_LD96"]) == (M.LD32, M.LD96)
-    for ld in (M.LD32, M.LD96):
-        assert ld % 32 == 8  # bank-conflict-free mma B-fragment loads
     for k, v in M._G.items():
         assert defs["MOLSDE_G_" + k] == v and v % 4 == 0
     for k, v in M._B.items():
@@ -53,11 +50,12 @@ def test_param_offsets_match_header():
         assert defs["MOLSDE_P_" + name] == getattr(M, "P_" + name)
     assert defs["MOLSDE_E0_BT_FLOATS"] == M.E0_BT_FLOATS == 2 * 32 * 32 * 2 // 4
     # sections are whole numbers of 128-byte lines (TMA bulk copies, 128 B aligned operand tiles); blocks do not overlap
-    for v in (M.P_E0_BT, M.P_E0_END, M.P_GAT_SZ, M.P_BASIS_STRIDE, M._G["WEC"], M._G["WQKV"]):
+    for v in (M.P_E0_BT, M.P_E0_END, M.P_GAT_SZ, M.P_BASIS_STRIDE, M._G["F0C"], M._G["F3C"], M._G["WEC"], M._G["WQKVS"]):
         assert v % 32 == 0
     assert M.P_E0_BT + 11 * M.E0_BT_FLOATS == M.P_E0_END
-    assert M._G["F3"] + 32 * M.LD32 == M._G["BQKV"] and M._G["LN2_B"] + 32 == M._G["WEC"] and M._G["WEC"] + 1024 == M._G["WP_SZ"]
-    assert M._G["WQKV"] + 32 * M.LD96 == M.P_GAT_SZ
+    assert M._G["F0C"] + 1024 == M._G["F3C"] and M._G["F3C"] + 1024 == M._G["WEC"] and M._G["WEC"] + 1024 == M._G["BQKVS"]
+    assert M._G["BQKVS"] + 128 == M._G["LN1_W"] and M._G["LN2_B"] + 32 == M._G["WP_SZ"] == M._G["WQKVS"]
+    assert M._G["WQKVS"] + 2 * 128 * 32 * 2 // 4 == M.P_GAT_SZ
     assert M._B["W1_LO"] == 128 * 64 * 2 // 4 and M._B["W1_LO"] + 4096 == M._B["EPI"] and M._B["EPI"] + 512 == M._B["B2"]
     api = open(os.path.join(REPO, "include", "molsde_b200.h")).read()
     assert int(re.search(r"#define MOLSDE_TILE_LD (\d+)", api).group(1)) == _abi.TILE_LD
@@ -148,17 +146,17 @@ def test_packed_blob_roundtrip(golden):
     we = tile(base + M._G["WEC"], 32, 32)
     ref_we = sd["score_network.gnn_layers.1.1.MHA.lin_edge.weight"]
     assert float((we - ref_we).abs().max()) <= 2.0 ** -21 * float(ref_we.abs().max())
-    # mma.sync weight blocks of the node GEMMs are stored as fp16 hi/lo pair words (pack_f16_pairs)
-    wqkv = M.unpack_f16_pairs(blob[base + M._G["WQKV"]:base + M._G["WQKV"] + 32 * M.LD96].view(32, M.LD96))
-    ref_k = sd["score_network.gnn_layers.1.1.MHA.lin_key.weight"].t()
-    assert float((wqkv[:, 32:64] - ref_k).abs().max()) <= 2.0 ** -21 * float(ref_k.abs().max()) and torch.all(wqkv[:, 96:] == 0)
-    # the packing itself: even k in the low half, hi row then lo row
-    blk = torch.tensor([[1.0, -2.5], [3.0e-5, 0.1], [7.0, 0.0], [-0.33, 1e-3]])
-    pk2 = M.pack_f16_pairs(blk).view(torch.int32)
-    h = blk.half()
-    assert pk2[0, 0].item() & 0xFFFF == h[0, 0].view(torch.int16).item() & 0xFFFF
-    assert (pk2[0, 0].item() >> 16) & 0xFFFF == h[1, 0].view(torch.int16).item() & 0xFFFF
-    assert float((M.unpack_f16_pairs(pk2.view(torch.float32)) - blk).abs().max()) <= 2.0 ** -21
+    # node GEMMs: q | k | v | skip as ONE B tile [128 n][32 k]; FFN.0 / FFN.3 tiles; bias vector in the same order
+    wq = tile(base + M._G["WQKVS"], 128, 32)
+    for part, key in enumerate(("lin_query", "lin_key", "lin_value", "lin_skip")):
+        ref_w = sd[f"score_network.gnn_layers.1.1.MHA.{key}.weight"]
+        assert float((wq[32 * part:32 * part + 32] - ref_w).abs().max()) <= 2.0 ** -21 * float(ref_w.abs().max()), key
+        assert torch.equal(blob[base + M._G["BQKVS"] + 32 * part:base + M._G["BQKVS"] + 32 * part + 32],
+                           sd[f"score_network.gnn_layers.1.1.MHA.{key}.bias"])
+    for off, key in ((M._G["F0C"], "FFN.0"), (M._G["F3C"], "FFN.3")):
+        ref_w = sd[f"score_network.gnn_layers.1.1.{key}.weight"]
+        assert float((tile(base + off, 32, 32) - ref_w).abs().max()) <= 2.0 ** -21 * float(ref_w.abs().max())
+    assert torch.equal(blob[base + M._G["LN2_B"]:base + M._G["LN2_B"] + 32], sd["score_network.gnn_layers.1.1.norm2.bias"])
     # basis MLP: tcgen05 B tile [128 n][64 k] (hi + lo == weight to 2^-22) and the epilogue table {b1, w2[0..2]} per hidden unit
     base = M.P_BASIS0 + M.P_BASIS_STRIDE
     w1 = sd["score_network.basis_mlp_modules.1.0.weight"]  # [128 (n), 64 (k)]
@@ -284,14 +282,19 @@ def test_edge_segments_randomised_edge_orders():
         assert G <= E and G >= 1
 
 
-def test_pack_f16_pairs_randomised():
-    import torch
-    from moleculesde_b200.sde_2d_to_3d import pack_f16_pairs, unpack_f16_pairs
-    g = torch.Generator().manual_seed(3)
-    for scale in (1e-3, 1.0, 50.0):
-        blk = torch.randn(64, 40, generator=g) * scale
-        back = unpack_f16_pairs(pack_f16_pairs(blk))
-        # hi + lo keeps 22 significant bits, or 2^-25 absolutely where lo falls into fp16's subnormal range
-        tol = torch.maximum(blk.abs() * 2.0 ** -21, torch.full_like(blk, 2.0 ** -24))
-        assert torch.all((back - blk).abs() <= tol)
-    assert torch.equal(pack_f16_pairs(torch.zeros(4, 8)), torch.zeros(4, 8))
+def test_umma_tile_split_randomised():
+    """fp16 hi/lo operand tiles of the tcgen05 GEMMs: hi + lo reproduces the fp32 weight to 2^-22 relative (fp16's narrow exponent:
+    absolute 2^-25 below 2^-14), the canonical core-matrix addressing round-trips, zeros stay zeros."""
+    from moleculesde_b200.sde_2d_to_3d import umma_tile_split_words, unpack_umma_tile_f16
+    g = torch.Generator().manual_seed(0)
+    for R, K, scale in ((32, 32, 1.0), (128, 64, 0.05), (128, 32, 30.0), (8, 8, 1e-3)):
+        w = torch.randn(R, K, generator=g) * scale
+        words = umma_tile_split_words(w)
+        n = R * K // 2
+        assert words.numel() == 2 * n and words.dtype == torch.float32
+        back = unpack_umma_tile_f16(words[:n], R, K) + unpack_umma_tile_f16(words[n:], R, K)
+        assert float((back - w).abs().max()) <= max(2.0 ** -21 * float(w.abs().max()), 2.0 ** -24)
+        hi = unpack_umma_tile_f16(words[:n], R, K)
+        assert torch.equal(hi, w.half().float())
+    assert torch.equal(umma_tile_split_words(torch.zeros(8, 8)), torch.zeros(64))
+
