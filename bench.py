@@ -42,7 +42,7 @@ def parse():
     p.add_argument("--molecules", type=int, default=1024, help="molecules per GPU (BASELINE configs[1]: 1024)")
     p.add_argument("--repeat", type=int, default=10, help="conformers per molecule (config.py:133)")
     p.add_argument("--pc-steps", type=int, default=1000, help="reverse-SDE steps (num_diffusion_timesteps)")
-    p.add_argument("--cpu-pc-steps", type=int, default=10, help="PC steps of the bounded CPU sample")
+    p.add_argument("--cpu-pc-steps", type=int, default=1000, help="PC steps per group of the CPU sample (default: the whole trajectory)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--pretrain-batch", type=int, default=256, help="molecules per GPU of the pretraining step (configs[2])")
@@ -130,61 +130,135 @@ class ClockSampler:
 # CPU arm: the oracle port of the reference algorithm (test infrastructure used as the measured
 # baseline here and nowhere else)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(mols, repeat, pc_steps_sample, total_pc_steps, state_dict, reps=1):
-    """conformers/s of the reference algorithm on this box's host cores: `pc_steps_sample` PC steps on
-    one sampling group (molecule 0 x `repeat` conformers), extrapolated to `total_pc_steps`."""
-    from moleculesde_b200.data import repeat_data
+def _cpu_group_worker(args):
+    """One worker process of the CPU arm: a whole sampling group (one molecule x `repeat` conformers) through the oracle port's
+    predictor-corrector loop with `threads` intra-op threads.  Returns (seconds, atoms) of the timed pass."""
+    (widx, seed, repeat, pc_steps, threads, sd, barrier) = args
+    import torch as _t
+    _t.set_num_threads(threads)
+    from moleculesde_b200.data import repeat_data, synth_molecules
     from oracle import model as O
     from oracle.ref_ops import extend_graph_index
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = {k: v.detach().cpu().float() for k, v in state_dict.items()}
-    mol = mols[0]
+    mol = synth_molecules(widx + 1, seed, "pcqm")[widx]
     mol.extended_edge_index = extend_graph_index(mol.edge_index, mol.num_nodes)
     rb = repeat_data(mol, repeat)
     sde = O.make_sde("VE", 0.2, 1.0, 1000)
-    g = torch.Generator().manual_seed(0)
+    g = _t.Generator().manual_seed(widx)
     n = rb.positions.size(0)
-    rep = torch.randn(n, 300, generator=g)
-    pos0 = torch.randn(n, 3, generator=g)
-    nc = torch.randn(pc_steps_sample, n, 3, generator=g)
-    npd = torch.randn(pc_steps_sample, n, 3, generator=g)
-    best = None
-    for _ in range(max(reps, 1)):
-        t0 = time.perf_counter()
-        O.pc_sample_2d3d(sd, sde, rep, rb.extended_edge_index, rb.batch, rb.num_graphs, pos0, nc, npd,
-                         n_diff_steps=pc_steps_sample)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    per_pc_step = best / pc_steps_sample
-    rate = repeat / (per_pc_step * total_pc_steps)
-    sample = (f"{pc_steps_sample} PC steps (2 score evals each) on one group of {repeat} conformers of a "
-              f"{mol.num_nodes}-atom molecule, extrapolated x{total_pc_steps / pc_steps_sample:g} to {total_pc_steps} steps; "
-              "oracle port (pure-torch restatement of the reference), fp32")
-    return rate, per_pc_step, sample
+    rep = _t.randn(n, 300, generator=g)
+    pos0 = _t.randn(n, 3, generator=g)
+    nc = _t.randn(pc_steps, n, 3, generator=g)
+    npd = _t.randn(pc_steps, n, 3, generator=g)
+    O.pc_sample_2d3d(sd, sde, rep, rb.extended_edge_index, rb.batch, rb.num_graphs, pos0, nc[:2], npd[:2], n_diff_steps=2)  # page in
+    if barrier is not None:
+        barrier.wait()
+    t0 = time.perf_counter()
+    O.pc_sample_2d3d(sd, sde, rep, rb.extended_edge_index, rb.batch, rb.num_graphs, pos0, nc, npd, n_diff_steps=pc_steps)
+    return time.perf_counter() - t0, n
+
+
+class CpuArm:
+    """The reference algorithm (oracle port) on this box's host cores.  A single sampling group (~150 atoms) is latency-bound on
+    one or two threads (measured here: 20.8 ms per PC step on 1 thread, 15.9 on 4, 58 on 16), so the arm that uses ALL host cores
+    runs `cores // threads` independent groups side by side (one process each), the way the reference's driver would be sharded by
+    molecule; conformers/s = groups x repeat / (slowest worker's seconds per PC step x total PC steps)."""
+
+    def __init__(self, repeat, state_dict, seed=0):
+        import multiprocessing as mp
+        self.repeat, self.seed = repeat, seed
+        self.cores = os.cpu_count() or 1
+        self.sd = {k: v.detach().cpu().float() for k, v in state_dict.items()}
+        ctx = mp.get_context("spawn")  # (a CUDA context may exist in this process: never fork it)
+        self.mgr = ctx.Manager()
+        self.pool = ctx.Pool(self.cores)
+
+    def run(self, pc_steps, threads=1):
+        """`cores // threads` groups x `pc_steps` PC steps -> (seconds of the slowest worker, #groups, atoms per molecule range)"""
+        workers = max(1, self.cores // threads)
+        barrier = self.mgr.Barrier(workers)
+        res = self.pool.map(_cpu_group_worker, [(w, self.seed, self.repeat, pc_steps, threads, self.sd, barrier) for w in range(workers)],
+                            chunksize=1)
+        atoms = [r[1] // self.repeat for r in res]
+        return max(r[0] for r in res), workers, (min(atoms), max(atoms))
+
+    def rate(self, seconds, workers, pc_steps, total_pc_steps):
+        return workers * self.repeat / (seconds / pc_steps * total_pc_steps)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+        self.mgr.shutdown()
+
+
+def cpu_reference_rate(repeat, pc_steps_sample, total_pc_steps, state_dict, seed=0, threads=1):
+    """One pass of the CPU arm (used for the `cpu_baseline` of the B200 line): the whole trajectory by default."""
+    arm = CpuArm(repeat, state_dict, seed)
+    try:
+        sec, workers, atoms = arm.run(pc_steps_sample, threads)
+        rate = arm.rate(sec, workers, pc_steps_sample, total_pc_steps)
+    finally:
+        arm.close()
+    scale = "" if pc_steps_sample == total_pc_steps else f", scaled x{total_pc_steps / pc_steps_sample:g} to {total_pc_steps} steps"
+    sample = (f"{workers} sampling groups in parallel ({workers} processes x {threads} thread(s) on {arm.cores} host cores), each "
+              f"{pc_steps_sample} predictor-corrector steps (2 score evals per step) of {repeat} conformers of one molecule "
+              f"({atoms[0]}-{atoms[1]} atoms){scale}; slowest worker {sec:.1f} s; oracle port (pure-torch restatement of the "
+              "reference), fp32")
+    return rate, sec / pc_steps_sample, sample, workers * threads
 
 
 def run_reference(args):
+    """CPU arm.  One bench step = one bounded sample: `cores // threads` groups side by side x S PC steps each; `ms_per_step` is the
+    measured wall time of that sample, `value` scales it to the 1000-step trajectory (every PC step costs the same: two score
+    evaluations of a static graph).  S = the whole trajectory when K steps of it fit a ~5 minute budget, else the largest
+    multiple of 50 that does; in that case the LAST warm-up step still runs one whole 1000-step trajectory and its rate is
+    reported beside the timed one (`full_trajectory`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    mols, _, _ = build_workload(min(args.molecules, 4), args.repeat, args.seed)
     model = make_model("cpu")
-    times = []
-    for i in range(args.warmup + args.steps):
-        rate, per_step, sample = cpu_reference_rate(mols, args.repeat, args.cpu_pc_steps, args.pc_steps, model.state_dict())
-        if i >= args.warmup:
-            times.append(per_step * args.pc_steps)  # seconds for `repeat` conformers, extrapolated
+    arm = CpuArm(args.repeat, model.state_dict(), args.seed)
+    try:
+        arm.run(4)  # page the workers in
+        sweep = {}
+        for th in sorted({1, 2, 4} & set(range(1, arm.cores + 1))):
+            sec, w, _ = arm.run(20, th)
+            sweep[th] = arm.rate(sec, w, 20, args.pc_steps)
+        threads = max(sweep, key=sweep.get)
+        sec, w, _ = arm.run(50, threads)
+        est_full = sec / 50 * args.cpu_pc_steps
+        budget = 300.0
+        S = args.cpu_pc_steps if est_full * args.steps <= budget else max(50, int(budget / args.steps / (sec / 50)) // 50 * 50)
+        full = None
+        for i in range(args.warmup):
+            if i == args.warmup - 1 and S < args.cpu_pc_steps:
+                sec, w, _ = arm.run(args.cpu_pc_steps, threads)
+                full = {"pc_steps": args.cpu_pc_steps, "seconds": sec, "value": arm.rate(sec, w, args.cpu_pc_steps, args.pc_steps)}
+            else:
+                arm.run(min(50, S), threads)
+        times = []
+        for _ in range(args.steps):
+            sec, w, atoms = arm.run(S, threads)
+            times.append(sec)
+    finally:
+        arm.close()
     t = float(np.mean(times))
-    value = args.repeat / t
-    cores = torch.get_num_threads()
+    value = arm.rate(t, w, S, args.pc_steps)
+    scale = "the whole trajectory" if S == args.pc_steps else f"scaled x{args.pc_steps / S:g} to {args.pc_steps} steps"
+    sample = (f"per bench step: {w} sampling groups in parallel ({w} processes x {threads} thread(s) on {arm.cores} host cores), each "
+              f"{S} predictor-corrector steps (2 score evals per step) of {args.repeat} conformers of one molecule ({atoms[0]}-{atoms[1]} "
+              f"atoms), {scale}; ms_per_step = measured wall time of that sample (slowest worker); thread sweep on 20 PC steps "
+              f"(conformers/s by threads per group): {({k: round(v, 2) for k, v in sweep.items()})}; oracle port (pure-torch restatement "
+              "of the reference), fp32")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": w * threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if full is not None:
+        line["cpu_baseline"]["full_trajectory"] = full
     print(json.dumps(line))
 
 
@@ -334,7 +408,7 @@ def run_b200(args):
         tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0  # derived: dense TF32 = bf16 / 2
         traffic = None
         try:  # dram bytes of one launch of this exact configuration, from an ncu capture committed under profiles/
-            tr = json.load(open(os.path.join(REPO, "profiles", "r1_pc_traffic.json")))
+            tr = json.load(open(os.path.join(REPO, "profiles", "r2_pc_traffic.json")))
             if tr.get("molecules") == args.molecules and tr.get("pc_steps") == args.pc_steps and tr.get("repeat") == args.repeat:
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
         except Exception:
@@ -354,9 +428,11 @@ def run_b200(args):
                                          else "fallback 1400/2"),
                          "note": "achieved = ALGORITHMIC FLOPs 2*(34,624 E_x + 24,576 N) per score eval x 2000 evals / kernel time. "
                                  "The kernel issues 3x that on the tensor pipe (two-way fp16 operand split, 3 product terms, for "
-                                 "fp32-grade accuracy): legacy mma.sync m16n8k16 for the edge/node tile GEMMs (measured 953 "
-                                 "MAC/clk/SM, profiles/r1_ubench_mma_rate.txt), tcgen05 3xTF32 for the basis MLP. traffic = ncu dram "
-                                 "bytes of one launch (v4 capture): node/edge state stays in shared memory for all 1000 steps."},
+                                 "fp32-grade accuracy), all of it as tcgen05.mma kind::f16 with TMEM accumulators (no mma.sync left: "
+                                 "profiles/r2_sass_pc_kernel.txt). traffic = ncu dram bytes of one launch of this build "
+                                 "(profiles/r2_pc_traffic.json): node/edge state stays in shared memory for all 1000 steps; the "
+                                 "remaining cost is MUFU (sin/cos/exp, 26% of active cycles), issue slots (45%) and barrier / "
+                                 "completion waits (profiles/r2_pc_ncu_full.txt, r2_pc_lines.txt)."},
             "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                              "note": "north_star's HBM view with the layer-granular algorithmic bytes of SURVEY 8(d): "
                                      "(156 N + 132 E_x + 4(N+1) + 266k) per eval + 48 N per step; small by construction (fused)"},
@@ -367,8 +443,8 @@ def run_b200(args):
         if pretrain is not None:
             line["pretrain"] = pretrain
         if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
-            rate, per_step, sample = cpu_reference_rate(mols, args.repeat, args.cpu_pc_steps, args.pc_steps, model.state_dict())
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+            rate, per_step, sample, used = cpu_reference_rate(args.repeat, args.cpu_pc_steps, args.pc_steps, model.state_dict(), args.seed)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": used, "kind": "port", "sample": sample}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
