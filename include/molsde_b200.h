@@ -248,6 +248,22 @@ int molsde_dense_pair_post(const float* m, const float* flags, int32_t B, int32_
 int molsde_dense_edge_final(const float* raw, const float* flags, const float* scale, int32_t B, int32_t Nm, float* out,
                             void* stream);
 
+/* Fused inference path of the edge score network (csrc/dense_fused.cu): channel-major stacks [B,C,Nm,Nm] end to end.
+ *  dense_attn_sym:  S[b,c,i,j] = (A_ij + A_ji)/2 of EdgeLayer (edge_network_dense.py:66-80); pairs with f_i f_j = 0 get 0;
+ *  dense_pair_mlp:  adjc_next[b,c',i,j] = ((m_ij + m_ji) f_j) f_i, m = MLP_elu(cat([S, adjc])[b,:,i,j]) (2Cin -> Hd -> Hd -> Co,
+ *                   :120-126); `symmetric` != 0 asserts bitwise-symmetric inputs (every layer but the first) and evaluates m once;
+ *  dense_edge_final_mlp: out[b,i,j] = MLP_silu(F -> H1 -> H2 -> 1)(all channels of the `nseg` stacks)[i,j] (i != j) f_i f_j scale[b]
+ *                   (invariant_scorenetwork_dense.py:84-93; get_score_fn :83,93).  seg_ptrs / seg_channels are HOST arrays. */
+int molsde_dense_attn_sym(const float* Q, const float* K, int64_t ldq, int32_t W, int32_t ds, const float* flags, int32_t B,
+                          int32_t C, int32_t Nm, float* S, void* stream);
+int molsde_dense_pair_mlp(const float* S, const float* adjc, const float* flags, const float* W0, const float* b0, const float* W1,
+                          const float* b1, const float* W2, const float* b2, int32_t B, int32_t Cin, int32_t Hd, int32_t Co,
+                          int32_t Nm, int32_t symmetric, float* adjc_next, void* stream);
+int molsde_dense_edge_final_mlp(const float* const* seg_ptrs, const int32_t* seg_channels, int32_t nseg, const float* flags,
+                                const float* scale, const float* W0, const float* b0, const float* W1, const float* b1,
+                                const float* W2, const float* b2, int32_t F, int32_t H1, int32_t H2, int32_t B, int32_t Nm, float* out,
+                                void* stream);
+
 /* perturbation prologue / loss epilogue of SDEModel3Dto2D_node_adj_dense.forward (:134-152,160-179) and the elementwise
  * steps of the 3D->2D PC sampler (examples/pretrain_MoleculeSDE_inference_3D_to_2D_VE_VP.py:167-252) */
 int molsde_dense_sym_noise(const float* raw, const float* flags, int32_t B, int32_t Nm, float* z, void* stream);

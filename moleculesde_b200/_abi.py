@@ -49,6 +49,7 @@ EXPORTS = [
     "molsde_dense_gcn", "molsde_dense_attn", "molsde_dense_pair_post", "molsde_dense_edge_final",
     "molsde_dense_sym_noise", "molsde_dense_perturb_adj", "molsde_dense_perturb_onehot", "molsde_graph_reduce",
     "molsde_langevin_step", "molsde_langevin_update", "molsde_reverse_update", "molsde_mask_rows",
+    "molsde_dense_attn_sym", "molsde_dense_pair_mlp", "molsde_dense_edge_final_mlp",
 ]
 
 
@@ -138,6 +139,11 @@ def lib() -> ctypes.CDLL:
     L.molsde_reverse_update.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p,
                                         c_void_p]
     L.molsde_mask_rows.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    L.molsde_dense_attn_sym.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                        c_void_p]
+    L.molsde_dense_pair_mlp.argtypes = [c_void_p] * 9 + [c_int32] * 6 + [c_void_p, c_void_p]
+    L.molsde_dense_edge_final_mlp.argtypes = [POINTER(c_void_p), POINTER(c_int32), c_int32] + [c_void_p] * 8 + [c_int32] * 5 + \
+                                             [c_void_p, c_void_p]
     L.molsde_schnet_cfconv.argtypes = [POINTER(Plan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int32, c_float, c_float, c_void_p, c_void_p]
     L.molsde_gather_rows.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]

@@ -101,9 +101,11 @@ pow2_kernel(const float* __restrict__ adj, int Nm, float* __restrict__ adjc, flo
         for (int k = 0; k < Nm; ++k) s = fmaf(A[r][k], A[k][c], s);
         o0[i] = A[r][c];
         o1[i] = s;
-        float* ac = allc + (static_cast<int64_t>(b) * Nm * Nm + i) * ld_all + all_off;
-        ac[0] = A[r][c];
-        ac[1] = s;
+        if (allc) {   // (NULL on the fused inference path: the head reads the channel-major stacks directly)
+            float* ac = allc + (static_cast<int64_t>(b) * Nm * Nm + i) * ld_all + all_off;
+            ac[0] = A[r][c];
+            ac[1] = s;
+        }
     }
 }
 
@@ -252,7 +254,7 @@ int molsde_grouped_linear(const float* X, int64_t rows, int64_t ldx, const float
 
 int molsde_dense_pow2(const float* adj, int32_t B, int32_t Nm, float* adjc, float* allc, int32_t ld_all, int32_t all_off,
                       void* stream) {
-    if (!adj || !adjc || !allc || B <= 0 || Nm <= 0) return MOLSDE_ERR_INVALID;
+    if (!adj || !adjc || B <= 0 || Nm <= 0) return MOLSDE_ERR_INVALID;
     if (Nm > DN_MAX) return MOLSDE_ERR_UNSUPPORTED;
     pow2_kernel<<<B, 256, 0, as_stream(stream)>>>(adj, Nm, adjc, allc, ld_all, all_off);
     return check_launch("dense_pow2");

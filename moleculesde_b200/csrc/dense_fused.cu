@@ -1,0 +1,323 @@
+// Fused inference kernels of the dense 3D->2D EDGE score network (sampling / get_score_fn path).
+//
+// Reference: layers/edge_network_dense.py:56-128 (EdgeLayer attention, EdgeNetwork_dense.forward) and
+// invariant_scorenetwork_dense.py:68-93 (EdgeScoreNetwork_dense.forward).  The layer-granular kernels of dense.cu +
+// mlp_rows.cu materialise, per layer, the channels-last pair tensor [B,Nm,Nm,2C] (written strided, read back by the
+// per-pair MLP), the MLP output [B*Nm^2, C'] and the all-channels buffer [B,Nm,Nm,30]: ~330 MB of HBM traffic and three
+// launches per layer for ~100 MB of algorithmic bytes.  Here every adjacency stack stays CHANNEL-MAJOR [B,C,Nm,Nm] (so
+// the thread of pair (i,j) reads and writes coalesced along j), and per layer there are two kernels:
+//   dense_attn_sym      S[b,c,i,j] = (A_ij + A_ji)/2,  A_ij = mean_h tanh(<q_c[i,h], k_c[j,h]>/sqrt(ds))      (:66-80)
+//   dense_pair_mlp      adjc'[b,c',i,j] = (m_ij + m_ji) f_i f_j,  m = MLP_elu([S | adjc][b,:,i,j])              (:120-126)
+// and one for the head:
+//   dense_edge_final_mlp  out[b,i,j] = MLP_silu(all channels of all layers)[i,j] (i != j) f_i f_j scale_b     (:84-93)
+// Pairs with f_i f_j = 0 (padding atoms) are skipped: their outputs are 0 whatever the MLP returns, and nothing else reads
+// their intermediates.  m_ji: the inputs of layers >= 1 are symmetric BITWISE by construction (S is symmetrised, adjc' of the
+// previous layer is (m_ij + m_ji) f f with commutative fp adds), so there m_ji == m_ij and `symmetric = 1` skips the second
+// evaluation; layer 0 sees adj, adj^2 of an arbitrary (in the reference's sampler: non-symmetric) adjacency and evaluates
+// the transposed pair too.  All math is fp32 FFMA with the weights broadcast from shared memory (rows are independent:
+// deterministic); activations use the SFU exp with a series branch near 0 (relative error ~1e-7).
+#include "common.cuh"
+
+namespace molsde {
+
+constexpr int DF_NM = 64;       // max padded atoms per graph
+constexpr int DF_K0 = 16;       // pair MLP: padded input width (2C <= 16)
+constexpr int DF_H = 16;        //           hidden width
+constexpr int DF_CO = 8;        //           padded output channels
+constexpr int DF_FK = 32;       // final MLP: padded input channels (fdim <= 32)
+constexpr int DF_FH = 64;       //            padded hidden width (2*fdim <= 64)
+constexpr int DF_MAX_SEGS = 6;
+
+__device__ __forceinline__ float df_tanh(float v) {
+    const float a = fabsf(v), v2 = v * v;
+    const float series = v * fmaf(v2, fmaf(v2, 2.0f / 15.0f, -1.0f / 3.0f), 1.0f);   // |v| < 0.1: next term 17 v^7/315 < 6e-9
+    const float e = __expf(-2.0f * a);
+    const float big = copysignf(__fdividef(1.0f - e, 1.0f + e), v);
+    return a < 0.1f ? series : big;
+}
+__device__ __forceinline__ float df_elu(float v) {
+    const float series = v * fmaf(v, fmaf(v, fmaf(v, 1.0f / 24.0f, 1.0f / 6.0f), 0.5f), 1.0f);
+    const float em1 = v > -0.1f ? series : __expf(v) - 1.0f;
+    return v > 0.0f ? v : em1;
+}
+__device__ __forceinline__ float df_silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+// ---------------------------------------------------------------------------------------
+// S[b,c,i,j]: grid (B, C), 256 threads.  Q, K: [B*Nm, ldq], channel c at columns c*W .. c*W+W-1 (W = H*ds <= 32, ds % 4 == 0)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dense_attn_sym_kernel(const float* __restrict__ Q, const float* __restrict__ K, int64_t ldq, int W, int ds,
+                      const float* __restrict__ flags, int C, int Nm, float* __restrict__ S) {
+    __shared__ __align__(16) float sQ[DF_NM][36], sK[DF_NM][36];   // 144 B rows: float4 aligned, conflict-free per quarter warp
+    __shared__ float sA[DF_NM][DF_NM + 1];
+    const int b = blockIdx.x, c = blockIdx.y, w4 = W >> 2;
+    for (int idx = threadIdx.x; idx < Nm * w4; idx += blockDim.x) {
+        const int r = idx / w4, k4 = idx % w4;
+        const int64_t g = (static_cast<int64_t>(b) * Nm + r) * ldq + c * W + 4 * k4;
+        *reinterpret_cast<float4*>(&sQ[r][4 * k4]) = __ldg(reinterpret_cast<const float4*>(Q + g));
+        *reinterpret_cast<float4*>(&sK[r][4 * k4]) = __ldg(reinterpret_cast<const float4*>(K + g));
+    }
+    __syncthreads();
+    const float* fl = flags + static_cast<int64_t>(b) * Nm;
+    const int H = W / ds, d4 = ds >> 2;
+    const float inv_sqrt = 1.0f / sqrtf(static_cast<float>(ds));
+    for (int p = threadIdx.x; p < Nm * Nm; p += blockDim.x) {
+        const int i = p / Nm, j = p % Nm;
+        float s = 0.0f;
+        if (fl[i] != 0.0f && fl[j] != 0.0f) {
+            const float4* q = reinterpret_cast<const float4*>(sQ[i]);
+            const float4* k = reinterpret_cast<const float4*>(sK[j]);
+            for (int h = 0; h < H; ++h) {
+                float d = 0.0f;
+                for (int kk = 0; kk < d4; ++kk) {
+                    const float4 a = q[h * d4 + kk], bb = k[h * d4 + kk];
+                    d = fmaf(a.x, bb.x, d); d = fmaf(a.y, bb.y, d); d = fmaf(a.z, bb.z, d); d = fmaf(a.w, bb.w, d);
+                }
+                s += df_tanh(d * inv_sqrt);
+            }
+            s = s / static_cast<float>(H);
+        }
+        sA[i][j] = s;
+    }
+    __syncthreads();
+    float* out = S + (static_cast<int64_t>(b) * C + c) * Nm * Nm;
+    for (int p = threadIdx.x; p < Nm * Nm; p += blockDim.x) {
+        const int i = p / Nm, j = p % Nm;
+        out[p] = (sA[i][j] + sA[j][i]) * 0.5f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// per-pair MLP (2C -> H -> H -> C', elu) + symmetrise + mask; thread = ordered pair (i, j) of graph blockIdx.y
+// ---------------------------------------------------------------------------------------
+struct PairMlpSmem {   // k-major weights: every input k streams one row of 16 (8) output weights as broadcast float4 loads
+    float W0[DF_K0][DF_H], W1[DF_H][DF_H], W2[DF_H][DF_CO], b0[DF_H], b1[DF_H], b2[DF_CO];
+};
+template <int K, int N>
+__device__ __forceinline__ void df_layer(const float* __restrict__ Wk, const float* __restrict__ bias, const float (&x)[K], float (&y)[N]) {
+#pragma unroll
+    for (int o = 0; o < N; ++o) y[o] = bias[o];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float4* w = reinterpret_cast<const float4*>(Wk + k * N);
+#pragma unroll
+        for (int o4 = 0; o4 < N / 4; ++o4) {
+            const float4 ww = w[o4];
+            y[4 * o4] = fmaf(x[k], ww.x, y[4 * o4]); y[4 * o4 + 1] = fmaf(x[k], ww.y, y[4 * o4 + 1]);
+            y[4 * o4 + 2] = fmaf(x[k], ww.z, y[4 * o4 + 2]); y[4 * o4 + 3] = fmaf(x[k], ww.w, y[4 * o4 + 3]);
+        }
+    }
+}
+__device__ __forceinline__ void pair_mlp_eval(const PairMlpSmem& P, const float (&x)[DF_K0], float (&y)[DF_CO]) {
+    float h1[DF_H], h2[DF_H];
+    df_layer<DF_K0, DF_H>(&P.W0[0][0], P.b0, x, h1);
+#pragma unroll
+    for (int o = 0; o < DF_H; ++o) h1[o] = df_elu(h1[o]);
+    df_layer<DF_H, DF_H>(&P.W1[0][0], P.b1, h1, h2);
+#pragma unroll
+    for (int o = 0; o < DF_H; ++o) h2[o] = df_elu(h2[o]);
+    df_layer<DF_H, DF_CO>(&P.W2[0][0], P.b2, h2, y);
+}
+
+__global__ void __launch_bounds__(256, 2)
+dense_pair_mlp_kernel(const float* __restrict__ S, const float* __restrict__ adjc, const float* __restrict__ flags,
+                      const float* __restrict__ W0, const float* __restrict__ b0, const float* __restrict__ W1,
+                      const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2, int Cin, int Hd,
+                      int Co, int Nm, int symmetric, float* __restrict__ adjc_next) {
+    __shared__ __align__(16) PairMlpSmem P;
+    const int K0 = 2 * Cin;
+    for (int i = threadIdx.x; i < DF_K0 * DF_H; i += blockDim.x) {
+        const int k = i / DF_H, o = i % DF_H;
+        P.W0[k][o] = (o < Hd && k < K0) ? W0[o * K0 + k] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < DF_H * DF_H; i += blockDim.x) {
+        const int k = i / DF_H, o = i % DF_H;
+        P.W1[k][o] = (o < Hd && k < Hd) ? W1[o * Hd + k] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < DF_H * DF_CO; i += blockDim.x) {
+        const int k = i / DF_CO, o = i % DF_CO;
+        P.W2[k][o] = (o < Co && k < Hd) ? W2[o * Hd + k] : 0.0f;
+    }
+    if (threadIdx.x < DF_H) {
+        P.b0[threadIdx.x] = threadIdx.x < Hd ? b0[threadIdx.x] : 0.0f;
+        P.b1[threadIdx.x] = threadIdx.x < Hd ? b1[threadIdx.x] : 0.0f;
+    }
+    if (threadIdx.x < DF_CO) P.b2[threadIdx.x] = threadIdx.x < Co ? b2[threadIdx.x] : 0.0f;
+    __syncthreads();
+    const int NN = Nm * Nm, b = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= NN) return;
+    const int i = p / Nm, j = p % Nm;
+    const float fi = flags[b * Nm + i], fj = flags[b * Nm + j];
+    float* out = adjc_next + static_cast<int64_t>(b) * Co * NN + p;
+    if (fi == 0.0f || fj == 0.0f) {
+        for (int c = 0; c < Co; ++c) out[static_cast<int64_t>(c) * NN] = 0.0f;
+        return;
+    }
+    const float* Sb = S + static_cast<int64_t>(b) * Cin * NN;
+    const float* Ab = adjc + static_cast<int64_t>(b) * Cin * NN;
+    float x[DF_K0], y[DF_CO], yt[DF_CO];
+#pragma unroll
+    for (int k = 0; k < DF_K0; ++k) x[k] = 0.0f;
+#pragma unroll
+    for (int c = 0; c < DF_K0 / 2; ++c)
+        if (c < Cin) { x[c] = __ldg(Sb + c * NN + p); }
+    // (the adjacency half sits at columns Cin .. 2Cin-1 of the reference's cat([A, adj]), :120)
+    if (Cin == DF_K0 / 2) {
+#pragma unroll
+        for (int c = 0; c < DF_K0 / 2; ++c) x[DF_K0 / 2 + c] = __ldg(Ab + c * NN + p);
+    } else {   // Cin == 2 (first layer): columns 2, 3
+        x[2] = __ldg(Ab + p);
+        x[3] = __ldg(Ab + NN + p);
+    }
+    pair_mlp_eval(P, x, y);
+    if (symmetric || i == j) {
+#pragma unroll
+        for (int c = 0; c < DF_CO; ++c) yt[c] = y[c];
+    } else {
+        const int pt = j * Nm + i;
+        if (Cin == DF_K0 / 2) {
+#pragma unroll
+            for (int c = 0; c < DF_K0 / 2; ++c) x[DF_K0 / 2 + c] = __ldg(Ab + c * NN + pt);
+        } else {
+            x[2] = __ldg(Ab + pt);
+            x[3] = __ldg(Ab + NN + pt);
+        }
+        pair_mlp_eval(P, x, yt);   // (S is symmetric by construction: only the adjacency half changes)
+    }
+#pragma unroll
+    for (int c = 0; c < DF_CO; ++c)
+        if (c < Co) out[static_cast<int64_t>(c) * NN] = ((y[c] + yt[c]) * fj) * fi;   // pair_post order (:124-126)
+}
+
+// ---------------------------------------------------------------------------------------
+// final head: MLP_silu(fdim -> H1 -> H2 -> 1) over the channels of all adjacency stacks, zero diagonal, mask, scale
+// ---------------------------------------------------------------------------------------
+struct DenseSegs {
+    const float* ptr[DF_MAX_SEGS];   // [B, ch, Nm, Nm] each
+    int ch[DF_MAX_SEGS];
+    int n;
+};
+
+__global__ void __launch_bounds__(256, 2)
+dense_edge_final_mlp_kernel(DenseSegs segs, const float* __restrict__ flags, const float* __restrict__ scale,
+                            const float* __restrict__ W0, const float* __restrict__ b0, const float* __restrict__ W1,
+                            const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2, int F, int H1,
+                            int H2, int Nm, float* __restrict__ out) {
+    extern __shared__ __align__(16) float fsm[];
+    float* W0k = fsm;                         // [DF_FK k][DF_FH o]   k-major
+    float* W1k = W0k + DF_FK * DF_FH;         // [DF_FH k][DF_FH o]
+    float* b0s = W1k + DF_FH * DF_FH;         // [DF_FH]
+    float* b1s = b0s + DF_FH;
+    float* w2s = b1s + DF_FH;
+    for (int i = threadIdx.x; i < DF_FK * DF_FH; i += blockDim.x) {
+        const int k = i / DF_FH, o = i % DF_FH;
+        W0k[i] = (k < F && o < H1) ? W0[o * F + k] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < DF_FH * DF_FH; i += blockDim.x) {
+        const int k = i / DF_FH, o = i % DF_FH;
+        W1k[i] = (k < H1 && o < H2) ? W1[o * H1 + k] : 0.0f;
+    }
+    if (threadIdx.x < DF_FH) {
+        b0s[threadIdx.x] = threadIdx.x < H1 ? b0[threadIdx.x] : 0.0f;
+        b1s[threadIdx.x] = threadIdx.x < H2 ? b1[threadIdx.x] : 0.0f;
+        w2s[threadIdx.x] = threadIdx.x < H2 ? W2[threadIdx.x] : 0.0f;
+    }
+    __syncthreads();
+    const int NN = Nm * Nm, b = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= NN) return;
+    const int i = p / Nm, j = p % Nm;
+    const float fi = flags[b * Nm + i], fj = flags[b * Nm + j];
+    float* o = out + static_cast<int64_t>(b) * NN + p;
+    if (i == j || fi == 0.0f || fj == 0.0f) { *o = 0.0f; return; }
+    float h1[DF_FH];
+#pragma unroll
+    for (int q = 0; q < DF_FH; ++q) h1[q] = b0s[q];
+    int k = 0;
+    for (int s = 0; s < segs.n; ++s) {
+        const float* base = segs.ptr[s] + static_cast<int64_t>(b) * segs.ch[s] * NN + p;
+        for (int c = 0; c < segs.ch[s]; ++c, ++k) {
+            const float xk = __ldg(base + static_cast<int64_t>(c) * NN);
+            const float4* w = reinterpret_cast<const float4*>(W0k + k * DF_FH);
+#pragma unroll
+            for (int q4 = 0; q4 < DF_FH / 4; ++q4) {
+                const float4 ww = w[q4];
+                h1[4 * q4] = fmaf(xk, ww.x, h1[4 * q4]); h1[4 * q4 + 1] = fmaf(xk, ww.y, h1[4 * q4 + 1]);
+                h1[4 * q4 + 2] = fmaf(xk, ww.z, h1[4 * q4 + 2]); h1[4 * q4 + 3] = fmaf(xk, ww.w, h1[4 * q4 + 3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < DF_FH; ++q) h1[q] = df_silu(h1[q]);   // (padded units: silu(0) = 0)
+    float r = b2[0];
+#pragma unroll 1
+    for (int oc = 0; oc < DF_FH / 16; ++oc) {
+        float acc[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[q] = b1s[16 * oc + q];
+#pragma unroll
+        for (int kk = 0; kk < DF_FH; ++kk) {
+            const float4* w = reinterpret_cast<const float4*>(W1k + kk * DF_FH + 16 * oc);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 ww = w[q4];
+                acc[4 * q4] = fmaf(h1[kk], ww.x, acc[4 * q4]); acc[4 * q4 + 1] = fmaf(h1[kk], ww.y, acc[4 * q4 + 1]);
+                acc[4 * q4 + 2] = fmaf(h1[kk], ww.z, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(h1[kk], ww.w, acc[4 * q4 + 3]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) r = fmaf(df_silu(acc[q]), w2s[16 * oc + q], r);
+    }
+    float v = (r * fi) * fj;                       // edge_final order: (raw * f_i) * f_j, then the per-graph scale
+    *o = scale ? v * scale[b] : v;
+}
+
+}  // namespace molsde
+
+using namespace molsde;
+
+extern "C" {
+
+int molsde_dense_attn_sym(const float* Q, const float* K, int64_t ldq, int32_t W, int32_t ds, const float* flags, int32_t B,
+                          int32_t C, int32_t Nm, float* S, void* stream) {
+    if (!Q || !K || !flags || !S || B <= 0 || C <= 0 || Nm <= 0 || W <= 0 || ds <= 0 || W % ds) return MOLSDE_ERR_INVALID;
+    if (Nm > DF_NM || W > 32 || (ds & 3) || (ldq & 3) || (reinterpret_cast<uintptr_t>(Q) & 15) || (reinterpret_cast<uintptr_t>(K) & 15))
+        return MOLSDE_ERR_UNSUPPORTED;
+    dense_attn_sym_kernel<<<dim3(B, C), 256, 0, as_stream(stream)>>>(Q, K, ldq, W, ds, flags, C, Nm, S);
+    return check_launch("dense_attn_sym");
+}
+
+int molsde_dense_pair_mlp(const float* S, const float* adjc, const float* flags, const float* W0, const float* b0, const float* W1,
+                          const float* b1, const float* W2, const float* b2, int32_t B, int32_t Cin, int32_t Hd, int32_t Co,
+                          int32_t Nm, int32_t symmetric, float* adjc_next, void* stream) {
+    if (!S || !adjc || !flags || !W0 || !b0 || !W1 || !b1 || !W2 || !b2 || !adjc_next || B <= 0 || Nm <= 0) return MOLSDE_ERR_INVALID;
+    if (Nm > DF_NM || (Cin != 2 && Cin != DF_K0 / 2) || Hd < 1 || Hd > DF_H || Co < 1 || Co > DF_CO) return MOLSDE_ERR_UNSUPPORTED;
+    dense_pair_mlp_kernel<<<dim3((Nm * Nm + 255) / 256, B), 256, 0, as_stream(stream)>>>(S, adjc, flags, W0, b0, W1, b1, W2, b2, Cin, Hd,
+                                                                                      Co, Nm, symmetric, adjc_next);
+    return check_launch("dense_pair_mlp");
+}
+
+int molsde_dense_edge_final_mlp(const float* const* seg_ptrs, const int32_t* seg_channels, int32_t nseg, const float* flags,
+                                const float* scale, const float* W0, const float* b0, const float* W1, const float* b1,
+                                const float* W2, const float* b2, int32_t F, int32_t H1, int32_t H2, int32_t B, int32_t Nm, float* out,
+                                void* stream) {
+    if (!seg_ptrs || !seg_channels || !flags || !W0 || !b0 || !W1 || !b1 || !W2 || !b2 || !out || B <= 0 || Nm <= 0) return MOLSDE_ERR_INVALID;
+    if (nseg < 1 || nseg > DF_MAX_SEGS || Nm > DF_NM || F > DF_FK || H1 > DF_FH || H2 > DF_FH) return MOLSDE_ERR_UNSUPPORTED;
+    DenseSegs segs;
+    int tot = 0;
+    for (int s = 0; s < DF_MAX_SEGS; ++s) {
+        segs.ptr[s] = s < nseg ? seg_ptrs[s] : nullptr;
+        segs.ch[s] = s < nseg ? seg_channels[s] : 0;
+        if (s < nseg && (!seg_ptrs[s] || seg_channels[s] < 1)) return MOLSDE_ERR_INVALID;
+        tot += segs.ch[s];
+    }
+    segs.n = nseg;
+    if (tot != F) return MOLSDE_ERR_INVALID;
+    const size_t smem = sizeof(float) * (DF_FK * DF_FH + DF_FH * DF_FH + 3 * DF_FH);
+    dense_edge_final_mlp_kernel<<<dim3((Nm * Nm + 255) / 256, B), 256, smem, as_stream(stream)>>>(segs, flags, scale, W0, b0, W1, b1, W2, b2, F,
+                                                                                               H1, H2, Nm, out);
+    return check_launch("dense_edge_final_mlp");
+}
+
+}  // extern "C"

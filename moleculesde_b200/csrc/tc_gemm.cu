@@ -17,6 +17,7 @@
 //     drained with tcgen05.ld into fp32 registers (warp w owns lanes 32*(w%4).., warps 0-3 / 4-7 split the columns);
 //     the epilogue applies bias / rowscale / activation / residual and stores, or writes a raw split-K partial.
 #include "common.cuh"
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 
 namespace molsde {
@@ -65,6 +66,8 @@ __device__ __forceinline__ float tc_act(float v, int act) {
         default: return v;
     }
 }
+
+__device__ __noinline__ float tc_act_call(float v, int act) { return tc_act(v, act); }   // (keeps unrolled epilogues small)
 
 // Staging of one [R x 32] K block of an operand in two phases so that the global-memory latency overlaps the tensor-core
 // work of the previous block:  tc_load (all loads of the block issued back to back into registers)  ->  ...  ->
@@ -328,6 +331,246 @@ __global__ void tc_splitk_reduce_simple_kernel(const float* __restrict__ ws, int
     *c = accumulate ? *c + t : t;
 }
 
+// =======================================================================================
+// TMA-fed variant (plain y = x W^T shapes: both operands K-contiguous, 16-byte aligned rows, no split-K / batch / ones row).
+//   * raw fp32 operand tiles [128 x 32] / [BN x 32] arrive by TMA (cp.async.bulk.tensor.2d, tensor maps encoded on the host
+//     with SWIZZLE_128B, out-of-bounds rows / K tail zero-filled by the hardware) into a 3-stage ring, completion on mbarriers;
+//   * 256 converter threads derive the lo tile IN THE SWIZZLED LAYOUT: the split is elementwise, so a thread reads a float4 at
+//     byte offset o of the raw tile and writes lo = v - trunc19(v) at offset o of the lo tile -- no address math, no layout
+//     transform, conflict-free 16-byte accesses; the raw tile IS the hi operand (kind::tf32 ignores the 13 low mantissa bits);
+//   * one thread issues the 12 tcgen05.mma (M = 128, N = BN = 128: the full-rate tf32 shape) per K block against
+//     SWIZZLE_128B K-major descriptors (8-row groups 1024 B apart, K step = +32 B on the start address) and commits to the
+//     stage's "empty" mbarrier, which gates the TMA refill of that stage; accumulator drains as in the kernel above.
+// =======================================================================================
+constexpr int TT_STAGES = 3;
+constexpr uint32_t TT_A_BYTES = TC_BM * 128;   // [128 rows][32 floats]
+
+__device__ __forceinline__ uint64_t tt_desc(uint32_t saddr) {   // K-major, SWIZZLE_128B: LBO unused (1), SBO = 1024 B
+    return static_cast<uint64_t>((saddr & 0x3FFFF) >> 4) | (static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+           (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+}
+__device__ __forceinline__ void tt_tma_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+// raw tile -> lo tile (`n16` 16-byte chunks, all 256 converter threads).  The raw tile itself serves as the hi operand: kind::tf32
+// reads the top 19 bits of every fp32 container and ignores the 13 low mantissa bits, i.e. the tensor core sees exactly
+// hi = v & 0xFFFFE000 (checked against fp64 to 5e-6 in tests/test_gpu_tcgemm.py: a rounding read would show up as ~2e-4).
+__device__ __forceinline__ void tt_split(const uint8_t* raw, uint8_t* lo, int n16) {
+    for (int i = threadIdx.x; i < n16; i += TC_THREADS) {
+        const float4 v = *reinterpret_cast<const float4*>(raw + i * 16);
+        float4 l;
+        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        *reinterpret_cast<float4*>(lo + i * 16) = l;
+    }
+}
+
+constexpr int TT_THREADS = TC_THREADS + 32;   // 8 converter / epilogue warps + 1 control warp (TMA producer + MMA issuer)
+
+template <int BN>
+__global__ void __launch_bounds__(TT_THREADS, 1)
+tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    extern __shared__ uint8_t tt_smem_raw[];
+    constexpr uint32_t B_BYTES = BN * 128, STAGE = 2 * (TT_A_BYTES + B_BYTES);
+    __shared__ uint64_t full[TT_STAGES], ready[TT_STAGES], empty[TT_STAGES];   // TMA landed | hi/lo written (256 arrivals) | MMAs done
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* tiles = tt_smem_raw + ((1024u - (tc_smem_u32(tt_smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms: 1024-byte aligned
+    const int64_t m0 = static_cast<int64_t>(blockIdx.y) * TC_BM, n0 = static_cast<int64_t>(blockIdx.x) * BN;
+    const int nkb = static_cast<int>((a.K + TC_BK - 1) / TC_BK);
+    if (tid == 0) {
+        for (int s = 0; s < TT_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&ready[s])), "r"(TC_THREADS));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&empty[s])));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)), "r"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    bool ok = true;
+    constexpr int HALF = BN / 2;
+    const int cbase = ((warp >> 2) & 1) * HALF;
+    float accr[HALF];
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) accr[j] = 0.0f;
+
+    if (warp == TC_THREADS / 32) {
+        // ---------------- control warp: one thread feeds the ring by TMA and issues the tensor-core work ----------------
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+            auto issue_tma = [&](int kb) {
+                const int s = kb % TT_STAGES;
+                const uint32_t st = tc_smem_u32(tiles) + s * STAGE, bar = tc_smem_u32(&full[s]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TT_A_BYTES + B_BYTES) : "memory");
+                tt_tma_2d(st, &tmA, kb * TC_BK, static_cast<int>(m0), bar);
+                tt_tma_2d(st + 2 * TT_A_BYTES, &tmB, kb * TC_BK, static_cast<int>(n0), bar);
+            };
+            for (int kb = 0; kb < TT_STAGES && kb < nkb; ++kb) issue_tma(kb);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % TT_STAGES;
+                const uint32_t ph = static_cast<uint32_t>(kb / TT_STAGES) & 1u;
+                ok &= tc_wait(tc_smem_u32(&ready[s]), ph);   // hi / lo tiles of block kb written by all converter threads
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ah = tc_smem_u32(tiles) + s * STAGE, al = ah + TT_A_BYTES, bh = al + TT_A_BYTES, bl = bh + B_BYTES;
+                uint32_t acc = (kb % TC_FLUSH) > 0 ? 1u : 0u;
+#pragma unroll 1
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t pa = (term == 0) ? al : ah, pb = (term == 1) ? bl : bh;
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                        tc_mma<BN>(tmem, tt_desc(pa + ks * 32), tt_desc(pb + ks * 32), acc);
+                        acc = 1u;
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&empty[s]))
+                             : "memory");
+                // refill the stage of the previous block (its MMAs were issued one block ago) with block kb - 1 + STAGES
+                if (kb >= 1 && kb - 1 + TT_STAGES < nkb) {
+                    ok &= tc_wait(tc_smem_u32(&empty[(kb - 1) % TT_STAGES]), static_cast<uint32_t>((kb - 1) / TT_STAGES) & 1u);
+                    issue_tma(kb - 1 + TT_STAGES);
+                }
+            }
+        }
+    } else {
+        // ---------------- converter warps: raw tile -> hi (in place) + lo, then arrive; drain TMEM at the flush points ----------------
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % TT_STAGES;
+            const uint32_t ph = static_cast<uint32_t>(kb / TT_STAGES) & 1u;
+            uint8_t* st = tiles + s * STAGE;
+            ok &= tc_wait(tc_smem_u32(&full[s]), ph);
+            tt_split(st, st + TT_A_BYTES, TT_A_BYTES / 16);
+            tt_split(st + 2 * TT_A_BYTES, st + 2 * TT_A_BYTES + B_BYTES, B_BYTES / 16);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // (orders an earlier TMEM drain before the next MMAs)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&ready[s])) : "memory");
+            if ((kb + 1) % TC_FLUSH == 0 || kb == nkb - 1) {
+                ok &= tc_wait(tc_smem_u32(&empty[s]), ph);   // this commit covers every MMA issued so far
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int c0 = 0; c0 < HALF; c0 += 16) {
+                    uint32_t r[16];
+                    const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(cbase + c0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) accr[c0 + j] += __uint_as_float(r[j]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+        }
+    }
+    if (!ok && a.status) *a.status = 1;
+    // ---- epilogue: the thread of output row r holds HALF columns in registers -> bias / rowscale / activation there -> staged
+    // through shared memory (the operand ring is idle: every TMA landed, every MMA completed) -> written out by whole rows, one
+    // coalesced 512-byte store per warp and row (residual / accumulate are read the same way).
+    if (warp < TC_THREADS / 32) {
+        constexpr int LDS = BN + 4;                          // 528-byte rows: the 16-byte row-segment stores of a quarter warp hit 8 bank groups
+        float* stage = reinterpret_cast<float*>(tiles);      // [128][LDS] floats = 66 KB of the 192 KB ring
+        const int r = 32 * (warp & 3) + lane;
+        const int64_t gm = m0 + r;
+        const float rs = (a.rowscale && gm < a.M) ? a.rowscale[gm] : 1.0f;
+        const bool slow_act = a.act >= 2;
+#pragma unroll
+        for (int j = 0; j < HALF; j += 4) {
+            float4 o;
+            float* ov = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t gn = n0 + cbase + j + q;
+                float v = accr[j + q];
+                if (a.bias && gn < a.N) v += a.bias[gn];
+                if (a.rowscale) v *= rs;
+                ov[q] = slow_act ? tc_act_call(v, a.act) : (a.act == 1 ? fmaxf(v, 0.0f) : v);
+            }
+            *reinterpret_cast<float4*>(stage + r * LDS + cbase + j) = o;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");
+        const int ncols = static_cast<int>(min(static_cast<int64_t>(BN), a.N - n0));
+        for (int rr = warp; rr < TC_BM; rr += TC_THREADS / 32) {
+            const int64_t row = m0 + rr;
+            if (row >= a.M) break;
+            float* c = a.C + row * a.ldc + n0;
+            const float* res = a.R ? a.R + row * a.ldr + n0 : nullptr;
+            if (a.vecC && !a.R && !a.accumulate && 4 * lane + 3 < ncols) {
+                *reinterpret_cast<float4*>(c + 4 * lane) = *reinterpret_cast<const float4*>(stage + rr * LDS + 4 * lane);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int col = 32 * q + lane;           // lanes along the columns: coalesced scalar accesses
+                    if (col >= ncols) continue;
+                    float v = stage[rr * LDS + col];
+                    if (res) v += res[col];
+                    c[col] = a.accumulate ? c[col] + v : v;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN));
+}
+
+typedef CUresult (*tt_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+static tt_encode_fn tt_encoder() {
+    static tt_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tt_encode_fn>(p);
+    }
+    return fn;
+}
+// [rows x K] fp32, K contiguous, row stride ld floats -> tensor map with a [box_rows x 32] box, 128-byte swizzle, zero fill
+static bool tt_make_map(CUtensorMap* tm, const float* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+    tt_encode_fn enc = tt_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+    const cuuint32_t box[2] = {TC_BK, static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool tt_eligible(const TcArgs& a, int splits) {
+    static const bool off = getenv("MOLSDE_TC_NO_TMA") != nullptr;
+    return !off && splits == 1 && a.batch == 1 && !a.colsum && a.sak == 1 && a.sbk == 1 && a.sam % 4 == 0 && a.sbn % 4 == 0 &&
+           (reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0 && a.N > 64 && a.M >= 256 &&
+           a.K >= 64 && a.M < (1ll << 31) && a.N < (1ll << 31) && a.K < (1ll << 31);
+}
+static int tt_launch(const TcArgs& a, cudaStream_t s) {
+    constexpr int BN = 128;
+    constexpr size_t smem = TT_STAGES * 2 * (TT_A_BYTES + BN * 128) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return MOLSDE_ERR_CUDA; }
+        configured = true;
+    }
+    CUtensorMap tmA, tmB;
+    if (!tt_make_map(&tmA, a.A, a.M, a.K, a.sam, TC_BM) || !tt_make_map(&tmB, a.B, a.N, a.K, a.sbn, BN)) return -1000;  // caller falls back
+    dim3 grid(static_cast<unsigned>((a.N + BN - 1) / BN), static_cast<unsigned>((a.M + TC_BM - 1) / TC_BM), 1);
+    tc_gemm_tma_kernel<BN><<<grid, TT_THREADS, smem, s>>>(tmA, tmB, a);
+    return check_launch("tc_gemm_tma");
+}
+
 template <int BN>
 static int tc_launch(const TcArgs& a, int splits, cudaStream_t s) {
     constexpr size_t smem = 2 * (2 * tc_tile_floats<TC_BM>() + 2 * tc_tile_floats<BN>()) * sizeof(float);
@@ -394,6 +637,10 @@ static int tc_run(int32_t batch, int64_t M, int64_t N, int64_t K, const float* A
     a.vecB = (sbk == 1 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && sbn % 4 == 0 && bsB % 4 == 0) ? 1 : 0;
     a.vecC = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0 && bsC % 4 == 0) ? 1 : 0;
     cudaStream_t s = as_stream(stream);
+    if (tt_eligible(a, splits)) {
+        const int st_tma = tt_launch(a, s);
+        if (st_tma != -1000) return st_tma;
+    }
     const int bn = tc_bn(a.Nx);
     int st = bn == 32 ? tc_launch<32>(a, splits, s) : bn == 64 ? tc_launch<64>(a, splits, s) : tc_launch<128>(a, splits, s);
     if (st != MOLSDE_OK || splits == 1) return st;

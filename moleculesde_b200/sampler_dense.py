@@ -1,6 +1,7 @@
 """3D->2D predictor-corrector sampler over (x, adj) with the reference's interface
-(`examples/pretrain_MoleculeSDE_inference_3D_to_2D_VE_VP.py:95-252`).  Host-driven loop this round:
-every score-network evaluation and every elementwise update is a kernel of `csrc/dense.cu`.
+(`examples/pretrain_MoleculeSDE_inference_3D_to_2D_VE_VP.py:95-252`).  Every score-network evaluation and every
+elementwise update is a kernel of `csrc/dense.cu` / `tc_gemm.cu` / `mlp_rows.cu`; one predictor-corrector step is captured in a
+CUDA graph and replayed per step (`node_adj_PC_generation(use_graph=...)`), the eager loop stays for injected draws.
 """
 from __future__ import annotations
 
@@ -17,7 +18,7 @@ def _per_graph_consts(sde, t):
     _, G = sde.discretize(torch.zeros(t.numel(), 1, 1, device=t.device), t)
     if hasattr(sde, "alphas"):
         ts = (t * (sde.N - 1) / sde.T).long()
-        sa = torch.sqrt(sde.alphas.to(t.device)[ts])
+        sa = torch.sqrt(sde._on("alphas", t.device)[ts])
     else:
         sa = torch.ones_like(t)
     return sa.float().contiguous(), G.float().contiguous()
@@ -33,8 +34,11 @@ class ReverseDiffusionPredictor:
         self.rsde = sde.reverse(score_fn, probability_flow)
 
     @torch.no_grad()
-    def update_fn(self, representation, x, adj, flags, t, raw_noise=None):
-        emb = self.SDE_model.embed(representation, x)
+    def update_fn(self, representation, x, adj, flags, t, raw_noise=None, emb=None):
+        """`emb` (keyword extension): `SDE_model.embed(representation, x)` when the caller already has it -- the adjacency and
+        the node update of one half-step embed the same (representation, x)."""
+        if emb is None:
+            emb = self.SDE_model.embed(representation, x)
         score = self.score_fn(emb, adj, flags, t)
         cur = adj if self.obj == "adj" else x
         z = gen_noise(cur, flags, sym=(self.obj == "adj"), raw=raw_noise)
@@ -56,8 +60,9 @@ class LangevinCorrector:
         self.snr, self.scale_eps, self.n_steps = snr, scale_eps, n_steps
 
     @torch.no_grad()
-    def update_fn(self, representation, x, adj, flags, t, raw_noise=None):
-        emb = self.SDE_model.embed(representation, x)
+    def update_fn(self, representation, x, adj, flags, t, raw_noise=None, emb=None):
+        if emb is None:
+            emb = self.SDE_model.embed(representation, x)
         cur = (adj if self.obj == "adj" else x).contiguous()
         B = cur.size(0)
         M = cur.numel() // B
@@ -79,10 +84,14 @@ class LangevinCorrector:
 @torch.no_grad()
 def node_adj_PC_generation(representation, data, SDE_model, B, max_num_nodes, num_class_X, probability_flow=False,
                            eps=1e-4, snr=0.2, scale_eps=0.9, n_steps=1, *, x_init=None, adj_init=None,
-                           draws: Optional[Callable[[str, int], torch.Tensor]] = None, diffusion_steps: Optional[int] = None):
+                           draws: Optional[Callable[[str, int], torch.Tensor]] = None, diffusion_steps: Optional[int] = None,
+                           use_graph: Optional[bool] = None):
     """Reference signature (`:95-101`).  Keyword-only extensions: `x_init` / `adj_init` inject the prior draws,
     `draws(kind, step)` with kind in {'c_adj','c_x','p_adj','p_x'} injects the raw `randn_like` of each update,
-    `diffusion_steps` truncates the `linspace(T, eps, N)` grid."""
+    `diffusion_steps` truncates the `linspace(T, eps, N)` grid, `use_graph` (default: on when no draws are injected) captures
+    ONE predictor-corrector step -- four score-network evaluations + the four state updates, ~170 kernels -- in a CUDA graph
+    over static state buffers and replays it for every step (the step's time comes from a device-side counter), so a
+    trajectory costs one graph launch per step instead of ~230 host launches."""
     require_device(representation)
     dev = representation.device
     sde_x, sde_adj = SDE_model.sde_x, SDE_model.sde_adj
@@ -104,14 +113,59 @@ def node_adj_PC_generation(representation, data, SDE_model, B, max_num_nodes, nu
     N = sde_adj.N
     steps = N if diffusion_steps is None else diffusion_steps
     timesteps = torch.linspace(sde_adj.T, eps, N, device=dev)
-    x_mean, adj_mean = x, adj
     get = (lambda k, i: None) if draws is None else draws
-    for i in range(steps):
-        vec_t = torch.ones(B, device=dev) * timesteps[i]
-        _x, _adj = x, adj
-        adj, adj_mean = corr_adj.update_fn(representation, _x, _adj, flags, vec_t, get("c_adj", i))
-        x, x_mean = corr_x.update_fn(representation, _x, _adj, flags, vec_t, get("c_x", i))
-        _x, _adj = x, adj
-        adj, adj_mean = pred_adj.update_fn(representation, _x, _adj, flags, vec_t, get("p_adj", i))
-        x, x_mean = pred_x.update_fn(representation, _x, _adj, flags, vec_t, get("p_x", i))
-    return x, adj, x_mean, adj_mean
+    # embedding_3D(representation) does not depend on the state: evaluated once per trajectory (the reference recomputes the
+    # same values inside every one of its 4 x N_steps embeds, `:228,240`)
+    rep3d = SDE_model.embed_3d(representation)
+
+    def pc_step(x, adj, vec_t, i):
+        """one iteration of the reference loop (`:134-147`)"""
+        emb = SDE_model.embed(representation, x, rep3d=rep3d)
+        adj1, _ = corr_adj.update_fn(representation, x, adj, flags, vec_t, get("c_adj", i), emb=emb)
+        x1, _ = corr_x.update_fn(representation, x, adj, flags, vec_t, get("c_x", i), emb=emb)
+        emb = SDE_model.embed(representation, x1, rep3d=rep3d)
+        adj2, adj_mean = pred_adj.update_fn(representation, x1, adj1, flags, vec_t, get("p_adj", i), emb=emb)
+        x2, x_mean = pred_x.update_fn(representation, x1, adj1, flags, vec_t, get("p_x", i), emb=emb)
+        return x2, adj2, x_mean, adj_mean
+
+    if use_graph is None:
+        use_graph = draws is None and steps >= 8
+    if not use_graph:
+        x_mean, adj_mean = x, adj
+        for i in range(steps):
+            x, adj, x_mean, adj_mean = pc_step(x, adj, torch.ones(B, device=dev) * timesteps[i], i)
+        return x, adj, x_mean, adj_mean
+
+    # ---- graph replay: static state, device-side step counter ----
+    for sde in (sde_x, sde_adj):
+        if hasattr(sde, "to_device"):
+            sde.to_device(dev)   # schedule tables resident on the device: no host copy inside the captured step
+    xs, adjs = x.clone(), adj.clone()
+    xm, am = torch.empty_like(xs), torch.empty_like(adjs)
+    idx = torch.zeros(1, dtype=torch.long, device=dev)
+    ones = torch.ones(B, device=dev)
+
+    if draws is not None:   # injected draws under replay: per-kind tables [steps, ...] indexed by the device-side step counter
+        tables = {k: torch.stack([draws(k, i).to(dev).float() for i in range(steps)]) for k in ("c_adj", "c_x", "p_adj", "p_x")}
+        get = lambda k, i: tables[k].index_select(0, idx).squeeze(0)  # noqa: E731
+
+    def body():
+        vec_t = ones * timesteps.index_select(0, idx)
+        x2, adj2, x_mean, adj_mean = pc_step(xs, adjs, vec_t, 0)
+        xs.copy_(x2); adjs.copy_(adj2); xm.copy_(x_mean); am.copy_(adj_mean)
+        idx.add_(1)
+
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        body()                                   # warm-up outside capture (weight packs, lazy inits), then restore the state
+        side.synchronize()
+        xs.copy_(x); adjs.copy_(adj); idx.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            body()
+        xs.copy_(x); adjs.copy_(adj); idx.zero_()   # (capture does not execute)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    for _ in range(steps):
+        graph.replay()
+    return xs, adjs, xm, am

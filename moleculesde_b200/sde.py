@@ -127,10 +127,21 @@ class VPSDE(SDE):
     def _timestep(self, t):
         return (t * (self.N - 1) / self.T).long()
 
+    def to_device(self, device):
+        """Keep device copies of the schedule tables (`_on`): needed when a sampling step is captured in a CUDA graph."""
+        self._dev_tables = {n: getattr(self, n).to(device) for n in ("discrete_betas", "alphas")}
+        self._dev_tables["device"] = torch.device(device)
+
+    def _on(self, name, device):
+        tabs = getattr(self, "_dev_tables", None)
+        if tabs is not None and tabs["device"] == torch.device(device):
+            return tabs[name]
+        return getattr(self, name).to(device)
+
     def discretize(self, x, t):
         ts = self._timestep(t)
-        beta = self.discrete_betas.to(x.device)[ts]
-        alpha = self.alphas.to(x.device)[ts]
+        beta = self._on("discrete_betas", x.device)[ts]
+        alpha = self._on("alphas", x.device)[ts]
         return torch.sqrt(alpha)[:, None] * x - x, torch.sqrt(beta)
 
     def _sqrt_alpha(self, t):
@@ -152,6 +163,15 @@ class VESDE(SDE):
     def T(self):
         return 1
 
+    def to_device(self, device):
+        self._dev_tables = {"discrete_sigmas": self.discrete_sigmas.to(device), "device": torch.device(device)}
+
+    def _on(self, name, device):
+        tabs = getattr(self, "_dev_tables", None)
+        if tabs is not None and tabs["device"] == torch.device(device):
+            return tabs[name]
+        return getattr(self, name).to(device)
+
     def sde(self, x, t):
         sigma = self.sigma_min * (self.sigma_max / self.sigma_min) ** t
         diffusion = sigma * torch.sqrt(
@@ -168,7 +188,7 @@ class VESDE(SDE):
     def discretize(self, x, t):
         # the reference indexes a CPU table with a device index (F10); here the table follows t
         ts = (t * (self.N - 1) / self.T).long()
-        sig = self.discrete_sigmas.to(t.device)
+        sig = self._on("discrete_sigmas", t.device)
         sigma = sig[ts]
         adjacent = torch.where(ts == 0, torch.zeros_like(t), sig[ts - 1])
         return torch.zeros_like(x), torch.sqrt(sigma ** 2 - adjacent ** 2)

@@ -180,6 +180,41 @@ class EdgeNetwork_dense(nn.Module):
         self._packed = (ver, pk)
         return pk
 
+    def _fusable(self) -> bool:
+        """`csrc/dense_fused.cu` covers the reference's pretraining / sampling configuration (3-layer pair MLP, <= 8 channels)."""
+        ls = self.mlp.layers
+        return (len(ls) == 3 and self.in_ch in (2, 8) and ls[0].out_features <= 16 and ls[1].out_features == ls[0].out_features
+                and self.out_ch <= 8 and 2 * self.attn_dim <= 32 and (self.attn_dim // self.num_heads) % 4 == 0)
+
+    @torch.no_grad()
+    def forward_fused(self, x, adjc, flags, symmetric: bool):
+        """Same values as `forward`, channel-major end to end: node-level GEMMs, `dense_attn_sym`, `dense_pair_mlp`.
+        Returns (x_out [B,Nm,conv_out], adj_out [B,C',Nm,Nm]); no channels-last pair / all-channels tensors are written."""
+        pk = self._pack()
+        B, C, Nm = adjc.size(0), adjc.size(1), adjc.size(-1)
+        W = 2 * self.attn_dim
+        ds = self.attn_dim // self.num_heads
+        s = stream_ptr(adjc)
+        x2 = x.flatten(0, 1) if x.dim() == 3 else x
+        h1 = linear(x2, pk["w1"], pk["b1"], act="tanh")
+        qk = _grouped_linear(h1, pk["w2"], pk["b2"], 2 * C, W, W, "none")
+        xw = linear(x2, pk["wv"])
+        V = torch.empty(B * Nm, C * self.conv_out, dtype=torch.float32, device=adjc.device)
+        _dense_gcn(adjc, C, xw, pk["bv"], self.conv_out, V, 0, "none")
+        S = torch.empty(B, C, Nm, Nm, dtype=torch.float32, device=adjc.device)
+        check(lib().molsde_dense_attn_sym(qk.data_ptr(), qk.data_ptr() + 4 * C * W, qk.stride(0), W, ds, ptr(flags), B, C, Nm, ptr(S), s),
+              "dense_attn_sym")
+        mc = self.multi_channel.layers
+        xo = linear(linear(V, mc[0].weight, mc[0].bias, act="elu"), mc[1].weight, mc[1].bias, act="tanh", rowscale=flags)
+        ml = self.mlp.layers
+        w = [l.weight.detach().float().contiguous() for l in ml]
+        bb = [l.bias.detach().float().contiguous() for l in ml]
+        adj_out = torch.empty(B, self.out_ch, Nm, Nm, dtype=torch.float32, device=adjc.device)
+        check(lib().molsde_dense_pair_mlp(ptr(S), ptr(adjc), ptr(flags), ptr(w[0]), ptr(bb[0]), ptr(w[1]), ptr(bb[1]), ptr(w[2]),
+                                          ptr(bb[2]), B, C, w[0].size(0), self.out_ch, Nm, int(symmetric), ptr(adj_out), s),
+              "dense_pair_mlp")
+        return xo.view(B, Nm, -1), adj_out
+
     @torch.no_grad()
     def forward(self, x, adjc, flags, allc: Optional[torch.Tensor] = None, all_off: int = 0):
         """x [B,Nm,Fin] (row view allowed), adjc [B,C,Nm,Nm] -> (x_out [B,Nm,conv_out], adj_out [B,C',Nm,Nm])."""
@@ -235,6 +270,10 @@ class EdgeScoreNetwork_dense(nn.Module):
         flags = flags.contiguous().float()
         B, Nm = adj.size(0), adj.size(1)
         s = stream_ptr(adj)
+        fl = self.final.layers
+        if len(fl) == 3 and self.fdim <= 32 and fl[0].out_features <= 64 and fl[1].out_features <= 64 and fl[2].out_features == 1 \
+                and all(l._fusable() for l in self.layers):
+            return self._forward_fused(x, adj, flags, scale)
         allc = torch.empty(B, Nm, Nm, self.fdim, dtype=torch.float32, device=adj.device)
         adjc = torch.empty(B, 2, Nm, Nm, dtype=torch.float32, device=adj.device)
         check(lib().molsde_dense_pow2(ptr(adj), B, Nm, ptr(adjc), ptr(allc), self.fdim, 0, s), "pow2")
@@ -246,6 +285,31 @@ class EdgeScoreNetwork_dense(nn.Module):
         out = torch.empty(B, Nm, Nm, dtype=torch.float32, device=adj.device)
         check(lib().molsde_dense_edge_final(ptr(m), ptr(flags), None if scale is None else ptr(scale.contiguous()), B, Nm, ptr(out), s),
               "edge_final")
+        return out
+
+
+    def _forward_fused(self, x, adj, flags, scale):
+        """Inference path on `csrc/dense_fused.cu`: channel-major adjacency stacks end to end; layers >= 1 see bitwise-symmetric
+        inputs by construction (outputs of `dense_pair_mlp`), layer 0 and the head make no symmetry assumption on `adj`."""
+        import ctypes
+        B, Nm = adj.size(0), adj.size(1)
+        s = stream_ptr(adj)
+        adjc = torch.empty(B, 2, Nm, Nm, dtype=torch.float32, device=adj.device)
+        check(lib().molsde_dense_pow2(ptr(adj), B, Nm, ptr(adjc), None, 0, 0, s), "pow2")
+        stacks = [adjc]
+        for li, lyr in enumerate(self.layers):
+            x, adjc = lyr.forward_fused(x, adjc, flags, symmetric=li > 0)
+            stacks.append(adjc)
+        fl = self.final.layers
+        w = [l.weight.detach().float().contiguous() for l in fl]
+        bb = [l.bias.detach().float().contiguous() for l in fl]
+        out = torch.empty(B, Nm, Nm, dtype=torch.float32, device=adj.device)
+        n = len(stacks)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in stacks])
+        chs = (ctypes.c_int32 * n)(*[t.size(1) for t in stacks])
+        check(lib().molsde_dense_edge_final_mlp(ptrs, chs, n, ptr(flags), None if scale is None else ptr(scale.contiguous()), ptr(w[0]),
+                                                ptr(bb[0]), ptr(w[1]), ptr(bb[1]), ptr(w[2]), ptr(bb[2]), self.fdim, w[0].size(0),
+                                                w[1].size(0), B, Nm, ptr(out), s), "dense_edge_final_mlp")
         return out
 
 
@@ -309,8 +373,14 @@ class SDEModel3Dto2D_node_adj_dense(nn.Module):
 
     # ---- `embedding_3D(representation) + embedding_X(x)` (:156; inference_3D_to_2D:228,240; SDE_dense.py:88,99) ----
     @torch.no_grad()
-    def embed(self, representation, x):
-        rep3d = linear(representation.contiguous().float(), self.embedding_3D.weight, self.embedding_3D.bias)
+    def embed_3d(self, representation):
+        return linear(representation.contiguous().float(), self.embedding_3D.weight, self.embedding_3D.bias)
+
+    @torch.no_grad()
+    def embed(self, representation, x, rep3d=None):
+        """`rep3d`: a cached `embed_3d(representation)` (the 3D part does not change along a sampling trajectory)."""
+        if rep3d is None:
+            rep3d = self.embed_3d(representation)
         return linear(x.contiguous().float(), self.embedding_X.weight, self.embedding_X.bias, residual=rep3d)
 
     def get_score_fn(self, sde, model, train=True, continuous=True):

@@ -56,8 +56,8 @@ class VPSDE(_DenseMixin, _sparse.VPSDE):
 
     def discretize(self, x, t):
         ts = self._timestep(t)
-        beta = self.discrete_betas.to(x.device)[ts]
-        alpha = self.alphas.to(x.device)[ts]
+        beta = self._on("discrete_betas", x.device)[ts]
+        alpha = self._on("alphas", x.device)[ts]
         return torch.sqrt(alpha)[:, None, None] * x - x, torch.sqrt(beta)
 
 

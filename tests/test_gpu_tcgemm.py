@@ -101,3 +101,31 @@ def test_fused_weight_and_bias_gradient(rows, nin, nout):
     torch.cuda.synchronize()
     assert _rel(dw, dy.double().t() @ x.double() + 2.0) < 5e-6
     assert _rel(db, dy.double().sum(0) - 1.0) < 5e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(16384, 728, 728), (16384, 728, 364), (4096, 300, 300), (1000, 200, 128), (257, 65, 64), (3607, 600, 300)])
+def test_tma_fed_path_shapes_and_epilogue(M, N, K):
+    """Shapes that take the TMA-fed kernel (K-contiguous operands, 16-byte aligned rows, N > 64, M >= 256, no split-K): ragged
+    M / N / K tails are zero-filled by the tensor maps; epilogue with bias, rowscale, activation, residual, strided output."""
+    dev = _dev()
+    g = torch.Generator(device="cpu").manual_seed(M * 3 + N + K)
+    xbig = torch.randn(M, K + 8, generator=g).to(dev)
+    x = xbig[:, 4:4 + K]                       # 16-byte aligned row-strided view (ld = K + 8)
+    w = torch.randn(N, K, generator=g).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    rs = torch.rand(M, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev)
+    y = torch.empty(M, N, device=dev)
+    _tc(M, N, K, x, x.stride(0), 1, w, K, 1, y, N, bias=b, split=False)
+    ref = x.double() @ w.double().t() + b.double()
+    assert _rel(y, ref) < 5e-6, _rel(y, ref)
+    out_big = torch.zeros(M, N + 5, device=dev)
+    y2 = out_big[:, 2:2 + N]
+    _tc(M, N, K, x, x.stride(0), 1, w, K, 1, y2, y2.stride(0), bias=b, act=2, rowscale=rs, R=res, split=False)
+    pre = ref * rs.double()[:, None]
+    ref2 = pre * torch.sigmoid(pre) + res.double()
+    assert _rel(y2, ref2) < 5e-6, _rel(y2, ref2)
+    assert float(out_big[:, :2].abs().max()) == 0 and float(out_big[:, 2 + N:].abs().max()) == 0
+    y3 = torch.empty(M, N, device=dev)       # bit-reproducible run to run
+    _tc(M, N, K, x, x.stride(0), 1, w, K, 1, y3, N, bias=b, split=False)
+    assert torch.equal(y, y3)

@@ -12,7 +12,7 @@ def timeit(fn, n=20):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
-for (M, N, K) in [(5120, 728, 728), (5120, 728, 364), (49000, 128, 128), (49000, 128, 51), (3585, 300, 300), (3585, 600, 300), (38424, 32, 300),
+for (M, N, K) in [(16384, 728, 728), (16384, 728, 364), (16384, 128, 300), (5120, 728, 728), (5120, 728, 364), (49000, 128, 128), (49000, 128, 51), (3585, 300, 300), (3585, 600, 300), (38424, 32, 300),
                   (38424, 32, 64), (38424, 128, 64), (102400, 16, 16), (102400, 60, 60), (5120, 32, 300), (5120, 32, 32), (40960, 300, 300)]:
     x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev); y = torch.empty(M, N, device=dev)
     s = torch.cuda.current_stream().cuda_stream
