@@ -49,6 +49,12 @@ def parse():
     p.add_argument("--pretrain-steps", type=int, default=50)
     p.add_argument("--cpu-pretrain-batch", type=int, default=32, help="molecules of the bounded CPU pretraining sample (configs[0])")
     p.add_argument("--skip-pretrain", action="store_true")
+    p.add_argument("--dense-graphs", type=int, default=256, help="graphs per GPU of the 3D->2D sampler (configs[3]: padded to 64 atoms)")
+    p.add_argument("--dense-pc-steps", type=int, default=1000, help="reverse-SDE steps of the 3D->2D trajectory")
+    p.add_argument("--skip-dense", action="store_true")
+    p.add_argument("--stress-molecules", type=int, default=512, help="drug-sized molecules per GPU (configs[4]: 4096 over 8 GPUs)")
+    p.add_argument("--stress-sample-molecules", type=int, default=64, help="of those, molecules sampled with 10 conformers each")
+    p.add_argument("--skip-stress", action="store_true")
     return p.parse_args()
 
 
@@ -388,6 +394,14 @@ def run_b200(args):
         del d, rep, pos0, prep, pm, pm2, d2, rep2, pos2
         torch.cuda.empty_cache()
         pretrain = bench_pretrain(args, dev, rank, world)
+    dense = None
+    if not args.skip_dense:
+        torch.cuda.empty_cache()
+        dense = bench_dense_sampler(args, dev, rank, world)
+    stress = None
+    if not args.skip_stress:
+        torch.cuda.empty_cache()
+        stress = bench_stress(args, dev, rank, world)
 
     if rank == 0:
         # roofline of the dominant kernel (sde2d3d_pc_kernel): SURVEY section 8(d) algorithmic work per launch
@@ -442,6 +456,10 @@ def run_b200(args):
         }
         if pretrain is not None:
             line["pretrain"] = pretrain
+        if dense is not None:
+            line["dense_sampler"] = dense
+        if stress is not None:
+            line["stress"] = stress
         if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
             rate, per_step, sample, used = cpu_reference_rate(args.repeat, args.cpu_pc_steps, args.pc_steps, model.state_dict(), args.seed)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": used, "kind": "port", "sample": sample}
@@ -625,6 +643,299 @@ def bench_pretrain(args, dev, rank, world):
         rate, dt, sample = cpu_pretrain_rate(args.cpu_pretrain_batch, args.seed)
         res["cpu_baseline"] = {"value": rate, "unit": "molecules/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
     return res
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[3]: 3D->2D VP sampling with SDEModel3Dto2D_node_adj_dense, noise_on_one_hot, graphs padded to 64 atoms
+# ------------------------------------------------------------------------------------------------
+def make_dense_model(dev, seed=1):
+    from moleculesde_b200.sde_3d_to_2d import SDEModel3Dto2D_node_adj_dense
+    torch.manual_seed(seed)
+    m = SDEModel3Dto2D_node_adj_dense(dim3D=300, c_init=2, c_hid=8, c_final=4, num_heads=4, adim=16, nhid=16, num_layers=4, emb_dim=300,
+                                      num_linears=3, beta_min=0.2, beta_max=1.0, num_diffusion_timesteps=1000, SDE_type="VP",
+                                      num_class_X=119, noise_on_one_hot=True)
+    return m.to(dev).eval()
+
+
+def cpu_dense_rate(graphs: int, pc_steps: int, total_pc_steps: int, seed: int):
+    """graphs/s of the reference 3D->2D predictor-corrector step on the host cores: `pc_steps` iterations of the reference loop
+    body (`..._inference_3D_to_2D_VE_VP.py:134-147,167-252`: 4 x [embed + score network] + the Langevin / reverse-diffusion updates)
+    on `graphs` graphs padded to 64 atoms through the oracle port, scaled to the `total_pc_steps`-step trajectory."""
+    from moleculesde_b200.data import synth_batch
+    from oracle import model as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    b = synth_batch(graphs, 3 + seed, "padded64")
+    sd = {k: v.detach().cpu().float() for k, v in make_dense_model("cpu").state_dict().items()}
+    g = torch.Generator().manual_seed(seed)
+    h3d = torch.randn(b.positions.size(0), 300, generator=g)
+    _, rep, _, flags = O.dense_inputs(h3d, b.x[:, 0], b.edge_index, b.edge_attr[:, 0], b.batch)
+    Bg, Nm = rep.size(0), rep.size(1)
+    sde = O.make_dense_sde("VP", 0.2, 1.0, 1000)
+    x = O.mask_x(torch.randn(Bg, Nm, 119, generator=g), flags)
+    adj = O.mask_adjs(torch.randn(Bg, Nm, Nm, generator=g), flags)
+    ts = torch.linspace(1.0, 1e-4, 1000)
+
+    def noise(like, sym):
+        z = torch.randn(like.shape, generator=g)
+        if sym:
+            z = z.triu(1)
+            z = z + z.transpose(-1, -2)
+            return O.mask_adjs(z, flags)
+        return O.mask_x(z, flags)
+
+    def one(i, x, adj):
+        t = torch.full((Bg,), float(ts[i]))
+        beta = sde.discrete_betas[(t * 999).long()]
+        alpha = 1.0 - beta
+        emb = O.embed_3d2d(sd, rep, x)
+        outs = []
+        for which, cur in (("adj", adj), ("x", x)):           # Langevin corrector (:208-252), alpha = 1 (SURVEY 2.1)
+            grad = O.score_3d2d(sd, sde, which, emb, adj, flags, t)
+            z = noise(cur, which == "adj")
+            gn = grad.reshape(Bg, -1).norm(dim=-1)
+            nn = z.reshape(Bg, -1).norm(dim=-1)
+            step = ((0.2 * nn / gn) ** 2 * 2)[:, None, None]
+            outs.append(cur + step * grad + torch.sqrt(step * 2) * z * 0.9)
+        adj1, x1 = outs
+        emb = O.embed_3d2d(sd, rep, x1)
+        outs = []
+        for which, cur in (("adj", adj1), ("x", x1)):         # reverse-diffusion predictor (:167-190)
+            score = O.score_3d2d(sd, sde, which, emb, adj1, flags, t)
+            f = torch.sqrt(alpha)[:, None, None] * cur - cur
+            rev_f = f - beta[:, None, None] * score
+            outs.append(cur - rev_f + torch.sqrt(beta)[:, None, None] * noise(cur, which == "adj"))
+        return outs[1], outs[0]
+
+    with torch.no_grad():
+        x, adj = one(0, x, adj)   # warm-up
+        t0 = time.perf_counter()
+        for i in range(pc_steps):
+            x, adj = one(i + 1, x, adj)
+        dt = (time.perf_counter() - t0) / pc_steps
+    sample = (f"{pc_steps} PC steps (4 score-network evaluations each) on {graphs} graphs padded to {Nm} atoms after 1 warm-up step, scaled "
+              f"to {total_pc_steps} steps; oracle port (pure-torch restatement of the reference), fp32, {torch.get_num_threads()} threads")
+    return graphs / (dt * total_pc_steps), dt, sample
+
+
+def bench_dense_sampler(args, dev, rank, world):
+    """One process per GPU, `--dense-graphs` graphs each (independent: no collective): the whole `node_adj_PC_generation`
+    trajectory -- one CUDA-graph replay per predictor-corrector step.  Returns the dict stored under "dense_sampler" (rank 0)."""
+    from moleculesde_b200.data import synth_batch
+    from moleculesde_b200.dist_util import max_over_ranks
+    from moleculesde_b200.loader import pin_batch
+    from moleculesde_b200.sampler_dense import node_adj_PC_generation
+    import torch.distributed as dist
+    B, S = args.dense_graphs, args.dense_pc_steps
+    model = make_dense_model(dev)
+    hb = synth_batch(B, 3 + args.seed + rank, "padded64")
+    g = torch.Generator().manual_seed(200 + rank)
+    h3d_h = torch.randn(hb.positions.size(0), 300, generator=g).pin_memory()
+    hbp = pin_batch(hb)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    SEG = 50   # an UNTRAINED network leaves the basin of finite states after ~100 steps: the state is re-drawn from the prior every
+               # SEG steps (the time index keeps running); the replays are the same kernels on the same shapes either way
+
+    def run(b, h3d, steps):
+        _, rep, _, _, Nm = model.dense_inputs(h3d, b)
+        pc, x0, adj0 = node_adj_PC_generation(rep, b, model, B=rep.size(0), max_num_nodes=Nm, num_class_X=119, n_steps=1,
+                                              diffusion_steps=steps, use_graph=True, return_graph=True)
+        done = 0
+        while done < steps:
+            n = min(SEG, steps - done)
+            pc.reset(x0, adj0, done)
+            pc.run(n)
+            done += n
+        return (pc.x, pc.adj, pc.x_mean, pc.adj_mean), Nm
+
+    b = hb.to(dev)
+    h3d = h3d_h.to(dev)
+    for _ in range(max(args.warmup, 3)):
+        run(b, h3d, 8)       # warm-up: weight packs, capture path, allocator pools
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    (x, adj, xm, am), Nm = run(b, h3d, S)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if not (torch.isfinite(xm).all() and torch.isfinite(am).all()):
+        raise SystemExit("non-finite state out of the 3D->2D sampler")
+    # end to end: pinned host batch + 3D representation in, dense prologue, capture, trajectory, final means back to the host
+    xm_h = torch.empty(B, Nm, 119).pin_memory()
+    am_h = torch.empty(B, Nm, Nm).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    b2 = hbp.to(dev)
+    (x2, adj2, xm2, am2), _ = run(b2, h3d_h.to(dev, non_blocking=True), S)
+    xm_h.copy_(xm2, non_blocking=True)
+    am_h.copy_(am2, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    ms, e2e_s = max_over_ranks([ms, e2e_s], dev)
+    if rank != 0:
+        return None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+    k4 = 2.0 * (B * Nm * 1_152_524 + B * Nm * Nm * (9_076 + Nm))      # SURVEY 8(d): one 3D->2D forward (embed + node net + edge net)
+    flops_step = 2.0 * k4                                               # a PC step evaluates both networks twice
+    tflops = flops_step * S / (ms * 1e-3) / 1e12
+    h2d = h3d_h.numel() * 4 + sum(getattr(hb, k).numel() * getattr(hb, k).element_size() for k in ("x", "edge_index", "edge_attr", "batch"))
+    res = {"metric": "3D->2D reverse-SDE graphs/sec", "value": world * B / (ms * 1e-3), "unit": "graphs/s", "ms_per_pc_step": ms / S,
+           "ms_per_trajectory": ms, "pc_steps": S, "graphs_per_gpu": B, "padded_atoms": Nm, "atoms": int(hb.positions.size(0)),
+           "n_gpus": world, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+           "config": "BASELINE configs[3]: SDEModel3Dto2D_node_adj_dense VP (beta 0.2..1), noise_on_one_hot, 119 classes, graphs padded to "
+                     "64 atoms, 1000-step predictor-corrector (snr 0.2, n_steps 1), random-init weights; an untrained network leaves the "
+                     "basin of finite states after ~100 steps, so the state is re-drawn from the prior every 50 steps (time index keeps "
+                     f"running); timed region = dense prologue + CUDA-graph capture of one PC step + {S} replays",
+           "gpu_launches_per_pc_step": "one CUDA-graph launch (~170 kernel nodes: TMA-fed / register-staged tcgen05 GEMMs, fused "
+                                       "channel-major pair kernels, dense GCN, updates)",
+           "e2e": {"value": world * B / e2e_s, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (xm_h.numel() + am_h.numel()) * 4,
+                   "includes": "H2D of the PyG batch + 3D representation, to_dense prologue, capture, trajectory, D2H of x_mean / adj_mean"},
+           "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tflops / tf32_peak, "traffic": None,
+                        "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (derived dense TF32)" if peaks else "fallback 1400/2"),
+                        "note": "achieved = ALGORITHMIC FLOPs of SURVEY 8(d) K4, 2*[B*Nm*1,152,524 + B*Nm^2*(9,076 + Nm)] per forward, x2 per PC "
+                                "step (both score networks twice; the reference's two extra embeds per step are not counted) / measured "
+                                "trajectory time.  Per-kernel shares: profiles/r2_dense_launches_*.txt"}}
+    if not args.no_cpu_baseline and world == 1:
+        rate, dt, sample = cpu_dense_rate(8, 3, S, args.seed)
+        res["cpu_baseline"] = {"value": rate, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: drug-sized molecules (<= 100 atoms), 3-hop extended graph, 10 A cutoff, 4096 molecules sharded by molecule
+# ------------------------------------------------------------------------------------------------
+def bench_stress(args, dev, rank, world):
+    """Per GPU `--stress-molecules` synthetic drug-sized molecules (30-100 atoms).  Two timed legs, no collective (molecule shards):
+      encode : extended graph + 10 A radius graph (neighbour cap binding) + GIN encoder + SchNet encoder + one 2D->3D score evaluation
+      sample : 10 conformers per molecule for the first `--stress-sample-molecules` molecules, full 1000-step predictor-corrector;
+               every sampling group has 300-1000 atoms, i.e. beyond one CTA: the step-wise CUDA-graph path of sampler.py."""
+    import torch.distributed as dist
+    from moleculesde_b200 import graph as G
+    from moleculesde_b200.data import Batch, repeat_data, synth_molecules
+    from moleculesde_b200.dist_util import max_over_ranks
+    from moleculesde_b200.gnn import GNN
+    from moleculesde_b200.sampler import position_PC_generation
+    from moleculesde_b200.schnet import SchNet
+    M = args.stress_molecules
+    mols = synth_molecules(M, 9000 + args.seed + rank, "drug")
+    hb = Batch.from_data_list(mols)
+    host = {k: getattr(hb, k).pin_memory() for k in ("x", "edge_index", "edge_attr", "positions", "batch")}
+    torch.manual_seed(1)
+    gnn = GNN(5, 300, JK="last", drop_ratio=0.0, gnn_type="GIN").to(dev).eval()
+    sch = SchNet(hidden_channels=300, num_filters=128, num_interactions=6, num_gaussians=51, cutoff=10, readout="mean", node_class=119)
+    sch = sch.to(dev).eval()
+    model = make_model(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def encode(b):
+        csr = G.extend_graph(b.edge_index, b.batch, b.num_graphs)
+        b.extended_edge_index, b._molsde_ext_csr = csr.edge_index, csr
+        h2d = gnn(b.x, b.edge_index, b.edge_attr)
+        out3d, h3d = sch(b.x[:, 0].contiguous(), b.positions, b.batch, return_latent=True)
+        t = torch.full((b.positions.size(0),), 0.5, device=dev)
+        score = model.get_score(h2d, b, b.positions, None, t)
+        return h2d, h3d, score, csr
+
+    def stage():
+        b = hb.__class__()
+        for k, v in host.items():
+            setattr(b, k, v.to(dev, non_blocking=True))
+        b.num_graphs = hb.num_graphs
+        return b
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            h2d, h3d, score, csr = encode(stage())
+        barrier()
+        K = max(args.steps, 5)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        bs = [stage() for _ in range(K)]
+        torch.cuda.synchronize()
+        e0.record()
+        for b in bs:
+            h2d, h3d, score, csr = encode(b)
+        e1.record()
+        barrier()
+        enc_ms = e0.elapsed_time(e1) / K
+        if not (torch.isfinite(score).all() and torch.isfinite(h3d).all()):
+            raise SystemExit("non-finite output in the stress workload")
+        N, E_b, E_x = int(hb.positions.size(0)), int(hb.edge_index.size(1)), int(csr.num_edges)
+        E_r = int(G.radius_graph(bs[0].positions, 10.0, bs[0].batch, M).num_edges)
+        del bs
+        t0 = time.perf_counter()
+        for _ in range(K):
+            h2d, h3d, score, csr = encode(stage())
+            sc_h = score.cpu()
+        barrier()
+        enc_e2e = (time.perf_counter() - t0) / K
+        # ---- sampling leg: groups of 10 conformers, 300-1000 atoms each
+        Ms, rep_n = min(args.stress_sample_molecules, M), args.repeat
+        groups = [repeat_data(m, rep_n) for m in mols[:Ms]]
+        big = Batch.from_data_list([d for gb in groups for d in gb.to_data_list()]).to(dev)
+        gptr = torch.arange(0, Ms * rep_n + 1, rep_n, dtype=torch.long)
+        csr_s = G.extend_graph(big.edge_index, big.batch, big.num_graphs)
+        big.extended_edge_index, big._molsde_ext_csr = csr_s.edge_index, csr_s
+        g = torch.Generator().manual_seed(300 + rank)
+        n_s = int(big.positions.size(0))
+        rep = torch.randn(n_s, 300, generator=g).to(dev)
+        pos0 = torch.randn(n_s, 3, generator=g).to(dev)
+        position_PC_generation(rep, big, pos0, model, model.sde_pos, group_ptr=gptr, seed=1, diffusion_steps=8)
+        barrier()
+        e0.record()
+        _, pm = position_PC_generation(rep, big, pos0, model, model.sde_pos, group_ptr=gptr, seed=2, diffusion_steps=args.pc_steps)
+        e1.record()
+        barrier()
+        smp_ms = e0.elapsed_time(e1)
+        if not torch.isfinite(pm).all():
+            raise SystemExit("non-finite positions out of the large-group sampler")
+    enc_ms, enc_e2e, smp_ms = max_over_ranks([enc_ms, enc_e2e, smp_ms], dev)
+    if rank != 0:
+        return None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    Bm = M
+    bytes_enc = (12 * N + 4 * (Bm + 1) + 4 * (N + 1) + 20 * E_r) + (8 * (N + 1) + 4 * E_b + 20 * E_x) \
+        + 6 * (2 * 1200 * N + 4 * (N + 1) + 8 * E_r + 762_272) + 1200 * N + (2 * 1200 * N + 722_000) + 1200 * Bm \
+        + (1200 * N + 4 * E_x + 4 * (N + 1) + 128 * E_x + 762_128) + (156 * N + 132 * E_x + 4 * (N + 1) + 266_000) \
+        + 5 * (2 * 1200 * N + 8 * E_b + 4 * 1_446_000 // 5)
+    gbs = bytes_enc / (enc_ms * 1e-3) / 1e9
+    return {"metric": "drug-sized molecules/sec (graph build + GIN + SchNet + 2D->3D score)", "value": world * M / (enc_ms * 1e-3),
+            "unit": "molecules/s", "ms_per_pass": enc_ms, "molecules_per_gpu": M, "n_gpus": world, "scaling": "weak", "dtype": "f32",
+            "data": "synthetic", "atoms": N, "bonds": E_b, "extended_edges": E_x, "radius_edges": E_r,
+            "config": "BASELINE configs[4]: synthetic drug-sized molecules (30-100 atoms), 3-hop extended graph, SchNet 10 A cutoff with "
+                      "the 32-neighbour cap binding, sharded by molecule (4096 molecules = 8 GPUs x 512); eval-mode encoders",
+            "e2e": {"value": world * M / enc_e2e, "unit": "molecules/s",
+                    "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()), "d2h_bytes_per_step": N * 12,
+                    "includes": "pinned-host H2D of the PyG batch, both graph builders, both encoders, the score evaluation, D2H of the score"},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                         "note": "layer-granular ALGORITHMIC bytes of SURVEY 8(d) (K1 + K1b incl. the int64 API tensors, 6 x K2 + embedding + "
+                                 "head + readout, a7, K3, 5 GIN layers) / measured pass time; a multi-kernel pass, so this is an upper-level "
+                                 "figure, not a single kernel's"},
+            "sampling": {"metric": "drug-sized 2D->3D conformers/sec (groups of 10 conformers, 300-1000 atoms each: step-wise path)",
+                         "value": world * Ms * rep_n / (smp_ms * 1e-3), "unit": "conformers/s", "molecules_per_gpu": Ms,
+                         "conformers_per_molecule": rep_n, "pc_steps": args.pc_steps, "atoms": n_s, "extended_edges": int(csr_s.num_edges),
+                         "ms_per_pc_step": smp_ms / args.pc_steps,
+                         "note": "one CUDA-graph replay per reverse step: score kernel over molecule chunks -> per-group corrector update -> "
+                                 "score -> predictor update (sampler._position_PC_stepwise)"}}
 
 
 def hot_path_pc_only(model, d, rep, pos0, group_ptr, seed, pc_steps):

@@ -187,6 +187,18 @@ int molsde_sde2d3d_pc_sample(const molsde_plan* plan, const molsde_sde2d3d_param
                              int64_t scratch_floats, int32_t* work_counter, int32_t* status_flag,
                              void* stream);
 
+/* Step-wise form of the same loop for sampling groups beyond the fused kernel's shared-memory limits (> 224 atoms / 64 tiles; the
+ * reference's position_PC_generation has no size limit, ..._inference_2D_to_3D_VE_VP.py:92-138).  One reverse step =
+ *   molsde_sde2d3d_forward_net (raw network output) -> pc_corrector_update (LangevinCorrector.update_fn :191-212, per-GROUP mean
+ *   norms: group_node_ptr int32 [G+1] node offsets) -> forward_net -> pc_predictor_update (ReverseDiffusionPredictor.update_fn
+ *   :163-168; also advances *step_counter).  step_table / seed / noise semantics are those of molsde_sde2d3d_pc_sample; the step
+ *   index is read from device memory so the four calls can be captured once in a CUDA graph and replayed per step. */
+int molsde_sde2d3d_pc_corrector_update(const float* net_out, float* pos, const int32_t* group_node_ptr, int32_t num_groups,
+                                       const float* step_table, const int32_t* step_counter, float snr, float scale_eps, uint64_t seed,
+                                       const float* noise_corr, int64_t N, void* stream);
+int molsde_sde2d3d_pc_predictor_update(const float* net_out, float* pos, float* pos_mean, const float* step_table,
+                                       int32_t* step_counter, uint64_t seed, const float* noise_pred, int64_t N, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * SchNet (Geom3D/models/schnet.py:16-216), forward
  * ---------------------------------------------------------------------------------- */

@@ -1210,6 +1210,82 @@ sde2d3d_pc_kernel(molsde_plan plan, const float* __restrict__ blob, const float*
 }
 
 // ---------------------------------------------------------------------------------------
+// Step-wise predictor / corrector updates for sampling groups that do NOT fit one CTA (> 224 atoms or > 64 edge tiles; the
+// reference has no limit: `num_repeat` conformers of a 30-atom molecule are already 300 atoms).  The host captures
+//   [score network over the batch (sde2d3d_score_kernel, chunks of whole molecules) -> corrector update -> score -> predictor update]
+// in a CUDA graph and replays it once per reverse step; the step index lives in device memory (`step_counter`), the per-step
+// schedule constants come from the same `step_table` as the fused kernel, the noise from the same Philox streams
+// (seed, node, step, 0 | 1), so a group small enough for both paths is sampled identically up to summation order.
+//   corrector: one CTA per group -- the Langevin step size is a per-group mean of norms (F9) -- fixed-order block reduction;
+//   predictor: elementwise over the atoms.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS)
+pc_corrector_update_kernel(const float* __restrict__ net_out, float* __restrict__ pos, const int32_t* __restrict__ group_node_ptr,
+                           const float* __restrict__ step_table, const int32_t* __restrict__ step_counter, float snr, float scale_eps,
+                           uint64_t seed, const float* __restrict__ noise_corr, int64_t N) {
+    __shared__ float red[64];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const int a = group_node_ptr[g], n = group_node_ptr[g + 1] - a;
+    if (n <= 0) return;
+    const int step = *step_counter;
+    const float stdv = step_table[step * 8 + 0], calpha = step_table[step * 8 + 3];
+    const float* nc = noise_corr ? noise_corr + static_cast<size_t>(step) * N * 3 : nullptr;
+    float gn = 0.0f, nn = 0.0f;
+    for (int i = tid; i < n; i += NTHREADS) {
+        const size_t o = static_cast<size_t>(a + i) * 3;
+        const float s0 = __fdiv_rn(-net_out[o], stdv), s1 = __fdiv_rn(-net_out[o + 1], stdv), s2 = __fdiv_rn(-net_out[o + 2], stdv);
+        float nz[3];
+        if (nc) { nz[0] = nc[o]; nz[1] = nc[o + 1]; nz[2] = nc[o + 2]; } else normal3(seed, a + i, step, 0u, nz);
+        gn += sqrtf(s0 * s0 + s1 * s1 + s2 * s2);
+        nn += sqrtf(nz[0] * nz[0] + nz[1] * nz[1] + nz[2] * nz[2]);
+    }
+    gn = block_sum(gn, red) / static_cast<float>(n);
+    nn = block_sum(nn, red) / static_cast<float>(n);
+    const float ratio = __fdiv_rn(__fmul_rn(snr, nn), gn);
+    const float step_size = __fmul_rn(__fmul_rn(__fmul_rn(ratio, ratio), 2.0f), calpha);   // :209
+    const float nscale = sqrtf(__fmul_rn(step_size, 2.0f));
+    for (int i = tid; i < n; i += NTHREADS) {
+        const size_t o = static_cast<size_t>(a + i) * 3;
+        float nz[3];
+        if (nc) { nz[0] = nc[o]; nz[1] = nc[o + 1]; nz[2] = nc[o + 2]; } else normal3(seed, a + i, step, 0u, nz);
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+            const float sc = __fdiv_rn(-net_out[o + ax], stdv);
+            const float xm = __fadd_rn(pos[o + ax], __fmul_rn(step_size, sc));                       // :210
+            pos[o + ax] = __fadd_rn(xm, __fmul_rn(__fmul_rn(nscale, nz[ax]), scale_eps));          // :211
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pc_predictor_update_kernel(const float* __restrict__ net_out, float* __restrict__ pos, float* __restrict__ pos_mean,
+                           const float* __restrict__ step_table, const int32_t* __restrict__ step_counter, uint64_t seed,
+                           const float* __restrict__ noise_pred, int64_t N) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= N) return;
+    const int step = *step_counter;
+    const float stdv = step_table[step * 8 + 0], Gd = step_table[step * 8 + 1], sqrt_alpha = step_table[step * 8 + 2];
+    float nz[3];
+    if (noise_pred) {
+        const float* np = noise_pred + (static_cast<size_t>(step) * N + i) * 3;
+        nz[0] = np[0]; nz[1] = np[1]; nz[2] = np[2];
+    } else {
+        normal3(seed, static_cast<uint32_t>(i), step, 1u, nz);
+    }
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const float x = pos[3 * i + ax];
+        const float sc = __fdiv_rn(-net_out[3 * i + ax], stdv);
+        const float f = __fsub_rn(__fmul_rn(sqrt_alpha, x), x);                    // SDE_sparse.py:160 / 220
+        const float rev_f = __fsub_rn(f, __fmul_rn(__fmul_rn(Gd, Gd), sc));        // SDE_sparse.py:98
+        const float xmean = __fsub_rn(x, rev_f);                                   // :166
+        pos[3 * i + ax] = __fadd_rn(xmean, __fmul_rn(Gd, nz[ax]));                 // :167
+        pos_mean[3 * i + ax] = xmean;
+    }
+}
+__global__ void pc_step_advance_kernel(int32_t* step_counter) { *step_counter += 1; }
+
+// ---------------------------------------------------------------------------------------
 // edge_2D_emb (eval): e2d tile = W3 . relu(U[src] + V[tgt]) + b3,  SDE_model_2D_to_3D.py:405-407
 // uv [N][600]: columns 0..299 = folded first layer applied to h[row], 300..599 to h[col].
 // One-time (loop-invariant) kernel: fp32 FFMA register tile, 256 threads, output in the [8][128][4] tile layout.
@@ -1516,6 +1592,29 @@ int molsde_sde2d3d_pc_sample(const molsde_plan* plan, const molsde_sde2d3d_param
         *plan, params->blob, nattr, e2d_tiles, pos_init, step_table, *cfg, noise_corr, noise_pred, pos_out,
         pos_mean_out, scratch, stride, work_counter, status_flag);
     return check_launch("sde2d3d_pc");
+}
+
+int molsde_sde2d3d_pc_corrector_update(const float* net_out, float* pos, const int32_t* group_node_ptr, int32_t num_groups,
+                                       const float* step_table, const int32_t* step_counter, float snr, float scale_eps, uint64_t seed,
+                                       const float* noise_corr, int64_t N, void* stream) {
+    if (!net_out || !pos || !group_node_ptr || !step_table || !step_counter || num_groups < 0 || N < 0) return MOLSDE_ERR_INVALID;
+    if (num_groups == 0) return MOLSDE_OK;
+    pc_corrector_update_kernel<<<num_groups, NTHREADS, 0, as_stream(stream)>>>(net_out, pos, group_node_ptr, step_table, step_counter, snr,
+                                                                              scale_eps, seed, noise_corr, N);
+    return check_launch("pc_corrector_update");
+}
+
+int molsde_sde2d3d_pc_predictor_update(const float* net_out, float* pos, float* pos_mean, const float* step_table,
+                                       int32_t* step_counter, uint64_t seed, const float* noise_pred, int64_t N, void* stream) {
+    if (!net_out || !pos || !pos_mean || !step_table || !step_counter || N < 0) return MOLSDE_ERR_INVALID;
+    if (N > 0) {
+        pc_predictor_update_kernel<<<static_cast<unsigned>((N + 255) / 256), 256, 0, as_stream(stream)>>>(net_out, pos, pos_mean, step_table,
+                                                                                                   step_counter, seed, noise_pred, N);
+        int st = check_launch("pc_predictor_update");
+        if (st != MOLSDE_OK) return st;
+    }
+    pc_step_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(step_counter);   // the next replay of the captured step reads step + 1
+    return check_launch("pc_step_advance");
 }
 
 }  // extern "C"

@@ -99,6 +99,10 @@ def position_PC_generation(representation, data, pos_init, scorenet, sde, probab
     table = sde.step_table(timesteps[:steps]).to(dev).contiguous()
     if group_ptr is None:
         group_ptr = torch.tensor([0, data.num_graphs], dtype=torch.long)
+    if not _groups_fit_fused(scorenet, data, group_ptr):
+        # a sampling group beyond one CTA's shared memory (> 224 atoms / 64 edge tiles): same algorithm, one CUDA-graph replay per step
+        return _position_PC_stepwise(representation, data, pos_init, scorenet, table, group_ptr, snr, scale_eps, noise_corr, noise_pred,
+                                     seed, steps, denoise)
     prep = scorenet.prepared(data, group_ptr)
     pk = scorenet.packed_params()
     nattr, e2d = scorenet.invariants(representation, prep)
@@ -129,3 +133,91 @@ def position_PC_generation(representation, data, pos_init, scorenet, sde, probab
                                f"({'chunk %d beyond the compiled limits' % (status - 1) if status > 0 else 'completion wait timed out'}); "
                                "the returned positions would be undefined")
     return (data, pos_mean) if denoise else (data, pos_out)
+
+
+def _groups_fit_fused(scorenet, data, group_ptr) -> bool:
+    """True when every sampling group fits the fused kernel (one CTA per group: <= CHUNK_MAX_NODES atoms, <= MAX_CHUNK_TILES tiles)."""
+    from .graph import segment_ptr
+    node_ptr = getattr(data, "_molsde_node_ptr_cpu", None)
+    if node_ptr is None:
+        node_ptr = segment_ptr(data.batch, data.num_graphs).cpu()
+        try:
+            data._molsde_node_ptr_cpu = node_ptr
+        except AttributeError:
+            pass
+    sizes = node_ptr[group_ptr.long()]
+    if int((sizes[1:] - sizes[:-1]).max()) > _abi.CHUNK_MAX_NODES:
+        return False
+    try:
+        scorenet.prepared(data, group_ptr)   # builds (and caches) the one-chunk-per-group plan; raises beyond the tile limit
+    except _abi.MolsdeError:
+        return False
+    return True
+
+
+def _position_PC_stepwise(representation, data, pos_init, scorenet, table, group_ptr, snr, scale_eps, noise_corr, noise_pred, seed,
+                          steps, denoise):
+    """`position_PC_generation` for sampling groups of any size: the score network runs over chunks of whole MOLECULES
+    (`molsde_sde2d3d_forward_net`), the Langevin step size is reduced per group by `molsde_sde2d3d_pc_corrector_update`, and
+    one reverse step [score, corrector, score, predictor] is captured in a CUDA graph and replayed `steps` times (the step index
+    is a device-side counter).  Same schedule table, same Philox noise streams as the fused kernel."""
+    from .sde_2d_to_3d import prepare_graph
+    dev = pos_init.device
+    key = "_molsde_prep_ext_free" if scorenet.use_extend_graph else "_molsde_prep_bond_free"
+    prep = getattr(data, key, None)
+    if prep is None:
+        csr = getattr(data, "_molsde_ext_csr", None) if scorenet.use_extend_graph else None
+        prep = prepare_graph(scorenet._edge_index(data), data.batch, data.num_graphs, None, csr)   # molecules packed into chunks
+        try:
+            setattr(data, key, prep)
+        except AttributeError:
+            pass
+    pk = scorenet.packed_params()
+    nattr, e2d = scorenet.invariants(representation, prep)
+    pos = pos_init.detach().float().contiguous().clone()
+    n_atoms = pos.size(0)
+    if (noise_corr is None) != (noise_pred is None):
+        raise ValueError("give both noise_corr and noise_pred or neither")
+    if noise_corr is not None:
+        noise_corr, noise_pred = noise_corr.float().contiguous(), noise_pred.float().contiguous()
+        assert tuple(noise_corr.shape) == (steps, n_atoms, 3) and tuple(noise_pred.shape) == (steps, n_atoms, 3)
+    gnp = prep.node_ptr.cpu()[group_ptr.long()].to(torch.int32).to(dev)      # node offsets of the groups
+    G = gnp.numel() - 1
+    net = torch.full_like(pos, float("nan"))
+    pos_mean = torch.empty_like(pos)
+    scratch = prep.get_scratch()
+    st = prep.plan.as_struct()
+    prm = _abi.Params(pk["blob"].data_ptr(), pk["blob"].numel())
+    counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    prep.status.zero_()
+    L, sd = lib(), int(seed) & 0xFFFFFFFFFFFFFFFF
+
+    def one_step():
+        s = stream_ptr(pos)
+        check(L.molsde_sde2d3d_forward_net(ctypes.byref(st), ctypes.byref(prm), ptr(nattr), ptr(e2d), ptr(pos), None, None, 0.0, ptr(net),
+                                           ptr(scratch), scratch.numel(), ptr(prep.status), s), "sde2d3d_forward_net")
+        check(L.molsde_sde2d3d_pc_corrector_update(ptr(net), ptr(pos), ptr(gnp), G, ptr(table), ptr(counter), float(snr), float(scale_eps),
+                                                   sd, ptr(noise_corr), n_atoms, s), "pc_corrector_update")
+        check(L.molsde_sde2d3d_forward_net(ctypes.byref(st), ctypes.byref(prm), ptr(nattr), ptr(e2d), ptr(pos), None, None, 0.0, ptr(net),
+                                           ptr(scratch), scratch.numel(), ptr(prep.status), s), "sde2d3d_forward_net")
+        check(L.molsde_sde2d3d_pc_predictor_update(ptr(net), ptr(pos), ptr(pos_mean), ptr(table), ptr(counter), sd, ptr(noise_pred),
+                                                   n_atoms, s), "pc_predictor_update")
+
+    if steps < 4:
+        for _ in range(steps):
+            one_step()
+    else:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                one_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for _ in range(steps):
+            graph.replay()
+    status = int(prep.status.item())
+    if status != 0:
+        raise _abi.MolsdeError(f"sde2d3d_forward_net: device status {status} (a molecule beyond the compiled limits of the score kernel: "
+                               f"{_abi.CHUNK_MAX_NODES} atoms / {_abi.MAX_CHUNK_TILES} tiles per chunk)")
+    return (data, pos_mean) if denoise else (data, pos)

@@ -85,13 +85,14 @@ class LangevinCorrector:
 def node_adj_PC_generation(representation, data, SDE_model, B, max_num_nodes, num_class_X, probability_flow=False,
                            eps=1e-4, snr=0.2, scale_eps=0.9, n_steps=1, *, x_init=None, adj_init=None,
                            draws: Optional[Callable[[str, int], torch.Tensor]] = None, diffusion_steps: Optional[int] = None,
-                           use_graph: Optional[bool] = None):
+                           use_graph: Optional[bool] = None, return_graph: bool = False):
     """Reference signature (`:95-101`).  Keyword-only extensions: `x_init` / `adj_init` inject the prior draws,
     `draws(kind, step)` with kind in {'c_adj','c_x','p_adj','p_x'} injects the raw `randn_like` of each update,
     `diffusion_steps` truncates the `linspace(T, eps, N)` grid, `use_graph` (default: on when no draws are injected) captures
     ONE predictor-corrector step -- four score-network evaluations + the four state updates, ~170 kernels -- in a CUDA graph
     over static state buffers and replays it for every step (the step's time comes from a device-side counter), so a
-    trajectory costs one graph launch per step instead of ~230 host launches."""
+    trajectory costs one graph launch per step instead of ~230 host launches.  `return_graph=True` returns
+    `(GraphedPCStep, x0, adj0)` instead of running the trajectory."""
     require_device(representation)
     dev = representation.device
     sde_x, sde_adj = SDE_model.sde_x, SDE_model.sde_adj
@@ -118,8 +119,10 @@ def node_adj_PC_generation(representation, data, SDE_model, B, max_num_nodes, nu
     # same values inside every one of its 4 x N_steps embeds, `:228,240`)
     rep3d = SDE_model.embed_3d(representation)
 
-    def pc_step(x, adj, vec_t, i):
+    def pc_step(x, adj, vec_t, i, get=get):
         """one iteration of the reference loop (`:134-147`)"""
+        if get is None:
+            get = lambda k, i: None  # noqa: E731
         emb = SDE_model.embed(representation, x, rep3d=rep3d)
         adj1, _ = corr_adj.update_fn(representation, x, adj, flags, vec_t, get("c_adj", i), emb=emb)
         x1, _ = corr_x.update_fn(representation, x, adj, flags, vec_t, get("c_x", i), emb=emb)
@@ -137,35 +140,58 @@ def node_adj_PC_generation(representation, data, SDE_model, B, max_num_nodes, nu
         return x, adj, x_mean, adj_mean
 
     # ---- graph replay: static state, device-side step counter ----
-    for sde in (sde_x, sde_adj):
-        if hasattr(sde, "to_device"):
-            sde.to_device(dev)   # schedule tables resident on the device: no host copy inside the captured step
-    xs, adjs = x.clone(), adj.clone()
-    xm, am = torch.empty_like(xs), torch.empty_like(adjs)
-    idx = torch.zeros(1, dtype=torch.long, device=dev)
-    ones = torch.ones(B, device=dev)
+    pc = GraphedPCStep(pc_step, x, adj, timesteps, [sde_x, sde_adj], draws, steps)
+    if return_graph:   # (x, adj) masked prior draws + the captured step: the caller drives `reset` / `run`
+        return pc, x, adj
+    pc.run(steps)
+    return pc.x, pc.adj, pc.x_mean, pc.adj_mean
 
-    if draws is not None:   # injected draws under replay: per-kind tables [steps, ...] indexed by the device-side step counter
-        tables = {k: torch.stack([draws(k, i).to(dev).float() for i in range(steps)]) for k in ("c_adj", "c_x", "p_adj", "p_x")}
-        get = lambda k, i: tables[k].index_select(0, idx).squeeze(0)  # noqa: E731
 
-    def body():
-        vec_t = ones * timesteps.index_select(0, idx)
-        x2, adj2, x_mean, adj_mean = pc_step(xs, adjs, vec_t, 0)
-        xs.copy_(x2); adjs.copy_(adj2); xm.copy_(x_mean); am.copy_(adj_mean)
-        idx.add_(1)
+class GraphedPCStep:
+    """One predictor-corrector step of `node_adj_PC_generation` captured in a CUDA graph over static state buffers.  The step's
+    time is read from `timesteps[counter]` with a device-side counter that the captured step advances, so `run(n)` is n graph
+    launches and nothing else.  `reset(x, adj, step_index)` rewinds / re-seeds the state (used by the benchmark, where an
+    UNTRAINED network leaves the basin of finite states after ~100 steps)."""
 
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(side):
-        body()                                   # warm-up outside capture (weight packs, lazy inits), then restore the state
-        side.synchronize()
-        xs.copy_(x); adjs.copy_(adj); idx.zero_()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            body()
-        xs.copy_(x); adjs.copy_(adj); idx.zero_()   # (capture does not execute)
-    torch.cuda.current_stream(dev).wait_stream(side)
-    for _ in range(steps):
-        graph.replay()
-    return xs, adjs, xm, am
+    def __init__(self, pc_step, x, adj, timesteps, sdes, draws=None, steps=None):
+        dev = x.device
+        for sde in sdes:
+            if hasattr(sde, "to_device"):
+                sde.to_device(dev)   # schedule tables resident on the device: no host copy inside the captured step
+        self.x, self.adj = x.clone(), adj.clone()
+        self.x_mean, self.adj_mean = torch.empty_like(x), torch.empty_like(adj)
+        self.idx = torch.zeros(1, dtype=torch.long, device=dev)
+        ones = torch.ones(x.size(0), device=dev)
+        self._pc_step = pc_step
+        if draws is not None:   # injected draws under replay: per-kind tables [steps, ...] indexed by the device-side step counter
+            tables = {k: torch.stack([draws(k, i).to(dev).float() for i in range(steps)]) for k in ("c_adj", "c_x", "p_adj", "p_x")}
+            self.get = lambda k, i: tables[k].index_select(0, self.idx).squeeze(0)
+        else:
+            self.get = None
+
+        def body():
+            vec_t = ones * timesteps.index_select(0, self.idx)
+            x2, adj2, x_mean, adj_mean = pc_step(self.x, self.adj, vec_t, 0, self.get)
+            self.x.copy_(x2); self.adj.copy_(adj2); self.x_mean.copy_(x_mean); self.adj_mean.copy_(adj_mean)
+            self.idx.add_(1)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            body()                                   # warm-up outside capture (weight packs, lazy inits), then restore the state
+            side.synchronize()
+            self.reset(x, adj)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                body()
+            self.reset(x, adj)                       # (capture does not execute)
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+    def reset(self, x, adj, step_index: int = 0):
+        self.x.copy_(x)
+        self.adj.copy_(adj)
+        self.idx.fill_(step_index)
+
+    def run(self, n: int):
+        for _ in range(n):
+            self.graph.replay()

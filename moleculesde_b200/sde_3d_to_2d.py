@@ -8,6 +8,7 @@ Forward values only this round (score networks, DSM losses, sampler); no autogra
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -271,7 +272,7 @@ class EdgeScoreNetwork_dense(nn.Module):
         B, Nm = adj.size(0), adj.size(1)
         s = stream_ptr(adj)
         fl = self.final.layers
-        if len(fl) == 3 and self.fdim <= 32 and fl[0].out_features <= 64 and fl[1].out_features <= 64 and fl[2].out_features == 1 \
+        if os.environ.get("MOLSDE_DENSE_UNFUSED") != "1" and len(fl) == 3 and self.fdim <= 32 and fl[0].out_features <= 64 and fl[1].out_features <= 64 and fl[2].out_features == 1 \
                 and all(l._fusable() for l in self.layers):
             return self._forward_fused(x, adj, flags, scale)
         allc = torch.empty(B, Nm, Nm, self.fdim, dtype=torch.float32, device=adj.device)

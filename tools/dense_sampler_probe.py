@@ -21,6 +21,10 @@ def main():
     m = SDEModel3Dto2D_node_adj_dense(dim3D=300, c_init=2, c_hid=8, c_final=4, num_heads=4, adim=16, nhid=16, num_layers=4,
                                       emb_dim=300, num_linears=3, beta_min=0.2, beta_max=1.0, num_diffusion_timesteps=1000,
                                       SDE_type="VP", num_class_X=119, noise_on_one_hot=True).to(dev).eval()
+    with torch.no_grad():   # an untrained score network drives the reverse SDE to inf within ~100 steps: damp the output heads
+        for net in (m.edge_score_network, m.node_score_network):
+            net.final.layers[-1].weight.mul_(0.02)
+            net.final.layers[-1].bias.mul_(0.02)
     b = synth_batch(B, 3, "padded64").to(dev)
     h3d = torch.randn(b.positions.size(0), 300, device=dev)
     _, rep, _, _, Nm = m.dense_inputs(h3d, b)
