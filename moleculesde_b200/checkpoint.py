@@ -45,11 +45,11 @@ def build_models(emb_dim: int = 300, SDE_type_2Dto3D: str = "VE", SDE_type_3Dto2
     from .gnn import GNN
     from .schnet import SchNet
     from . import sde_2d_to_3d as M23
-    from .sde_3d_to_2d import SDEModel3Dto2D_node_adj_dense
+    from . import sde_3d_to_2d as M32
     if SDE_2Dto3D_model not in ("SDEModel2Dto3D_01", "SDEModel2Dto3D_02"):
         raise NotImplementedError(f"{SDE_2Dto3D_model}: only the _01 and _02 variants are selectable in the reference script (:258-271)")
-    if SDE_3Dto2D_model != "SDEModel3Dto2D_node_adj_dense":
-        raise NotImplementedError(f"{SDE_3Dto2D_model}: the _dense_02/_03 ablations are out of scope (DESIGN.md section 7)")
+    if SDE_3Dto2D_model not in ("SDEModel3Dto2D_node_adj_dense", "SDEModel3Dto2D_node_adj_dense_02"):
+        raise NotImplementedError(f"{SDE_3Dto2D_model}: the _dense_03 ablation is out of scope (DESIGN.md section 7)")
     k23, lo23, hi23, n23 = resolve_sde_type(SDE_type_2Dto3D, "2Dto3D")
     k32, lo32, hi32, n32 = resolve_sde_type(SDE_type_3Dto2D, "3Dto2D")
     return {
@@ -59,7 +59,7 @@ def build_models(emb_dim: int = 300, SDE_type_2Dto3D: str = "VE", SDE_type_3Dto2
         "SDE_2Dto3D_model": getattr(M23, SDE_2Dto3D_model)(
             emb_dim=emb_dim, hidden_dim=32, beta_schedule=None, beta_min=lo23, beta_max=hi23, num_diffusion_timesteps=n23,
             SDE_type=k23, use_extend_graph=use_extend_graph),
-        "SDE_3Dto2D_model": SDEModel3Dto2D_node_adj_dense(
+        "SDE_3Dto2D_model": getattr(M32, SDE_3Dto2D_model)(
             dim3D=emb_dim, c_init=2, c_hid=8, c_final=4, num_heads=4, adim=16, nhid=16, num_layers=4, emb_dim=emb_dim,
             num_linears=3, beta_min=lo32, beta_max=hi32, num_diffusion_timesteps=n32, SDE_type=k32, num_class_X=119,
             noise_on_one_hot=noise_on_one_hot),
@@ -81,6 +81,14 @@ def variant_of(state_dict: Dict[str, torch.Tensor]) -> str:
     return "SDEModel2Dto3D_02" if "input_mlp.layers.0.weight" in state_dict else "SDEModel2Dto3D_01"
 
 
+def variant_3d2d_of(state_dict: Dict[str, torch.Tensor]) -> str:
+    """Which 3D->2D class a `SDE_3Dto2D_model` state_dict belongs to: `_dense_02` feeds its score networks the 2 x dim3D-wide
+    concatenation (`SDE_model_3D_to_2D_node_adj_dense.py:225-236`), visible in the first GCN weight of the node network."""
+    w = state_dict["node_score_network.layers.0.weight"]
+    f = state_dict["embedding_3D.weight"].shape[0]
+    return "SDEModel3Dto2D_node_adj_dense_02" if w.shape[0] == 2 * f else "SDEModel3Dto2D_node_adj_dense"
+
+
 def load_model(path: str, models: Optional[Dict[str, nn.Module]] = None, strict: bool = True, **build_kwargs) -> Dict[str, nn.Module]:
     """Load a reference-format checkpoint.  Without `models`, the module set is built first (`build_models(**build_kwargs)`),
     picking the 2D->3D variant from the keys present in the file.  Entries missing from the file (the fine-tuning scripts
@@ -89,6 +97,8 @@ def load_model(path: str, models: Optional[Dict[str, nn.Module]] = None, strict:
     if models is None:
         if "SDE_2Dto3D_model" in blob:
             build_kwargs.setdefault("SDE_2Dto3D_model", variant_of(blob["SDE_2Dto3D_model"]))
+        if "SDE_3Dto2D_model" in blob:
+            build_kwargs.setdefault("SDE_3Dto2D_model", variant_3d2d_of(blob["SDE_3Dto2D_model"]))
         models = build_models(**build_kwargs)
     for k in KEYS:
         if k in blob:

@@ -745,7 +745,12 @@ def tape_3d2d(tp: Tape, model, P: Dict[str, Var], h3d: Var, data, anneal_power: 
     # ---- embedding :156
     e3 = tp.linear(rep_v, P["embedding_3D.weight"], P["embedding_3D.bias"])
     ex = tp.linear(Var(p_x.view(rows, K)), P["embedding_X.weight"], P["embedding_X.bias"])
-    emb = tp.add(e3, ex)
+    if getattr(model, "concat_embedding", False):   # `_dense_02` (:333): cat([embedding_3D, embedding_X], -1)
+        emb = Var(tp.empty(rows, 2 * F), False)
+        tp.copy_cols(e3, emb, 0)
+        tp.copy_cols(ex, emb, F)
+    else:
+        emb = tp.add(e3, ex)
 
     # ---- EdgeScoreNetwork_dense (invariant_scorenetwork_dense.py:74-93)
     esn = model.edge_score_network

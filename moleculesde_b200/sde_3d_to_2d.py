@@ -346,6 +346,8 @@ class NodeScoreNetwork_dense(nn.Module):
 
 
 class SDEModel3Dto2D_node_adj_dense(nn.Module):
+    concat_embedding = False   # True in SDEModel3Dto2D_node_adj_dense_02: cat([embedding_3D, embedding_X]) instead of their sum
+
     def __init__(self, dim3D, nhid, num_layers, num_linears, c_hid, c_final, adim, emb_dim, beta_min, beta_max,
                  num_diffusion_timesteps, c_init=1, num_heads=4, conv="MLP", noise_mode="discrete", SDE_type="VE",
                  num_class_X=119, noise_on_one_hot=True):
@@ -367,10 +369,11 @@ class SDEModel3Dto2D_node_adj_dense(nn.Module):
         self.num_class_X, self.noise_on_one_hot = num_class_X, noise_on_one_hot
         self.embedding_X = nn.Linear(num_class_X, dim3D)
         self.embedding_3D = nn.Linear(dim3D, dim3D)
-        self.edge_score_network = EdgeScoreNetwork_dense(dim3D=dim3D, nhid=nhid, num_layers=num_layers, num_linears=num_linears,
+        net_in = 2 * dim3D if self.concat_embedding else dim3D
+        self.edge_score_network = EdgeScoreNetwork_dense(dim3D=net_in, nhid=nhid, num_layers=num_layers, num_linears=num_linears,
                                                          c_init=c_init, c_hid=c_hid, c_final=c_final, adim=adim, num_heads=4,
                                                          conv=conv)
-        self.node_score_network = NodeScoreNetwork_dense(nfeat=dim3D, depth=num_layers, nhid=nhid, nout=num_class_X)
+        self.node_score_network = NodeScoreNetwork_dense(nfeat=net_in, depth=num_layers, nhid=nhid, nout=num_class_X)
 
     # ---- `embedding_3D(representation) + embedding_X(x)` (:156; inference_3D_to_2D:228,240; SDE_dense.py:88,99) ----
     @torch.no_grad()
@@ -382,6 +385,12 @@ class SDEModel3Dto2D_node_adj_dense(nn.Module):
         """`rep3d`: a cached `embed_3d(representation)` (the 3D part does not change along a sampling trajectory)."""
         if rep3d is None:
             rep3d = self.embed_3d(representation)
+        if self.concat_embedding:   # `_dense_02` (:333): [B,Nm,2F] = cat([embedding_3D(rep), embedding_X(x)], -1)
+            F = self.nfeat
+            out = torch.empty(*x.shape[:-1], 2 * F, dtype=torch.float32, device=x.device)
+            out[..., :F].copy_(rep3d.view(*x.shape[:-1], F))
+            linear(x.contiguous().float(), self.embedding_X.weight, self.embedding_X.bias, out=out[..., F:])
+            return out
         return linear(x.contiguous().float(), self.embedding_X.weight, self.embedding_X.bias, residual=rep3d)
 
     def get_score_fn(self, sde, model, train=True, continuous=True):
@@ -484,3 +493,11 @@ class SDEModel3Dto2D_node_adj_dense(nn.Module):
         losses_x = graph_reduce(score_x, z_x, wx, 1)
         losses_adj = graph_reduce(score_adj, z_adj, wa, 1)
         return torch.mean(losses_x), torch.mean(losses_adj)
+
+
+class SDEModel3Dto2D_node_adj_dense_02(SDEModel3Dto2D_node_adj_dense):
+    """`SDE_model_3D_to_2D_node_adj_dense.py:182-350`: the variant whose score networks see the CONCATENATION of
+    `embedding_3D(representation)` and `embedding_X(perturbed x)` (600 features) instead of their sum (`:333`).  Same constructor,
+    `forward` / `get_score_fn` signatures and state_dict keys as the reference class; the same kernels (the first-layer GEMMs and the
+    node network's final MLP are simply wider: 664 -> 1328 -> 1328 -> 119)."""
+    concat_embedding = True

@@ -421,3 +421,82 @@ def test_gpu_gnn_forward_without_batch_vector(golden):
     h1 = gnn(b2)
     assert torch.equal(h1, h3)
     assert dt < 1.0, f"3-argument GNN forward on {b.x.size(0)} atoms took {dt:.2f} s"
+
+
+# ------------------------------------------------------------------------------------------------
+# SDEModel3Dto2D_node_adj_dense_02 (SDE_model_3D_to_2D_node_adj_dense.py:182-350): fixture tests/golden/golden_dense02.pt
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gd02():
+    return torch.load(os.path.join(HERE, "golden", "golden_dense02.pt"), weights_only=False)
+
+
+def _dense02(kind, gd02, golden):
+    from moleculesde_b200.sde_3d_to_2d import SDEModel3Dto2D_node_adj_dense_02
+    m = SDEModel3Dto2D_node_adj_dense_02(
+        dim3D=300, c_init=2, c_hid=8, c_final=4, num_heads=4, adim=16, nhid=16, num_layers=4, emb_dim=300, num_linears=3,
+        beta_min=0.1 if kind == "VE" else 0.2, beta_max=1.0, num_diffusion_timesteps=1000, SDE_type=kind, num_class_X=119,
+        noise_on_one_hot=True)
+    man = gd02["dense02_" + kind]["manifest"]
+    assert {k: (tuple(v.shape), str(v.dtype)) for k, v in m.state_dict().items()} == man
+    m.load_state_dict(sd_from_manifest(man, golden["meta"]["weight_seed"]))
+    return m
+
+
+def test_dense02_state_dict_and_checkpoint_detection(gd02, golden, tmp_path):
+    """Same keys / shapes as the reference class; a checkpoint holding it is recognised and rebuilt by `load_model`."""
+    from moleculesde_b200 import checkpoint as C
+    m = _dense02("VE", gd02, golden)
+    assert C.variant_3d2d_of(m.state_dict()) == "SDEModel3Dto2D_node_adj_dense_02"
+    models = C.build_models(SDE_3Dto2D_model="SDEModel3Dto2D_node_adj_dense_02")
+    models["SDE_3Dto2D_model"].load_state_dict(m.state_dict())
+    path = C.save_model(models, str(tmp_path))
+    back = C.load_model(path)
+    assert type(back["SDE_3Dto2D_model"]).__name__ == "SDEModel3Dto2D_node_adj_dense_02"
+    for k, v in m.state_dict().items():
+        assert torch.equal(back["SDE_3Dto2D_model"].state_dict()[k], v)
+    plain = C.build_models()
+    assert C.variant_3d2d_of(plain["SDE_3Dto2D_model"].state_dict()) == "SDEModel3Dto2D_node_adj_dense"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["VE", "VP"])
+def test_gpu_dense02_scores_losses_and_gradients(kind, gd02, golden, golden_batch):
+    """Both scores on the fixed perturbed state, both DSM losses with the recorded draws, every parameter gradient and
+    d loss / d h3d of (loss_x + loss_adj) / 2 -- against the unmodified reference (1e-4)."""
+    from test_gpu_pretrain import REL_TOL, _check_module_grads, check_grad_summary
+    from test_gpu_sde2d3d import assert_parity
+    from moleculesde_b200.pretrain import ParamStore, tape_3d2d
+    from moleculesde_b200.tape import Tape, Var
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    dev = torch.device("cuda:0")
+    sec, fix = gd02["dense02_" + kind], golden["sde3d2d_" + kind]
+    _, batch = golden_batch
+    m = _dense02(kind, gd02, golden).to(dev).eval()
+    b = batch.to(dev)
+    h3d = golden["schnet"]["h"].to(dev)
+    _, rep, _, flags, Nm = m.dense_inputs(h3d, b)
+    assert Nm == fix["nmax"] and torch.equal(flags.cpu(), fix["flags"])
+    emb = m.embed(rep, fix["x"].to(dev))
+    assert emb.shape[-1] == 600
+    s_a = m.get_score_fn(m.sde_adj, m.edge_score_network, train=False)(emb, fix["adj"].to(dev), flags, fix["t"].to(dev))
+    s_x = m.get_score_fn(m.sde_x, m.node_score_network, train=False)(emb, fix["adj"].to(dev), flags, fix["t"].to(dev))
+    assert_parity(s_a, sec["score_adj"], f"dense_02 edge score [{kind}]")
+    assert_parity(s_x, sec["score_x"], f"dense_02 node score [{kind}]")
+    lx, la = m(h3d, b, continuous=True, train=False, reduce_mean=True, anneal_power=0, draws=sec["draws"])
+    assert abs(float(lx) - float(sec["loss_x"])) <= REL_TOL * abs(float(sec["loss_x"]))
+    assert abs(float(la) - float(sec["loss_adj"])) <= REL_TOL * abs(float(sec["loss_adj"]))
+    # training tape: losses + gradients
+    m.train()
+    store = ParamStore({"sde3d2d": m}, dev)
+    tp = Tape(dev)
+    hv = Var(h3d.contiguous(), True)
+    lx, la = tape_3d2d(tp, m, store.vars("sde3d2d"), hv, b, 0.0, sec["draws"], coef=0.5)
+    assert abs(float(lx) - float(sec["loss_x"])) <= REL_TOL * abs(float(sec["loss_x"]))
+    assert abs(float(la) - float(sec["loss_adj"])) <= REL_TOL * abs(float(sec["loss_adj"]))
+    tp.backward()
+    torch.cuda.synchronize()
+    _check_module_grads(store, "sde3d2d", {"grads": {"sde3d2d": sec["grads"]}}, tag="dense02.")
+    d = hv.grad.cpu()
+    assert float((d - sec["d_h3d"]).abs().max() / sec["d_h3d"].abs().max()) < REL_TOL
