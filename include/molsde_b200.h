@@ -354,6 +354,15 @@ int molsde_schnet_edge_feat(const float* pos, const int32_t* src, const int32_t*
 int molsde_schnet_edge_feat_bwd(const float* pos, const int32_t* src, const int32_t* tgt, int64_t E, const float* mu, int32_t ng,
                                 float coeff, float cutoff, const float* ea, const float* dea, const float* dC, float* g, void* stream);
 int molsde_rowdot(const float* a, const float* b, int64_t rows, int32_t cols, int32_t accumulate, float* out, void* stream);
+/* Second-order pieces of SchNet (a force term INSIDE the training loss: examples/finetune_MD17.py:66-77 differentiates
+ * pred_force = -grad(E, pos, create_graph=True) with respect to the parameters).  The host propagates a forward-mode tangent
+ * along the position displacement v = d loss / d force through the network (the same GEMM / CFConv / activation kernels) and
+ * back-propagates through primal + tangent; the two kernels it needs beyond the first-order set:
+ *   act_bwd2:                out (+)= act''(x) * a * b          (x = pre-activation)
+ *   schnet_edge_feat_tangent: ea_dot[e,k], C_dot[e] = d/d eps of GaussianSmearing / cosine cutoff at pos + eps v (schnet.py:185-188) */
+int molsde_act_bwd2(const float* x, const float* a, const float* b, int64_t n, int32_t act, int32_t accumulate, float* out, void* stream);
+int molsde_schnet_edge_feat_tangent(const float* pos, const float* v, const int32_t* src, const int32_t* tgt, int64_t E, const float* mu,
+                                    int32_t ng, float coeff, float cutoff, const float* ea, float* ea_dot, float* C_dot, void* stream);
 /* backward of molsde_ebm_node_dot's loss_acc[0] scaled by coef; invperm = inverse permutation of perm */
 int molsde_ebm_node_dot_bwd(const float* X, const float* Y, const int64_t* perm, const int64_t* invperm, const float* pred_pos,
                             const float* pred_neg, int64_t N, int32_t D, float T, float coef, int32_t accumulate, float* dX, float* dY,

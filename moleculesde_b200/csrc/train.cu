@@ -129,6 +129,24 @@ __device__ __forceinline__ float act_df(float x, int act) {
         default: return 1.0f;
     }
 }
+// second derivative of the activations (double backward of SchNet: a force term inside the training loss, finetune_MD17.py:66-77)
+__device__ __forceinline__ float act_d2f(float x, int act) {
+    switch (act) {
+        case 2: { const float s = 1.0f / (1.0f + expf(-x)); return s * (1.0f - s) * (2.0f + x * (1.0f - 2.0f * s)); }
+        case 3: { const float s = 1.0f / (1.0f + expf(-x)); return s * (1.0f - s); }
+        case 4: { const float t = tanhf(x); return -2.0f * t * (1.0f - t * t); }
+        case 5: return x > 0.0f ? 0.0f : expf(x);
+        default: return 0.0f;   // identity, relu
+    }
+}
+// out = act''(x) * a * b  (+ out if accumulate)
+__global__ void act_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b, int64_t n, int act,
+                                int accumulate, float* __restrict__ out) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const float v = act_d2f(x[i], act) * a[i] * b[i];
+    out[i] = accumulate ? out[i] + v : v;
+}
 __global__ void act_fwd_kernel(const float* __restrict__ x, int64_t n, int act, float* __restrict__ y) {
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (i < n) y[i] = act_f(x[i], act);
@@ -333,6 +351,30 @@ __global__ void schnet_edge_feat_kernel(const float* __restrict__ pos, const int
     const float t = d - mu[k];
     ea[idx] = expf(coeff * (t * t));
     if (k == 0) C[e] = 0.5f * (cosf(d * 3.14159274101257324f / cutoff) + 1.0f);
+}
+
+// Directional derivative of the edge features along a displacement field v [N,3] of the positions (forward-mode tangent; the
+// double backward of SchNet differentiates  <v, dE/dpos> = d/d eps E(pos + eps v)  with respect to the parameters):
+//   dd = <pos[src] - pos[tgt], v[src] - v[tgt]> / d;   ea_dot[e,k] = ea[e,k] 2 coeff (d - mu_k) dd;   C_dot[e] = -pi/(2 cutoff) sin(pi d/cutoff) dd
+__global__ void schnet_edge_feat_tangent_kernel(const float* __restrict__ pos, const float* __restrict__ v, const int32_t* __restrict__ src,
+                                                const int32_t* __restrict__ tgt, int64_t E, const float* __restrict__ mu, int ng,
+                                                float coeff, float cutoff, const float* __restrict__ ea, float* __restrict__ ea_dot,
+                                                float* __restrict__ C_dot) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= E * ng) return;
+    const int64_t e = idx / ng;
+    const int k = static_cast<int>(idx % ng);
+    const int r = src[e], c = tgt[e];
+    const float dx = __fsub_rn(pos[3 * r], pos[3 * c]), dy = __fsub_rn(pos[3 * r + 1], pos[3 * c + 1]),
+                dz = __fsub_rn(pos[3 * r + 2], pos[3 * c + 2]);
+    const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float pv = dx * (v[3 * r] - v[3 * c]) + dy * (v[3 * r + 1] - v[3 * c + 1]) + dz * (v[3 * r + 2] - v[3 * c + 2]);
+    const float dd = d > 0.0f ? pv / d : 0.0f;
+    ea_dot[idx] = ea[idx] * (2.0f * coeff * (d - mu[k])) * dd;
+    if (k == 0) {
+        const float w = 3.14159274101257324f / cutoff;
+        C_dot[e] = -0.5f * w * sinf(d * w) * dd;
+    }
 }
 
 // ---- d/d pos of the SchNet edge features (finetune_MD17.py:66: force = -dE/dpos) ----
@@ -667,6 +709,20 @@ int molsde_act_bwd(const float* x, const float* dy, int64_t n, int32_t act, floa
     if (n == 0) return MOLSDE_OK;
     act_bwd_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(x, dy, n, act, dx);
     return check_launch("act_bwd");
+}
+int molsde_act_bwd2(const float* x, const float* a, const float* b, int64_t n, int32_t act, int32_t accumulate, float* out, void* stream) {
+    if (!x || !a || !b || !out || n < 0) return MOLSDE_ERR_INVALID;
+    if (n == 0) return MOLSDE_OK;
+    act_bwd2_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(x, a, b, n, act, accumulate, out);
+    return check_launch("act_bwd2");
+}
+int molsde_schnet_edge_feat_tangent(const float* pos, const float* v, const int32_t* src, const int32_t* tgt, int64_t E, const float* mu,
+                                    int32_t ng, float coeff, float cutoff, const float* ea, float* ea_dot, float* C_dot, void* stream) {
+    if (!pos || !v || !src || !tgt || !mu || !ea || !ea_dot || !C_dot || E < 0 || ng < 1) return MOLSDE_ERR_INVALID;
+    if (E == 0) return MOLSDE_OK;
+    schnet_edge_feat_tangent_kernel<<<blocks_for(E * ng), 256, 0, as_stream(stream)>>>(pos, v, src, tgt, E, mu, ng, coeff, cutoff, ea, ea_dot,
+                                                                                    C_dot);
+    return check_launch("schnet_edge_feat_tangent");
 }
 int molsde_ew(int32_t op, const float* a, const float* b, const float* c, float alpha, int64_t n, int64_t cols, float* out,
               void* stream) {

@@ -474,6 +474,57 @@ def tape_schnet(tp: Tape, model, P: Dict[str, Var], z: torch.Tensor, pos: torch.
     return tp.linear(h, P["lin2.weight"], P["lin2.bias"])
 
 
+def tape_schnet_dual(tp: Tape, model, P: Dict[str, Var], z: torch.Tensor, pos: torch.Tensor, vdir: torch.Tensor, batch: torch.Tensor,
+                     num_graphs: int, cache: Optional[dict]):
+    """SchNet node representation h [N, hidden] TOGETHER with its directional derivative h_dot = d/d eps h(pos + eps vdir)
+    (forward-mode tangent), every op recorded on the tape, so that a reverse sweep seeded on h_dot yields
+    d/d theta <vdir, d(.)/d pos> -- the parameter gradient of a force term (`finetune_MD17.py:66-77`).  The tangent flows through
+    the same kernels as the primal: Linear without bias, `act_tangent` (act', with act'' in its backward), CFConv applied to
+    (x_dot, W) and (x, W_dot); the edge features' tangent (GaussianSmearing, cosine cutoff) does not depend on the parameters and
+    is one forward kernel.  Returns (h, h_dot)."""
+    L, dev = tp.L, pos.device
+    require_device(pos)
+    pos = pos.detach().float().contiguous()
+    vdir = vdir.detach().float().contiguous()
+    cache = cache if cache is not None else {}
+    prepare_schnet(cache, model, z, pos, batch, num_graphs)
+    es, zkeys, zidx, ea, C = cache["schnet"]
+    E, ng = es.E, model.num_gaussians
+    ea_dot, C_dot = tp.empty(E, ng), tp.empty(max(E, 1))
+    tp._call(L.molsde_schnet_edge_feat_tangent, ptr(pos), ptr(vdir), ptr(es.src.idx), ptr(es.tgt.idx), E,
+             ptr(model.distance_expansion.offset), ng, float(model.distance_expansion.coeff), float(model.cutoff), ptr(ea), ptr(ea_dot),
+             ptr(C_dot), tp.s, what="schnet_edge_feat_tangent")
+    ea_v, ead_v = Var(ea, False), Var(ea_dot, False)
+    Cc, Cd = C[:E], C_dot[:E]
+    h = tp.embed_sum(P["embedding.weight"], zkeys, zidx)
+    hd = None                                        # the embedding does not depend on the positions
+    for i in range(model.num_interactions):
+        pf = f"interactions.{i}."
+        W0, b0, W2, b2 = P[pf + "mlp.0.weight"], P[pf + "mlp.0.bias"], P[pf + "mlp.2.weight"], P[pf + "mlp.2.bias"]
+        p1 = tp.linear(ea_v, W0, b0)
+        f2 = tp.linear(tp.act(p1, "ssp"), W2, b2)
+        Wf = tp.rowscale(f2, Cc)
+        f2d = tp.linear(tp.act_tangent(p1, tp.linear(ead_v, W0, None), "ssp"), W2, None)
+        Wfd = tp.add(tp.rowscale(f2d, Cc), tp.rowscale(f2, Cd))
+        W1 = P[pf + "conv.lin1.weight"]
+        x = tp.linear(h, W1, None)
+        agg = tp.edge_mul_reduce(x, Wf, es.rowptr, es.src, es.tgt)
+        aggd = tp.edge_mul_reduce(x, Wfd, es.rowptr, es.src, es.tgt)
+        if hd is not None:
+            aggd = tp.add(aggd, tp.edge_mul_reduce(tp.linear(hd, W1, None), Wf, es.rowptr, es.src, es.tgt))
+        Wc, bc = P[pf + "conv.lin2.weight"], P[pf + "conv.lin2.bias"]
+        p2 = tp.linear(agg, Wc, bc)
+        td = tp.act_tangent(p2, tp.linear(aggd, Wc, None), "ssp")
+        Wl, bl = P[pf + "lin.weight"], P[pf + "lin.bias"]
+        h = tp.add(h, tp.linear(tp.act(p2, "ssp"), Wl, bl))
+        ud = tp.linear(td, Wl, None)
+        hd = ud if hd is None else tp.add(hd, ud)
+    p3 = tp.linear(h, P["lin1.weight"], P["lin1.bias"])
+    out = tp.linear(tp.act(p3, "ssp"), P["lin2.weight"], P["lin2.bias"])
+    outd = tp.linear(tp.act_tangent(p3, tp.linear(hd, P["lin1.weight"], None), "ssp"), P["lin2.weight"], None)
+    return out, outd
+
+
 # ======================================================================================================
 # dual_CL, EBM_node_dot_prod (examples/util.py:52-79)
 # ======================================================================================================

@@ -164,9 +164,17 @@ class SchNet(nn.Module):
                     out.grad = gouts[0]
                     h.grad = None if gouts[1] is None else gouts[1].clone()   # the readout backward accumulates into it in place
                 return [out.data, h.data], seed
+            def dual(tp, ins, tans, P):
+                """primal + forward-mode tangent along a position displacement (the double backward of the force term)"""
+                from .pretrain import tape_schnet_dual
+                h, hd = tape_schnet_dual(tp, self, P, z.contiguous(), pos, tans[0], batch, num_graphs, {})
+                out = tp.segment_readout(h, node_ptr, row2seg, mean)
+                outd = tp.segment_readout(hd, node_ptr, row2seg, mean)
+                return [out, h], [outd, hd]
             # positions take part in autograd only when the caller asked for it (`positions.requires_grad_()`, finetune_MD17.py:49):
-            # first-order forces -dE/dpos; `create_graph=True` (a force term inside the training loss) is not supported
-            out, h = AG.apply(self, build, [pos] if pos.requires_grad else [])
+            # forces -dE/dpos; with `create_graph=True` (a force term inside the training loss, :66-77) the force is itself
+            # differentiable in the parameters through the tangent builder above
+            out, h = AG.apply(self, build, [pos] if pos.requires_grad else [], dual=dual)
             return (out, h) if return_latent else out
         with torch.no_grad():
             return self._forward_inference(z, pos, batch, num_graphs, return_latent)

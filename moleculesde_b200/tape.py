@@ -318,6 +318,29 @@ class Tape:
             self.ops.append(bwd)
         return out
 
+    def act_tangent(self, pre: Var, xdot: Var, act: str) -> Var:
+        """Forward-mode tangent of y = act(pre): ydot = act'(pre) * xdot, differentiable in BOTH arguments
+        (d pre += act''(pre) * xdot * dydot, d xdot = act'(pre) * dydot) -- the op the double backward of SchNet is built from."""
+        a = ACT[act]
+        y = self.empty(pre.data.shape)
+        self._call(self.L.molsde_act_bwd, _p(pre.data), _p(xdot.data), y.numel(), a, _p(y), self.s, what="act_bwd")
+        out = Var(y, pre.needs or xdot.needs)
+        if out.needs:
+            def bwd():
+                if out.grad is None:
+                    return
+                if xdot.needs:
+                    g = self.empty(y.shape)
+                    self._call(self.L.molsde_act_bwd, _p(pre.data), _p(out.grad), g.numel(), a, _p(g), self.s, what="act_bwd")
+                    self.accum(xdot, g)
+                if pre.needs:
+                    g = self.empty(y.shape)
+                    self._call(self.L.molsde_act_bwd2, _p(pre.data), _p(xdot.data), _p(out.grad), g.numel(), a, 0, _p(g), self.s,
+                               what="act_bwd2")
+                    self.accum(pre, g)
+            self.ops.append(bwd)
+        return out
+
     def add(self, a: Var, b: Var, alpha: float = 1.0) -> Var:
         y = self.empty(a.data.shape)
         self.ew(0, a.data, b.data, None, alpha, y)
