@@ -111,13 +111,21 @@ class ParamStore:
     def zero_grad(self) -> None:
         self.grad.zero_()  # cudaMemsetAsync
 
-    def all_reduce(self) -> float:
-        """Data-parallel gradient exchange: one NCCL all-reduce (sum) over the flat buffer; returns 1/world for Adam."""
+    def all_reduce(self, modules: Optional[Sequence[str]] = None, async_op: bool = False):
+        """Data-parallel gradient exchange: NCCL all-reduce (sum) over the flat buffer, or over the contiguous slice that holds the
+        gradients of `modules` (a bucket).  Returns 1/world for Adam -- with `async_op`, (1/world, work handle): the collective is
+        ordered after the current stream's work and runs on NCCL's stream, `work.wait()` makes the current stream wait for it."""
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
-            return 1.0 / dist.get_world_size()
-        return 1.0
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return (1.0, None) if async_op else 1.0
+        buf = self.grad
+        if modules is not None:
+            spans = sorted(self.ranges[m] for m in modules if self.ranges[m][1] > self.ranges[m][0])
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1)), "bucket modules must be adjacent in the flat buffer"
+            buf = self.grad[spans[0][0]:spans[-1][1]]
+        work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=async_op)
+        scale = 1.0 / dist.get_world_size()
+        return (scale, work) if async_op else scale
 
     def adam_step(self, lr: float = 1e-4, lr_scale: Optional[Dict[str, float]] = None, betas=(0.9, 0.999), eps: float = 1e-8,
                   weight_decay: float = 0.0, grad_scale: float = 1.0, skip: Sequence[str] = ()) -> None:
@@ -919,8 +927,11 @@ class PretrainStep:
                 batch._molsde_dense_dims = (batch.num_graphs, int(max_nodes), node_ptr)
         return batch
 
-    def forward_backward(self, batch, draws: Optional[dict] = None) -> Dict[str, torch.Tensor]:
-        """Forward + backward of one batch; gradients are left in `store.grad`.  `draws` (parity tests):
+    def forward_backward(self, batch, draws: Optional[dict] = None, split: bool = False):
+        """Forward + backward of one batch; gradients are left in `store.grad`.  `split=True` stops after the loss branches
+        (forward of everything, backward of dual_CL / 2D->3D / 3D->2D: the gradients of the two SDE models are final) and returns
+        `(out, finish)`; `finish()` runs the two encoder backwards.  Data-parallel callers put the all-reduce of the SDE models'
+        gradient bucket between the two halves, so that it overlaps the encoders' backward (`step`, bench.py).  `draws` (parity tests):
         {"cl": (perm1, perm2), "sde2d3d": {...}, "sde3d2d": [randint, randn_adj, randn_x]}.
 
         The iteration is a fork/join graph, not a chain (pretrain_MoleculeSDE.py:131-147: the two encoders are independent, and
@@ -936,7 +947,11 @@ class PretrainStep:
         bit-identical to the single-stream order (`MOLSDE_SINGLE_STREAM=1`)."""
         caller = torch.cuda.current_stream(self.dev) if self.dev.type == "cuda" else None
         if caller is None or _SINGLE_STREAM:
-            return self._forward_backward(batch, draws or {}, caller, caller, caller, None, None)
+            out, fin = self._forward_backward(batch, draws or {}, caller, caller, caller, None, None)
+            if split:
+                return out, fin
+            fin()
+            return out
         if self._streams is None:
             # the dependent chains (branch streams) get the high priority, the weight-gradient side streams the low one: a
             # pending CTA of the critical path is scheduled before the leaves that only have to finish by the end of the step
@@ -947,9 +962,20 @@ class PretrainStep:
             w0 = w1 = None
         s0.wait_stream(caller)
         with torch.cuda.stream(s0):
-            out = self._forward_backward(batch, draws or {}, s0, s1, s2, w0, w1)
+            out, fin = self._forward_backward(batch, draws or {}, s0, s1, s2, w0, w1)
+            if not split:
+                fin()
         caller.wait_stream(s0)
-        return out
+        if not split:
+            return out
+
+        def finish():
+            cur = torch.cuda.current_stream(self.dev)
+            s0.wait_stream(cur)
+            with torch.cuda.stream(s0):
+                fin()
+            cur.wait_stream(s0)
+        return out, finish
 
     def _forward_backward(self, batch, draws, main, s1, s2, w0, w1) -> Dict[str, torch.Tensor]:
         st = self.store
@@ -1011,28 +1037,44 @@ class PretrainStep:
             g2d.append(cl2)
             g3d.append(cl3)
         launches = sum(t.launches for t in keep if isinstance(t, Tape))
-        # ---- join, add the branch gradients (fixed order: SDE branch, then CL), encoder backwards on main / s1
+        # ---- join: every loss branch is done (the gradients of sde2d3d / sde3d2d are final here)
         fork(main, s1, s2)
         fork(s1, main, s2)
-        for v in g2d:
-            if v.grad is not None:
-                tp_g.accum(h2d, v.grad)
-        tp_g.backward()
-        with torch.cuda.stream(s1):
-            for v in g3d:
-                if v.grad is not None:
-                    tp_s.accum(h3d, v.grad)
-            tp_s.backward()
-        fork(main, s1)
-        self.launches = launches + tp_g.launches + tp_s.launches
         out["h2d"], out["h3d"] = h2d, h3d
         out["_keep"] = keep
-        return out
+
+        def finish():
+            """add the branch gradients (fixed order: SDE branch, then CL), encoder backwards on main / s1"""
+            fork(s1, main)
+            for v in g2d:
+                if v.grad is not None:
+                    tp_g.accum(h2d, v.grad)
+            tp_g.backward()
+            with torch.cuda.stream(s1):
+                for v in g3d:
+                    if v.grad is not None:
+                        tp_s.accum(h3d, v.grad)
+                tp_s.backward()
+            fork(main, s1)
+            self.launches = launches + tp_g.launches + tp_s.launches
+        return out, finish
+
+    SDE_BUCKET, ENCODER_BUCKET = ("sde2d3d", "sde3d2d"), ("gnn", "schnet")
 
     def step(self, batch, draws: Optional[dict] = None) -> Dict[str, torch.Tensor]:
-        out = self.forward_backward(batch, draws)
-        scale = self.store.all_reduce()
+        """One iteration.  Data-parallel: the gradient all-reduce runs in two buckets -- the SDE models' gradients are final when
+        the loss branches end, their exchange overlaps the encoders' backward; the encoders' bucket follows."""
+        import torch.distributed as dist
         skip = [m for m, c in (("sde2d3d", self.c_23), ("sde3d2d", self.c_32)) if not c > 0]
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            out, finish = self.forward_backward(batch, draws, split=True)
+            scale, work = self.store.all_reduce(self.SDE_BUCKET, async_op=True)
+            finish()
+            work.wait()
+            self.store.all_reduce(self.ENCODER_BUCKET)
+        else:
+            out = self.forward_backward(batch, draws)
+            scale = 1.0
         self.store.adam_step(self.lr, self.lr_scale, weight_decay=self.weight_decay, grad_scale=scale, skip=skip)
         return out
 

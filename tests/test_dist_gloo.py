@@ -75,6 +75,20 @@ def _dp_worker(rank, world, port, out):
     store.grad_view("a", "weight").fill_(float(rank + 1))      # rank-dependent gradients
     store.grad_view("b", "1.bias").fill_(10.0 * (rank + 1))
     scale = store.all_reduce()
+    # bucketed exchange (PretrainStep.step: the SDE models' bucket overlaps the encoders' backward): a bucket = the contiguous slice of
+    # the modules' gradients; the async form returns a work handle; together the buckets equal one whole-buffer all-reduce
+    whole = store.grad.clone()
+    store.grad_view("a", "weight").fill_(float(rank + 1))
+    store.grad_view("a", "bias").zero_()
+    for n in ("0.weight", "0.bias", "1.weight"):
+        store.grad_view("b", n).zero_()
+    store.grad_view("b", "1.bias").fill_(10.0 * (rank + 1))
+    s2, work = store.all_reduce(("b",), async_op=True)
+    assert work is not None and s2 == scale
+    work.wait()
+    assert torch.all(store.grad_view("a", "weight") == float(rank + 1)), "the other bucket is untouched"
+    store.all_reduce(("a",))
+    assert torch.equal(store.grad, whole)
     res = (scale, store.grad_view("a", "weight").clone(), store.grad_view("b", "1.bias").clone(), store.numel)
     if rank == 0:
         out.put(res)

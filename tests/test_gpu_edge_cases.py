@@ -49,7 +49,8 @@ def test_get_score_degenerate_molecules(golden):
 
 
 def test_pc_group_at_size_limit_and_overflow(golden):
-    """A sampling group of 11 x 20 = 220 atoms (limit 224) runs; 12 x 20 = 240 atoms is rejected before launch."""
+    """A sampling group of 11 x 20 = 220 atoms (the fused kernel's limit is 224) runs in one CTA; 12 x 20 = 240 atoms takes the
+    step-wise path (score kernel over molecule chunks + per-group update kernels) and follows the same oracle trajectory."""
     import numpy as np
     from moleculesde_b200 import _abi
     from moleculesde_b200.data import repeat_data, synth_molecule
@@ -69,9 +70,17 @@ def test_pc_group_at_size_limit_and_overflow(golden):
     _, ref = O.pc_sample_2d3d(sd, O.make_sde("VE", 0.2, 1.0, 1000), rep, b.extended_edge_index.cpu(), rb.batch, rb.num_graphs, pos0,
                               nc, npd, n_diff_steps=steps)
     assert rel_err(pm.cpu(), ref) < 1e-3
-    big = _gpu_batch(repeat_data(mol, 12), dev)
-    with pytest.raises(_abi.MolsdeError):
-        position_PC_generation(torch.randn(240, 300).to(dev), big, torch.randn(240, 3).to(dev), model, model.sde_pos, diffusion_steps=1)
+    rb2 = repeat_data(mol, 12)
+    big = _gpu_batch(rb2, dev)
+    N2 = rb2.positions.size(0)
+    assert N2 == 240 > _abi.CHUNK_MAX_NODES
+    rep2, pos2 = torch.randn(N2, 300, generator=g), torch.randn(N2, 3, generator=g)
+    nc2, npd2 = torch.randn(steps, N2, 3, generator=g), torch.randn(steps, N2, 3, generator=g)
+    _, pm2 = position_PC_generation(rep2.to(dev), big, pos2.to(dev), model, model.sde_pos, noise_corr=nc2.to(dev), noise_pred=npd2.to(dev),
+                                    diffusion_steps=steps)
+    _, ref2 = O.pc_sample_2d3d(sd, O.make_sde("VE", 0.2, 1.0, 1000), rep2, big.extended_edge_index.cpu(), rb2.batch, rb2.num_graphs, pos2,
+                               nc2, npd2, n_diff_steps=steps)
+    assert rel_err(pm2.cpu(), ref2) < 1e-3
 
 
 @pytest.mark.parametrize("kind", ["VE", "VP"])
