@@ -42,6 +42,12 @@ typedef enum molsde_status {
 #define MOLSDE_HID 32              /* hidden_dim of SDEModel2Dto3D_02 (pretrain_MoleculeSDE.py:226) */
 #define MOLSDE_EMB 300             /* emb_dim (config.py:84) */
 
+/* Host-side bookkeeping behind the `molsde_plan` struct, no device work: chunk / tile boundaries from HOST copies of the CSR row pointer and the
+ * molecule offsets; `groups` (optional, [G+1] molecule offsets) fixes one chunk per sampling group.  counts_out[4] = {num_chunks,
+ * num_tiles, max tiles per chunk, offending index}; see csrc/core.cu. */
+int molsde_build_plan_host(const int64_t* rowptr, const int64_t* node_ptr, int32_t B, const int64_t* groups, int32_t G, int32_t tile_edges,
+                           int32_t max_nodes, int32_t max_tiles, int32_t* chunk_tile_ptr, int32_t* tile_tgt_ptr, int64_t* counts_out);
+
 const char* molsde_version(void);
 const char* molsde_last_error_string(void);
 /* compute capability check: returns MOLSDE_OK only on an sm_100 device */

@@ -50,7 +50,7 @@ EXPORTS = [
     "molsde_dense_sym_noise", "molsde_dense_perturb_adj", "molsde_dense_perturb_onehot", "molsde_graph_reduce",
     "molsde_langevin_step", "molsde_langevin_update", "molsde_reverse_update", "molsde_mask_rows",
     "molsde_dense_attn_sym", "molsde_dense_pair_mlp", "molsde_dense_edge_final_mlp",
-    "molsde_sde2d3d_pc_corrector_update", "molsde_sde2d3d_pc_predictor_update", "molsde_act_bwd2", "molsde_schnet_edge_feat_tangent",
+    "molsde_sde2d3d_pc_corrector_update", "molsde_sde2d3d_pc_predictor_update", "molsde_act_bwd2", "molsde_schnet_edge_feat_tangent", "molsde_build_plan_host",
 ]
 
 
@@ -228,6 +228,7 @@ def lib() -> ctypes.CDLL:
     L.molsde_sde2d3d_pc_sample.argtypes = [POINTER(Plan), POINTER(Params), c_void_p, c_void_p, c_void_p, c_void_p,
                                            POINTER(PCConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_int64, c_void_p, c_void_p, c_void_p]
+    L.molsde_build_plan_host.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     L.molsde_act_bwd2.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]
     L.molsde_schnet_edge_feat_tangent.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_float, c_float,
                                                   c_void_p, c_void_p, c_void_p, c_void_p]

@@ -46,4 +46,56 @@ int molsde_check_device(int device) {
     return MOLSDE_OK;
 }
 
+/* Host-side chunk / tile plan of a batch (the bookkeeping behind molsde_plan): chunks = runs of whole molecules (<= max_nodes atoms,
+ * greedy under an edge budget of 0.6 * max_tiles * tile_edges) or the caller's fixed groups; tiles = runs of whole target nodes with
+ * <= tile_edges incoming edges (greedy, <= tile_edges targets).  Plain sequential C over HOST arrays: the Python loop it replaces cost
+ * ~15 ms for a 1 M-edge batch.  Outputs: chunk_tile_ptr [num_chunks + 1], tile_tgt_ptr [num_tiles + 1] (capacities: B + 2 / N + 2);
+ * counts_out = {num_chunks, num_tiles, max_chunk_tiles, offending index}.  Returns MOLSDE_OK, or MOLSDE_ERR_UNSUPPORTED with
+ * counts_out[3] = the node with more than tile_edges incoming edges (code -2), the chunk beyond max_nodes (-3) or max_tiles (-4)
+ * in counts_out[2]. */
+int molsde_build_plan_host(const int64_t* rowptr, const int64_t* node_ptr, int32_t B, const int64_t* groups, int32_t G, int32_t tile_edges,
+                           int32_t max_nodes, int32_t max_tiles, int32_t* chunk_tile_ptr, int32_t* tile_tgt_ptr, int64_t* counts_out) {
+    if (!rowptr || !node_ptr || !chunk_tile_ptr || !tile_tgt_ptr || !counts_out || B < 0) return MOLSDE_ERR_INVALID;
+    const int64_t N = node_ptr[B];
+    int64_t nchunks = 0, ntiles = 0, max_ct = 0;
+    chunk_tile_ptr[0] = 0;
+    const int64_t edge_budget = static_cast<int64_t>(static_cast<double>(max_tiles) * tile_edges * 0.6);
+    int32_t m = 0, gi = 0;
+    while (groups ? gi < G : m < B) {
+        int64_t a, b;
+        if (groups) {
+            a = node_ptr[groups[gi]]; b = node_ptr[groups[gi + 1]]; ++gi;
+        } else {
+            int32_t end = m;
+            while (end < B && node_ptr[end + 1] - node_ptr[m] <= max_nodes &&
+                   rowptr[node_ptr[end + 1]] - rowptr[node_ptr[m]] <= edge_budget) ++end;
+            if (end == m) end = m + 1;   // a single big molecule: the exact checks below decide
+            a = node_ptr[m]; b = node_ptr[end]; m = end;
+        }
+        if (b - a > max_nodes) { counts_out[2] = -3; counts_out[3] = nchunks; return MOLSDE_ERR_UNSUPPORTED; }
+        int64_t ct = 0, i = a;
+        while (i < b) {
+            tile_tgt_ptr[ntiles++] = static_cast<int32_t>(i);
+            ++ct;
+            // largest j with rowptr[j] <= rowptr[i] + tile_edges  (rowptr ascending)
+            int64_t lo = i, hi = N;   // invariant: rowptr[lo] <= limit
+            const int64_t limit = rowptr[i] + tile_edges;
+            while (hi - lo > 0) {
+                const int64_t mid = lo + (hi - lo + 1) / 2;
+                if (rowptr[mid] <= limit) lo = mid; else hi = mid - 1;
+            }
+            if (lo <= i) { counts_out[2] = -2; counts_out[3] = i; return MOLSDE_ERR_UNSUPPORTED; }
+            int64_t nx = lo < b ? lo : b;
+            if (i + tile_edges < nx) nx = i + tile_edges;
+            i = nx;
+        }
+        if (ct > max_tiles) { counts_out[2] = -4; counts_out[3] = nchunks; counts_out[1] = ct; return MOLSDE_ERR_UNSUPPORTED; }
+        if (ct > max_ct) max_ct = ct;
+        chunk_tile_ptr[++nchunks] = static_cast<int32_t>(ntiles);
+    }
+    tile_tgt_ptr[ntiles] = static_cast<int32_t>(N);
+    counts_out[0] = nchunks; counts_out[1] = ntiles; counts_out[2] = max_ct; counts_out[3] = 0;
+    return MOLSDE_OK;
+}
+
 }  // extern "C"

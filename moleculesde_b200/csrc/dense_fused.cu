@@ -10,8 +10,9 @@
 //   dense_pair_mlp      adjc'[b,c',i,j] = (m_ij + m_ji) f_i f_j,  m = MLP_elu([S | adjc][b,:,i,j])              (:120-126)
 // and one for the head:
 //   dense_edge_final_mlp  out[b,i,j] = MLP_silu(all channels of all layers)[i,j] (i != j) f_i f_j scale_b     (:84-93)
-// Pairs with f_i f_j = 0 (padding atoms) are skipped: their outputs are 0 whatever the MLP returns, and nothing else reads
-// their intermediates.  m_ji: the inputs of layers >= 1 are symmetric BITWISE by construction (S is symmetrised, adjc' of the
+// Pairs with f_i f_j = 0 (padding atoms) are skipped: their outputs are 0 whatever the MLP returns (the caller zero-fills the
+// output stacks), nothing else reads their intermediates, and the kernels enumerate the n x n valid pairs of a graph densely
+// (compact valid-atom list per CTA), so padding occupies no lanes.  m_ji: the inputs of layers >= 1 are symmetric BITWISE by construction (S is symmetrised, adjc' of the
 // previous layer is (m_ij + m_ji) f f with commutative fp adds), so there m_ji == m_ij and `symmetric = 1` skips the second
 // evaluation; layer 0 sees adj, adj^2 of an arbitrary (in the reference's sampler: non-symmetric) adjacency and evaluates
 // the transposed pair too.  All math is fp32 FFMA with the weights broadcast from shared memory (rows are independent:
@@ -42,6 +43,24 @@ __device__ __forceinline__ float df_elu(float v) {
 }
 __device__ __forceinline__ float df_silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
+// Compact list of the valid atoms of one graph (flags != 0) in shared memory: idx[0..n) ascending; returns n.  Threads then enumerate
+// the n*n valid ordered pairs densely (t -> (idx[t / n], idx[t % n])), so padding atoms do not occupy lanes.  Call with all threads.
+__device__ __forceinline__ int df_valid_nodes(const float* __restrict__ fl, int Nm, int* idx, int* count) {
+    if (threadIdx.x < 32) {
+        int n = 0;
+        for (int base = 0; base < Nm; base += 32) {
+            const int node = base + threadIdx.x;
+            const bool ok = node < Nm && fl[node] != 0.0f;
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) idx[n + __popc(m & ((1u << threadIdx.x) - 1u))] = node;
+            n += __popc(m);
+        }
+        if (threadIdx.x == 0) *count = n;
+    }
+    __syncthreads();
+    return *count;
+}
+
 // ---------------------------------------------------------------------------------------
 // S[b,c,i,j]: grid (B, C), 256 threads.  Q, K: [B*Nm, ldq], channel c at columns c*W .. c*W+W-1 (W = H*ds <= 32, ds % 4 == 0)
 // ---------------------------------------------------------------------------------------
@@ -57,33 +76,31 @@ dense_attn_sym_kernel(const float* __restrict__ Q, const float* __restrict__ K, 
         *reinterpret_cast<float4*>(&sQ[r][4 * k4]) = __ldg(reinterpret_cast<const float4*>(Q + g));
         *reinterpret_cast<float4*>(&sK[r][4 * k4]) = __ldg(reinterpret_cast<const float4*>(K + g));
     }
-    __syncthreads();
+    __shared__ int vidx[DF_NM], vcount;
     const float* fl = flags + static_cast<int64_t>(b) * Nm;
+    const int n = df_valid_nodes(fl, Nm, vidx, &vcount);   // (also the barrier after the Q / K staging)
     const int H = W / ds, d4 = ds >> 2;
     const float inv_sqrt = 1.0f / sqrtf(static_cast<float>(ds));
-    for (int p = threadIdx.x; p < Nm * Nm; p += blockDim.x) {
-        const int i = p / Nm, j = p % Nm;
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+        const int a = t / n, cc = t % n;
+        const float4* q = reinterpret_cast<const float4*>(sQ[vidx[a]]);
+        const float4* k = reinterpret_cast<const float4*>(sK[vidx[cc]]);
         float s = 0.0f;
-        if (fl[i] != 0.0f && fl[j] != 0.0f) {
-            const float4* q = reinterpret_cast<const float4*>(sQ[i]);
-            const float4* k = reinterpret_cast<const float4*>(sK[j]);
-            for (int h = 0; h < H; ++h) {
-                float d = 0.0f;
-                for (int kk = 0; kk < d4; ++kk) {
-                    const float4 a = q[h * d4 + kk], bb = k[h * d4 + kk];
-                    d = fmaf(a.x, bb.x, d); d = fmaf(a.y, bb.y, d); d = fmaf(a.z, bb.z, d); d = fmaf(a.w, bb.w, d);
-                }
-                s += df_tanh(d * inv_sqrt);
+        for (int h = 0; h < H; ++h) {
+            float d = 0.0f;
+            for (int kk = 0; kk < d4; ++kk) {
+                const float4 x = q[h * d4 + kk], y = k[h * d4 + kk];
+                d = fmaf(x.x, y.x, d); d = fmaf(x.y, y.y, d); d = fmaf(x.z, y.z, d); d = fmaf(x.w, y.w, d);
             }
-            s = s / static_cast<float>(H);
+            s += df_tanh(d * inv_sqrt);
         }
-        sA[i][j] = s;
+        sA[a][cc] = s / static_cast<float>(H);
     }
     __syncthreads();
-    float* out = S + (static_cast<int64_t>(b) * C + c) * Nm * Nm;
-    for (int p = threadIdx.x; p < Nm * Nm; p += blockDim.x) {
-        const int i = p / Nm, j = p % Nm;
-        out[p] = (sA[i][j] + sA[j][i]) * 0.5f;
+    float* out = S + (static_cast<int64_t>(b) * C + c) * Nm * Nm;   // (entries of padding pairs are never read: left unwritten)
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+        const int a = t / n, cc = t % n;
+        out[vidx[a] * Nm + vidx[cc]] = (sA[a][cc] + sA[cc][a]) * 0.5f;
     }
 }
 
@@ -143,17 +160,14 @@ dense_pair_mlp_kernel(const float* __restrict__ S, const float* __restrict__ adj
         P.b1[threadIdx.x] = threadIdx.x < Hd ? b1[threadIdx.x] : 0.0f;
     }
     if (threadIdx.x < DF_CO) P.b2[threadIdx.x] = threadIdx.x < Co ? b2[threadIdx.x] : 0.0f;
-    __syncthreads();
     const int NN = Nm * Nm, b = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= NN) return;
-    const int i = p / Nm, j = p % Nm;
+    __shared__ int vidx[DF_NM], vcount;
+    const int n = df_valid_nodes(flags + static_cast<int64_t>(b) * Nm, Nm, vidx, &vcount);   // (also the barrier after the weight staging)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * n) return;                  // adjc_next is zero-filled by the caller: padding pairs stay 0
+    const int i = vidx[t / n], j = vidx[t % n], p = i * Nm + j;
     const float fi = flags[b * Nm + i], fj = flags[b * Nm + j];
     float* out = adjc_next + static_cast<int64_t>(b) * Co * NN + p;
-    if (fi == 0.0f || fj == 0.0f) {
-        for (int c = 0; c < Co; ++c) out[static_cast<int64_t>(c) * NN] = 0.0f;
-        return;
-    }
     const float* Sb = S + static_cast<int64_t>(b) * Cin * NN;
     const float* Ab = adjc + static_cast<int64_t>(b) * Cin * NN;
     float x[DF_K0], y[DF_CO], yt[DF_CO];
@@ -223,14 +237,15 @@ dense_edge_final_mlp_kernel(DenseSegs segs, const float* __restrict__ flags, con
         b1s[threadIdx.x] = threadIdx.x < H2 ? b1[threadIdx.x] : 0.0f;
         w2s[threadIdx.x] = threadIdx.x < H2 ? W2[threadIdx.x] : 0.0f;
     }
-    __syncthreads();
     const int NN = Nm * Nm, b = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= NN) return;
-    const int i = p / Nm, j = p % Nm;
+    __shared__ int vidx[DF_NM], vcount;
+    const int n = df_valid_nodes(flags + static_cast<int64_t>(b) * Nm, Nm, vidx, &vcount);   // (also the barrier after the weight staging)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * n) return;                  // `out` is zero-filled by the caller: padding pairs stay 0
+    const int i = vidx[t / n], j = vidx[t % n], p = i * Nm + j;
     const float fi = flags[b * Nm + i], fj = flags[b * Nm + j];
     float* o = out + static_cast<int64_t>(b) * NN + p;
-    if (i == j || fi == 0.0f || fj == 0.0f) { *o = 0.0f; return; }
+    if (i == j) return;                      // zero diagonal
     float h1[DF_FH];
 #pragma unroll
     for (int q = 0; q < DF_FH; ++q) h1[q] = b0s[q];

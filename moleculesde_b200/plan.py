@@ -53,6 +53,39 @@ def build_plan(csr: CSR, node_ptr: torch.Tensor, groups: Optional[Sequence[int]]
     """`node_ptr`: molecule offsets [B+1] (any device).  `groups`: optional molecule offsets
     [G+1] of fixed chunks (sampling groups: one chunk per group, required by the PC kernel);
     otherwise molecules are packed greedily into chunks."""
+    rowptr = np.ascontiguousarray(csr.rowptr.detach().cpu().numpy().astype(np.int64))
+    nptr = np.ascontiguousarray(node_ptr.detach().cpu().numpy().astype(np.int64))
+    N, E = int(nptr[-1]), int(rowptr[-1])
+    B = len(nptr) - 1
+    te, maxn, maxt = _abi.TILE_EDGES, _abi.CHUNK_MAX_NODES, _abi.MAX_CHUNK_TILES
+    grp = None if groups is None else np.ascontiguousarray(np.asarray(groups, dtype=np.int64))
+    ctp = np.empty((B if grp is None else len(grp) - 1) + 2, dtype=np.int32)
+    ttp = np.empty(N + 2, dtype=np.int32)
+    counts = np.zeros(4, dtype=np.int64)
+    st = _abi.lib().molsde_build_plan_host(rowptr.ctypes.data, nptr.ctypes.data, B, None if grp is None else grp.ctypes.data,
+                                           0 if grp is None else len(grp) - 1, te, maxn, maxt, ctp.ctypes.data, ttp.ctypes.data,
+                                           counts.ctypes.data)
+    if st != 0:
+        code, where = int(counts[2]), int(counts[3])
+        if code == -2:
+            raise _abi.MolsdeError(f"node {where} has more than {te} incoming edges (unsupported)")
+        if code == -3:
+            raise _abi.MolsdeError(f"sampling group {where} has more than {maxn} atoms; the fused PC kernel holds at most {maxn}")
+        if code == -4:
+            raise _abi.MolsdeError(f"chunk {where} needs {int(counts[1])} tiles (> {maxt})")
+        raise _abi.MolsdeError(f"build_plan_host failed with status {st}")
+    nchunks, ntiles, max_tiles = int(counts[0]), int(counts[1]), int(counts[2])
+    chunk_tile_ptr = ctp[:nchunks + 1]
+    tile_starts = ttp[:ntiles + 1]
+    dev = csr.rowptr.device
+    tiles_per_chunk = np.diff(chunk_tile_ptr.astype(np.int64))
+    order = np.argsort(-tiles_per_chunk, kind="stable").astype(np.int32)
+    return TilePlan(csr, torch.from_numpy(chunk_tile_ptr.copy()).to(dev), torch.from_numpy(tile_starts.copy()).to(dev),
+                    torch.from_numpy(order).to(dev), nchunks, ntiles, max_tiles, N, E)
+
+
+def build_plan_py(csr: CSR, node_ptr: torch.Tensor, groups: Optional[Sequence[int]] = None) -> TilePlan:
+    """Pure-Python statement of the same plan (the specification `molsde_build_plan_host` is tested against)."""
     rowptr = csr.rowptr.detach().cpu().numpy().astype(np.int64)
     nptr = node_ptr.detach().cpu().numpy().astype(np.int64)
     N, E = int(nptr[-1]), int(rowptr[-1])

@@ -391,7 +391,7 @@ def tape_gin(tp: Tape, model, P: Dict[str, Var], x: torch.Tensor, edge_index: to
         T_bond = _concat_tables(tp, P, [pf + f"bond_encoder.bond_embedding_list.{i}.weight" for i in range(len(BOND_FEATURE_DIMS))])
         pre = tp.gin_aggregate(h, T_bond, ekeys, eidx, csr.rowptr, src, tgt, P[pf + "eps"])
         bn1, bn2 = model.gnns[l].mlp[1], model.batch_norms[l]
-        z = tp.linear(pre, P[pf + "mlp.0.weight"], P[pf + "mlp.0.bias"], exact=True)   # feeds BatchNorm + ReLU
+        z = tp.linear(pre, P[pf + "mlp.0.weight"], P[pf + "mlp.0.bias"], exact=model.training)   # feeds BatchNorm + ReLU (train: sign decisions feed gradients)
         last = l == model.num_layer - 1
         if model.training:
             z = tp.batchnorm(z, P[pf + "mlp.1.weight"], P[pf + "mlp.1.bias"], bn1.running_mean, bn1.running_var, bn1.eps,
@@ -399,7 +399,7 @@ def tape_gin(tp: Tape, model, P: Dict[str, Var], x: torch.Tensor, edge_index: to
             bn1.num_batches_tracked += 1
         else:
             z = tp.batchnorm_eval(z, P[pf + "mlp.1.weight"], P[pf + "mlp.1.bias"], bn1.running_mean, bn1.running_var, bn1.eps, relu=True)
-        z = tp.linear(z, P[pf + "mlp.3.weight"], P[pf + "mlp.3.bias"], exact=True)
+        z = tp.linear(z, P[pf + "mlp.3.weight"], P[pf + "mlp.3.bias"], exact=model.training)
         if model.training:
             h = tp.batchnorm(z, P[f"batch_norms.{l}.weight"], P[f"batch_norms.{l}.bias"], bn2.running_mean, bn2.running_var,
                              bn2.eps, bn2.momentum, relu=not last)

@@ -5,6 +5,7 @@ CUDA graph and replayed per step (`node_adj_PC_generation(use_graph=...)`), the 
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import torch
@@ -119,16 +120,35 @@ def node_adj_PC_generation(representation, data, SDE_model, B, max_num_nodes, nu
     # same values inside every one of its 4 x N_steps embeds, `:228,240`)
     rep3d = SDE_model.embed_3d(representation)
 
+    side = {"stream": None}   # set by the graph path: the node-network half of every half-step runs on a second stream
+
+    def both(upd_adj, upd_x, x, adj, vec_t, emb, za, zx):
+        """adjacency update (edge score network) and node update (node score network) of one half-step: independent given
+        (x, adj, emb) -- under graph capture they are forked onto two streams and overlap (the node network is three large GEMMs,
+        the edge network many small kernels)."""
+        s2 = side["stream"]
+        if s2 is None:
+            a = upd_adj.update_fn(representation, x, adj, flags, vec_t, za, emb=emb)
+            b = upd_x.update_fn(representation, x, adj, flags, vec_t, zx, emb=emb)
+            return a, b
+        cur = torch.cuda.current_stream(dev)
+        s2.wait_stream(cur)
+        with torch.cuda.stream(s2):
+            b = upd_x.update_fn(representation, x, adj, flags, vec_t, zx, emb=emb)
+        a = upd_adj.update_fn(representation, x, adj, flags, vec_t, za, emb=emb)
+        cur.wait_stream(s2)
+        for t in b:
+            t.record_stream(cur)
+        return a, b
+
     def pc_step(x, adj, vec_t, i, get=get):
         """one iteration of the reference loop (`:134-147`)"""
         if get is None:
             get = lambda k, i: None  # noqa: E731
         emb = SDE_model.embed(representation, x, rep3d=rep3d)
-        adj1, _ = corr_adj.update_fn(representation, x, adj, flags, vec_t, get("c_adj", i), emb=emb)
-        x1, _ = corr_x.update_fn(representation, x, adj, flags, vec_t, get("c_x", i), emb=emb)
+        (adj1, _), (x1, _) = both(corr_adj, corr_x, x, adj, vec_t, emb, get("c_adj", i), get("c_x", i))
         emb = SDE_model.embed(representation, x1, rep3d=rep3d)
-        adj2, adj_mean = pred_adj.update_fn(representation, x1, adj1, flags, vec_t, get("p_adj", i), emb=emb)
-        x2, x_mean = pred_x.update_fn(representation, x1, adj1, flags, vec_t, get("p_x", i), emb=emb)
+        (adj2, adj_mean), (x2, x_mean) = both(pred_adj, pred_x, x1, adj1, vec_t, emb, get("p_adj", i), get("p_x", i))
         return x2, adj2, x_mean, adj_mean
 
     if use_graph is None:
@@ -140,6 +160,8 @@ def node_adj_PC_generation(representation, data, SDE_model, B, max_num_nodes, nu
         return x, adj, x_mean, adj_mean
 
     # ---- graph replay: static state, device-side step counter ----
+    if os.environ.get("MOLSDE_DENSE_ONE_STREAM") != "1":
+        side["stream"] = torch.cuda.Stream(device=dev)
     pc = GraphedPCStep(pc_step, x, adj, timesteps, [sde_x, sde_adj], draws, steps)
     if return_graph:   # (x, adj) masked prior draws + the captured step: the caller drives `reset` / `run`
         return pc, x, adj

@@ -210,7 +210,7 @@ class EdgeNetwork_dense(nn.Module):
         ml = self.mlp.layers
         w = [l.weight.detach().float().contiguous() for l in ml]
         bb = [l.bias.detach().float().contiguous() for l in ml]
-        adj_out = torch.empty(B, self.out_ch, Nm, Nm, dtype=torch.float32, device=adjc.device)
+        adj_out = torch.zeros(B, self.out_ch, Nm, Nm, dtype=torch.float32, device=adjc.device)   # padding pairs stay 0
         check(lib().molsde_dense_pair_mlp(ptr(S), ptr(adjc), ptr(flags), ptr(w[0]), ptr(bb[0]), ptr(w[1]), ptr(bb[1]), ptr(w[2]),
                                           ptr(bb[2]), B, C, w[0].size(0), self.out_ch, Nm, int(symmetric), ptr(adj_out), s),
               "dense_pair_mlp")
@@ -304,7 +304,7 @@ class EdgeScoreNetwork_dense(nn.Module):
         fl = self.final.layers
         w = [l.weight.detach().float().contiguous() for l in fl]
         bb = [l.bias.detach().float().contiguous() for l in fl]
-        out = torch.empty(B, Nm, Nm, dtype=torch.float32, device=adj.device)
+        out = torch.zeros(B, Nm, Nm, dtype=torch.float32, device=adj.device)   # padding pairs and the diagonal stay 0
         n = len(stacks)
         ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in stacks])
         chs = (ctypes.c_int32 * n)(*[t.size(1) for t in stacks])

@@ -298,3 +298,35 @@ def test_umma_tile_split_randomised():
         assert torch.equal(hi, w.half().float())
     assert torch.equal(umma_tile_split_words(torch.zeros(8, 8)), torch.zeros(64))
 
+
+
+def test_build_plan_host_matches_python_specification():
+    """`molsde_build_plan_host` (C, sequential) == the pure-Python plan on random batches: free packing and fixed sampling groups,
+    including the error cases (a node with > 128 incoming edges, a group beyond 224 atoms)."""
+    import numpy as np
+    from moleculesde_b200 import _abi
+    from moleculesde_b200.graph import CSR
+    from moleculesde_b200.plan import build_plan, build_plan_py
+    rng = np.random.default_rng(0)
+    for trial in range(30):
+        B = int(rng.integers(1, 40))
+        sizes = rng.integers(1, 60 if trial % 3 else 120, size=B)
+        nptr = np.concatenate([[0], np.cumsum(sizes)])
+        N = int(nptr[-1])
+        deg = rng.integers(0, 40 if trial % 4 else 100, size=N)
+        rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+        csr = CSR(torch.from_numpy(rowptr), torch.zeros(int(rowptr[-1]), dtype=torch.int32))
+        node_ptr = torch.from_numpy(nptr.astype(np.int32))
+        groups = None
+        if trial % 2:
+            cuts = sorted(set([0, B] + rng.integers(0, B + 1, size=3).tolist()))
+            groups = cuts
+        res = []
+        for fn in (build_plan, build_plan_py):
+            try:
+                p = fn(csr, node_ptr, groups)
+                res.append((p.num_chunks, p.num_tiles, p.max_chunk_tiles, p.chunk_tile_ptr.tolist(), p.tile_tgt_ptr.tolist(),
+                            p.chunk_order.tolist()))
+            except _abi.MolsdeError as e:
+                res.append(("error", str(e).split(" ")[0]))
+        assert res[0] == res[1], (trial, res[0][:3], res[1][:3])
