@@ -136,6 +136,22 @@ dense_gcn_kernel(const float* __restrict__ adjc, int64_t adj_stride_b, int64_t a
     __syncthreads();
     const float* xb = xw + static_cast<int64_t>(b) * Nm * ldxw + c * Fo;
     float* ob = out + static_cast<int64_t>(b) * Nm * ldo + out_off + c * Fo;
+    // the graph's xw tile [Nm][Fo] is read Nm times by every output row: staged once in shared memory (Fo <= 32), pre-scaled by dis_j
+    __shared__ float Xs[DN_MAX][33];
+    if (Fo <= 32) {
+        for (int p = threadIdx.x; p < Nm * Fo; p += blockDim.x) {
+            const int j = p / Fo, f = p % Fo;
+            Xs[j][f] = xb[j * ldxw + f];
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < Nm * Fo; p += blockDim.x) {
+            const int i = p / Fo, f = p % Fo;
+            float s = 0.0f;
+            for (int j = 0; j < Nm; ++j) s = fmaf((dis[i] * A[i][j]) * dis[j], Xs[j][f], s);
+            ob[i * ldo + f] = dense_act(s + bias[c * Fo + f], act);
+        }
+        return;
+    }
     for (int p = threadIdx.x; p < Nm * Fo; p += blockDim.x) {
         const int i = p / Fo, f = p % Fo;
         float s = 0.0f;

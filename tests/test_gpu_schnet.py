@@ -39,7 +39,7 @@ def test_schnet_vs_golden(golden, golden_batch):
     assert torch.equal(out, out2)  # deterministic
 
 
-@pytest.mark.parametrize("kind,num,seed", [("pcqm", 96, 5), ("drug", 10, 6)])
+@pytest.mark.parametrize("kind,num,seed", [("pcqm", 96, 5), ("drug", 10, 6), ("drug", 64, 7)])
 def test_schnet_vs_oracle(kind, num, seed, golden):
     """Larger batches; on drug-sized molecules the 32-neighbour cap binds."""
     from moleculesde_b200.data import synth_batch

@@ -94,7 +94,7 @@ def test_edge2d_and_node_invariants_vs_oracle(golden, golden_batch):
     assert_parity(got, ref[perm], "edge_2D_emb (eval)")
 
 
-@pytest.mark.parametrize("kind,num,seed", [("pcqm", 64, 11), ("drug", 6, 12)])
+@pytest.mark.parametrize("kind,num,seed", [("pcqm", 64, 11), ("drug", 6, 12), ("drug", 64, 13)])
 def test_get_score_vs_oracle_multichunk(kind, num, seed, golden):
     """Batches that need several CTA chunks / many tiles, incl. drug-sized molecules (<=100 atoms)."""
     from moleculesde_b200.data import Batch, synth_molecules
