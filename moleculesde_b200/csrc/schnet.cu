@@ -5,40 +5,43 @@
 //       tiles of <=128 edges, compute in-kernel from the distance d (GaussianSmearing is never
 //       materialised):   W = (Lin(51,128) -> ssp -> Lin(128,128))(exp(coeff (d - mu_k)^2)) * 0.5 (cos(d pi / rc) + 1)
 //       (schnet.py:185-187,205-207), message x_j * W (:194-195) and the deterministic ascending-source
-//       sum per target (:190).  Both filter GEMMs run on the tensor cores (3xTF32, mma_tile.cuh) on
-//       warp-private 16-edge stripes; x = lin1(h) is gathered from L2.
+//       sum per target (:190).  Both filter GEMMs run on tcgen05 (kind::f16, two-way fp16 operand split, TMEM accumulators,
+//       thread = edge slot); x = lin1(h) is gathered from L2.
 //   gather_rows / segment_reduce -- embedding lookup (:89) and per-graph readout (:115).
 //   ebm_node_dot_kernel   -- row-wise dots of X with Y and with Y[perm] (HBM-bound, not a GEMM),
 //       BCE-with-logits partial sums reduced in a fixed order.
 #include <math_constants.h>
 
 #include "common.cuh"
-#include "mma_tile.cuh"
+#include "tc05.cuh"
 
 namespace molsde {
 
-constexpr int SN_THREADS = 256;
-constexpr int SN_TE = MOLSDE_TILE_EDGES;  // 128
-constexpr int SN_LDA = MOLSDE_TILE_LD;    // 136
+// ---- CFConv on tcgen05 (round 2): two QUADS of 128 threads per CTA, a quad owns one edge tile at a time, thread = edge slot = TMEM
+// lane.  Both filter GEMMs are tcgen05.mma kind::f16 (M = 128 edges, N = 128 filters, fp32 accumulator in the quad's TMEM columns)
+// with the two-way fp16 operand split (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi: 22-bit operands; Gaussian features lie in [0,1], ssp
+// outputs and trained weights are O(1)):
+//   thread: (src, tgt) by bisection, d, C(d) -> 51 Gaussians -> fp16 hi/lo A row [128 x 64]      -> MMA 1 (4 K-steps x 3 terms)
+//   epilogue 1: accumulator row (tcgen05.ld) + b1 -> ssp -> fp16 hi/lo A row [128 x 128]          -> MMA 2 (8 K-steps x 3 terms)
+//   epilogue 2: (row + b2) * C * x[src] -> message tile (fp32, granules XOR-swizzled by the slot) -> per-target ascending-source sum
+// Weights are converted ONCE per persistent CTA into the canonical K-major core-matrix B tiles.  Shared memory: B tiles 96 KB +
+// one 64 KB union per quad (A1 | A2 | messages) = 225.5 KB.  The legacy kernel this replaces ran both GEMMs as warp-level
+// mma.sync 3xTF32 (profiles/r2_cfconv_ncu.txt: tensor pipe 42 % busy, 8 warps, 1.58 ms per 1.1 M edges).
+constexpr int SN_THREADS = 256, SN_QUADS = 2, SN_QT = 128;
 constexpr int SN_F = 128;                 // num_filters (config.py:66)
-constexpr int SN_G = 56;                  // num_gaussians (51) padded to a multiple of 8
-constexpr int SN_LDM = 132;               // slot-major message tile [128][132]
-
-// smem float offsets
-constexpr int SS_W1 = 0;                        // [56][136]  mlp.0.weight^T (rows >= num_gaussians zero)
-constexpr int SS_W2 = SS_W1 + SN_G * SN_LDA;    // [128][136] mlp.2.weight^T
-constexpr int SS_B1 = SS_W2 + SN_F * SN_LDA;    // [128]
-constexpr int SS_B2 = SS_B1 + SN_F;             // [128]
-constexpr int SS_MU = SS_B2 + SN_F;             // [64]   gaussian offsets
-constexpr int SS_A1 = SS_MU + 64;               // [56][136]  gaussian features, k-major
-constexpr int SS_A2 = SS_A1 + SN_G * SN_LDA;    // [128][136] hidden, k-major; later the message tile [128][132]
-constexpr int SS_D = SS_A2 + SN_F * SN_LDA;     // [128] distance
-constexpr int SS_C = SS_D + SN_TE;              // [128] cosine cutoff
-constexpr int SS_FLOATS = SS_C + SN_TE;
-constexpr int SSI_SRC = 0, SSI_TGT = SN_TE, SS_INTS = 2 * SN_TE;
-constexpr size_t SN_SMEM = sizeof(float) * SS_FLOATS + sizeof(int) * SS_INTS;
+constexpr int SN_G = 56;                  // num_gaussians (51) padded (layout of the host-packed w1t)
+constexpr int SN_LDA = MOLSDE_TILE_LD;    // 136: row length of the host-packed k-major weights w1t / w2t
+constexpr int SN_K1 = 64;                 // K of GEMM 1 (Gaussians padded to 4 K-steps of 16)
+// byte offsets
+constexpr int SB_W1H = 0, SB_W1L = SB_W1H + SN_F * SN_K1 * 2;          // [8 k-chunks][128 n][16 B] each
+constexpr int SB_W2H = SB_W1L + SN_F * SN_K1 * 2, SB_W2L = SB_W2H + SN_F * SN_F * 2;   // [16 k-chunks][128 n][16 B] each
+constexpr int SB_U = SB_W2L + SN_F * SN_F * 2;                          // per quad: 64 KB union
+constexpr int SN_U_BYTES = 65536;
+constexpr int SB_B1 = SB_U + SN_QUADS * SN_U_BYTES, SB_B2 = SB_B1 + SN_F * 4, SB_MU = SB_B2 + SN_F * 4;
+constexpr int SB_BARS = SB_MU + 64 * 4, SB_TMEM = SB_BARS + SN_QUADS * 8;
+constexpr size_t SN_SMEM = SB_TMEM + 16;
 static_assert(SN_SMEM <= 232448, "smem");
-static_assert(SN_TE * SN_LDM <= SN_F * SN_LDA, "message tile aliases the hidden tile");
+static_assert(SB_U % 128 == 0 && SB_W2H % 128 == 0, "operand tile alignment");
 
 __device__ __forceinline__ float ssp_fast(float x) {
     // ShiftedSoftplus (schnet.py:210-216): softplus(x) - float32(log 2), softplus threshold 20
@@ -51,105 +54,151 @@ schnet_cfconv_kernel(molsde_plan plan, const float* __restrict__ pos, const floa
                      const float* __restrict__ w1t /*[56][136]*/, const float* __restrict__ b1,
                      const float* __restrict__ w2t /*[128][136]*/, const float* __restrict__ b2,
                      const float* __restrict__ mu /*[56]*/, int num_gaussians, float coeff, float cutoff,
-                     float* __restrict__ agg /*[N][128]*/) {
-    extern __shared__ __align__(16) float smem[];
-    int* si = reinterpret_cast<int*>(smem + SS_FLOATS);
-    const int tid = threadIdx.x, lane = tid & 31, slab = tid >> 5;
-    const int g = lane >> 2, t4 = lane & 3;
-    for (int i = tid * 4; i < SN_G * SN_LDA; i += SN_THREADS * 4) cp_async16(smem + SS_W1 + i, w1t + i);
-    for (int i = tid * 4; i < SN_F * SN_LDA; i += SN_THREADS * 4) cp_async16(smem + SS_W2 + i, w2t + i);
-    cp_async_commit();
-    if (tid < SN_F) { smem[SS_B1 + tid] = b1[tid]; smem[SS_B2 + tid] = b2[tid]; }
-    if (tid < 64) smem[SS_MU + tid] = tid < SN_G ? mu[tid] : 0.0f;
-    cp_async_wait<0>();
+                     float* __restrict__ agg /*[N][128]*/, int32_t* __restrict__ status) {
+    extern __shared__ __align__(128) uint8_t sn_smem[];
+    const int tid = threadIdx.x, q = tid >> 7, e = tid & (SN_QT - 1), warp = tid >> 5;
+    float* B1 = reinterpret_cast<float*>(sn_smem + SB_B1);
+    float* B2 = reinterpret_cast<float*>(sn_smem + SB_B2);
+    float* MU = reinterpret_cast<float*>(sn_smem + SB_MU);
+    // ---- one-time: weights -> fp16 hi/lo B tiles (element (n, k) at (k/8) * 2048 + n * 16 + (k%8) * 2), biases, offsets, barriers, TMEM
+    for (int item = tid; item < (SN_K1 / 8) * SN_F; item += SN_THREADS) {
+        const int kc = item / SN_F, n = item % SN_F;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int k = 8 * kc + j; v[j] = k < SN_G ? w1t[k * SN_LDA + n] : 0.0f; }
+        tc05::store_chunk(sn_smem + SB_W1H, sn_smem + SB_W1L, n, kc, SN_F * 16, v);
+    }
+    for (int item = tid; item < (SN_F / 8) * SN_F; item += SN_THREADS) {
+        const int kc = item / SN_F, n = item % SN_F;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = w2t[(8 * kc + j) * SN_LDA + n];
+        tc05::store_chunk(sn_smem + SB_W2H, sn_smem + SB_W2L, n, kc, SN_F * 16, v);
+    }
+    if (tid < SN_F) { B1[tid] = b1[tid]; B2[tid] = b2[tid]; }
+    if (tid < 64) MU[tid] = tid < SN_G ? mu[tid] : 0.0f;
+    if (tid < SN_QUADS) tc05::mbar_init(tc05::smem_u32(sn_smem + SB_BARS + 8 * tid), 1);
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc05::smem_u32(sn_smem + SB_TMEM)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc05::fence_proxy_async_smem();
+    tc05::fence_before();
     __syncthreads();
-    float* A1 = smem + SS_A1 + slab * 16;
-    float* A2 = smem + SS_A2 + slab * 16;
-    float* Mm = smem + SS_A2;
+    tc05::fence_after();
+    const uint32_t tmem_q = *reinterpret_cast<const uint32_t*>(sn_smem + SB_TMEM) + q * 256;   // 2 x 128 accumulator columns per quad
+    const uint32_t tlane = tmem_q + (static_cast<uint32_t>(e & ~31) << 16);
+    const uint32_t bar = tc05::smem_u32(sn_smem + SB_BARS + 8 * q);
+    uint8_t* U = sn_smem + SB_U + q * SN_U_BYTES;
+    const uint32_t u_addr = tc05::smem_u32(U), w1h = tc05::smem_u32(sn_smem + SB_W1H), w1l = tc05::smem_u32(sn_smem + SB_W1L);
+    const uint32_t w2h = tc05::smem_u32(sn_smem + SB_W2H), w2l = tc05::smem_u32(sn_smem + SB_W2L);
+    float* Mm = reinterpret_cast<float*>(U);
     const float pi_over_rc = 3.14159265358979323846f / cutoff;
-    for (int tile = blockIdx.x; tile < plan.num_tiles; tile += gridDim.x) {
+    uint32_t ph = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x * SN_QUADS + q; tile < plan.num_tiles; tile += gridDim.x * SN_QUADS) {
         const int ta = plan.tile_tgt_ptr[tile], tb = plan.tile_tgt_ptr[tile + 1];
         const int ea = plan.rowptr[ta], ne = plan.rowptr[tb] - ea;
-        if (lane < 16) {
-            const int slot = slab * 16 + lane;
-            int sj = 0, tg = ta;
-            float d = 0.0f, cc = 0.0f;
-            if (slot < ne) {
-                const int e = ea + slot;
-                int lo = ta, hi = tb;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (plan.rowptr[mid] <= e) lo = mid; else hi = mid;
+        const bool live = e < ne;
+        int sj = 0;
+        float d = 0.0f, cc = 0.0f;
+        if (live) {
+            const int eg = ea + e;
+            int lo = ta, hi = tb;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (plan.rowptr[mid] <= eg) lo = mid; else hi = mid;
+            }
+            sj = plan.src[eg];
+            // edge_weight = (pos[row] - pos[col]).norm(dim=-1)   (:93)
+            const float dx = __fsub_rn(pos[3 * sj], pos[3 * lo]), dy = __fsub_rn(pos[3 * sj + 1], pos[3 * lo + 1]);
+            const float dz = __fsub_rn(pos[3 * sj + 2], pos[3 * lo + 2]);
+            d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+            cc = 0.5f * (cosf(d * pi_over_rc) + 1.0f);  // :186
+        }
+        // ---- A1 row: GaussianSmearing (:205-207) of this edge, 64 columns (rows of dead slots are zero)
+#pragma unroll
+        for (int kc = 0; kc < SN_K1 / 8; ++kc) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = 8 * kc + j;
+                const float u = d - MU[k];
+                v[j] = (live && k < num_gaussians) ? __expf(coeff * u * u) : 0.0f;
+            }
+            tc05::store_chunk(U, U + 16384, e, kc, 2048, v);
+        }
+        tc05::fence_proxy_async_smem();
+        tc05::fence_before();
+        tc05::group_sync(1 + q, SN_QT);
+        if (e == 0) {
+            tc05::fence_after();
+            tc05::mma_split_f16<SN_F, SN_K1 / 16>(tmem_q, u_addr, u_addr + 16384, w1h, w1l, 0u);
+            tc05::commit(bar);
+        }
+        ok &= tc05::mbar_wait(bar, ph);
+        ph ^= 1u;
+        tc05::fence_after();
+        // ---- epilogue 1: hidden = ssp(acc + b1) -> A2 row [128 x 128] (overlays A1: its MMAs are complete)
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+            float hv[32];
+            tc05::tmem_ld32(tlane + 32 * cb, hv);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) hv[j] = ssp_fast(hv[j] + B1[32 * cb + j]);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) tc05::store_chunk(U, U + 32768, e, 4 * cb + k4, 2048, hv + 8 * k4);
+        }
+        tc05::fence_proxy_async_smem();
+        tc05::fence_before();
+        tc05::group_sync(1 + q, SN_QT);
+        if (e == 0) {
+            tc05::fence_after();
+            tc05::mma_split_f16<SN_F, SN_F / 16>(tmem_q + 128, u_addr, u_addr + 32768, w2h, w2l, 0u);
+            tc05::commit(bar);
+        }
+        ok &= tc05::mbar_wait(bar, ph);
+        ph ^= 1u;
+        tc05::fence_after();
+        // ---- epilogue 2: message = x_j * ((acc + b2) * C)   (:187,194-195) -> message tile (overlays A2: its MMAs are complete)
+        const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(sj) * SN_F);
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+            float wv[32];
+            tc05::tmem_ld32(tlane + 128 + 32 * cb, wv);
+            if (live) {
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4) {
+                    const int g = 8 * cb + g4;
+                    const float4 xv = __ldg(xr + g);
+                    float4 m;
+                    m.x = xv.x * ((wv[4 * g4] + B2[4 * g]) * cc);
+                    m.y = xv.y * ((wv[4 * g4 + 1] + B2[4 * g + 1]) * cc);
+                    m.z = xv.z * ((wv[4 * g4 + 2] + B2[4 * g + 2]) * cc);
+                    m.w = xv.w * ((wv[4 * g4 + 3] + B2[4 * g + 3]) * cc);
+                    *reinterpret_cast<float4*>(Mm + e * SN_F + ((g ^ (e & 31)) << 2)) = m;
                 }
-                tg = lo;
-                sj = plan.src[e];
-                // edge_weight = (pos[row] - pos[col]).norm(dim=-1)   (:93)
-                const float dx = __fsub_rn(pos[3 * sj], pos[3 * tg]), dy = __fsub_rn(pos[3 * sj + 1], pos[3 * tg + 1]);
-                const float dz = __fsub_rn(pos[3 * sj + 2], pos[3 * tg + 2]);
-                d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-                cc = 0.5f * (cosf(d * pi_over_rc) + 1.0f);  // :186
-            }
-            si[SSI_SRC + slot] = sj;
-            si[SSI_TGT + slot] = tg;
-            smem[SS_D + slot] = d;
-            smem[SS_C + slot] = cc;
-        }
-        __syncwarp();
-        {   // GaussianSmearing (:205-207) of the warp's 16 edges into its A1 stripe
-            const int fe = lane & 15, kb = (lane >> 4) * (SN_G / 2);
-            const float d = smem[SS_D + slab * 16 + fe];
-#pragma unroll 4
-            for (int i = 0; i < SN_G / 2; ++i) {
-                const int k = kb + i;
-                const float u = d - smem[SS_MU + k];
-                A1[k * SN_LDA + fe] = k < num_gaussians ? __expf(coeff * u * u) : 0.0f;
             }
         }
-        __syncwarp();
-        float acc[16][4];
-        zero_frag(acc);
-        mma_gemm<16, SN_LDA, SN_LDA>(A1, smem + SS_W1, SN_G, lane, acc);
-#pragma unroll
-        for (int nb = 0; nb < 16; ++nb)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int col = nb * 8 + 2 * t4 + j;
-                const float bj = smem[SS_B1 + col];
-                A2[col * SN_LDA + g] = ssp_fast(acc[nb][j] + bj);
-                A2[col * SN_LDA + g + 8] = ssp_fast(acc[nb][2 + j] + bj);
-            }
-        __syncwarp();
-        zero_frag(acc);
-        mma_gemm<16, SN_LDA, SN_LDA>(A2, smem + SS_W2, SN_F, lane, acc);
-        __syncthreads();  // every warp is done reading its hidden stripe: the region becomes the message tile
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int slot = slab * 16 + g + 8 * rr;
-            if (slot < ne) {
-                const float cc = smem[SS_C + slot];
-                const float* xr = x + static_cast<size_t>(si[SSI_SRC + slot]) * SN_F;
-#pragma unroll
-                for (int nb = 0; nb < 16; ++nb) {
-                    const int col = nb * 8 + 2 * t4;
-                    const float2 xv = __ldg(reinterpret_cast<const float2*>(xr + col));
-                    // message = x_j * (nn(edge_attr) * C)   (:187,194-195)
-                    const float w0 = (acc[nb][2 * rr] + smem[SS_B2 + col]) * cc;
-                    const float w1 = (acc[nb][2 * rr + 1] + smem[SS_B2 + col + 1]) * cc;
-                    *reinterpret_cast<float2*>(Mm + slot * SN_LDM + col) = make_float2(xv.x * w0, xv.y * w1);
-                }
-            }
-        }
-        __syncthreads();
+        tc05::fence_before();
+        tc05::group_sync(1 + q, SN_QT);
+        // ---- per-target ascending-source sum, aggr="add" (:190); thread = (target, column)
         const int ntg = tb - ta;
-        for (int p = tid; p < ntg * SN_F; p += SN_THREADS) {
+        for (int p = e; p < ntg * SN_F; p += SN_QT) {
             const int i = ta + (p >> 7), col = p & (SN_F - 1);
             const int s0 = plan.rowptr[i] - ea, s1 = plan.rowptr[i + 1] - ea;
             float sacc = 0.0f;
-            for (int s = s0; s < s1; ++s) sacc += Mm[s * SN_LDM + col];  // ascending source order, aggr="add"
+            for (int s = s0; s < s1; ++s) sacc += Mm[s * SN_F + ((((col >> 2) ^ (s & 31)) << 2) | (col & 3))];
             agg[static_cast<size_t>(i) * SN_F + col] = sacc;
         }
-        __syncthreads();
+        tc05::fence_proxy_async_smem();   // the union is rewritten through the generic proxy, then read by the tensor core
+        tc05::group_sync(1 + q, SN_QT);
     }
+    if (!ok && status) *status = 1;
+    tc05::fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*reinterpret_cast<const uint32_t*>(sn_smem + SB_TMEM)), "r"(512u));
 }
 
 // out[r, :] = table[idx[r], :]
@@ -243,9 +292,10 @@ int molsde_schnet_cfconv(const molsde_plan* plan, const float* pos, const float*
     if (plan->num_tiles == 0) return MOLSDE_OK;
     cudaError_t err = cudaFuncSetAttribute(schnet_cfconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SN_SMEM);
     if (err != cudaSuccess) { set_last_error(cudaGetErrorString(err)); return MOLSDE_ERR_CUDA; }
-    const int grid = plan->num_tiles < kNumSMs ? plan->num_tiles : kNumSMs;
+    const int want = (plan->num_tiles + SN_QUADS - 1) / SN_QUADS;
+    const int grid = want < kNumSMs ? want : kNumSMs;
     schnet_cfconv_kernel<<<grid, SN_THREADS, SN_SMEM, as_stream(stream)>>>(*plan, pos, x, w1t, b1, w2t, b2, mu,
-                                                                          num_gaussians, coeff, cutoff, agg);
+                                                                          num_gaussians, coeff, cutoff, agg, nullptr);
     return check_launch("schnet_cfconv");
 }
 
