@@ -245,43 +245,68 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tc_gemm_kernel
     }
     if (!ok && a.status) *a.status = 1;
 
-    // ---- epilogue from the register accumulators
-    const int64_t gm = m0 + 32 * (warp & 3) + lane;
-    float* part = a.ws ? a.ws + static_cast<size_t>(blockIdx.z) * a.M * a.Nx : nullptr;   // [batch][split][M][Nx]
-    float* Cb = a.C + bz * a.bsC;
-    const float* biasb = a.bias ? a.bias + bz * a.bsBias : nullptr;
-    const bool fast = !part && !a.accumulate && !a.R && a.vecC && n0 + cbase + HALF <= a.N;  // (never contains the ones column)
-    if (gm < a.M && fast) {  // full tile, 16-byte aligned rows: float4 stores
-        const float rs = a.rowscale ? a.rowscale[gm] : 1.0f;
-        float* c = Cb + gm * a.ldc + n0 + cbase;
+    // ---- epilogue: the thread of output row r holds HALF columns in registers -> bias / rowscale / activation there -> staged through
+    // shared memory (the operand stages are idle: every MMA completed) -> written out by whole rows with the lanes along the columns
+    // (coalesced; residual / accumulate / split-K partials / the ones column are handled on the way out).  The row-per-thread stores
+    // this replaces cost ~30 % of the kernel on the TMA-fed variant.
+    {
+        constexpr int LDS = BN + 4;
+        float* stage = tc_smem;                      // [128][LDS] floats (<= 66 KB of the staging ring)
+        const int r = 32 * (warp & 3) + lane;
+        const int64_t gm = m0 + r;
+        float* part = a.ws ? a.ws + static_cast<size_t>(blockIdx.z) * a.M * a.Nx : nullptr;   // [batch][split][M][Nx]
+        float* Cb = a.C + bz * a.bsC;
+        const float* biasb = (a.bias && !part) ? a.bias + bz * a.bsBias : nullptr;
+        const float rs = (a.rowscale && !part && gm < a.M) ? a.rowscale[gm] : 1.0f;
+        const bool plain = part != nullptr;          // split-K partial: raw accumulator
+        const bool slow_act = !plain && a.act >= 2;
+        __syncthreads();                             // (all warps are past their last read of the operand stages)
 #pragma unroll
         for (int j = 0; j < HALF; j += 4) {
             float4 o;
             float* ov = reinterpret_cast<float*>(&o);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
+                const int64_t gn = n0 + cbase + j + q;
                 float v = accr[j + q];
-                if (biasb) v += biasb[n0 + cbase + j + q];
-                if (a.rowscale) v *= rs;
-                ov[q] = tc_act(v, a.act);
+                if (!plain && gn < a.N) {            // (the ones column n == N stays raw)
+                    if (biasb) v += biasb[gn];
+                    if (a.rowscale) v *= rs;
+                    v = slow_act ? tc_act_call(v, a.act) : (a.act == 1 ? fmaxf(v, 0.0f) : v);
+                }
+                ov[q] = v;
             }
-            *reinterpret_cast<float4*>(c + j) = o;
+            *reinterpret_cast<float4*>(stage + r * LDS + cbase + j) = o;
         }
-    } else if (gm < a.M) {
-        const float rs = a.rowscale ? a.rowscale[gm] : 1.0f;
+        __syncthreads();
+        const int ncols = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(BN), a.Nx - n0)));
+        for (int rr = warp; rr < TC_BM; rr += TC_THREADS / 32) {
+            const int64_t row = m0 + rr;
+            if (row >= a.M) break;
+            const float* srow = stage + rr * LDS;
+            if (part) {
+                float* pr = part + row * a.Nx + n0;
+                for (int col = lane; col < ncols; col += 32) pr[col] = srow[col];
+                continue;
+            }
+            float* c = Cb + row * a.ldc + n0;
+            const float* res = a.R ? a.R + row * a.ldr + n0 : nullptr;
+            const bool vec = a.vecC && !res && !a.accumulate && !a.colsum;
+            for (int c4 = lane; 4 * c4 < ncols; c4 += 32) {
+                if (vec && 4 * c4 + 3 < ncols) {
+                    *reinterpret_cast<float4*>(c + 4 * c4) = *reinterpret_cast<const float4*>(srow + 4 * c4);
+                    continue;
+                }
 #pragma unroll
-        for (int j = 0; j < HALF; ++j) {
-            const int64_t gn = n0 + cbase + j;
-            if (gn >= a.Nx) continue;
-            float v = accr[j];
-            if (part) { part[gm * a.Nx + gn] = v; continue; }
-            if (gn == a.N) { a.colsum[gm] = a.accumulate ? a.colsum[gm] + v : v; continue; }  // the ones column
-            if (biasb) v += biasb[gn];
-            if (a.rowscale) v *= rs;
-            v = tc_act(v, a.act);
-            if (a.R) v += a.R[gm * a.ldr + gn];
-            float* c = Cb + gm * a.ldc + gn;
-            *c = a.accumulate ? *c + v : v;
+                for (int q = 0; q < 4; ++q) {
+                    const int col = 4 * c4 + q;
+                    if (col >= ncols) break;
+                    float v = srow[col];
+                    if (n0 + col == a.N) { a.colsum[row] = a.accumulate ? a.colsum[row] + v : v; continue; }   // the ones column
+                    if (res) v += res[col];
+                    c[col] = a.accumulate ? c[col] + v : v;
+                }
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
