@@ -277,6 +277,14 @@ int molsde_dense_attn_sym(const float* Q, const float* K, int64_t ldq, int32_t W
 int molsde_dense_pair_mlp(const float* S, const float* adjc, const float* flags, const float* W0, const float* b0, const float* W1,
                           const float* b1, const float* W2, const float* b2, int32_t B, int32_t Cin, int32_t Hd, int32_t Co,
                           int32_t Nm, int32_t symmetric, float* adjc_next, void* stream);
+/* Node-side chain of an EdgeLayer with a narrow input (Fin <= 16: every layer but the first) in one launch: h1 = tanh(W1 x + b1)
+ * [G*W], qk group g = W2[g] h1[g*W:(g+1)*W] + b2 (G = 2C groups, W = 32), xw = Wv x [NV]  (edge_network_dense.py:45-53,
+ * node_network_dense.py:73); and the multi_channel MLP (:113-118): out = tanh(W1 elu(W0 v + b0) + b1) * rowflag. */
+int molsde_dense_node_side(const float* X, int64_t rows, int64_t ldx, int32_t Fin, const float* W1, const float* b1, const float* W2,
+                           const float* b2, const float* Wv, int32_t G, int32_t W, int32_t NV, float* QK, int64_t ldqk, float* XW,
+                           int64_t ldxw, void* stream);
+int molsde_dense_multi_channel(const float* V, int64_t rows, int32_t K, const float* W0, const float* b0, int32_t H, const float* W1,
+                               const float* b1, int32_t NO, const float* rowflag, float* out, void* stream);
 int molsde_dense_edge_final_mlp(const float* const* seg_ptrs, const int32_t* seg_channels, int32_t nseg, const float* flags,
                                 const float* scale, const float* W0, const float* b0, const float* W1, const float* b1,
                                 const float* W2, const float* b2, int32_t F, int32_t H1, int32_t H2, int32_t B, int32_t Nm, float* out,

@@ -49,7 +49,7 @@ EXPORTS = [
     "molsde_dense_gcn", "molsde_dense_attn", "molsde_dense_pair_post", "molsde_dense_edge_final",
     "molsde_dense_sym_noise", "molsde_dense_perturb_adj", "molsde_dense_perturb_onehot", "molsde_graph_reduce",
     "molsde_langevin_step", "molsde_langevin_update", "molsde_reverse_update", "molsde_mask_rows",
-    "molsde_dense_attn_sym", "molsde_dense_pair_mlp", "molsde_dense_edge_final_mlp",
+    "molsde_dense_attn_sym", "molsde_dense_pair_mlp", "molsde_dense_edge_final_mlp", "molsde_dense_node_side", "molsde_dense_multi_channel",
     "molsde_sde2d3d_pc_corrector_update", "molsde_sde2d3d_pc_predictor_update", "molsde_act_bwd2", "molsde_schnet_edge_feat_tangent", "molsde_build_plan_host",
 ]
 
@@ -142,6 +142,10 @@ def lib() -> ctypes.CDLL:
     L.molsde_mask_rows.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
     L.molsde_dense_attn_sym.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p,
                                         c_void_p]
+    L.molsde_dense_node_side.argtypes = [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                         c_int32, c_int32, c_void_p, c_int64, c_void_p, c_int64, c_void_p]
+    L.molsde_dense_multi_channel.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
+                                             c_void_p, c_void_p]
     L.molsde_dense_pair_mlp.argtypes = [c_void_p] * 9 + [c_int32] * 6 + [c_void_p, c_void_p]
     L.molsde_dense_edge_final_mlp.argtypes = [POINTER(c_void_p), POINTER(c_int32), c_int32] + [c_void_p] * 8 + [c_int32] * 5 + \
                                              [c_void_p, c_void_p]

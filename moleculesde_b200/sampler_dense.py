@@ -160,8 +160,8 @@ def node_adj_PC_generation(representation, data, SDE_model, B, max_num_nodes, nu
         return x, adj, x_mean, adj_mean
 
     # ---- graph replay: static state, device-side step counter ----
-    if os.environ.get("MOLSDE_DENSE_TWO_STREAMS") == "1":   # measured: 5.09 ms/step forked vs 4.90 on one stream (every large kernel of
-        side["stream"] = torch.cuda.Stream(device=dev)      # either network already fills the GPU) -> off by default
+    if os.environ.get("MOLSDE_DENSE_ONE_STREAM") != "1":    # measured (256 graphs x 64 atoms, device-timed replays): 4.81 ms/step on one
+        side["stream"] = torch.cuda.Stream(device=dev)      # stream, 4.44 with the node network forked onto a second one
     pc = GraphedPCStep(pc_step, x, adj, timesteps, [sde_x, sde_adj], draws, steps)
     if return_graph:   # (x, adj) masked prior draws + the captured step: the caller drives `reset` / `run`
         return pc, x, adj

@@ -197,16 +197,33 @@ class EdgeNetwork_dense(nn.Module):
         ds = self.attn_dim // self.num_heads
         s = stream_ptr(adjc)
         x2 = x.flatten(0, 1) if x.dim() == 3 else x
-        h1 = linear(x2, pk["w1"], pk["b1"], act="tanh")
-        qk = _grouped_linear(h1, pk["w2"], pk["b2"], 2 * C, W, W, "none")
-        xw = linear(x2, pk["wv"])
+        rows, Fin = x2.size(0), x2.size(1)
+        if Fin <= 16 and W == 32 and 2 * C <= 16 and x2.stride(1) == 1:   # narrow input (every layer but the first): one row kernel
+            qk = torch.empty(rows, 2 * C * W, dtype=torch.float32, device=adjc.device)
+            xw = torch.empty(rows, C * self.conv_out, dtype=torch.float32, device=adjc.device)
+            check(lib().molsde_dense_node_side(x2.data_ptr(), rows, x2.stride(0), Fin, ptr(pk["w1"]), ptr(pk["b1"]), ptr(pk["w2"]),
+                                               ptr(pk["b2"]), ptr(pk["wv"]), 2 * C, W, C * self.conv_out, ptr(qk), qk.stride(0), ptr(xw),
+                                               xw.stride(0), s), "dense_node_side")
+        else:
+            h1 = linear(x2, pk["w1"], pk["b1"], act="tanh")
+            qk = _grouped_linear(h1, pk["w2"], pk["b2"], 2 * C, W, W, "none")
+            xw = linear(x2, pk["wv"])
         V = torch.empty(B * Nm, C * self.conv_out, dtype=torch.float32, device=adjc.device)
         _dense_gcn(adjc, C, xw, pk["bv"], self.conv_out, V, 0, "none")
         S = torch.empty(B, C, Nm, Nm, dtype=torch.float32, device=adjc.device)
         check(lib().molsde_dense_attn_sym(qk.data_ptr(), qk.data_ptr() + 4 * C * W, qk.stride(0), W, ds, ptr(flags), B, C, Nm, ptr(S), s),
               "dense_attn_sym")
         mc = self.multi_channel.layers
-        xo = linear(linear(V, mc[0].weight, mc[0].bias, act="elu"), mc[1].weight, mc[1].bias, act="tanh", rowscale=flags)
+        Kv = V.size(1)
+        if len(mc) == 2 and mc[0].out_features <= 16 and mc[1].out_features <= 16 and Kv % 4 == 0 and Kv <= 256:
+            xo = torch.empty(rows, mc[1].out_features, dtype=torch.float32, device=adjc.device)
+            check(lib().molsde_dense_multi_channel(ptr(V), rows, Kv, ptr(mc[0].weight.detach().float().contiguous()),
+                                                   ptr(mc[0].bias.detach().float().contiguous()), mc[0].out_features,
+                                                   ptr(mc[1].weight.detach().float().contiguous()),
+                                                   ptr(mc[1].bias.detach().float().contiguous()), mc[1].out_features,
+                                                   ptr(flags.reshape(-1).contiguous()), ptr(xo), s), "dense_multi_channel")
+        else:
+            xo = linear(linear(V, mc[0].weight, mc[0].bias, act="elu"), mc[1].weight, mc[1].bias, act="tanh", rowscale=flags)
         ml = self.mlp.layers
         w = [l.weight.detach().float().contiguous() for l in ml]
         bb = [l.bias.detach().float().contiguous() for l in ml]
