@@ -215,7 +215,7 @@ def cpu_reference_rate(repeat, pc_steps_sample, total_pc_steps, state_dict, seed
 def run_reference(args):
     """CPU arm.  One bench step = one bounded sample: `cores // threads` groups side by side x S PC steps each; `ms_per_step` is the
     measured wall time of that sample, `value` scales it to the 1000-step trajectory (every PC step costs the same: two score
-    evaluations of a static graph).  S = the whole trajectory when K steps of it fit a ~5 minute budget, else the largest
+    evaluations of a static graph).  S = the whole trajectory when K steps of it fit a ~200 s budget, else the largest
     multiple of 50 that does; in that case the LAST warm-up step still runs one whole 1000-step trajectory and its rate is
     reported beside the timed one (`full_trajectory`)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -232,7 +232,7 @@ def run_reference(args):
         threads = max(sweep, key=sweep.get)
         sec, w, _ = arm.run(50, threads)
         est_full = sec / 50 * args.cpu_pc_steps
-        budget = 300.0
+        budget = 200.0   # seconds of timed CPU work over all bench steps
         S = args.cpu_pc_steps if est_full * args.steps <= budget else max(50, int(budget / args.steps / (sec / 50)) // 50 * 50)
         full = None
         for i in range(args.warmup):
