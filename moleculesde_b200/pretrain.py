@@ -20,6 +20,7 @@ from .graph import csr_by_target
 from .tape import Index, Tape, Var, _p
 
 import os as _os
+_GIN_EXACT = _os.environ.get("MOLSDE_GIN_TC") != "1"   # experiment switch: GIN linears on the tensor cores in training too
 _SINGLE_STREAM = _os.environ.get("MOLSDE_SINGLE_STREAM") == "1"   # A/B switch: issue the whole iteration on one stream
 # parameter gradients on side streams (Tape.wgrad): "capture" = only while a CUDA graph is being captured (the eager step is
 # bound by host launch time, where the extra event calls cost more than the overlap returns), "1" always, "0" never
@@ -391,7 +392,7 @@ def tape_gin(tp: Tape, model, P: Dict[str, Var], x: torch.Tensor, edge_index: to
         T_bond = _concat_tables(tp, P, [pf + f"bond_encoder.bond_embedding_list.{i}.weight" for i in range(len(BOND_FEATURE_DIMS))])
         pre = tp.gin_aggregate(h, T_bond, ekeys, eidx, csr.rowptr, src, tgt, P[pf + "eps"])
         bn1, bn2 = model.gnns[l].mlp[1], model.batch_norms[l]
-        z = tp.linear(pre, P[pf + "mlp.0.weight"], P[pf + "mlp.0.bias"], exact=model.training)   # feeds BatchNorm + ReLU (train: sign decisions feed gradients)
+        z = tp.linear(pre, P[pf + "mlp.0.weight"], P[pf + "mlp.0.bias"], exact=model.training and _GIN_EXACT)   # feeds BatchNorm + ReLU (train: sign decisions feed gradients)
         last = l == model.num_layer - 1
         if model.training:
             z = tp.batchnorm(z, P[pf + "mlp.1.weight"], P[pf + "mlp.1.bias"], bn1.running_mean, bn1.running_var, bn1.eps,
@@ -399,7 +400,7 @@ def tape_gin(tp: Tape, model, P: Dict[str, Var], x: torch.Tensor, edge_index: to
             bn1.num_batches_tracked += 1
         else:
             z = tp.batchnorm_eval(z, P[pf + "mlp.1.weight"], P[pf + "mlp.1.bias"], bn1.running_mean, bn1.running_var, bn1.eps, relu=True)
-        z = tp.linear(z, P[pf + "mlp.3.weight"], P[pf + "mlp.3.bias"], exact=model.training)
+        z = tp.linear(z, P[pf + "mlp.3.weight"], P[pf + "mlp.3.bias"], exact=model.training and _GIN_EXACT)
         if model.training:
             h = tp.batchnorm(z, P[f"batch_norms.{l}.weight"], P[f"batch_norms.{l}.bias"], bn2.running_mean, bn2.running_var,
                              bn2.eps, bn2.momentum, relu=not last)
