@@ -39,6 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd += ["-Xptxas", "-v"]
         if os.environ.get("MOLSDE_PROF") == "1":
             cmd += ["-DMOLSDE_PROF"]
+        if os.environ.get("MOLSDE_CFLAGS"):   # A/B switches of single kernels (e.g. -DMOLSDE_SINCOS_REF_ROUNDING)
+            cmd += os.environ["MOLSDE_CFLAGS"].split()
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()

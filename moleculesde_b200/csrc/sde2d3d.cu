@@ -157,6 +157,18 @@ __device__ __forceinline__ void sincos_reduced(float x, float& s, float& c) {
     c = __cosf(r);
 }
 
+// sin / cos of 2*pi*u for a phase u given in TURNS (GaussianFourierProjection: u = x * W): the integer part is removed exactly
+// (u - rint(u) is exact in fp32), the remaining |f| <= 0.5 is scaled to radians once and fed to the SFU.  5 FMA-pipe instructions
+// instead of 8 for "form x*W*2*pi as the reference rounds it, then Cody-Waite by 2*pi".  Against the reference's argument
+// rn(rn(rn(x W) 2) pi_f32) the phase differs by <= 0.5 ulp(arg) + 2.8e-8 arg (pi_f32 vs pi) -- 1e-6 rad at arg = 30, far below the
+// 1e-4 bar; at the VE03 preset's args of ~1e4 rad both sit inside the stated 2e-3 (one ulp of the argument there is 1e-3 rad).
+__device__ __forceinline__ void sincos_turns(float u, float& s, float& c) {
+    const float k = __fsub_rn(__fadd_rn(u, 12582912.0f), 12582912.0f);   // rint(u), |u| < 2^22
+    const float r = __fmul_rn(__fsub_rn(u, k), 6.2831854820251465f);
+    s = __sinf(r);
+    c = __cosf(r);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 // ---- mbarrier / TMA bulk copy / tcgen05 primitives --------------------------------------------
@@ -501,9 +513,12 @@ __device__ __noinline__ uint32_t phase_edge_features(const Chunk c, const float*
                 const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    // GaussianFourierProjection.forward, :64-66  (x * W * 2 * pi, fp32, in that order)
-                    const float arg = __fmul_rn(__fmul_rn(__fmul_rn(xb, wv[j]), 2.0f), 3.14159274101257324f);
-                    sincos_reduced(arg, v[4 * i4 + j], v[16 + 4 * i4 + j]);
+                    // GaussianFourierProjection.forward, :64-66: sin / cos of x * W * 2 * pi, evaluated from the phase in turns
+#ifdef MOLSDE_SINCOS_REF_ROUNDING
+                    sincos_reduced(__fmul_rn(__fmul_rn(__fmul_rn(xb, wv[j]), 2.0f), 3.14159274101257324f), v[4 * i4 + j], v[16 + 4 * i4 + j]);
+#else
+                    sincos_turns(__fmul_rn(xb, wv[j]), v[4 * i4 + j], v[16 + 4 * i4 + j]);
+#endif
                 }
             }
             ring_use(v, tq + tcol + (blk == 0 ? 0 : 32), w_bt + b * (MOLSDE_E0_BT_FLOATS * 4), (b == 0 || b == 2) ? 0u : 1u);
