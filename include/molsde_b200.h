@@ -48,6 +48,10 @@ typedef enum molsde_status {
 int molsde_build_plan_host(const int64_t* rowptr, const int64_t* node_ptr, int32_t B, const int64_t* groups, int32_t G, int32_t tile_edges,
                            int32_t max_nodes, int32_t max_tiles, int32_t* chunk_tile_ptr, int32_t* tile_tgt_ptr, int64_t* counts_out);
 
+/* test hook: echoes its arguments into out[12] and returns 7 (calling-convention check of the Python fast-call path) */
+int molsde_debug_echo(int64_t a, float x, int32_t b, const void* p, float y, int64_t c, int32_t d, uint64_t e, int64_t f, float z,
+                      int64_t g, int32_t h, double* out);
+
 const char* molsde_version(void);
 const char* molsde_last_error_string(void);
 /* compute capability check: returns MOLSDE_OK only on an sm_100 device */

@@ -50,7 +50,7 @@ EXPORTS = [
     "molsde_dense_sym_noise", "molsde_dense_perturb_adj", "molsde_dense_perturb_onehot", "molsde_graph_reduce",
     "molsde_langevin_step", "molsde_langevin_update", "molsde_reverse_update", "molsde_mask_rows",
     "molsde_dense_attn_sym", "molsde_dense_pair_mlp", "molsde_dense_edge_final_mlp", "molsde_dense_node_side", "molsde_dense_multi_channel",
-    "molsde_sde2d3d_pc_corrector_update", "molsde_sde2d3d_pc_predictor_update", "molsde_act_bwd2", "molsde_schnet_edge_feat_tangent", "molsde_build_plan_host",
+    "molsde_sde2d3d_pc_corrector_update", "molsde_sde2d3d_pc_predictor_update", "molsde_act_bwd2", "molsde_schnet_edge_feat_tangent", "molsde_build_plan_host", "molsde_debug_echo",
 ]
 
 
@@ -232,6 +232,8 @@ def lib() -> ctypes.CDLL:
     L.molsde_sde2d3d_pc_sample.argtypes = [POINTER(Plan), POINTER(Params), c_void_p, c_void_p, c_void_p, c_void_p,
                                            POINTER(PCConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_int64, c_void_p, c_void_p, c_void_p]
+    L.molsde_debug_echo.argtypes = [c_int64, c_float, c_int32, c_void_p, c_float, c_int64, c_int32, c_uint64, c_int64, c_float, c_int64,
+                                    c_int32, c_void_p]
     L.molsde_build_plan_host.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     L.molsde_act_bwd2.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]
     L.molsde_schnet_edge_feat_tangent.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_float, c_float,
@@ -243,8 +245,40 @@ def lib() -> ctypes.CDLL:
         fn = getattr(L, name)
         if fn.restype is ctypes.c_int:
             fn.restype = c_int32
-    _lib = L
-    return L
+    _lib = _fast_lib(L)
+    return _lib
+
+
+class _FastLib:
+    """The CDLL with its status-returning entry points rebound through `_molsde_fastcall` (csrc/fastcall.c): ~0.3 us per call
+    instead of ~3 us of ctypes marshalling -- the eager training step makes ~750 calls per iteration.  Entry points that take
+    ctypes structures / arrays by reference, return something else than the int status, or have no declared argtypes stay on ctypes."""
+
+    def __init__(self, cdll, fc):
+        self._cdll = cdll
+        plain = {c_void_p: "i", c_int32: "i", c_int64: "i", c_uint64: "i", c_float: "f"}
+        for name in EXPORTS:
+            fn = getattr(cdll, name)
+            at = fn.argtypes
+            if at is None or fn.restype is not c_int32 or any(t not in plain for t in at):
+                continue
+            sig = "".join(plain[t] for t in at)
+            if sig.count("i") > 28 or sig.count("f") > 8:
+                continue
+            setattr(self, name, fc.bind(ctypes.cast(fn, c_void_p).value, sig))
+
+    def __getattr__(self, name):   # anything not rebound: the ctypes function
+        return getattr(self._cdll, name)
+
+
+def _fast_lib(cdll):
+    if os.environ.get("MOLSDE_NO_FASTCALL") == "1":
+        return cdll
+    try:
+        from . import _molsde_fastcall as fc
+    except ImportError:
+        return cdll   # the extension is an optimisation of the HOST path only; ctypes reaches the same kernels
+    return _FastLib(cdll, fc)
 
 
 _device_checked = set()

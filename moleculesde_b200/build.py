@@ -8,6 +8,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmolsde_b200.so")
+FASTCALL_PATH = os.path.join(_HERE, "_molsde_fastcall.so")   # CPython extension: low-overhead call path (csrc/fastcall.c)
 
 
 def sources():
@@ -23,7 +24,21 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in deps)
 
 
+def build_fastcall(force: bool = False) -> str:
+    """gcc-compiled CPython extension next to the library (x86-64 SysV); rebuilt when its source is newer."""
+    import sysconfig
+    src = os.path.join(CSRC, "fastcall.c")
+    if not force and os.path.exists(FASTCALL_PATH) and os.path.getmtime(FASTCALL_PATH) >= os.path.getmtime(src):
+        return FASTCALL_PATH
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-shared", "-fPIC", "-I" + sysconfig.get_paths()["include"], src, "-o", FASTCALL_PATH]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"gcc failed on fastcall.c:\n{r.stdout}")
+    return FASTCALL_PATH
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    build_fastcall(force)
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -46,6 +46,16 @@ int molsde_check_device(int device) {
     return MOLSDE_OK;
 }
 
+/* Test hook for the calling-convention shortcut of csrc/fastcall.c: echoes its (deliberately interleaved, stack-spilling) arguments. */
+int molsde_debug_echo(int64_t a, float x, int32_t b, const void* p, float y, int64_t c, int32_t d, uint64_t e, int64_t f, float z,
+                      int64_t g, int32_t h, double* out) {
+    if (!out) return MOLSDE_ERR_INVALID;
+    out[0] = static_cast<double>(a); out[1] = x; out[2] = b; out[3] = static_cast<double>(reinterpret_cast<uintptr_t>(p)); out[4] = y;
+    out[5] = static_cast<double>(c); out[6] = d; out[7] = static_cast<double>(e); out[8] = static_cast<double>(f); out[9] = z;
+    out[10] = static_cast<double>(g); out[11] = h;
+    return 7;
+}
+
 /* Host-side chunk / tile plan of a batch (the bookkeeping behind molsde_plan): chunks = runs of whole molecules (<= max_nodes atoms,
  * greedy under an edge budget of 0.6 * max_tiles * tile_edges) or the caller's fixed groups; tiles = runs of whole target nodes with
  * <= tile_edges incoming edges (greedy, <= tile_edges targets).  Plain sequential C over HOST arrays: the Python loop it replaces cost

@@ -330,3 +330,30 @@ def test_build_plan_host_matches_python_specification():
             except _abi.MolsdeError as e:
                 res.append(("error", str(e).split(" ")[0]))
         assert res[0] == res[1], (trial, res[0][:3], res[1][:3])
+
+
+def test_fastcall_matches_ctypes_calling_convention(built_lib):
+    """`_molsde_fastcall` (csrc/fastcall.c) passes interleaved int32 / int64 / uint64 / pointer / float arguments -- more integer-class
+    arguments than registers, so some travel on the stack -- exactly like ctypes does, None becomes NULL, ints are accepted for float
+    parameters, wrong arity raises; and `_abi.lib()` rebinds the status-returning entry points through it."""
+    import ctypes
+    import numpy as np
+    from moleculesde_b200 import _abi
+    L = _abi.lib()
+    assert type(L).__name__ == "_FastLib" and type(L.molsde_debug_echo).__name__ == "Bound"
+    assert type(L.molsde_version).__name__ != "Bound"                    # returns a string: stays on ctypes
+    assert type(L.molsde_sde2d3d_pc_sample).__name__ != "Bound"          # takes structures by reference: stays on ctypes
+    raw = ctypes.CDLL(built_lib)
+    raw.molsde_debug_echo.argtypes = L._cdll.molsde_debug_echo.argtypes
+    raw.molsde_debug_echo.restype = ctypes.c_int32
+    args = (-(2 ** 40) - 3, 1.25, -7, 0x7F00DEADBEE0, -3.5, 2 ** 41 + 1, 123456, 2 ** 63 + 5, -9, 0.1, 77, -2 ** 31)
+    a, b = np.zeros(16), np.zeros(16)
+    assert L.molsde_debug_echo(*args, a.ctypes.data) == 7
+    assert raw.molsde_debug_echo(*args, b.ctypes.data) == 7
+    assert np.array_equal(a, b) and a[0] == args[0] and a[9] == np.float32(0.1) and a[11] == -2 ** 31
+    c = np.zeros(16)
+    assert L.molsde_debug_echo(1, 2, 3, None, 4, 5, 6, 7, 8, 9, 10, 11, c.ctypes.data) == 7   # ints for floats, None for the pointer
+    assert c[1] == 2.0 and c[3] == 0.0 and c[4] == 4.0 and c[9] == 9.0
+    assert L.molsde_debug_echo(*args, None) == -1                                               # MOLSDE_ERR_INVALID
+    with pytest.raises(TypeError):
+        L.molsde_debug_echo(1, 2, 3)
