@@ -351,6 +351,12 @@ int molsde_edge_mul_reduce(const float* A, const int32_t* ia, const float* W, co
 /* out[e,:] = A[ia[e],:] * B[ib[e],:] */
 int molsde_edge_mul_gather(const float* A, const int32_t* ia, const float* B, const int32_t* ib, int64_t E, int32_t cols, float* out,
                            void* stream);
+/* the same two with a leading dimension: W is a column block of a wider [E, ldw] filter stack (all SchNet interactions' filters
+ * side by side, schnet.py:185-195 evaluated once per batch), out a column block of the matching gradient stack [E, ldo] */
+int molsde_edge_mul_reduce_ld(const float* A, const int32_t* ia, const float* W, int64_t ldw, const int32_t* ptr, const int32_t* perm,
+                              int64_t segments, int32_t cols, float* out, void* stream);
+int molsde_edge_mul_gather_ld(const float* A, const int32_t* ia, const float* B, const int32_t* ib, int64_t E, int32_t cols, float* out,
+                              int64_t ldo, void* stream);
 /* out[0] (+)= alpha <a,b>;  ws: >= 128 doubles */
 int molsde_dot(const float* a, const float* b, int64_t n, float alpha, int32_t accumulate, float* out, double* ws, void* stream);
 /* do_CL, metric InfoNCE_dot_prod (examples/util.py:23-32): rows of logits [B,B] = X Y^T / T (a molsde_tc_gemm):

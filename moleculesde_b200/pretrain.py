@@ -30,6 +30,9 @@ _STREAM_PRIORITY = _os.environ.get("MOLSDE_STREAM_PRIORITY", "1") == "1"   # A/B
 
 _CH = re.compile(r"^edge_score_network\.layers\.(\d+)\.attn\.(\d+)\.(func_q|func_k)\.layers\.(\d)\.(weight|bias)$")
 _CV = re.compile(r"^edge_score_network\.layers\.(\d+)\.attn\.(\d+)\.func_v\.(weight|bias)$")
+_QKVS = ("lin_query", "lin_key", "lin_value", "lin_skip")
+_CG = re.compile(r"^score_network\.gnn_layers\.(\d+)\.(\d+)\.MHA\.(lin_query|lin_key|lin_value|lin_skip)\.(weight|bias)$")
+_CF = re.compile(r"^interactions\.(\d+)\.mlp\.(0|2)\.(weight|bias)$")
 
 
 def _layout_key(pname: str):
@@ -44,11 +47,28 @@ def _layout_key(pname: str):
     m = _CV.match(pname)
     if m:
         return (0, int(m.group(1)), 4 + (m.group(3) == "bias"), 0, int(m.group(2)))
+    m = _CG.match(pname)   # TransformerConv projections of one GATLayer: q | k | v | skip = ONE [128, 32] weight (one GEMM per layer)
+    if m:
+        return (0, 2 * int(m.group(1)) + int(m.group(2)), m.group(4) == "bias", _QKVS.index(m.group(3)), 0)
+    m = _CF.match(pname)   # SchNet filter networks: the same layer of all interactions = one [G*128, 51] / [G, 128, 128] stack
+    if m:
+        return (0, 0, 2 * (m.group(2) == "2") + (m.group(3) == "bias"), 0, int(m.group(1)))
     return (1,)
 
 
 def _stacked(P: Dict[str, "Var"], names, shape) -> Optional["Var"]:
-    """Zero-copy [G, ...] view over parameters that are adjacent in a ParamStore (data and gradient), else None."""
+    """Zero-copy [G, ...] view over parameters that are adjacent in a ParamStore (data and gradient), else None.
+    The views of a ParamStore never move, so the result is cached in `P` itself."""
+    cache = P.get("__stacked__")
+    if cache is None:
+        cache = P["__stacked__"] = {}
+    key = (names[0], shape)
+    if key not in cache:
+        cache[key] = _stacked_uncached(P, names, shape)
+    return cache[key]
+
+
+def _stacked_uncached(P: Dict[str, "Var"], names, shape) -> Optional["Var"]:
     vs = [P[n] for n in names]
     if any(v.grad is None for v in vs):
         return None
@@ -301,11 +321,14 @@ def _gat_layer(tp: Tape, P: Dict[str, Var], pf: str, x: Var, edge_attr: Var, es:
     """GATLayer.forward (`equivariant_scorenetwork.py:34-40`) over TransformerConv heads 8 x 4."""
     L, N, E, s = tp.L, es.N, es.E, tp.s
     attn_keep, ffn_keep = keep
-    qkvs = Var(tp.empty(N, 128), False)
-    tp.linear(x, P[pf + "MHA.lin_query.weight"], P[pf + "MHA.lin_query.bias"], into=qkvs, col0=0)
-    tp.linear(x, P[pf + "MHA.lin_key.weight"], P[pf + "MHA.lin_key.bias"], into=qkvs, col0=32)
-    tp.linear(x, P[pf + "MHA.lin_value.weight"], P[pf + "MHA.lin_value.bias"], into=qkvs, col0=64)
-    tp.linear(x, P[pf + "MHA.lin_skip.weight"], P[pf + "MHA.lin_skip.bias"], into=qkvs, col0=96)
+    Wq = _stacked(P, [pf + f"MHA.{n}.weight" for n in _QKVS], (128, 32))
+    bq = _stacked(P, [pf + f"MHA.{n}.bias" for n in _QKVS], (128,))
+    if Wq is not None and bq is not None:   # q | k | v | skip adjacent in the flat buffer (`_layout_key`): ONE [N,32] x [128,32]^T GEMM
+        qkvs = tp.linear(x, Wq, bq)
+    else:
+        qkvs = Var(tp.empty(N, 128), False)
+        for j, n in enumerate(_QKVS):
+            tp.linear(x, P[pf + f"MHA.{n}.weight"], P[pf + f"MHA.{n}.bias"], into=qkvs, col0=32 * j)
     eproj = tp.linear(edge_attr, P[pf + "MHA.lin_edge.weight"], None)
     alpha, out = tp.empty(E, 8), Var(tp.empty(N, 32), True)
     tp._call(L.molsde_tconv_fwd, ptr(qkvs.data), ptr(eproj.data), ptr(es.rowptr), ptr(es.src.idx), N, _p(attn_keep), p_drop,
@@ -379,7 +402,7 @@ def tape_gin(tp: Tape, model, P: Dict[str, Var], x: torch.Tensor, edge_index: to
     from .tape import bucket_index
     dev = x.device
     require_device(x)
-    train = any(v.needs for v in P.values())
+    train = any(v.needs for v in P.values() if isinstance(v, Var))
     cache = cache if cache is not None else {}
     prepare_gin(cache, x, edge_index, edge_attr, batch, num_graphs, train)
     csr, es, akeys, ekeys, aidx, eidx = cache["gin"]
@@ -469,13 +492,30 @@ def tape_schnet(tp: Tape, model, P: Dict[str, Var], z: torch.Tensor, pos: torch.
             tp.ew(0, dpos, dneg, None, -1.0, dpos)
             tp.accum(pos_var, dpos)
         tp.ops.append(pos_bwd)
-    for i in range(model.num_interactions):
+    # The filter networks W_i(e) = C(d_e) * mlp_i(GaussianSmearing(d_e)) depend on the edges only, not on h: all interactions'
+    # filters are evaluated up front as ONE stack [E, G*F] (first layers = one GEMM against the [G*F, 51] weight stack, second
+    # layers = one grouped GEMM) when the parameters are adjacent in the flat buffer (`_layout_key`); their backward runs once,
+    # after every interaction deposited d W_i in its column block.  Same dot products as the per-interaction form.
+    G = model.num_interactions
+    F_, ng = P["interactions.0.mlp.2.weight"].data.shape[0], ea.shape[1]
+    Wf_all = None
+    if not need_pos and G > 0 and es.E > 0:
+        names = lambda k: [f"interactions.{i}.mlp.{k}" for i in range(G)]   # noqa: E731
+        W0s, b0s = _stacked(P, names("0.weight"), (G * F_, ng)), _stacked(P, names("0.bias"), (G * F_,))
+        W2s, b2s = _stacked(P, names("2.weight"), (G, F_, F_)), _stacked(P, names("2.bias"), (G * F_,))
+        if None not in (W0s, b0s, W2s, b2s):
+            f1 = tp.linear(ea_v, W0s, b0s, act="ssp")
+            Wf_all = tp.rowscale(tp.grouped_linear(f1, W2s, b2s, G), C)
+    for i in range(G):
         pf = f"interactions.{i}."
-        f1 = tp.linear(ea_v, P[pf + "mlp.0.weight"], P[pf + "mlp.0.bias"], act="ssp")
-        f2 = tp.linear(f1, P[pf + "mlp.2.weight"], P[pf + "mlp.2.bias"])
-        Wf = tp.rowscale_var(f2, C_v) if need_pos else tp.rowscale(f2, C)
         x = tp.linear(h, P[pf + "conv.lin1.weight"], None)
-        agg = tp.edge_mul_reduce(x, Wf, es.rowptr, es.src, es.tgt)
+        if Wf_all is not None:
+            agg = tp.edge_mul_reduce(x, Wf_all, es.rowptr, es.src, es.tgt, wcol0=i * F_)
+        else:
+            f1 = tp.linear(ea_v, P[pf + "mlp.0.weight"], P[pf + "mlp.0.bias"], act="ssp")
+            f2 = tp.linear(f1, P[pf + "mlp.2.weight"], P[pf + "mlp.2.bias"])
+            Wf = tp.rowscale_var(f2, C_v) if need_pos else tp.rowscale(f2, C)
+            agg = tp.edge_mul_reduce(x, Wf, es.rowptr, es.src, es.tgt)
         t = tp.linear(agg, P[pf + "conv.lin2.weight"], P[pf + "conv.lin2.bias"], act="ssp")
         u = tp.linear(t, P[pf + "lin.weight"], P[pf + "lin.bias"])
         h = tp.add(h, u)

@@ -387,16 +387,14 @@ class Tape:
     def scale_mask(self, x: Var, mask: torch.Tensor, alpha: float) -> Var:
         """x * mask * alpha (dropout with a given keep mask)."""
         y = self.empty(x.data.shape)
-        self.ew(1, x.data, mask, None, 1.0, y)
-        self.ew(0, y, None, None, alpha, y)
+        self.ew(2, x.data, mask, None, alpha, y, cols=1)   # x * alpha * mask in one launch (mask is 0/1: same bits as (x*mask)*alpha)
         out = Var(y, x.needs)
         if x.needs:
             def bwd():
                 if out.grad is None:
                     return
                 g = self.empty(y.shape)
-                self.ew(1, out.grad, mask, None, 1.0, g)
-                self.ew(0, g, None, None, alpha, g)
+                self.ew(2, out.grad, mask, None, alpha, g, cols=1)
                 self.accum(x, g)
             self.ops.append(bwd)
         return out
@@ -558,12 +556,16 @@ class Tape:
             self.ops.append(bwd)
         return out
 
-    def edge_mul_reduce(self, x: Var, W: Var, rowptr: torch.Tensor, src: Index, tgt: Index) -> Var:
-        """CFConv message + aggregation: out[i] = sum_{e->i} x[src_e] * W[e]  (schnet.py:186-195)."""
+    def edge_mul_reduce(self, x: Var, W: Var, rowptr: torch.Tensor, src: Index, tgt: Index, wcol0: Optional[int] = None) -> Var:
+        """CFConv message + aggregation: out[i] = sum_{e->i} x[src_e] * W[e]  (schnet.py:186-195).
+        `wcol0`: the filter is the column block [wcol0, wcol0+cols) of the wider stack W (all interactions' filters side by
+        side); its gradient is WRITTEN into the same block of W.grad (each block has exactly one consumer)."""
         N, cols = x.data.shape
         E = W.data.shape[0]
         y = self.empty(N, cols)
-        self._call(self.L.molsde_edge_mul_reduce, _p(x.data), _p(src.idx), _p(W.data), _p(rowptr), None, N, cols, _p(y), self.s,
+        Wd = W.data if wcol0 is None else W.data[:, wcol0:wcol0 + cols]
+        ldw = _ld(Wd)
+        self._call(self.L.molsde_edge_mul_reduce_ld, _p(x.data), _p(src.idx), _p(Wd), ldw, _p(rowptr), None, N, cols, _p(y), self.s,
                    what="edge_mul_reduce")
         out = Var(y, x.needs or W.needs)
         if out.needs:
@@ -571,14 +573,21 @@ class Tape:
                 if out.grad is None:
                     return
                 if W.needs:
-                    dW = self.empty(E, cols)
-                    self._call(self.L.molsde_edge_mul_gather, _p(out.grad), _p(tgt.idx), _p(x.data), _p(src.idx), E, cols, _p(dW),
-                               self.s, what="edge_mul_gather")
-                    self.accum(W, dW)
+                    if wcol0 is None:
+                        dW = self.empty(E, cols)
+                        self._call(self.L.molsde_edge_mul_gather_ld, _p(out.grad), _p(tgt.idx), _p(x.data), _p(src.idx), E, cols, _p(dW),
+                                   cols, self.s, what="edge_mul_gather")
+                        self.accum(W, dW)
+                    else:
+                        if W.grad is None:
+                            W.grad = self.empty(W.data.shape)   # every column block is written by its interaction's backward
+                        dW = W.grad[:, wcol0:wcol0 + cols]
+                        self._call(self.L.molsde_edge_mul_gather_ld, _p(out.grad), _p(tgt.idx), _p(x.data), _p(src.idx), E, cols, _p(dW),
+                                   _ld(dW), self.s, what="edge_mul_gather")
                 if x.needs:
                     dx = self.empty(N, cols)
-                    self._call(self.L.molsde_edge_mul_reduce, _p(out.grad), _p(tgt.idx), _p(W.data), _p(src.ptr), _p(src.perm), N, cols,
-                               _p(dx), self.s, what="edge_mul_reduce")
+                    self._call(self.L.molsde_edge_mul_reduce_ld, _p(out.grad), _p(tgt.idx), _p(Wd), ldw, _p(src.ptr), _p(src.perm), N,
+                               cols, _p(dx), self.s, what="edge_mul_reduce")
                     self.accum(x, dx)
             self.ops.append(bwd)
         return out
