@@ -357,6 +357,20 @@ int molsde_edge_mul_reduce_ld(const float* A, const int32_t* ia, const float* W,
                               int64_t segments, int32_t cols, float* out, void* stream);
 int molsde_edge_mul_gather_ld(const float* A, const int32_t* ia, const float* B, const int32_t* ib, int64_t E, int32_t cols, float* out,
                               int64_t ldo, void* stream);
+/* Whole-chain kernels of the narrow 3-layer MLPs applied to the B*Nm^2 atom pairs in TRAINING (EdgeNetwork_dense.mlp,
+ * edge_network_dense.py:120-123; EdgeScoreNetwork_dense.final, invariant_scorenetwork_dense.py:60-62): y = W3 act(W2 act(W1 x + b1)
+ * + b2) + b3, thread = row, hidden vectors in registers, fp32 FFMA.  fwd keeps the pre-activations p1, p2 [rows, h]; bwd runs the
+ * whole input-gradient chain and leaves a1 = act(p1), a2 = act(p2), d1, d2 [rows, h] (the operands of the three weight-gradient
+ * GEMMs) and dx [rows, d0] (row stride lddx; NULL = not wanted).  x row stride ldx; y, dy dense [rows, d3].
+ * act: 2 silu, 5 elu.  Only the (d0, h, d3, act) combinations reported by molsde_mlp3_train_supported exist (others:
+ * MOLSDE_ERR_UNSUPPORTED; the host keeps the layer-granular path). */
+int molsde_mlp3_train_supported(int32_t d0, int32_t h, int32_t d3, int32_t act);   /* 1 / 0 */
+int molsde_mlp3_train_fwd(const float* x, int64_t rows, int64_t ldx, int32_t d0, int32_t h, int32_t d3, int32_t act, const float* W1,
+                          const float* b1, const float* W2, const float* b2, const float* W3, const float* b3, float* p1, float* p2,
+                          float* y, void* stream);
+int molsde_mlp3_train_bwd(const float* p1, const float* p2, const float* dy, int64_t rows, int32_t d0, int32_t h, int32_t d3, int32_t act,
+                          const float* W1, const float* W2, const float* W3, float* a1, float* a2, float* d1, float* d2, float* dx,
+                          int64_t lddx, void* stream);
 /* out[0] (+)= alpha <a,b>;  ws: >= 128 doubles */
 int molsde_dot(const float* a, const float* b, int64_t n, float alpha, int32_t accumulate, float* out, double* ws, void* stream);
 /* do_CL, metric InfoNCE_dot_prod (examples/util.py:23-32): rows of logits [B,B] = X Y^T / T (a molsde_tc_gemm):

@@ -40,7 +40,7 @@ EXPORTS = [
     "molsde_expand_rowptr", "molsde_layernorm_fwd", "molsde_layernorm_bwd", "molsde_bn_ws_doubles", "molsde_bn_train_fwd",
     "molsde_bn_train_bwd", "molsde_adam_step", "molsde_sde2d3d_edge_geom", "molsde_tconv_fwd", "molsde_tconv_bwd",
     "molsde_equi_fwd", "molsde_equi_bwd", "molsde_dsm_pos_loss_bwd", "molsde_embed_sum", "molsde_edge_mul_reduce",
-    "molsde_edge_mul_gather", "molsde_edge_mul_reduce_ld", "molsde_edge_mul_gather_ld", "molsde_dot", "molsde_gin_aggregate_fwd", "molsde_gin_message_bwd", "molsde_schnet_edge_feat",
+    "molsde_edge_mul_gather", "molsde_edge_mul_reduce_ld", "molsde_edge_mul_gather_ld", "molsde_mlp3_train_supported", "molsde_mlp3_train_fwd", "molsde_mlp3_train_bwd", "molsde_dot", "molsde_gin_aggregate_fwd", "molsde_gin_message_bwd", "molsde_schnet_edge_feat",
     "molsde_schnet_edge_feat_bwd", "molsde_rowdot", "molsde_bn_train_bwd_fused",
     "molsde_ebm_node_dot_bwd", "molsde_infonce_rows", "molsde_bn_eval", "molsde_dense_gcn_bwd", "molsde_dense_attn_bwd",
     "molsde_dense_pair_post_bwd", "molsde_dense_edge_final_bwd", "molsde_graph_mse_bwd", "molsde_from_dense_batch", "molsde_copy2d", "molsde_mean", "molsde_sum_slices", "molsde_tc_gemm_ws_floats", "molsde_tc_gemm", "molsde_tc_gemm_batched_ws_floats", "molsde_tc_gemm_batched", "molsde_tc_gemm_dw_db", "molsde_mlp3_rows",
@@ -178,6 +178,9 @@ def lib() -> ctypes.CDLL:
     L.molsde_edge_mul_gather.argtypes = [P, P, P, P, c_int64, c_int32, P, P]
     L.molsde_edge_mul_reduce_ld.argtypes = [P, P, P, c_int64, P, P, c_int64, c_int32, P, P]
     L.molsde_edge_mul_gather_ld.argtypes = [P, P, P, P, c_int64, c_int32, P, c_int64, P]
+    L.molsde_mlp3_train_supported.argtypes = [c_int32, c_int32, c_int32, c_int32]
+    L.molsde_mlp3_train_fwd.argtypes = [P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P]
+    L.molsde_mlp3_train_bwd.argtypes = [P, P, P, c_int64, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, P, P, P, c_int64, P]
     L.molsde_dot.argtypes = [P, P, c_int64, c_float, c_int32, P, P, P]
     L.molsde_gin_aggregate_fwd.argtypes = [P, P, P, c_int32, P, P, P, c_int64, c_int32, P, P]
     L.molsde_gin_message_bwd.argtypes = [P, P, P, c_int32, P, P, P, c_int64, c_int32, P, P]

@@ -18,6 +18,7 @@ batch after asking for the next one unless you keep your own reference to it unt
 from __future__ import annotations
 
 import queue
+import sys
 import threading
 from typing import Callable, Iterable, Iterator, Optional
 
@@ -93,6 +94,11 @@ class DeviceLoader:
     def __iter__(self) -> Iterator:
         q: "queue.Queue" = queue.Queue(maxsize=self.depth)
         stop = threading.Event()
+        # The consumer's eager step is ~10 ms of pure Python that never blocks; with CPython's default 5 ms switch interval the
+        # loader thread would get the GIL back only 5 ms after each of its host syncs (a handful per batch) and become the
+        # bottleneck.  A short interval hands the GIL over promptly; restored when the iteration ends.
+        old_switch = sys.getswitchinterval()
+        sys.setswitchinterval(min(old_switch, 2e-4))
         th = threading.Thread(target=self._worker, args=(q, stop), daemon=True, name="molsde-loader")
         th.start()
         retired = []      # (batch, event on the consumer stream): kept until the consumer's work on the batch has finished
@@ -116,6 +122,7 @@ class DeviceLoader:
                 prev = b
                 yield b
         finally:
+            sys.setswitchinterval(old_switch)
             stop.set()
             while th.is_alive():      # unblock a producer waiting on a full queue
                 try:

@@ -21,6 +21,7 @@ from .tape import Index, Tape, Var, _p
 
 import os as _os
 _GIN_EXACT = _os.environ.get("MOLSDE_GIN_TC") != "1"   # experiment switch: GIN linears on the tensor cores in training too
+_NO_MLP3 = _os.environ.get("MOLSDE_NO_MLP3") == "1"   # A/B switch: layer-granular pair MLPs instead of the whole-chain kernels
 _SINGLE_STREAM = _os.environ.get("MOLSDE_SINGLE_STREAM") == "1"   # A/B switch: issue the whole iteration on one stream
 # parameter gradients on side streams (Tape.wgrad): "capture" = only while a CUDA graph is being captured (the eager step is
 # bound by host launch time, where the extra event calls cost more than the overlap returns), "1" always, "0" never
@@ -688,6 +689,11 @@ def _dense_gcn(tp: Tape, adjc: Var, c: int, C: int, xw: Var, xw_col0: int, bias:
 
 
 def _mlp(tp: Tape, P: Dict[str, Var], prefix: str, x: Var, n_layers: int, act: str, last_rowscale=None, last_act: str = "none") -> Var:
+    if n_layers == 3 and last_rowscale is None and last_act == "none" and not _NO_MLP3:
+        Ws = [P[f"{prefix}.layers.{i}.weight"] for i in range(3)]
+        bs = [P.get(f"{prefix}.layers.{i}.bias") for i in range(3)]
+        if tp.mlp3_supported(x, Ws, bs, act):     # narrow pair MLPs: one forward + one input-gradient launch (csrc/train_mlp.cu)
+            return tp.mlp3(x, Ws, bs, act)
     for i in range(n_layers):
         last = i == n_layers - 1
         x = tp.linear(x, P[f"{prefix}.layers.{i}.weight"], P[f"{prefix}.layers.{i}.bias"], act=last_act if last else act,

@@ -23,11 +23,14 @@ TC_MIN_WORK = (1 << 62) if _os.environ.get("MOLSDE_NO_TC") == "1" else (1 << 20)
 FUSED_DB = _os.environ.get("MOLSDE_NO_FUSED_DB") != "1"   # bias gradient through the all-ones row of the dW GEMM
 
 
+_CHECK = _abi.CHECK_ABI
+
+
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
     """data pointer of a contiguous tensor or of a 2-D row-strided view (stride(1) == 1)."""
     if t is None:
         return None
-    if _abi.CHECK_ABI and not t.is_contiguous():
+    if _CHECK and not t.is_contiguous():
         assert t.dim() == 2 and t.stride(1) == 1, "only contiguous tensors and row-strided 2-D views cross the C ABI"
     return t.data_ptr()
 
@@ -103,7 +106,9 @@ class Tape:
 
     def _call(self, fn, *args, what=""):
         self.launches += 1
-        check(fn(*args), what or fn.__name__)
+        st = fn(*args)
+        if st:
+            check(st, what or fn.__name__)
 
     def ew(self, op, a, b, c, alpha, out, cols=1):
         self._call(self.L.molsde_ew, op, _p(a), _p(b), _p(c), float(alpha), out.numel(), cols, _p(out), self.s, what="ew")
@@ -234,18 +239,7 @@ class Tape:
                     t = self.empty(M, Nout)
                     self.ew(2, dpre, rowscale, None, 1.0, t, cols=Nout)
                     dpre = t
-                with self.wgrad(dpre, x.data):
-                    if FUSED_DB and W.needs and b is not None and b.needs and Nout * K * M >= TC_MIN_WORK:
-                        # dW and db in one tensor-core GEMM (db = the product with an all-ones extra row)
-                        n = self.L.molsde_tc_gemm_ws_floats(Nout, K + 1, M)
-                        ws = self.empty(n) if n > 0 else None
-                        self._call(self.L.molsde_tc_gemm_dw_db, Nout, K, M, _p(dpre), 1, _ld(dpre), _p(x.data), 1, _ld(x.data),
-                                   _p(W.grad), _ld(W.grad), _p(b.grad), 1, _p(ws), n, None, self.s, what="tc_gemm_dw_db")
-                    else:
-                        if W.needs:
-                            self.gemm(1, 0, Nout, K, M, dpre, _ld(dpre), x.data, _ld(x.data), W.grad, _ld(W.grad), accumulate=True)
-                        if b is not None and b.needs:
-                            self.colsum(dpre, M, Nout, _ld(dpre), b.grad, accumulate=True)
+                self.linear_wgrad(dpre, x.data, W, b)
                 if x_cols is not None:
                     if full.needs:
                         g = self.grad_of(full)[:, x_cols[0]:x_cols[1]]
@@ -259,6 +253,67 @@ class Tape:
                         self.gemm(0, 0, M, K, Nout, dpre, _ld(dpre), W.data, _ld(W.data), dx, K)
                         self.accum(x, dx)
             self.ops.append(bwd)
+        return out
+
+    def linear_wgrad(self, dpre: torch.Tensor, xd: torch.Tensor, W: Var, b: Optional[Var]) -> None:
+        """Parameter gradients of y = x W^T + b on the side stream: W.grad += dpre^T x, b.grad += column sums of dpre."""
+        M, K = xd.shape
+        Nout = dpre.shape[1]
+        with self.wgrad(dpre, xd):
+            if FUSED_DB and W.needs and b is not None and b.needs and Nout * K * M >= TC_MIN_WORK:
+                # dW and db in one tensor-core GEMM (db = the product with an all-ones extra row)
+                n = self.L.molsde_tc_gemm_ws_floats(Nout, K + 1, M)
+                ws = self.empty(n) if n > 0 else None
+                self._call(self.L.molsde_tc_gemm_dw_db, Nout, K, M, _p(dpre), 1, _ld(dpre), _p(xd), 1, _ld(xd),
+                           _p(W.grad), _ld(W.grad), _p(b.grad), 1, _p(ws), n, None, self.s, what="tc_gemm_dw_db")
+            else:
+                if W.needs:
+                    self.gemm(1, 0, Nout, K, M, dpre, _ld(dpre), xd, _ld(xd), W.grad, _ld(W.grad), accumulate=True)
+                if b is not None and b.needs:
+                    self.colsum(dpre, M, Nout, _ld(dpre), b.grad, accumulate=True)
+
+    _mlp3_ok: dict = {}
+
+    def mlp3_supported(self, x: Var, Ws, bs, act: str) -> bool:
+        """True when `molsde_mlp3_train_*` has an instantiation for these three layers (narrow, contiguous weights, all biases)."""
+        if len(Ws) != 3 or any(b is None for b in bs) or ACT[act] not in (2, 5) or x.data.dim() != 2 or x.data.stride(1) != 1:
+            return False
+        d0, h, d3 = x.data.shape[1], Ws[0].data.shape[0], Ws[2].data.shape[0]
+        if Ws[0].data.shape != (h, d0) or Ws[1].data.shape != (h, h) or Ws[2].data.shape != (d3, h):
+            return False
+        if not all(w.data.is_contiguous() for w in Ws):
+            return False
+        key = (d0, h, d3, ACT[act])
+        ok = Tape._mlp3_ok.get(key)
+        if ok is None:
+            ok = Tape._mlp3_ok[key] = bool(self.L.molsde_mlp3_train_supported(*key))
+        return ok
+
+    def mlp3(self, x: Var, Ws, bs, act: str) -> Var:
+        """y = W3 act(W2 act(W1 x + b1) + b2) + b3 as ONE forward and ONE input-gradient launch (csrc/train_mlp.cu); the three
+        weight-gradient GEMMs stay leaves on the side stream.  Call only when `mlp3_supported`."""
+        rows, d0 = x.data.shape
+        h, d3 = Ws[0].data.shape[0], Ws[2].data.shape[0]
+        a = ACT[act]
+        p1, p2, y = self.empty(rows, h), self.empty(rows, h), self.empty(rows, d3)
+        self._call(self.L.molsde_mlp3_train_fwd, _p(x.data), rows, _ld(x.data), d0, h, d3, a, _p(Ws[0].data), _p(bs[0].data),
+                   _p(Ws[1].data), _p(bs[1].data), _p(Ws[2].data), _p(bs[2].data), _p(p1), _p(p2), _p(y), self.s, what="mlp3_train_fwd")
+        out = Var(y, True)
+
+        def bwd():
+            if out.grad is None:
+                return
+            dy = out.grad
+            a1, a2, d1, d2 = self.empty(rows, h), self.empty(rows, h), self.empty(rows, h), self.empty(rows, h)
+            dx = self.empty(rows, d0) if x.needs else None
+            self._call(self.L.molsde_mlp3_train_bwd, _p(p1), _p(p2), _p(dy), rows, d0, h, d3, a, _p(Ws[0].data), _p(Ws[1].data),
+                       _p(Ws[2].data), _p(a1), _p(a2), _p(d1), _p(d2), _p(dx), d0, self.s, what="mlp3_train_bwd")
+            self.linear_wgrad(dy, a2, Ws[2], bs[2])
+            self.linear_wgrad(d2, a1, Ws[1], bs[1])
+            self.linear_wgrad(d1, x.data, Ws[0], bs[0])
+            if dx is not None:
+                self.accum(x, dx)
+        self.ops.append(bwd)
         return out
 
     def matmul(self, x: Var, Wio: Var, into: Optional[Var] = None, col0: int = 0) -> Var:

@@ -12,13 +12,14 @@ b = build_batch(B, 0, dev)
 for _ in range(3):
     ps.step(b)
 torch.cuda.synchronize()
-t0 = time.perf_counter()
-for _ in range(10):
-    ps.step(b)
-t_issue = (time.perf_counter() - t0) / 10
-torch.cuda.synchronize()
-t_total = (time.perf_counter() - t0) / 10
-print(f"eager step: host issue {t_issue * 1e3:.2f} ms, incl. device drain {t_total * 1e3:.2f} ms, {ps.launches} launches")
+for rep in range(3):
+    t0 = time.perf_counter()
+    for _ in range(10):
+        ps.step(b)
+    t_issue = (time.perf_counter() - t0) / 10
+    torch.cuda.synchronize()
+    t_total = (time.perf_counter() - t0) / 10
+    print(f"eager step: host issue {t_issue * 1e3:.2f} ms, incl. device drain {t_total * 1e3:.2f} ms, {ps.launches} launches")
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(10):
@@ -26,4 +27,5 @@ for _ in range(10):
 pr.disable()
 torch.cuda.synchronize()
 st = pstats.Stats(pr)
-st.sort_stats("tottime").print_stats(22)
+st.sort_stats("tottime").print_stats(45)
+st.sort_stats("cumtime").print_stats(40)
