@@ -626,7 +626,7 @@ def bench_pretrain(args, dev, rank, world):
     # read back.  The input pipeline (loader.DeviceLoader) stages batch k+1 -- copies + PretrainStep.prepare on a copy stream in
     # a background thread -- while step k runs; the loader is created INSIDE the timed region, so every H2D copy is in it.
     from moleculesde_b200.loader import DeviceLoader, pin_batch
-    e2e_steps = 20
+    e2e_steps = 60
     loss_h = [torch.empty(1).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event() for _ in range(2)]
     hbp = pin_batch(hb)

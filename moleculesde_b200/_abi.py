@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmolsde_b200.so")
+LIB_PATH = os.environ.get("MOLSDE_LIB_PATH") or os.path.join(_HERE, "libmolsde_b200.so")   # (override: A/B of two builds)
 
 # keep in sync with include/molsde_b200.h
 MAX_MOL_NODES = 128

@@ -144,6 +144,9 @@ constexpr uint32_t QS_MMA0 = 1u, QS_MMA1 = 2u, QS_TMA = 4u, QS_DEAD = 8u, QS_FUL
 // ---------------------------------------------------------------------------------------
 // fast, accuracy-checked elementwise helpers (absolute / relative error ~1e-6, far below the 1e-4 bar)
 // ---------------------------------------------------------------------------------------
+// (Measured and rejected: the reciprocal on the FMA pipe -- integer-trick seed + three Newton steps, ONE SFU instruction per SiLU
+// instead of two -- is 6 % SLOWER on the whole PC pass, 20.6 vs 19.35 ms on the 296-group probe: the SiLU bursts are bound by issue
+// slots, 11 instructions against 5, not by the 16 SFU lanes.)
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // sin/cos of an fp32 argument of magnitude up to ~1e5: 2-term Cody-Waite reduction by 2*pi (exact products through FMA; the

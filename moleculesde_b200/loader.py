@@ -36,11 +36,13 @@ def pin_batch(batch):
 
 
 class DeviceLoader:
-    def __init__(self, host_batches: Iterable, device: torch.device, prepare: Optional[Callable] = None, depth: int = 2):
+    def __init__(self, host_batches: Iterable, device: torch.device, prepare: Optional[Callable] = None, depth: int = 2,
+                 switch_interval: Optional[float] = None):
         """`host_batches`: iterable of collated host batches (ideally pinned, see `pin_batch`).  `prepare(batch_on_device,
         max_nodes)`: optional callback run on the copy stream in the loader thread (e.g. `PretrainStep.prepare`).
         `depth`: batches in flight ahead of the consumer."""
         self.src, self.dev, self.prepare, self.depth = host_batches, torch.device(device), prepare, max(1, int(depth))
+        self.switch_interval = switch_interval   # CPython GIL switch interval while the loader thread runs (None: unchanged)
         self.cuda = self.dev.type == "cuda"
 
     def __len__(self):
@@ -94,11 +96,9 @@ class DeviceLoader:
     def __iter__(self) -> Iterator:
         q: "queue.Queue" = queue.Queue(maxsize=self.depth)
         stop = threading.Event()
-        # The consumer's eager step is ~10 ms of pure Python that never blocks; with CPython's default 5 ms switch interval the
-        # loader thread would get the GIL back only 5 ms after each of its host syncs (a handful per batch) and become the
-        # bottleneck.  A short interval hands the GIL over promptly; restored when the iteration ends.
         old_switch = sys.getswitchinterval()
-        sys.setswitchinterval(min(old_switch, 2e-4))
+        if self.switch_interval is not None:
+            sys.setswitchinterval(self.switch_interval)
         th = threading.Thread(target=self._worker, args=(q, stop), daemon=True, name="molsde-loader")
         th.start()
         retired = []      # (batch, event on the consumer stream): kept until the consumer's work on the batch has finished
@@ -131,4 +131,46 @@ class DeviceLoader:
                     pass
                 th.join(timeout=0.05)
             if self.cuda and (retired or prev is not None):
+                torch.cuda.current_stream(self.dev).synchronize()
+
+
+class InlineLoader(DeviceLoader):
+    """The same one-batch-ahead staging WITHOUT a second Python thread: the consumer thread itself copies batch k+1 and runs
+    `prepare` on the copy stream right after it received batch k -- i.e. after `__next__` returns the consumer queues step k, and
+    the staging of batch k+1 is issued at the START of the following `__next__` ... which would be too late to overlap, so the
+    staging of batch k+1 is issued BEFORE batch k is handed out: while the consumer issues step k (host-bound, ~10 ms of Python),
+    the copy stream already holds the kernels of batch k+1.  The few host syncs of the graph builders (output sizes) wait only for
+    the copy stream's short kernels.  No GIL hand-overs: with an eager step that never blocks, a loader THREAD only gets the GIL
+    at CPython's switch interval and its host syncs stretch to milliseconds (tools/e2e_loader_probe.py)."""
+
+    def __iter__(self) -> Iterator:
+        stream = torch.cuda.Stream(self.dev) if self.cuda else None
+        src = iter(self.src)
+
+        def stage():
+            try:
+                hb = next(src)
+            except StopIteration:
+                return None
+            if self.cuda:
+                with torch.cuda.stream(stream):
+                    return self._stage(hb, stream)
+            return self._stage(hb, None)
+
+        retired = []
+        nxt = stage()
+        try:
+            while nxt is not None:
+                b, ev = nxt
+                nxt = stage()          # batch k+1 is on the copy stream before the consumer starts issuing step k
+                if ev is not None:
+                    torch.cuda.current_stream(self.dev).wait_event(ev)
+                yield b
+                if self.cuda:          # the consumer queued its work on `b`: keep it referenced until that work is done
+                    e2 = torch.cuda.Event()
+                    e2.record(torch.cuda.current_stream(self.dev))
+                    retired.append((b, e2))
+                    retired = [(x, e) for x, e in retired if not e.query()]
+        finally:
+            if self.cuda and retired:
                 torch.cuda.current_stream(self.dev).synchronize()

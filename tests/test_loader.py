@@ -4,14 +4,15 @@ import pytest
 import torch
 
 from moleculesde_b200.data import Batch, synth_molecules
-from moleculesde_b200.loader import DeviceLoader, pin_batch
+from moleculesde_b200.loader import DeviceLoader, InlineLoader, pin_batch
 
 
 def _host_batches(n, size=4):
     return [Batch.from_data_list(synth_molecules(size, 40 + s, "pcqm")) for s in range(n)]
 
 
-def test_loader_order_prepare_and_max_nodes():
+@pytest.mark.parametrize("Loader", [DeviceLoader, InlineLoader])
+def test_loader_order_prepare_and_max_nodes(Loader):
     hbs = _host_batches(6)
     calls = []
 
@@ -19,12 +20,26 @@ def test_loader_order_prepare_and_max_nodes():
         calls.append(max_nodes)
         b.tag = len(calls)
 
-    got = list(DeviceLoader(hbs, torch.device("cpu"), prepare, depth=2))
+    got = list(Loader(hbs, torch.device("cpu"), prepare, depth=2))
     assert len(got) == 6 and [b.tag for b in got] == [1, 2, 3, 4, 5, 6], "every batch once, in order"
     for b, hb in zip(got, hbs):
         assert torch.equal(b.x, hb.x) and torch.equal(b.edge_index, hb.edge_index) and b.num_graphs == hb.num_graphs
     assert calls == [int((hb.ptr[1:] - hb.ptr[:-1]).max()) for hb in hbs], "largest molecule from the host offsets"
-    assert len(DeviceLoader(hbs, torch.device("cpu"))) == 6
+    assert len(Loader(hbs, torch.device("cpu"))) == 6
+    assert [b.num_graphs for b in Loader(hbs[:1], torch.device("cpu"), None, switch_interval=1e-3)] == [hbs[0].num_graphs]
+
+
+def test_inline_loader_propagates_errors():
+    hbs = _host_batches(4)
+    seen = []
+
+    def bad(b, max_nodes):
+        if len(seen) == 1:
+            raise ValueError("boom")
+
+    with pytest.raises(ValueError, match="boom"):
+        for b in InlineLoader(hbs, torch.device("cpu"), bad):
+            seen.append(b)
 
 
 def test_loader_propagates_errors_and_stops_early():
@@ -49,7 +64,8 @@ def test_loader_propagates_errors_and_stops_early():
 
 
 @pytest.mark.gpu
-def test_loader_batches_give_identical_gradients():
+@pytest.mark.parametrize("Loader", [DeviceLoader, InlineLoader])
+def test_loader_batches_give_identical_gradients(Loader):
     import bench
     from moleculesde_b200 import graph as G
     from moleculesde_b200.pretrain import PretrainStep
@@ -79,7 +95,7 @@ def test_loader_batches_give_identical_gradients():
         want.append((ps.store.grad.clone(), float(out["loss_2d3d"]), float(out["loss_adj"])))
     torch.cuda.synchronize()
     n = 0
-    for b, d, w in zip(DeviceLoader([pin_batch(hb) for hb in hbs], dev, prepare=ps.prepare, depth=2), draws, want):
+    for b, d, w in zip(Loader([pin_batch(hb) for hb in hbs], dev, prepare=ps.prepare, depth=2), draws, want):
         assert b.x.is_cuda and getattr(b, "extended_edge_index", None) is not None and "schnet" in b._molsde_train_cache
         assert b._molsde_dense_dims[1] == int((hbs[n].ptr[1:] - hbs[n].ptr[:-1]).max())
         out = ps.forward_backward(b, d)
