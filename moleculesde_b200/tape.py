@@ -86,7 +86,11 @@ class Tape:
         self.launches = 0
         self._main = torch.cuda.current_stream(device) if device.type == "cuda" else None
         self._s = self._main.cuda_stream if self._main is not None else 0  # one stream per tape (+ the optional wstream)
-        self._w = wstream if (wstream is not None and self._main is not None and wstream != self._main) else None
+        # `wstream` may be a list of side streams: consecutive leaves rotate over them (they are independent of each other too)
+        ws = list(wstream) if isinstance(wstream, (list, tuple)) else ([wstream] if wstream is not None else [])
+        self._ws = [w for w in ws if self._main is not None and w != self._main]
+        self._wi = 0
+        self._w = self._ws[0] if self._ws else None
         self._hold: list = []
         self._w_used = False
 
@@ -139,18 +143,22 @@ class Tape:
             yield
             return
         self._hold.extend(t for t in operands if t is not None)
-        self._w.wait_stream(self._main)
-        prev, self._s, self._w_used = self._s, self._w.cuda_stream, True
+        w = self._ws[self._wi % len(self._ws)]
+        self._wi += 1
+        w.wait_stream(self._main)
+        prev, self._s, self._w_used = self._s, w.cuda_stream, True
         try:
-            with torch.cuda.stream(self._w):   # workspaces allocated inside come from the side stream's pool
+            with torch.cuda.stream(w):   # workspaces allocated inside come from the side stream's pool
                 yield
         finally:
             self._s = prev
 
     def join(self) -> None:
         if self._w_used:
-            self._main.wait_stream(self._w)
+            for w in self._ws[:max(1, min(self._wi, len(self._ws)))]:
+                self._main.wait_stream(w)
             self._w_used = False
+            self._wi = 0
         self._hold.clear()
 
     def backward(self) -> None:
