@@ -17,7 +17,7 @@ from torch import nn
 from . import _abi
 from ._abi import check, lib, ptr, require_device, stream_ptr
 from .graph import segment_ptr
-from .ops import linear
+from .ops import gather_rows, linear
 from .sde_2d_to_3d import MultiLayerPerceptron
 from .sde_dense import VESDE, VPSDE, subVPSDE
 
@@ -345,6 +345,7 @@ class NodeScoreNetwork_dense(nn.Module):
     def forward(self, x, adj, flags, scale: Optional[torch.Tensor] = None):
         require_device(adj)
         adj = adj.contiguous().float()
+        flags_arg = flags
         flags = flags.contiguous().float()
         B, Nm = adj.size(0), adj.size(1)
         xs = torch.empty(B * Nm, self.fdim, dtype=torch.float32, device=adj.device)  # cat(x_list), built in place
@@ -355,11 +356,48 @@ class NodeScoreNetwork_dense(nn.Module):
             _dense_gcn(adj, 1, xw, lyr.bias.detach().float().contiguous(), self.nhid, xs, off, "tanh")  # tanh(GCN), :121-122
             cur, off = xs[:, off:off + self.nhid], off + self.nhid
         fl = self.final.layers
+        comp = self._valid_rows(flags_arg, flags)
+        if comp is not None:
+            # The final MLP (fdim -> 2 fdim -> 2 fdim -> nout: the largest GEMMs of a score evaluation) is row-wise and its output
+            # is masked: run it on the VALID atom rows only (a padded batch of 256 x 64 holds ~10.8k atoms in 16.4k rows) and put
+            # the rows back with the padding rows reading a zero row.  Same kernels, same per-row arithmetic: bit-identical.
+            idx, inv, gidx, N = comp
+            h = linear(gather_rows(xs, idx), fl[0].weight, fl[0].bias, act="silu")
+            h = linear(h, fl[1].weight, fl[1].bias, act="silu")
+            outc = torch.empty(N + 1, self.nout, dtype=torch.float32, device=adj.device)
+            outc[N:].zero_()
+            linear(h, fl[2].weight, fl[2].bias, rowscale=None if scale is None else scale.index_select(0, gidx), out=outc[:N])
+            return gather_rows(outc, inv).view(B, Nm, self.nout)
         h = linear(xs, fl[0].weight, fl[0].bias, act="silu")
         h = linear(h, fl[1].weight, fl[1].bias, act="silu")
         rs = flags.reshape(-1) if scale is None else (flags * scale[:, None]).reshape(-1)
         out = linear(h, fl[2].weight, fl[2].bias, rowscale=rs)                          # mask_x (and -1/std)
         return out.view(B, Nm, self.nout)
+
+    def _valid_rows(self, key_tensor, flags):
+        """Row indices of the valid atoms of a padded batch, cached on the identity (+ version) of the caller's `flags` tensor
+        (static along a sampling trajectory; the cache holds the tensor, so its address cannot be reused).  None when the padding
+        is small, the batch is small, or the index would have to be built (host sync) while a CUDA graph is being captured."""
+        if os.environ.get("MOLSDE_DENSE_NO_COMPACT") == "1":
+            return None
+        rows = flags.numel()
+        if rows < 4096:
+            return None
+        c = self.__dict__.get("_rows_cache")
+        if c is None or c[0] is not key_tensor or c[1] != key_tensor._version:
+            if torch.cuda.is_current_stream_capturing():
+                return None
+            valid = flags.reshape(-1) > 0
+            if not bool(((flags == 0) | (flags == 1)).all()):     # the compact path drops the mask multiply: exact only for 0/1 flags
+                c = (key_tensor, key_tensor._version, None)
+            else:
+                idx = valid.nonzero().reshape(-1)
+                N = int(idx.numel())
+                inv = torch.full((rows,), N, dtype=torch.int64, device=flags.device)
+                inv[idx] = torch.arange(N, device=flags.device)
+                c = (key_tensor, key_tensor._version, (idx, inv, idx // flags.size(1), N) if 0 < N <= 0.8 * rows else None)
+            self.__dict__["_rows_cache"] = c
+        return c[2]
 
 
 class SDEModel3Dto2D_node_adj_dense(nn.Module):

@@ -172,3 +172,30 @@ def test_dense_pc_sampler_20_steps_teacher_forced_vs_oracle(golden):
             ref = O.score_3d2d(sd, sde, which, emb_o, adjs.cpu(), flags_o, t)
             got = model.get_score_fn(s, net, train=False)(emb_d, adjs, flags, t.to(dev))
             assert_parity(got, ref, f"{which} score after {n} PC steps")
+
+
+def test_node_network_valid_row_compaction_is_bit_identical(monkeypatch):
+    """NodeScoreNetwork_dense: the final MLP evaluated on the valid atom rows only (sde_3d_to_2d._valid_rows) gives the same bits
+    as the padded evaluation (`invariant_scorenetwork_dense.py:118-131`), including an isolated (flag 0) atom in the middle of a graph."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from moleculesde_b200.sde_3d_to_2d import NodeScoreNetwork_dense
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    B, Nm, F = 128, 48, 40
+    net = NodeScoreNetwork_dense(nfeat=F, depth=2, nhid=16, nout=23).to(dev).eval()
+    n = torch.randint(5, 30, (B,))
+    flags = (torch.arange(Nm)[None, :] < n[:, None]).float()
+    flags[3, 2] = 0.0                                           # node_flags can leave holes (an atom without bonds)
+    flags = flags.to(dev)
+    adj = torch.rand(B, Nm, Nm, device=dev)
+    adj = (adj + adj.transpose(1, 2)) * flags[:, :, None] * flags[:, None, :]
+    x = torch.randn(B, Nm, F, device=dev) * flags[:, :, None]
+    scale = -1.0 / (0.5 + torch.rand(B, device=dev))
+    got = net(x, adj, flags, scale)
+    assert net.__dict__["_rows_cache"][2] is not None, "compaction active"
+    got2 = net(x, adj, flags, scale)                            # cache hit
+    monkeypatch.setenv("MOLSDE_DENSE_NO_COMPACT", "1")
+    want = net(x, adj, flags, scale)
+    assert torch.equal(got, want) and torch.equal(got2, want)
+    assert float(want.abs().max()) > 0 and float((want * (1 - flags[:, :, None])).abs().max()) == 0
