@@ -358,7 +358,7 @@ int molsde_edge_mul_reduce_ld(const float* A, const int32_t* ia, const float* W,
 int molsde_edge_mul_gather_ld(const float* A, const int32_t* ia, const float* B, const int32_t* ib, int64_t E, int32_t cols, float* out,
                               int64_t ldo, void* stream);
 /* Whole-chain kernels of the narrow 3-layer MLPs applied to the B*Nm^2 atom pairs in TRAINING (EdgeNetwork_dense.mlp,
- * edge_network_dense.py:120-123; EdgeScoreNetwork_dense.final, invariant_scorenetwork_dense.py:60-62): y = W3 act(W2 act(W1 x + b1)
+ * edge_network_dense.py:120-123): y = W3 act(W2 act(W1 x + b1)
  * + b2) + b3, thread = row, hidden vectors in registers, fp32 FFMA.  fwd keeps the pre-activations p1, p2 [rows, h]; bwd runs the
  * whole input-gradient chain and leaves a1 = act(p1), a2 = act(p2), d1, d2 [rows, h] (the operands of the three weight-gradient
  * GEMMs) and dx [rows, d0] (row stride lddx; NULL = not wanted).  x row stride ldx; y, dy dense [rows, d3].
