@@ -89,7 +89,9 @@ def _dp_worker(rank, world, port, out):
     assert torch.all(store.grad_view("a", "weight") == float(rank + 1)), "the other bucket is untouched"
     store.all_reduce(("a",))
     assert torch.equal(store.grad, whole)
-    res = (scale, store.grad_view("a", "weight").clone(), store.grad_view("b", "1.bias").clone(), store.numel)
+    # plain Python values: a tensor sent through an mp.Queue is fetched from the PRODUCER process when the consumer unpickles it,
+    # which races with this worker's exit (ConnectionRefusedError / EOFError in the parent)
+    res = (scale, store.grad_view("a", "weight").flatten().tolist(), store.grad_view("b", "1.bias").flatten().tolist(), store.numel)
     if rank == 0:
         out.put(res)
     dist.barrier()
@@ -108,5 +110,5 @@ def test_two_rank_flat_gradient_allreduce():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert scale == 0.5
-    assert torch.all(gw == 3.0) and torch.all(gb == 30.0)   # sum over ranks; Adam multiplies by 1/world
+    assert len(gw) == 15 and all(v == 3.0 for v in gw) and len(gb) == 2 and all(v == 30.0 for v in gb)   # sum over ranks; Adam multiplies by 1/world
     assert numel % 4 == 0 and numel >= 15 + 3 + 6 + 2 + 2 + 2

@@ -45,14 +45,18 @@ def test_inline_loader_propagates_errors():
 def test_loader_propagates_errors_and_stops_early():
     hbs = _host_batches(5)
 
-    def bad(b, max_nodes):
-        if b.num_graphs and len(seen) == 2:
+    calls = []
+
+    def bad(b, max_nodes):    # the third batch fails in the loader thread (a count of calls: independent of the consumer's pace)
+        calls.append(1)
+        if len(calls) == 3:
             raise ValueError("boom")
 
     seen = []
     with pytest.raises(ValueError, match="boom"):
         for b in DeviceLoader(hbs, torch.device("cpu"), bad, depth=1):
             seen.append(b)
+    assert len(seen) == 2, "the batches staged before the failure are delivered, then the error surfaces in the consumer"
     import threading
     before = threading.active_count()
     for i, b in enumerate(DeviceLoader(hbs, torch.device("cpu"), None, depth=1)):
