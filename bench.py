@@ -369,6 +369,11 @@ def run_b200(args):
     # ---------------- end to end (`e2e`): host buffers in, host result out ----------------
     out_h = torch.empty(n_atoms, 3).pin_memory()
     e2e_steps = max(1, min(args.steps, 2))
+    # one untimed end-to-end pass: its fresh input / tile / scratch buffers (~0.6 GB) come from cudaMalloc while the device-resident
+    # copies above are still alive; the timed passes then reuse the allocator's cached blocks, as any steady-state caller does
+    d2, rep2, pos2 = stage_inputs()
+    out_h.copy_(hot_path(d2, rep2, pos2, 1999), non_blocking=True)
+    del d2, rep2, pos2
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
