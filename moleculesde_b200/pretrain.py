@@ -499,9 +499,9 @@ def tape_schnet(tp: Tape, model, P: Dict[str, Var], z: torch.Tensor, pos: torch.
     # layers = one grouped GEMM) when the parameters are adjacent in the flat buffer (`_layout_key`); their backward runs once,
     # after every interaction deposited d W_i in its column block.  Same dot products as the per-interaction form.
     G = model.num_interactions
-    F_, ng = P["interactions.0.mlp.2.weight"].data.shape[0], ea.shape[1]
     Wf_all = None
     if not need_pos and G > 0 and es.E > 0:
+        F_, ng = P["interactions.0.mlp.2.weight"].data.shape[0], ea.shape[1]
         names = lambda k: [f"interactions.{i}.mlp.{k}" for i in range(G)]   # noqa: E731
         W0s, b0s = _stacked(P, names("0.weight"), (G * F_, ng)), _stacked(P, names("0.bias"), (G * F_,))
         W2s, b2s = _stacked(P, names("2.weight"), (G, F_, F_)), _stacked(P, names("2.bias"), (G * F_,))

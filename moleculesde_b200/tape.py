@@ -634,6 +634,10 @@ class Tape:
         if out.needs:
             def bwd():
                 if out.grad is None:
+                    if wcol0 is not None and W.needs:   # an unused output: its column block of the stack's gradient is zero, not garbage
+                        if W.grad is None:
+                            W.grad = self.empty(W.data.shape)
+                        W.grad[:, wcol0:wcol0 + cols].zero_()
                     return
                 if W.needs:
                     if wcol0 is None:
