@@ -103,6 +103,50 @@ def test_all_module_state_dicts_match_reference_manifest(golden):
     assert b[0] == a[0] + a[1]
 
 
+def test_flat_layout_stacks_of_the_fused_tape_paths():
+    """`pretrain._layout_key` places (a) q | k | v | skip of every GATLayer and (b) the filter-network layers of all SchNet
+    interactions side by side in the flat buffer, so that `_stacked` returns zero-copy [128, 32] / [G*128, 51] / [G, 128, 128]
+    views (data AND gradient) -- the precondition of the one-GEMM q|k|v|skip projection and of the hoisted SchNet filter stack
+    (`pretrain._gat_layer`, `tape_schnet`); state_dict values are untouched by the re-ordering."""
+    from moleculesde_b200 import sde_2d_to_3d as M
+    from moleculesde_b200.pretrain import ParamStore, _QKVS, _stacked
+    from moleculesde_b200.schnet import SchNet
+    torch.manual_seed(3)
+    m23 = M.SDEModel2Dto3D_02(300, 32, None, 0.2, 1.0, 1000, "VE", use_extend_graph=True)
+    sch = SchNet(hidden_channels=300, num_filters=128, num_interactions=6, num_gaussians=51, cutoff=10, readout="mean", node_class=119)
+    before = {n: {k: v.clone() for k, v in m.state_dict().items()} for n, m in (("sde2d3d", m23), ("schnet", sch))}
+    store = ParamStore({"schnet": sch, "sde2d3d": m23}, torch.device("cpu"))
+    for n, m in (("sde2d3d", m23), ("schnet", sch)):
+        for k, v in m.state_dict().items():
+            assert torch.equal(v, before[n][k]), (n, k)
+    P = store.vars("sde2d3d")
+    for m in range(2):
+        for c in range(2):
+            pf = f"score_network.gnn_layers.{m}.{c}."
+            W = _stacked(P, [pf + f"MHA.{n}.weight" for n in _QKVS], (128, 32))
+            b = _stacked(P, [pf + f"MHA.{n}.bias" for n in _QKVS], (128,))
+            assert W is not None and b is not None, pf
+            for j, n in enumerate(_QKVS):
+                lin = getattr(m23.score_network.gnn_layers[m][c].MHA, n)
+                assert torch.equal(W.data[32 * j:32 * j + 32], lin.weight.data) and torch.equal(b.data[32 * j:32 * j + 32], lin.bias.data)
+                assert W.data[32 * j:].data_ptr() == lin.weight.data_ptr() and W.grad[32 * j:].data_ptr() == P[pf + f"MHA.{n}.weight"].grad.data_ptr()
+    assert _stacked(P, [f"score_network.gnn_layers.0.0.MHA.{n}.weight" for n in _QKVS], (128, 32)) is \
+        _stacked(P, [f"score_network.gnn_layers.0.0.MHA.{n}.weight" for n in _QKVS], (128, 32)), "cached per parameter dict"
+    S = store.vars("schnet")
+    G = 6
+    W0 = _stacked(S, [f"interactions.{i}.mlp.0.weight" for i in range(G)], (G * 128, 51))
+    b0 = _stacked(S, [f"interactions.{i}.mlp.0.bias" for i in range(G)], (G * 128,))
+    W2 = _stacked(S, [f"interactions.{i}.mlp.2.weight" for i in range(G)], (G, 128, 128))
+    b2 = _stacked(S, [f"interactions.{i}.mlp.2.bias" for i in range(G)], (G * 128,))
+    assert None not in (W0, b0, W2, b2)
+    for i in range(G):
+        mlp = sch.interactions[i].mlp
+        assert torch.equal(W0.data[128 * i:128 * i + 128], mlp[0].weight.data) and torch.equal(W2.data[i], mlp[2].weight.data)
+        assert torch.equal(b0.data[128 * i:128 * i + 128], mlp[0].bias.data) and torch.equal(b2.data[128 * i:128 * i + 128], mlp[2].bias.data)
+    # parameters that are NOT adjacent give None (the tapes then keep the per-layer path)
+    assert _stacked(S, ["interactions.0.mlp.0.weight", "interactions.0.mlp.2.weight"], (256, 51)) is None
+
+
 def test_packed_blob_roundtrip(golden):
     from conftest import sd_from_manifest
     from moleculesde_b200 import sde_2d_to_3d as M
