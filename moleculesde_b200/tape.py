@@ -19,7 +19,7 @@ from ._abi import check, lib, ptr, require_device, stream_ptr
 ACT = {"none": 0, "relu": 1, "silu": 2, "ssp": 3, "tanh": 4, "elu": 5}
 import os as _os
 # M*N*K below which a GEMM stays on the FFMA kernels (tensor-core tiles would be mostly padding); MOLSDE_NO_TC=1 disables
-TC_MIN_WORK = (1 << 62) if _os.environ.get("MOLSDE_NO_TC") == "1" else (1 << 20)
+TC_MIN_WORK = (1 << 62) if _os.environ.get("MOLSDE_NO_TC") == "1" else int(_os.environ.get("MOLSDE_TC_MIN_WORK", 1 << 20))
 FUSED_DB = _os.environ.get("MOLSDE_NO_FUSED_DB") != "1"   # bias gradient through the all-ones row of the dW GEMM
 
 
