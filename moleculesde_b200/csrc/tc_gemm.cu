@@ -626,8 +626,17 @@ static int tc_bn(int64_t N) {
 static int tc_splits(int64_t M, int64_t N, int64_t K, int batch) {
     const int bn = tc_bn(N);
     const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn) * batch;
-    int64_t s = (2 * kNumSMs + tiles - 1) / tiles;   // ~2 waves of CTAs
-    const int64_t maxs = (K + 4 * TC_BK - 1) / (4 * TC_BK);  // >= 4 K blocks per split
+    // Split-K policy, tuned on the whole pretraining step (graph replay, batch 256), where these GEMMs never run alone -- two or three
+    // streams keep the SMs busy, so a GEMM does not have to fill the GPU by itself and every split costs partial-tile writes plus a
+    // reduce launch:  no split once the output has >= 100 tiles (2/3 of a wave);  otherwise ~ONE wave of CTAs (was two);  >= 8 K
+    // blocks per split (was 4).  Step 8.81 -> 8.20 ms; 0.5 waves or a 60-tile cut-off are slower again (8.5-8.6 ms).
+    // MOLSDE_TC_NOSPLIT_TILES / MOLSDE_TC_SPLIT_WAVES / MOLSDE_TC_SPLIT_MIN_KB re-open the A/B.
+    static const int64_t no_split_tiles = getenv("MOLSDE_TC_NOSPLIT_TILES") ? atoll(getenv("MOLSDE_TC_NOSPLIT_TILES")) : 100;
+    if (tiles >= no_split_tiles) return 1;
+    static const double waves = getenv("MOLSDE_TC_SPLIT_WAVES") ? atof(getenv("MOLSDE_TC_SPLIT_WAVES")) : 1.0;
+    int64_t s = (static_cast<int64_t>(waves * kNumSMs) + tiles - 1) / tiles;
+    static const int64_t min_kb = getenv("MOLSDE_TC_SPLIT_MIN_KB") ? atoll(getenv("MOLSDE_TC_SPLIT_MIN_KB")) : 8;
+    const int64_t maxs = (K + min_kb * TC_BK - 1) / (min_kb * TC_BK);  // >= min_kb K blocks per split
     if (s > maxs) s = maxs;
     if (s > 512) s = 512;
     return s < 1 ? 1 : static_cast<int>(s);
