@@ -628,12 +628,13 @@ static int tc_splits(int64_t M, int64_t N, int64_t K, int batch) {
     const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn) * batch;
     // Split-K policy, tuned on the whole pretraining step (graph replay, batch 256), where these GEMMs never run alone -- two or three
     // streams keep the SMs busy, so a GEMM does not have to fill the GPU by itself and every split costs partial-tile writes plus a
-    // reduce launch:  no split once the output has >= 100 tiles (2/3 of a wave);  otherwise ~ONE wave of CTAs (was two);  >= 8 K
-    // blocks per split (was 4).  Step 8.81 -> 8.20 ms; 0.5 waves or a 60-tile cut-off are slower again (8.5-8.6 ms).
+    // reduce launch:  no split once the output has >= 100 tiles (2/3 of a wave);  otherwise ~0.8 waves of CTAs (was two);  >= 8 K
+    // blocks per split (was 4).  Step 8.81 -> 8.20 ms (one wave) -> 7.94 ms (0.8 waves, with two side streams for the weight-gradient
+    // leaves); the plateau is flat: 0.5-0.8 waves and cut-offs of 60-100 tiles all land within 7.90-8.02 ms.
     // MOLSDE_TC_NOSPLIT_TILES / MOLSDE_TC_SPLIT_WAVES / MOLSDE_TC_SPLIT_MIN_KB re-open the A/B.
     static const int64_t no_split_tiles = getenv("MOLSDE_TC_NOSPLIT_TILES") ? atoll(getenv("MOLSDE_TC_NOSPLIT_TILES")) : 100;
     if (tiles >= no_split_tiles) return 1;
-    static const double waves = getenv("MOLSDE_TC_SPLIT_WAVES") ? atof(getenv("MOLSDE_TC_SPLIT_WAVES")) : 1.0;
+    static const double waves = getenv("MOLSDE_TC_SPLIT_WAVES") ? atof(getenv("MOLSDE_TC_SPLIT_WAVES")) : 0.8;
     int64_t s = (static_cast<int64_t>(waves * kNumSMs) + tiles - 1) / tiles;
     static const int64_t min_kb = getenv("MOLSDE_TC_SPLIT_MIN_KB") ? atoll(getenv("MOLSDE_TC_SPLIT_MIN_KB")) : 8;
     const int64_t maxs = (K + min_kb * TC_BK - 1) / (min_kb * TC_BK);  // >= min_kb K blocks per split
