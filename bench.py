@@ -812,6 +812,9 @@ def bench_dense_sampler(args, dev, rank, world):
     h3d = h3d_h.to(dev)
     for _ in range(max(args.warmup, 3)):
         run(b, h3d, 8)       # warm-up: weight packs, capture path, allocator pools
+    run(b, h3d, S)           # one untimed full-length pass: the timed one then sees the allocator / graph-pool state of a steady caller
+    #                          (a full bench run once measured 4.5 ms per step here against 3.5 in every other run and in the e2e pass
+    #                          that follows: a one-off stall right after the pretraining leg released its graphs)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
