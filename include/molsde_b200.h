@@ -331,6 +331,9 @@ int molsde_colsum(const float* X, int64_t M, int32_t N, int64_t ldx, float* out,
 /* y = act(x);  dx = dy * act'(x) with x the pre-activation (act codes of molsde_linear) */
 int molsde_act_fwd(const float* x, int64_t n, int32_t act, float* y, void* stream);
 int molsde_act_bwd(const float* x, const float* dy, int64_t n, int32_t act, float* dx, void* stream);
+/* the same from the OUTPUT y = f(pre) for relu (1), shifted softplus (3), tanh (4), elu (5): dx = dy * f'(pre(y)); a linear layer
+ * whose activation is one of these applies it in the GEMM epilogue and keeps one tensor (others: MOLSDE_ERR_UNSUPPORTED) */
+int molsde_act_bwd_y(const float* y, const float* dy, int64_t n, int32_t act, float* dx, void* stream);
 /* op 0: out = a + alpha*b (b NULL: alpha*a);  op 1: out = a*b (+c);  op 2: out[r,:] = a[r,:] * alpha * b[r];  op 3: out[r,c] = a[r,c] + b[c]  (cols per row);
  * op 4: out = a * (1 + b[0]) (+c).
  * out may alias a. */

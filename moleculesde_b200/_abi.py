@@ -35,7 +35,7 @@ EXPORTS = [
     "molsde_linear",
     "molsde_edge2d_emb_eval", "molsde_sde2d3d_score", "molsde_sde2d3d_scratch_floats", "molsde_tile_floats",
     "molsde_sde2d3d_pc_sample", "molsde_edge2d_bn_train", "molsde_sde2d3d_forward_net", "molsde_dsm_pos_loss", "molsde_perturb_rows",
-    "molsde_gemm_ws_floats", "molsde_gemm", "molsde_colsum_ws_floats", "molsde_colsum", "molsde_act_fwd", "molsde_act_bwd",
+    "molsde_gemm_ws_floats", "molsde_gemm", "molsde_colsum_ws_floats", "molsde_colsum", "molsde_act_fwd", "molsde_act_bwd", "molsde_act_bwd_y",
     "molsde_ew", "molsde_gather_pair", "molsde_seg_gather_sum", "molsde_bucket_count", "molsde_bucket_fill",
     "molsde_expand_rowptr", "molsde_layernorm_fwd", "molsde_layernorm_bwd", "molsde_bn_ws_doubles", "molsde_bn_train_fwd",
     "molsde_bn_train_bwd", "molsde_adam_step", "molsde_sde2d3d_edge_geom", "molsde_tconv_fwd", "molsde_tconv_bwd",
@@ -170,6 +170,7 @@ def lib() -> ctypes.CDLL:
     L.molsde_colsum.argtypes = [P, c_int64, c_int32, c_int64, P, c_int32, P, c_int64, P]
     L.molsde_act_fwd.argtypes = [P, c_int64, c_int32, P, P]
     L.molsde_act_bwd.argtypes = [P, P, c_int64, c_int32, P, P]
+    L.molsde_act_bwd_y.argtypes = [P, P, c_int64, c_int32, P, P]
     L.molsde_ew.argtypes = [c_int32, P, P, P, c_float, c_int64, c_int64, P, P]
     L.molsde_gather_pair.argtypes = [P, P, P, P, c_int64, c_int32, P, P]
     L.molsde_seg_gather_sum.argtypes = [P, P, P, c_int64, c_int32, P, c_int32, c_int32, P, P]

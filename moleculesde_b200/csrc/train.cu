@@ -151,6 +151,22 @@ __global__ void act_fwd_kernel(const float* __restrict__ x, int64_t n, int act, 
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (i < n) y[i] = act_f(x[i], act);
 }
+// f'(pre) from the OUTPUT y = f(pre), for the activations where that is a closed form: relu (y > 0), shifted softplus
+// (sigmoid(pre) = 1 - exp(-(y + ln 2))), tanh (1 - y^2), elu (y > 0 ? 1 : y + 1).  Lets a linear layer apply the activation in its
+// GEMM epilogue and keep ONE tensor instead of pre-activation + output (SiLU has no such form and keeps its pre-activation).
+__device__ __forceinline__ float act_df_from_y(float y, int act) {
+    switch (act) {
+        case 1: return y > 0.0f ? 1.0f : 0.0f;
+        case 3: return 1.0f - expf(-(y + 0.69314718246459961f));
+        case 4: return 1.0f - y * y;
+        case 5: return y > 0.0f ? 1.0f : y + 1.0f;
+        default: return 1.0f;
+    }
+}
+__global__ void act_bwd_y_kernel(const float* __restrict__ y, const float* __restrict__ dy, int64_t n, int act, float* __restrict__ dx) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) dx[i] = dy[i] * act_df_from_y(y[i], act);
+}
 __global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t n, int act, float* __restrict__ dx) {
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (i < n) dx[i] = dy[i] * act_df(x[i], act);
@@ -709,6 +725,13 @@ int molsde_act_bwd(const float* x, const float* dy, int64_t n, int32_t act, floa
     if (n == 0) return MOLSDE_OK;
     act_bwd_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(x, dy, n, act, dx);
     return check_launch("act_bwd");
+}
+int molsde_act_bwd_y(const float* y, const float* dy, int64_t n, int32_t act, float* dx, void* stream) {
+    if (!y || !dy || !dx || n < 0) return MOLSDE_ERR_INVALID;
+    if (act != 1 && act != 3 && act != 4 && act != 5) return MOLSDE_ERR_UNSUPPORTED;
+    if (n == 0) return MOLSDE_OK;
+    act_bwd_y_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(y, dy, n, act, dx);
+    return check_launch("act_bwd_y");
 }
 int molsde_act_bwd2(const float* x, const float* a, const float* b, int64_t n, int32_t act, int32_t accumulate, float* out, void* stream) {
     if (!x || !a || !b || !out || n < 0) return MOLSDE_ERR_INVALID;

@@ -21,6 +21,8 @@ import os as _os
 # M*N*K below which a GEMM stays on the FFMA kernels (tensor-core tiles would be mostly padding); MOLSDE_NO_TC=1 disables
 TC_MIN_WORK = (1 << 62) if _os.environ.get("MOLSDE_NO_TC") == "1" else int(_os.environ.get("MOLSDE_TC_MIN_WORK", 1 << 20))
 FUSED_DB = _os.environ.get("MOLSDE_NO_FUSED_DB") != "1"   # bias gradient through the all-ones row of the dW GEMM
+_FUSE_ACT = _os.environ.get("MOLSDE_NO_FUSED_ACT") != "1"  # A/B switch: activation in the GEMM epilogue, derivative from the output
+_ACT_FROM_Y = (1, 3, 4, 5)                                 # relu, ssp, tanh, elu (molsde_act_bwd_y)
 
 
 _CHECK = _abi.CHECK_ABI
@@ -207,14 +209,19 @@ class Tape:
             y = into.data[:, col0:col0 + Nout]
         else:
             y = self.empty(M, Nout)
-        pre = y if a == 0 else self.empty(M, Nout)
-        if M * Nout * K >= TC_MIN_WORK and not exact:  # tensor cores; W may be a column slice of a wider weight (ld = its row stride)
+        use_tc = M * Nout * K >= TC_MIN_WORK and not exact
+        # relu / ssp / tanh / elu: f'(pre) is a closed form of the OUTPUT, so the activation runs in the GEMM epilogue and only y is
+        # kept (one launch and one [M, Nout] tensor less; SiLU keeps its pre-activation)
+        act_in_gemm = a in _ACT_FROM_Y and _FUSE_ACT and (use_tc or W.data.is_contiguous())
+        pre = y if (a == 0 or act_in_gemm) else self.empty(M, Nout)
+        a_gemm = a if act_in_gemm else 0
+        if use_tc:  # tensor cores; W may be a column slice of a wider weight (ld = its row stride)
             self._call(self.L.molsde_tc_gemm, M, Nout, K, _p(x.data), _ld(x.data), 1, _p(W.data), _ld(W.data), 1,
-                       _p(b.data) if b is not None else None, 0, _p(rowscale), None, 0, _p(pre), _ld(pre), 0, None, 0, None, self.s,
+                       _p(b.data) if b is not None else None, a_gemm, _p(rowscale), None, 0, _p(pre), _ld(pre), 0, None, 0, None, self.s,
                        what="tc_gemm")
         elif W.data.is_contiguous():
             self._call(self.L.molsde_linear, _p(x.data), M, K, _ld(x.data), _p(W.data), _p(b.data) if b is not None else None, Nout,
-                       _p(pre), _ld(pre), 0, None, 0, _p(rowscale), self.s, what="linear")
+                       _p(pre), _ld(pre), a_gemm, None, 0, _p(rowscale), self.s, what="linear")
         else:
             assert rowscale is None and pre.is_contiguous()
             n = self.L.molsde_gemm_ws_floats(M, Nout, K)
@@ -223,7 +230,7 @@ class Tape:
                        _p(ws), n, self.s, what="gemm")
             if b is not None:
                 self.ew(3, pre, b.data, None, 1.0, pre, cols=Nout)
-        if a:
+        if a and not act_in_gemm:
             self._call(self.L.molsde_act_fwd, _p(pre), pre.numel(), a, _p(y), self.s, what="act_fwd")
         x_needs = full.needs if x_cols is not None else x.needs
         needs = x_needs or W.needs or (b is not None and b.needs)
@@ -240,7 +247,10 @@ class Tape:
                     dy = out.grad
                 if a:
                     dpre = self.empty(M, Nout)
-                    self._call(self.L.molsde_act_bwd, _p(pre), _p(dy), dpre.numel(), a, _p(dpre), self.s, what="act_bwd")
+                    if act_in_gemm:
+                        self._call(self.L.molsde_act_bwd_y, _p(y), _p(dy), dpre.numel(), a, _p(dpre), self.s, what="act_bwd_y")
+                    else:
+                        self._call(self.L.molsde_act_bwd, _p(pre), _p(dy), dpre.numel(), a, _p(dpre), self.s, what="act_bwd")
                 else:
                     dpre = dy
                 if rowscale is not None:
