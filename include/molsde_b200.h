@@ -355,11 +355,13 @@ int molsde_edge_mul_reduce(const float* A, const int32_t* ia, const float* W, co
 int molsde_edge_mul_gather(const float* A, const int32_t* ia, const float* B, const int32_t* ib, int64_t E, int32_t cols, float* out,
                            void* stream);
 /* the same two with a leading dimension: W is a column block of a wider [E, ldw] filter stack (all SchNet interactions' filters
- * side by side, schnet.py:185-195 evaluated once per batch), out a column block of the matching gradient stack [E, ldo] */
-int molsde_edge_mul_reduce_ld(const float* A, const int32_t* ia, const float* W, int64_t ldw, const int32_t* ptr, const int32_t* perm,
-                              int64_t segments, int32_t cols, float* out, void* stream);
-int molsde_edge_mul_gather_ld(const float* A, const int32_t* ia, const float* B, const int32_t* ib, int64_t E, int32_t cols, float* out,
-                              int64_t ldo, void* stream);
+ * side by side, schnet.py:185-195 evaluated once per batch), out a column block of the matching gradient stack [E, ldo];
+ * escale (optional, [E]): the cosine cutoff C(d_e) (schnet.py:187-188) applied on the fly -- reduce uses W[e,:] * escale[e], gather
+ * returns (A[ia[e],:] * B[ib[e],:]) * escale[e], i.e. the gradient with respect to the UNSCALED filter */
+int molsde_edge_mul_reduce_ld(const float* A, const int32_t* ia, const float* W, int64_t ldw, const float* escale, const int32_t* ptr,
+                              const int32_t* perm, int64_t segments, int32_t cols, float* out, void* stream);
+int molsde_edge_mul_gather_ld(const float* A, const int32_t* ia, const float* B, const int32_t* ib, const float* escale, int64_t E,
+                              int32_t cols, float* out, int64_t ldo, void* stream);
 /* Whole-chain kernels of the narrow 3-layer MLPs applied to the B*Nm^2 atom pairs in TRAINING (EdgeNetwork_dense.mlp,
  * edge_network_dense.py:120-123): y = W3 act(W2 act(W1 x + b1)
  * + b2) + b3, thread = row, hidden vectors in registers, fp32 FFMA.  fwd keeps the pre-activations p1, p2 [rows, h]; bwd runs the

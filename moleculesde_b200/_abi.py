@@ -177,8 +177,8 @@ def lib() -> ctypes.CDLL:
     L.molsde_embed_sum.argtypes = [P, P, c_int64, c_int32, c_int32, P, P]
     L.molsde_edge_mul_reduce.argtypes = [P, P, P, P, P, c_int64, c_int32, P, P]
     L.molsde_edge_mul_gather.argtypes = [P, P, P, P, c_int64, c_int32, P, P]
-    L.molsde_edge_mul_reduce_ld.argtypes = [P, P, P, c_int64, P, P, c_int64, c_int32, P, P]
-    L.molsde_edge_mul_gather_ld.argtypes = [P, P, P, P, c_int64, c_int32, P, c_int64, P]
+    L.molsde_edge_mul_reduce_ld.argtypes = [P, P, P, c_int64, P, P, P, c_int64, c_int32, P, P]
+    L.molsde_edge_mul_gather_ld.argtypes = [P, P, P, P, P, c_int64, c_int32, P, c_int64, P]
     L.molsde_mlp3_train_supported.argtypes = [c_int32, c_int32, c_int32, c_int32]
     L.molsde_mlp3_train_fwd.argtypes = [P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P]
     L.molsde_mlp3_train_bwd.argtypes = [P, P, P, c_int64, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, P, P, P, c_int64, P]

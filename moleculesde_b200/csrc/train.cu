@@ -276,9 +276,11 @@ __global__ void embed_sum_kernel(const float* __restrict__ T, const int32_t* __r
 
 // out[s,c] = sum_{p in [ptr[s],ptr[s+1])} A[ia[e],c] * W[e,c],  e = perm ? perm[p] : p
 //   CFConv message + aggregation (schnet.py:186-195): s = target, ia = source;   its dx: s = source (CSR by source), ia = target
+// `escale` (optional, per edge): the filter is W[e,:] * escale[e] -- the cosine cutoff C(d_e) of CFConv applied on the fly (rounded
+// once, exactly as the materialised product was), so the scaled filter stack is never written
 __global__ void edge_mul_reduce_kernel(const float* __restrict__ A, const int32_t* __restrict__ ia, const float* __restrict__ W, int64_t ldw,
-                                       const int32_t* __restrict__ ptr, const int32_t* __restrict__ perm, int64_t segments, int cols,
-                                       float* __restrict__ out) {
+                                       const float* __restrict__ escale, const int32_t* __restrict__ ptr, const int32_t* __restrict__ perm,
+                                       int64_t segments, int cols, float* __restrict__ out) {
     const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (idx >= segments * cols) return;
     const int64_t s = idx / cols;
@@ -286,18 +288,23 @@ __global__ void edge_mul_reduce_kernel(const float* __restrict__ A, const int32_
     float acc = 0.0f;
     for (int p = ptr[s]; p < ptr[s + 1]; ++p) {
         const int64_t e = perm ? perm[p] : p;
-        acc = fmaf(A[static_cast<int64_t>(ia[e]) * cols + c], W[e * ldw + c], acc);
+        float w = W[e * ldw + c];
+        if (escale) w = __fmul_rn(w, escale[e]);
+        acc = fmaf(A[static_cast<int64_t>(ia[e]) * cols + c], w, acc);
     }
     out[idx] = acc;
 }
 // out[e,c] = A[ia[e],c] * B[ib[e],c]      (dW of the CFConv message; `ldo` = row stride of out)
 __global__ void edge_mul_gather_kernel(const float* __restrict__ A, const int32_t* __restrict__ ia, const float* __restrict__ B,
-                                       const int32_t* __restrict__ ib, int64_t E, int cols, float* __restrict__ out, int64_t ldo) {
+                                       const int32_t* __restrict__ ib, const float* __restrict__ escale, int64_t E, int cols,
+                                       float* __restrict__ out, int64_t ldo) {
     const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (idx >= E * cols) return;
     const int64_t e = idx / cols;
     const int c = static_cast<int>(idx % cols);
-    out[e * ldo + c] = A[static_cast<int64_t>(ia[e]) * cols + c] * B[static_cast<int64_t>(ib[e]) * cols + c];
+    float v = __fmul_rn(A[static_cast<int64_t>(ia[e]) * cols + c], B[static_cast<int64_t>(ib[e]) * cols + c]);
+    if (escale) v = __fmul_rn(v, escale[e]);     // gradient w.r.t. the UNSCALED filter (two roundings, as product-then-row-scale had)
+    out[e * ldo + c] = v;
 }
 
 // out[0] (+)= alpha * <a, b>: DOT_CTAS fp64 partial sums into the caller's workspace, then a fixed-order finish
@@ -780,27 +787,27 @@ int molsde_embed_sum(const float* T, const int32_t* keys, int64_t rows, int32_t 
     embed_sum_kernel<<<blocks_for(rows * cols), 256, 0, as_stream(stream)>>>(T, keys, rows, F, cols, out);
     return check_launch("embed_sum");
 }
-int molsde_edge_mul_reduce_ld(const float* A, const int32_t* ia, const float* W, int64_t ldw, const int32_t* ptr, const int32_t* perm,
-                              int64_t segments, int32_t cols, float* out, void* stream) {
+int molsde_edge_mul_reduce_ld(const float* A, const int32_t* ia, const float* W, int64_t ldw, const float* escale, const int32_t* ptr,
+                              const int32_t* perm, int64_t segments, int32_t cols, float* out, void* stream) {
     if (!A || !ia || !W || !ptr || !out || segments < 0 || cols <= 0 || ldw < cols) return MOLSDE_ERR_INVALID;
     if (segments == 0) return MOLSDE_OK;
-    edge_mul_reduce_kernel<<<blocks_for(segments * cols), 256, 0, as_stream(stream)>>>(A, ia, W, ldw, ptr, perm, segments, cols, out);
+    edge_mul_reduce_kernel<<<blocks_for(segments * cols), 256, 0, as_stream(stream)>>>(A, ia, W, ldw, escale, ptr, perm, segments, cols, out);
     return check_launch("edge_mul_reduce");
 }
 int molsde_edge_mul_reduce(const float* A, const int32_t* ia, const float* W, const int32_t* ptr, const int32_t* perm, int64_t segments,
                            int32_t cols, float* out, void* stream) {
-    return molsde_edge_mul_reduce_ld(A, ia, W, cols, ptr, perm, segments, cols, out, stream);
+    return molsde_edge_mul_reduce_ld(A, ia, W, cols, nullptr, ptr, perm, segments, cols, out, stream);
 }
-int molsde_edge_mul_gather_ld(const float* A, const int32_t* ia, const float* B, const int32_t* ib, int64_t E, int32_t cols, float* out,
-                              int64_t ldo, void* stream) {
+int molsde_edge_mul_gather_ld(const float* A, const int32_t* ia, const float* B, const int32_t* ib, const float* escale, int64_t E,
+                              int32_t cols, float* out, int64_t ldo, void* stream) {
     if (!A || !ia || !B || !ib || !out || E < 0 || cols <= 0 || ldo < cols) return MOLSDE_ERR_INVALID;
     if (E == 0) return MOLSDE_OK;
-    edge_mul_gather_kernel<<<blocks_for(E * cols), 256, 0, as_stream(stream)>>>(A, ia, B, ib, E, cols, out, ldo);
+    edge_mul_gather_kernel<<<blocks_for(E * cols), 256, 0, as_stream(stream)>>>(A, ia, B, ib, escale, E, cols, out, ldo);
     return check_launch("edge_mul_gather");
 }
 int molsde_edge_mul_gather(const float* A, const int32_t* ia, const float* B, const int32_t* ib, int64_t E, int32_t cols, float* out,
                            void* stream) {
-    return molsde_edge_mul_gather_ld(A, ia, B, ib, E, cols, out, cols, stream);
+    return molsde_edge_mul_gather_ld(A, ia, B, ib, nullptr, E, cols, out, cols, stream);
 }
 int molsde_dot(const float* a, const float* b, int64_t n, float alpha, int32_t accumulate, float* out, double* ws, void* stream) {
     if (!a || !b || !out || !ws || n < 0) return MOLSDE_ERR_INVALID;  // ws: >= 128 doubles

@@ -509,12 +509,12 @@ def tape_schnet(tp: Tape, model, P: Dict[str, Var], z: torch.Tensor, pos: torch.
         W2s, b2s = _stacked(P, names("2.weight"), (G, F_, F_)), _stacked(P, names("2.bias"), (G * F_,))
         if None not in (W0s, b0s, W2s, b2s):
             f1 = tp.linear(ea_v, W0s, b0s, act="ssp")
-            Wf_all = tp.rowscale(tp.grouped_linear(f1, W2s, b2s, G), C)
+            Wf_all = tp.grouped_linear(f1, W2s, b2s, G)      # UNSCALED: the cosine cutoff C(d_e) is applied inside the CFConv kernels
     for i in range(G):
         pf = f"interactions.{i}."
         x = tp.linear(h, P[pf + "conv.lin1.weight"], None)
         if Wf_all is not None:
-            agg = tp.edge_mul_reduce(x, Wf_all, es.rowptr, es.src, es.tgt, wcol0=i * F_)
+            agg = tp.edge_mul_reduce(x, Wf_all, es.rowptr, es.src, es.tgt, wcol0=i * F_, escale=C)
         else:
             f1 = tp.linear(ea_v, P[pf + "mlp.0.weight"], P[pf + "mlp.0.bias"], act="ssp")
             f2 = tp.linear(f1, P[pf + "mlp.2.weight"], P[pf + "mlp.2.bias"])

@@ -629,17 +629,20 @@ class Tape:
             self.ops.append(bwd)
         return out
 
-    def edge_mul_reduce(self, x: Var, W: Var, rowptr: torch.Tensor, src: Index, tgt: Index, wcol0: Optional[int] = None) -> Var:
+    def edge_mul_reduce(self, x: Var, W: Var, rowptr: torch.Tensor, src: Index, tgt: Index, wcol0: Optional[int] = None,
+                        escale: Optional[torch.Tensor] = None) -> Var:
         """CFConv message + aggregation: out[i] = sum_{e->i} x[src_e] * W[e]  (schnet.py:186-195).
         `wcol0`: the filter is the column block [wcol0, wcol0+cols) of the wider stack W (all interactions' filters side by
-        side); its gradient is WRITTEN into the same block of W.grad (each block has exactly one consumer)."""
+        side); its gradient is WRITTEN into the same block of W.grad (each block has exactly one consumer).
+        `escale` [E] (no gradient): the filter is W[e] * escale[e] -- the cosine cutoff applied inside the kernels, so that neither
+        the scaled stack nor the gradient of the scaled stack is ever materialised (same roundings as the two-step form)."""
         N, cols = x.data.shape
         E = W.data.shape[0]
         y = self.empty(N, cols)
         Wd = W.data if wcol0 is None else W.data[:, wcol0:wcol0 + cols]
         ldw = _ld(Wd)
-        self._call(self.L.molsde_edge_mul_reduce_ld, _p(x.data), _p(src.idx), _p(Wd), ldw, _p(rowptr), None, N, cols, _p(y), self.s,
-                   what="edge_mul_reduce")
+        self._call(self.L.molsde_edge_mul_reduce_ld, _p(x.data), _p(src.idx), _p(Wd), ldw, _p(escale), _p(rowptr), None, N, cols, _p(y),
+                   self.s, what="edge_mul_reduce")
         out = Var(y, x.needs or W.needs)
         if out.needs:
             def bwd():
@@ -652,19 +655,19 @@ class Tape:
                 if W.needs:
                     if wcol0 is None:
                         dW = self.empty(E, cols)
-                        self._call(self.L.molsde_edge_mul_gather_ld, _p(out.grad), _p(tgt.idx), _p(x.data), _p(src.idx), E, cols, _p(dW),
-                                   cols, self.s, what="edge_mul_gather")
+                        self._call(self.L.molsde_edge_mul_gather_ld, _p(out.grad), _p(tgt.idx), _p(x.data), _p(src.idx), _p(escale), E, cols,
+                                   _p(dW), cols, self.s, what="edge_mul_gather")
                         self.accum(W, dW)
                     else:
                         if W.grad is None:
                             W.grad = self.empty(W.data.shape)   # every column block is written by its interaction's backward
                         dW = W.grad[:, wcol0:wcol0 + cols]
-                        self._call(self.L.molsde_edge_mul_gather_ld, _p(out.grad), _p(tgt.idx), _p(x.data), _p(src.idx), E, cols, _p(dW),
-                                   _ld(dW), self.s, what="edge_mul_gather")
+                        self._call(self.L.molsde_edge_mul_gather_ld, _p(out.grad), _p(tgt.idx), _p(x.data), _p(src.idx), _p(escale), E, cols,
+                                   _p(dW), _ld(dW), self.s, what="edge_mul_gather")
                 if x.needs:
                     dx = self.empty(N, cols)
-                    self._call(self.L.molsde_edge_mul_reduce_ld, _p(out.grad), _p(tgt.idx), _p(Wd), ldw, _p(src.ptr), _p(src.perm), N,
-                               cols, _p(dx), self.s, what="edge_mul_reduce")
+                    self._call(self.L.molsde_edge_mul_reduce_ld, _p(out.grad), _p(tgt.idx), _p(Wd), ldw, _p(escale), _p(src.ptr),
+                               _p(src.perm), N, cols, _p(dx), self.s, what="edge_mul_reduce")
                     self.accum(x, dx)
             self.ops.append(bwd)
         return out
