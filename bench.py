@@ -394,15 +394,15 @@ def run_b200(args):
     value = world * n_conf / (ms_per_step * 1e-3)
     e2e_value = world * n_conf / e2e_s
 
-    pretrain = None
-    if not args.skip_pretrain:
-        del d, rep, pos0, prep, pm, pm2, d2, rep2, pos2
-        torch.cuda.empty_cache()
-        pretrain = bench_pretrain(args, dev, rank, world)
+    del d, rep, pos0, prep, pm, pm2, d2, rep2, pos2
     dense = None
     if not args.skip_dense:
         torch.cuda.empty_cache()
         dense = bench_dense_sampler(args, dev, rank, world)
+    pretrain = None
+    if not args.skip_pretrain:
+        torch.cuda.empty_cache()
+        pretrain = bench_pretrain(args, dev, rank, world)
     stress = None
     if not args.skip_stress:
         torch.cuda.empty_cache()
