@@ -686,7 +686,7 @@ def _dense_gcn(tp: Tape, adjc: Var, c: int, C: int, xw: Var, xw_col0: int, bias:
                  out.data.data_ptr(), dout.data_ptr(), out.data.stride(0), out_off, code, ptr(dpre),
                  dxw.data_ptr() + 4 * xw_col0, dxw.stride(0), da_ptr, C * Nm * Nm, 1, s, what="dense_gcn_bwd")
         if bias.needs:
-            with tp.wgrad(dpre):
+            with tp.wgrad(dpre, key=bias.grad):
                 tp.colsum(dpre, B * Nm, Fo, Fo, bias.grad, accumulate=True)
     tp.ops.append(bwd)
 
@@ -768,7 +768,7 @@ def _dense_gcn_all(tp: Tape, adjc: Var, C: int, xw: Var, bias: Var, Fo: int, out
         tp._call(L.molsde_dense_gcn_bwd, ptr(a), sb, sc, B, C, Nm, ptr(xw.data), xw.data.stride(0), Fo, ptr(out.data), ptr(dout),
                  out.data.stride(0), 0, 0, ptr(dpre), ptr(dxw), C * Fo, _p(da), C * Nm * Nm, 1, s, what="dense_gcn_bwd")
         if bias.needs:
-            with tp.wgrad(dpre):
+            with tp.wgrad(dpre, key=bias.grad):
                 tp.colsum(dpre, B * Nm, C * Fo, C * Fo, bias.grad, accumulate=True)
         tp.accum(xw, dxw)
     tp.ops.append(bwd)
@@ -895,7 +895,7 @@ def tape_3d2d(tp: Tape, model, P: Dict[str, Var], h3d: Var, data, anneal_power: 
             if xw.grad is None:
                 return
             xv = xs.data[:, cur_off:cur_off + width]
-            with tp.wgrad(xw.grad, xs.data):
+            with tp.wgrad(xw.grad, xs.data, key=W.grad):
                 tp.gemm(1, 0, width, nsn.nhid, rows, xv, xs.data.stride(0), xw.grad, nsn.nhid, W.grad, nsn.nhid, accumulate=True)
             g = tp.grad_of(xs)[:, cur_off:cur_off + width]
             tp.gemm(0, 1, rows, width, nsn.nhid, xw.grad, nsn.nhid, W.data, nsn.nhid, g, xs.data.stride(0), accumulate=True)

@@ -138,15 +138,19 @@ class Tape:
         return v.grad
 
     @contextmanager
-    def wgrad(self, *operands):
-        """Run the enclosed launches (a parameter-gradient leaf) on the side stream, ordered after everything issued so far on
-        the tape's stream.  `operands`: tensors read by those launches that could otherwise be freed before the join."""
+    def wgrad(self, *operands, key: Optional[torch.Tensor] = None):
+        """Run the enclosed launches (a parameter-gradient leaf) on a side stream, ordered after everything issued so far on
+        the tape's stream.  `operands`: tensors read by those launches that could otherwise be freed before the join.
+        `key`: the gradient tensor the leaf ACCUMULATES into.  With several side streams the stream is a function of the key's
+        address, so every leaf that adds to the same parameter gradient (a weight used twice, e.g. `coff_mlp` on both edge ends)
+        runs on the same stream in issue order -- no concurrent read-modify-write, and the same summation order as the eager path."""
         if self._w is None:
             yield
             return
         self._hold.extend(t for t in operands if t is not None)
-        w = self._ws[self._wi % len(self._ws)]
-        self._wi += 1
+        n = len(self._ws)
+        w = self._ws[0 if (key is None or n == 1) else ((key.data_ptr() >> 4) * 2654435761 >> 12) % n]
+        self._wi = n   # (join waits for every side stream)
         w.wait_stream(self._main)
         prev, self._s, self._w_used = self._s, w.cuda_stream, True
         try:
@@ -277,7 +281,7 @@ class Tape:
         """Parameter gradients of y = x W^T + b on the side stream: W.grad += dpre^T x, b.grad += column sums of dpre."""
         M, K = xd.shape
         Nout = dpre.shape[1]
-        with self.wgrad(dpre, xd):
+        with self.wgrad(dpre, xd, key=W.grad if W.needs else (b.grad if b is not None and b.needs else None)):
             if FUSED_DB and W.needs and b is not None and b.needs and Nout * K * M >= TC_MIN_WORK:
                 # dW and db in one tensor-core GEMM (db = the product with an all-ones extra row)
                 n = self.L.molsde_tc_gemm_ws_floats(Nout, K + 1, M)
@@ -353,7 +357,7 @@ class Tape:
                         return
                     dy = out.grad
                 if Wio.needs:
-                    with self.wgrad(dy, x.data):
+                    with self.wgrad(dy, x.data, key=Wio.grad):
                         self.gemm(1, 0, K, Nout, M, x.data, _ld(x.data), dy, _ld(dy), Wio.grad, _ld(Wio.grad), accumulate=True)
                 if x.needs:
                     dx = self.empty(M, K)
@@ -531,7 +535,7 @@ class Tape:
             dx, dyx = self.empty(M, D), self.empty(M, D)
             self._call(self.L.molsde_layernorm_bwd, _p(x.data), _p(out.grad), M, D, _p(g.data), _p(mean), _p(rstd), _p(dx), _p(dyx),
                        self.s, what="layernorm_bwd")
-            with self.wgrad(dyx, out.grad):
+            with self.wgrad(dyx, out.grad, key=g.grad if g.needs else b.grad):
                 if g.needs:
                     self.colsum(dyx, M, D, D, g.grad, accumulate=True)
                 if b.needs:
@@ -593,7 +597,7 @@ class Tape:
             def bwd():
                 if out.grad is None:
                     return
-                with self.wgrad(out.grad):
+                with self.wgrad(out.grad, key=T.grad):
                     self.seg_sum(out.grad, index, cols, T.grad, accumulate=True, row_div=F)
             self.ops.append(bwd)
         return out
@@ -614,7 +618,7 @@ class Tape:
                 dmsg = self.empty(E, cols)
                 self._call(self.L.molsde_gin_message_bwd, _p(x.data), _p(T.data), _p(ekeys), F, _p(src.idx), _p(tgt.idx), _p(out.grad),
                            E, cols, _p(dmsg), self.s, what="gin_message_bwd")
-                with self.wgrad(dmsg, out.grad, x.data):
+                with self.wgrad(dmsg, out.grad, x.data, key=T.grad if T.needs else eps.grad):
                     if T.needs:
                         self.seg_sum(dmsg, ekey_index, cols, T.grad, accumulate=True, row_div=F)
                     if eps.needs:
@@ -755,7 +759,7 @@ class Tape:
             if out.grad is None:
                 return
             dy = out.grad
-            with self.wgrad(dy, x.data):
+            with self.wgrad(dy, x.data, key=Wp.grad if Wp.needs else bp.grad):
                 if Wp.needs:   # dW_g = dy_g^T x_g
                     self.gemm_batched(G, No, Ki, rows, dy, 1, G * No, No, x.data, 1, ldx, Ki, Wp.grad, Ki, No * Ki, accumulate=True)
                 if bp.needs:
@@ -781,7 +785,7 @@ class Tape:
                 return
             dy = out.grad
             if Wp.needs:   # dW_g [Fin,Fo] = x^T dy_g
-                with self.wgrad(dy, x.data):
+                with self.wgrad(dy, x.data, key=Wp.grad):
                     self.gemm_batched(G, Fin, Fo, rows, x.data, 1, ldx, 0, dy, 1, G * Fo, Fo, Wp.grad, Fo, Fin * Fo, accumulate=True)
             if x.needs:    # dx = sum_g dy_g W_g^T : per-group products into a scratch, then a fixed-order sum over the groups
                 tmp = self.empty(G, rows, Fin)
